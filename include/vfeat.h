@@ -1,0 +1,109 @@
+/* libvfeat.so -- C ABI of the B200-native video-feature engine.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes, returns an int status
+ * (VF_OK == 0) and never throws.  Device buffers are raw CUDA device pointers owned by the
+ * caller; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Handles
+ * are opaque, own their device weights + workspace, and are not shared between threads.
+ *
+ * Each function names the reference interface it replaces
+ * (Kamino666/video_features @ dc9df59e, paths relative to the reference root).
+ */
+#ifndef VFEAT_H_
+#define VFEAT_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VF_OK 0
+#define VF_ERR_INVALID 1   /* bad argument */
+#define VF_ERR_CUDA 2      /* a CUDA runtime / driver call failed */
+#define VF_ERR_NOMEM 3
+#define VF_ERR_UNSUPPORTED 4
+
+#define VF_ACT_NONE 0
+#define VF_ACT_QUICKGELU 1 /* x * sigmoid(1.702 x) */
+#define VF_ACT_RELU 2
+
+#define VF_FILTER_BILINEAR 2 /* PIL.Image.BILINEAR */
+#define VF_FILTER_BICUBIC 3  /* PIL.Image.BICUBIC  */
+
+/* ABI version; bumped on any signature change. */
+int vf_version(void);
+/* Text of the last error raised on the calling thread ("" if none). */
+const char* vf_last_error(void);
+
+/* ---- sampler: utils/utils.py:297-333 `extract_frames` index arithmetic -------------------------
+ * method "uni": n = param; "fix": n = (int)(frame_cnt / fps * param).  Writes
+ * np.linspace(1, frame_cnt-2, n).astype(int) into out_idx (capacity cap) and n into *out_n;
+ * out_idx == NULL only queries n. */
+int vf_sample_indices(const char* method, int param, int64_t frame_cnt, double fps, int64_t* out_idx, int64_t cap,
+                      int64_t* out_n);
+/* contiguous chunk shard of `n_items` over `n_parts` as torch.chunk does (main.py:49-53):
+ * part p gets [*begin, *end); parts beyond the last non-empty chunk get begin == end. */
+int vf_shard_range(int64_t n_items, int n_parts, int part, int64_t* begin, int64_t* end);
+
+/* ---- PIL-compatible resample: Pillow Image.resize as used by torchvision Resize in the CLIP
+ * transform (models/CLIP/extract_clip.py:112) and models/i3d/transforms/transforms.py:121,125.
+ * src: n frames HWC uint8 (3 channels) on the device; dst: n x out_h x out_w x 3 uint8.
+ * tmp: device scratch of n*in_h*out_w*3 bytes (horizontal pass output); byte-exact with Pillow. */
+int vf_resize_u8(const uint8_t* src, int n, int in_h, int in_w, uint8_t* dst, int out_h, int out_w, int filter,
+                 uint8_t* tmp, void* stream);
+/* output geometry of "short side -> size" (torchvision Resize(int) / ResizeImproved). */
+int vf_resize_geometry(int in_h, int in_w, int size, int to_smaller_edge, int* out_h, int* out_w);
+
+/* ---- CLIP transform: ToTensor + Normalize + CenterCrop(224) (clip.clip._transform as invoked at
+ * models/CLIP/extract_clip.py:107-113,125-126).  src: n x src_h x src_w x 3 uint8 (already
+ * resized); dst: n x 3 x 224 x 224 fp32, bit-exact with torchvision's fp32 arithmetic. */
+int vf_clip_normalize_u8(const uint8_t* src, int n, int src_h, int src_w, float* dst, void* stream);
+
+/* ---- tensor-core GEMM (exported for the parity tests): D = act(A . B^T * scale + bias) + residual
+ * A: M x K fp16 (row pitch lda elements), B: N x K fp16 (torch Linear weight layout),
+ * D: fp16 or fp32 (out_f32), bias/scale: fp32 [N] or NULL, residual: fp32 M x ldr or NULL. */
+int vf_gemm_f16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, void* D, int ldd, int out_f32,
+                const float* bias, const float* scale, const float* residual, int ldr, int act, void* stream);
+
+/* ---- CLIP ViT-B/32 image tower: replaces `clip.load(...)` + `model.encode_image(frames)`
+ * (models/CLIP/extract_clip.py:47,128).  Weight pointers are HOST fp32 arrays in openai layout. */
+typedef struct vf_clip_layer_weights {
+    const float *ln_1_w, *ln_1_b;           /* [768] */
+    const float *in_proj_w, *in_proj_b;     /* [2304,768], [2304] */
+    const float *out_proj_w, *out_proj_b;   /* [768,768], [768] */
+    const float *ln_2_w, *ln_2_b;           /* [768] */
+    const float *c_fc_w, *c_fc_b;           /* [3072,768], [3072] */
+    const float *c_proj_w, *c_proj_b;       /* [768,3072], [768] */
+} vf_clip_layer_weights;
+
+typedef struct vf_clip_weights {
+    const float* conv1_w;                   /* [768,3,32,32] */
+    const float* class_embedding;           /* [768] */
+    const float* positional_embedding;      /* [50,768] */
+    const float *ln_pre_w, *ln_pre_b, *ln_post_w, *ln_post_b; /* [768] */
+    const float* proj;                      /* [768,512] */
+    vf_clip_layer_weights layers[12];
+} vf_clip_weights;
+
+typedef struct vf_clip vf_clip_t;
+
+/* Uploads weights to `device` (fp16 GEMM operands, fp32 vectors) and allocates workspace for
+ * chunks of `chunk_frames` frames (0 = default). */
+int vf_clip_create(vf_clip_t** out, const vf_clip_weights* w, int device, int chunk_frames);
+int vf_clip_destroy(vf_clip_t* h);
+/* encode_image on n already-transformed frames: frames n x 3 x 224 x 224 fp32 (device) -> out n x 512 fp32. */
+int vf_clip_encode_f32(vf_clip_t* h, const float* frames, int n, float* out, void* stream);
+/* Fused transform + encode_image: frames n x src_h x src_w x 3 uint8 (device, as the decoder delivers
+ * them, channel order untouched) -> Resize(224,bicubic) -> CenterCrop(224) -> normalise -> tower. */
+int vf_clip_encode_u8(vf_clip_t* h, const uint8_t* frames, int n, int src_h, int src_w, float* out, void* stream);
+/* Same with HOST buffers: stages H2D copies of the frames and the D2H copy of the features on
+ * `stream` and synchronises it before returning (the call ExtractCLIP.extract makes per video). */
+int vf_clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, int src_h, int src_w, float* out_host,
+                           void* stream);
+/* number of kernels this library has launched on behalf of `h` so far (diagnostics / bench). */
+int64_t vf_clip_launch_count(const vf_clip_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VFEAT_H_ */

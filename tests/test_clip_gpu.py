@@ -1,0 +1,103 @@
+"""CLIP ViT-B/32 tower through the C ABI against the fp32 oracle (oracle/clip_tower.py), same seeded frames.
+
+Tolerance (BASELINE.json north_star): 1e-3 relative vs the fp32 torch path --
+per row  ||y - y_ref||_2 / ||y_ref||_2 <= 1e-3  and  max|y - y_ref| <= 1e-3 * max|y_ref|.
+CLIP caveat: synthetic weights, restated oracle (the reference's `clip` package and weights are absent offline).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+MEAN = torch.tensor([0.48145466, 0.4578275, 0.40821073])
+STD = torch.tensor([0.26862954, 0.26130258, 0.27577711])
+
+
+def _transform_224(frames_u8: torch.Tensor) -> torch.Tensor:
+    """ToTensor + Normalize on 224x224 frames (Resize/CenterCrop are identities at this size)."""
+    x = frames_u8.permute(0, 3, 1, 2).to(torch.float32).div(255)
+    return x.sub(MEAN[None, :, None, None]).div(STD[None, :, None, None])
+
+
+@pytest.fixture(scope="module")
+def tower(cuda_device):
+    from oracle import clip_tower
+    from video_features_b200.clip_engine import ClipEngine
+    sd = clip_tower.synthetic_state_dict(0)
+    eng = ClipEngine(sd, device=0)
+    yield sd, eng
+    eng.close()
+
+
+def _check_rows(y, ref, tol=1e-3):
+    y, ref = y.double().cpu(), ref.double().cpu()
+    rel = ((y - ref).norm(dim=1) / ref.norm(dim=1)).max().item()
+    mx = ((y - ref).abs().amax(dim=1) / ref.abs().amax(dim=1)).max().item()
+    assert rel <= tol, f"row rel-L2 {rel:.3e} > {tol}"
+    assert mx <= tol, f"row max-abs {mx:.3e} > {tol}"
+    return rel, mx
+
+
+def test_transform_is_bit_exact(cuda_device):
+    g = torch.Generator().manual_seed(3)
+    frames = torch.randint(0, 256, (5, 224, 224, 3), dtype=torch.uint8, generator=g)
+    got = torch.ops.vfeat.clip_normalize_u8(frames.to(cuda_device)).cpu()
+    assert torch.equal(got, _transform_224(frames))
+
+
+def test_encode_small_batch_vs_cpu_oracle(tower, cuda_device):
+    from oracle import clip_tower
+    sd, eng = tower
+    g = torch.Generator().manual_seed(0)
+    frames = torch.randint(0, 256, (8, 224, 224, 3), dtype=torch.uint8, generator=g)
+    ref = clip_tower.encode_image(sd, _transform_224(frames))            # fp32 on CPU
+    y_u8 = eng.encode_frames_u8(frames.to(cuda_device))
+    y_f32 = eng.encode_image(_transform_224(frames).to(cuda_device))
+    y_host = eng.encode_frames_u8_host(frames)
+    torch.cuda.synchronize()
+    print("u8 path:", _check_rows(y_u8, ref))
+    _check_rows(y_f32, ref)
+    assert torch.equal(y_u8.cpu(), y_f32.cpu()), "uint8 and fp32 entry points must agree bit-for-bit"
+    assert torch.equal(y_u8.cpu(), y_host), "host-buffer entry point must agree bit-for-bit"
+
+
+def test_encode_multi_chunk_vs_gpu_fp32_oracle(tower, cuda_device):
+    """270 frames = 2 full chunks of 120 + a ragged tail of 30; oracle runs in fp32 (TF32 off) on the GPU."""
+    from oracle import clip_tower
+    sd, eng = tower
+    g = torch.Generator().manual_seed(1)
+    frames = torch.randint(0, 256, (270, 224, 224, 3), dtype=torch.uint8, generator=g)
+    sd_gpu = {k: v.to(cuda_device) for k, v in sd.items()}
+    ref = torch.cat([clip_tower.encode_image(sd_gpu, _transform_224(frames[i:i + 54]).to(cuda_device))
+                     for i in range(0, 270, 54)])
+    y = eng.encode_frames_u8(frames.to(cuda_device))
+    y_host = eng.encode_frames_u8_host(frames)
+    print("multi-chunk:", _check_rows(y, ref))
+    assert torch.equal(y.cpu(), y_host)
+    # batch-composition independence: a frame's features do not depend on its neighbours
+    y1 = eng.encode_frames_u8(frames[100:101].to(cuda_device))
+    assert torch.equal(y1.cpu(), y[100:101].cpu())
+
+
+def test_encode_empty_and_single(tower, cuda_device):
+    sd, eng = tower
+    out = eng.encode_frames_u8(torch.empty((0, 224, 224, 3), dtype=torch.uint8, device=cuda_device))
+    assert out.shape == (0, 512)
+
+
+def test_resize_path_matches_pillow_then_oracle(tower, cuda_device):
+    """240x320 frames: Resize(224, bicubic) -> CenterCrop -> normalise, Pillow/torchvision semantics."""
+    from PIL import Image
+    from oracle import clip_tower
+    sd, eng = tower
+    g = torch.Generator().manual_seed(2)
+    frames = torch.randint(0, 256, (3, 240, 320, 3), dtype=torch.uint8, generator=g)
+    tens = []
+    for f in frames.numpy():
+        im = Image.fromarray(f).resize((298, 224), Image.BICUBIC)
+        a = torch.from_numpy(np.asarray(im).copy())[:, 37:37 + 224, :]
+        tens.append(a)
+    ref = clip_tower.encode_image(sd, _transform_224(torch.stack(tens)))
+    y = eng.encode_frames_u8(frames.to(cuda_device))
+    _check_rows(y, ref)

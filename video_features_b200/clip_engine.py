@@ -1,0 +1,113 @@
+"""CLIP ViT-B/32 image tower handle: the object that stands where the reference keeps the result of
+``clip.load("ViT-B/32", device)`` (models/CLIP/extract_clip.py:47) -- ``encode_image`` included.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ClipWeights, check, lib
+
+_LAYER_KEYS = {
+    "ln_1_w": "ln_1.weight", "ln_1_b": "ln_1.bias",
+    "in_proj_w": "attn.in_proj_weight", "in_proj_b": "attn.in_proj_bias",
+    "out_proj_w": "attn.out_proj.weight", "out_proj_b": "attn.out_proj.bias",
+    "ln_2_w": "ln_2.weight", "ln_2_b": "ln_2.bias",
+    "c_fc_w": "mlp.c_fc.weight", "c_fc_b": "mlp.c_fc.bias",
+    "c_proj_w": "mlp.c_proj.weight", "c_proj_b": "mlp.c_proj.bias",
+}
+_TOP_KEYS = {
+    "conv1_w": "conv1.weight", "class_embedding": "class_embedding",
+    "positional_embedding": "positional_embedding", "ln_pre_w": "ln_pre.weight", "ln_pre_b": "ln_pre.bias",
+    "ln_post_w": "ln_post.weight", "ln_post_b": "ln_post.bias", "proj": "proj",
+}
+_SHAPES = {"conv1_w": (768, 3, 32, 32), "class_embedding": (768,), "positional_embedding": (50, 768), "proj": (768, 512)}
+
+
+class ClipEngine:
+    """Owns device weights + workspace of one GPU.  ``state_dict`` uses openai's ``visual.*`` keys (a full CLIP
+    state dict or a JIT archive's ``state_dict()`` works unchanged; text-tower keys are ignored)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device: int = 0, chunk_frames: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("ClipEngine needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", device)
+        keep = []     # keep numpy arrays alive across the create call
+
+        def arr(key: str, shape=None) -> C.POINTER(C.c_float):
+            full = "visual." + key
+            if full not in state_dict:
+                raise KeyError(f"CLIP checkpoint is missing '{full}'")
+            a = np.ascontiguousarray(state_dict[full].detach().to("cpu", torch.float32).numpy())
+            if shape is not None and tuple(a.shape) != tuple(shape):
+                raise ValueError(f"'{full}' has shape {a.shape}, ViT-B/32 needs {shape}")
+            keep.append(a)
+            return a.ctypes.data_as(C.POINTER(C.c_float))
+
+        w = ClipWeights()
+        for f, k in _TOP_KEYS.items():
+            setattr(w, f, arr(k, _SHAPES.get(f)))
+        for i in range(12):
+            for f, k in _LAYER_KEYS.items():
+                setattr(w.layers[i], f, arr(f"transformer.resblocks.{i}.{k}"))
+        h = C.c_void_p()
+        check(lib().vf_clip_create(C.byref(h), C.byref(w), device, chunk_frames))
+        self._h = h
+        del keep
+
+    # ---- model.encode_image(frames) : frames (T,3,224,224) float on this device
+    def encode_image(self, frames: torch.Tensor) -> torch.Tensor:
+        if not frames.is_cuda:
+            raise RuntimeError("encode_image expects CUDA frames (no CPU fallback)")
+        frames = frames.to(torch.float32).contiguous()
+        assert frames.dim() == 4 and tuple(frames.shape[1:]) == (3, 224, 224), frames.shape
+        out = torch.empty((frames.shape[0], 512), device=frames.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(lib().vf_clip_encode_f32(self._h, frames.data_ptr(), frames.shape[0], out.data_ptr(),
+                                           torch.cuda.current_stream().cuda_stream))
+        return out
+
+    # ---- fused preprocess + encode_image on raw decoder output: (T,H,W,3) uint8 on this device
+    def encode_frames_u8(self, frames: torch.Tensor) -> torch.Tensor:
+        assert frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3
+        frames = frames.contiguous()
+        n, hh, ww, _ = frames.shape
+        out = torch.empty((n, 512), device=frames.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(lib().vf_clip_encode_u8(self._h, frames.data_ptr(), n, hh, ww, out.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream))
+        return out
+
+    # ---- same with host buffers (numpy / CPU tensors): H2D + tower + D2H, synchronous
+    def encode_frames_u8_host(self, frames, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if isinstance(frames, np.ndarray):
+            frames = torch.from_numpy(np.ascontiguousarray(frames))
+        assert (not frames.is_cuda) and frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3
+        frames = frames.contiguous()
+        n, hh, ww, _ = frames.shape
+        if out is None:
+            out = torch.empty((n, 512), dtype=torch.float32)
+        assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (n, 512)
+        with torch.cuda.device(self.device):
+            check(lib().vf_clip_encode_u8_host(self._h, frames.data_ptr(), n, hh, ww, out.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream))
+        return out
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().vf_clip_launch_count(self._h))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().vf_clip_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

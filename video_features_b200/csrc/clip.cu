@@ -1,0 +1,318 @@
+// CLIP ViT-B/32 image tower on the tcgen05 GEMM + memory-bound kernels.
+// Replaces `clip.load("ViT-B/32")` + `model.encode_image(frames)` (reference: models/CLIP/extract_clip.py:47,128;
+// algorithm: third-party openai/CLIP clip/model.py VisionTransformer.forward, restated in oracle/clip_tower.py).
+//
+// Numerics: GEMM operands fp16, accumulation fp32 (TMEM), residual stream / LayerNorm / softmax fp32.
+// Frames are packed along M (row = frame*50 + token), processed in chunks sized so that one chunk's
+// activations stay L2-resident between kernels.
+#include <string.h>
+
+#include <vector>
+
+#include "internal.h"
+
+namespace vf {
+
+constexpr int W = 768, L = 12, H = 12, T = 50, P = 49, MLPW = 3072, E = 512, PK = 3072;
+
+struct ClipLayerDev {
+    float *ln1_w, *ln1_b, *ln2_w, *ln2_b, *b_qkv, *b_o, *b_fc, *b_proj;
+    __half *w_qkv, *w_o, *w_fc, *w_proj;
+};
+
+}  // namespace vf
+
+struct vf_clip {
+    int device = 0;
+    int chunk = 0;
+    int64_t launches = 0;
+    std::vector<void*> allocs;
+    // weights
+    __half* w_patch = nullptr;   // [768, 3072]
+    __half* w_proj = nullptr;    // [512, 768]  (proj^T)
+    float *pos = nullptr, *cls_pos0 = nullptr, *lnpre_w = nullptr, *lnpre_b = nullptr, *lnpost_w = nullptr,
+          *lnpost_b = nullptr;
+    vf::ClipLayerDev layer[12];
+    // workspace (per chunk)
+    __half *patches = nullptr, *h = nullptr, *qkv = nullptr, *att = nullptr, *mlp = nullptr, *cls = nullptr;
+    float* x = nullptr;
+    // transform scratch (grown on demand)
+    uint8_t *stage_u8 = nullptr, *resized = nullptr, *resize_tmp = nullptr;
+    size_t stage_cap = 0, resized_cap = 0, tmp_cap = 0;
+    float* out_dev = nullptr;
+    size_t out_cap = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+};
+
+namespace vf {
+
+template <typename Tp>
+static int dev_alloc(vf_clip* h, Tp** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(Tp));
+    if (e != cudaSuccess) return fail(VF_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(Tp), cudaGetErrorString(e));
+    h->allocs.push_back(q);
+    *p = static_cast<Tp*>(q);
+    return VF_OK;
+}
+static int upload_f32(vf_clip* h, float** dst, const float* src, size_t count) {
+    if (!src) return fail(VF_ERR_INVALID, "clip_create: missing weight tensor");
+    VF_TRY(dev_alloc(h, dst, count));
+    VF_CUDA(cudaMemcpy(*dst, src, count * sizeof(float), cudaMemcpyHostToDevice));
+    return VF_OK;
+}
+// fp32 host [rows, cols] (optionally transposed on the way) -> fp16 device, round-to-nearest-even
+static int upload_f16(vf_clip* h, __half** dst, const float* src, size_t rows, size_t cols, bool transpose) {
+    if (!src) return fail(VF_ERR_INVALID, "clip_create: missing weight tensor");
+    std::vector<__half> tmp(rows * cols);
+    if (!transpose) {
+        for (size_t i = 0; i < rows * cols; ++i) tmp[i] = __float2half_rn(src[i]);
+    } else {   // src is [rows, cols]; produce [cols, rows]
+        for (size_t r = 0; r < rows; ++r)
+            for (size_t c = 0; c < cols; ++c) tmp[c * rows + r] = __float2half_rn(src[r * cols + c]);
+    }
+    VF_TRY(dev_alloc(h, dst, rows * cols));
+    VF_CUDA(cudaMemcpy(*dst, tmp.data(), tmp.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    return VF_OK;
+}
+
+static int grow(uint8_t** p, size_t* cap, size_t need) {
+    if (need <= *cap) return VF_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), need);
+    if (e != cudaSuccess) return fail(VF_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", need, cudaGetErrorString(e));
+    *cap = need;
+    return VF_OK;
+}
+
+static GemmEpi epi(void* out, int ldo, int out_f32, const float* bias, int act) {
+    GemmEpi e;
+    memset(&e, 0, sizeof(e));
+    e.out = out; e.ldo = ldo; e.out_f32 = out_f32; e.bias = bias; e.act = act;
+    return e;
+}
+
+// the tower on one chunk whose patch matrix is already in h->patches; writes c x 512 fp32 to out
+static int clip_tower_chunk(vf_clip* h, int c, float* out, cudaStream_t s) {
+    const int M = c * T;
+    // patch embedding: [c*49, 3072] x [768, 3072]^T, rows scattered to token slots 1..49, + positional embedding
+    {
+        GemmEpi e = epi(h->x, W, 1, nullptr, VF_ACT_NONE);
+        e.addend = h->pos; e.gin = P; e.gout = T; e.goff = 1;
+        VF_TRY(gemm_f16(h->patches, PK, h->w_patch, PK, c * P, W, PK, e, s));
+    }
+    // ln_pre in place; CLS rows are sourced from class_embedding + pos[0]
+    VF_TRY(launch_layernorm(h->x, W, h->cls_pos0, T, h->lnpre_w, h->lnpre_b, h->x, W, 1, M, W, s));
+    h->launches += 2;
+    for (int l = 0; l < L; ++l) {
+        const ClipLayerDev& w = h->layer[l];
+        VF_TRY(launch_layernorm(h->x, W, nullptr, 0, w.ln1_w, w.ln1_b, h->h, W, 0, M, W, s));
+        VF_TRY(gemm_f16(h->h, W, w.w_qkv, W, M, 3 * W, W, epi(h->qkv, 3 * W, 0, w.b_qkv, VF_ACT_NONE), s));
+        VF_TRY(launch_attention(h->qkv, h->att, c, T, H, s));
+        {
+            GemmEpi e = epi(h->x, W, 1, w.b_o, VF_ACT_NONE);
+            e.residual = h->x; e.ldr = W;
+            VF_TRY(gemm_f16(h->att, W, w.w_o, W, M, W, W, e, s));
+        }
+        VF_TRY(launch_layernorm(h->x, W, nullptr, 0, w.ln2_w, w.ln2_b, h->h, W, 0, M, W, s));
+        VF_TRY(gemm_f16(h->h, W, w.w_fc, W, M, MLPW, W, epi(h->mlp, MLPW, 0, w.b_fc, VF_ACT_QUICKGELU), s));
+        {
+            GemmEpi e = epi(h->x, W, 1, w.b_proj, VF_ACT_NONE);
+            e.residual = h->x; e.ldr = W;
+            VF_TRY(gemm_f16(h->mlp, MLPW, w.w_proj, MLPW, M, W, MLPW, e, s));
+        }
+        h->launches += 7;
+    }
+    // ln_post on the CLS rows, then the 768 -> 512 projection
+    VF_TRY(launch_layernorm(h->x, int64_t(T) * W, nullptr, 0, h->lnpost_w, h->lnpost_b, h->cls, W, 0, c, W, s));
+    VF_TRY(gemm_f16(h->cls, W, h->w_proj, W, c, E, W, epi(out, E, 1, nullptr, VF_ACT_NONE), s));
+    h->launches += 2;
+    return VF_OK;
+}
+
+// transform geometry of the CLIP preprocess for a (src_h, src_w) frame
+struct ClipGeom { int rh, rw, cy, cx; bool resize; };
+static int clip_geometry(int src_h, int src_w, ClipGeom* g) {
+    if (src_h <= 0 || src_w <= 0) return fail(VF_ERR_INVALID, "clip: bad frame geometry %dx%d", src_h, src_w);
+    VF_TRY(vf_resize_geometry(src_h, src_w, 224, 1, &g->rh, &g->rw));
+    g->resize = (g->rh != src_h) || (g->rw != src_w);
+    g->cy = center_crop_offset(g->rh, 224);
+    g->cx = center_crop_offset(g->rw, 224);
+    return VF_OK;
+}
+
+// device uint8 frames (c of them, original geometry) -> h->patches
+static int clip_transform_chunk(vf_clip* h, const uint8_t* frames, int c, int src_h, int src_w, const ClipGeom& g,
+                                cudaStream_t s) {
+    const uint8_t* cur = frames;
+    int ch = src_h, cw = src_w;
+    if (g.resize) {
+        VF_TRY(grow(&h->resized, &h->resized_cap, size_t(h->chunk) * g.rh * g.rw * 3));
+        VF_TRY(grow(&h->resize_tmp, &h->tmp_cap, size_t(h->chunk) * src_h * g.rw * 3));
+        VF_TRY(resize_u8(frames, c, src_h, src_w, h->resized, g.rh, g.rw, VF_FILTER_BICUBIC, h->resize_tmp, s));
+        h->launches += (g.rh != src_h) + (g.rw != src_w);
+        cur = h->resized; ch = g.rh; cw = g.rw;
+    }
+    VF_TRY(launch_clip_patchify(cur, c, ch, cw, g.cy, g.cx, h->patches, s));
+    h->launches += 1;
+    return VF_OK;
+}
+
+}  // namespace vf
+
+using namespace vf;
+
+extern "C" {
+
+int vf_clip_create(vf_clip_t** out, const vf_clip_weights* w, int device, int chunk_frames) {
+    if (!out || !w) return fail(VF_ERR_INVALID, "clip_create: null argument");
+    *out = nullptr;
+    if (chunk_frames <= 0) chunk_frames = 120;   // 6000 rows = 47 M-tiles: 3/1/4/1 near-full waves of 148 SMs
+    if (chunk_frames > 4096) return fail(VF_ERR_INVALID, "clip_create: chunk_frames %d too large", chunk_frames);
+    VF_CUDA(cudaSetDevice(device));
+    int major = 0, minor = 0;
+    VF_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    VF_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+    if (major != 10)
+        return fail(VF_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, major, minor);
+    vf_clip* h = new vf_clip();
+    h->device = device;
+    h->chunk = chunk_frames;
+    int st = VF_OK;
+    auto body = [&]() -> int {
+        VF_TRY(upload_f16(h, &h->w_patch, w->conv1_w, W, PK, false));
+        VF_TRY(upload_f16(h, &h->w_proj, w->proj, W, E, true));
+        VF_TRY(upload_f32(h, &h->pos, w->positional_embedding, size_t(T) * W));
+        if (!w->class_embedding) return fail(VF_ERR_INVALID, "clip_create: missing class_embedding");
+        {
+            std::vector<float> c0(W);
+            for (int i = 0; i < W; ++i) c0[i] = w->class_embedding[i] + w->positional_embedding[i];
+            VF_TRY(upload_f32(h, &h->cls_pos0, c0.data(), W));
+        }
+        VF_TRY(upload_f32(h, &h->lnpre_w, w->ln_pre_w, W));
+        VF_TRY(upload_f32(h, &h->lnpre_b, w->ln_pre_b, W));
+        VF_TRY(upload_f32(h, &h->lnpost_w, w->ln_post_w, W));
+        VF_TRY(upload_f32(h, &h->lnpost_b, w->ln_post_b, W));
+        for (int l = 0; l < L; ++l) {
+            const vf_clip_layer_weights& s = w->layers[l];
+            ClipLayerDev& d = h->layer[l];
+            VF_TRY(upload_f32(h, &d.ln1_w, s.ln_1_w, W));
+            VF_TRY(upload_f32(h, &d.ln1_b, s.ln_1_b, W));
+            VF_TRY(upload_f32(h, &d.ln2_w, s.ln_2_w, W));
+            VF_TRY(upload_f32(h, &d.ln2_b, s.ln_2_b, W));
+            VF_TRY(upload_f32(h, &d.b_qkv, s.in_proj_b, 3 * W));
+            VF_TRY(upload_f32(h, &d.b_o, s.out_proj_b, W));
+            VF_TRY(upload_f32(h, &d.b_fc, s.c_fc_b, MLPW));
+            VF_TRY(upload_f32(h, &d.b_proj, s.c_proj_b, W));
+            VF_TRY(upload_f16(h, &d.w_qkv, s.in_proj_w, 3 * W, W, false));
+            VF_TRY(upload_f16(h, &d.w_o, s.out_proj_w, W, W, false));
+            VF_TRY(upload_f16(h, &d.w_fc, s.c_fc_w, MLPW, W, false));
+            VF_TRY(upload_f16(h, &d.w_proj, s.c_proj_w, W, MLPW, false));
+        }
+        const size_t C = size_t(chunk_frames);
+        VF_TRY(dev_alloc(h, &h->patches, C * P * PK));
+        VF_TRY(dev_alloc(h, &h->x, C * T * W));
+        VF_TRY(dev_alloc(h, &h->h, C * T * W));
+        VF_TRY(dev_alloc(h, &h->qkv, C * T * 3 * W));
+        VF_TRY(dev_alloc(h, &h->att, C * T * W));
+        VF_TRY(dev_alloc(h, &h->mlp, C * T * MLPW));
+        VF_TRY(dev_alloc(h, &h->cls, C * W));
+        VF_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            VF_CUDA(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
+            VF_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+        }
+        return VF_OK;
+    };
+    st = body();
+    if (st != VF_OK) { vf_clip_destroy(h); return st; }
+    *out = h;
+    return VF_OK;
+}
+
+int vf_clip_destroy(vf_clip_t* h) {
+    if (!h) return VF_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->stage_u8) cudaFree(h->stage_u8);
+    if (h->resized) cudaFree(h->resized);
+    if (h->resize_tmp) cudaFree(h->resize_tmp);
+    if (h->out_dev) cudaFree(h->out_dev);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+    }
+    delete h;
+    return VF_OK;
+}
+
+int vf_clip_encode_f32(vf_clip_t* h, const float* frames, int n, float* out, void* stream) {
+    if (!h || (n > 0 && (!frames || !out))) return fail(VF_ERR_INVALID, "clip_encode_f32: null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    for (int b0 = 0; b0 < n; b0 += h->chunk) {
+        const int c = (n - b0 < h->chunk) ? (n - b0) : h->chunk;
+        VF_TRY(launch_clip_patchify_f32(frames + size_t(b0) * 3 * 224 * 224, c, h->patches, s));
+        h->launches += 1;
+        VF_TRY(clip_tower_chunk(h, c, out + size_t(b0) * E, s));
+    }
+    return VF_OK;
+}
+
+int vf_clip_encode_u8(vf_clip_t* h, const uint8_t* frames, int n, int src_h, int src_w, float* out, void* stream) {
+    if (!h || (n > 0 && (!frames || !out))) return fail(VF_ERR_INVALID, "clip_encode_u8: null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ClipGeom g;
+    VF_TRY(clip_geometry(src_h, src_w, &g));
+    const size_t fbytes = size_t(src_h) * src_w * 3;
+    for (int b0 = 0; b0 < n; b0 += h->chunk) {
+        const int c = (n - b0 < h->chunk) ? (n - b0) : h->chunk;
+        VF_TRY(clip_transform_chunk(h, frames + size_t(b0) * fbytes, c, src_h, src_w, g, s));
+        VF_TRY(clip_tower_chunk(h, c, out + size_t(b0) * E, s));
+    }
+    return VF_OK;
+}
+
+int vf_clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, int src_h, int src_w, float* out_host,
+                           void* stream) {
+    if (!h || (n > 0 && (!frames_host || !out_host))) return fail(VF_ERR_INVALID, "clip_encode_u8_host: null argument");
+    if (n <= 0) return VF_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ClipGeom g;
+    VF_TRY(clip_geometry(src_h, src_w, &g));
+    const size_t fbytes = size_t(src_h) * src_w * 3;
+    // two staging slots: the H2D copy of chunk i+1 (copy stream) overlaps the tower on chunk i (compute stream)
+    VF_TRY(grow(&h->stage_u8, &h->stage_cap, 2 * size_t(h->chunk) * fbytes));
+    if (h->out_cap < size_t(n) * E * sizeof(float)) {
+        if (h->out_dev) cudaFree(h->out_dev);
+        h->out_dev = nullptr; h->out_cap = 0;
+        VF_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->out_dev), size_t(n) * E * sizeof(float)));
+        h->out_cap = size_t(n) * E * sizeof(float);
+    }
+    const int nchunks = (n + h->chunk - 1) / h->chunk;
+    for (int i = 0; i < nchunks; ++i) {
+        const int b0 = i * h->chunk;
+        const int c = (n - b0 < h->chunk) ? (n - b0) : h->chunk;
+        const int slot = i & 1;
+        uint8_t* dst = h->stage_u8 + size_t(slot) * h->chunk * fbytes;
+        if (i >= 2) VF_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));   // slot free again
+        VF_CUDA(cudaMemcpyAsync(dst, frames_host + size_t(b0) * fbytes, size_t(c) * fbytes, cudaMemcpyHostToDevice,
+                                h->copy_stream));
+        VF_CUDA(cudaEventRecord(h->ev_copy[slot], h->copy_stream));
+        VF_CUDA(cudaStreamWaitEvent(s, h->ev_copy[slot], 0));
+        VF_TRY(clip_transform_chunk(h, dst, c, src_h, src_w, g, s));
+        VF_CUDA(cudaEventRecord(h->ev_done[slot], s));   // staging slot consumed
+        VF_TRY(clip_tower_chunk(h, c, h->out_dev + size_t(b0) * E, s));
+    }
+    VF_CUDA(cudaMemcpyAsync(out_host, h->out_dev, size_t(n) * E * sizeof(float), cudaMemcpyDeviceToHost, s));
+    VF_CUDA(cudaStreamSynchronize(s));
+    return VF_OK;
+}
+
+int64_t vf_clip_launch_count(const vf_clip_t* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

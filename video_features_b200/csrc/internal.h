@@ -1,0 +1,71 @@
+// Host-side internals shared by the translation units of libvfeat.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/vfeat.h"
+
+namespace vf {
+
+// thread-local last-error text behind vf_last_error()
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+
+#define VF_CUDA(expr)                                                                       \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return vf::fail(VF_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,      \
+                            cudaGetErrorString(_e));                                        \
+    } while (0)
+#define VF_TRY(expr)                  \
+    do {                              \
+        int _s = (expr);              \
+        if (_s != VF_OK) return _s;   \
+    } while (0)
+
+// ---- tensor maps (driver entry point fetched at run time; the library does not link libcuda)
+int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes,
+                     uint32_t box_rows, uint32_t box_cols);
+
+// ---- GEMM: D[M,N] = epilogue(A[M,K] . B[N,K]^T), fp16 operands, fp32 accumulate (tcgen05)
+struct GemmEpi {
+    void* out;              // fp16 or fp32, row pitch ldo elements
+    const float* bias;      // [N] or null          v = acc * scale[n] + bias[n]
+    const float* scale;     // [N] or null
+    const float* residual;  // fp32 [rows, ldr] or null, indexed by the OUTPUT row; added after activation
+    const float* addend;    // fp32 [gout, N] or null: added per (output row within group, n) -- positional embedding
+    int ldo, ldr;
+    int out_f32;            // 0: fp16 out, 1: fp32 out
+    int act;                // VF_ACT_*
+    int gin, gout, goff;    // row remap: out_row = (m / gin) * gout + goff + m % gin   (gin == 0: identity)
+};
+int gemm_f16(const __half* A, int lda, const __half* B, int ldb, int M, int N, int K, const GemmEpi& ep,
+             cudaStream_t stream);
+int device_sm_count();
+
+// ---- elementwise / reduction kernels
+int launch_clip_patchify(const uint8_t* src, int n, int src_h, int src_w, int crop_y, int crop_x, __half* patches,
+                         cudaStream_t s);
+int launch_clip_patchify_f32(const float* src_chw, int n, __half* patches, cudaStream_t s);
+int launch_clip_normalize_f32(const uint8_t* src, int n, int src_h, int src_w, int crop_y, int crop_x, float* dst_chw,
+                              cudaStream_t s);
+int launch_layernorm(const float* x, int64_t x_row_stride, const float* cls_row, int cls_period, const float* gamma,
+                     const float* beta, void* out, int64_t out_row_stride, int out_f32, int rows, int width,
+                     cudaStream_t s);
+int launch_attention(const __half* qkv, __half* out, int n_frames, int tokens, int heads, cudaStream_t s);
+int launch_resample(const uint8_t* src, int n, int in_h, int in_w, uint8_t* tmp, uint8_t* dst, int out_h, int out_w,
+                    const int* kh_bounds, const int* kh_coef, int kh_size, const int* kv_bounds, const int* kv_coef,
+                    int kv_size, cudaStream_t s);
+
+// host: Pillow-compatible resize (coefficient tables built in float64, cached on the device per geometry)
+int resize_u8(const uint8_t* src, int n, int in_h, int in_w, uint8_t* dst, int out_h, int out_w, int filter,
+              uint8_t* tmp, cudaStream_t s);
+// torchvision CenterCrop offset: int(round((dim - crop) / 2.0)), Python round-half-to-even
+int center_crop_offset(int dim, int crop);
+
+}  // namespace vf

@@ -1,0 +1,352 @@
+// Memory-bound kernels of the CLIP path: frame transform (normalise / patchify), LayerNorm,
+// 50-token attention, and the Pillow-compatible fixed-point resample.  All are HBM/L2-bound
+// byte-and-float shuffles: 128-bit accesses, warp-shuffle reductions, no tensor cores.
+#include "common.cuh"
+#include "internal.h"
+
+namespace vf {
+
+namespace {
+
+// clip.clip._transform Normalize constants (third-party openai/CLIP), float32-rounded like torch does
+__constant__ float kClipMean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
+__constant__ float kClipStd[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+
+__device__ __forceinline__ float clip_norm(uint8_t v, int c) {
+    // ToTensor: float32(v) / 255 ; Normalize: (x - mean) / std -- IEEE fp32 ops, same order as torchvision
+    return __fdiv_rn(__fsub_rn(__fdiv_rn(float(v), 255.0f), kClipMean[c]), kClipStd[c]);
+}
+
+// uint8 HWC frames (cropped window 224x224 at (cy,cx)) -> fp16 patch matrix [n*49, 3072],
+// column = c*1024 + ky*32 + kx  (the natural flattening of conv1.weight[768,3,32,32]).
+// One thread: 16 pixels (48 B in, 3 x 32 B out).
+__global__ void clip_patchify_u8_kernel(const uint8_t* __restrict__ src, int n, int src_h, int src_w, int cy, int cx,
+                                        __half* __restrict__ out) {
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(n) * 224 * 14;
+    if (idx >= total) return;
+    const int xg = int(idx % 14);
+    const int y = int((idx / 14) % 224);
+    const int b = int(idx / (14 * 224));
+    const uint8_t* p = src + ((int64_t(b) * src_h + cy + y) * src_w + cx + xg * 16) * 3;
+    __align__(16) uint8_t px[48];
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        const uint4* p4 = reinterpret_cast<const uint4*>(p);
+        uint4* d4 = reinterpret_cast<uint4*>(px);
+        d4[0] = __ldg(p4);
+        d4[1] = __ldg(p4 + 1);
+        d4[2] = __ldg(p4 + 2);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 48; ++i) px[i] = __ldg(p + i);
+    }
+    const int py = y >> 5, ky = y & 31, pxi = xg >> 1, kx0 = (xg & 1) * 16;
+    __half* orow = out + (int64_t(b) * 49 + py * 7 + pxi) * 3072 + ky * 32 + kx0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            pk[i] = pack_half2(clip_norm(px[(2 * i) * 3 + c], c), clip_norm(px[(2 * i + 1) * 3 + c], c));
+        uint4* o4 = reinterpret_cast<uint4*>(orow + c * 1024);
+        o4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        o4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    }
+}
+
+// fp32 CHW frames (already transformed, what encode_image receives) -> fp16 patch matrix. 8 px / thread.
+__global__ void clip_patchify_f32_kernel(const float* __restrict__ src, int n, __half* __restrict__ out) {
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(n) * 3 * 224 * 28;
+    if (idx >= total) return;
+    const int xg = int(idx % 28);
+    const int y = int((idx / 28) % 224);
+    const int c = int((idx / (28 * 224)) % 3);
+    const int b = int(idx / (28 * 224 * 3));
+    const float4* p = reinterpret_cast<const float4*>(src + ((int64_t(b) * 3 + c) * 224 + y) * 224 + xg * 8);
+    const float4 a = __ldg(p), d = __ldg(p + 1);
+    const int py = y >> 5, ky = y & 31, pxi = xg >> 2, kx0 = (xg & 3) * 8;
+    __half* o = out + (int64_t(b) * 49 + py * 7 + pxi) * 3072 + c * 1024 + ky * 32 + kx0;
+    *reinterpret_cast<uint4*>(o) =
+        make_uint4(pack_half2(a.x, a.y), pack_half2(a.z, a.w), pack_half2(d.x, d.y), pack_half2(d.z, d.w));
+}
+
+// uint8 HWC (crop window) -> fp32 CHW normalised: the tensor the reference feeds encode_image. 4 px / thread.
+__global__ void clip_normalize_f32_kernel(const uint8_t* __restrict__ src, int n, int src_h, int src_w, int cy, int cx,
+                                          float* __restrict__ dst) {
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(n) * 224 * 56;
+    if (idx >= total) return;
+    const int xg = int(idx % 56);
+    const int y = int((idx / 56) % 224);
+    const int b = int(idx / (56 * 224));
+    const uint8_t* p = src + ((int64_t(b) * src_h + cy + y) * src_w + cx + xg * 4) * 3;
+    uint8_t px[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) px[i] = __ldg(p + i);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float4 v = make_float4(clip_norm(px[c], c), clip_norm(px[3 + c], c), clip_norm(px[6 + c], c),
+                               clip_norm(px[9 + c], c));
+        *reinterpret_cast<float4*>(dst + ((int64_t(b) * 3 + c) * 224 + y) * 224 + xg * 4) = v;
+    }
+}
+
+// LayerNorm over rows of 768 fp32 (eps 1e-5, biased variance), one warp per row, two-pass in registers.
+// Rows with (row % cls_period == 0) read `cls_row` instead of x (the CLS token = class_embedding + pos[0]).
+__global__ void layernorm768_kernel(const float* __restrict__ x, int64_t x_row_stride,
+                                    const float* __restrict__ cls_row, int cls_period,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta, void* out,
+                                    int64_t out_row_stride, int out_f32, int rows) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (row >= rows) return;
+    const float* src = x + int64_t(row) * x_row_stride;
+    if (cls_row != nullptr && (row % cls_period) == 0) src = cls_row;
+    float4 v[6];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        v[i] = *reinterpret_cast<const float4*>(src + (lane + 32 * i) * 4);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * (1.0f / 768.0f);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / 768.0f) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int col = (lane + 32 * i) * 4;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + col));
+        float4 y;
+        y.x = (v[i].x - mean) * rstd * g.x + bb.x;
+        y.y = (v[i].y - mean) * rstd * g.y + bb.y;
+        y.z = (v[i].z - mean) * rstd * g.z + bb.z;
+        y.w = (v[i].w - mean) * rstd * g.w + bb.w;
+        if (out_f32) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + int64_t(row) * out_row_stride + col) = y;
+        } else {
+            *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + int64_t(row) * out_row_stride + col) =
+                make_uint2(pack_half2(y.x, y.y), pack_half2(y.z, y.w));
+        }
+    }
+}
+
+// Self-attention for one (frame, head): S = 50 tokens, head_dim 64, no mask.  q is scaled by 1/8 after the
+// in-projection (torch nn.MultiheadAttention semantics).  Thread t owns query t; K and V rows live in shared
+// memory as fp32 and are read as warp-wide broadcasts; softmax is computed in fp32 registers.
+constexpr int ATT_S = 50, ATT_D = 64;
+__global__ void __launch_bounds__(64) attention50_kernel(const __half* __restrict__ qkv, __half* __restrict__ out,
+                                                         int heads) {
+    __shared__ __align__(16) float Ks[ATT_S][ATT_D];
+    __shared__ __align__(16) float Vs[ATT_S][ATT_D];
+    const int frame = blockIdx.x / heads, head = blockIdx.x % heads;
+    const int width = heads * ATT_D;
+    const int64_t row0 = int64_t(frame) * ATT_S;
+    const int ld = 3 * width;
+    for (int i = threadIdx.x; i < ATT_S * 8; i += blockDim.x) {
+        const int r = i >> 3, seg = i & 7;
+        const __half* base = qkv + (row0 + r) * ld + head * ATT_D + seg * 8;
+        const uint4 kraw = __ldg(reinterpret_cast<const uint4*>(base + width));
+        const uint4 vraw = __ldg(reinterpret_cast<const uint4*>(base + 2 * width));
+        const __half2* kh = reinterpret_cast<const __half2*>(&kraw);
+        const __half2* vh = reinterpret_cast<const __half2*>(&vraw);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 kf = __half22float2(kh[j]), vf2 = __half22float2(vh[j]);
+            Ks[r][seg * 8 + 2 * j] = kf.x;
+            Ks[r][seg * 8 + 2 * j + 1] = kf.y;
+            Vs[r][seg * 8 + 2 * j] = vf2.x;
+            Vs[r][seg * 8 + 2 * j + 1] = vf2.y;
+        }
+    }
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t >= ATT_S) return;
+    float q[ATT_D];
+    {
+        const __half* qp = qkv + (row0 + t) * ld + head * ATT_D;
+#pragma unroll
+        for (int seg = 0; seg < 8; ++seg) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(qp + seg * 8));
+            const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h[j]);
+                q[seg * 8 + 2 * j] = f.x * 0.125f;
+                q[seg * 8 + 2 * j + 1] = f.y * 0.125f;
+            }
+        }
+    }
+    float sc[ATT_S];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < ATT_S; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int d = 0; d < ATT_D; d += 4) {
+            const float4 k4 = *reinterpret_cast<const float4*>(&Ks[j][d]);
+            a = fmaf(q[d], k4.x, a);
+            a = fmaf(q[d + 1], k4.y, a);
+            a = fmaf(q[d + 2], k4.z, a);
+            a = fmaf(q[d + 3], k4.w, a);
+        }
+        sc[j] = a;
+        mx = fmaxf(mx, a);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < ATT_S; ++j) {
+        sc[j] = __expf(sc[j] - mx);
+        sum += sc[j];
+    }
+    const float inv = 1.0f / sum;
+    float o[ATT_D];
+#pragma unroll
+    for (int d = 0; d < ATT_D; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < ATT_S; ++j) {
+        const float p = sc[j] * inv;
+#pragma unroll
+        for (int d = 0; d < ATT_D; d += 4) {
+            const float4 v4 = *reinterpret_cast<const float4*>(&Vs[j][d]);
+            o[d] = fmaf(p, v4.x, o[d]);
+            o[d + 1] = fmaf(p, v4.y, o[d + 1]);
+            o[d + 2] = fmaf(p, v4.z, o[d + 2]);
+            o[d + 3] = fmaf(p, v4.w, o[d + 3]);
+        }
+    }
+    __half* op = out + (row0 + t) * width + head * ATT_D;
+#pragma unroll
+    for (int seg = 0; seg < 8; ++seg) {
+        *reinterpret_cast<uint4*>(op + seg * 8) =
+            make_uint4(pack_half2(o[seg * 8], o[seg * 8 + 1]), pack_half2(o[seg * 8 + 2], o[seg * 8 + 3]),
+                       pack_half2(o[seg * 8 + 4], o[seg * 8 + 5]), pack_half2(o[seg * 8 + 6], o[seg * 8 + 7]));
+    }
+}
+
+// Pillow ImagingResampleHorizontal_8bpc / Vertical_8bpc (third-party Pillow, libImaging/Resample.c), 3 channels:
+//   acc = 2^21 + sum_i px[i] * k[i]  (int32) ;  out = clip8(acc >> 22)
+__device__ __forceinline__ uint8_t clip8(int acc) {
+    const int v = acc >> 22;
+    return uint8_t(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+__global__ void resample_h_kernel(const uint8_t* __restrict__ src, int n, int in_h, int in_w, uint8_t* __restrict__ dst,
+                                  int out_w, const int* __restrict__ bounds, const int* __restrict__ coef, int ksize) {
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(n) * in_h * out_w;
+    if (idx >= total) return;
+    const int xx = int(idx % out_w);
+    const int64_t row = idx / out_w;   // b*in_h + y
+    const int xmin = __ldg(bounds + 2 * xx), cnt = __ldg(bounds + 2 * xx + 1);
+    const int* k = coef + int64_t(xx) * ksize;
+    const uint8_t* p = src + (row * in_w + xmin) * 3;
+    int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
+    for (int i = 0; i < cnt; ++i) {
+        const int kv = __ldg(k + i);
+        s0 += int(__ldg(p + 3 * i)) * kv;
+        s1 += int(__ldg(p + 3 * i + 1)) * kv;
+        s2 += int(__ldg(p + 3 * i + 2)) * kv;
+    }
+    uint8_t* o = dst + (row * out_w + xx) * 3;
+    o[0] = clip8(s0);
+    o[1] = clip8(s1);
+    o[2] = clip8(s2);
+}
+__global__ void resample_v_kernel(const uint8_t* __restrict__ src, int n, int in_h, int w, uint8_t* __restrict__ dst,
+                                  int out_h, const int* __restrict__ bounds, const int* __restrict__ coef, int ksize) {
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(n) * out_h * w;
+    if (idx >= total) return;
+    const int x = int(idx % w);
+    const int yy = int((idx / w) % out_h);
+    const int b = int(idx / (int64_t(w) * out_h));
+    const int ymin = __ldg(bounds + 2 * yy), cnt = __ldg(bounds + 2 * yy + 1);
+    const int* k = coef + int64_t(yy) * ksize;
+    const uint8_t* p = src + ((int64_t(b) * in_h + ymin) * w + x) * 3;
+    const int64_t pitch = int64_t(w) * 3;
+    int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
+    for (int i = 0; i < cnt; ++i) {
+        const int kv = __ldg(k + i);
+        s0 += int(__ldg(p + i * pitch)) * kv;
+        s1 += int(__ldg(p + i * pitch + 1)) * kv;
+        s2 += int(__ldg(p + i * pitch + 2)) * kv;
+    }
+    uint8_t* o = dst + ((int64_t(b) * out_h + yy) * w + x) * 3;
+    o[0] = clip8(s0);
+    o[1] = clip8(s1);
+    o[2] = clip8(s2);
+}
+
+inline unsigned blocks_for(int64_t total, int threads) { return unsigned((total + threads - 1) / threads); }
+
+}  // namespace
+
+int launch_clip_patchify(const uint8_t* src, int n, int src_h, int src_w, int crop_y, int crop_x, __half* patches,
+                         cudaStream_t s) {
+    const int64_t total = int64_t(n) * 224 * 14;
+    clip_patchify_u8_kernel<<<blocks_for(total, 256), 256, 0, s>>>(src, n, src_h, src_w, crop_y, crop_x, patches);
+    VF_CUDA(cudaGetLastError());
+    return VF_OK;
+}
+int launch_clip_patchify_f32(const float* src_chw, int n, __half* patches, cudaStream_t s) {
+    const int64_t total = int64_t(n) * 3 * 224 * 28;
+    clip_patchify_f32_kernel<<<blocks_for(total, 256), 256, 0, s>>>(src_chw, n, patches);
+    VF_CUDA(cudaGetLastError());
+    return VF_OK;
+}
+int launch_clip_normalize_f32(const uint8_t* src, int n, int src_h, int src_w, int crop_y, int crop_x, float* dst_chw,
+                              cudaStream_t s) {
+    const int64_t total = int64_t(n) * 224 * 56;
+    clip_normalize_f32_kernel<<<blocks_for(total, 256), 256, 0, s>>>(src, n, src_h, src_w, crop_y, crop_x, dst_chw);
+    VF_CUDA(cudaGetLastError());
+    return VF_OK;
+}
+int launch_layernorm(const float* x, int64_t x_row_stride, const float* cls_row, int cls_period, const float* gamma,
+                     const float* beta, void* out, int64_t out_row_stride, int out_f32, int rows, int width,
+                     cudaStream_t s) {
+    if (width != 768) return fail(VF_ERR_UNSUPPORTED, "layernorm: width %d (only 768 is built)", width);
+    const int warps = 8;
+    layernorm768_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, s>>>(x, x_row_stride, cls_row, cls_period, gamma,
+                                                                         beta, out, out_row_stride, out_f32, rows);
+    VF_CUDA(cudaGetLastError());
+    return VF_OK;
+}
+int launch_attention(const __half* qkv, __half* out, int n_frames, int tokens, int heads, cudaStream_t s) {
+    if (tokens != ATT_S) return fail(VF_ERR_UNSUPPORTED, "attention: %d tokens (only 50 is built)", tokens);
+    attention50_kernel<<<n_frames * heads, 64, 0, s>>>(qkv, out, heads);
+    VF_CUDA(cudaGetLastError());
+    return VF_OK;
+}
+int launch_resample(const uint8_t* src, int n, int in_h, int in_w, uint8_t* tmp, uint8_t* dst, int out_h, int out_w,
+                    const int* kh_bounds, const int* kh_coef, int kh_size, const int* kv_bounds, const int* kv_coef,
+                    int kv_size, cudaStream_t s) {
+    // Pillow order: horizontal pass first (rounded to uint8), then vertical; a pass is skipped when the
+    // axis size is unchanged (ImagingResample: need_horizontal / need_vertical).
+    const bool need_h = out_w != in_w, need_v = out_h != in_h;
+    const uint8_t* cur = src;
+    if (need_h) {
+        uint8_t* hdst = need_v ? tmp : dst;
+        const int64_t total = int64_t(n) * in_h * out_w;
+        resample_h_kernel<<<blocks_for(total, 256), 256, 0, s>>>(cur, n, in_h, in_w, hdst, out_w, kh_bounds, kh_coef,
+                                                                 kh_size);
+        VF_CUDA(cudaGetLastError());
+        cur = hdst;
+    }
+    if (need_v) {
+        const int64_t total = int64_t(n) * out_h * out_w;
+        resample_v_kernel<<<blocks_for(total, 256), 256, 0, s>>>(cur, n, in_h, out_w, dst, out_h, kv_bounds, kv_coef,
+                                                                 kv_size);
+        VF_CUDA(cudaGetLastError());
+    } else if (!need_h) {
+        VF_CUDA(cudaMemcpyAsync(dst, src, size_t(n) * in_h * in_w * 3, cudaMemcpyDeviceToDevice, s));
+    }
+    return VF_OK;
+}
+
+}  // namespace vf
