@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the CLIP ViT-B/32 hot path (BASELINE.json configs[1]) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one pass of the hot path (uint8 frames -> transform -> ViT-B/32 tower -> (n,512) fp32 features)
+over one batch of 1000 synthetic 224x224x3 uint8 frames per GPU.  Prints ONE JSON line (rank 0):
+  value     whole-job frames/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       same metric through the host-buffer C-ABI call (pinned host frames in, host features out; the H2D and
+            D2H copies are inside the timed region)
+  roofline  tensor-pipe roofline of the dominant kernel (the tcgen05 GEMM), from per-launch CUDA events
+  cpu_baseline  the oracle port (PIL transform + fp32 torch tower) timed on this box's host cores (N=1, rank 0)
+`--impl reference` times only that CPU path (the reference's `--cpu` path restated) and prints the
+same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FRAMES_PER_STEP = 1000
+METRIC = "frames/sec CLIP-ViT-B/32 @224px"
+UNIT = "frames/s"
+WORKLOAD = "CLIP-ViT-B/32 fix_2 on 1k synthetic 224x224 RGB frames (BASELINE.json configs[1])"
+GEMM_FLOP_PER_FRAME = 231_211_008 + 12 * (715_468_800 - 2 * 3_840_000) + 786_432   # 2*M*N*K of the GEMM launches
+FLOP_PER_FRAME = 231_211_008 + 12 * 715_468_800 + 786_432                            # 8.818 GFLOP
+
+
+def base_config(n_gpus: int) -> dict:
+    return {
+        "workload": WORKLOAD,
+        "feature_type": "CLIP-ViT-B/32",
+        "frames_per_step_per_gpu": FRAMES_PER_STEP,
+        "frame": "224x224x3 uint8 HWC",
+        "weights": "synthetic, seed 0, openai visual.* layout (real CLIP weights are not available offline)",
+        "accumulate": "fp32",
+        "l2": "inputs are 150.5 MB per step per GPU > 126 MB L2 (no explicit flush needed)",
+        "parallelism": f"dp{n_gpus}: frame list sharded per rank, one NCCL all_gather of the (n,512) features per step"
+        if n_gpus > 1 else "dp1",
+    }
+
+
+def load_peaks() -> dict:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tflops_sustained": float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0))),
+                "tflops_burst": float(d.get("bf16_tflops", 1590.0)), "hbm_gbs": float(d.get("hbm_gbs", 6650.0)),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.mktemp(prefix="vf_clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load": samples in the upper half of the observed power range
+        thr = (max(pw) + min(pw)) / 2 if pw else 0
+        loaded = [s for s, p in zip(sm, pw) if p >= thr] or sm
+        return {"sm_mhz": statistics.median(loaded), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------- CPU (oracle) arm
+def synth_frames_host(n: int, seed: int):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, 256, (n, 224, 224, 3), dtype=torch.uint8, generator=g)
+
+
+def cpu_step(sd, frames_np):
+    """The reference's per-video flow (models/CLIP/extract_clip.py:107-131) on the oracle port:
+    PIL transform per frame -> stack -> fp32 tower -> numpy."""
+    import torch
+    from oracle import clip_preprocess, clip_tower
+    batch = clip_preprocess.preprocess_batch(frames_np)
+    with torch.no_grad():
+        return clip_tower.encode_image(sd, batch).numpy()
+
+
+def time_cpu(sample: int, reps: int, warm: int):
+    import torch
+    from oracle import clip_tower
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = clip_tower.synthetic_state_dict(0)
+    frames = synth_frames_host(sample, 1234).numpy()
+    for _ in range(warm):
+        cpu_step(sd, frames)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_step(sd, frames)
+        ts.append(time.perf_counter() - t0)
+    return ts, cores
+
+
+def cpu_model_name() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args, rank: int) -> None:
+    if rank != 0:
+        return
+    sample = 256
+    ts, cores = time_cpu(sample, max(args.steps, 1), max(args.warmup, 1))
+    total = sum(ts)
+    value = sample * len(ts) / total
+    desc = (f"{sample} of the 1000 frames per step; PIL transform + fp32 torch tower (oracle port of the "
+            f"reference --cpu path), torch threads={cores}, {cpu_model_name()}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(ts), "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * total / len(ts),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": base_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------- GPU arm
+def run_engine(args, rank: int, world: int, local_rank: int) -> None:
+    import torch
+    import torch.distributed as dist
+    from oracle import clip_tower                      # synthetic weight generator only (checker infrastructure)
+    from video_features_b200.clip_engine import ClipEngine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    sd = clip_tower.synthetic_state_dict(0)
+    eng = ClipEngine(sd, device=local_rank, chunk_frames=args.chunk)
+    n = FRAMES_PER_STEP
+    frames_host = synth_frames_host(n, 100 + rank).pin_memory()
+    frames_dev = frames_host.to(dev)
+    out_host = torch.empty((n, 512), dtype=torch.float32).pin_memory()
+    gathered = torch.empty((world * n, 512), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_dev():
+        y = eng.encode_frames_u8(frames_dev)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, y)
+        return y
+
+    def step_host():
+        y = eng.encode_frames_u8_host(frames_host, out_host)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, y.to(dev, non_blocking=True))
+        return y
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item())
+
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+    for _ in range(W):
+        step_dev()
+    launches0 = eng.launch_count
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_total = timed(step_dev, K)
+    clocks = sampler.stop() if sampler else None
+    launches = (eng.launch_count - launches0) // K
+    value = world * n * K / (ms_total / 1e3)
+
+    # end-to-end through the host-buffer entry point
+    for _ in range(2):
+        step_host()
+    ms_e2e = timed(step_host, K)
+    e2e_value = world * n * K / (ms_e2e / 1e3)
+
+    # roofline of the dominant kernel: per-launch CUDA events around every tcgen05 GEMM launch, separate pass over
+    # the same steps so the timed region above is not perturbed
+    eng.profile(True)
+    pk = min(K, 5)
+    for _ in range(pk):
+        eng.encode_frames_u8(frames_dev)
+    gemm_ms, gemm_launches, gemm_flops = eng.profile_read()
+    eng.profile(False)
+    peaks = load_peaks()
+    achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {
+        "bound": "tensor", "kernel": "vf::gemm_f16_kernel (tcgen05.mma kind::f16, fp32 accumulate in TMEM)",
+        "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+        "frac": achieved / peaks["tflops_sustained"], "peak_source": peaks["source"] + ", bf16 dense sustained",
+        "traffic": None,
+        "launches_per_step": gemm_launches // pk, "avg_launch_us": 1e3 * gemm_ms / max(gemm_launches, 1),
+        "algorithmic_flop_per_launch_avg": gemm_flops / max(gemm_launches, 1),
+        "gemm_share_of_step": (gemm_ms / pk) / (ms_total / K),
+        "whole_step_tflops": value / world * FLOP_PER_FRAME / 1e12,
+        "whole_step_frac": value / world * FLOP_PER_FRAME / 1e12 / peaks["tflops_sustained"],
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic",
+        "config": dict(base_config(world), chunk_frames=args.chunk or 240),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
+                "h2d_bytes_per_step": int(frames_host.numel()) * world,
+                "d2h_bytes_per_step": int(out_host.numel() * 4) * world,
+                "api": "vf_clip_encode_u8_host (ClipEngine.encode_frames_u8_host), pinned host buffers"},
+        "gpu_launches": int(launches * K),
+        "gpu_launches_per_step": int(launches),
+        "roofline": roofline,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        ts, cores = time_cpu(256, 3, 1)
+        v = 256 * len(ts) / sum(ts)
+        line["cpu_baseline"] = {
+            "value": v, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"256 of the 1000 frames x {len(ts)} reps (+1 warm-up); PIL transform + fp32 torch tower "
+                      f"(oracle port of the reference --cpu path), torch threads={cores}, {cpu_model_name()}",
+            "median_s_per_rep": statistics.median(ts)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--chunk", type=int, default=0, help="frames per tower chunk (0 = library default)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run on this node
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29541"),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_engine(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -102,6 +102,11 @@ int vf_clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, int 
                            void* stream);
 /* number of kernels this library has launched on behalf of `h` so far (diagnostics / bench). */
 int64_t vf_clip_launch_count(const vf_clip_t* h);
+/* Roofline instrumentation for bench.py: while enabled, every tensor-core GEMM launch of `h` is bracketed by a
+ * pair of CUDA events recorded on the launching stream.  vf_clip_profile_read synchronises the device, returns the
+ * summed GEMM device time (ms), the number of GEMM launches and their algorithmic FLOPs (2*M*N*K), and resets. */
+int vf_clip_profile(vf_clip_t* h, int enable);
+int vf_clip_profile_read(vf_clip_t* h, double* gemm_ms, int64_t* gemm_launches, double* gemm_flops);
 
 #ifdef __cplusplus
 }

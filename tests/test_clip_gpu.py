@@ -8,6 +8,8 @@ import numpy as np
 import pytest
 import torch
 
+import video_features_b200  # noqa: F401  (registers torch.ops.vfeat)
+
 pytestmark = pytest.mark.gpu
 
 MEAN = torch.tensor([0.48145466, 0.4578275, 0.40821073])

@@ -4,6 +4,8 @@ import torch
 
 from conftest import rel_l2
 
+import video_features_b200  # noqa: F401  (registers torch.ops.vfeat)
+
 pytestmark = pytest.mark.gpu
 
 

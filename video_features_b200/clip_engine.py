@@ -101,6 +101,15 @@ class ClipEngine:
     def launch_count(self) -> int:
         return int(lib().vf_clip_launch_count(self._h))
 
+    def profile(self, enable: bool) -> None:
+        check(lib().vf_clip_profile(self._h, int(enable)))
+
+    def profile_read(self):
+        """-> (gemm device ms, gemm launches, gemm algorithmic FLOPs) since the last read."""
+        ms, n, fl = C.c_double(), C.c_int64(), C.c_double()
+        check(lib().vf_clip_profile_read(self._h, C.byref(ms), C.byref(n), C.byref(fl)))
+        return ms.value, n.value, fl.value
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             lib().vf_clip_destroy(self._h)

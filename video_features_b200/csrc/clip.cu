@@ -41,6 +41,11 @@ struct vf_clip {
     size_t stage_cap = 0, resized_cap = 0, tmp_cap = 0;
     float* out_dev = nullptr;
     size_t out_cap = 0;
+    // roofline instrumentation (vf_clip_profile)
+    bool prof = false;
+    std::vector<cudaEvent_t> prof_events;   // pairs
+    size_t prof_used = 0;
+    double prof_flops = 0.0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
 };
@@ -95,6 +100,26 @@ static GemmEpi epi(void* out, int ldo, int out_f32, const float* bias, int act) 
     return e;
 }
 
+// GEMM launch of the tower; bracketed by events when profiling is on
+static int tower_gemm(vf_clip* h, const __half* A, int lda, const __half* B, int ldb, int M, int N, int K,
+                      const GemmEpi& ep, cudaStream_t s) {
+    if (!h->prof) return gemm_f16(A, lda, B, ldb, M, N, K, ep, s);
+    if (h->prof_used + 2 > h->prof_events.size()) {
+        for (int i = 0; i < 2; ++i) {
+            cudaEvent_t e;
+            VF_CUDA(cudaEventCreate(&e));
+            h->prof_events.push_back(e);
+        }
+    }
+    cudaEvent_t e0 = h->prof_events[h->prof_used], e1 = h->prof_events[h->prof_used + 1];
+    VF_CUDA(cudaEventRecord(e0, s));
+    VF_TRY(gemm_f16(A, lda, B, ldb, M, N, K, ep, s));
+    VF_CUDA(cudaEventRecord(e1, s));
+    h->prof_used += 2;
+    h->prof_flops += 2.0 * double(M) * double(N) * double(K);
+    return VF_OK;
+}
+
 // the tower on one chunk whose patch matrix is already in h->patches; writes c x 512 fp32 to out
 static int clip_tower_chunk(vf_clip* h, int c, float* out, cudaStream_t s) {
     const int M = c * T;
@@ -102,7 +127,7 @@ static int clip_tower_chunk(vf_clip* h, int c, float* out, cudaStream_t s) {
     {
         GemmEpi e = epi(h->x, W, 1, nullptr, VF_ACT_NONE);
         e.addend = h->pos; e.gin = P; e.gout = T; e.goff = 1;
-        VF_TRY(gemm_f16(h->patches, PK, h->w_patch, PK, c * P, W, PK, e, s));
+        VF_TRY(tower_gemm(h, h->patches, PK, h->w_patch, PK, c * P, W, PK, e, s));
     }
     // ln_pre in place; CLS rows are sourced from class_embedding + pos[0]
     VF_TRY(launch_layernorm(h->x, W, h->cls_pos0, T, h->lnpre_w, h->lnpre_b, h->x, W, 1, M, W, s));
@@ -110,25 +135,25 @@ static int clip_tower_chunk(vf_clip* h, int c, float* out, cudaStream_t s) {
     for (int l = 0; l < L; ++l) {
         const ClipLayerDev& w = h->layer[l];
         VF_TRY(launch_layernorm(h->x, W, nullptr, 0, w.ln1_w, w.ln1_b, h->h, W, 0, M, W, s));
-        VF_TRY(gemm_f16(h->h, W, w.w_qkv, W, M, 3 * W, W, epi(h->qkv, 3 * W, 0, w.b_qkv, VF_ACT_NONE), s));
+        VF_TRY(tower_gemm(h, h->h, W, w.w_qkv, W, M, 3 * W, W, epi(h->qkv, 3 * W, 0, w.b_qkv, VF_ACT_NONE), s));
         VF_TRY(launch_attention(h->qkv, h->att, c, T, H, s));
         {
             GemmEpi e = epi(h->x, W, 1, w.b_o, VF_ACT_NONE);
             e.residual = h->x; e.ldr = W;
-            VF_TRY(gemm_f16(h->att, W, w.w_o, W, M, W, W, e, s));
+            VF_TRY(tower_gemm(h, h->att, W, w.w_o, W, M, W, W, e, s));
         }
         VF_TRY(launch_layernorm(h->x, W, nullptr, 0, w.ln2_w, w.ln2_b, h->h, W, 0, M, W, s));
-        VF_TRY(gemm_f16(h->h, W, w.w_fc, W, M, MLPW, W, epi(h->mlp, MLPW, 0, w.b_fc, VF_ACT_QUICKGELU), s));
+        VF_TRY(tower_gemm(h, h->h, W, w.w_fc, W, M, MLPW, W, epi(h->mlp, MLPW, 0, w.b_fc, VF_ACT_QUICKGELU), s));
         {
             GemmEpi e = epi(h->x, W, 1, w.b_proj, VF_ACT_NONE);
             e.residual = h->x; e.ldr = W;
-            VF_TRY(gemm_f16(h->mlp, MLPW, w.w_proj, MLPW, M, W, MLPW, e, s));
+            VF_TRY(tower_gemm(h, h->mlp, MLPW, w.w_proj, MLPW, M, W, MLPW, e, s));
         }
         h->launches += 7;
     }
     // ln_post on the CLS rows, then the 768 -> 512 projection
     VF_TRY(launch_layernorm(h->x, int64_t(T) * W, nullptr, 0, h->lnpost_w, h->lnpost_b, h->cls, W, 0, c, W, s));
-    VF_TRY(gemm_f16(h->cls, W, h->w_proj, W, c, E, W, epi(out, E, 1, nullptr, VF_ACT_NONE), s));
+    VF_TRY(tower_gemm(h, h->cls, W, h->w_proj, W, c, E, W, epi(out, E, 1, nullptr, VF_ACT_NONE), s));
     h->launches += 2;
     return VF_OK;
 }
@@ -170,7 +195,7 @@ extern "C" {
 int vf_clip_create(vf_clip_t** out, const vf_clip_weights* w, int device, int chunk_frames) {
     if (!out || !w) return fail(VF_ERR_INVALID, "clip_create: null argument");
     *out = nullptr;
-    if (chunk_frames <= 0) chunk_frames = 120;   // 6000 rows = 47 M-tiles: 3/1/4/1 near-full waves of 148 SMs
+    if (chunk_frames <= 0) chunk_frames = 240;   // 12000 rows per GEMM; activations of a chunk stay L2-resident
     if (chunk_frames > 4096) return fail(VF_ERR_INVALID, "clip_create: chunk_frames %d too large", chunk_frames);
     VF_CUDA(cudaSetDevice(device));
     int major = 0, minor = 0;
@@ -242,6 +267,7 @@ int vf_clip_destroy(vf_clip_t* h) {
     if (h->resized) cudaFree(h->resized);
     if (h->resize_tmp) cudaFree(h->resize_tmp);
     if (h->out_dev) cudaFree(h->out_dev);
+    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
@@ -314,5 +340,29 @@ int vf_clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, int 
 }
 
 int64_t vf_clip_launch_count(const vf_clip_t* h) { return h ? h->launches : 0; }
+
+int vf_clip_profile(vf_clip_t* h, int enable) {
+    if (!h) return fail(VF_ERR_INVALID, "clip_profile: null handle");
+    h->prof = enable != 0;
+    return VF_OK;
+}
+
+int vf_clip_profile_read(vf_clip_t* h, double* gemm_ms, int64_t* gemm_launches, double* gemm_flops) {
+    if (!h) return fail(VF_ERR_INVALID, "clip_profile_read: null handle");
+    VF_CUDA(cudaSetDevice(h->device));
+    VF_CUDA(cudaDeviceSynchronize());
+    double ms = 0.0;
+    for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+        float t = 0.f;
+        VF_CUDA(cudaEventElapsedTime(&t, h->prof_events[i], h->prof_events[i + 1]));
+        ms += t;
+    }
+    if (gemm_ms) *gemm_ms = ms;
+    if (gemm_launches) *gemm_launches = int64_t(h->prof_used / 2);
+    if (gemm_flops) *gemm_flops = h->prof_flops;
+    h->prof_used = 0;
+    h->prof_flops = 0.0;
+    return VF_OK;
+}
 
 }  // extern "C"

@@ -39,7 +39,7 @@ struct GemmCfg {
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == VF_ACT_QUICKGELU) {
         // x * sigmoid(1.702 x)
-        return v / (1.0f + __expf(-1.702f * v));
+        return __fdividef(v, 1.0f + __expf(-1.702f * v));
     } else if (act == VF_ACT_RELU) {
         return fmaxf(v, 0.0f);
     }

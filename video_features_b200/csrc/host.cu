@@ -208,11 +208,11 @@ int vf_shard_range(int64_t n_items, int n_parts, int part, int64_t* begin, int64
 
 int vf_resize_geometry(int in_h, int in_w, int size, int to_smaller_edge, int* out_h, int* out_w) {
     if (in_h <= 0 || in_w <= 0 || size <= 0 || !out_h || !out_w) return fail(VF_ERR_INVALID, "resize_geometry");
-    // models/i3d/transforms/transforms.py:108-125 (== torchvision Resize(int) for to_smaller_edge)
-    const bool w_is_target = to_smaller_edge ? (in_w <= in_h) : (in_w >= in_h);
-    if ((w_is_target && in_w == size) || (!w_is_target && in_h == size)) { *out_h = in_h; *out_w = in_w; return VF_OK; }
-    if (w_is_target) { *out_w = size; *out_h = int(double(size) * in_h / in_w); }
-    else             { *out_h = size; *out_w = int(double(size) * in_w / in_h); }
+    // models/i3d/transforms/transforms.py:114-125 (== torchvision Resize(int) for to_smaller_edge)
+    const int w = in_w, h = in_h;
+    if ((w <= h && w == size) || (h <= w && h == size)) { *out_h = h; *out_w = w; return VF_OK; }
+    if ((w < h) == (to_smaller_edge != 0)) { *out_w = size; *out_h = int(double(int64_t(size) * h) / double(w)); }
+    else                                   { *out_h = size; *out_w = int(double(int64_t(size) * w) / double(h)); }
     return VF_OK;
 }
 

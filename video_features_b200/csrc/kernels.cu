@@ -138,95 +138,133 @@ __global__ void layernorm768_kernel(const float* __restrict__ x, int64_t x_row_s
 }
 
 // Self-attention for one (frame, head): S = 50 tokens, head_dim 64, no mask.  q is scaled by 1/8 after the
-// in-projection (torch nn.MultiheadAttention semantics).  Thread t owns query t; K and V rows live in shared
-// memory as fp32 and are read as warp-wide broadcasts; softmax is computed in fp32 registers.
-constexpr int ATT_S = 50, ATT_D = 64;
-__global__ void __launch_bounds__(64) attention50_kernel(const __half* __restrict__ qkv, __half* __restrict__ out,
-                                                         int heads) {
-    __shared__ __align__(16) float Ks[ATT_S][ATT_D];
-    __shared__ __align__(16) float Vs[ATT_S][ATT_D];
+// in-projection (torch nn.MultiheadAttention semantics; applied here to the fp32 scores, which is the same
+// arithmetic since 1/8 is a power of two).  The two contractions are 64x64x64 after padding -- far too small for a
+// tcgen05 tile, so they run on warp-level mma.sync (m16n8k16, fp16 in / fp32 accumulate): one block of 4 warps
+// per (frame, head), warp w owns query rows 16w..16w+15; K and V^T are staged once in shared memory; the
+// softmax lives in the accumulator fragments (fp32) with quad shuffles for the row max / row sum.
+constexpr int ATT_S = 50, ATT_D = 64, ATT_LD = 72;   // 72-half row pitch: conflict-free fragment loads
+
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(128) attention50_kernel(const __half* __restrict__ qkv, __half* __restrict__ out,
+                                                          int heads) {
+    __shared__ __align__(16) __half Ks[64][ATT_LD];   // [key][dim]
+    __shared__ __align__(16) __half Vt[64][ATT_LD];   // [dim][key]
     const int frame = blockIdx.x / heads, head = blockIdx.x % heads;
     const int width = heads * ATT_D;
-    const int64_t row0 = int64_t(frame) * ATT_S;
     const int ld = 3 * width;
-    for (int i = threadIdx.x; i < ATT_S * 8; i += blockDim.x) {
+    const int64_t row0 = int64_t(frame) * ATT_S;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+
+    // stage K (row-major) and V (transposed); keys 50..63 are zero-filled
+    for (int i = tid; i < 64 * 8; i += 128) {
         const int r = i >> 3, seg = i & 7;
-        const __half* base = qkv + (row0 + r) * ld + head * ATT_D + seg * 8;
-        const uint4 kraw = __ldg(reinterpret_cast<const uint4*>(base + width));
-        const uint4 vraw = __ldg(reinterpret_cast<const uint4*>(base + 2 * width));
-        const __half2* kh = reinterpret_cast<const __half2*>(&kraw);
-        const __half2* vh = reinterpret_cast<const __half2*>(&vraw);
+        uint4 kraw = make_uint4(0, 0, 0, 0), vraw = make_uint4(0, 0, 0, 0);
+        if (r < ATT_S) {
+            const __half* base = qkv + (row0 + r) * ld + head * ATT_D + seg * 8;
+            kraw = __ldg(reinterpret_cast<const uint4*>(base + width));
+            vraw = __ldg(reinterpret_cast<const uint4*>(base + 2 * width));
+        }
+        *reinterpret_cast<uint4*>(&Ks[r][seg * 8]) = kraw;
+        const __half* vh = reinterpret_cast<const __half*>(&vraw);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float2 kf = __half22float2(kh[j]), vf2 = __half22float2(vh[j]);
-            Ks[r][seg * 8 + 2 * j] = kf.x;
-            Ks[r][seg * 8 + 2 * j + 1] = kf.y;
-            Vs[r][seg * 8 + 2 * j] = vf2.x;
-            Vs[r][seg * 8 + 2 * j + 1] = vf2.y;
+        for (int j = 0; j < 8; ++j) Vt[seg * 8 + j][r] = vh[j];
+    }
+
+    // Q fragments straight from global (each element is used by exactly one warp)
+    const int q0 = warp * 16;
+    const int r_lo = q0 + g, r_hi = q0 + g + 8;
+    uint32_t aq[4][4];
+    {
+        const __half* qlo = qkv + (row0 + r_lo) * ld + head * ATT_D;
+        const __half* qhi = qkv + (row0 + r_hi) * ld + head * ATT_D;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const int c = ks * 16 + 2 * t;
+            aq[ks][0] = r_lo < ATT_S ? __ldg(reinterpret_cast<const uint32_t*>(qlo + c)) : 0u;
+            aq[ks][1] = r_hi < ATT_S ? __ldg(reinterpret_cast<const uint32_t*>(qhi + c)) : 0u;
+            aq[ks][2] = r_lo < ATT_S ? __ldg(reinterpret_cast<const uint32_t*>(qlo + c + 8)) : 0u;
+            aq[ks][3] = r_hi < ATT_S ? __ldg(reinterpret_cast<const uint32_t*>(qhi + c + 8)) : 0u;
         }
     }
     __syncthreads();
-    const int t = threadIdx.x;
-    if (t >= ATT_S) return;
-    float q[ATT_D];
-    {
-        const __half* qp = qkv + (row0 + t) * ld + head * ATT_D;
+
+    // S = Q K^T : 8 key tiles x 4 dim steps
+    float s[8][4];
 #pragma unroll
-        for (int seg = 0; seg < 8; ++seg) {
-            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(qp + seg * 8));
-            const __half2* h = reinterpret_cast<const __half2*>(&raw);
+    for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(h[j]);
-                q[seg * 8 + 2 * j] = f.x * 0.125f;
-                q[seg * 8 + 2 * j + 1] = f.y * 0.125f;
-            }
+        for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + g][ks * 16 + 2 * t]);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + g][ks * 16 + 2 * t + 8]);
+            mma16816(s[nt], aq[ks], b0, b1);
         }
     }
-    float sc[ATT_S];
-    float mx = -INFINITY;
+    // softmax over the 50 valid keys; rows r_lo (regs 0,1) and r_hi (regs 2,3)
+    const float sc = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
+    float m_lo = -INFINITY, m_hi = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < ATT_S; ++j) {
-        float a = 0.f;
+    for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-        for (int d = 0; d < ATT_D; d += 4) {
-            const float4 k4 = *reinterpret_cast<const float4*>(&Ks[j][d]);
-            a = fmaf(q[d], k4.x, a);
-            a = fmaf(q[d + 1], k4.y, a);
-            a = fmaf(q[d + 2], k4.z, a);
-            a = fmaf(q[d + 3], k4.w, a);
-        }
-        sc[j] = a;
-        mx = fmaxf(mx, a);
-    }
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < ATT_S; ++j) {
-        sc[j] = __expf(sc[j] - mx);
-        sum += sc[j];
-    }
-    const float inv = 1.0f / sum;
-    float o[ATT_D];
-#pragma unroll
-    for (int d = 0; d < ATT_D; ++d) o[d] = 0.f;
-#pragma unroll
-    for (int j = 0; j < ATT_S; ++j) {
-        const float p = sc[j] * inv;
-#pragma unroll
-        for (int d = 0; d < ATT_D; d += 4) {
-            const float4 v4 = *reinterpret_cast<const float4*>(&Vs[j][d]);
-            o[d] = fmaf(p, v4.x, o[d]);
-            o[d + 1] = fmaf(p, v4.y, o[d + 1]);
-            o[d + 2] = fmaf(p, v4.z, o[d + 2]);
-            o[d + 3] = fmaf(p, v4.w, o[d + 3]);
+        for (int j = 0; j < 2; ++j) {
+            const bool valid = nt * 8 + 2 * t + j < ATT_S;
+            s[nt][j] = valid ? s[nt][j] * sc : -INFINITY;
+            s[nt][2 + j] = valid ? s[nt][2 + j] * sc : -INFINITY;
+            m_lo = fmaxf(m_lo, s[nt][j]);
+            m_hi = fmaxf(m_hi, s[nt][2 + j]);
         }
     }
-    __half* op = out + (row0 + t) * width + head * ATT_D;
+    m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1));
+    m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
+    m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
+    m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+    float sum_lo = 0.f, sum_hi = 0.f;
 #pragma unroll
-    for (int seg = 0; seg < 8; ++seg) {
-        *reinterpret_cast<uint4*>(op + seg * 8) =
-            make_uint4(pack_half2(o[seg * 8], o[seg * 8 + 1]), pack_half2(o[seg * 8 + 2], o[seg * 8 + 3]),
-                       pack_half2(o[seg * 8 + 4], o[seg * 8 + 5]), pack_half2(o[seg * 8 + 6], o[seg * 8 + 7]));
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            s[nt][j] = exp2f(s[nt][j] - m_lo);          // exp2f(-inf) == 0 for the padded keys
+            s[nt][2 + j] = exp2f(s[nt][2 + j] - m_hi);
+            sum_lo += s[nt][j];
+            sum_hi += s[nt][2 + j];
+        }
+    }
+    sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1);
+    sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
+    sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1);
+    sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
+    const float inv_lo = 1.0f / sum_lo, inv_hi = 1.0f / sum_hi;
+
+    // O = P V : accumulator fragments of S become the A fragments of P (normalised in fp32 first)
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        pa[kk][0] = pack_half2(s[2 * kk][0] * inv_lo, s[2 * kk][1] * inv_lo);
+        pa[kk][1] = pack_half2(s[2 * kk][2] * inv_hi, s[2 * kk][3] * inv_hi);
+        pa[kk][2] = pack_half2(s[2 * kk + 1][0] * inv_lo, s[2 * kk + 1][1] * inv_lo);
+        pa[kk][3] = pack_half2(s[2 * kk + 1][2] * inv_hi, s[2 * kk + 1][3] * inv_hi);
+    }
+    __half* olo = out + (row0 + r_lo) * width + head * ATT_D;
+    __half* ohi = out + (row0 + r_hi) * width + head * ATT_D;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Vt[nt * 8 + g][kk * 16 + 2 * t]);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Vt[nt * 8 + g][kk * 16 + 2 * t + 8]);
+            mma16816(o, pa[kk], b0, b1);
+        }
+        if (r_lo < ATT_S) *reinterpret_cast<uint32_t*>(olo + nt * 8 + 2 * t) = pack_half2(o[0], o[1]);
+        if (r_hi < ATT_S) *reinterpret_cast<uint32_t*>(ohi + nt * 8 + 2 * t) = pack_half2(o[2], o[3]);
     }
 }
 
@@ -319,7 +357,7 @@ int launch_layernorm(const float* x, int64_t x_row_stride, const float* cls_row,
 }
 int launch_attention(const __half* qkv, __half* out, int n_frames, int tokens, int heads, cudaStream_t s) {
     if (tokens != ATT_S) return fail(VF_ERR_UNSUPPORTED, "attention: %d tokens (only 50 is built)", tokens);
-    attention50_kernel<<<n_frames * heads, 64, 0, s>>>(qkv, out, heads);
+    attention50_kernel<<<n_frames * heads, 128, 0, s>>>(qkv, out, heads);
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
