@@ -13,6 +13,8 @@
 // Used for every dense contraction of the hot path: the ViT patch-embed / QKV / out-proj / FFN GEMMs
 // (reference: third-party clip `VisionTransformer.forward`, called at models/CLIP/extract_clip.py:128).
 #include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "internal.h"
@@ -229,6 +231,209 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
 }
 
+
+// =====================================================================================================
+// v2: CTA pairs (tcgen05 cta_group::2).  A cluster of two CTAs (one TPC) owns a 256 x BN output tile: each CTA stages
+// its own 128 rows of A and HALF of the B tile (BN/2 rows), the leader issues one UMMA of M=256 that reads both
+// halves, and each CTA's TMEM receives the 128 x BN block of its rows.  Versus the single-CTA kernel this halves the
+// B bytes every SM pulls from L2 (the measured limiter of v1: ~41 B/clk/SM of L2->SM traffic at 47 % tensor-pipe
+// utilisation) and frees shared memory for a staged, fully coalesced epilogue:
+//   warps 4-11 (8 epilogue warps): tcgen05.ld (thread = row) -> padded smem transpose -> (lane = 4 columns) ->
+//   scale / bias / activation / addend / residual -> 128-byte-per-row global stores.
+template <int BN, int STAGES>
+struct Gemm2Cfg {
+    static constexpr uint32_t A_BYTES = BM * BK * 2;          // 128 rows of A per CTA
+    static constexpr uint32_t B_BYTES = (BN / 2) * BK * 2;    // half of the B tile per CTA
+    static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr uint32_t TMEM_COLS = 2 * BN;
+    static constexpr uint32_t EPI_WARPS = 8;
+    static constexpr uint32_t STG_LD = 36;                    // words per staged row (32 + 4 pad: conflict-free)
+    static constexpr uint32_t STG_BYTES = EPI_WARPS * 32 * STG_LD * 4;
+    static constexpr uint32_t BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;
+    static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const GemmEpi ep, const int M, const int N, const int K) {
+    using Cfg = Gemm2Cfg<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+    float* stg = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::STG_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta = cluster_ctarank();        // 0 = leader (issues the MMAs), 1 = peer
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int num_m = (M + 2 * BM - 1) / (2 * BM);
+    const int num_n = (N + BN - 1) / BN;
+    const int num_tiles = num_m * num_n;
+    const int num_k = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], 1);      // leader's own arrive.expect_tx; bytes of BOTH CTAs are credited here
+            mbar_init(&empty[i], 1);     // multicast tcgen05.commit from the leader
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);                       // multicast tcgen05.commit
+            mbar_init(&tempty[i], 2 * Cfg::EPI_WARPS);     // (leader only is waited on) every epilogue warp of both CTAs
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    cluster_sync_all();      // barriers of both CTAs initialised before any remote arrive / TMA credit
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                const int m_blk = tile % num_m, n_blk = tile / num_m;
+                const int m0 = m_blk * 2 * BM + int(cta) * BM;
+                const int n0 = n_blk * BN + int(cta) * (BN / 2);
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (cta == 0) mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+                    const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
+                    tma_load_2d_2sm(sA + stage * Cfg::A_BYTES, &tmA, bar, kb * BK, m0);
+                    tma_load_2d_2sm(sB + stage * Cfg::B_BYTES, &tmB, bar, kb * BK, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (leader CTA, one lane)
+        if (cta == 0 && lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN, 0);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = umma_desc_sw128(sA + stage * Cfg::A_BYTES);
+                    const uint64_t bdesc = umma_desc_sw128(sB + stage * Cfg::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit_2sm(&empty[stage], 3);    // free this smem slot in both CTAs
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_2sm(&tfull[acc], 3);           // accumulators of both CTAs complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------ epilogue: 8 warps per CTA
+        const int e = warp - 4;
+        const int q = e & 3;                   // TMEM lane quarter (warp id % 4)
+        const int half = e >> 2;               // which half of the BN columns this warp drains
+        float* my = stg + e * 32 * Cfg::STG_LD;
+        const int rq = lane >> 3, cq = (lane & 7) * 4;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+            const int m_blk = tile % num_m, n_blk = tile / num_m;
+            const int mrow0 = m_blk * 2 * BM + int(cta) * BM + q * 32;
+            // the 8 rows this lane stores (after the transpose): mrow0 + i*4 + rq
+            int64_t orow[8];
+            int arow[8];
+            bool rok[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int m = mrow0 + i * 4 + rq;
+                rok[i] = m < M;
+                orow[i] = m;
+                arow[i] = 0;
+                if (ep.gin > 0) {
+                    const int g = m / ep.gin, r = m - g * ep.gin;
+                    orow[i] = int64_t(g) * ep.gout + ep.goff + r;
+                    arow[i] = ep.goff + r;
+                }
+            }
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + acc * BN + (uint32_t(q * 32) << 16);
+#pragma unroll 1
+            for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+                uint32_t raw[32];
+                tmem_ld_32x32(t_row + c, raw);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<uint4*>(my + lane * Cfg::STG_LD + j) =
+                        make_uint4(raw[j], raw[j + 1], raw[j + 2], raw[j + 3]);
+                __syncwarp();
+                const int n = n_blk * BN + c + cq;       // first of this lane's 4 columns
+                if (n < N) {
+                    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), bi = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ep.scale) sc = __ldg(reinterpret_cast<const float4*>(ep.scale + n));
+                    if (ep.bias) bi = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (!rok[i]) continue;
+                        float4 v = *reinterpret_cast<const float4*>(my + (i * 4 + rq) * Cfg::STG_LD + cq);
+                        v.x = fmaf(v.x, sc.x, bi.x); v.y = fmaf(v.y, sc.y, bi.y);
+                        v.z = fmaf(v.z, sc.z, bi.z); v.w = fmaf(v.w, sc.w, bi.w);
+                        if (ep.act != VF_ACT_NONE) {
+                            v.x = apply_act(v.x, ep.act); v.y = apply_act(v.y, ep.act);
+                            v.z = apply_act(v.z, ep.act); v.w = apply_act(v.w, ep.act);
+                        }
+                        if (ep.addend) {
+                            const float4 a = __ldg(reinterpret_cast<const float4*>(ep.addend + int64_t(arow[i]) * N + n));
+                            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+                        }
+                        if (ep.residual) {
+                            const float4 r = *reinterpret_cast<const float4*>(ep.residual + orow[i] * ep.ldr + n);
+                            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+                        }
+                        if (ep.out_f32) {
+                            *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + orow[i] * ep.ldo + n) = v;
+                        } else {
+                            *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out) + orow[i] * ep.ldo + n) =
+                                make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(&tempty[acc], 0);   // tell the leader's MMA issuer this stage is drained
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();      // the peer's smem / barriers stay alive until the leader's MMAs and commits are done
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -261,6 +466,36 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpi& e
     gemm_f16_kernel<BN, STAGES><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, ep, M, N, K);
     VF_CUDA(cudaGetLastError());
     return VF_OK;
+}
+
+template <int BN, int STAGES>
+int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpi& ep, int M, int N, int K,
+                     cudaStream_t stream) {
+    using Cfg = Gemm2Cfg<BN, STAGES>;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    VF_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        VF_CUDA(cudaFuncSetAttribute(gemm_f16_pair_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::SMEM_BYTES));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+    const int pairs = device_sm_count() / 2;
+    const int grid = 2 * (tiles < pairs ? tiles : pairs);
+    gemm_f16_pair_kernel<BN, STAGES><<<grid, 384, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, ep, M, N, K);
+    VF_CUDA(cudaGetLastError());
+    return VF_OK;
+}
+
+// VF_GEMM=1cta selects the single-CTA kernel (kept for A/B measurements); default is the CTA-pair kernel
+bool use_single_cta() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VF_GEMM");
+        v = (e && strcmp(e, "1cta") == 0) ? 1 : 0;
+    }
+    return v == 1;
 }
 
 }  // namespace
@@ -297,7 +532,7 @@ int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 int gemm_f16(const __half* A, int lda, const __half* B, int ldb, int M, int N, int K, const GemmEpi& ep,
              cudaStream_t stream) {
     if (M <= 0 || N <= 0 || K <= 0) return fail(VF_ERR_INVALID, "gemm: empty problem %dx%dx%d", M, N, K);
-    if (N % 32) return fail(VF_ERR_INVALID, "gemm: N=%d must be a multiple of 32", N);
+    if (N % 8) return fail(VF_ERR_INVALID, "gemm: N=%d must be a multiple of 8", N);
     if (K % 8 || lda % 8 || ldb % 8) return fail(VF_ERR_INVALID, "gemm: K/lda/ldb must be multiples of 8");
     if (ep.out_f32 ? (ep.ldo % 4) : (ep.ldo % 8)) return fail(VF_ERR_INVALID, "gemm: ldo breaks 16-byte stores");
     if (ep.residual && (ep.ldr % 4)) return fail(VF_ERR_INVALID, "gemm: ldr must be a multiple of 4");
@@ -305,6 +540,14 @@ int gemm_f16(const __half* A, int lda, const __half* B, int ldb, int M, int N, i
     const int bn = (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : 64;
     CUtensorMap tmA, tmB;
     VF_TRY(make_tmap_2d_f16(&tmA, A, uint64_t(M), uint64_t(K), uint64_t(lda) * 2, BM, BK));
+    if (!use_single_cta()) {
+        const int bn2 = (N > 128) ? 256 : (N > 64) ? 128 : 64;     // pair-tile width; B box = half of it
+        VF_TRY(make_tmap_2d_f16(&tmB, B, uint64_t(N), uint64_t(K), uint64_t(ldb) * 2, uint32_t(bn2 / 2), BK));
+        if (bn2 == 256) return launch_gemm_pair<256, 5>(tmA, tmB, ep, M, N, K, stream);
+        if (bn2 == 128) return launch_gemm_pair<128, 6>(tmA, tmB, ep, M, N, K, stream);
+        return launch_gemm_pair<64, 8>(tmA, tmB, ep, M, N, K, stream);
+    }
+    if (N % 32) return fail(VF_ERR_INVALID, "gemm(1cta): N=%d must be a multiple of 32", N);
     VF_TRY(make_tmap_2d_f16(&tmB, B, uint64_t(N), uint64_t(K), uint64_t(ldb) * 2, uint32_t(bn), BK));
     if (bn == 256) return launch_gemm<256, 4>(tmA, tmB, ep, M, N, K, stream);
     if (bn == 128) return launch_gemm<128, 6>(tmA, tmB, ep, M, N, K, stream);
