@@ -129,13 +129,48 @@ def cpu_step(sd, frames_np):
         return clip_tower.encode_image(sd, batch).numpy()
 
 
-def time_cpu(sample: int, reps: int, warm: int):
+def usable_cores() -> int:
+    """Host cores this process may actually use: affinity mask capped by the cgroup CPU quota (os.cpu_count()
+    reports the whole machine inside a container and oversubscribing OpenMP threads stalls for minutes)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(p)
+    except Exception:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / p
+        except Exception:
+            pass
+    if quota:
+        n = min(n, max(1, int(quota + 0.5)))
+    return max(1, n)
+
+
+def time_cpu(reps: int, warm: int, budget_s: float = 20.0):
+    """Times the oracle port on a bounded sample: the sample size is chosen from a probe so that warm-up + reps stay
+    near `budget_s` seconds of CPU work.  -> (per-rep seconds, cores, sample)"""
     import torch
     from oracle import clip_tower
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     sd = clip_tower.synthetic_state_dict(0)
-    frames = synth_frames_host(sample, 1234).numpy()
+    frames = synth_frames_host(256, 1234).numpy()
+    cpu_step(sd, frames[:4])                                   # page in / thread pool start
+    t0 = time.perf_counter()
+    cpu_step(sd, frames[:16])
+    probe = max(time.perf_counter() - t0, 1e-3)
+    per_frame = probe / 16
+    sample = int(max(16, min(256, budget_s / max(reps + warm, 1) / per_frame)))
+    sample -= sample % 8
+    frames = frames[:sample]
     for _ in range(warm):
         cpu_step(sd, frames)
     ts = []
@@ -143,7 +178,7 @@ def time_cpu(sample: int, reps: int, warm: int):
         t0 = time.perf_counter()
         cpu_step(sd, frames)
         ts.append(time.perf_counter() - t0)
-    return ts, cores
+    return ts, cores, sample
 
 
 def cpu_model_name() -> str:
@@ -159,15 +194,15 @@ def cpu_model_name() -> str:
 def run_reference(args, rank: int) -> None:
     if rank != 0:
         return
-    sample = 256
-    ts, cores = time_cpu(sample, max(args.steps, 1), max(args.warmup, 1))
+    steps = min(max(args.steps, 1), 10)        # each step is a bounded sample; the whole arm stays within minutes
+    ts, cores, sample = time_cpu(steps, min(max(args.warmup, 1), 3), budget_s=30.0)
     total = sum(ts)
     value = sample * len(ts) / total
     desc = (f"{sample} of the 1000 frames per step; PIL transform + fp32 torch tower (oracle port of the "
             f"reference --cpu path), torch threads={cores}, {cpu_model_name()}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(ts), "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * total / len(ts),
+        "steps": len(ts), "warmup": min(max(args.warmup, 1), 3), "ms_per_step": 1e3 * total / len(ts),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": base_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
@@ -283,11 +318,11 @@ def run_engine(args, rank: int, world: int, local_rank: int) -> None:
         "roofline": roofline,
     }
     if rank == 0 and world == 1 and not args.no_cpu:
-        ts, cores = time_cpu(256, 3, 1)
-        v = 256 * len(ts) / sum(ts)
+        ts, cores, sample = time_cpu(3, 1, budget_s=20.0)
+        v = sample * len(ts) / sum(ts)
         line["cpu_baseline"] = {
             "value": v, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"256 of the 1000 frames x {len(ts)} reps (+1 warm-up); PIL transform + fp32 torch tower "
+            "sample": f"{sample} of the 1000 frames x {len(ts)} reps (+1 warm-up); PIL transform + fp32 torch tower "
                       f"(oracle port of the reference --cpu path), torch threads={cores}, {cpu_model_name()}",
             "median_s_per_rep": statistics.median(ts)}
     if rank == 0:

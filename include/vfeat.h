@@ -59,11 +59,11 @@ int vf_resize_geometry(int in_h, int in_w, int size, int to_smaller_edge, int* o
  * resized); dst: n x 3 x 224 x 224 fp32, bit-exact with torchvision's fp32 arithmetic. */
 int vf_clip_normalize_u8(const uint8_t* src, int n, int src_h, int src_w, float* dst, void* stream);
 
-/* ---- tensor-core GEMM (exported for the parity tests): D = act(A . B^T * scale + bias) + residual
+/* ---- tensor-core GEMM (exported for the parity tests): D = act(A . B^T * scale + bias)
  * A: M x K fp16 (row pitch lda elements), B: N x K fp16 (torch Linear weight layout),
- * D: fp16 or fp32 (out_f32), bias/scale: fp32 [N] or NULL, residual: fp32 M x ldr or NULL. */
+ * D: fp16 or fp32 (out_f32, row pitch ldd elements, 16-byte aligned rows), bias/scale: fp32 [N] or NULL. */
 int vf_gemm_f16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, void* D, int ldd, int out_f32,
-                const float* bias, const float* scale, const float* residual, int ldr, int act, void* stream);
+                const float* bias, const float* scale, int act, void* stream);
 
 /* ---- CLIP ViT-B/32 image tower: replaces `clip.load(...)` + `model.encode_image(frames)`
  * (models/CLIP/extract_clip.py:47,128).  Weight pointers are HOST fp32 arrays in openai layout. */

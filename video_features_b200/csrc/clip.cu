@@ -35,7 +35,7 @@ struct vf_clip {
     vf::ClipLayerDev layer[12];
     // workspace (per chunk)
     __half *patches = nullptr, *h = nullptr, *qkv = nullptr, *att = nullptr, *mlp = nullptr, *cls = nullptr;
-    float* x = nullptr;
+    float *x = nullptr, *y = nullptr, *emb = nullptr;   // residual stream, GEMM fp32 output, patch embeddings
     // transform scratch (grown on demand)
     uint8_t *stage_u8 = nullptr, *resized = nullptr, *resize_tmp = nullptr;
     size_t stage_cap = 0, resized_cap = 0, tmp_cap = 0;
@@ -120,39 +120,31 @@ static int tower_gemm(vf_clip* h, const __half* A, int lda, const __half* B, int
     return VF_OK;
 }
 
-// the tower on one chunk whose patch matrix is already in h->patches; writes c x 512 fp32 to out
+// The tower on one chunk whose patch matrix is already in h->patches; writes c x 512 fp32 to out.
+// The residual stream x stays fp32; every "x += GEMM output" is fused into the LayerNorm kernel that follows it,
+// so GEMM epilogues are write-only (bias / QuickGELU) and stream out through TMA stores.
 static int clip_tower_chunk(vf_clip* h, int c, float* out, cudaStream_t s) {
     const int M = c * T;
-    // patch embedding: [c*49, 3072] x [768, 3072]^T, rows scattered to token slots 1..49, + positional embedding
-    {
-        GemmEpi e = epi(h->x, W, 1, nullptr, VF_ACT_NONE);
-        e.addend = h->pos; e.gin = P; e.gout = T; e.goff = 1;
-        VF_TRY(tower_gemm(h, h->patches, PK, h->w_patch, PK, c * P, W, PK, e, s));
-    }
-    // ln_pre in place; CLS rows are sourced from class_embedding + pos[0]
-    VF_TRY(launch_layernorm(h->x, W, h->cls_pos0, T, h->lnpre_w, h->lnpre_b, h->x, W, 1, M, W, s));
+    // patch embedding: [c*49, 3072] x [768, 3072]^T -> emb (fp32)
+    VF_TRY(tower_gemm(h, h->patches, PK, h->w_patch, PK, c * P, W, PK, epi(h->emb, W, 1, nullptr, VF_ACT_NONE), s));
+    // token assembly (+ class / positional embedding) fused with ln_pre -> x
+    VF_TRY(launch_embed_layernorm(h->emb, h->pos, h->cls_pos0, h->lnpre_w, h->lnpre_b, h->x, c, s));
     h->launches += 2;
     for (int l = 0; l < L; ++l) {
         const ClipLayerDev& w = h->layer[l];
-        VF_TRY(launch_layernorm(h->x, W, nullptr, 0, w.ln1_w, w.ln1_b, h->h, W, 0, M, W, s));
+        // x += y of the previous block's MLP (none for block 0); h = ln_1(x)
+        VF_TRY(launch_add_layernorm(h->x, l == 0 ? nullptr : h->y, W, 1, w.ln1_w, w.ln1_b, h->h, W, 0, M, s));
         VF_TRY(tower_gemm(h, h->h, W, w.w_qkv, W, M, 3 * W, W, epi(h->qkv, 3 * W, 0, w.b_qkv, VF_ACT_NONE), s));
         VF_TRY(launch_attention(h->qkv, h->att, c, T, H, s));
-        {
-            GemmEpi e = epi(h->x, W, 1, w.b_o, VF_ACT_NONE);
-            e.residual = h->x; e.ldr = W;
-            VF_TRY(tower_gemm(h, h->att, W, w.w_o, W, M, W, W, e, s));
-        }
-        VF_TRY(launch_layernorm(h->x, W, nullptr, 0, w.ln2_w, w.ln2_b, h->h, W, 0, M, W, s));
+        VF_TRY(tower_gemm(h, h->att, W, w.w_o, W, M, W, W, epi(h->y, W, 1, w.b_o, VF_ACT_NONE), s));
+        // x += attention output; h = ln_2(x)
+        VF_TRY(launch_add_layernorm(h->x, h->y, W, 1, w.ln2_w, w.ln2_b, h->h, W, 0, M, s));
         VF_TRY(tower_gemm(h, h->h, W, w.w_fc, W, M, MLPW, W, epi(h->mlp, MLPW, 0, w.b_fc, VF_ACT_QUICKGELU), s));
-        {
-            GemmEpi e = epi(h->x, W, 1, w.b_proj, VF_ACT_NONE);
-            e.residual = h->x; e.ldr = W;
-            VF_TRY(tower_gemm(h, h->mlp, MLPW, w.w_proj, MLPW, M, W, MLPW, e, s));
-        }
+        VF_TRY(tower_gemm(h, h->mlp, MLPW, w.w_proj, MLPW, M, W, MLPW, epi(h->y, W, 1, w.b_proj, VF_ACT_NONE), s));
         h->launches += 7;
     }
-    // ln_post on the CLS rows, then the 768 -> 512 projection
-    VF_TRY(launch_layernorm(h->x, int64_t(T) * W, nullptr, 0, h->lnpost_w, h->lnpost_b, h->cls, W, 0, c, W, s));
+    // CLS rows only: x += y of the last MLP; ln_post; then the 768 -> 512 projection
+    VF_TRY(launch_add_layernorm(h->x, h->y, int64_t(T) * W, 0, h->lnpost_w, h->lnpost_b, h->cls, W, 0, c, s));
     VF_TRY(tower_gemm(h, h->cls, W, h->w_proj, W, c, E, W, epi(out, E, 1, nullptr, VF_ACT_NONE), s));
     h->launches += 2;
     return VF_OK;
@@ -240,6 +232,8 @@ int vf_clip_create(vf_clip_t** out, const vf_clip_weights* w, int device, int ch
         const size_t C = size_t(chunk_frames);
         VF_TRY(dev_alloc(h, &h->patches, C * P * PK));
         VF_TRY(dev_alloc(h, &h->x, C * T * W));
+        VF_TRY(dev_alloc(h, &h->y, C * T * W));
+        VF_TRY(dev_alloc(h, &h->emb, C * P * W));
         VF_TRY(dev_alloc(h, &h->h, C * T * W));
         VF_TRY(dev_alloc(h, &h->qkv, C * T * 3 * W));
         VF_TRY(dev_alloc(h, &h->att, C * T * W));

@@ -68,6 +68,28 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* t
         : "memory");
 }
 
+// TMA store (shared -> global, bulk async group) and its bookkeeping
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(tm)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {   // <= N groups still reading their shared-memory source
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait() {        // <= N groups not yet complete
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// make generic-proxy shared-memory writes visible to the async proxy (TMA) before it reads them
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
@@ -153,6 +175,10 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta) 
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(smem_u32(bar), cta))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t cta) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(smem_u32(bar), cta))
                  : "memory");
 }
 // TMA load issued by either CTA of a pair; the transaction bytes are credited to the barrier `bar_cluster_addr`

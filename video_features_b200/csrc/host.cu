@@ -231,12 +231,11 @@ int vf_clip_normalize_u8(const uint8_t* src, int n, int src_h, int src_w, float*
 }
 
 int vf_gemm_f16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, void* D, int ldd, int out_f32,
-                const float* bias, const float* scale, const float* residual, int ldr, int act, void* stream) {
+                const float* bias, const float* scale, int act, void* stream) {
     if (!A || !B || !D) return fail(VF_ERR_INVALID, "gemm: null buffer");
     GemmEpi ep;
     memset(&ep, 0, sizeof(ep));
-    ep.out = D; ep.ldo = ldd; ep.out_f32 = out_f32; ep.bias = bias; ep.scale = scale;
-    ep.residual = residual; ep.ldr = ldr; ep.act = act;
+    ep.out = D; ep.ldo = ldd; ep.out_f32 = out_f32; ep.bias = bias; ep.scale = scale; ep.act = act;
     return gemm_f16(static_cast<const __half*>(A), lda, static_cast<const __half*>(B), ldb, M, N, K, ep,
                     static_cast<cudaStream_t>(stream));
 }

@@ -28,21 +28,19 @@ int fail(int code, const char* fmt, ...);
         if (_s != VF_OK) return _s;   \
     } while (0)
 
-// ---- tensor maps (driver entry point fetched at run time; the library does not link libcuda)
-int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes,
-                     uint32_t box_rows, uint32_t box_cols);
+// ---- tensor maps (driver entry point fetched at run time; the library does not link libcuda).
+// 2-D row-major tensor of 2- or 4-byte elements, 128-byte-swizzled boxes of box_rows x (128 / elem_bytes) columns.
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols,
+                 uint64_t row_pitch_bytes, uint32_t box_rows, uint32_t box_cols);
 
-// ---- GEMM: D[M,N] = epilogue(A[M,K] . B[N,K]^T), fp16 operands, fp32 accumulate (tcgen05)
+// ---- GEMM: D[M,N] = act(A[M,K] . B[N,K]^T * scale[n] + bias[n]), fp16 operands, fp32 accumulate (tcgen05)
 struct GemmEpi {
-    void* out;              // fp16 or fp32, row pitch ldo elements
-    const float* bias;      // [N] or null          v = acc * scale[n] + bias[n]
+    void* out;              // fp16 or fp32, row pitch ldo elements, 16-byte aligned rows
+    const float* bias;      // [N] or null
     const float* scale;     // [N] or null
-    const float* residual;  // fp32 [rows, ldr] or null, indexed by the OUTPUT row; added after activation
-    const float* addend;    // fp32 [gout, N] or null: added per (output row within group, n) -- positional embedding
-    int ldo, ldr;
+    int ldo;
     int out_f32;            // 0: fp16 out, 1: fp32 out
     int act;                // VF_ACT_*
-    int gin, gout, goff;    // row remap: out_row = (m / gin) * gout + goff + m % gin   (gin == 0: identity)
 };
 int gemm_f16(const __half* A, int lda, const __half* B, int ldb, int M, int N, int K, const GemmEpi& ep,
              cudaStream_t stream);
@@ -54,9 +52,12 @@ int launch_clip_patchify(const uint8_t* src, int n, int src_h, int src_w, int cr
 int launch_clip_patchify_f32(const float* src_chw, int n, __half* patches, cudaStream_t s);
 int launch_clip_normalize_f32(const uint8_t* src, int n, int src_h, int src_w, int crop_y, int crop_x, float* dst_chw,
                               cudaStream_t s);
-int launch_layernorm(const float* x, int64_t x_row_stride, const float* cls_row, int cls_period, const float* gamma,
-                     const float* beta, void* out, int64_t out_row_stride, int out_f32, int rows, int width,
-                     cudaStream_t s);
+// x (+= y) ; out = LayerNorm(x) -- rows of 768 fp32.  y may be null; write_x stores the summed residual stream back.
+int launch_add_layernorm(float* x, const float* y, int64_t xy_row_stride, int write_x, const float* gamma,
+                         const float* beta, void* out, int64_t out_row_stride, int out_f32, int rows, cudaStream_t s);
+// ViT embedding rows: token 0 = cls_pos0, token t>0 = emb[frame*49 + t-1] + pos[t]; x = ln_pre(row) (fp32)
+int launch_embed_layernorm(const float* emb, const float* pos, const float* cls_pos0, const float* gamma,
+                           const float* beta, float* x, int n_frames, cudaStream_t s);
 int launch_attention(const __half* qkv, __half* out, int n_frames, int tokens, int heads, cudaStream_t s);
 int launch_resample(const uint8_t* src, int n, int in_h, int in_w, uint8_t* tmp, uint8_t* dst, int out_h, int out_w,
                     const int* kh_bounds, const int* kh_coef, int kh_size, const int* kv_bounds, const int* kv_coef,

@@ -92,29 +92,21 @@ __global__ void clip_normalize_f32_kernel(const uint8_t* __restrict__ src, int n
     }
 }
 
-// LayerNorm over rows of 768 fp32 (eps 1e-5, biased variance), one warp per row, two-pass in registers.
-// Rows with (row % cls_period == 0) read `cls_row` instead of x (the CLS token = class_embedding + pos[0]).
-__global__ void layernorm768_kernel(const float* __restrict__ x, int64_t x_row_stride,
-                                    const float* __restrict__ cls_row, int cls_period,
-                                    const float* __restrict__ gamma, const float* __restrict__ beta, void* out,
-                                    int64_t out_row_stride, int out_f32, int rows) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (row >= rows) return;
-    const float* src = x + int64_t(row) * x_row_stride;
-    if (cls_row != nullptr && (row % cls_period) == 0) src = cls_row;
+// LayerNorm over rows of 768 fp32 (eps 1e-5, biased variance): one warp per row, the row lives in registers
+// (6 float4 per lane), mean and variance by warp shuffles (two-pass, no E[x^2]-E[x]^2 cancellation).
+struct Row768 {
     float4 v[6];
+};
+__device__ __forceinline__ void ln768_write(const Row768& r, int lane, const float* __restrict__ gamma,
+                                            const float* __restrict__ beta, void* out_row, int out_f32) {
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        v[i] = *reinterpret_cast<const float4*>(src + (lane + 32 * i) * 4);
-        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
+    for (int i = 0; i < 6; ++i) s += (r.v[i].x + r.v[i].y) + (r.v[i].z + r.v[i].w);
     const float mean = warp_sum(s) * (1.0f / 768.0f);
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        const float a = r.v[i].x - mean, b = r.v[i].y - mean, c = r.v[i].z - mean, d = r.v[i].w - mean;
         q += (a * a + b * b) + (c * c + d * d);
     }
     const float rstd = rsqrtf(warp_sum(q) * (1.0f / 768.0f) + 1e-5f);
@@ -124,17 +116,68 @@ __global__ void layernorm768_kernel(const float* __restrict__ x, int64_t x_row_s
         const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col));
         const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + col));
         float4 y;
-        y.x = (v[i].x - mean) * rstd * g.x + bb.x;
-        y.y = (v[i].y - mean) * rstd * g.y + bb.y;
-        y.z = (v[i].z - mean) * rstd * g.z + bb.z;
-        y.w = (v[i].w - mean) * rstd * g.w + bb.w;
-        if (out_f32) {
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + int64_t(row) * out_row_stride + col) = y;
-        } else {
-            *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + int64_t(row) * out_row_stride + col) =
-                make_uint2(pack_half2(y.x, y.y), pack_half2(y.z, y.w));
+        y.x = (r.v[i].x - mean) * rstd * g.x + bb.x;
+        y.y = (r.v[i].y - mean) * rstd * g.y + bb.y;
+        y.z = (r.v[i].z - mean) * rstd * g.z + bb.z;
+        y.w = (r.v[i].w - mean) * rstd * g.w + bb.w;
+        if (out_f32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_row) + col) = y;
+        else *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out_row) + col) =
+                 make_uint2(pack_half2(y.x, y.y), pack_half2(y.z, y.w));
+    }
+}
+
+// residual-stream update fused with the following LayerNorm:  x += y (the previous GEMM's fp32 output), out = LN(x)
+__global__ void add_layernorm768_kernel(float* __restrict__ x, const float* __restrict__ y, int64_t row_stride,
+                                        int write_x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                        void* out, int64_t out_row_stride, int out_f32, int rows) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (row >= rows) return;
+    float* xr = x + int64_t(row) * row_stride;
+    Row768 r;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) r.v[i] = *reinterpret_cast<const float4*>(xr + (lane + 32 * i) * 4);
+    if (y != nullptr) {
+        const float* yr = y + int64_t(row) * row_stride;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(yr + (lane + 32 * i) * 4));
+            r.v[i].x += t.x; r.v[i].y += t.y; r.v[i].z += t.z; r.v[i].w += t.w;
+        }
+        if (write_x) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) *reinterpret_cast<float4*>(xr + (lane + 32 * i) * 4) = r.v[i];
         }
     }
+    void* orow = out_f32 ? static_cast<void*>(reinterpret_cast<float*>(out) + int64_t(row) * out_row_stride)
+                         : static_cast<void*>(reinterpret_cast<__half*>(out) + int64_t(row) * out_row_stride);
+    ln768_write(r, lane, gamma, beta, orow, out_f32);
+}
+
+// ViT token assembly fused with ln_pre: row (frame, t): t == 0 -> class_embedding + pos[0] (precomputed),
+// t > 0 -> patch embedding row (frame*49 + t-1) + pos[t];  x = ln_pre(row) in fp32.
+__global__ void embed_layernorm768_kernel(const float* __restrict__ emb, const float* __restrict__ pos,
+                                          const float* __restrict__ cls_pos0, const float* __restrict__ gamma,
+                                          const float* __restrict__ beta, float* __restrict__ x, int rows) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (row >= rows) return;
+    const int frame = row / 50, t = row - frame * 50;
+    Row768 r;
+    if (t == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) r.v[i] = __ldg(reinterpret_cast<const float4*>(cls_pos0 + (lane + 32 * i) * 4));
+    } else {
+        const float* er = emb + (int64_t(frame) * 49 + (t - 1)) * 768;
+        const float* pr = pos + t * 768;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(er + (lane + 32 * i) * 4));
+            const float4 p = __ldg(reinterpret_cast<const float4*>(pr + (lane + 32 * i) * 4));
+            r.v[i] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+        }
+    }
+    ln768_write(r, lane, gamma, beta, x + int64_t(row) * 768, 1);
 }
 
 // Self-attention for one (frame, head): S = 50 tokens, head_dim 64, no mask.  q is scaled by 1/8 after the
@@ -345,13 +388,18 @@ int launch_clip_normalize_f32(const uint8_t* src, int n, int src_h, int src_w, i
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
-int launch_layernorm(const float* x, int64_t x_row_stride, const float* cls_row, int cls_period, const float* gamma,
-                     const float* beta, void* out, int64_t out_row_stride, int out_f32, int rows, int width,
-                     cudaStream_t s) {
-    if (width != 768) return fail(VF_ERR_UNSUPPORTED, "layernorm: width %d (only 768 is built)", width);
+int launch_add_layernorm(float* x, const float* y, int64_t xy_row_stride, int write_x, const float* gamma,
+                         const float* beta, void* out, int64_t out_row_stride, int out_f32, int rows, cudaStream_t s) {
     const int warps = 8;
-    layernorm768_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, s>>>(x, x_row_stride, cls_row, cls_period, gamma,
-                                                                         beta, out, out_row_stride, out_f32, rows);
+    add_layernorm768_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, s>>>(x, y, xy_row_stride, write_x, gamma, beta,
+                                                                             out, out_row_stride, out_f32, rows);
+    VF_CUDA(cudaGetLastError());
+    return VF_OK;
+}
+int launch_embed_layernorm(const float* emb, const float* pos, const float* cls_pos0, const float* gamma,
+                           const float* beta, float* x, int n_frames, cudaStream_t s) {
+    const int warps = 8, rows = n_frames * 50;
+    embed_layernorm768_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, s>>>(emb, pos, cls_pos0, gamma, beta, x, rows);
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }

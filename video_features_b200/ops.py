@@ -34,21 +34,21 @@ def _need_cuda(*ts: torch.Tensor) -> None:
 # ----------------------------------------------------------------------------- GEMM
 @torch.library.custom_op("vfeat::gemm_f16", mutates_args=())
 def gemm_f16(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor], scale: Optional[torch.Tensor],
-             residual: Optional[torch.Tensor], act: int, out_f32: bool) -> torch.Tensor:
-    """act(a @ b.T * scale + bias) + residual; a (M,K) fp16, b (N,K) fp16; fp32 accumulate on tcgen05."""
-    _need_cuda(a, b, bias, scale, residual)
+             act: int, out_f32: bool) -> torch.Tensor:
+    """act(a @ b.T * scale + bias); a (M,K) fp16, b (N,K) fp16; fp32 accumulate on tcgen05."""
+    _need_cuda(a, b, bias, scale)
     assert a.dtype == torch.float16 and b.dtype == torch.float16 and a.shape[1] == b.shape[1]
     M, K = a.shape
     N = b.shape[0]
     out = torch.empty((M, N), device=a.device, dtype=torch.float32 if out_f32 else torch.float16)
     with torch.cuda.device(a.device):
         check(lib().vf_gemm_f16(a.data_ptr(), K, b.data_ptr(), K, M, N, K, out.data_ptr(), N, int(out_f32),
-                                _ptr(bias), _ptr(scale), _ptr(residual), N, act, _stream()))
+                                _ptr(bias), _ptr(scale), act, _stream()))
     return out
 
 
 @gemm_f16.register_fake
-def _(a, b, bias, scale, residual, act, out_f32):
+def _(a, b, bias, scale, act, out_f32):
     return a.new_empty((a.shape[0], b.shape[0]), dtype=torch.float32 if out_f32 else torch.float16)
 
 
