@@ -6,7 +6,7 @@ from oracle import clip_tower
 from video_features_b200.clip_engine import ClipEngine
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
-chunks = [int(c) for c in sys.argv[2].split(",")] if len(sys.argv) > 2 else [120]
+chunks = [int(c) for c in sys.argv[2].split(",")] if len(sys.argv) > 2 else [256]
 sd = clip_tower.synthetic_state_dict(0)
 frames = torch.randint(0, 256, (n, 224, 224, 3), dtype=torch.uint8, device="cuda")
 for chunk in chunks:

@@ -5,8 +5,10 @@
 // Numerics: GEMM operands fp16, accumulation fp32 (TMEM), residual stream / LayerNorm / softmax fp32.
 // Frames are packed along M (row = frame*50 + token), processed in chunks sized so that one chunk's
 // activations stay L2-resident between kernels.
+#include <stdlib.h>
 #include <string.h>
 
+#include <map>
 #include <vector>
 
 #include "internal.h"
@@ -46,6 +48,15 @@ struct vf_clip {
     std::vector<cudaEvent_t> prof_events;   // pairs
     size_t prof_used = 0;
     double prof_flops = 0.0;
+    // All work of a call runs on the engine's own compute stream `cs` (ordered against the caller's stream with a
+    // pair of events), so that the per-chunk tower can be captured once into a CUDA graph and replayed: ~90 kernel
+    // launches and ~150 tensor-map encodes per chunk collapse into one cudaGraphLaunch (the legacy NULL stream, which
+    // is what torch hands over by default, cannot be captured).
+    cudaStream_t cs = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    bool use_graph = true;
+    std::map<int, cudaGraphExec_t> graphs;   // frames in chunk -> instantiated tower graph (writes h->feat)
+    float* feat = nullptr;                    // [chunk, 512] tower output of the current chunk
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
 };
@@ -123,7 +134,7 @@ static int tower_gemm(vf_clip* h, const __half* A, int lda, const __half* B, int
 // The tower on one chunk whose patch matrix is already in h->patches; writes c x 512 fp32 to out.
 // The residual stream x stays fp32; every "x += GEMM output" is fused into the LayerNorm kernel that follows it,
 // so GEMM epilogues are write-only (bias / QuickGELU) and stream out through TMA stores.
-static int clip_tower_chunk(vf_clip* h, int c, float* out, cudaStream_t s) {
+static int clip_tower_eager(vf_clip* h, int c, float* out, cudaStream_t s) {
     const int M = c * T;
     // patch embedding: [c*49, 3072] x [768, 3072]^T -> emb (fp32)
     VF_TRY(tower_gemm(h, h->patches, PK, h->w_patch, PK, c * P, W, PK, epi(h->emb, W, 1, nullptr, VF_ACT_NONE), s));
@@ -147,6 +158,53 @@ static int clip_tower_chunk(vf_clip* h, int c, float* out, cudaStream_t s) {
     VF_TRY(launch_add_layernorm(h->x, h->y, int64_t(T) * W, 0, h->lnpost_w, h->lnpost_b, h->cls, W, 0, c, s));
     VF_TRY(tower_gemm(h, h->cls, W, h->w_proj, W, c, E, W, epi(out, E, 1, nullptr, VF_ACT_NONE), s));
     h->launches += 2;
+    return VF_OK;
+}
+
+constexpr int TOWER_LAUNCHES = 2 + 7 * L + 2;
+
+// Tower on one chunk: replay (capturing on first use) the CUDA graph for this chunk size, then copy the features out.
+static int clip_tower_chunk(vf_clip* h, int c, float* out, cudaStream_t s) {
+    if (!h->use_graph || h->prof) return clip_tower_eager(h, c, out, s);
+    auto it = h->graphs.find(c);
+    if (it == h->graphs.end()) {
+        const int64_t before = h->launches;
+        cudaGraph_t graph = nullptr;
+        VF_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+        const int st = clip_tower_eager(h, c, h->feat, s);
+        const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        h->launches = before;
+        if (st != VF_OK) { if (graph) cudaGraphDestroy(graph); return st; }
+        if (ce != cudaSuccess) return fail(VF_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) return fail(VF_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie));
+        it = h->graphs.emplace(c, exec).first;
+    }
+    VF_CUDA(cudaGraphLaunch(it->second, s));
+    VF_CUDA(cudaMemcpyAsync(out, h->feat, size_t(c) * E * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    h->launches += TOWER_LAUNCHES;
+    return VF_OK;
+}
+
+// frames per chunk for a batch of n: as few chunks as the workspace allows, all (nearly) the same size, so no
+// ragged tail chunk runs the 12-layer launch sequence on a handful of rows
+static int balanced_chunk(const vf_clip* h, int n) {
+    const int nchunks = (n + h->chunk - 1) / h->chunk;
+    return nchunks > 0 ? (n + nchunks - 1) / nchunks : h->chunk;
+}
+
+// order the engine stream after the caller's stream (enter) and the caller's stream after the engine's (leave)
+static int enter(vf_clip* h, cudaStream_t user) {
+    VF_CUDA(cudaSetDevice(h->device));
+    VF_CUDA(cudaEventRecord(h->ev_in, user));
+    VF_CUDA(cudaStreamWaitEvent(h->cs, h->ev_in, 0));
+    return VF_OK;
+}
+static int leave(vf_clip* h, cudaStream_t user) {
+    VF_CUDA(cudaEventRecord(h->ev_out, h->cs));
+    VF_CUDA(cudaStreamWaitEvent(user, h->ev_out, 0));
     return VF_OK;
 }
 
@@ -187,7 +245,7 @@ extern "C" {
 int vf_clip_create(vf_clip_t** out, const vf_clip_weights* w, int device, int chunk_frames) {
     if (!out || !w) return fail(VF_ERR_INVALID, "clip_create: null argument");
     *out = nullptr;
-    if (chunk_frames <= 0) chunk_frames = 240;   // 12000 rows per GEMM; activations of a chunk stay L2-resident
+    if (chunk_frames <= 0) chunk_frames = 256;   // up to 12800 token rows per GEMM launch
     if (chunk_frames > 4096) return fail(VF_ERR_INVALID, "clip_create: chunk_frames %d too large", chunk_frames);
     VF_CUDA(cudaSetDevice(device));
     int major = 0, minor = 0;
@@ -239,6 +297,14 @@ int vf_clip_create(vf_clip_t** out, const vf_clip_weights* w, int device, int ch
         VF_TRY(dev_alloc(h, &h->att, C * T * W));
         VF_TRY(dev_alloc(h, &h->mlp, C * T * MLPW));
         VF_TRY(dev_alloc(h, &h->cls, C * W));
+        VF_TRY(dev_alloc(h, &h->feat, C * E));
+        VF_CUDA(cudaStreamCreateWithFlags(&h->cs, cudaStreamNonBlocking));
+        VF_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+        VF_CUDA(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+        {
+            const char* e = getenv("VF_NO_GRAPH");
+            h->use_graph = !(e && e[0] == '1');
+        }
         VF_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
             VF_CUDA(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
@@ -262,6 +328,10 @@ int vf_clip_destroy(vf_clip_t* h) {
     if (h->resize_tmp) cudaFree(h->resize_tmp);
     if (h->out_dev) cudaFree(h->out_dev);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+    if (h->cs) cudaStreamDestroy(h->cs);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->ev_out) cudaEventDestroy(h->ev_out);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
@@ -273,37 +343,44 @@ int vf_clip_destroy(vf_clip_t* h) {
 
 int vf_clip_encode_f32(vf_clip_t* h, const float* frames, int n, float* out, void* stream) {
     if (!h || (n > 0 && (!frames || !out))) return fail(VF_ERR_INVALID, "clip_encode_f32: null argument");
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    for (int b0 = 0; b0 < n; b0 += h->chunk) {
-        const int c = (n - b0 < h->chunk) ? (n - b0) : h->chunk;
+    if (n <= 0) return VF_OK;
+    cudaStream_t user = static_cast<cudaStream_t>(stream), s = h->cs;
+    VF_TRY(enter(h, user));
+    const int step = balanced_chunk(h, n);
+    for (int b0 = 0; b0 < n; b0 += step) {
+        const int c = (n - b0 < step) ? (n - b0) : step;
         VF_TRY(launch_clip_patchify_f32(frames + size_t(b0) * 3 * 224 * 224, c, h->patches, s));
         h->launches += 1;
         VF_TRY(clip_tower_chunk(h, c, out + size_t(b0) * E, s));
     }
-    return VF_OK;
+    return leave(h, user);
 }
 
 int vf_clip_encode_u8(vf_clip_t* h, const uint8_t* frames, int n, int src_h, int src_w, float* out, void* stream) {
     if (!h || (n > 0 && (!frames || !out))) return fail(VF_ERR_INVALID, "clip_encode_u8: null argument");
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (n <= 0) return VF_OK;
+    cudaStream_t user = static_cast<cudaStream_t>(stream), s = h->cs;
     ClipGeom g;
     VF_TRY(clip_geometry(src_h, src_w, &g));
+    VF_TRY(enter(h, user));
     const size_t fbytes = size_t(src_h) * src_w * 3;
-    for (int b0 = 0; b0 < n; b0 += h->chunk) {
-        const int c = (n - b0 < h->chunk) ? (n - b0) : h->chunk;
+    const int step = balanced_chunk(h, n);
+    for (int b0 = 0; b0 < n; b0 += step) {
+        const int c = (n - b0 < step) ? (n - b0) : step;
         VF_TRY(clip_transform_chunk(h, frames + size_t(b0) * fbytes, c, src_h, src_w, g, s));
         VF_TRY(clip_tower_chunk(h, c, out + size_t(b0) * E, s));
     }
-    return VF_OK;
+    return leave(h, user);
 }
 
 int vf_clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, int src_h, int src_w, float* out_host,
                            void* stream) {
     if (!h || (n > 0 && (!frames_host || !out_host))) return fail(VF_ERR_INVALID, "clip_encode_u8_host: null argument");
     if (n <= 0) return VF_OK;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaStream_t user = static_cast<cudaStream_t>(stream), s = h->cs;
     ClipGeom g;
     VF_TRY(clip_geometry(src_h, src_w, &g));
+    VF_TRY(enter(h, user));
     const size_t fbytes = size_t(src_h) * src_w * 3;
     // two staging slots: the H2D copy of chunk i+1 (copy stream) overlaps the tower on chunk i (compute stream)
     VF_TRY(grow(&h->stage_u8, &h->stage_cap, 2 * size_t(h->chunk) * fbytes));
@@ -313,10 +390,12 @@ int vf_clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, int 
         VF_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->out_dev), size_t(n) * E * sizeof(float)));
         h->out_cap = size_t(n) * E * sizeof(float);
     }
-    const int nchunks = (n + h->chunk - 1) / h->chunk;
+    const int step = balanced_chunk(h, n);
+    const int nchunks = (n + step - 1) / step;
+    VF_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_in, 0));
     for (int i = 0; i < nchunks; ++i) {
-        const int b0 = i * h->chunk;
-        const int c = (n - b0 < h->chunk) ? (n - b0) : h->chunk;
+        const int b0 = i * step;
+        const int c = (n - b0 < step) ? (n - b0) : step;
         const int slot = i & 1;
         uint8_t* dst = h->stage_u8 + size_t(slot) * h->chunk * fbytes;
         if (i >= 2) VF_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));   // slot free again
@@ -329,6 +408,7 @@ int vf_clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, int 
         VF_TRY(clip_tower_chunk(h, c, h->out_dev + size_t(b0) * E, s));
     }
     VF_CUDA(cudaMemcpyAsync(out_host, h->out_dev, size_t(n) * E * sizeof(float), cudaMemcpyDeviceToHost, s));
+    VF_TRY(leave(h, user));
     VF_CUDA(cudaStreamSynchronize(s));
     return VF_OK;
 }
