@@ -288,6 +288,7 @@ def run_engine(args, rank: int, world: int, local_rank: int) -> None:
     for _ in range(pk):
         eng.encode_frames_u8(frames_dev)
     gemm_ms, gemm_launches, gemm_flops = eng.profile_read()
+    cats = {k: v / pk for k, v in eng.profile_categories().items()}
     eng.profile(False)
     peaks = load_peaks()
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
@@ -299,6 +300,7 @@ def run_engine(args, rank: int, world: int, local_rank: int) -> None:
         "launches_per_step": gemm_launches // pk, "avg_launch_us": 1e3 * gemm_ms / max(gemm_launches, 1),
         "algorithmic_flop_per_launch_avg": gemm_flops / max(gemm_launches, 1),
         "gemm_share_of_step": (gemm_ms / pk) / (ms_total / K),
+        "eager_ms_per_step_by_kernel": cats,
         "whole_step_tflops": value / world * FLOP_PER_FRAME / 1e12,
         "whole_step_frac": value / world * FLOP_PER_FRAME / 1e12 / peaks["tflops_sustained"],
     }

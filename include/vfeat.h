@@ -107,6 +107,9 @@ int64_t vf_clip_launch_count(const vf_clip_t* h);
  * summed GEMM device time (ms), the number of GEMM launches and their algorithmic FLOPs (2*M*N*K), and resets. */
 int vf_clip_profile(vf_clip_t* h, int enable);
 int vf_clip_profile_read(vf_clip_t* h, double* gemm_ms, int64_t* gemm_launches, double* gemm_flops);
+/* device ms per kernel category of the last vf_clip_profile_read window: [0] GEMM, [1] LayerNorm, [2] attention,
+ * [3] frame transform (resize / normalise / patchify). */
+int vf_clip_profile_categories(const vf_clip_t* h, double* ms4);
 
 #ifdef __cplusplus
 }

@@ -110,6 +110,12 @@ class ClipEngine:
         check(lib().vf_clip_profile_read(self._h, C.byref(ms), C.byref(n), C.byref(fl)))
         return ms.value, n.value, fl.value
 
+    def profile_categories(self):
+        """device ms of the last profile_read window: {gemm, layernorm, attention, transform}."""
+        ms = (C.c_double * 4)()
+        check(lib().vf_clip_profile_categories(self._h, ms))
+        return dict(zip(("gemm", "layernorm", "attention", "transform"), list(ms)))
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             lib().vf_clip_destroy(self._h)

@@ -37,7 +37,8 @@ struct vf_clip {
     vf::ClipLayerDev layer[12];
     // workspace (per chunk)
     __half *patches = nullptr, *h = nullptr, *qkv = nullptr, *att = nullptr, *mlp = nullptr, *cls = nullptr;
-    float *x = nullptr, *y = nullptr, *emb = nullptr;   // residual stream, GEMM fp32 output, patch embeddings
+    float *x = nullptr, *emb = nullptr;   // residual stream (fp32), patch embeddings (fp32)
+    __half* y = nullptr;                  // residual-branch increment written by out-proj / fc2 (fp16)
     // transform scratch (grown on demand)
     uint8_t *stage_u8 = nullptr, *resized = nullptr, *resize_tmp = nullptr;
     size_t stage_cap = 0, resized_cap = 0, tmp_cap = 0;
@@ -46,6 +47,8 @@ struct vf_clip {
     // roofline instrumentation (vf_clip_profile)
     bool prof = false;
     std::vector<cudaEvent_t> prof_events;   // pairs
+    std::vector<int> prof_cat;              // category of each pair: 0 gemm, 1 layernorm, 2 attention, 3 transform
+    double prof_cat_ms[4] = {0, 0, 0, 0};
     size_t prof_used = 0;
     double prof_flops = 0.0;
     // All work of a call runs on the engine's own compute stream `cs` (ordered against the caller's stream with a
@@ -111,24 +114,48 @@ static GemmEpi epi(void* out, int ldo, int out_f32, const float* bias, int act) 
     return e;
 }
 
-// GEMM launch of the tower; bracketed by events when profiling is on
+// event bracket around one launch when profiling is on (vf_clip_profile): category 0 gemm, 1 layernorm,
+// 2 attention, 3 transform
+struct ProfScope {
+    vf_clip* h; cudaStream_t s; bool on;
+    ProfScope(vf_clip* h_, int cat, cudaStream_t s_) : h(h_), s(s_), on(h_->prof) {
+        if (!on) return;
+        if (h->prof_used + 2 > h->prof_events.size()) {
+            for (int i = 0; i < 2; ++i) {
+                cudaEvent_t e;
+                if (cudaEventCreate(&e) != cudaSuccess) { on = false; return; }
+                h->prof_events.push_back(e);
+            }
+        }
+        cudaEventRecord(h->prof_events[h->prof_used], s);
+        h->prof_cat.resize(h->prof_used / 2 + 1);
+        h->prof_cat[h->prof_used / 2] = cat;
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(h->prof_events[h->prof_used + 1], s);
+        h->prof_used += 2;
+    }
+};
+
 static int tower_gemm(vf_clip* h, const __half* A, int lda, const __half* B, int ldb, int M, int N, int K,
                       const GemmEpi& ep, cudaStream_t s) {
-    if (!h->prof) return gemm_f16(A, lda, B, ldb, M, N, K, ep, s);
-    if (h->prof_used + 2 > h->prof_events.size()) {
-        for (int i = 0; i < 2; ++i) {
-            cudaEvent_t e;
-            VF_CUDA(cudaEventCreate(&e));
-            h->prof_events.push_back(e);
-        }
-    }
-    cudaEvent_t e0 = h->prof_events[h->prof_used], e1 = h->prof_events[h->prof_used + 1];
-    VF_CUDA(cudaEventRecord(e0, s));
-    VF_TRY(gemm_f16(A, lda, B, ldb, M, N, K, ep, s));
-    VF_CUDA(cudaEventRecord(e1, s));
-    h->prof_used += 2;
-    h->prof_flops += 2.0 * double(M) * double(N) * double(K);
-    return VF_OK;
+    ProfScope p(h, 0, s);
+    if (h->prof) h->prof_flops += 2.0 * double(M) * double(N) * double(K);
+    return gemm_f16(A, lda, B, ldb, M, N, K, ep, s);
+}
+static int tower_embed_ln(vf_clip* h, int c, cudaStream_t s) {
+    ProfScope p(h, 1, s);
+    return launch_embed_layernorm(h->emb, h->pos, h->cls_pos0, h->lnpre_w, h->lnpre_b, h->x, c, s);
+}
+static int tower_add_ln(vf_clip* h, float* x, const __half* y, int64_t stride, int write_x, const float* g,
+                        const float* b, void* out, int64_t ostride, int rows, cudaStream_t s) {
+    ProfScope p(h, 1, s);
+    return launch_add_layernorm(x, y, stride, write_x, g, b, out, ostride, 0, rows, s);
+}
+static int tower_attention(vf_clip* h, int c, cudaStream_t s) {
+    ProfScope p(h, 2, s);
+    return launch_attention(h->qkv, h->att, c, T, H, s);
 }
 
 // The tower on one chunk whose patch matrix is already in h->patches; writes c x 512 fp32 to out.
@@ -139,23 +166,23 @@ static int clip_tower_eager(vf_clip* h, int c, float* out, cudaStream_t s) {
     // patch embedding: [c*49, 3072] x [768, 3072]^T -> emb (fp32)
     VF_TRY(tower_gemm(h, h->patches, PK, h->w_patch, PK, c * P, W, PK, epi(h->emb, W, 1, nullptr, VF_ACT_NONE), s));
     // token assembly (+ class / positional embedding) fused with ln_pre -> x
-    VF_TRY(launch_embed_layernorm(h->emb, h->pos, h->cls_pos0, h->lnpre_w, h->lnpre_b, h->x, c, s));
+    VF_TRY(tower_embed_ln(h, c, s));
     h->launches += 2;
     for (int l = 0; l < L; ++l) {
         const ClipLayerDev& w = h->layer[l];
         // x += y of the previous block's MLP (none for block 0); h = ln_1(x)
-        VF_TRY(launch_add_layernorm(h->x, l == 0 ? nullptr : h->y, W, 1, w.ln1_w, w.ln1_b, h->h, W, 0, M, s));
+        VF_TRY(tower_add_ln(h, h->x, l == 0 ? nullptr : h->y, W, 1, w.ln1_w, w.ln1_b, h->h, W, M, s));
         VF_TRY(tower_gemm(h, h->h, W, w.w_qkv, W, M, 3 * W, W, epi(h->qkv, 3 * W, 0, w.b_qkv, VF_ACT_NONE), s));
-        VF_TRY(launch_attention(h->qkv, h->att, c, T, H, s));
-        VF_TRY(tower_gemm(h, h->att, W, w.w_o, W, M, W, W, epi(h->y, W, 1, w.b_o, VF_ACT_NONE), s));
+        VF_TRY(tower_attention(h, c, s));
+        VF_TRY(tower_gemm(h, h->att, W, w.w_o, W, M, W, W, epi(h->y, W, 0, w.b_o, VF_ACT_NONE), s));
         // x += attention output; h = ln_2(x)
-        VF_TRY(launch_add_layernorm(h->x, h->y, W, 1, w.ln2_w, w.ln2_b, h->h, W, 0, M, s));
+        VF_TRY(tower_add_ln(h, h->x, h->y, W, 1, w.ln2_w, w.ln2_b, h->h, W, M, s));
         VF_TRY(tower_gemm(h, h->h, W, w.w_fc, W, M, MLPW, W, epi(h->mlp, MLPW, 0, w.b_fc, VF_ACT_QUICKGELU), s));
-        VF_TRY(tower_gemm(h, h->mlp, MLPW, w.w_proj, MLPW, M, W, MLPW, epi(h->y, W, 1, w.b_proj, VF_ACT_NONE), s));
+        VF_TRY(tower_gemm(h, h->mlp, MLPW, w.w_proj, MLPW, M, W, MLPW, epi(h->y, W, 0, w.b_proj, VF_ACT_NONE), s));
         h->launches += 7;
     }
     // CLS rows only: x += y of the last MLP; ln_post; then the 768 -> 512 projection
-    VF_TRY(launch_add_layernorm(h->x, h->y, int64_t(T) * W, 0, h->lnpost_w, h->lnpost_b, h->cls, W, 0, c, s));
+    VF_TRY(tower_add_ln(h, h->x, h->y, int64_t(T) * W, 0, h->lnpost_w, h->lnpost_b, h->cls, W, c, s));
     VF_TRY(tower_gemm(h, h->cls, W, h->w_proj, W, c, E, W, epi(out, E, 1, nullptr, VF_ACT_NONE), s));
     h->launches += 2;
     return VF_OK;
@@ -222,6 +249,7 @@ static int clip_geometry(int src_h, int src_w, ClipGeom* g) {
 // device uint8 frames (c of them, original geometry) -> h->patches
 static int clip_transform_chunk(vf_clip* h, const uint8_t* frames, int c, int src_h, int src_w, const ClipGeom& g,
                                 cudaStream_t s) {
+    ProfScope p(h, 3, s);
     const uint8_t* cur = frames;
     int ch = src_h, cw = src_w;
     if (g.resize) {
@@ -425,17 +453,27 @@ int vf_clip_profile_read(vf_clip_t* h, double* gemm_ms, int64_t* gemm_launches, 
     if (!h) return fail(VF_ERR_INVALID, "clip_profile_read: null handle");
     VF_CUDA(cudaSetDevice(h->device));
     VF_CUDA(cudaDeviceSynchronize());
-    double ms = 0.0;
+    double ms[4] = {0, 0, 0, 0};
+    int64_t n_gemm = 0;
     for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
         float t = 0.f;
         VF_CUDA(cudaEventElapsedTime(&t, h->prof_events[i], h->prof_events[i + 1]));
-        ms += t;
+        const int cat = h->prof_cat[i / 2];
+        ms[cat] += t;
+        n_gemm += (cat == 0);
     }
-    if (gemm_ms) *gemm_ms = ms;
-    if (gemm_launches) *gemm_launches = int64_t(h->prof_used / 2);
+    for (int i = 0; i < 4; ++i) h->prof_cat_ms[i] = ms[i];
+    if (gemm_ms) *gemm_ms = ms[0];
+    if (gemm_launches) *gemm_launches = n_gemm;
     if (gemm_flops) *gemm_flops = h->prof_flops;
     h->prof_used = 0;
     h->prof_flops = 0.0;
+    return VF_OK;
+}
+
+int vf_clip_profile_categories(const vf_clip_t* h, double* ms4) {
+    if (!h || !ms4) return fail(VF_ERR_INVALID, "clip_profile_categories: null argument");
+    for (int i = 0; i < 4; ++i) ms4[i] = h->prof_cat_ms[i];
     return VF_OK;
 }
 

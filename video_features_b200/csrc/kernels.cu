@@ -126,8 +126,10 @@ __device__ __forceinline__ void ln768_write(const Row768& r, int lane, const flo
     }
 }
 
-// residual-stream update fused with the following LayerNorm:  x += y (the previous GEMM's fp32 output), out = LN(x)
-__global__ void add_layernorm768_kernel(float* __restrict__ x, const float* __restrict__ y, int64_t row_stride,
+// residual-stream update fused with the following LayerNorm:  x += y (the previous GEMM's output, fp16: it is a
+// small residual-branch increment, so its 2^-11 rounding is far below the fp16 operand rounding of the GEMMs; x
+// itself stays fp32), out = LN(x)
+__global__ void __launch_bounds__(256, 6) add_layernorm768_kernel(float* __restrict__ x, const __half* __restrict__ y, int64_t row_stride,
                                         int write_x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                         void* out, int64_t out_row_stride, int out_f32, int rows) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -138,11 +140,13 @@ __global__ void add_layernorm768_kernel(float* __restrict__ x, const float* __re
 #pragma unroll
     for (int i = 0; i < 6; ++i) r.v[i] = *reinterpret_cast<const float4*>(xr + (lane + 32 * i) * 4);
     if (y != nullptr) {
-        const float* yr = y + int64_t(row) * row_stride;
+        const __half* yr = y + int64_t(row) * row_stride;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(yr + (lane + 32 * i) * 4));
-            r.v[i].x += t.x; r.v[i].y += t.y; r.v[i].z += t.z; r.v[i].w += t.w;
+            const uint2 raw = __ldg(reinterpret_cast<const uint2*>(yr + (lane + 32 * i) * 4));
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+            r.v[i].x += a.x; r.v[i].y += a.y; r.v[i].z += b.x; r.v[i].w += b.y;
         }
         if (write_x) {
 #pragma unroll
@@ -156,7 +160,7 @@ __global__ void add_layernorm768_kernel(float* __restrict__ x, const float* __re
 
 // ViT token assembly fused with ln_pre: row (frame, t): t == 0 -> class_embedding + pos[0] (precomputed),
 // t > 0 -> patch embedding row (frame*49 + t-1) + pos[t];  x = ln_pre(row) in fp32.
-__global__ void embed_layernorm768_kernel(const float* __restrict__ emb, const float* __restrict__ pos,
+__global__ void __launch_bounds__(256, 6) embed_layernorm768_kernel(const float* __restrict__ emb, const float* __restrict__ pos,
                                           const float* __restrict__ cls_pos0, const float* __restrict__ gamma,
                                           const float* __restrict__ beta, float* __restrict__ x, int rows) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -184,9 +188,11 @@ __global__ void embed_layernorm768_kernel(const float* __restrict__ emb, const f
 // in-projection (torch nn.MultiheadAttention semantics; applied here to the fp32 scores, which is the same
 // arithmetic since 1/8 is a power of two).  The two contractions are 64x64x64 after padding -- far too small for a
 // tcgen05 tile, so they run on warp-level mma.sync (m16n8k16, fp16 in / fp32 accumulate): one block of 4 warps
-// per (frame, head), warp w owns query rows 16w..16w+15; K and V^T are staged once in shared memory; the
-// softmax lives in the accumulator fragments (fp32) with quad shuffles for the row max / row sum.
-constexpr int ATT_S = 50, ATT_D = 64, ATT_LD = 72;   // 72-half row pitch: conflict-free fragment loads
+// per (frame, head), warp w owns query rows 16w..16w+15.  Q, K, V are staged once in shared memory with 16-byte
+// cp.async (row pitch 144 B: conflict-free ldmatrix), fragments come from ldmatrix (.trans for V), the softmax
+// lives in the accumulator fragments (fp32) with quad shuffles, and O goes back through shared memory so that the
+// global stores are full 128-byte rows.
+constexpr int ATT_S = 50, ATT_D = 64, ATT_LD = 72;
 
 __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
     asm volatile(
@@ -194,11 +200,23 @@ __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void ldsm_x4(uint32_t* r, const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t* r, const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
 
 __global__ void __launch_bounds__(128) attention50_kernel(const __half* __restrict__ qkv, __half* __restrict__ out,
                                                           int heads) {
+    __shared__ __align__(16) __half Qs[64][ATT_LD];   // [query][dim]; reused for O
     __shared__ __align__(16) __half Ks[64][ATT_LD];   // [key][dim]
-    __shared__ __align__(16) __half Vt[64][ATT_LD];   // [dim][key]
+    __shared__ __align__(16) __half Vs[64][ATT_LD];   // [key][dim]
     const int frame = blockIdx.x / heads, head = blockIdx.x % heads;
     const int width = heads * ATT_D;
     const int ld = 3 * width;
@@ -206,52 +224,40 @@ __global__ void __launch_bounds__(128) attention50_kernel(const __half* __restri
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
 
-    // stage K (row-major) and V (transposed); keys 50..63 are zero-filled
-    for (int i = tid; i < 64 * 8; i += 128) {
-        const int r = i >> 3, seg = i & 7;
-        uint4 kraw = make_uint4(0, 0, 0, 0), vraw = make_uint4(0, 0, 0, 0);
-        if (r < ATT_S) {
-            const __half* base = qkv + (row0 + r) * ld + head * ATT_D + seg * 8;
-            kraw = __ldg(reinterpret_cast<const uint4*>(base + width));
-            vraw = __ldg(reinterpret_cast<const uint4*>(base + 2 * width));
-        }
-        *reinterpret_cast<uint4*>(&Ks[r][seg * 8]) = kraw;
-        const __half* vh = reinterpret_cast<const __half*>(&vraw);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) Vt[seg * 8 + j][r] = vh[j];
+    // stage Q, K, V rows 0..49 (3 x 400 16-byte chunks); zero K/V rows 50..63 (0 * garbage must stay 0 in P.V)
+    for (int i = tid; i < 3 * ATT_S * 8; i += 128) {
+        const int m = i / (ATT_S * 8), rem = i - m * (ATT_S * 8);
+        const int r = rem >> 3, seg = rem & 7;
+        const __half* src = qkv + (row0 + r) * ld + m * width + head * ATT_D + seg * 8;
+        __half* dst = (m == 0 ? &Qs[r][seg * 8] : m == 1 ? &Ks[r][seg * 8] : &Vs[r][seg * 8]);
+        cp_async16(dst, src);
     }
-
-    // Q fragments straight from global (each element is used by exactly one warp)
-    const int q0 = warp * 16;
-    const int r_lo = q0 + g, r_hi = q0 + g + 8;
-    uint32_t aq[4][4];
-    {
-        const __half* qlo = qkv + (row0 + r_lo) * ld + head * ATT_D;
-        const __half* qhi = qkv + (row0 + r_hi) * ld + head * ATT_D;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            const int c = ks * 16 + 2 * t;
-            aq[ks][0] = r_lo < ATT_S ? __ldg(reinterpret_cast<const uint32_t*>(qlo + c)) : 0u;
-            aq[ks][1] = r_hi < ATT_S ? __ldg(reinterpret_cast<const uint32_t*>(qhi + c)) : 0u;
-            aq[ks][2] = r_lo < ATT_S ? __ldg(reinterpret_cast<const uint32_t*>(qlo + c + 8)) : 0u;
-            aq[ks][3] = r_hi < ATT_S ? __ldg(reinterpret_cast<const uint32_t*>(qhi + c + 8)) : 0u;
-        }
+    for (int i = tid; i < 2 * 14 * 8; i += 128) {
+        const int m = i / (14 * 8), rem = i - m * (14 * 8);
+        const int r = ATT_S + (rem >> 3), seg = rem & 7;
+        *reinterpret_cast<uint4*>(m == 0 ? &Ks[r][seg * 8] : &Vs[r][seg * 8]) = make_uint4(0, 0, 0, 0);
     }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
-    // S = Q K^T : 8 key tiles x 4 dim steps
+    const int q0 = warp * 16;
+    // S = Q K^T : A fragments of this warp's 16 query rows (4 dim steps), B fragments of K per key tile
+    uint32_t aq[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) ldsm_x4(aq[ks], &Qs[q0 + (lane & 15)][ks * 16 + (lane >> 4) * 8]);
     float s[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
         s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + g][ks * 16 + 2 * t]);
-            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + g][ks * 16 + 2 * t + 8]);
-            mma16816(s[nt], aq[ks], b0, b1);
+        for (int kp = 0; kp < 2; ++kp) {   // two dim steps per ldmatrix.x4
+            uint32_t bk[4];
+            ldsm_x4(bk, &Ks[nt * 8 + (lane & 7)][kp * 32 + (lane >> 3) * 8]);
+            mma16816(s[nt], aq[2 * kp], bk[0], bk[1]);
+            mma16816(s[nt], aq[2 * kp + 1], bk[2], bk[3]);
         }
     }
-    // softmax over the 50 valid keys; rows r_lo (regs 0,1) and r_hi (regs 2,3)
+    // softmax over the 50 valid keys; this thread holds rows q0+g (regs 0,1) and q0+g+8 (regs 2,3)
     const float sc = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
     float m_lo = -INFINITY, m_hi = -INFINITY;
 #pragma unroll
@@ -295,19 +301,30 @@ __global__ void __launch_bounds__(128) attention50_kernel(const __half* __restri
         pa[kk][2] = pack_half2(s[2 * kk + 1][0] * inv_lo, s[2 * kk + 1][1] * inv_lo);
         pa[kk][3] = pack_half2(s[2 * kk + 1][2] * inv_hi, s[2 * kk + 1][3] * inv_hi);
     }
-    __half* olo = out + (row0 + r_lo) * width + head * ATT_D;
-    __half* ohi = out + (row0 + r_hi) * width + head * ATT_D;
+    __syncwarp();   // every lane's ldmatrix reads of this warp's Q rows are done before they are overwritten with O
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-        float o[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int np = 0; np < 4; ++np) {        // two dim tiles per ldmatrix.x4.trans
+        float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Vt[nt * 8 + g][kk * 16 + 2 * t]);
-            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Vt[nt * 8 + g][kk * 16 + 2 * t + 8]);
-            mma16816(o, pa[kk], b0, b1);
+            uint32_t bv[4];
+            ldsm_x4_trans(bv, &Vs[kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][np * 16 + (lane >> 4) * 8]);
+            mma16816(o0, pa[kk], bv[0], bv[1]);
+            mma16816(o1, pa[kk], bv[2], bv[3]);
         }
-        if (r_lo < ATT_S) *reinterpret_cast<uint32_t*>(olo + nt * 8 + 2 * t) = pack_half2(o[0], o[1]);
-        if (r_hi < ATT_S) *reinterpret_cast<uint32_t*>(ohi + nt * 8 + 2 * t) = pack_half2(o[2], o[3]);
+        *reinterpret_cast<uint32_t*>(&Qs[q0 + g][np * 16 + 2 * t]) = pack_half2(o0[0], o0[1]);
+        *reinterpret_cast<uint32_t*>(&Qs[q0 + g + 8][np * 16 + 2 * t]) = pack_half2(o0[2], o0[3]);
+        *reinterpret_cast<uint32_t*>(&Qs[q0 + g][np * 16 + 8 + 2 * t]) = pack_half2(o1[0], o1[1]);
+        *reinterpret_cast<uint32_t*>(&Qs[q0 + g + 8][np * 16 + 8 + 2 * t]) = pack_half2(o1[2], o1[3]);
+    }
+    __syncwarp();
+    // this warp's 16 output rows, 128 B each, as 16-byte stores (8 lanes cover one row)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = q0 + i * 4 + (lane >> 3), seg = lane & 7;
+        if (r < ATT_S)
+            *reinterpret_cast<uint4*>(out + (row0 + r) * width + head * ATT_D + seg * 8) =
+                *reinterpret_cast<const uint4*>(&Qs[r][seg * 8]);
     }
 }
 
@@ -388,7 +405,7 @@ int launch_clip_normalize_f32(const uint8_t* src, int n, int src_h, int src_w, i
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
-int launch_add_layernorm(float* x, const float* y, int64_t xy_row_stride, int write_x, const float* gamma,
+int launch_add_layernorm(float* x, const __half* y, int64_t xy_row_stride, int write_x, const float* gamma,
                          const float* beta, void* out, int64_t out_row_stride, int out_f32, int rows, cudaStream_t s) {
     const int warps = 8;
     add_layernorm768_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, s>>>(x, y, xy_row_stride, write_x, gamma, beta,
