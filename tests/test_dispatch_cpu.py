@@ -1,0 +1,75 @@
+"""--device_ids dispatch: shard arithmetic and the feature all-gather, on a world_size-2 gloo group (CPU)."""
+import argparse
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _gather_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from video_features_b200.dispatch import gather_feature_blocks, shard_indices
+    n_videos = 5
+    idx = list(shard_indices(n_videos, world, rank))
+    # video v has v+1 rows, every element equals v
+    blocks = [torch.full((v + 1, 8), float(v)) for v in idx]
+    allb = gather_feature_blocks(blocks, 8, torch.device("cpu"))
+    q.put((rank, idx, [(b.shape[0], float(b[0, 0])) for b in allb]))
+    dist.destroy_process_group()
+
+
+def test_gather_feature_blocks_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    res.sort()
+    assert res[0][1] == [0, 1, 2] and res[1][1] == [3, 4]          # torch.chunk(arange(5), 2)
+    want = [(v + 1, float(v)) for v in range(5)]
+    assert res[0][2] == want and res[1][2] == want                   # every rank holds all blocks, list order
+
+
+class _Recorder:
+    """Stands in for an extractor: records which indices each rank received."""
+
+    def __init__(self, out_dir):
+        self.out_dir = out_dir
+
+    def __call__(self, indices):
+        rank = dist.get_rank()
+        with open(os.path.join(self.out_dir, f"rank{rank}.txt"), "w") as f:
+            f.write(",".join(str(int(i)) for i in indices))
+
+
+def _make_recorder(out_dir):
+    return _Recorder(out_dir)
+
+
+def test_parallel_feature_extraction_gloo(tmp_path):
+    import functools
+    from video_features_b200.dispatch import parallel_feature_extraction
+    parallel_feature_extraction(functools.partial(_make_recorder, str(tmp_path)), 10, [0, 1, 2, 3], backend="gloo",
+                                port=29900 + os.getpid() % 90)
+    got = [open(tmp_path / f"rank{r}.txt").read() for r in range(4)]
+    assert got == ["0,1,2", "3,4,5", "6,7,8", "9"]                  # == torch.arange(10).chunk(4)
+
+
+def test_main_cli_parser_matches_reference_flags():
+    import main
+    p = main.make_parser()
+    a = p.parse_args(["--feature_type", "CLIP-ViT-B/32", "--video_paths", "x.mp4", "--extract_method", "uni_12",
+                      "--device_ids", "0", "1", "--on_extraction", "save_numpy", "--output_direct"])
+    assert a.device_ids == [0, 1] and a.flow_type == "pwc" and a.batch_size == 1 and a.resize_to_smaller_edge is True
+    assert a.tmp_path == "./tmp" and a.output_path == "./output" and a.cpu is False
+    with pytest.raises(NotADirectoryError):
+        main.build_extractor(argparse.Namespace(feature_type="nonsense"))

@@ -273,7 +273,7 @@ extern "C" {
 int vf_clip_create(vf_clip_t** out, const vf_clip_weights* w, int device, int chunk_frames) {
     if (!out || !w) return fail(VF_ERR_INVALID, "clip_create: null argument");
     *out = nullptr;
-    if (chunk_frames <= 0) chunk_frames = 256;   // up to 12800 token rows per GEMM launch
+    if (chunk_frames <= 0) chunk_frames = 512;   // up to 25600 token rows per GEMM launch (~0.6 GB workspace)
     if (chunk_frames > 4096) return fail(VF_ERR_INVALID, "clip_create: chunk_frames %d too large", chunk_frames);
     VF_CUDA(cudaSetDevice(device));
     int major = 0, minor = 0;

@@ -1,0 +1,120 @@
+"""``ExtractCLIP`` -- drop-in for the reference's models/CLIP/extract_clip.py on the B200 engine.
+
+Same constructor, attributes, ``forward(indices)`` / ``extract(...)`` signatures, dict keys and file naming.  What
+changes underneath: ``clip.load`` is replaced by a ``ClipEngine`` (device weights + workspace), and ``preprocess`` +
+``model.encode_image`` by ONE call into libvfeat.so that takes the decoder's raw uint8 frames and runs the
+Pillow-exact bicubic resize, centre crop, normalisation and the ViT-B/32 tower on the GPU.
+
+Differences a user can observe, all deliberate:
+  * features are float32 on the GPU as well (the reference's GPU path returns float16 because ``clip.load`` keeps the
+    model in half precision on CUDA; its ``--cpu`` path returns float32);
+  * a CPU device is refused (no CPU fallback);
+  * weights come from a local checkpoint (``$VF_CLIP_CKPT`` or ``~/.cache/clip/ViT-B-32.pt``), never the network.
+"""
+from __future__ import annotations
+
+import os
+import pathlib
+import traceback
+from typing import Dict
+
+import numpy as np
+import torch
+from tqdm import tqdm
+
+from ..clip_engine import ClipEngine
+from ..utils import action_on_extraction, extract_frames, form_list_from_user_input
+
+_CKPT_NAMES = {'CLIP-ViT-B/32': 'ViT-B-32.pt', 'CLIP4CLIP-ViT-B-32': 'CLIP4CLIP-ViT-B-32.pth'}
+
+
+def load_clip_state_dict(feature_type: str) -> Dict[str, torch.Tensor]:
+    """Checkpoint in openai's format: a TorchScript archive (what ``clip.load`` downloads) or a plain state dict.
+    ``VF_CLIP_SYNTHETIC=<seed>`` selects seeded synthetic weights (benchmarks / tests without the real file)."""
+    if os.environ.get("VF_CLIP_SYNTHETIC") is not None:
+        from oracle import clip_tower            # weight generator only
+        return clip_tower.synthetic_state_dict(int(os.environ["VF_CLIP_SYNTHETIC"] or 0))
+    name = _CKPT_NAMES[feature_type]
+    cands = [os.environ.get("VF_CLIP_CKPT"), os.path.join(pathlib.Path(__file__).parent, 'checkpoints', name),
+             os.path.expanduser(os.path.join("~/.cache/clip", name))]
+    for p in cands:
+        if p and os.path.exists(p):
+            try:
+                return torch.jit.load(p, map_location="cpu").state_dict()
+            except RuntimeError:
+                sd = torch.load(p, map_location="cpu")
+                return sd.get("state_dict", sd)
+    if feature_type == 'CLIP4CLIP-ViT-B-32':
+        raise ValueError(cands[1])                 # extract_clip.py:57-58
+    raise FileNotFoundError(f"CLIP checkpoint {name} not found (looked at {[c for c in cands if c]}); "
+                            "there is no network access -- set VF_CLIP_CKPT")
+
+
+class ExtractCLIP(torch.nn.Module):
+
+    def __init__(self, args, external_call=False):
+        super(ExtractCLIP, self).__init__()
+        self.feature_type = args.feature_type
+        self.path_list = form_list_from_user_input(args)
+        self.extraction_fps = args.extraction_fps
+        self.extract_method = args.extract_method
+        self.on_extraction = args.on_extraction
+        self.external_call = external_call
+        if external_call is False:
+            self.output_direct = args.output_direct
+            if self.output_direct is True:
+                self.output_path = args.output_path
+            else:
+                self.output_path = os.path.join(args.output_path, self.feature_type)
+        self.progress = tqdm(total=len(self.path_list))
+        self._engines: Dict[int, ClipEngine] = {}
+
+    def _engine(self, device: torch.device) -> ClipEngine:
+        if device.type != 'cuda':
+            raise RuntimeError("the B200 engine has no CPU path: pass indices on a CUDA device "
+                               "(the reference's --cpu flow is timed by bench.py --impl reference)")
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if idx not in self._engines:
+            if self.feature_type not in _CKPT_NAMES:
+                # the reference lists B/16 and the ResNet towers as well (extract_clip.py:46-64); only the
+                # ViT-B/32 tower is built here (north_star)
+                raise NotImplementedError(self.feature_type)
+            self._engines[idx] = ClipEngine(load_clip_state_dict(self.feature_type), device=idx)
+        return self._engines[idx]
+
+    def forward(self, indices: torch.LongTensor):
+        """indices {torch.LongTensor} -- indices to self.path_list; the device is taken from ``indices.device``."""
+        device = indices.device
+        model = self._engine(device)          # one engine per device, kept across calls
+        feats_list = []
+        for idx in indices:
+            try:
+                feats_dict = self.extract(device, model, None, self.path_list[idx])
+                if self.external_call is False:
+                    action_on_extraction(feats_dict, self.path_list[idx], self.output_path,
+                                         self.on_extraction, self.output_direct)
+                else:
+                    feats_list.append(feats_dict)
+            except KeyboardInterrupt:
+                raise KeyboardInterrupt
+            except Exception as e:
+                print(e)
+                print(f'Extraction failed at: {self.path_list[idx]} with error (↑). Continuing extraction')
+                traceback.print_exc()
+            self.progress.update()
+        return feats_list
+
+    def extract(self, device: torch.device, model: ClipEngine, preprocess_func=None, video_path=None):
+        """-> {feature_type: (T,512) float32, 'fps': (), 'timestamps_ms': (T,)}.  ``preprocess_func`` is accepted for
+        signature compatibility; the transform is fused into the engine call."""
+        frames, fps, timestamps_ms = extract_frames(str(video_path), self.extract_method)
+        frames = [f for f in frames if f is not None]
+        if len(frames) == 0:
+            raise RuntimeError(f"no frames decoded from {video_path}")
+        batch = torch.from_numpy(np.stack(frames))          # (T,H,W,3) uint8, decoder channel order untouched
+        features = model.encode_frames_u8_host(batch)       # H2D + transform + tower + D2H
+        return {
+            self.feature_type: features.numpy(),
+            'fps': np.array(fps),
+            'timestamps_ms': np.array(timestamps_ms),
+        }
