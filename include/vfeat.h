@@ -111,6 +111,32 @@ int vf_clip_profile_read(vf_clip_t* h, double* gemm_ms, int64_t* gemm_launches, 
  * [3] frame transform (resize / normalise / patchify). */
 int vf_clip_profile_categories(const vf_clip_t* h, double* ms4);
 
+/* ---- I3D (Inception-3D) feature extractor: replaces `I3D(400, modality)(x, features=True)`
+ * (models/i3d/i3d_src/i3d_net.py:238-264, called at models/i3d/extract_i3d.py:186).
+ * One conv unit = Conv3d (no bias) + BatchNorm3d (eval) + ReLU (Unit3Dpy, i3d_net.py:37-105); weights are HOST fp32
+ * in the checkpoint's own layout.  Unit order: conv3d_1a_7x7, conv3d_2b_1x1, conv3d_2c_3x3, then for each of
+ * mixed_3b,3c,4b,4c,4d,4e,4f,5b,5c: branch_0, branch_1.0, branch_1.1, branch_2.0, branch_2.1, branch_3.1. */
+#define VF_I3D_UNITS 57
+typedef struct vf_conv_unit {
+    const float* w;                               /* [cout, cin, k, k, k] */
+    const float *bn_w, *bn_b, *bn_mean, *bn_var;  /* [cout] */
+    int cout, cin, k;
+} vf_conv_unit;
+typedef struct vf_i3d_weights {
+    vf_conv_unit units[VF_I3D_UNITS];
+} vf_i3d_weights;
+typedef struct vf_i3d vf_i3d_t;
+
+/* in_channels: 3 (rgb stream) or 2 (flow stream).  Workspace is sized for max_stacks clips of max_T frames. */
+int vf_i3d_create(vf_i3d_t** out, const vf_i3d_weights* w, int in_channels, int device, int max_stacks, int max_T);
+int vf_i3d_destroy(vf_i3d_t* h);
+/* clips: n x C x T x 224 x 224 fp32 on the device (the tensor the reference passes to I3D) -> out n x 1024 fp32. */
+int vf_i3d_forward_f32(vf_i3d_t* h, const float* clips, int n, int T, float* out, void* stream);
+/* Diagnostics: copy a retained internal activation (0: conv3d_1a, 1: conv3d_2c, 3: mixed_5b, 4: mixed_5c) of the
+ * last forward to fp32 NCTHW; dims5 receives (n, C, T, H, W); out == NULL only queries the shape. */
+int vf_i3d_read_stage(vf_i3d_t* h, int stage, float* out, int64_t capacity, int* dims5, void* stream);
+int64_t vf_i3d_launch_count(const vf_i3d_t* h);
+
 #ifdef __cplusplus
 }
 #endif

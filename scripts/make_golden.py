@@ -140,5 +140,51 @@ def main():
                         y_oracle=y_or.numpy())
 
 
-if __name__ == "__main__":
+
+
+def i3d_golden():
+    """Reference I3D module + vendored checkpoints vs the restated oracle, seeded inputs; stores only the outputs."""
+    import torch
+    sys.path.insert(0, REF)
+    cwd = os.getcwd()
+    os.chdir(REF)
+    try:
+        from models.i3d.i3d_src.i3d_net import I3D
+        from oracle import i3d_net
+        d = {}
+        for mod, cin in (("rgb", 3), ("flow", 2)):
+            sd = torch.load(f"models/i3d/checkpoints/i3d_{mod}.pt", map_location="cpu")
+            net = I3D(num_classes=400, modality=mod).eval()
+            net.load_state_dict(sd)
+            for T in (16, 11):
+                x = torch.rand(1, cin, T, 224, 224, generator=torch.Generator().manual_seed(100 + T)) * 2 - 1
+                with torch.no_grad():
+                    y_ref = net(x, features=True)
+                y_or = i3d_net.forward_features(sd, x)
+                rel = float((y_or - y_ref).norm() / y_ref.norm())
+                print(f"i3d {mod} T={T}: oracle vs reference rel {rel:.2e}")
+                assert rel < 1e-5
+                d[f"{mod}_T{T}"] = y_ref.numpy()
+        # synthetic-weight outputs, so the oracle is also pinned where the checkpoints are not available
+        for mod, cin in (("rgb", 3), ("flow", 2)):
+            sd = i3d_net.synthetic_state_dict(mod, 0)
+            net = I3D(num_classes=400, modality=mod).eval()
+            net.load_state_dict(sd, strict=False)
+            x = torch.rand(1, cin, 12, 224, 224, generator=torch.Generator().manual_seed(7)) * 2 - 1
+            with torch.no_grad():
+                y_ref = net(x, features=True)
+            y_or = i3d_net.forward_features(sd, x)
+            print(f"i3d {mod} synthetic: rel {float((y_or - y_ref).norm() / y_ref.norm()):.2e}")
+            d[f"{mod}_synth_T12"] = y_ref.numpy()
+        np.savez_compressed(os.path.join(OUT, "i3d_outputs.npz"), **d)
+    finally:
+        os.chdir(cwd)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "i3d":
+    i3d_golden()
+
+
+if __name__ == "__main__" and len(sys.argv) == 1:
     main()
+    i3d_golden()

@@ -1,0 +1,75 @@
+"""I3D features through the C ABI against the fp32 oracle (oracle/i3d_net.py, pinned to the reference module).
+
+Bar (north_star): 1e-3 relative vs the fp32 torch path.  Synthetic weights always; the reference's vendored
+checkpoints when a copy is present under checkpoints/ (scripts/fetch_checkpoints.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import video_features_b200  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _rel(y, ref):
+    y, ref = y.double().cpu(), ref.double().cpu()
+    return float(((y - ref).norm(dim=-1) / ref.norm(dim=-1)).max()), float(
+        ((y - ref).abs().amax(-1) / ref.abs().amax(-1)).max())
+
+
+def _oracle_gpu(sd, x, dev, stages=False):
+    from oracle import i3d_net
+    sdg = {k: v.to(dev) for k, v in sd.items()}
+    return i3d_net.forward_features(sdg, x.to(dev), return_stages=stages)
+
+
+@pytest.mark.parametrize("modality,T", [("rgb", 16), ("flow", 12), ("rgb", 11)])
+def test_i3d_synthetic_weights_vs_oracle(cuda_device, modality, T):
+    from oracle import i3d_net
+    from video_features_b200.i3d_engine import I3DEngine
+    sd = i3d_net.synthetic_state_dict(modality, 0)
+    cin = 3 if modality == "rgb" else 2
+    x = torch.rand(2, cin, T, 224, 224, generator=torch.Generator().manual_seed(T)) * 2 - 1
+    eng = I3DEngine(sd, modality, 0, max_stacks=2, max_T=16)
+    y = eng(x.to(cuda_device))
+    ref, st = _oracle_gpu(sd, x, cuda_device, stages=True)
+    for sid, name in ((0, "1a"), (1, "2c"), (4, "5c")):
+        got = eng.read_stage(sid)
+        want = st[name]
+        assert got.shape == want.shape, (name, got.shape, want.shape)
+        err = float((got - want).norm() / want.norm())
+        print(f"stage {name}: rel {err:.3e}")
+        assert err < 5e-3, (name, err)
+    rel, mx = _rel(y, ref)
+    print(f"{modality} T={T}: rel-L2 {rel:.3e} max {mx:.3e}; launches {eng.launch_count}")
+    assert rel < 1e-3 and mx < 1e-3
+    eng.close()
+
+
+@pytest.mark.parametrize("modality", ["rgb", "flow"])
+def test_i3d_reference_checkpoint_vs_oracle_and_golden(cuda_device, modality):
+    path = os.path.join(ROOT, "checkpoints", f"i3d_{modality}.pt")
+    if not os.path.exists(path):
+        pytest.skip("reference checkpoint copy not present (scripts/fetch_checkpoints.py)")
+    from video_features_b200.i3d_engine import I3DEngine
+    sd = torch.load(path, map_location="cpu")
+    cin = 3 if modality == "rgb" else 2
+    eng = I3DEngine(sd, modality, 0, max_stacks=1, max_T=64)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "i3d_outputs.npz"))
+    for T in (16, 11):
+        x = torch.rand(1, cin, T, 224, 224, generator=torch.Generator().manual_seed(100 + T)) * 2 - 1
+        y = eng(x.to(cuda_device))
+        ref = torch.from_numpy(gold[f"{modality}_T{T}"])          # the reference module's own output (fixture)
+        rel, mx = _rel(y, ref)
+        print(f"{modality} real weights T={T}: rel-L2 {rel:.3e} max {mx:.3e}")
+        assert rel < 1e-3 and mx < 1.5e-3
+    x = torch.rand(1, cin, 64, 224, 224, generator=torch.Generator().manual_seed(5)) * 2 - 1
+    y = eng(x.to(cuda_device))
+    ref = _oracle_gpu(sd, x, cuda_device)
+    rel, mx = _rel(y, ref)
+    print(f"{modality} real weights T=64: rel-L2 {rel:.3e} max {mx:.3e}")
+    assert rel < 1e-3
+    eng.close()

@@ -34,6 +34,19 @@ class ClipWeights(C.Structure):
         "ln_pre_w", "ln_pre_b", "ln_post_w", "ln_post_b", "proj")] + [("layers", ClipLayerWeights * 12)]
 
 
+class ConvUnitW(C.Structure):
+    _fields_ = [("w", C.POINTER(C.c_float)), ("bn_w", C.POINTER(C.c_float)), ("bn_b", C.POINTER(C.c_float)),
+                ("bn_mean", C.POINTER(C.c_float)), ("bn_var", C.POINTER(C.c_float)),
+                ("cout", C.c_int), ("cin", C.c_int), ("k", C.c_int)]
+
+
+I3D_UNITS = 57
+
+
+class I3DWeights(C.Structure):
+    _fields_ = [("units", ConvUnitW * I3D_UNITS)]
+
+
 _lock = threading.Lock()
 _lib = None
 
@@ -56,6 +69,11 @@ SIGNATURES = {
     "vf_clip_encode_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "vf_clip_encode_u8_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "vf_clip_launch_count": (C.c_int64, [C.c_void_p]),
+    "vf_i3d_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(I3DWeights), C.c_int, C.c_int, C.c_int, C.c_int]),
+    "vf_i3d_destroy": (C.c_int, [C.c_void_p]),
+    "vf_i3d_forward_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "vf_i3d_read_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int), C.c_void_p]),
+    "vf_i3d_launch_count": (C.c_int64, [C.c_void_p]),
     "vf_clip_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "vf_clip_profile_categories": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "vf_clip_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64),

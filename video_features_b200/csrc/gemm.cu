@@ -88,7 +88,7 @@ template <int BN, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmO, const GemmEpi ep, const int M, const int N,
-                     const int K) {
+                     const __grid_constant__ ConvGeom cg) {
     using Cfg = GemmCfg<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -108,7 +108,8 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int num_m = (M + 2 * BM - 1) / (2 * BM);
     const int num_n = (N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
-    const int num_k = (K + BK - 1) / BK;
+    const int kpt = (cg.k_per_tap + BK - 1) / BK;    // K blocks per filter tap (a plain GEMM is one "tap")
+    const int num_k = cg.ntaps * kpt;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -141,13 +142,17 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const int m_blk = tile % num_m, n_blk = tile / num_m;
                 const int m0 = m_blk * 2 * BM + int(cta) * BM;
                 const int n0 = n_blk * BN + int(cta) * (BN / 2);
-                for (int kb = 0; kb < num_k; ++kb) {
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    if (cta == 0) mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
-                    const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
-                    tma_load_2d_2sm(sA + stage * Cfg::A_BYTES, &tmA, bar, kb * BK, m0);
-                    tma_load_2d_2sm(sB + stage * Cfg::B_BYTES, &tmB, bar, kb * BK, n0);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                for (int tap = 0; tap < cg.ntaps; ++tap) {
+                    const int arow = m0 + cg.tap_off[tap];       // may be negative / past the end: TMA zero-fills
+                    const int bcol = tap * cg.k_per_tap;
+                    for (int kk = 0; kk < kpt; ++kk) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        if (cta == 0) mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+                        const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
+                        tma_load_2d_2sm(sA + stage * Cfg::A_BYTES, &tmA, bar, kk * BK, arow);
+                        tma_load_2d_2sm(sB + stage * Cfg::B_BYTES, &tmB, bar, bcol + kk * BK, n0);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
                 }
             }
         }
@@ -194,6 +199,14 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * BN + (uint32_t(q * 32) << 16);
+            bool keep = true;     // rows outside the valid conv region become the next layer's zero padding
+            if (cg.mask) {
+                const int m = m0 + row;
+                const int w = m % cg.Wp, r1 = m / cg.Wp;
+                const int hh = r1 % cg.Hp, r2 = r1 / cg.Hp;
+                const int tt = r2 % cg.Tp;
+                keep = (w >= cg.w0) && (w < cg.w1) && (hh >= cg.h0) && (hh < cg.h1) && (tt >= cg.t0) && (tt < cg.t1);
+            }
 #pragma unroll 1
             for (int c = grp * slice_cols; c < BN; c += 2 * slice_cols) {
                 uint8_t* buf = bufs + (it & 1) * SLICE_BYTES;
@@ -210,6 +223,10 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
                     epi_math32(v, ep, n, N);
+                    if (!keep) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         *reinterpret_cast<float4*>(myrow + ((uint32_t(j) ^ sw) << 4)) =
@@ -224,6 +241,10 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
                         epi_math32(v, ep, n + hh * 32, N);
+                        if (!keep) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                        }
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             *reinterpret_cast<uint4*>(myrow + ((uint32_t(hh * 4 + j) ^ sw) << 4)) =
@@ -273,7 +294,7 @@ EncodeTiledFn get_encode_tiled() {
 
 template <int BN, int STAGES>
 int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmEpi& ep, int M,
-                     int N, int K, cudaStream_t stream) {
+                     int N, const ConvGeom& cg, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, STAGES>;
     static bool attr_set[64] = {false};
     int dev = 0;
@@ -286,7 +307,7 @@ int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
     const int pairs = device_sm_count() / 2;
     const int grid = 2 * (tiles < pairs ? tiles : pairs);
-    gemm_f16_pair_kernel<BN, STAGES><<<grid, 384, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, ep, M, N, K);
+    gemm_f16_pair_kernel<BN, STAGES><<<grid, 384, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, ep, M, N, cg);
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
@@ -323,22 +344,46 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t ro
     return VF_OK;
 }
 
+static int run_gemm(const CUtensorMap& tmA, const __half* B, int ldb, int64_t Ktot, int M, int N, const ConvGeom& cg,
+                    const GemmEpi& ep, cudaStream_t stream) {
+    if (!ep.out) return fail(VF_ERR_INVALID, "gemm: null output");
+    if (N % 8) return fail(VF_ERR_INVALID, "gemm: N=%d must be a multiple of 8", N);
+    if (ep.out_f32 ? (ep.ldo % 4) : (ep.ldo % 8)) return fail(VF_ERR_INVALID, "gemm: ldo breaks 16-byte rows");
+    const int bn = (N > 128) ? 256 : (N > 64) ? 128 : 64;     // pair-tile width; the B box is half of it
+    CUtensorMap tmB, tmO;
+    VF_TRY(make_tmap_2d(&tmB, B, 2, uint64_t(N), uint64_t(Ktot), uint64_t(ldb) * 2, uint32_t(bn / 2), BK));
+    if (ep.out_f32) VF_TRY(make_tmap_2d(&tmO, ep.out, 4, uint64_t(M), uint64_t(N), uint64_t(ep.ldo) * 4, BM, 32));
+    else            VF_TRY(make_tmap_2d(&tmO, ep.out, 2, uint64_t(M), uint64_t(N), uint64_t(ep.ldo) * 2, BM, 64));
+    if (bn == 256) return launch_gemm_pair<256, 5>(tmA, tmB, tmO, ep, M, N, cg, stream);
+    if (bn == 128) return launch_gemm_pair<128, 6>(tmA, tmB, tmO, ep, M, N, cg, stream);
+    return launch_gemm_pair<64, 8>(tmA, tmB, tmO, ep, M, N, cg, stream);
+}
+
 int gemm_f16(const __half* A, int lda, const __half* B, int ldb, int M, int N, int K, const GemmEpi& ep,
              cudaStream_t stream) {
     if (M <= 0 || N <= 0 || K <= 0) return fail(VF_ERR_INVALID, "gemm: empty problem %dx%dx%d", M, N, K);
-    if (N % 8) return fail(VF_ERR_INVALID, "gemm: N=%d must be a multiple of 8", N);
     if (K % 8 || lda % 8 || ldb % 8) return fail(VF_ERR_INVALID, "gemm: K/lda/ldb must be multiples of 8");
-    if (!ep.out) return fail(VF_ERR_INVALID, "gemm: null output");
-    if (ep.out_f32 ? (ep.ldo % 4) : (ep.ldo % 8)) return fail(VF_ERR_INVALID, "gemm: ldo breaks 16-byte rows");
-    const int bn = (N > 128) ? 256 : (N > 64) ? 128 : 64;     // pair-tile width; the B box is half of it
-    CUtensorMap tmA, tmB, tmO;
+    ConvGeom cg;
+    memset(&cg, 0, sizeof(cg));
+    cg.ntaps = 1;
+    cg.k_per_tap = K;
+    CUtensorMap tmA;
     VF_TRY(make_tmap_2d(&tmA, A, 2, uint64_t(M), uint64_t(K), uint64_t(lda) * 2, BM, BK));
-    VF_TRY(make_tmap_2d(&tmB, B, 2, uint64_t(N), uint64_t(K), uint64_t(ldb) * 2, uint32_t(bn / 2), BK));
-    if (ep.out_f32) VF_TRY(make_tmap_2d(&tmO, ep.out, 4, uint64_t(M), uint64_t(N), uint64_t(ep.ldo) * 4, BM, 32));
-    else            VF_TRY(make_tmap_2d(&tmO, ep.out, 2, uint64_t(M), uint64_t(N), uint64_t(ep.ldo) * 2, BM, 64));
-    if (bn == 256) return launch_gemm_pair<256, 5>(tmA, tmB, tmO, ep, M, N, K, stream);
-    if (bn == 128) return launch_gemm_pair<128, 6>(tmA, tmB, tmO, ep, M, N, K, stream);
-    return launch_gemm_pair<64, 8>(tmA, tmB, tmO, ep, M, N, K, stream);
+    return run_gemm(tmA, B, ldb, K, M, N, cg, ep, stream);
+}
+
+int conv_gemm_f16(const __half* X, int C, int64_t P, const __half* Wt, int N, const ConvGeom& g, const GemmEpi& ep,
+                  cudaStream_t stream) {
+    if (P <= 0 || P > 0x7fffffff || N <= 0 || C <= 0) return fail(VF_ERR_INVALID, "conv_gemm: bad size");
+    if (C % 8) return fail(VF_ERR_INVALID, "conv_gemm: C=%d must be a multiple of 8", C);
+    if (g.ntaps < 1 || g.ntaps > 64 || g.k_per_tap < 8 || g.k_per_tap % 8)
+        return fail(VF_ERR_INVALID, "conv_gemm: bad tap geometry (%d taps x %d)", g.ntaps, g.k_per_tap);
+    // overlapping-row view: row p = k_per_tap contiguous elements starting at element p*C
+    CUtensorMap tmA;
+    VF_TRY(make_tmap_2d(&tmA, X, 2, uint64_t(P), uint64_t(g.k_per_tap), uint64_t(C) * 2, BM, BK));
+    const int64_t Ktot = int64_t(g.ntaps) * g.k_per_tap;
+    if (Ktot % 8) return fail(VF_ERR_INVALID, "conv_gemm: K must be a multiple of 8");
+    return run_gemm(tmA, Wt, int(Ktot), Ktot, int(P), N, g, ep, stream);
 }
 
 }  // namespace vf

@@ -1,0 +1,333 @@
+// Inception-3D (I3D) feature extractor on the tcgen05 conv-GEMM.
+// Replaces `I3D(num_classes=400, modality).forward(x, features=True)` (reference: models/i3d/i3d_src/i3d_net.py:238-264,
+// called at models/i3d/extract_i3d.py:186) and the stream transforms around it (extract_i3d.py:62-73).
+//
+// Data layout: every activation is channels-last fp16 in a ZERO-BORDERED volume [n][Tp][Hp][Wp][C] (border 1 around
+// the valid T x H x W region), flattened to rows of C channels.  With that layout
+//   * a 1x1x1 conv is a plain GEMM over the rows,
+//   * a 3x3x3 conv is 9 (dt,dh) "taps", each a constant row shift whose 3 kw neighbours are one contiguous run of
+//     3*C elements (conv_gemm_f16), the zero border IS the SAME padding, and the epilogue re-zeroes border rows,
+//   * the zero-padding max pools of the reference (MaxPool3dTFPadding pads with 0, i3d_net.py:114) read the border,
+//   * the 7x7x7 stride-2 stem becomes a 4x4x4 stride-1 conv over the 8 space-time phases of the input
+//     ([n][T/2+3][115][115][8*C]), 16 (dt,dh) taps of 4*8*C contiguous elements.
+// BatchNorm (eval) is folded into the epilogue's per-channel scale/bias (fp32), ReLU fused; branch outputs of a Mixed
+// block are written straight into their channel slice of the concat buffer (TMA store with the concat row pitch).
+//
+// Numerics: activations fp16, accumulate fp32.  With single-fp16 weights the 1024-d feature is 1.7e-3 off the fp32
+// reference (trained weights; CPU emulation in DESIGN.md); weights are therefore carried as a hi+lo fp16 pair and
+// every K block is issued twice (A.W_hi + A.W_lo), which brings it to 8e-4.  VF_I3D_FAST=1 selects single fp16.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "internal.h"
+
+namespace vf {
+
+struct Vol {
+    int n, Tp, Hp, Wp, t0, t1, h0, h1, w0, w1;
+    int64_t rows() const { return int64_t(n) * Tp * Hp * Wp; }
+    int T() const { return t1 - t0; }
+    int H() const { return h1 - h0; }
+    int W() const { return w1 - w0; }
+};
+static Vol bordered(int n, int T, int H, int W) { return Vol{n, T + 2, H + 2, W + 2, 1, 1 + T, 1, 1 + H, 1, 1 + W}; }
+
+struct ConvUnit {
+    int cout = 0, cin = 0, k = 0;     // k: 1, 3, or 7 (the stem)
+    int ntaps = 0, k_per_tap = 0;     // base tap geometry (before the hi/lo split)
+    int nsplit = 1;
+    __half* w = nullptr;              // [cout, nsplit * ntaps * k_per_tap]
+    float *scale = nullptr, *bias = nullptr;
+};
+
+// kernels (i3d_kernels.cu); volumes are passed as pointers to the 10 leading ints of Vol
+int launch_i3d_phase_pack_f32(const float* x, int n, int C, int T, __half* out, int Tq, cudaStream_t s);
+int launch_maxpool3d_raw(const __half* in, const void* vi, __half* out, const void* vo, int C, int kt, int kh, int kw,
+                         int st, int sh, int sw, int pt, int ph, int pw, cudaStream_t s);
+int launch_i3d_head_raw(const __half* in, const void* vi, int C, float* out, cudaStream_t s);
+int launch_unpack_ndhwc_raw(const __half* in, const void* vi, int C, int c_off, int c_cnt, int ld, float* out,
+                            cudaStream_t s);
+static int launch_maxpool3d(const __half* in, const Vol& vi, __half* out, const Vol& vo, int C, int kt, int kh, int kw,
+                            int st, int sh, int sw, int pt, int ph, int pw, cudaStream_t s) {
+    return launch_maxpool3d_raw(in, &vi, out, &vo, C, kt, kh, kw, st, sh, sw, pt, ph, pw, s);
+}
+static int launch_i3d_head(const __half* in, const Vol& vi, int C, float* out, cudaStream_t s) {
+    return launch_i3d_head_raw(in, &vi, C, out, s);
+}
+static int launch_unpack_ndhwc(const __half* in, const Vol& vi, int C, int c_off, int c_cnt, int ld, float* out,
+                               cudaStream_t s) {
+    return launch_unpack_ndhwc_raw(in, &vi, C, c_off, c_cnt, ld, out, s);
+}
+
+}  // namespace vf
+
+using namespace vf;
+
+static const int kMixed[9][7] = {
+    // cin, b0, b1a, b1b, b2a, b2b, b3     (i3d_net.py:206-224)
+    {192, 64, 96, 128, 16, 32, 32},   {256, 128, 128, 192, 32, 96, 64},  {480, 192, 96, 208, 16, 48, 64},
+    {512, 160, 112, 224, 24, 64, 64}, {512, 128, 128, 256, 24, 64, 64},  {512, 112, 144, 288, 32, 64, 64},
+    {528, 256, 160, 320, 32, 128, 128}, {832, 256, 160, 320, 32, 128, 128}, {832, 384, 192, 384, 48, 128, 128}};
+
+struct vf_i3d {
+    int device = 0, cin = 3, max_stacks = 0, max_T = 0;
+    int nsplit = 2;
+    std::vector<void*> allocs;
+    ConvUnit units[VF_I3D_UNITS];
+    // activation buffers (sized for max_stacks x max_T at create)
+    __half *s0 = nullptr, *a1 = nullptr, *p1 = nullptr, *c2b = nullptr, *c2c = nullptr;
+    __half *bufA = nullptr, *bufB = nullptr, *t1 = nullptr, *t2 = nullptr, *tp = nullptr;
+    size_t cap_s0 = 0, cap_a1 = 0, cap_s1 = 0, cap_rows2 = 0;
+    int64_t launches = 0;
+    // last forward's stage views, for vf_i3d_read_stage
+    struct StageRef { const __half* p; Vol v; int C; } stages[5];
+};
+
+namespace vf {
+
+template <typename Tp>
+static int i3d_alloc(vf_i3d* h, Tp** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(Tp));
+    if (e != cudaSuccess) return fail(VF_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(Tp), cudaGetErrorString(e));
+    h->allocs.push_back(q);
+    *p = static_cast<Tp*>(q);
+    return VF_OK;
+}
+
+// fold BN, re-lay the filter for the shifted-row GEMM, split into hi/lo fp16, upload
+static int prepare_unit(vf_i3d* h, ConvUnit& u, const vf_conv_unit& src, int idx) {
+    if (!src.w || !src.bn_w || !src.bn_b || !src.bn_mean || !src.bn_var)
+        return fail(VF_ERR_INVALID, "i3d_create: unit %d has a null tensor", idx);
+    u.cout = src.cout; u.cin = src.cin; u.k = src.k;
+    const int co = u.cout, ci = u.cin, k = u.k;
+    std::vector<float> wt;   // [co][ntaps*k_per_tap]
+    if (k == 1) {
+        u.ntaps = 1; u.k_per_tap = ci;
+        wt.assign(src.w, src.w + size_t(co) * ci);
+    } else if (k == 3) {
+        u.ntaps = 9; u.k_per_tap = 3 * ci;
+        wt.resize(size_t(co) * 27 * ci);
+        for (int o = 0; o < co; ++o)
+            for (int c = 0; c < ci; ++c)
+                for (int kt = 0; kt < 3; ++kt)
+                    for (int kh = 0; kh < 3; ++kh)
+                        for (int kw = 0; kw < 3; ++kw)
+                            wt[(size_t(o) * 9 + kt * 3 + kh) * (3 * ci) + kw * ci + c] =
+                                src.w[(((size_t(o) * ci + c) * 3 + kt) * 3 + kh) * 3 + kw];
+    } else if (k == 7) {
+        // stride-2 7x7x7 with TF-SAME padding (2 before, 3 after) == 4x4x4 stride-1 over the 8 phases:
+        // filter index kk = 2*a + p for tap a in 0..3 (row offset a-1) and phase p in 0..1; kk == 7 does not exist
+        const int pc = 8 * ci;
+        u.ntaps = 16; u.k_per_tap = 4 * pc;
+        wt.assign(size_t(co) * 16 * 4 * pc, 0.f);
+        for (int o = 0; o < co; ++o)
+            for (int c = 0; c < ci; ++c)
+                for (int a = 0; a < 4; ++a) for (int pt = 0; pt < 2; ++pt) {
+                    const int kt = 2 * a + pt; if (kt > 6) continue;
+                    for (int b = 0; b < 4; ++b) for (int ph = 0; ph < 2; ++ph) {
+                        const int kh = 2 * b + ph; if (kh > 6) continue;
+                        for (int cw = 0; cw < 4; ++cw) for (int pw = 0; pw < 2; ++pw) {
+                            const int kw = 2 * cw + pw; if (kw > 6) continue;
+                            wt[(size_t(o) * 16 + a * 4 + b) * (4 * pc) + cw * pc + ((pt * 2 + ph) * 2 + pw) * ci + c] =
+                                src.w[(((size_t(o) * ci + c) * 7 + kt) * 7 + kh) * 7 + kw];
+                        }
+                    }
+                }
+    } else {
+        return fail(VF_ERR_UNSUPPORTED, "i3d_create: unit %d has kernel size %d", idx, k);
+    }
+    if (u.k_per_tap % 8) return fail(VF_ERR_UNSUPPORTED, "i3d_create: unit %d: %d channels per tap", idx, u.k_per_tap);
+    u.nsplit = h->nsplit;
+    const size_t Kb = size_t(u.ntaps) * u.k_per_tap, Kt = Kb * u.nsplit;
+    std::vector<__half> wh(size_t(co) * Kt);
+    for (int o = 0; o < co; ++o)
+        for (size_t j = 0; j < Kb; ++j) {
+            const float v = wt[size_t(o) * Kb + j];
+            const __half hi = __float2half_rn(v);
+            wh[size_t(o) * Kt + j] = hi;
+            if (u.nsplit == 2) wh[size_t(o) * Kt + Kb + j] = __float2half_rn(v - __half2float(hi));
+        }
+    std::vector<float> sc(co), bi(co);
+    for (int o = 0; o < co; ++o) {
+        const float s = src.bn_w[o] / sqrtf(src.bn_var[o] + 1e-5f);   // BatchNorm3d eval, eps 1e-5 (i3d_net.py:92)
+        sc[o] = s;
+        bi[o] = src.bn_b[o] - src.bn_mean[o] * s;
+    }
+    VF_TRY(i3d_alloc(h, &u.w, wh.size()));
+    VF_TRY(i3d_alloc(h, &u.scale, size_t(co)));
+    VF_TRY(i3d_alloc(h, &u.bias, size_t(co)));
+    VF_CUDA(cudaMemcpy(u.w, wh.data(), wh.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    VF_CUDA(cudaMemcpy(u.scale, sc.data(), co * sizeof(float), cudaMemcpyHostToDevice));
+    VF_CUDA(cudaMemcpy(u.bias, bi.data(), co * sizeof(float), cudaMemcpyHostToDevice));
+    return VF_OK;
+}
+
+// conv + BN + ReLU of one unit over a bordered volume; out rows keep the input's row indexing
+static int run_unit(vf_i3d* h, const ConvUnit& u, const __half* X, int ldx_channels, const Vol& v, __half* out, int ldo,
+                    cudaStream_t s) {
+    ConvGeom g;
+    memset(&g, 0, sizeof(g));
+    g.k_per_tap = u.k_per_tap;
+    g.ntaps = u.ntaps * u.nsplit;
+    const int hw = v.Hp * v.Wp;
+    for (int rep = 0; rep < u.nsplit; ++rep)
+        for (int j = 0; j < u.ntaps; ++j) {
+            int off = 0;
+            if (u.k == 3) off = (j / 3 - 1) * hw + (j % 3 - 1) * v.Wp - 1;
+            else if (u.k == 7) off = (j / 4 - 1) * hw + (j % 4 - 1) * v.Wp - 1;
+            g.tap_off[rep * u.ntaps + j] = off;
+        }
+    g.mask = 1;
+    g.Tp = v.Tp; g.Hp = v.Hp; g.Wp = v.Wp;
+    g.t0 = v.t0; g.t1 = v.t1; g.h0 = v.h0; g.h1 = v.h1; g.w0 = v.w0; g.w1 = v.w1;
+    GemmEpi ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.out = out; ep.ldo = ldo; ep.out_f32 = 0; ep.bias = u.bias; ep.scale = u.scale; ep.act = VF_ACT_RELU;
+    h->launches += 1;
+    return conv_gemm_f16(X, ldx_channels, v.rows(), u.w, u.cout, g, ep, s);
+}
+
+static int mixed_block(vf_i3d* h, int m, const __half* x, const Vol& v, __half* out, cudaStream_t s) {
+    const int* c = kMixed[m];
+    const ConvUnit* u = &h->units[3 + 6 * m];
+    const int cin = c[0], ctot = c[1] + c[3] + c[5] + c[6];
+    VF_TRY(run_unit(h, u[0], x, cin, v, out, ctot, s));                                   // branch_0
+    VF_TRY(run_unit(h, u[1], x, cin, v, h->t1, c[2], s));                                 // branch_1.0
+    VF_TRY(run_unit(h, u[2], h->t1, c[2], v, out + c[1], ctot, s));                       // branch_1.1 (3x3x3)
+    VF_TRY(run_unit(h, u[3], x, cin, v, h->t2, c[4], s));                                 // branch_2.0
+    VF_TRY(run_unit(h, u[4], h->t2, c[4], v, out + c[1] + c[3], ctot, s));                // branch_2.1 (3x3x3)
+    VF_TRY(launch_maxpool3d(x, v, h->tp, v, cin, 3, 3, 3, 1, 1, 1, 1, 1, 1, s));          // branch_3 pool (zero pad)
+    h->launches += 1;
+    VF_TRY(run_unit(h, u[5], h->tp, cin, v, out + c[1] + c[3] + c[5], ctot, s));          // branch_3.1
+    return VF_OK;
+}
+
+static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace vf
+
+extern "C" {
+
+int vf_i3d_create(vf_i3d_t** out, const vf_i3d_weights* w, int in_channels, int device, int max_stacks, int max_T) {
+    if (!out || !w) return fail(VF_ERR_INVALID, "i3d_create: null argument");
+    *out = nullptr;
+    if (in_channels != 3 && in_channels != 2) return fail(VF_ERR_INVALID, "i3d_create: in_channels must be 3 (rgb) or 2 (flow)");
+    if (max_stacks <= 0) max_stacks = 4;
+    if (max_T <= 0) max_T = 64;
+    VF_CUDA(cudaSetDevice(device));
+    int major = 0;
+    VF_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) return fail(VF_ERR_UNSUPPORTED, "device %d is not sm_100; this library is built for sm_100a only", device);
+    vf_i3d* h = new vf_i3d();
+    h->device = device; h->cin = in_channels; h->max_stacks = max_stacks; h->max_T = max_T;
+    {
+        const char* e = getenv("VF_I3D_FAST");
+        h->nsplit = (e && e[0] == '1') ? 1 : 2;
+    }
+    auto body = [&]() -> int {
+        for (int i = 0; i < VF_I3D_UNITS; ++i) VF_TRY(prepare_unit(h, h->units[i], w->units[i], i));
+        if (h->units[0].cin != in_channels || h->units[0].k != 7) return fail(VF_ERR_INVALID, "i3d_create: stem shape");
+        const size_t n = size_t(max_stacks);
+        const int T1 = max_T / 2, Tq = T1 + 3;       // stem: floor((T + 5 - 7) / 2) + 1 = T / 2
+        const size_t rows0 = n * Tq * 115 * 115;
+        VF_TRY(i3d_alloc(h, &h->s0, rows0 * 8 * in_channels + 4096));
+        VF_TRY(i3d_alloc(h, &h->a1, rows0 * 64));
+        const size_t rows1 = n * (T1 + 2) * 58 * 58;
+        VF_TRY(i3d_alloc(h, &h->p1, rows1 * 64));
+        VF_TRY(i3d_alloc(h, &h->c2b, rows1 * 64));
+        VF_TRY(i3d_alloc(h, &h->c2c, rows1 * 192));
+        const size_t rows2 = n * (T1 + 2) * 30 * 30;    // largest Mixed stage
+        VF_TRY(i3d_alloc(h, &h->bufA, rows2 * 1024));
+        VF_TRY(i3d_alloc(h, &h->bufB, rows2 * 1024));
+        VF_TRY(i3d_alloc(h, &h->t1, rows2 * 192));
+        VF_TRY(i3d_alloc(h, &h->t2, rows2 * 64));
+        VF_TRY(i3d_alloc(h, &h->tp, rows2 * 832));
+        h->cap_rows2 = rows2;
+        return VF_OK;
+    };
+    const int st = body();
+    if (st != VF_OK) { vf_i3d_destroy(h); return st; }
+    *out = h;
+    return VF_OK;
+}
+
+int vf_i3d_destroy(vf_i3d_t* h) {
+    if (!h) return VF_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+    return VF_OK;
+}
+
+int vf_i3d_forward_f32(vf_i3d_t* h, const float* clips, int n, int T, float* out, void* stream) {
+    if (!h || (n > 0 && (!clips || !out))) return fail(VF_ERR_INVALID, "i3d_forward: null argument");
+    if (n <= 0) return VF_OK;
+    if (T < 10 || T > h->max_T) return fail(VF_ERR_INVALID, "i3d_forward: T=%d outside [10, %d]", T, h->max_T);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    VF_CUDA(cudaSetDevice(h->device));
+    for (int b0 = 0; b0 < n; b0 += h->max_stacks) {
+        const int nb = (n - b0 < h->max_stacks) ? (n - b0) : h->max_stacks;
+        const float* x = clips + size_t(b0) * h->cin * T * 224 * 224;
+        // ---- stem: phase-pack, 7x7x7/2 conv as 16-tap shifted GEMM
+        const int T1 = T / 2, Tq = T1 + 3;            // torch conv3d, pad (2,3), stride 2: floor((T-2)/2)+1
+        VF_TRY(launch_i3d_phase_pack_f32(x, nb, h->cin, T, h->s0, Tq, s));
+        h->launches += 1;
+        const Vol v0{nb, Tq, 115, 115, 1, 1 + T1, 1, 113, 1, 113};
+        VF_TRY(run_unit(h, h->units[0], h->s0, 8 * h->cin, v0, h->a1, 64, s));
+        // ---- maxPool3d_2a (1,3,3)/(1,2,2), SAME pad (0,1) on H,W
+        const Vol v1 = bordered(nb, T1, 56, 56);
+        VF_TRY(launch_maxpool3d(h->a1, v0, h->p1, v1, 64, 1, 3, 3, 1, 2, 2, 0, 0, 0, s));
+        VF_TRY(run_unit(h, h->units[1], h->p1, 64, v1, h->c2b, 64, s));
+        VF_TRY(run_unit(h, h->units[2], h->c2b, 64, v1, h->c2c, 192, s));
+        // ---- maxPool3d_3a
+        const Vol v2 = bordered(nb, T1, 28, 28);
+        VF_TRY(launch_maxpool3d(h->c2c, v1, h->bufA, v2, 192, 1, 3, 3, 1, 2, 2, 0, 0, 0, s));
+        VF_TRY(mixed_block(h, 0, h->bufA, v2, h->bufB, s));     // 3b -> 256
+        VF_TRY(mixed_block(h, 1, h->bufB, v2, h->bufA, s));     // 3c -> 480
+        // ---- maxPool3d_4a 3x3x3 / 2, SAME pad (0,1)
+        const int T2 = ceil_div(T1, 2);
+        const Vol v3 = bordered(nb, T2, 14, 14);
+        VF_TRY(launch_maxpool3d(h->bufA, v2, h->bufB, v3, 480, 3, 3, 3, 2, 2, 2, 0, 0, 0, s));
+        VF_TRY(mixed_block(h, 2, h->bufB, v3, h->bufA, s));     // 4b -> 512
+        VF_TRY(mixed_block(h, 3, h->bufA, v3, h->bufB, s));     // 4c
+        VF_TRY(mixed_block(h, 4, h->bufB, v3, h->bufA, s));     // 4d
+        VF_TRY(mixed_block(h, 5, h->bufA, v3, h->bufB, s));     // 4e -> 528
+        VF_TRY(mixed_block(h, 6, h->bufB, v3, h->bufA, s));     // 4f -> 832
+        // ---- maxPool3d_5a 2x2x2 / 2, no padding, ceil mode
+        const int T3 = ceil_div(T2, 2);
+        const Vol v4 = bordered(nb, T3, 7, 7);
+        VF_TRY(launch_maxpool3d(h->bufA, v3, h->bufB, v4, 832, 2, 2, 2, 2, 2, 2, 0, 0, 0, s));
+        VF_TRY(mixed_block(h, 7, h->bufB, v4, h->bufA, s));     // 5b -> 832
+        VF_TRY(mixed_block(h, 8, h->bufA, v4, h->bufB, s));     // 5c -> 1024
+        if (T3 < 2) return fail(VF_ERR_INVALID, "i3d_forward: T=%d leaves %d temporal positions for the (2,7,7) pool", T, T3);
+        // ---- AvgPool3d((2,7,7),1) + mean over time
+        VF_TRY(launch_i3d_head(h->bufB, v4, 1024, out + size_t(b0) * 1024, s));
+        h->launches += 6;
+        h->stages[0] = {h->a1, v0, 64};
+        h->stages[1] = {h->c2c, v1, 192};
+        h->stages[2] = {nullptr, v2, 480};     // overwritten by later blocks; only valid when read right after
+        h->stages[3] = {h->bufA, v3, 832};     // (4f output is clobbered by 5b; see vf_i3d_read_stage)
+        h->stages[4] = {h->bufB, v4, 1024};
+    }
+    return VF_OK;
+}
+
+int vf_i3d_read_stage(vf_i3d_t* h, int stage, float* out, int64_t capacity, int* dims5, void* stream) {
+    if (!h || stage < 0 || stage > 4 || !dims5) return fail(VF_ERR_INVALID, "i3d_read_stage: bad argument");
+    const vf_i3d::StageRef& r = h->stages[stage];
+    if (!r.p) return fail(VF_ERR_UNSUPPORTED, "i3d_read_stage: stage %d is not retained", stage);
+    dims5[0] = r.v.n; dims5[1] = r.C; dims5[2] = r.v.T(); dims5[3] = r.v.H(); dims5[4] = r.v.W();
+    const int64_t need = int64_t(r.v.n) * r.C * r.v.T() * r.v.H() * r.v.W();
+    if (!out) return VF_OK;
+    if (capacity < need) return fail(VF_ERR_INVALID, "i3d_read_stage: capacity %lld < %lld", (long long)capacity, (long long)need);
+    return launch_unpack_ndhwc(r.p, r.v, r.C, 0, r.C, r.C, out, static_cast<cudaStream_t>(stream));
+}
+
+int64_t vf_i3d_launch_count(const vf_i3d_t* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

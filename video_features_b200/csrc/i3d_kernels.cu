@@ -1,0 +1,173 @@
+// Memory-bound kernels of the I3D path: stem phase packing, zero-padding max pools, the (2,7,7) average pool +
+// temporal mean head, and a diagnostic unpack.  All operate on channels-last fp16 rows of zero-bordered volumes.
+#include "common.cuh"
+#include "internal.h"
+
+namespace vf {
+
+struct DVol {   // device-side view of a zero-bordered volume (same leading fields as Vol in i3d.cu)
+    int n, Tp, Hp, Wp, t0, t1, h0, h1, w0, w1;
+};
+
+namespace {
+
+inline unsigned nblocks(int64_t total, int threads) { return unsigned((total + threads - 1) / threads); }
+
+// x: [n][C][T][224][224] fp32 (already cropped + scaled to [-1,1], what the reference feeds I3D)
+// out: [n][Tq][115][115][8*C] fp16 with out[tq][hq][wq][((pt*2+ph)*2+pw)*C + c] = x[c][2(tq-1)+pt][2(hq-1)+ph][2(wq-1)+pw]
+// (zero outside the clip): the 8 space-time phases of the stride-2 stem as channels, origin shifted by one.
+__global__ void i3d_phase_pack_f32_kernel(const float* __restrict__ x, int n, int C, int T, __half* __restrict__ out,
+                                          int Tq) {
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(n) * Tq * 115 * 115;
+    if (idx >= total) return;
+    const int wq = int(idx % 115);
+    const int hq = int((idx / 115) % 115);
+    const int tq = int((idx / (115 * 115)) % Tq);
+    const int b = int(idx / (int64_t(115) * 115 * Tq));
+    __half* o = out + idx * (8 * C);
+    const int w0 = 2 * (wq - 1);
+    for (int pt = 0; pt < 2; ++pt) {
+        const int t = 2 * (tq - 1) + pt;
+        for (int ph = 0; ph < 2; ++ph) {
+            const int hh = 2 * (hq - 1) + ph;
+            const bool ok = (t >= 0) && (t < T) && (hh >= 0) && (hh < 224) && (w0 >= 0) && (w0 < 224);
+            for (int c = 0; c < C; ++c) {
+                float2 v = make_float2(0.f, 0.f);
+                if (ok) v = __ldg(reinterpret_cast<const float2*>(
+                            x + (((int64_t(b) * C + c) * T + t) * 224 + hh) * 224 + w0));
+                o[((pt * 2 + ph) * 2 + 0) * C + c] = __float2half_rn(v.x);
+                o[((pt * 2 + ph) * 2 + 1) * C + c] = __float2half_rn(v.y);
+            }
+        }
+    }
+}
+
+// Max pool over the VALID region of the input volume with ZERO padding semantics (MaxPool3dTFPadding: ConstantPad3d(0)
+// then ceil-mode MaxPool3d; inputs are post-ReLU so 0 never wins wrongly).  One thread = one output position x 8
+// channels; border positions of the output volume are written as zeros.
+__global__ void maxpool3d_kernel(const __half* __restrict__ in, DVol vi, __half* __restrict__ out, DVol vo, int C,
+                                 int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph, int pw) {
+    const int cg = C >> 3;
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(vo.n) * vo.Tp * vo.Hp * vo.Wp * cg;
+    if (idx >= total) return;
+    const int c8 = int(idx % cg);
+    const int64_t pos = idx / cg;
+    const int w = int(pos % vo.Wp);
+    const int hh = int((pos / vo.Wp) % vo.Hp);
+    const int t = int((pos / (int64_t(vo.Wp) * vo.Hp)) % vo.Tp);
+    const int b = int(pos / (int64_t(vo.Wp) * vo.Hp * vo.Tp));
+    __half2 m[4];
+    const __half2 zero = __float2half2_rn(0.f);
+    m[0] = m[1] = m[2] = m[3] = zero;
+    const bool valid = (t >= vo.t0) && (t < vo.t1) && (hh >= vo.h0) && (hh < vo.h1) && (w >= vo.w0) && (w < vo.w1);
+    if (valid) {
+        const int ot = t - vo.t0, oh = hh - vo.h0, ow = w - vo.w0;     // output coordinates
+        const int Ti = vi.t1 - vi.t0, Hi = vi.h1 - vi.h0, Wi = vi.w1 - vi.w0;
+        for (int a = 0; a < kt; ++a) {
+            const int it = ot * st - pt + a;
+            if (it < 0 || it >= Ti) continue;
+            for (int bq = 0; bq < kh; ++bq) {
+                const int ih = oh * sh - ph + bq;
+                if (ih < 0 || ih >= Hi) continue;
+                for (int cc = 0; cc < kw; ++cc) {
+                    const int iw = ow * sw - pw + cc;
+                    if (iw < 0 || iw >= Wi) continue;
+                    const int64_t r = ((int64_t(b) * vi.Tp + it + vi.t0) * vi.Hp + ih + vi.h0) * vi.Wp + iw + vi.w0;
+                    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(in + r * C + c8 * 8));
+                    const __half2* v = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) m[j] = __hmax2(m[j], v[j]);
+                }
+            }
+        }
+    }
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&m[0]);
+    o.y = *reinterpret_cast<uint32_t*>(&m[1]);
+    o.z = *reinterpret_cast<uint32_t*>(&m[2]);
+    o.w = *reinterpret_cast<uint32_t*>(&m[3]);
+    *reinterpret_cast<uint4*>(out + pos * C + c8 * 8) = o;
+}
+
+// AvgPool3d((2,7,7), stride 1) on a T3 x 7 x 7 map -> (T3-1) x 1 x 1, squeeze, mean over time (i3d_net.py:258-264):
+// feature[c] = 1/(T3-1) * sum_{t'} 1/98 * sum_{dt<2,h,w} x[t'+dt][h][w][c].   One block per clip, thread = channel.
+__global__ void i3d_head_kernel(const __half* __restrict__ in, DVol v, int C, float* __restrict__ out) {
+    const int b = blockIdx.x;
+    const int T3 = v.t1 - v.t0;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = 0.f;
+        for (int t = 0; t < T3; ++t) {
+            float plane = 0.f;
+            for (int hh = 0; hh < 7; ++hh)
+                for (int w = 0; w < 7; ++w) {
+                    const int64_t r = ((int64_t(b) * v.Tp + t + v.t0) * v.Hp + hh + v.h0) * v.Wp + w + v.w0;
+                    plane += __half2float(in[r * C + c]);
+                }
+            const float wgt = (t == 0 || t == T3 - 1) ? 1.f : 2.f;    // interior planes sit in two (2,7,7) windows
+            acc += wgt * plane;
+        }
+        out[int64_t(b) * C + c] = acc / (98.f * float(T3 - 1));
+    }
+}
+
+// diagnostic: valid region of a bordered channels-last volume -> fp32 NCTHW
+__global__ void unpack_ndhwc_kernel(const __half* __restrict__ in, DVol v, int ld, int c_off, int c_cnt,
+                                    float* __restrict__ out) {
+    const int T = v.t1 - v.t0, H = v.h1 - v.h0, W = v.w1 - v.w0;
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(v.n) * c_cnt * T * H * W;
+    if (idx >= total) return;
+    const int w = int(idx % W);
+    const int hh = int((idx / W) % H);
+    const int t = int((idx / (int64_t(W) * H)) % T);
+    const int c = int((idx / (int64_t(W) * H * T)) % c_cnt);
+    const int b = int(idx / (int64_t(W) * H * T * c_cnt));
+    const int64_t r = ((int64_t(b) * v.Tp + t + v.t0) * v.Hp + hh + v.h0) * v.Wp + w + v.w0;
+    out[idx] = __half2float(in[r * ld + c_off + c]);
+}
+
+}  // namespace
+
+// the host-side Vol in i3d.cu has the same leading fields; these launchers take it by const reference there
+struct VolHost {
+    int n, Tp, Hp, Wp, t0, t1, h0, h1, w0, w1;
+};
+static DVol to_dev(const void* p) {
+    const VolHost* v = static_cast<const VolHost*>(p);
+    return DVol{v->n, v->Tp, v->Hp, v->Wp, v->t0, v->t1, v->h0, v->h1, v->w0, v->w1};
+}
+
+int launch_i3d_phase_pack_f32(const float* x, int n, int C, int T, __half* out, int Tq, cudaStream_t s) {
+    const int64_t total = int64_t(n) * Tq * 115 * 115;
+    i3d_phase_pack_f32_kernel<<<nblocks(total, 256), 256, 0, s>>>(x, n, C, T, out, Tq);
+    VF_CUDA(cudaGetLastError());
+    return VF_OK;
+}
+int launch_maxpool3d_raw(const __half* in, const void* vi, __half* out, const void* vo, int C, int kt, int kh, int kw,
+                         int st, int sh, int sw, int pt, int ph, int pw, cudaStream_t s) {
+    if (C % 8) return fail(VF_ERR_INVALID, "maxpool3d: C=%d must be a multiple of 8", C);
+    const DVol a = to_dev(vi), b = to_dev(vo);
+    const int64_t total = int64_t(b.n) * b.Tp * b.Hp * b.Wp * (C / 8);
+    maxpool3d_kernel<<<nblocks(total, 256), 256, 0, s>>>(in, a, out, b, C, kt, kh, kw, st, sh, sw, pt, ph, pw);
+    VF_CUDA(cudaGetLastError());
+    return VF_OK;
+}
+int launch_i3d_head_raw(const __half* in, const void* vi, int C, float* out, cudaStream_t s) {
+    const DVol a = to_dev(vi);
+    i3d_head_kernel<<<a.n, 256, 0, s>>>(in, a, C, out);
+    VF_CUDA(cudaGetLastError());
+    return VF_OK;
+}
+int launch_unpack_ndhwc_raw(const __half* in, const void* vi, int C, int c_off, int c_cnt, int ld, float* out,
+                            cudaStream_t s) {
+    const DVol a = to_dev(vi);
+    const int64_t total = int64_t(a.n) * c_cnt * (a.t1 - a.t0) * (a.h1 - a.h0) * (a.w1 - a.w0);
+    (void)C;
+    unpack_ndhwc_kernel<<<nblocks(total, 256), 256, 0, s>>>(in, a, ld, c_off, c_cnt, out);
+    VF_CUDA(cudaGetLastError());
+    return VF_OK;
+}
+
+}  // namespace vf

@@ -44,6 +44,25 @@ struct GemmEpi {
 };
 int gemm_f16(const __half* A, int lda, const __half* B, int ldb, int M, int N, int K, const GemmEpi& ep,
              cudaStream_t stream);
+
+// ---- shifted-row ("implicit GEMM") convolution on the same kernel.
+// Activations live channels-last in a zero-bordered volume [n][Tp][Hp][Wp][C] flattened to P rows of C channels.
+// A filter tap (dt,dh,dw) is then a constant row shift of the whole matrix, and because consecutive w positions are
+// consecutive rows, the kw taps of one (dt,dh) form ONE contiguous run of kw*C elements: the A operand of tap j is
+// the overlapping-row view  A_j[p, 0:k_per_tap] = X[(p + tap_off[j]) * C : ... + k_per_tap].
+// Rows whose position lies outside the valid region [t0,t1)x[h0,h1)x[w0,w1) are written as zeros (they are the
+// zero padding the next layer reads).
+struct ConvGeom {
+    int ntaps;          // number of (dt,dh) taps (1 for a 1x1x1 conv)
+    int k_per_tap;      // contiguous K elements per tap (kw * C)
+    int tap_off[64];    // row shift of each tap (includes the shift to the first kw tap)
+    int mask;           // 1: zero the rows outside the valid region
+    int Tp, Hp, Wp;     // padded volume extents (rows per sample = Tp*Hp*Wp)
+    int t0, t1, h0, h1, w0, w1;
+};
+// X: [P, C] fp16 (row pitch C), Wt: [N, ntaps*k_per_tap] fp16, output rows = P
+int conv_gemm_f16(const __half* X, int C, int64_t P, const __half* Wt, int N, const ConvGeom& g, const GemmEpi& ep,
+                  cudaStream_t stream);
 int device_sm_count();
 
 // ---- elementwise / reduction kernels

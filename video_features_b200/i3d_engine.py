@@ -1,0 +1,98 @@
+"""I3D feature extractor handle: stands where the reference keeps ``I3D(num_classes=400, modality=...)`` with its
+checkpoint loaded (models/i3d/extract_i3d.py:109-118); ``engine(x, features=True)`` mirrors ``model(x, features=True)``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict
+
+import numpy as np
+import torch
+
+from ._lib import I3D_UNITS, I3DWeights, check, lib
+
+_MIXED = ["mixed_3b", "mixed_3c", "mixed_4b", "mixed_4c", "mixed_4d", "mixed_4e", "mixed_4f", "mixed_5b", "mixed_5c"]
+
+
+def unit_names():
+    names = ["conv3d_1a_7x7", "conv3d_2b_1x1", "conv3d_2c_3x3"]
+    for m in _MIXED:
+        names += [f"{m}.branch_0", f"{m}.branch_1.0", f"{m}.branch_1.1", f"{m}.branch_2.0", f"{m}.branch_2.1",
+                  f"{m}.branch_3.1"]
+    return names
+
+
+class I3DEngine:
+    """``state_dict``: the reference checkpoint layout (i3d_rgb.pt / i3d_flow.pt keys)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], modality: str = "rgb", device: int = 0,
+                 max_stacks: int = 4, max_T: int = 64):
+        if not torch.cuda.is_available():
+            raise RuntimeError("I3DEngine needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.modality = modality
+        self.cin = 3 if modality == "rgb" else 2
+        self.device = torch.device("cuda", device)
+        keep = []
+
+        def arr(key):
+            if key not in state_dict:
+                raise KeyError(f"I3D checkpoint is missing '{key}'")
+            a = np.ascontiguousarray(state_dict[key].detach().to("cpu", torch.float32).numpy())
+            keep.append(a)
+            return a, a.ctypes.data_as(C.POINTER(C.c_float))
+
+        w = I3DWeights()
+        names = unit_names()
+        assert len(names) == I3D_UNITS
+        for i, n in enumerate(names):
+            wa, wp = arr(f"{n}.conv3d.weight")
+            u = w.units[i]
+            u.w = wp
+            u.cout, u.cin, u.k = int(wa.shape[0]), int(wa.shape[1]), int(wa.shape[2])
+            u.bn_w = arr(f"{n}.batch3d.weight")[1]
+            u.bn_b = arr(f"{n}.batch3d.bias")[1]
+            u.bn_mean = arr(f"{n}.batch3d.running_mean")[1]
+            u.bn_var = arr(f"{n}.batch3d.running_var")[1]
+        h = C.c_void_p()
+        check(lib().vf_i3d_create(C.byref(h), C.byref(w), self.cin, device, max_stacks, max_T))
+        self._h = h
+        del keep
+
+    def __call__(self, x: torch.Tensor, features: bool = True) -> torch.Tensor:
+        """x (B, C, T, 224, 224) float on this device, values in [-1, 1] -> (B, 1024) float32."""
+        if not features:
+            raise NotImplementedError("only features=True (the extraction path) is built")
+        if not x.is_cuda:
+            raise RuntimeError("I3DEngine expects CUDA input (no CPU fallback)")
+        x = x.to(torch.float32).contiguous()
+        assert x.dim() == 5 and x.shape[1] == self.cin and tuple(x.shape[3:]) == (224, 224), x.shape
+        out = torch.empty((x.shape[0], 1024), device=x.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(lib().vf_i3d_forward_f32(self._h, x.data_ptr(), x.shape[0], x.shape[2], out.data_ptr(),
+                                           torch.cuda.current_stream().cuda_stream))
+        return out
+
+    def read_stage(self, stage: int) -> torch.Tensor:
+        """Diagnostics: a retained internal activation of the last forward as fp32 (n, C, T, H, W)."""
+        dims = (C.c_int * 5)()
+        check(lib().vf_i3d_read_stage(self._h, stage, None, 0, dims, None))
+        out = torch.empty(tuple(dims), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(lib().vf_i3d_read_stage(self._h, stage, out.data_ptr(), out.numel(), dims,
+                                          torch.cuda.current_stream().cuda_stream))
+        return out
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().vf_i3d_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().vf_i3d_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
