@@ -132,6 +132,12 @@ int vf_i3d_create(vf_i3d_t** out, const vf_i3d_weights* w, int in_channels, int 
 int vf_i3d_destroy(vf_i3d_t* h);
 /* clips: n x C x T x 224 x 224 fp32 on the device (the tensor the reference passes to I3D) -> out n x 1024 fp32. */
 int vf_i3d_forward_f32(vf_i3d_t* h, const float* clips, int n, int T, float* out, void* stream);
+/* rgb stream with the T2 transform fused (extract_i3d.py:62-66): frames n x T x Hr x Wr x 3 uint8 on the device,
+ * already resized (vf_resize_u8, bilinear, short side 256) -> TensorCenterCrop(224) -> 2x/255-1 -> I3D. */
+int vf_i3d_forward_u8(vf_i3d_t* h, const uint8_t* frames, int n, int T, int Hr, int Wr, float* out, void* stream);
+/* flow stream with the T3 transform fused (extract_i3d.py:67-73): flow n x T x 2 x H x W fp32 on the device (the RAFT
+ * output, still padded) -> crop 224 -> clamp(+-20) -> 128+255/40 f -> round -> 2x/255-1 -> I3D. */
+int vf_i3d_forward_flow(vf_i3d_t* h, const float* flow, int n, int T, int H, int W, float* out, void* stream);
 /* Diagnostics: copy a retained internal activation (0: conv3d_1a, 1: conv3d_2c, 3: mixed_5b, 4: mixed_5c) of the
  * last forward to fp32 NCTHW; dims5 receives (n, C, T, H, W); out == NULL only queries the shape. */
 int vf_i3d_read_stage(vf_i3d_t* h, int stage, float* out, int64_t capacity, int* dims5, void* stream);

@@ -73,3 +73,39 @@ def test_i3d_reference_checkpoint_vs_oracle_and_golden(cuda_device, modality):
     print(f"{modality} real weights T=64: rel-L2 {rel:.3e} max {mx:.3e}")
     assert rel < 1e-3
     eng.close()
+
+
+def test_i3d_fused_stream_transforms(cuda_device):
+    """forward_frames_u8 / forward_flow == oracle transform (extract_i3d.py:62-73) + oracle net on the same data,
+    including the reference's quirks: floor-offset crop, +20 px flow quantised to 256."""
+    from oracle import i3d_net
+    from video_features_b200.i3d_engine import I3DEngine
+    g = torch.Generator().manual_seed(3)
+    # rgb: 12 resized frames 256x341 (the 4:3 sample geometry)
+    sd = i3d_net.synthetic_state_dict("rgb", 1)
+    frames = torch.randint(0, 256, (1, 12, 256, 341, 3), dtype=torch.uint8, generator=g)
+    eng = I3DEngine(sd, "rgb", 0, max_stacks=1, max_T=16)
+    y = eng.forward_frames_u8(frames.to(cuda_device))
+    x = i3d_net.rgb_transform(frames[0].permute(0, 3, 1, 2).float())
+    ref = _oracle_gpu(sd, x, cuda_device)
+    rel, mx = _rel(y, ref)
+    print(f"rgb u8 path: {rel:.3e} {mx:.3e}")
+    assert rel < 1e-3 and mx < 1e-3
+    # the fused transform must equal transform-then-forward bit for bit
+    assert torch.equal(y, eng(x.to(cuda_device)))
+    eng.close()
+    # flow: values beyond +-20, exact +-20 and half-way quantisation points
+    sdf = i3d_net.synthetic_state_dict("flow", 2)
+    flow = torch.randn(1, 12, 2, 256, 344, generator=g) * 12
+    flow[0, 0, 0, 20:30, 70:90] = 20.0
+    flow[0, 1, 1, 40:50, 70:90] = -20.0
+    flow[0, 2, 0, 60:70, 70:90] = (0.5 - 128) * 40 / 255      # 128 + 6.375 f lands on x.5
+    engf = I3DEngine(sdf, "flow", 0, max_stacks=1, max_T=16)
+    yf = engf.forward_flow(flow.to(cuda_device))
+    xf = i3d_net.flow_transform(flow[0])
+    reff = _oracle_gpu(sdf, xf, cuda_device)
+    rel, mx = _rel(yf, reff)
+    print(f"flow path: {rel:.3e} {mx:.3e}")
+    assert rel < 1e-3 and mx < 1e-3
+    assert torch.equal(yf, engf(xf.to(cuda_device)))
+    engf.close()

@@ -45,6 +45,10 @@ struct ConvUnit {
 
 // kernels (i3d_kernels.cu); volumes are passed as pointers to the 10 leading ints of Vol
 int launch_i3d_phase_pack_f32(const float* x, int n, int C, int T, __half* out, int Tq, cudaStream_t s);
+int launch_i3d_phase_pack_u8(const uint8_t* frames, int n, int T, int Hr, int Wr, int cy, int cx, __half* out, int Tq,
+                             cudaStream_t s);
+int launch_i3d_phase_pack_flow(const float* flow, int n, int T, int H, int W, int cy, int cx, __half* out, int Tq,
+                               cudaStream_t s);
 int launch_maxpool3d_raw(const __half* in, const void* vi, __half* out, const void* vo, int C, int kt, int kh, int kw,
                          int st, int sh, int sw, int pt, int ph, int pw, cudaStream_t s);
 int launch_i3d_head_raw(const __half* in, const void* vi, int C, float* out, cudaStream_t s);
@@ -264,55 +268,98 @@ int vf_i3d_destroy(vf_i3d_t* h) {
     return VF_OK;
 }
 
-int vf_i3d_forward_f32(vf_i3d_t* h, const float* clips, int n, int T, float* out, void* stream) {
-    if (!h || (n > 0 && (!clips || !out))) return fail(VF_ERR_INVALID, "i3d_forward: null argument");
-    if (n <= 0) return VF_OK;
+}  // extern "C"
+
+// everything after the stem's phase volume h->s0 has been filled for nb clips of T frames
+static int i3d_trunk(vf_i3d* h, int nb, int T, float* out, cudaStream_t s) {
+    const int T1 = T / 2, Tq = T1 + 3;            // torch conv3d, pad (2,3), stride 2: floor((T-2)/2)+1
+    const Vol v0{nb, Tq, 115, 115, 1, 1 + T1, 1, 113, 1, 113};
+    VF_TRY(run_unit(h, h->units[0], h->s0, 8 * h->cin, v0, h->a1, 64, s));
+    // ---- maxPool3d_2a (1,3,3)/(1,2,2), SAME pad (0,1) on H,W
+    const Vol v1 = bordered(nb, T1, 56, 56);
+    VF_TRY(launch_maxpool3d(h->a1, v0, h->p1, v1, 64, 1, 3, 3, 1, 2, 2, 0, 0, 0, s));
+    VF_TRY(run_unit(h, h->units[1], h->p1, 64, v1, h->c2b, 64, s));
+    VF_TRY(run_unit(h, h->units[2], h->c2b, 64, v1, h->c2c, 192, s));
+    // ---- maxPool3d_3a
+    const Vol v2 = bordered(nb, T1, 28, 28);
+    VF_TRY(launch_maxpool3d(h->c2c, v1, h->bufA, v2, 192, 1, 3, 3, 1, 2, 2, 0, 0, 0, s));
+    VF_TRY(mixed_block(h, 0, h->bufA, v2, h->bufB, s));     // 3b -> 256
+    VF_TRY(mixed_block(h, 1, h->bufB, v2, h->bufA, s));     // 3c -> 480
+    // ---- maxPool3d_4a 3x3x3 / 2, SAME pad (0,1)
+    const int T2 = ceil_div(T1, 2);
+    const Vol v3 = bordered(nb, T2, 14, 14);
+    VF_TRY(launch_maxpool3d(h->bufA, v2, h->bufB, v3, 480, 3, 3, 3, 2, 2, 2, 0, 0, 0, s));
+    VF_TRY(mixed_block(h, 2, h->bufB, v3, h->bufA, s));     // 4b -> 512
+    VF_TRY(mixed_block(h, 3, h->bufA, v3, h->bufB, s));     // 4c
+    VF_TRY(mixed_block(h, 4, h->bufB, v3, h->bufA, s));     // 4d
+    VF_TRY(mixed_block(h, 5, h->bufA, v3, h->bufB, s));     // 4e -> 528
+    VF_TRY(mixed_block(h, 6, h->bufB, v3, h->bufA, s));     // 4f -> 832
+    // ---- maxPool3d_5a 2x2x2 / 2, no padding, ceil mode
+    const int T3 = ceil_div(T2, 2);
+    if (T3 < 2) return fail(VF_ERR_INVALID, "i3d_forward: T=%d leaves %d temporal positions for the (2,7,7) pool", T, T3);
+    const Vol v4 = bordered(nb, T3, 7, 7);
+    VF_TRY(launch_maxpool3d(h->bufA, v3, h->bufB, v4, 832, 2, 2, 2, 2, 2, 2, 0, 0, 0, s));
+    VF_TRY(mixed_block(h, 7, h->bufB, v4, h->bufA, s));     // 5b -> 832
+    VF_TRY(mixed_block(h, 8, h->bufA, v4, h->bufB, s));     // 5c -> 1024
+    // ---- AvgPool3d((2,7,7),1) + mean over time
+    VF_TRY(launch_i3d_head(h->bufB, v4, 1024, out, s));
+    h->launches += 5;
+    h->stages[0] = {h->a1, v0, 64};
+    h->stages[1] = {h->c2c, v1, 192};
+    h->stages[2] = {nullptr, v2, 480};
+    h->stages[3] = {h->bufA, v3, 832};
+    h->stages[4] = {h->bufB, v4, 1024};
+    return VF_OK;
+}
+
+static int i3d_check(vf_i3d* h, const void* in, int n, int T, const void* out, int need_cin) {
+    if (!h || (n > 0 && (!in || !out))) return fail(VF_ERR_INVALID, "i3d_forward: null argument");
     if (T < 10 || T > h->max_T) return fail(VF_ERR_INVALID, "i3d_forward: T=%d outside [10, %d]", T, h->max_T);
+    if (need_cin && h->cin != need_cin) return fail(VF_ERR_INVALID, "i3d_forward: handle was created for %d input channels", h->cin);
+    return VF_OK;
+}
+
+extern "C" {
+
+int vf_i3d_forward_f32(vf_i3d_t* h, const float* clips, int n, int T, float* out, void* stream) {
+    VF_TRY(i3d_check(h, clips, n, T, out, 0));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     VF_CUDA(cudaSetDevice(h->device));
     for (int b0 = 0; b0 < n; b0 += h->max_stacks) {
         const int nb = (n - b0 < h->max_stacks) ? (n - b0) : h->max_stacks;
-        const float* x = clips + size_t(b0) * h->cin * T * 224 * 224;
-        // ---- stem: phase-pack, 7x7x7/2 conv as 16-tap shifted GEMM
-        const int T1 = T / 2, Tq = T1 + 3;            // torch conv3d, pad (2,3), stride 2: floor((T-2)/2)+1
-        VF_TRY(launch_i3d_phase_pack_f32(x, nb, h->cin, T, h->s0, Tq, s));
+        VF_TRY(launch_i3d_phase_pack_f32(clips + size_t(b0) * h->cin * T * 224 * 224, nb, h->cin, T, h->s0, T / 2 + 3, s));
         h->launches += 1;
-        const Vol v0{nb, Tq, 115, 115, 1, 1 + T1, 1, 113, 1, 113};
-        VF_TRY(run_unit(h, h->units[0], h->s0, 8 * h->cin, v0, h->a1, 64, s));
-        // ---- maxPool3d_2a (1,3,3)/(1,2,2), SAME pad (0,1) on H,W
-        const Vol v1 = bordered(nb, T1, 56, 56);
-        VF_TRY(launch_maxpool3d(h->a1, v0, h->p1, v1, 64, 1, 3, 3, 1, 2, 2, 0, 0, 0, s));
-        VF_TRY(run_unit(h, h->units[1], h->p1, 64, v1, h->c2b, 64, s));
-        VF_TRY(run_unit(h, h->units[2], h->c2b, 64, v1, h->c2c, 192, s));
-        // ---- maxPool3d_3a
-        const Vol v2 = bordered(nb, T1, 28, 28);
-        VF_TRY(launch_maxpool3d(h->c2c, v1, h->bufA, v2, 192, 1, 3, 3, 1, 2, 2, 0, 0, 0, s));
-        VF_TRY(mixed_block(h, 0, h->bufA, v2, h->bufB, s));     // 3b -> 256
-        VF_TRY(mixed_block(h, 1, h->bufB, v2, h->bufA, s));     // 3c -> 480
-        // ---- maxPool3d_4a 3x3x3 / 2, SAME pad (0,1)
-        const int T2 = ceil_div(T1, 2);
-        const Vol v3 = bordered(nb, T2, 14, 14);
-        VF_TRY(launch_maxpool3d(h->bufA, v2, h->bufB, v3, 480, 3, 3, 3, 2, 2, 2, 0, 0, 0, s));
-        VF_TRY(mixed_block(h, 2, h->bufB, v3, h->bufA, s));     // 4b -> 512
-        VF_TRY(mixed_block(h, 3, h->bufA, v3, h->bufB, s));     // 4c
-        VF_TRY(mixed_block(h, 4, h->bufB, v3, h->bufA, s));     // 4d
-        VF_TRY(mixed_block(h, 5, h->bufA, v3, h->bufB, s));     // 4e -> 528
-        VF_TRY(mixed_block(h, 6, h->bufB, v3, h->bufA, s));     // 4f -> 832
-        // ---- maxPool3d_5a 2x2x2 / 2, no padding, ceil mode
-        const int T3 = ceil_div(T2, 2);
-        const Vol v4 = bordered(nb, T3, 7, 7);
-        VF_TRY(launch_maxpool3d(h->bufA, v3, h->bufB, v4, 832, 2, 2, 2, 2, 2, 2, 0, 0, 0, s));
-        VF_TRY(mixed_block(h, 7, h->bufB, v4, h->bufA, s));     // 5b -> 832
-        VF_TRY(mixed_block(h, 8, h->bufA, v4, h->bufB, s));     // 5c -> 1024
-        if (T3 < 2) return fail(VF_ERR_INVALID, "i3d_forward: T=%d leaves %d temporal positions for the (2,7,7) pool", T, T3);
-        // ---- AvgPool3d((2,7,7),1) + mean over time
-        VF_TRY(launch_i3d_head(h->bufB, v4, 1024, out + size_t(b0) * 1024, s));
-        h->launches += 6;
-        h->stages[0] = {h->a1, v0, 64};
-        h->stages[1] = {h->c2c, v1, 192};
-        h->stages[2] = {nullptr, v2, 480};     // overwritten by later blocks; only valid when read right after
-        h->stages[3] = {h->bufA, v3, 832};     // (4f output is clobbered by 5b; see vf_i3d_read_stage)
-        h->stages[4] = {h->bufB, v4, 1024};
+        VF_TRY(i3d_trunk(h, nb, T, out + size_t(b0) * 1024, s));
+    }
+    return VF_OK;
+}
+
+int vf_i3d_forward_u8(vf_i3d_t* h, const uint8_t* frames, int n, int T, int Hr, int Wr, float* out, void* stream) {
+    VF_TRY(i3d_check(h, frames, n, T, out, 3));
+    if (Hr < 224 || Wr < 224) return fail(VF_ERR_INVALID, "i3d_forward_u8: %dx%d frames are smaller than the 224 crop", Hr, Wr);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    VF_CUDA(cudaSetDevice(h->device));
+    const int cy = (Hr - 224) / 2, cx = (Wr - 224) / 2;     // TensorCenterCrop: floor offsets (transforms.py:14-15)
+    for (int b0 = 0; b0 < n; b0 += h->max_stacks) {
+        const int nb = (n - b0 < h->max_stacks) ? (n - b0) : h->max_stacks;
+        VF_TRY(launch_i3d_phase_pack_u8(frames + size_t(b0) * T * Hr * Wr * 3, nb, T, Hr, Wr, cy, cx, h->s0, T / 2 + 3, s));
+        h->launches += 1;
+        VF_TRY(i3d_trunk(h, nb, T, out + size_t(b0) * 1024, s));
+    }
+    return VF_OK;
+}
+
+int vf_i3d_forward_flow(vf_i3d_t* h, const float* flow, int n, int T, int H, int W, float* out, void* stream) {
+    VF_TRY(i3d_check(h, flow, n, T, out, 2));
+    if (H < 224 || W < 224) return fail(VF_ERR_INVALID, "i3d_forward_flow: %dx%d flow is smaller than the 224 crop", H, W);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    VF_CUDA(cudaSetDevice(h->device));
+    const int cy = (H - 224) / 2, cx = (W - 224) / 2;
+    for (int b0 = 0; b0 < n; b0 += h->max_stacks) {
+        const int nb = (n - b0 < h->max_stacks) ? (n - b0) : h->max_stacks;
+        VF_TRY(launch_i3d_phase_pack_flow(flow + size_t(b0) * T * 2 * H * W, nb, T, H, W, cy, cx, h->s0, T / 2 + 3, s));
+        h->launches += 1;
+        VF_TRY(i3d_trunk(h, nb, T, out + size_t(b0) * 1024, s));
     }
     return VF_OK;
 }

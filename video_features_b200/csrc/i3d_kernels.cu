@@ -43,6 +43,90 @@ __global__ void i3d_phase_pack_f32_kernel(const float* __restrict__ x, int n, in
     }
 }
 
+// Fused T2 transform + phase packing straight from the resized uint8 frames (extract_i3d.py:62-66 rgb stream):
+// frames [n][T][Hr][Wr][3] uint8 -> TensorCenterCrop(224) at (cy,cx) -> 2*x/255 - 1 (fp32, the reference's operation
+// order) -> fp16 phase volume.  Channel order is the decoder's (the reference never swaps BGR).
+__global__ void i3d_phase_pack_u8_kernel(const uint8_t* __restrict__ frames, int n, int T, int Hr, int Wr, int cy, int cx,
+                                         __half* __restrict__ out, int Tq) {
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(n) * Tq * 115 * 115;
+    if (idx >= total) return;
+    const int wq = int(idx % 115);
+    const int hq = int((idx / 115) % 115);
+    const int tq = int((idx / (115 * 115)) % Tq);
+    const int b = int(idx / (int64_t(115) * 115 * Tq));
+    __align__(16) __half vals[24];
+    const int w0 = 2 * (wq - 1);
+#pragma unroll
+    for (int pt = 0; pt < 2; ++pt) {
+        const int t = 2 * (tq - 1) + pt;
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+            const int hh = 2 * (hq - 1) + ph;
+            const bool ok = (t >= 0) && (t < T) && (hh >= 0) && (hh < 224) && (w0 >= 0) && (w0 < 224);
+            const uint8_t* p = frames + (((int64_t(b) * T + (ok ? t : 0)) * Hr + cy + (ok ? hh : 0)) * Wr + cx + (ok ? w0 : 0)) * 3;
+#pragma unroll
+            for (int pw = 0; pw < 2; ++pw)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float v = 0.f;
+                    if (ok) v = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, float(__ldg(p + pw * 3 + c))), 255.0f), 1.0f);
+                    vals[((pt * 2 + ph) * 2 + pw) * 3 + c] = __float2half_rn(v);
+                }
+        }
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + idx * 24);
+    const uint4* v4 = reinterpret_cast<const uint4*>(vals);
+    o[0] = v4[0]; o[1] = v4[1]; o[2] = v4[2];
+}
+
+// Fused T3 transform + phase packing for the flow stream (extract_i3d.py:67-73): flow [n][T][2][H][W] fp32 (the RAFT
+// output, still padded) -> crop 224 at (cy,cx) -> clamp(+-20) -> 128 + 255/40*f -> round half-to-even (+20 -> 256, not
+// clipped, as the reference) -> 2*x/255 - 1 -> fp16 phase volume with 16 channels.
+__global__ void i3d_phase_pack_flow_kernel(const float* __restrict__ flow, int n, int T, int H, int W, int cy, int cx,
+                                           __half* __restrict__ out, int Tq) {
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(n) * Tq * 115 * 115;
+    if (idx >= total) return;
+    const int wq = int(idx % 115);
+    const int hq = int((idx / 115) % 115);
+    const int tq = int((idx / (115 * 115)) % Tq);
+    const int b = int(idx / (int64_t(115) * 115 * Tq));
+    __align__(16) __half vals[16];
+    const int w0 = 2 * (wq - 1);
+#pragma unroll
+    for (int pt = 0; pt < 2; ++pt) {
+        const int t = 2 * (tq - 1) + pt;
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+            const int hh = 2 * (hq - 1) + ph;
+            const bool ok = (t >= 0) && (t < T) && (hh >= 0) && (hh < 224) && (w0 >= 0) && (w0 < 224);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float2 f = make_float2(0.f, 0.f);
+                bool live = ok;
+                if (ok) {
+                    const float* p = flow + (((int64_t(b) * T + t) * 2 + c) * H + cy + hh) * W + cx + w0;
+                    f.x = __ldg(p); f.y = __ldg(p + 1);
+                }
+#pragma unroll
+                for (int pw = 0; pw < 2; ++pw) {
+                    float v = pw ? f.y : f.x;
+                    if (live) {
+                        v = fminf(fmaxf(v, -20.0f), 20.0f);
+                        v = rintf(__fadd_rn(128.0f, __fmul_rn(6.375f, v)));
+                        v = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, v), 255.0f), 1.0f);
+                    }
+                    vals[((pt * 2 + ph) * 2 + pw) * 2 + c] = __float2half_rn(v);
+                }
+            }
+        }
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + idx * 16);
+    const uint4* v4 = reinterpret_cast<const uint4*>(vals);
+    o[0] = v4[0]; o[1] = v4[1];
+}
+
 // Max pool over the VALID region of the input volume with ZERO padding semantics (MaxPool3dTFPadding: ConstantPad3d(0)
 // then ceil-mode MaxPool3d; inputs are post-ReLU so 0 never wins wrongly).  One thread = one output position x 8
 // channels; border positions of the output volume are written as zeros.
@@ -94,9 +178,9 @@ __global__ void maxpool3d_kernel(const __half* __restrict__ in, DVol vi, __half*
 // AvgPool3d((2,7,7), stride 1) on a T3 x 7 x 7 map -> (T3-1) x 1 x 1, squeeze, mean over time (i3d_net.py:258-264):
 // feature[c] = 1/(T3-1) * sum_{t'} 1/98 * sum_{dt<2,h,w} x[t'+dt][h][w][c].   One block per clip, thread = channel.
 __global__ void i3d_head_kernel(const __half* __restrict__ in, DVol v, int C, float* __restrict__ out) {
-    const int b = blockIdx.x;
+    const int b = blockIdx.y;
     const int T3 = v.t1 - v.t0;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
         float acc = 0.f;
         for (int t = 0; t < T3; ++t) {
             float plane = 0.f;
@@ -145,6 +229,20 @@ int launch_i3d_phase_pack_f32(const float* x, int n, int C, int T, __half* out, 
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
+int launch_i3d_phase_pack_u8(const uint8_t* frames, int n, int T, int Hr, int Wr, int cy, int cx, __half* out, int Tq,
+                             cudaStream_t s) {
+    const int64_t total = int64_t(n) * Tq * 115 * 115;
+    i3d_phase_pack_u8_kernel<<<nblocks(total, 256), 256, 0, s>>>(frames, n, T, Hr, Wr, cy, cx, out, Tq);
+    VF_CUDA(cudaGetLastError());
+    return VF_OK;
+}
+int launch_i3d_phase_pack_flow(const float* flow, int n, int T, int H, int W, int cy, int cx, __half* out, int Tq,
+                               cudaStream_t s) {
+    const int64_t total = int64_t(n) * Tq * 115 * 115;
+    i3d_phase_pack_flow_kernel<<<nblocks(total, 256), 256, 0, s>>>(flow, n, T, H, W, cy, cx, out, Tq);
+    VF_CUDA(cudaGetLastError());
+    return VF_OK;
+}
 int launch_maxpool3d_raw(const __half* in, const void* vi, __half* out, const void* vo, int C, int kt, int kh, int kw,
                          int st, int sh, int sw, int pt, int ph, int pw, cudaStream_t s) {
     if (C % 8) return fail(VF_ERR_INVALID, "maxpool3d: C=%d must be a multiple of 8", C);
@@ -156,7 +254,7 @@ int launch_maxpool3d_raw(const __half* in, const void* vi, __half* out, const vo
 }
 int launch_i3d_head_raw(const __half* in, const void* vi, int C, float* out, cudaStream_t s) {
     const DVol a = to_dev(vi);
-    i3d_head_kernel<<<a.n, 256, 0, s>>>(in, a, C, out);
+    i3d_head_kernel<<<dim3((C + 63) / 64, a.n), 64, 0, s>>>(in, a, C, out);
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }

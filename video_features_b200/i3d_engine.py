@@ -72,6 +72,28 @@ class I3DEngine:
                                            torch.cuda.current_stream().cuda_stream))
         return out
 
+    def forward_frames_u8(self, frames: torch.Tensor) -> torch.Tensor:
+        """rgb stream from resized uint8 frames (n, T, Hr, Wr, 3) on this device; crop/scale/permute fused."""
+        assert frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 5 and frames.shape[4] == 3
+        frames = frames.contiguous()
+        n, T, Hr, Wr, _ = frames.shape
+        out = torch.empty((n, 1024), device=frames.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(lib().vf_i3d_forward_u8(self._h, frames.data_ptr(), n, T, Hr, Wr, out.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream))
+        return out
+
+    def forward_flow(self, flow: torch.Tensor) -> torch.Tensor:
+        """flow stream from raw optical flow (n, T, 2, H, W) fp32 on this device; T3 transform fused."""
+        assert flow.is_cuda and flow.dtype == torch.float32 and flow.dim() == 5 and flow.shape[2] == 2
+        flow = flow.contiguous()
+        n, T, _, H, W = flow.shape
+        out = torch.empty((n, 1024), device=flow.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(lib().vf_i3d_forward_flow(self._h, flow.data_ptr(), n, T, H, W, out.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream))
+        return out
+
     def read_stage(self, stage: int) -> torch.Tensor:
         """Diagnostics: a retained internal activation of the last forward as fp32 (n, C, T, H, W)."""
         dims = (C.c_int * 5)()
