@@ -26,6 +26,8 @@ extern "C" {
 #define VF_ACT_NONE 0
 #define VF_ACT_QUICKGELU 1 /* x * sigmoid(1.702 x) */
 #define VF_ACT_RELU 2
+#define VF_ACT_SIGMOID 3
+#define VF_ACT_TANH 4
 
 #define VF_FILTER_BILINEAR 2 /* PIL.Image.BILINEAR */
 #define VF_FILTER_BICUBIC 3  /* PIL.Image.BICUBIC  */
@@ -142,6 +144,33 @@ int vf_i3d_forward_flow(vf_i3d_t* h, const float* flow, int n, int T, int H, int
  * last forward to fp32 NCTHW; dims5 receives (n, C, T, H, W); out == NULL only queries the shape. */
 int vf_i3d_read_stage(vf_i3d_t* h, int stage, float* out, int64_t capacity, int* dims5, void* stream);
 int64_t vf_i3d_launch_count(const vf_i3d_t* h);
+
+/* ---- RAFT optical flow: replaces `RAFT()(image1, image2, iters=20, test_mode=True)` + InputPadder
+ * (models/raft/raft_src/raft.py:27-44,115-174; called at models/raft/extract_raft.py:94-104 and
+ * models/i3d/extract_i3d.py:172).  Weights: the checkpoint's tensors by name (keys of raft-sintel.pth without the
+ * "module." prefix), HOST fp32. */
+typedef struct vf_named_tensor {
+    const char* name;
+    const float* data;
+    int64_t numel;
+} vf_named_tensor;
+typedef struct vf_raft vf_raft_t;
+
+/* Workspace is sized for windows of max_frames frames of at most max_h x max_w pixels (before /8 padding). */
+int vf_raft_create(vf_raft_t** out, const vf_named_tensor* tensors, int n_tensors, int device, int max_frames, int max_h,
+                   int max_w);
+int vf_raft_destroy(vf_raft_t* h);
+/* Flow between consecutive frames of a window: frames n_frames x (Hs x Ws x 3 if !chw_layout else 3 x Hs x Ws), uint8
+ * or fp32 in [0,255] on the device, RGB order as given; == model(pad(frames)[:-1], pad(frames)[1:]).
+ * out: (n_frames-1) x 2 x Ho x Wo fp32 with (Ho,Wo) = (Hs,Ws) if unpad (extract_raft.py:101) else the /8-padded size
+ * (extract_i3d.py:172 never unpads; query it with vf_raft_padded_size). */
+int vf_raft_flow(vf_raft_t* h, const void* frames, int is_u8, int chw_layout, int n_frames, int Hs, int Ws, int iters,
+                 int unpad, float* out, void* stream);
+int vf_raft_padded_size(int Hs, int Ws, int* H, int* W);
+/* Diagnostics: internal tensors of the last call as fp32 NCHW at 1/8 resolution.  what: 0 fnet features (all
+ * frames), 1 cnet output (raw), 2 GRU hidden state, 3 low-res flow, 4 last correlation lookup (324 ch). */
+int vf_raft_debug_read(vf_raft_t* h, int what, float* out, int64_t capacity, int* dims4, void* stream);
+int64_t vf_raft_launch_count(const vf_raft_t* h);
 
 #ifdef __cplusplus
 }

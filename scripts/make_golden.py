@@ -183,8 +183,46 @@ def i3d_golden():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "i3d":
     i3d_golden()
+    raft_golden()
 
 
 if __name__ == "__main__" and len(sys.argv) == 1:
     main()
     i3d_golden()
+    raft_golden()
+
+
+def raft_golden():
+    """Reference RAFT module + vendored raft-sintel.pth vs the restated oracle on synthetic moving frames."""
+    import torch
+    sys.path.insert(0, REF)
+    cwd = os.getcwd()
+    os.chdir(REF)
+    try:
+        from models.raft.raft_src.raft import RAFT, InputPadder
+        from oracle import raft_net
+        sd = torch.load("models/raft/checkpoints/raft-sintel.pth", map_location="cpu")
+        net = torch.nn.DataParallel(RAFT(), device_ids=None)
+        net.load_state_dict(sd)
+        net = net.module.eval()
+        d = {}
+        for (h, w, n) in ((128, 160, 3), (270, 480, 2)):
+            fr = raft_net.synthetic_frames(n, h, w, seed=h)
+            padder = InputPadder(fr.shape)
+            x = padder.pad(fr)
+            assert torch.equal(x, raft_net.pad(fr))
+            with torch.no_grad():
+                y_ref = net(x[:-1], x[1:], iters=20)
+            y_or = raft_net.forward(sd, x[:-1], x[1:], 20)
+            rel = float((y_or - y_ref).norm() / y_ref.norm())
+            print(f"raft {h}x{w}: oracle vs reference rel {rel:.2e}; mean |flow| {float(y_ref.abs().mean()):.3f}")
+            assert rel < 1e-4
+            full = padder.unpad(y_ref).numpy().astype(np.float32)
+            d[f"flow_{h}x{w}"] = full if h < 200 else full[:, :, ::3, ::3]      # keep the fixture small
+        np.savez_compressed(os.path.join(OUT, "raft_outputs.npz"), **d)
+    finally:
+        os.chdir(cwd)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "raft":
+    raft_golden()

@@ -1,0 +1,97 @@
+"""RAFT flow through the C ABI against the fp32 oracle (oracle/raft_net.py, pinned bit-for-bit to the reference
+module) and against the reference module's own output (tests/golden/raft_outputs.npz).
+
+Bar: rel-L2 <= 1e-3 and max-abs <= 1e-3 * max|ref| on the flow field.  Needs the reference checkpoint copy
+under checkpoints/ (scripts/fetch_checkpoints.py) -- RAFT with random weights is not a meaningful dynamical system."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import video_features_b200  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CKPT = os.path.join(ROOT, "checkpoints", "raft-sintel.pth")
+
+
+def _err(y, ref):
+    y, ref = y.double().cpu(), ref.double().cpu()
+    return float((y - ref).norm() / ref.norm()), float((y - ref).abs().max() / ref.abs().max())
+
+
+@pytest.fixture(scope="module")
+def raft(cuda_device):
+    if not os.path.exists(CKPT):
+        pytest.skip("reference checkpoint copy not present (scripts/fetch_checkpoints.py)")
+    from video_features_b200.raft_engine import RAFTEngine
+    sd = torch.load(CKPT, map_location="cpu")
+    eng = RAFTEngine(sd, 0, max_frames=5, max_h=272, max_w=480)
+    yield sd, eng
+    eng.close()
+
+
+def test_raft_stages_and_one_iteration(raft, cuda_device):
+    """Encoders, correlation lookup and one GRU step against the oracle's intermediates."""
+    from oracle import raft_net as R
+    sd, eng = raft
+    sdg = {k: v.to(cuda_device) for k, v in R._strip(sd).items()}
+    fr = R.synthetic_frames(3, 128, 160, seed=128)
+    x = fr.to(cuda_device)
+    y1 = eng.flow(x, iters=1, unpad=False)
+    img = 2 * (x / 255.0) - 1.0
+    fmap = R.encoder(sdg, "fnet", img, "instance")
+    e = _err(eng.debug_read(0), fmap)
+    print("fnet features:", e)
+    assert e[0] < 3e-3
+    cnet = R.encoder(sdg, "cnet", img[:-1], "batch")
+    e = _err(eng.debug_read(1), cnet)
+    print("cnet output:", e)
+    assert e[0] < 3e-3
+    # first lookup (coords = grid) against the oracle's pyramid lookup
+    pyr = R.corr_pyramid(fmap[:-1].float(), fmap[1:].float())
+    H8, W8 = 16, 20
+    ys, xs = torch.meshgrid(torch.arange(H8), torch.arange(W8), indexing="ij")
+    coords0 = torch.stack([xs, ys], 0).float()[None].repeat(2, 1, 1, 1).to(cuda_device)
+    look = R.corr_lookup(pyr, coords0)
+    eng.flow(x, iters=1, unpad=False)
+    e = _err(eng.debug_read(4), look)       # (the last lookup of a 1-iteration run is the first one)
+    print("corr lookup:", e)
+    assert e[0] < 5e-3
+    ref1, low1 = R.forward(sd_to(sd, cuda_device), x[:-1], x[1:], 1, return_lowres=True)
+    e = _err(eng.debug_read(3), low1)
+    print("low-res flow after 1 iteration:", e)
+    assert e[0] < 5e-3
+    e = _err(y1, ref1)
+    print("flow_up after 1 iteration:", e)
+    assert e[0] < 5e-3
+
+
+def sd_to(sd, dev):
+    return {k: v.to(dev) for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("h,w,n", [(128, 160, 3), (270, 480, 2)])
+def test_raft_20_iterations_vs_oracle_and_reference_golden(raft, cuda_device, h, w, n):
+    from oracle import raft_net as R
+    sd, eng = raft
+    fr = R.synthetic_frames(n, h, w, seed=h)
+    x = fr.to(cuda_device)
+    y = eng.flow(x, iters=20, unpad=True)
+    xp = R.pad(x)
+    ref = R.unpad(R.forward(sd_to(sd, cuda_device), xp[:-1], xp[1:], 20), h, w)
+    rel, mx = _err(y, ref)
+    print(f"{h}x{w}: vs oracle rel-L2 {rel:.3e} max {mx:.3e}; mean |flow| {float(ref.abs().mean()):.3f}; launches {eng.launch_count}")
+    assert rel < 1e-3 and mx < 1e-3
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "raft_outputs.npz"))[f"flow_{h}x{w}"]
+    got = y.cpu().numpy() if h < 200 else y.cpu().numpy()[:, :, ::3, ::3]
+    rel_g = float(np.linalg.norm(got - gold) / np.linalg.norm(gold))
+    print(f"{h}x{w}: vs reference-module golden rel-L2 {rel_g:.3e}")
+    assert rel_g < 1e-3
+    # uint8 HWC entry == float CHW entry on integer-valued frames
+    y8 = eng.flow(fr.permute(0, 2, 3, 1).contiguous().to(torch.uint8).to(cuda_device), iters=20, unpad=True)
+    assert torch.equal(y8, y)
+    # unpadded window of the padded output
+    yp = eng.flow(x, iters=20, unpad=False)
+    assert torch.equal(R.unpad(yp, h, w), y)

@@ -54,6 +54,10 @@ __device__ __forceinline__ float apply_act(float v, int act) {
         return __fdividef(v, 1.0f + __expf(-1.702f * v));   // x * sigmoid(1.702 x)
     } else if (act == VF_ACT_RELU) {
         return fmaxf(v, 0.0f);
+    } else if (act == VF_ACT_SIGMOID) {
+        return __fdividef(1.0f, 1.0f + __expf(-v));
+    } else if (act == VF_ACT_TANH) {
+        return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * v));   // saturates cleanly to +-1
     }
     return v;
 }

@@ -1,0 +1,534 @@
+// RAFT optical flow (full model, 20 refinement iterations) on the tcgen05 conv-GEMM.
+// Replaces `RAFT()(image1, image2, iters=20, test_mode=True)` (reference: models/raft/raft_src/raft.py:115-174, called at
+// models/raft/extract_raft.py:99 and models/i3d/extract_i3d.py:172) together with InputPadder (raft.py:27-44).
+//
+// Layout: channels-last fp16 rows of zero-bordered 2-D volumes; every convolution is a shifted-row GEMM
+// (conv_gemm_f16): kw taps of one kernel row are one contiguous K run, stride-2 convs run on a space-to-depth
+// ("phase") repack of their input, InstanceNorm (fnet) is a stats + apply pass around the raw conv output,
+// BatchNorm (cnet, eval) is folded into the conv epilogue.  All-pairs correlation is one GEMM per pair
+// (fmap1 . fmap2^T / 16, fp32 out) followed by the 3-level average pooling; the per-iteration lookup gathers the
+// 4 x 9x9 bilinear windows (the reference's transposed window) straight into the motion encoder's operand rows.
+// The GRU state lives in `hx` = [h | inp | motion(126)+pad | flow(2)+pad] (392 columns) so that the 1x5 / 5x1 gate
+// convolutions read one contiguous run per tap; `qx` is the same row with r*h in place of h.
+// The convex-upsampling mask head and the 8x upsample run once, after the last iteration (the reference evaluates
+// them every iteration and discards 19 of the 20 results, raft.py:166-172).
+// fnet runs once per frame (the reference encodes every interior frame twice: as image2 of one pair and image1 of
+// the next; InstanceNorm is per sample, so the features are identical).
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "internal.h"
+#include "raft_kernels.h"
+
+namespace vf {
+
+struct ConvW {       // a convolution prepared for conv_gemm_f16
+    int n_out = 0;          // GEMM N (padded to a multiple of 8)
+    int ntaps = 0, k_per_tap = 0;
+    std::vector<int> dh, dw0;   // per tap: row offset (in kernel rows) and the column shift of its first element
+    __half* w = nullptr;
+    float *scale = nullptr, *bias = nullptr;
+};
+
+static const int HX = 392;   // [h 128 | inp 128 | motion-out 126 + 2 pad | flow 2 + 6 pad]
+static const int CF = 328;   // 324 correlation features + 4 pad
+
+}  // namespace vf
+
+using namespace vf;
+
+struct vf_raft {
+    int device = 0, max_frames = 0, max_h = 0, max_w = 0;
+    std::vector<void*> allocs;
+    // encoders: [0] = fnet (instance norm), [1] = cnet (batch norm folded)
+    struct Enc {
+        ConvW conv1, l1[4], l2c1, l2down, l2[3], l3c1, l3down, l3[3], conv2;
+    } enc[2];
+    ConvW convc1, convc2, convf1, convf2, convm, zr1, q1, zr2, q2, fh1, fh2, mk0, mk2;
+    float* sixteenth = nullptr;      // 1/16 for the correlation scale
+    // workspace
+    __half *s0 = nullptr, *bufA = nullptr, *bufB = nullptr, *bufC = nullptr, *bufD = nullptr, *bufE = nullptr;
+    __half *fmap_b = nullptr, *fmaps = nullptr, *cnet_b = nullptr;
+    double *st_a = nullptr, *st_b = nullptr;
+    float *corr = nullptr, *coords1 = nullptr, *delta = nullptr, *mask = nullptr;
+    __half *corrfeat = nullptr, *c1 = nullptr, *c2f = nullptr, *f1 = nullptr, *flow8 = nullptr, *hx = nullptr, *qx = nullptr,
+           *zr = nullptr, *qb = nullptr, *fh = nullptr, *mk = nullptr;
+    int64_t launches = 0;
+    // geometry of the last call (for debug reads)
+    int last_n = 0, last_H8 = 0, last_W8 = 0, corr_ld = 0, P8 = 0;
+    Vol2 g8e{}, g8u{};
+};
+
+namespace vf {
+
+template <typename Tp>
+static int ralloc(vf_raft* h, Tp** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(Tp));
+    if (e != cudaSuccess) return fail(VF_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(Tp), cudaGetErrorString(e));
+    h->allocs.push_back(q);
+    *p = static_cast<Tp*>(q);
+    return VF_OK;
+}
+
+struct TensorTable {
+    const vf_named_tensor* t; int n;
+    const float* get(const std::string& name, int64_t numel) const {
+        for (int i = 0; i < n; ++i)
+            if (name == t[i].name) return t[i].numel == numel ? t[i].data : nullptr;
+        return nullptr;
+    }
+};
+
+// Generic filter re-layout.  w: [co][ci][kh][kw]; col(dh, dw, c) -> K column or -1.  Output rows padded to n_out.
+static int upload_conv(vf_raft* h, ConvW& cw, const float* w, const float* b, int co, int ci, int kh, int kw, int n_out,
+                       int Ktot, const std::function<int(int, int, int)>& col, const float* bn_scale,
+                       const float* bn_shift, float extra_scale) {
+    std::vector<__half> B(size_t(n_out) * Ktot, __float2half_rn(0.f));
+    for (int o = 0; o < co; ++o)
+        for (int c = 0; c < ci; ++c)
+            for (int a = 0; a < kh; ++a)
+                for (int d = 0; d < kw; ++d) {
+                    const int k = col(a, d, c);
+                    if (k < 0) continue;
+                    if (k >= Ktot) return fail(VF_ERR_INVALID, "raft_create: filter column out of range");
+                    B[size_t(o) * Ktot + k] = __float2half_rn(w[((size_t(o) * ci + c) * kh + a) * kw + d]);
+                }
+    std::vector<float> sc(n_out, 0.f), bi(n_out, 0.f);
+    for (int o = 0; o < co; ++o) {
+        const float s = (bn_scale ? bn_scale[o] : 1.f) * extra_scale;
+        sc[o] = s;
+        bi[o] = (b ? b[o] : 0.f) * s + (bn_shift ? bn_shift[o] : 0.f) * extra_scale;
+    }
+    cw.n_out = n_out;
+    VF_TRY(ralloc(h, &cw.w, B.size()));
+    VF_TRY(ralloc(h, &cw.scale, size_t(n_out)));
+    VF_TRY(ralloc(h, &cw.bias, size_t(n_out)));
+    VF_CUDA(cudaMemcpy(cw.w, B.data(), B.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    VF_CUDA(cudaMemcpy(cw.scale, sc.data(), n_out * sizeof(float), cudaMemcpyHostToDevice));
+    VF_CUDA(cudaMemcpy(cw.bias, bi.data(), n_out * sizeof(float), cudaMemcpyHostToDevice));
+    return VF_OK;
+}
+
+struct BnFold { std::vector<float> scale, shift; };
+static bool bn_fold(const TensorTable& T, const std::string& p, int c, BnFold* f) {
+    const float *g = T.get(p + ".weight", c), *b = T.get(p + ".bias", c), *m = T.get(p + ".running_mean", c),
+                *v = T.get(p + ".running_var", c);
+    if (!g || !b || !m || !v) return false;
+    f->scale.resize(c); f->shift.resize(c);
+    for (int i = 0; i < c; ++i) {
+        const float s = g[i] / sqrtf(v[i] + 1e-5f);
+        f->scale[i] = s;
+        f->shift[i] = b[i] - m[i] * s;
+    }
+    return true;
+}
+
+// stride-1 kh x kw conv whose input rows have `pitch` channels with the conv's channel c stored at column chan(c):
+// taps = kernel rows, each a run of kw*pitch elements starting (kw/2) positions to the left.
+static int prep_same_conv(vf_raft* h, ConvW& cw, const TensorTable& T, const std::string& name, int co, int ci, int kh,
+                          int kw, int pitch, const std::function<int(int)>& chan, int n_out, const BnFold* bn,
+                          float extra_scale = 1.f) {
+    const float* w = T.get(name + ".weight", int64_t(co) * ci * kh * kw);
+    const float* b = T.get(name + ".bias", co);
+    if (!w || !b) return fail(VF_ERR_INVALID, "raft_create: missing or mis-shaped tensor '%s'", name.c_str());
+    cw.ntaps = kh; cw.k_per_tap = kw * pitch;
+    cw.dh.clear(); cw.dw0.clear();
+    for (int a = 0; a < kh; ++a) { cw.dh.push_back(a - kh / 2); cw.dw0.push_back(-(kw / 2)); }
+    const int kpt = cw.k_per_tap;
+    return upload_conv(h, cw, w, b, co, ci, kh, kw, n_out, kh * kpt,
+                       [=](int a, int d, int c) { return a * kpt + d * pitch + chan(c); },
+                       bn ? bn->scale.data() : nullptr, bn ? bn->shift.data() : nullptr, extra_scale);
+}
+// same, but every (kh, kw) position is its own tap reading `ci` channels at column offset 0 of rows with a wider pitch
+static int prep_unmerged_conv(vf_raft* h, ConvW& cw, const TensorTable& T, const std::string& name, int co, int ci, int kh,
+                              int kw, int n_out, float extra_scale = 1.f) {
+    const float* w = T.get(name + ".weight", int64_t(co) * ci * kh * kw);
+    const float* b = T.get(name + ".bias", co);
+    if (!w || !b) return fail(VF_ERR_INVALID, "raft_create: missing or mis-shaped tensor '%s'", name.c_str());
+    cw.ntaps = kh * kw; cw.k_per_tap = ci;
+    cw.dh.clear(); cw.dw0.clear();
+    for (int a = 0; a < kh; ++a)
+        for (int d = 0; d < kw; ++d) { cw.dh.push_back(a - kh / 2); cw.dw0.push_back(d - kw / 2); }
+    return upload_conv(h, cw, w, b, co, ci, kh, kw, n_out, kh * kw * ci,
+                       [=](int a, int d, int c) { return (a * kw + d) * ci + c; }, nullptr, nullptr, extra_scale);
+}
+// stride-2 k x k conv (pad k/2) on the phase repack of its input: phase volume row q holds x[2(q-B)+p] with B =
+// border-before (2 for k=7, 1 for k=3) and `pc` = 4*C' channels ((ph*2+pw)*C' + c); filter index = 2a + p - 1
+// for tap a (both k=7: a in 0..3, k=3: a in 0..1).
+static int prep_stride2_conv(vf_raft* h, ConvW& cw, const TensorTable& T, const std::string& name, int co, int ci, int k,
+                             int cpad, int n_out, const BnFold* bn) {
+    const float* w = T.get(name + ".weight", int64_t(co) * ci * k * k);
+    const float* b = T.get(name + ".bias", co);
+    if (!w || !b) return fail(VF_ERR_INVALID, "raft_create: missing or mis-shaped tensor '%s'", name.c_str());
+    const int na = (k == 7) ? 4 : 2, before = (k == 7) ? 2 : 1, pc = 4 * cpad;
+    cw.ntaps = na; cw.k_per_tap = na * pc;
+    cw.dh.clear(); cw.dw0.clear();
+    for (int a = 0; a < na; ++a) { cw.dh.push_back(a - before); cw.dw0.push_back(-before); }
+    const int kpt = cw.k_per_tap;
+    // invert (kh, kw) -> (a, ph), (bq, pw): kh = 2a + ph - 1
+    return upload_conv(h, cw, w, b, co, ci, k, k, n_out, na * kpt,
+                       [=](int kh, int kw, int c) {
+                           const int a = (kh + 1) / 2, ph = (kh + 1) % 2, bq = (kw + 1) / 2, pw = (kw + 1) % 2;
+                           return a * kpt + bq * pc + (ph * 2 + pw) * cpad + c;
+                       },
+                       bn ? bn->scale.data() : nullptr, bn ? bn->shift.data() : nullptr, 1.f);
+}
+// 1x1 stride-2 downsample: phase (0,0) of the repacked row = its first `ci` channels
+static int prep_down_conv(vf_raft* h, ConvW& cw, const TensorTable& T, const std::string& name, int co, int ci, int n_out,
+                          const BnFold* bn) {
+    const float* w = T.get(name + ".weight", int64_t(co) * ci);
+    const float* b = T.get(name + ".bias", co);
+    if (!w || !b) return fail(VF_ERR_INVALID, "raft_create: missing or mis-shaped tensor '%s'", name.c_str());
+    cw.ntaps = 1; cw.k_per_tap = ci;
+    cw.dh = {0}; cw.dw0 = {0};
+    return upload_conv(h, cw, w, b, co, ci, 1, 1, n_out, ci, [=](int, int, int c) { return c; },
+                       bn ? bn->scale.data() : nullptr, bn ? bn->shift.data() : nullptr, 1.f);
+}
+
+static int prep_encoder(vf_raft* h, vf_raft::Enc& e, const TensorTable& T, const std::string& p, bool batch, int out_dim) {
+    auto ident = [](int c) { return c; };
+    BnFold f; const BnFold* bn = nullptr;
+    auto fold = [&](const std::string& name, int c) -> int {
+        if (!batch) { bn = nullptr; return VF_OK; }
+        if (!bn_fold(T, name, c, &f)) return fail(VF_ERR_INVALID, "raft_create: missing BatchNorm '%s'", name.c_str());
+        bn = &f; return VF_OK;
+    };
+    VF_TRY(fold(p + ".norm1", 64));
+    VF_TRY(prep_stride2_conv(h, e.conv1, T, p + ".conv1", 64, 3, 7, 4, 64, bn));     // phase row: 4 phases x 4 (3 used)
+    for (int blk = 0; blk < 2; ++blk)
+        for (int cv = 0; cv < 2; ++cv) {
+            const std::string b = p + ".layer1." + std::to_string(blk);
+            VF_TRY(fold(b + ".norm" + std::to_string(cv + 1), 64));
+            VF_TRY(prep_same_conv(h, e.l1[blk * 2 + cv], T, b + ".conv" + std::to_string(cv + 1), 64, 64, 3, 3, 64, ident, 64, bn));
+        }
+    const int dims[2][2] = {{64, 96}, {96, 128}};
+    for (int L = 0; L < 2; ++L) {
+        const std::string lp = p + ".layer" + std::to_string(L + 2);
+        const int ci = dims[L][0], co = dims[L][1];
+        ConvW& c1 = L == 0 ? e.l2c1 : e.l3c1;
+        ConvW& dn = L == 0 ? e.l2down : e.l3down;
+        ConvW* rest = L == 0 ? e.l2 : e.l3;
+        VF_TRY(fold(lp + ".0.norm1", co));
+        VF_TRY(prep_stride2_conv(h, c1, T, lp + ".0.conv1", co, ci, 3, ci, co, bn));
+        VF_TRY(fold(lp + ".0.downsample.1", co));
+        VF_TRY(prep_down_conv(h, dn, T, lp + ".0.downsample.0", co, ci, co, bn));
+        VF_TRY(fold(lp + ".0.norm2", co));
+        VF_TRY(prep_same_conv(h, rest[0], T, lp + ".0.conv2", co, co, 3, 3, co, ident, co, bn));
+        VF_TRY(fold(lp + ".1.norm1", co));
+        VF_TRY(prep_same_conv(h, rest[1], T, lp + ".1.conv1", co, co, 3, 3, co, ident, co, bn));
+        VF_TRY(fold(lp + ".1.norm2", co));
+        VF_TRY(prep_same_conv(h, rest[2], T, lp + ".1.conv2", co, co, 3, 3, co, ident, co, bn));
+    }
+    VF_TRY(prep_same_conv(h, e.conv2, T, p + ".conv2", out_dim, 128, 1, 1, 128, ident, out_dim, nullptr));
+    return VF_OK;
+}
+
+static int run_conv(vf_raft* h, const ConvW& cw, const __half* X, int pitch, const Vol2& v, void* out, int ldo, int out_f32,
+                    int act, cudaStream_t s) {
+    ConvGeom g;
+    memset(&g, 0, sizeof(g));
+    g.ntaps = cw.ntaps; g.k_per_tap = cw.k_per_tap;
+    for (int j = 0; j < cw.ntaps; ++j) g.tap_off[j] = cw.dh[j] * v.Wp + cw.dw0[j];
+    g.mask = 1;
+    g.Tp = 1; g.Hp = v.Hp; g.Wp = v.Wp; g.t0 = 0; g.t1 = 1; g.h0 = v.h0; g.h1 = v.h1; g.w0 = v.w0; g.w1 = v.w1;
+    GemmEpi ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.out = out; ep.ldo = ldo; ep.out_f32 = out_f32; ep.bias = cw.bias; ep.scale = cw.scale; ep.act = act;
+    h->launches += 1;
+    return conv_gemm_f16(X, pitch, v.rows(), cw.w, cw.n_out, g, ep, s);
+}
+
+// BasicEncoder.forward on m frames whose stem phase volume is in h->s0; result rows (border-1 /8 geometry) in `out`
+static int run_encoder(vf_raft* h, const vf_raft::Enc& e, bool inst, int m, int H, int W, __half* out, int out_dim,
+                       cudaStream_t s) {
+    const Vol2 g2{m, H / 2 + 3, W / 2 + 3, 2, 2 + H / 2, 2, 2 + W / 2};
+    const Vol2 g4{m, H / 4 + 2, W / 4 + 2, 1, 1 + H / 4, 1, 1 + W / 4};
+    const Vol2 g8{m, H / 8 + 2, W / 8 + 2, 1, 1 + H / 8, 1, 1 + W / 8};
+    __half *x = h->bufA, *y = h->bufB, *r = h->bufC, *r2 = h->bufD, *ph = h->bufE;
+    const int relu_if_bn = inst ? VF_ACT_NONE : VF_ACT_RELU;
+    auto norm_relu = [&](const __half* raw, __half* dst, const Vol2& v, int C) -> int {   // dst = relu(IN(raw))
+        VF_TRY(raft_instnorm_stats(raw, v, C, h->st_a, s));
+        h->launches += 2;
+        return raft_instnorm_apply(raw, h->st_a, nullptr, nullptr, dst, v, C, s);
+    };
+    // conv1 + norm1 + relu
+    if (inst) { VF_TRY(run_conv(h, e.conv1, h->s0, 16, g2, r, 64, 0, VF_ACT_NONE, s)); VF_TRY(norm_relu(r, x, g2, 64)); }
+    else      { VF_TRY(run_conv(h, e.conv1, h->s0, 16, g2, x, 64, 0, VF_ACT_RELU, s)); }
+    // a stride-1 residual block at geometry v with C channels: x <- relu(x + relu(norm2(conv2(relu(norm1(conv1(x)))))))
+    auto res_block = [&](const ConvW& c1, const ConvW& c2, const Vol2& v, int C) -> int {
+        if (inst) {
+            VF_TRY(run_conv(h, c1, x, C, v, r, C, 0, VF_ACT_NONE, s));
+            VF_TRY(norm_relu(r, y, v, C));
+            VF_TRY(run_conv(h, c2, y, C, v, r, C, 0, VF_ACT_NONE, s));
+            VF_TRY(raft_instnorm_stats(r, v, C, h->st_a, s));
+            VF_TRY(raft_instnorm_apply(r, h->st_a, x, nullptr, x, v, C, s));
+            h->launches += 2;
+        } else {
+            VF_TRY(run_conv(h, c1, x, C, v, y, C, 0, VF_ACT_RELU, s));
+            VF_TRY(run_conv(h, c2, y, C, v, r, C, 0, VF_ACT_RELU, s));
+            VF_TRY(raft_add_relu(x, r, x, v, C, s));
+            h->launches += 1;
+        }
+        return VF_OK;
+    };
+    VF_TRY(res_block(e.l1[0], e.l1[1], g2, 64));
+    VF_TRY(res_block(e.l1[2], e.l1[3], g2, 64));
+    // a stride-2 residual block: vin (Cin) -> vout (Cout)
+    auto down_block = [&](const ConvW& c1, const ConvW& dn, const ConvW& c2, const Vol2& vin, const Vol2& vout, int Cin,
+                          int Cout) -> int {
+        VF_TRY(raft_phase_repack(x, vin, Cin, ph, vout, s));
+        h->launches += 1;
+        if (inst) {
+            VF_TRY(run_conv(h, c1, ph, 4 * Cin, vout, r, Cout, 0, VF_ACT_NONE, s));
+            VF_TRY(norm_relu(r, y, vout, Cout));
+            VF_TRY(run_conv(h, c2, y, Cout, vout, r, Cout, 0, VF_ACT_NONE, s));
+            VF_TRY(run_conv(h, dn, ph, 4 * Cin, vout, r2, Cout, 0, VF_ACT_NONE, s));
+            VF_TRY(raft_instnorm_stats(r, vout, Cout, h->st_a, s));
+            VF_TRY(raft_instnorm_stats(r2, vout, Cout, h->st_b, s));
+            VF_TRY(raft_instnorm_apply(r, h->st_a, r2, h->st_b, x, vout, Cout, s));    // relu(IN(down) + relu(IN(c2)))
+            h->launches += 3;
+        } else {
+            VF_TRY(run_conv(h, c1, ph, 4 * Cin, vout, y, Cout, 0, VF_ACT_RELU, s));
+            VF_TRY(run_conv(h, c2, y, Cout, vout, r, Cout, 0, VF_ACT_RELU, s));
+            VF_TRY(run_conv(h, dn, ph, 4 * Cin, vout, r2, Cout, 0, VF_ACT_NONE, s));    // norm3 folded, no relu
+            VF_TRY(raft_add_relu(r2, r, x, vout, Cout, s));
+            h->launches += 1;
+        }
+        return VF_OK;
+    };
+    VF_TRY(down_block(e.l2c1, e.l2down, e.l2[0], g2, g4, 64, 96));
+    VF_TRY(res_block(e.l2[1], e.l2[2], g4, 96));
+    VF_TRY(down_block(e.l3c1, e.l3down, e.l3[0], g4, g8, 96, 128));
+    VF_TRY(res_block(e.l3[1], e.l3[2], g8, 128));
+    VF_TRY(run_conv(h, e.conv2, x, 128, g8, out, out_dim, 0, VF_ACT_NONE, s));
+    return VF_OK;
+}
+
+}  // namespace vf
+
+extern "C" {
+
+int vf_raft_create(vf_raft_t** out, const vf_named_tensor* tensors, int n_tensors, int device, int max_frames, int max_h,
+                   int max_w) {
+    if (!out || !tensors || n_tensors <= 0) return fail(VF_ERR_INVALID, "raft_create: null argument");
+    *out = nullptr;
+    if (max_frames < 2) max_frames = 2;
+    if (max_h <= 0 || max_w <= 0) return fail(VF_ERR_INVALID, "raft_create: max frame size required");
+    VF_CUDA(cudaSetDevice(device));
+    int major = 0;
+    VF_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) return fail(VF_ERR_UNSUPPORTED, "device %d is not sm_100; this library is built for sm_100a only", device);
+    vf_raft* h = new vf_raft();
+    h->device = device; h->max_frames = max_frames;
+    h->max_h = (max_h + 7) / 8 * 8; h->max_w = (max_w + 7) / 8 * 8;
+    const TensorTable T{tensors, n_tensors};
+    auto ident = [](int c) { return c; };
+    auto body = [&]() -> int {
+        VF_TRY(prep_encoder(h, h->enc[0], T, "fnet", false, 256));
+        VF_TRY(prep_encoder(h, h->enc[1], T, "cnet", true, 256));
+        const std::string u = "update_block.";
+        VF_TRY(prep_same_conv(h, h->convc1, T, u + "encoder.convc1", 256, 324, 1, 1, CF, ident, 256, nullptr));
+        VF_TRY(prep_same_conv(h, h->convc2, T, u + "encoder.convc2", 192, 256, 3, 3, 256, ident, 192, nullptr));
+        VF_TRY(prep_same_conv(h, h->convf1, T, u + "encoder.convf1", 128, 2, 7, 7, 8, ident, 128, nullptr));
+        VF_TRY(prep_same_conv(h, h->convf2, T, u + "encoder.convf2", 64, 128, 3, 3, 128, ident, 64, nullptr));
+        VF_TRY(prep_same_conv(h, h->convm, T, u + "encoder.conv", 126, 256, 3, 3, 256, ident, 128, nullptr));
+        // GRU gates read hx / qx rows: input channel j -> column j for j < 382 (h, inp, motion-out), flow -> 384, 385
+        auto gmap = [](int c) { return c < 382 ? c : c + 2; };
+        // z and r share their input: one GEMM with N = 256 (z | r)
+        for (int dir = 0; dir < 2; ++dir) {
+            const std::string sfx = dir == 0 ? "1" : "2";
+            const int kh = dir == 0 ? 1 : 5, kw = dir == 0 ? 5 : 1;
+            ConvW& zr = dir == 0 ? h->zr1 : h->zr2;
+            ConvW& qq = dir == 0 ? h->q1 : h->q2;
+            // stack convz | convr weights into one [256, 384, kh, kw] filter
+            const float *wz = T.get(u + "gru.convz" + sfx + ".weight", 128 * 384 * 5), *bz = T.get(u + "gru.convz" + sfx + ".bias", 128);
+            const float *wr = T.get(u + "gru.convr" + sfx + ".weight", 128 * 384 * 5), *br = T.get(u + "gru.convr" + sfx + ".bias", 128);
+            if (!wz || !bz || !wr || !br) return fail(VF_ERR_INVALID, "raft_create: missing GRU gate tensors");
+            std::vector<float> wzr(size_t(256) * 384 * 5), bzr(256);
+            memcpy(wzr.data(), wz, sizeof(float) * 128 * 384 * 5);
+            memcpy(wzr.data() + size_t(128) * 384 * 5, wr, sizeof(float) * 128 * 384 * 5);
+            memcpy(bzr.data(), bz, sizeof(float) * 128);
+            memcpy(bzr.data() + 128, br, sizeof(float) * 128);
+            const vf_named_tensor tmp[2] = {{"zr.weight", wzr.data(), int64_t(wzr.size())}, {"zr.bias", bzr.data(), 256}};
+            const TensorTable TT{tmp, 2};
+            VF_TRY(prep_same_conv(h, zr, TT, "zr", 256, 384, kh, kw, HX, gmap, 256, nullptr));
+            VF_TRY(prep_same_conv(h, qq, T, u + "gru.convq" + sfx, 128, 384, kh, kw, HX, gmap, 128, nullptr));
+        }
+        VF_TRY(prep_unmerged_conv(h, h->fh1, T, u + "flow_head.conv1", 256, 128, 3, 3, 256));
+        VF_TRY(prep_same_conv(h, h->fh2, T, u + "flow_head.conv2", 2, 256, 3, 3, 256, ident, 8, nullptr));
+        VF_TRY(prep_unmerged_conv(h, h->mk0, T, u + "mask.0", 256, 128, 3, 3, 256));
+        VF_TRY(prep_same_conv(h, h->mk2, T, u + "mask.2", 576, 256, 1, 1, 256, ident, 576, nullptr, 0.25f));   // .25 * mask
+        {
+            const size_t np8 = (size_t(h->max_h / 8) * (h->max_w / 8) + 7) / 8 * 8 + 64;
+            std::vector<float> s16(np8, 1.0f / 16.0f);     // corr / sqrt(256) (corr.py:60)
+            VF_TRY(ralloc(h, &h->sixteenth, s16.size()));
+            VF_CUDA(cudaMemcpy(h->sixteenth, s16.data(), s16.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
+        // ---- workspace
+        const size_t F = size_t(max_frames), NP = F - 1;
+        const int H = h->max_h, W = h->max_w;
+        const size_t rows2 = F * (H / 2 + 3) * (W / 2 + 3), rows4 = F * (H / 4 + 2) * (W / 4 + 2);
+        const size_t rows8e = F * (H / 8 + 2) * (W / 8 + 2), rows8u = NP * (H / 8 + 6) * (W / 8 + 6);
+        const size_t enc_elems = rows2 * 64 > rows4 * 96 ? rows2 * 64 : rows4 * 96;
+        VF_TRY(ralloc(h, &h->s0, rows2 * 16));
+        VF_TRY(ralloc(h, &h->bufA, enc_elems)); VF_TRY(ralloc(h, &h->bufB, enc_elems));
+        VF_TRY(ralloc(h, &h->bufC, enc_elems)); VF_TRY(ralloc(h, &h->bufD, enc_elems));
+        const size_t ph_elems = rows4 * 256 > rows8e * 384 ? rows4 * 256 : rows8e * 384;
+        VF_TRY(ralloc(h, &h->bufE, ph_elems));
+        VF_TRY(ralloc(h, &h->fmap_b, rows8e * 256));
+        VF_TRY(ralloc(h, &h->cnet_b, rows8e * 256));
+        const size_t P = size_t(H / 8) * (W / 8), P8 = (P + 7) / 8 * 8;
+        VF_TRY(ralloc(h, &h->fmaps, F * P8 * 256));
+        VF_TRY(ralloc(h, &h->st_a, F * 128 * 2)); VF_TRY(ralloc(h, &h->st_b, F * 128 * 2));
+        const size_t ld = (P8 + P / 4 + P / 16 + P / 64 + 64 + 3) / 4 * 4;
+        VF_TRY(ralloc(h, &h->corr, NP * P * ld));
+        VF_TRY(ralloc(h, &h->coords1, NP * P * 2));
+        VF_TRY(ralloc(h, &h->corrfeat, rows8u * CF)); VF_TRY(ralloc(h, &h->c1, rows8u * 256));
+        VF_TRY(ralloc(h, &h->c2f, rows8u * 256));     VF_TRY(ralloc(h, &h->f1, rows8u * 128));
+        VF_TRY(ralloc(h, &h->flow8, rows8u * 8));     VF_TRY(ralloc(h, &h->hx, rows8u * HX));
+        VF_TRY(ralloc(h, &h->qx, rows8u * HX));       VF_TRY(ralloc(h, &h->zr, rows8u * 256));
+        VF_TRY(ralloc(h, &h->qb, rows8u * 128));      VF_TRY(ralloc(h, &h->fh, rows8u * 256));
+        VF_TRY(ralloc(h, &h->mk, rows8u * 256));
+        VF_TRY(ralloc(h, &h->delta, rows8u * 8));     VF_TRY(ralloc(h, &h->mask, rows8u * 576));
+        return VF_OK;
+    };
+    const int st = body();
+    if (st != VF_OK) { vf_raft_destroy(h); return st; }
+    *out = h;
+    return VF_OK;
+}
+
+int vf_raft_destroy(vf_raft_t* h) {
+    if (!h) return VF_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+    return VF_OK;
+}
+
+int vf_raft_flow(vf_raft_t* h, const void* frames, int is_u8, int chw_layout, int n_frames, int Hs, int Ws, int iters,
+                 int unpad, float* out, void* stream) {
+    if (!h || !frames || !out) return fail(VF_ERR_INVALID, "raft_flow: null argument");
+    if (n_frames < 2 || n_frames > h->max_frames) return fail(VF_ERR_INVALID, "raft_flow: %d frames outside [2, %d]", n_frames, h->max_frames);
+    if (iters < 1) return fail(VF_ERR_INVALID, "raft_flow: iters must be >= 1");
+    // InputPadder 'sintel' (raft.py:29-34)
+    const int pad_h = (((Hs / 8) + 1) * 8 - Hs) % 8, pad_w = (((Ws / 8) + 1) * 8 - Ws) % 8;
+    const int pl = pad_w / 2, pt = pad_h / 2;
+    const int H = Hs + pad_h, W = Ws + pad_w;
+    if (H > h->max_h || W > h->max_w || H < 16 || W < 16)
+        return fail(VF_ERR_INVALID, "raft_flow: padded frame %dx%d outside the workspace (%dx%d)", H, W, h->max_h, h->max_w);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    VF_CUDA(cudaSetDevice(h->device));
+    const int F = n_frames, NP = F - 1, H8 = H / 8, W8 = W / 8, P = H8 * W8, P8 = (P + 7) / 8 * 8;
+    if (P8 != P) return fail(VF_ERR_UNSUPPORTED, "raft_flow: (H/8)*(W/8) = %d must be a multiple of 8", P);
+    // ---- feature network on all F frames (instance norm)
+    VF_TRY(raft_input_pack(frames, is_u8, chw_layout, F, Hs, Ws, pt, pl, H, W, h->s0, H / 2 + 3, W / 2 + 3, s));
+    VF_TRY(run_encoder(h, h->enc[0], true, F, H, W, h->fmap_b, 256, s));
+    const Vol2 g8eF{F, H8 + 2, W8 + 2, 1, 1 + H8, 1, 1 + W8};
+    VF_CUDA(cudaMemsetAsync(h->fmaps, 0, size_t(F) * P8 * 256 * sizeof(__half), s));
+    if (P8 == P) {
+        VF_TRY(raft_gather_valid(h->fmap_b, g8eF, 256, 256, h->fmaps, s));
+    } else {   // per-frame slabs of P8 rows (zero tail rows)
+        for (int f = 0; f < F; ++f) {
+            const Vol2 one{1, H8 + 2, W8 + 2, 1, 1 + H8, 1, 1 + W8};
+            VF_TRY(raft_gather_valid(h->fmap_b + size_t(f) * one.rows() * 256, one, 256, 256, h->fmaps + size_t(f) * P8 * 256, s));
+        }
+    }
+    // ---- all-pairs correlation + pyramid: corr[b] = fmap[b] . fmap[b+1]^T / 16
+    int lvl_off[4], lvl_h[4], lvl_w[4];
+    lvl_off[0] = 0; lvl_h[0] = H8; lvl_w[0] = W8;
+    int ldc = P8;
+    for (int l = 1; l < 4; ++l) { lvl_h[l] = lvl_h[l - 1] / 2; lvl_w[l] = lvl_w[l - 1] / 2; lvl_off[l] = ldc; ldc += lvl_h[l] * lvl_w[l]; }
+    ldc = (ldc + 3) / 4 * 4;
+    for (int b = 0; b < NP; ++b) {
+        GemmEpi ep;
+        memset(&ep, 0, sizeof(ep));
+        ep.out = h->corr + size_t(b) * P * ldc; ep.ldo = ldc; ep.out_f32 = 1; ep.scale = h->sixteenth; ep.act = VF_ACT_NONE;
+        VF_TRY(gemm_f16(h->fmaps + size_t(b) * P8 * 256, 256, h->fmaps + size_t(b + 1) * P8 * 256, 256, P, P8, 256, ep, s));
+    }
+    for (int l = 1; l < 4; ++l)
+        VF_TRY(raft_corr_pool(h->corr, int64_t(NP) * P, ldc, lvl_off[l - 1], lvl_h[l - 1], lvl_w[l - 1], lvl_off[l], s));
+    h->launches += NP + 6;
+    // (the lookup kernel recomputes the level offsets as cumulative H*W, which equals lvl_off because P8 == P)
+    // ---- context network on frames[:-1] (batch norm folded)
+    VF_TRY(run_encoder(h, h->enc[1], false, NP, H, W, h->cnet_b, 256, s));   // reuses s0: the first NP frames' phase rows
+    const Vol2 g8e{NP, H8 + 2, W8 + 2, 1, 1 + H8, 1, 1 + W8};
+    const Vol2 g8u{NP, H8 + 6, W8 + 6, 3, 3 + H8, 3, 3 + W8};
+    const size_t rows8u = size_t(g8u.rows());
+    // zero the update-block operand buffers once: their border rows are read as conv padding
+    VF_CUDA(cudaMemsetAsync(h->hx, 0, rows8u * HX * sizeof(__half), s));
+    VF_CUDA(cudaMemsetAsync(h->qx, 0, rows8u * HX * sizeof(__half), s));
+    VF_CUDA(cudaMemsetAsync(h->flow8, 0, rows8u * 8 * sizeof(__half), s));
+    VF_CUDA(cudaMemsetAsync(h->corrfeat, 0, rows8u * CF * sizeof(__half), s));
+    VF_TRY(raft_cnet_split(h->cnet_b, g8e, h->hx, h->qx, g8u, HX, s));
+    VF_TRY(raft_coords_update(h->coords1, nullptr, h->hx, h->qx, h->flow8, g8u, HX, s));    // coords1 = grid, flow = 0
+    h->launches += 4;
+    // ---- refinement iterations
+    for (int it = 0; it < iters; ++it) {
+        VF_TRY(raft_corr_lookup(h->corr, ldc, h->coords1, NP, H8, W8, h->corrfeat, g8u, CF, s));
+        VF_TRY(run_conv(h, h->convc1, h->corrfeat, CF, g8u, h->c1, 256, 0, VF_ACT_RELU, s));
+        VF_TRY(run_conv(h, h->convc2, h->c1, 256, g8u, h->c2f, 256, 0, VF_ACT_RELU, s));            // cols 0..191
+        VF_TRY(run_conv(h, h->convf1, h->flow8, 8, g8u, h->f1, 128, 0, VF_ACT_RELU, s));
+        VF_TRY(run_conv(h, h->convf2, h->f1, 128, g8u, h->c2f + 192, 256, 0, VF_ACT_RELU, s));       // cols 192..255
+        VF_TRY(run_conv(h, h->convm, h->c2f, 256, g8u, h->hx + 256, HX, 0, VF_ACT_RELU, s));         // cols 256..383
+        for (int dir = 0; dir < 2; ++dir) {
+            const ConvW& zr = dir == 0 ? h->zr1 : h->zr2;
+            const ConvW& qq = dir == 0 ? h->q1 : h->q2;
+            VF_TRY(run_conv(h, zr, h->hx, HX, g8u, h->zr, 256, 0, VF_ACT_SIGMOID, s));
+            VF_TRY(raft_gru_rh(h->hx, h->zr, h->qx, g8u, HX, s));
+            VF_TRY(run_conv(h, qq, h->qx, HX, g8u, h->qb, 128, 0, VF_ACT_TANH, s));
+            VF_TRY(raft_gru_update(h->hx, h->zr, h->qb, g8u, HX, s));
+        }
+        VF_TRY(run_conv(h, h->fh1, h->hx, HX, g8u, h->fh, 256, 0, VF_ACT_RELU, s));
+        VF_TRY(run_conv(h, h->fh2, h->fh, 256, g8u, h->delta, 8, 1, VF_ACT_NONE, s));
+        VF_TRY(raft_coords_update(h->coords1, h->delta, h->hx, h->qx, h->flow8, g8u, HX, s));
+        h->launches += 6;
+    }
+    // ---- convex upsampling, once
+    VF_TRY(run_conv(h, h->mk0, h->hx, HX, g8u, h->mk, 256, 0, VF_ACT_RELU, s));
+    VF_TRY(run_conv(h, h->mk2, h->mk, 256, g8u, h->mask, 576, 1, VF_ACT_NONE, s));
+    if (unpad) VF_TRY(raft_upsample_flow(h->coords1, h->mask, g8u, NP, H8, W8, pt, pl, Hs, Ws, out, s));
+    else       VF_TRY(raft_upsample_flow(h->coords1, h->mask, g8u, NP, H8, W8, 0, 0, H, W, out, s));
+    h->launches += 1;
+    h->last_n = NP; h->last_H8 = H8; h->last_W8 = W8; h->corr_ld = ldc; h->P8 = P8; h->g8e = g8e; h->g8u = g8u;
+    return VF_OK;
+}
+
+int vf_raft_padded_size(int Hs, int Ws, int* H, int* W) {
+    if (!H || !W || Hs <= 0 || Ws <= 0) return fail(VF_ERR_INVALID, "raft_padded_size: bad argument");
+    *H = Hs + (((Hs / 8) + 1) * 8 - Hs) % 8;
+    *W = Ws + (((Ws / 8) + 1) * 8 - Ws) % 8;
+    return VF_OK;
+}
+
+int vf_raft_debug_read(vf_raft_t* h, int what, float* out, int64_t capacity, int* dims4, void* stream) {
+    if (!h || !dims4 || h->last_n <= 0) return fail(VF_ERR_INVALID, "raft_debug_read: no forward has run");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int n = h->last_n, H8 = h->last_H8, W8 = h->last_W8;
+    int64_t need = 0;
+    if (what == 0) { dims4[0] = n + 1; dims4[1] = 256; dims4[2] = H8; dims4[3] = W8; }
+    else if (what == 1) { dims4[0] = n; dims4[1] = 256; dims4[2] = H8; dims4[3] = W8; }
+    else if (what == 2) { dims4[0] = n; dims4[1] = 128; dims4[2] = H8; dims4[3] = W8; }
+    else if (what == 3) { dims4[0] = n; dims4[1] = 2; dims4[2] = H8; dims4[3] = W8; }
+    else if (what == 4) { dims4[0] = n; dims4[1] = 324; dims4[2] = H8; dims4[3] = W8; }
+    else return fail(VF_ERR_INVALID, "raft_debug_read: unknown tensor id %d", what);
+    need = int64_t(dims4[0]) * dims4[1] * dims4[2] * dims4[3];
+    if (!out) return VF_OK;
+    if (capacity < need) return fail(VF_ERR_INVALID, "raft_debug_read: capacity too small");
+    if (what == 0) { Vol2 v = h->g8e; v.n = n + 1; return raft_unpack2d(h->fmap_b, v, 256, 0, 256, out, s); }
+    if (what == 1) return raft_unpack2d(h->cnet_b, h->g8e, 256, 0, 256, out, s);
+    if (what == 2) return raft_unpack2d(h->hx, h->g8u, HX, 0, 128, out, s);          // GRU hidden state
+    if (what == 3) return raft_unpack2d(h->hx, h->g8u, HX, 384, 2, out, s);          // low-res flow (fp16 copy)
+    return raft_unpack2d(h->corrfeat, h->g8u, CF, 0, 324, out, s);                   // last lookup
+}
+
+int64_t vf_raft_launch_count(const vf_raft_t* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,459 @@
+// Memory-bound kernels of the RAFT path.  Activations are channels-last fp16 rows of zero-bordered 2-D volumes
+// [n][Hp][Wp][C] (see raft.cu for the geometry); coordinates / flow / correlation volume are fp32.
+#include "common.cuh"
+#include "internal.h"
+#include "raft_kernels.h"
+
+namespace vf {
+
+namespace {
+
+inline unsigned nb(int64_t total, int threads) { return unsigned((total + threads - 1) / threads); }
+
+// images [n][H][W][3] (uint8 or fp32 in [0,255]) -> 2*(x/255) - 1 (raft.py:118-119) -> phase volume for the 7x7
+// stride-2 pad-3 stem: out[hq][wq][((ph*2+pw)*4 + c)] = x[2(hq-2)+ph][2(wq-2)+pw][c], 16 channels (12 used).
+// (Hs, Ws) is the source frame; (H, W) the /8-padded frame with the source at (pad_top, pad_left): InputPadder's
+// replicate padding (raft.py:36-37) is a coordinate clamp.
+template <typename TIn>
+__global__ void raft_input_pack_kernel(const TIn* __restrict__ img, int n, int Hs, int Ws, int pad_top, int pad_left,
+                                       int H, int W, int chw_layout, __half* __restrict__ out, int Hq, int Wq) {
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(n) * Hq * Wq;
+    if (idx >= total) return;
+    const int wq = int(idx % Wq), hq = int((idx / Wq) % Hq), b = int(idx / (int64_t(Wq) * Hq));
+    __align__(16) __half vals[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) vals[i] = __float2half_rn(0.f);
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph)
+#pragma unroll
+        for (int pw = 0; pw < 2; ++pw) {
+            const int yp = 2 * (hq - 2) + ph, xp = 2 * (wq - 2) + pw;
+            if (yp < 0 || yp >= H || xp < 0 || xp >= W) continue;       // the conv's own zero padding
+            const int y = min(max(yp - pad_top, 0), Hs - 1), x = min(max(xp - pad_left, 0), Ws - 1);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float v = chw_layout ? float(img[((int64_t(b) * 3 + c) * Hs + y) * Ws + x])
+                                           : float(img[((int64_t(b) * Hs + y) * Ws + x) * 3 + c]);
+                vals[(ph * 2 + pw) * 4 + c] =
+                    __float2half_rn(__fsub_rn(__fmul_rn(2.0f, __fdiv_rn(v, 255.0f)), 1.0f));
+            }
+        }
+    uint4* o = reinterpret_cast<uint4*>(out + idx * 16);
+    o[0] = reinterpret_cast<const uint4*>(vals)[0];
+    o[1] = reinterpret_cast<const uint4*>(vals)[1];
+}
+
+// space-to-depth for a stride-2 3x3 (pad 1) consumer: out[q][(ph*2+pw)*C + c] = in_valid[2(q-1)+ph][2(q'-1)+pw][c]
+// (zero outside the valid region); out is a border-1 volume at half resolution with 4*C channels.
+__global__ void phase_repack_kernel(const __half* __restrict__ in, Vol2 vi, int C, __half* __restrict__ out, Vol2 vo) {
+    const int cg = C >> 3;
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(vo.n) * vo.Hp * vo.Wp * 4 * cg;
+    if (idx >= total) return;
+    const int c8 = int(idx % cg);
+    const int p = int((idx / cg) % 4);
+    const int64_t pos = idx / (4 * cg);
+    const int wq = int(pos % vo.Wp), hq = int((pos / vo.Wp) % vo.Hp), b = int(pos / (int64_t(vo.Wp) * vo.Hp));
+    const int y = 2 * (hq - 1) + (p >> 1), x = 2 * (wq - 1) + (p & 1);     // valid-region coordinates of the input
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (y >= 0 && y < vi.h1 - vi.h0 && x >= 0 && x < vi.w1 - vi.w0)
+        v = __ldg(reinterpret_cast<const uint4*>(in + ((int64_t(b) * vi.Hp + y + vi.h0) * vi.Wp + x + vi.w0) * C + c8 * 8));
+    *reinterpret_cast<uint4*>(out + pos * (4 * C) + p * C + c8 * 8) = v;
+}
+
+// InstanceNorm2d statistics: per (sample, channel) sum and sum of squares over the valid region, accumulated in
+// double (fp32 partials per thread).  grid (row chunks, n), block = C threads.
+__global__ void instnorm_stats_kernel(const __half* __restrict__ x, Vol2 v, int C, double* __restrict__ stats) {
+    const int b = blockIdx.y, c = threadIdx.x;
+    const int H = v.h1 - v.h0, W = v.w1 - v.w0;
+    const int rows_per = (H + gridDim.x - 1) / gridDim.x;
+    const int y0 = blockIdx.x * rows_per, y1 = min(H, y0 + rows_per);
+    double s = 0.0, ss = 0.0;
+    for (int y = y0; y < y1; ++y) {
+        const __half* row = x + ((int64_t(b) * v.Hp + y + v.h0) * v.Wp + v.w0) * C + c;
+        float fs = 0.f, fss = 0.f;
+        for (int xw = 0; xw < W; ++xw) {
+            const float t = __half2float(row[int64_t(xw) * C]);
+            fs += t;
+            fss = fmaf(t, t, fss);
+        }
+        s += fs; ss += fss;
+    }
+    if (y1 > y0) {
+        atomicAdd(&stats[(int64_t(b) * C + c) * 2], s);
+        atomicAdd(&stats[(int64_t(b) * C + c) * 2 + 1], ss);
+    }
+}
+
+// y = relu(IN(a))                                   (res == nullptr)
+// y = relu(res' + relu(IN(a)))  with res' = res or IN(res) (res_stats != nullptr)      -- ResidualBlock tail
+// only valid positions are touched (borders stay zero).  One thread = 8 channels.
+__global__ void instnorm_apply_kernel(const __half* __restrict__ a, const double* __restrict__ a_stats,
+                                      const __half* __restrict__ res, const double* __restrict__ res_stats,
+                                      __half* __restrict__ out, Vol2 v, int C) {
+    const int cg = C >> 3;
+    const int H = v.h1 - v.h0, W = v.w1 - v.w0;
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(v.n) * H * W * cg;
+    if (idx >= total) return;
+    const int c8 = int(idx % cg);
+    const int64_t pos = idx / cg;
+    const int xw = int(pos % W), y = int((pos / W) % H), b = int(pos / (int64_t(W) * H));
+    const int64_t off = ((int64_t(b) * v.Hp + y + v.h0) * v.Wp + xw + v.w0) * C + c8 * 8;
+    const double cnt = double(H) * double(W);
+    const uint4 raw = *reinterpret_cast<const uint4*>(a + off);
+    const __half* ah = reinterpret_cast<const __half*>(&raw);
+    uint4 rraw = make_uint4(0, 0, 0, 0);
+    if (res) rraw = *reinterpret_cast<const uint4*>(res + off);
+    const __half* rh = reinterpret_cast<const __half*>(&rraw);
+    __align__(16) __half o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = c8 * 8 + j;
+        const double m = a_stats[(int64_t(b) * C + c) * 2] / cnt;
+        const double var = a_stats[(int64_t(b) * C + c) * 2 + 1] / cnt - m * m;
+        float y0 = (__half2float(ah[j]) - float(m)) * rsqrtf(float(var) + 1e-5f);
+        y0 = fmaxf(y0, 0.f);
+        if (res) {
+            float r = __half2float(rh[j]);
+            if (res_stats) {
+                const double rm = res_stats[(int64_t(b) * C + c) * 2] / cnt;
+                const double rv = res_stats[(int64_t(b) * C + c) * 2 + 1] / cnt - rm * rm;
+                r = (r - float(rm)) * rsqrtf(float(rv) + 1e-5f);
+            }
+            y0 = fmaxf(r + y0, 0.f);
+        }
+        o[j] = __float2half_rn(y0);
+    }
+    *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(o);
+}
+
+// out = relu(a + b) on valid positions (batch-norm encoder: norms are folded into the conv epilogues)
+__global__ void add_relu_kernel(const __half* __restrict__ a, const __half* __restrict__ bsrc, __half* __restrict__ out,
+                                Vol2 v, int C) {
+    const int cg = C >> 3;
+    const int H = v.h1 - v.h0, W = v.w1 - v.w0;
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(v.n) * H * W * cg;
+    if (idx >= total) return;
+    const int c8 = int(idx % cg);
+    const int64_t pos = idx / cg;
+    const int xw = int(pos % W), y = int((pos / W) % H), b = int(pos / (int64_t(W) * H));
+    const int64_t off = ((int64_t(b) * v.Hp + y + v.h0) * v.Wp + xw + v.w0) * C + c8 * 8;
+    const uint4 ra = *reinterpret_cast<const uint4*>(a + off), rb = *reinterpret_cast<const uint4*>(bsrc + off);
+    const __half2* ha = reinterpret_cast<const __half2*>(&ra);
+    const __half2* hb = reinterpret_cast<const __half2*>(&rb);
+    uint4 o;
+    __half2* ho = reinterpret_cast<__half2*>(&o);
+    const __half2 z = __float2half2_rn(0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 fa = __half22float2(ha[j]), fb = __half22float2(hb[j]);
+        ho[j] = __hmax2(__floats2half2_rn(fa.x + fb.x, fa.y + fb.y), z);
+    }
+    *reinterpret_cast<uint4*>(out + off) = o;
+}
+
+// valid rows of a bordered volume -> dense [n][H*W][C]
+__global__ void gather_valid_kernel(const __half* __restrict__ in, Vol2 v, int C, int ld, __half* __restrict__ out) {
+    const int cg = C >> 3;
+    const int H = v.h1 - v.h0, W = v.w1 - v.w0;
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(v.n) * H * W * cg;
+    if (idx >= total) return;
+    const int c8 = int(idx % cg);
+    const int64_t pos = idx / cg;
+    const int xw = int(pos % W), y = int((pos / W) % H), b = int(pos / (int64_t(W) * H));
+    const int64_t off = ((int64_t(b) * v.Hp + y + v.h0) * v.Wp + xw + v.w0) * ld + c8 * 8;
+    *reinterpret_cast<uint4*>(out + pos * C + c8 * 8) = *reinterpret_cast<const uint4*>(in + off);
+}
+
+// correlation pyramid: level l+1 = avg_pool2d(level l, 2, 2) over the (h2, w2) axes of every query row
+// (corr.py:24-27; floor sizes).  corr row layout: [lvl0 H*W | lvl1 | lvl2 | lvl3] floats, pitch `ld`.
+__global__ void corr_pool_kernel(float* __restrict__ corr, int64_t rows, int ld, int off_in, int Hi, int Wi, int off_out) {
+    const int Ho = Hi / 2, Wo = Wi / 2;
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = rows * Ho * Wo;
+    if (idx >= total) return;
+    const int xo = int(idx % Wo), yo = int((idx / Wo) % Ho);
+    const int64_t r = idx / (int64_t(Wo) * Ho);
+    const float* p = corr + r * ld + off_in + (2 * yo) * Wi + 2 * xo;
+    corr[r * ld + off_out + yo * Wo + xo] = 0.25f * ((p[0] + p[1]) + (p[Wi] + p[Wi + 1]));
+}
+
+// CorrBlock.__call__ (corr.py:29-50): for every query position and pyramid level, the 9x9 window of bilinear
+// samples (zero outside the map, align_corners=True pixel coordinates) around coords/2^l.  The window is the
+// reference's TRANSPOSED one: output channel l*81 + i*9 + j samples (x + i-4, y + j-4).
+// One warp per (query, level): the 10x10 integer neighbourhood is fetched once, the 81 blends come from it.
+__global__ void corr_lookup_kernel(const float* __restrict__ corr, int ld, const float* __restrict__ coords, int n,
+                                   int H8, int W8, __half* __restrict__ out, Vol2 vo, int out_ld) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t total = int64_t(n) * H8 * W8 * 4;
+    if (wid >= total) return;
+    const int lvl = int(wid & 3);
+    const int64_t q = wid >> 2;                      // b*H8*W8 + y*W8 + x
+    const int x0 = int(q % W8), y0 = int((q / W8) % H8), b = int(q / (int64_t(W8) * H8));
+    int Hl = H8, Wl = W8, off = 0;
+    for (int l = 0; l < lvl; ++l) { off += Hl * Wl; Hl >>= 1; Wl >>= 1; }
+    const float inv = 1.0f / float(1 << lvl);
+    const float cx = coords[q * 2] * inv, cy = coords[q * 2 + 1] * inv;
+    const float fx0 = floorf(cx), fy0 = floorf(cy);
+    const float ax = cx - fx0, ay = cy - fy0;
+    const int ix = int(fx0) - 4, iy = int(fy0) - 4;     // top-left of the 10x10 neighbourhood
+    const float* row = corr + q * ld + off;
+    __shared__ float nbuf[8][104];
+    float* nbr = nbuf[(threadIdx.x >> 5)];
+    for (int i = lane; i < 100; i += 32) {
+        const int yy = iy + i / 10, xx = ix + i % 10;
+        nbr[i] = (yy >= 0 && yy < Hl && xx >= 0 && xx < Wl) ? row[yy * Wl + xx] : 0.f;
+    }
+    __syncwarp();
+    const int64_t orow = (int64_t(b) * vo.Hp + y0 + vo.h0) * vo.Wp + x0 + vo.w0;
+    __half* o = out + orow * out_ld + lvl * 81;
+    for (int k = lane; k < 81; k += 32) {
+        const int i = k / 9, j = k % 9;                 // i offsets x, j offsets y (transposed window)
+        const float v00 = nbr[j * 10 + i], v01 = nbr[j * 10 + i + 1];
+        const float v10 = nbr[(j + 1) * 10 + i], v11 = nbr[(j + 1) * 10 + i + 1];
+        const float v = (1.f - ay) * ((1.f - ax) * v00 + ax * v01) + ay * ((1.f - ax) * v10 + ax * v11);
+        o[k] = __float2half_rn(v);
+    }
+    if (lvl == 3 && lane < 4) o[81 + lane] = __float2half_rn(0.f);    // pad channels 324..327
+}
+
+// context network output (raw conv2 output, 256 ch at border-1 geometry) -> hx: h = tanh(net) in cols [0,128),
+// inp = relu(inp) in cols [128,256) of both hx and qx (raft.py:141-143)
+__global__ void cnet_split_kernel(const __half* __restrict__ cnet, Vol2 vi, __half* __restrict__ hx,
+                                  __half* __restrict__ qx, Vol2 vo, int ld) {
+    const int H = vo.h1 - vo.h0, W = vo.w1 - vo.w0;
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(vo.n) * H * W * 256;
+    if (idx >= total) return;
+    const int c = int(idx % 256);
+    const int64_t pos = idx / 256;
+    const int xw = int(pos % W), y = int((pos / W) % H), b = int(pos / (int64_t(W) * H));
+    const float v = __half2float(cnet[((int64_t(b) * vi.Hp + y + vi.h0) * vi.Wp + xw + vi.w0) * 256 + c]);
+    const int64_t orow = (int64_t(b) * vo.Hp + y + vo.h0) * vo.Wp + xw + vo.w0;
+    if (c < 128) {
+        hx[orow * ld + c] = __float2half_rn(tanhf(v));
+    } else {
+        const __half r = __float2half_rn(fmaxf(v, 0.f));
+        hx[orow * ld + c] = r;
+        qx[orow * ld + c] = r;
+    }
+}
+
+// qx[:, 0:128] = r * h ; qx[:, 256:392] = hx[:, 256:392] (motion features + flow), valid rows.  zr = [z | r].
+__global__ void gru_rh_kernel(const __half* __restrict__ hx, const __half* __restrict__ zr, __half* __restrict__ qx,
+                              Vol2 v, int ld) {
+    const int H = v.h1 - v.h0, W = v.w1 - v.w0;
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(v.n) * H * W * 33;       // 16 groups of 8 for r*h + 17 groups for cols 256..391
+    if (idx >= total) return;
+    const int gidx = int(idx % 33);
+    const int64_t pos = idx / 33;
+    const int xw = int(pos % W), y = int((pos / W) % H), b = int(pos / (int64_t(W) * H));
+    const int64_t row = (int64_t(b) * v.Hp + y + v.h0) * v.Wp + xw + v.w0;
+    if (gidx < 16) {
+        const uint4 hr = *reinterpret_cast<const uint4*>(hx + row * ld + gidx * 8);
+        const uint4 rr = *reinterpret_cast<const uint4*>(zr + row * 256 + 128 + gidx * 8);
+        const __half2* hh = reinterpret_cast<const __half2*>(&hr);
+        const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 a = __half22float2(hh[j]), r = __half22float2(rh[j]);
+            oh[j] = __floats2half2_rn(a.x * r.x, a.y * r.y);
+        }
+        *reinterpret_cast<uint4*>(qx + row * ld + gidx * 8) = o;
+    } else {
+        const int c = 256 + (gidx - 16) * 8;
+        *reinterpret_cast<uint4*>(qx + row * ld + c) = *reinterpret_cast<const uint4*>(hx + row * ld + c);
+    }
+}
+
+// h = (1 - z) * h + z * q   (update.py:55,62), valid rows, in place in hx[:, 0:128]
+__global__ void gru_update_kernel(__half* __restrict__ hx, const __half* __restrict__ zr, const __half* __restrict__ q,
+                                  Vol2 v, int ld) {
+    const int H = v.h1 - v.h0, W = v.w1 - v.w0;
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(v.n) * H * W * 16;
+    if (idx >= total) return;
+    const int g8 = int(idx % 16);
+    const int64_t pos = idx / 16;
+    const int xw = int(pos % W), y = int((pos / W) % H), b = int(pos / (int64_t(W) * H));
+    const int64_t row = (int64_t(b) * v.Hp + y + v.h0) * v.Wp + xw + v.w0;
+    const uint4 hr = *reinterpret_cast<const uint4*>(hx + row * ld + g8 * 8);
+    const uint4 zz = *reinterpret_cast<const uint4*>(zr + row * 256 + g8 * 8);
+    const uint4 qq = *reinterpret_cast<const uint4*>(q + row * 128 + g8 * 8);
+    const __half2* hh = reinterpret_cast<const __half2*>(&hr);
+    const __half2* zh = reinterpret_cast<const __half2*>(&zz);
+    const __half2* qh = reinterpret_cast<const __half2*>(&qq);
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 a = __half22float2(hh[j]), z = __half22float2(zh[j]), qv = __half22float2(qh[j]);
+        oh[j] = __floats2half2_rn((1.f - z.x) * a.x + z.x * qv.x, (1.f - z.y) * a.y + z.y * qv.y);
+    }
+    *reinterpret_cast<uint4*>(hx + row * ld + g8 * 8) = o;
+}
+
+// coords1 += delta (fp32, first 2 of 8 GEMM output columns; delta == nullptr initialises coords to the grid);
+// flow = coords1 - coords0 written (fp16) to the flow slots of hx / qx (cols 384,385) and of flow8 (cols 0,1).
+__global__ void coords_update_kernel(float* __restrict__ coords1, const float* __restrict__ delta, __half* __restrict__ hx,
+                                     __half* __restrict__ qx, __half* __restrict__ flow8, Vol2 v, int ld) {
+    const int H = v.h1 - v.h0, W = v.w1 - v.w0;
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(v.n) * H * W;
+    if (idx >= total) return;
+    const int xw = int(idx % W), y = int((idx / W) % H), b = int(idx / (int64_t(W) * H));
+    const int64_t row = (int64_t(b) * v.Hp + y + v.h0) * v.Wp + xw + v.w0;
+    float cx, cy;
+    if (delta) {
+        cx = coords1[idx * 2] + delta[row * 8];
+        cy = coords1[idx * 2 + 1] + delta[row * 8 + 1];
+    } else {
+        cx = float(xw); cy = float(y);
+    }
+    coords1[idx * 2] = cx;
+    coords1[idx * 2 + 1] = cy;
+    const __half fx = __float2half_rn(cx - float(xw)), fy = __float2half_rn(cy - float(y));
+    hx[row * ld + 384] = fx; hx[row * ld + 385] = fy;
+    qx[row * ld + 384] = fx; qx[row * ld + 385] = fy;
+    flow8[row * 8] = fx; flow8[row * 8 + 1] = fy;
+}
+
+// RAFT.upsample_flow (raft.py:100-111): convex combination of the 3x3 neighbourhood of 8*flow with
+// softmax(mask over the 9 taps); mask channel = k*64 + sy*8 + sx.  mask already carries the 0.25 factor.
+// One thread per output pixel pair (both flow components).
+// The output is the window [oy, oy+Ho) x [ox, ox+Wo) of the padded flow (InputPadder.unpad, raft.py:41-44).
+__global__ void upsample_flow_kernel(const float* __restrict__ coords1, const float* __restrict__ mask, Vol2 v, int n,
+                                     int H8, int W8, int oy, int ox, int Ho, int Wo, float* __restrict__ flow_up) {
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(n) * Ho * Wo;
+    if (idx >= total) return;
+    const int Xo = int(idx % Wo), Yo = int((idx / Wo) % Ho), b = int(idx / (int64_t(Wo) * Ho));
+    const int X = Xo + ox, Y = Yo + oy;
+    const int x = X >> 3, sx = X & 7, y = Y >> 3, sy = Y & 7;
+    const int64_t row = (int64_t(b) * v.Hp + y + v.h0) * v.Wp + x + v.w0;
+    const float* m = mask + row * 576 + sy * 8 + sx;
+    float mv[9], mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { mv[k] = m[k * 64]; mx = fmaxf(mx, mv[k]); }
+    float den = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { mv[k] = __expf(mv[k] - mx); den += mv[k]; }
+    float ux = 0.f, uy = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;       // F.unfold(3x3, padding=1): zeros outside
+        if (yy >= 0 && yy < H8 && xx >= 0 && xx < W8) {
+            const int64_t qi = (int64_t(b) * H8 + yy) * W8 + xx;
+            ux += mv[k] * 8.f * (coords1[qi * 2] - float(xx));
+            uy += mv[k] * 8.f * (coords1[qi * 2 + 1] - float(yy));
+        }
+    }
+    const float inv = 1.f / den;
+    flow_up[((int64_t(b) * 2 + 0) * Ho + Yo) * Wo + Xo] = ux * inv;
+    flow_up[((int64_t(b) * 2 + 1) * Ho + Yo) * Wo + Xo] = uy * inv;
+}
+
+// diagnostics: valid region of channels [c0, c0+cc) of a bordered fp16 volume -> fp32 NCHW
+__global__ void unpack2d_kernel(const __half* __restrict__ in, Vol2 v, int ld, int c0, int cc, float* __restrict__ out) {
+    const int H = v.h1 - v.h0, W = v.w1 - v.w0;
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(v.n) * cc * H * W;
+    if (idx >= total) return;
+    const int xw = int(idx % W), y = int((idx / W) % H), c = int((idx / (int64_t(W) * H)) % cc);
+    const int b = int(idx / (int64_t(W) * H * cc));
+    out[idx] = __half2float(in[((int64_t(b) * v.Hp + y + v.h0) * v.Wp + xw + v.w0) * ld + c0 + c]);
+}
+
+}  // namespace
+
+#define LAUNCH_CHECK() do { VF_CUDA(cudaGetLastError()); return VF_OK; } while (0)
+
+int raft_input_pack(const void* img, int is_u8, int chw, int n, int Hs, int Ws, int pad_top, int pad_left, int H, int W,
+                    __half* out, int Hq, int Wq, cudaStream_t s) {
+    const int64_t total = int64_t(n) * Hq * Wq;
+    if (is_u8) raft_input_pack_kernel<uint8_t><<<nb(total, 256), 256, 0, s>>>(static_cast<const uint8_t*>(img), n, Hs, Ws, pad_top, pad_left, H, W, chw, out, Hq, Wq);
+    else       raft_input_pack_kernel<float><<<nb(total, 256), 256, 0, s>>>(static_cast<const float*>(img), n, Hs, Ws, pad_top, pad_left, H, W, chw, out, Hq, Wq);
+    LAUNCH_CHECK();
+}
+int raft_phase_repack(const __half* in, const Vol2& vi, int C, __half* out, const Vol2& vo, cudaStream_t s) {
+    const int64_t total = int64_t(vo.n) * vo.Hp * vo.Wp * 4 * (C / 8);
+    phase_repack_kernel<<<nb(total, 256), 256, 0, s>>>(in, vi, C, out, vo);
+    LAUNCH_CHECK();
+}
+int raft_instnorm_stats(const __half* x, const Vol2& v, int C, double* stats, cudaStream_t s) {
+    VF_CUDA(cudaMemsetAsync(stats, 0, size_t(v.n) * C * 2 * sizeof(double), s));
+    const int H = v.h1 - v.h0;
+    const int chunks = H < 32 ? H : 32;
+    instnorm_stats_kernel<<<dim3(chunks, v.n), C, 0, s>>>(x, v, C, stats);
+    LAUNCH_CHECK();
+}
+int raft_instnorm_apply(const __half* a, const double* a_stats, const __half* res, const double* res_stats, __half* out,
+                        const Vol2& v, int C, cudaStream_t s) {
+    const int64_t total = int64_t(v.n) * (v.h1 - v.h0) * (v.w1 - v.w0) * (C / 8);
+    instnorm_apply_kernel<<<nb(total, 256), 256, 0, s>>>(a, a_stats, res, res_stats, out, v, C);
+    LAUNCH_CHECK();
+}
+int raft_add_relu(const __half* a, const __half* b, __half* out, const Vol2& v, int C, cudaStream_t s) {
+    const int64_t total = int64_t(v.n) * (v.h1 - v.h0) * (v.w1 - v.w0) * (C / 8);
+    add_relu_kernel<<<nb(total, 256), 256, 0, s>>>(a, b, out, v, C);
+    LAUNCH_CHECK();
+}
+int raft_gather_valid(const __half* in, const Vol2& v, int C, int ld, __half* out, cudaStream_t s) {
+    const int64_t total = int64_t(v.n) * (v.h1 - v.h0) * (v.w1 - v.w0) * (C / 8);
+    gather_valid_kernel<<<nb(total, 256), 256, 0, s>>>(in, v, C, ld, out);
+    LAUNCH_CHECK();
+}
+int raft_corr_pool(float* corr, int64_t rows, int ld, int off_in, int Hi, int Wi, int off_out, cudaStream_t s) {
+    const int64_t total = rows * (Hi / 2) * (Wi / 2);
+    if (total <= 0) return VF_OK;
+    corr_pool_kernel<<<nb(total, 256), 256, 0, s>>>(corr, rows, ld, off_in, Hi, Wi, off_out);
+    LAUNCH_CHECK();
+}
+int raft_corr_lookup(const float* corr, int ld, const float* coords, int n, int H8, int W8, __half* out, const Vol2& vo,
+                     int out_ld, cudaStream_t s) {
+    const int64_t warps = int64_t(n) * H8 * W8 * 4;
+    corr_lookup_kernel<<<nb(warps * 32, 256), 256, 0, s>>>(corr, ld, coords, n, H8, W8, out, vo, out_ld);
+    LAUNCH_CHECK();
+}
+int raft_cnet_split(const __half* cnet, const Vol2& vi, __half* hx, __half* qx, const Vol2& vo, int ld, cudaStream_t s) {
+    const int64_t total = int64_t(vo.n) * (vo.h1 - vo.h0) * (vo.w1 - vo.w0) * 256;
+    cnet_split_kernel<<<nb(total, 256), 256, 0, s>>>(cnet, vi, hx, qx, vo, ld);
+    LAUNCH_CHECK();
+}
+int raft_gru_rh(const __half* hx, const __half* zr, __half* qx, const Vol2& v, int ld, cudaStream_t s) {
+    const int64_t total = int64_t(v.n) * (v.h1 - v.h0) * (v.w1 - v.w0) * 33;
+    gru_rh_kernel<<<nb(total, 256), 256, 0, s>>>(hx, zr, qx, v, ld);
+    LAUNCH_CHECK();
+}
+int raft_gru_update(__half* hx, const __half* zr, const __half* q, const Vol2& v, int ld, cudaStream_t s) {
+    const int64_t total = int64_t(v.n) * (v.h1 - v.h0) * (v.w1 - v.w0) * 16;
+    gru_update_kernel<<<nb(total, 256), 256, 0, s>>>(hx, zr, q, v, ld);
+    LAUNCH_CHECK();
+}
+int raft_coords_update(float* coords1, const float* delta, __half* hx, __half* qx, __half* flow8, const Vol2& v, int ld,
+                       cudaStream_t s) {
+    const int64_t total = int64_t(v.n) * (v.h1 - v.h0) * (v.w1 - v.w0);
+    coords_update_kernel<<<nb(total, 256), 256, 0, s>>>(coords1, delta, hx, qx, flow8, v, ld);
+    LAUNCH_CHECK();
+}
+int raft_upsample_flow(const float* coords1, const float* mask, const Vol2& v, int n, int H8, int W8, int oy, int ox,
+                       int Ho, int Wo, float* flow_up, cudaStream_t s) {
+    const int64_t total = int64_t(n) * Ho * Wo;
+    upsample_flow_kernel<<<nb(total, 256), 256, 0, s>>>(coords1, mask, v, n, H8, W8, oy, ox, Ho, Wo, flow_up);
+    LAUNCH_CHECK();
+}
+int raft_unpack2d(const __half* in, const Vol2& v, int ld, int c0, int cc, float* out, cudaStream_t s) {
+    const int64_t total = int64_t(v.n) * cc * (v.h1 - v.h0) * (v.w1 - v.w0);
+    unpack2d_kernel<<<nb(total, 256), 256, 0, s>>>(in, v, ld, c0, cc, out);
+    LAUNCH_CHECK();
+}
+
+}  // namespace vf
