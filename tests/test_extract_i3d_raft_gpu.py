@@ -1,0 +1,93 @@
+"""ExtractI3D / ExtractRAFT (reference-facing classes) on a synthetic video, real checkpoints, against the oracle run
+on the same decoded frames."""
+import argparse
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HAVE = all(os.path.exists(os.path.join(ROOT, "checkpoints", f)) for f in ("i3d_rgb.pt", "i3d_flow.pt", "raft-sintel.pth"))
+
+
+def _write_video(path, n, h=120, w=160, fps=25.0):
+    import cv2
+    from oracle import raft_net
+    fr = raft_net.synthetic_frames(n, h, w, seed=11, shift=(0.8, 0.5)).permute(0, 2, 3, 1).numpy().astype(np.uint8)
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), fps, (w, h))
+    assert vw.isOpened()
+    for f in fr:
+        vw.write(f)
+    vw.release()
+
+
+def _ns(**kw):
+    d = dict(feature_type='i3d', video_paths=None, flow_paths=None, file_with_video_paths=None, video_dir=None, flow_dir=None,
+             extraction_fps=None, extract_method=None, on_extraction='save_numpy', output_path='./output',
+             output_direct=False, tmp_path='./tmp', streams=None, flow_type='raft', stack_size=None, step_size=None,
+             show_pred=False, keep_tmp_files=False, batch_size=1, resize_to_smaller_edge=True, side_size=None)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+@pytest.mark.skipif(not HAVE, reason="reference checkpoint copies not present (scripts/fetch_checkpoints.py)")
+def test_extract_i3d_two_streams_vs_oracle(cuda_device, tmp_path):
+    from PIL import Image
+    from oracle import i3d_net, raft_net
+    from video_features_b200 import utils
+    from video_features_b200.extract.extract_i3d import ExtractI3D
+    vid = str(tmp_path / "clip.mp4")
+    _write_video(vid, 20)
+    out = str(tmp_path / "out")
+    ex = ExtractI3D(_ns(video_paths=[vid], output_path=out, tmp_path=str(tmp_path / "tmp"), stack_size=12, step_size=12),
+                    external_call=True)
+    res = ex(torch.zeros([1], dtype=torch.long, device=cuda_device))[0]
+    assert set(res) == {'rgb', 'flow', 'fps', 'timestamps_ms'}
+    assert res['rgb'].shape == (1, 1024) and res['flow'].shape == (1, 1024) and res['rgb'].dtype == np.float64
+    # oracle on the same decoded frames: PIL bilinear resize to 256 -> rgb / RAFT+flow transforms -> I3D
+    rd = utils.VideoReader(vid)
+    frames = [rd.get_frame(i) for i in range(13)]
+    rs = torch.stack([torch.from_numpy(np.asarray(Image.fromarray(f).resize((341, 256), Image.BILINEAR)).copy())
+                      for f in frames]).permute(0, 3, 1, 2).float().to(cuda_device)
+    sd_rgb = {k: v.to(cuda_device) for k, v in torch.load(os.path.join(ROOT, "checkpoints", "i3d_rgb.pt")).items()}
+    ref_rgb = i3d_net.forward_features(sd_rgb, i3d_net.rgb_transform(rs[:-1]))
+    rel = float((torch.from_numpy(res['rgb']).to(cuda_device) - ref_rgb).norm() / ref_rgb.norm())
+    print("ExtractI3D rgb vs oracle:", rel)
+    assert rel < 1e-3
+    sd_raft = {k: v.to(cuda_device) for k, v in torch.load(os.path.join(ROOT, "checkpoints", "raft-sintel.pth")).items()}
+    xp = raft_net.pad(rs)
+    flow = raft_net.forward(sd_raft, xp[:-1], xp[1:], 20)                # padded, never unpadded (extract_i3d.py:172)
+    sd_flow = {k: v.to(cuda_device) for k, v in torch.load(os.path.join(ROOT, "checkpoints", "i3d_flow.pt")).items()}
+    ref_flow = i3d_net.forward_features(sd_flow, i3d_net.flow_transform(flow))
+    rel = float((torch.from_numpy(res['flow']).to(cuda_device) - ref_flow).norm() / ref_flow.norm())
+    print("ExtractI3D flow (RAFT -> I3D) vs oracle:", rel)
+    assert rel < 3e-3      # quantisation to 8-bit flow levels amplifies sub-1e-3 flow differences at rounding boundaries
+
+
+@pytest.mark.skipif(not HAVE, reason="reference checkpoint copies not present (scripts/fetch_checkpoints.py)")
+def test_extract_raft_writes_flow(cuda_device, tmp_path):
+    from oracle import raft_net
+    from video_features_b200.extract.extract_raft import ExtractRAFT
+    vid = str(tmp_path / "clip2.mp4")
+    _write_video(vid, 6, h=96, w=128)
+    out = str(tmp_path / "out")
+    ex = ExtractRAFT(_ns(feature_type='raft', video_paths=[vid], output_path=out, tmp_path=str(tmp_path / "tmp"), batch_size=2))
+    assert ex(torch.zeros([1], dtype=torch.long, device=cuda_device)) is None
+    flow = np.load(os.path.join(out, "raft", "clip2_raft.npy"))
+    assert flow.shape == (5, 2, 96, 128) and flow.dtype == np.float64
+    import cv2
+    cap = cv2.VideoCapture(vid)
+    fr = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        fr.append(cv2.cvtColor(f, cv2.COLOR_BGR2RGB))
+    x = torch.from_numpy(np.stack(fr)).permute(0, 3, 1, 2).float().to(cuda_device)
+    sd = {k: v.to(cuda_device) for k, v in torch.load(os.path.join(ROOT, "checkpoints", "raft-sintel.pth")).items()}
+    ref = raft_net.forward(sd, x[:-1], x[1:], 20).cpu().numpy()
+    rel = np.linalg.norm(flow - ref) / np.linalg.norm(ref)
+    print("ExtractRAFT vs oracle:", rel)
+    assert rel < 1e-3

@@ -56,8 +56,10 @@ struct vf_raft {
     __half *fmap_b = nullptr, *fmaps = nullptr, *cnet_b = nullptr;
     double *st_a = nullptr, *st_b = nullptr;
     float *corr = nullptr, *coords1 = nullptr, *delta = nullptr, *mask = nullptr;
+    float *rawA = nullptr, *rawB = nullptr;     // fp32 conv outputs feeding InstanceNorm
+    float *h32 = nullptr, *zr = nullptr, *qb = nullptr;   // fp32 GRU state and gates
     __half *corrfeat = nullptr, *c1 = nullptr, *c2f = nullptr, *f1 = nullptr, *flow8 = nullptr, *hx = nullptr, *qx = nullptr,
-           *zr = nullptr, *qb = nullptr, *fh = nullptr, *mk = nullptr;
+           *fh = nullptr, *mk = nullptr;
     int64_t launches = 0;
     // geometry of the last call (for debug reads)
     int last_n = 0, last_H8 = 0, last_W8 = 0, corr_ld = 0, P8 = 0;
@@ -251,23 +253,23 @@ static int run_encoder(vf_raft* h, const vf_raft::Enc& e, bool inst, int m, int 
     const Vol2 g4{m, H / 4 + 2, W / 4 + 2, 1, 1 + H / 4, 1, 1 + W / 4};
     const Vol2 g8{m, H / 8 + 2, W / 8 + 2, 1, 1 + H / 8, 1, 1 + W / 8};
     __half *x = h->bufA, *y = h->bufB, *r = h->bufC, *r2 = h->bufD, *ph = h->bufE;
-    const int relu_if_bn = inst ? VF_ACT_NONE : VF_ACT_RELU;
-    auto norm_relu = [&](const __half* raw, __half* dst, const Vol2& v, int C) -> int {   // dst = relu(IN(raw))
+    float *rf = h->rawA, *rf2 = h->rawB;
+    auto norm_relu = [&](const float* raw, __half* dst, const Vol2& v, int C) -> int {   // dst = relu(IN(raw))
         VF_TRY(raft_instnorm_stats(raw, v, C, h->st_a, s));
         h->launches += 2;
-        return raft_instnorm_apply(raw, h->st_a, nullptr, nullptr, dst, v, C, s);
+        return raft_instnorm_apply(raw, h->st_a, nullptr, nullptr, nullptr, dst, v, C, s);
     };
     // conv1 + norm1 + relu
-    if (inst) { VF_TRY(run_conv(h, e.conv1, h->s0, 16, g2, r, 64, 0, VF_ACT_NONE, s)); VF_TRY(norm_relu(r, x, g2, 64)); }
+    if (inst) { VF_TRY(run_conv(h, e.conv1, h->s0, 16, g2, rf, 64, 1, VF_ACT_NONE, s)); VF_TRY(norm_relu(rf, x, g2, 64)); }
     else      { VF_TRY(run_conv(h, e.conv1, h->s0, 16, g2, x, 64, 0, VF_ACT_RELU, s)); }
     // a stride-1 residual block at geometry v with C channels: x <- relu(x + relu(norm2(conv2(relu(norm1(conv1(x)))))))
     auto res_block = [&](const ConvW& c1, const ConvW& c2, const Vol2& v, int C) -> int {
         if (inst) {
-            VF_TRY(run_conv(h, c1, x, C, v, r, C, 0, VF_ACT_NONE, s));
-            VF_TRY(norm_relu(r, y, v, C));
-            VF_TRY(run_conv(h, c2, y, C, v, r, C, 0, VF_ACT_NONE, s));
-            VF_TRY(raft_instnorm_stats(r, v, C, h->st_a, s));
-            VF_TRY(raft_instnorm_apply(r, h->st_a, x, nullptr, x, v, C, s));
+            VF_TRY(run_conv(h, c1, x, C, v, rf, C, 1, VF_ACT_NONE, s));
+            VF_TRY(norm_relu(rf, y, v, C));
+            VF_TRY(run_conv(h, c2, y, C, v, rf, C, 1, VF_ACT_NONE, s));
+            VF_TRY(raft_instnorm_stats(rf, v, C, h->st_a, s));
+            VF_TRY(raft_instnorm_apply(rf, h->st_a, x, nullptr, nullptr, x, v, C, s));
             h->launches += 2;
         } else {
             VF_TRY(run_conv(h, c1, x, C, v, y, C, 0, VF_ACT_RELU, s));
@@ -285,13 +287,13 @@ static int run_encoder(vf_raft* h, const vf_raft::Enc& e, bool inst, int m, int 
         VF_TRY(raft_phase_repack(x, vin, Cin, ph, vout, s));
         h->launches += 1;
         if (inst) {
-            VF_TRY(run_conv(h, c1, ph, 4 * Cin, vout, r, Cout, 0, VF_ACT_NONE, s));
-            VF_TRY(norm_relu(r, y, vout, Cout));
-            VF_TRY(run_conv(h, c2, y, Cout, vout, r, Cout, 0, VF_ACT_NONE, s));
-            VF_TRY(run_conv(h, dn, ph, 4 * Cin, vout, r2, Cout, 0, VF_ACT_NONE, s));
-            VF_TRY(raft_instnorm_stats(r, vout, Cout, h->st_a, s));
-            VF_TRY(raft_instnorm_stats(r2, vout, Cout, h->st_b, s));
-            VF_TRY(raft_instnorm_apply(r, h->st_a, r2, h->st_b, x, vout, Cout, s));    // relu(IN(down) + relu(IN(c2)))
+            VF_TRY(run_conv(h, c1, ph, 4 * Cin, vout, rf, Cout, 1, VF_ACT_NONE, s));
+            VF_TRY(norm_relu(rf, y, vout, Cout));
+            VF_TRY(run_conv(h, c2, y, Cout, vout, rf, Cout, 1, VF_ACT_NONE, s));
+            VF_TRY(run_conv(h, dn, ph, 4 * Cin, vout, rf2, Cout, 1, VF_ACT_NONE, s));
+            VF_TRY(raft_instnorm_stats(rf, vout, Cout, h->st_a, s));
+            VF_TRY(raft_instnorm_stats(rf2, vout, Cout, h->st_b, s));
+            VF_TRY(raft_instnorm_apply(rf, h->st_a, nullptr, rf2, h->st_b, x, vout, Cout, s));   // relu(IN(down) + relu(IN(c2)))
             h->launches += 3;
         } else {
             VF_TRY(run_conv(h, c1, ph, 4 * Cin, vout, y, Cout, 0, VF_ACT_RELU, s));
@@ -379,6 +381,7 @@ int vf_raft_create(vf_raft_t** out, const vf_named_tensor* tensors, int n_tensor
         VF_TRY(ralloc(h, &h->s0, rows2 * 16));
         VF_TRY(ralloc(h, &h->bufA, enc_elems)); VF_TRY(ralloc(h, &h->bufB, enc_elems));
         VF_TRY(ralloc(h, &h->bufC, enc_elems)); VF_TRY(ralloc(h, &h->bufD, enc_elems));
+        VF_TRY(ralloc(h, &h->rawA, enc_elems)); VF_TRY(ralloc(h, &h->rawB, enc_elems));
         const size_t ph_elems = rows4 * 256 > rows8e * 384 ? rows4 * 256 : rows8e * 384;
         VF_TRY(ralloc(h, &h->bufE, ph_elems));
         VF_TRY(ralloc(h, &h->fmap_b, rows8e * 256));
@@ -394,6 +397,7 @@ int vf_raft_create(vf_raft_t** out, const vf_named_tensor* tensors, int n_tensor
         VF_TRY(ralloc(h, &h->flow8, rows8u * 8));     VF_TRY(ralloc(h, &h->hx, rows8u * HX));
         VF_TRY(ralloc(h, &h->qx, rows8u * HX));       VF_TRY(ralloc(h, &h->zr, rows8u * 256));
         VF_TRY(ralloc(h, &h->qb, rows8u * 128));      VF_TRY(ralloc(h, &h->fh, rows8u * 256));
+        VF_TRY(ralloc(h, &h->h32, rows8u * 128));
         VF_TRY(ralloc(h, &h->mk, rows8u * 256));
         VF_TRY(ralloc(h, &h->delta, rows8u * 8));     VF_TRY(ralloc(h, &h->mask, rows8u * 576));
         return VF_OK;
@@ -467,7 +471,7 @@ int vf_raft_flow(vf_raft_t* h, const void* frames, int is_u8, int chw_layout, in
     VF_CUDA(cudaMemsetAsync(h->qx, 0, rows8u * HX * sizeof(__half), s));
     VF_CUDA(cudaMemsetAsync(h->flow8, 0, rows8u * 8 * sizeof(__half), s));
     VF_CUDA(cudaMemsetAsync(h->corrfeat, 0, rows8u * CF * sizeof(__half), s));
-    VF_TRY(raft_cnet_split(h->cnet_b, g8e, h->hx, h->qx, g8u, HX, s));
+    VF_TRY(raft_cnet_split(h->cnet_b, g8e, h->hx, h->qx, h->h32, g8u, HX, s));
     VF_TRY(raft_coords_update(h->coords1, nullptr, h->hx, h->qx, h->flow8, g8u, HX, s));    // coords1 = grid, flow = 0
     h->launches += 4;
     // ---- refinement iterations
@@ -481,10 +485,10 @@ int vf_raft_flow(vf_raft_t* h, const void* frames, int is_u8, int chw_layout, in
         for (int dir = 0; dir < 2; ++dir) {
             const ConvW& zr = dir == 0 ? h->zr1 : h->zr2;
             const ConvW& qq = dir == 0 ? h->q1 : h->q2;
-            VF_TRY(run_conv(h, zr, h->hx, HX, g8u, h->zr, 256, 0, VF_ACT_SIGMOID, s));
-            VF_TRY(raft_gru_rh(h->hx, h->zr, h->qx, g8u, HX, s));
-            VF_TRY(run_conv(h, qq, h->qx, HX, g8u, h->qb, 128, 0, VF_ACT_TANH, s));
-            VF_TRY(raft_gru_update(h->hx, h->zr, h->qb, g8u, HX, s));
+            VF_TRY(run_conv(h, zr, h->hx, HX, g8u, h->zr, 256, 1, VF_ACT_SIGMOID, s));
+            VF_TRY(raft_gru_rh(h->hx, h->h32, h->zr, h->qx, g8u, HX, s));
+            VF_TRY(run_conv(h, qq, h->qx, HX, g8u, h->qb, 128, 1, VF_ACT_TANH, s));
+            VF_TRY(raft_gru_update(h->hx, h->h32, h->zr, h->qb, g8u, HX, s));
         }
         VF_TRY(run_conv(h, h->fh1, h->hx, HX, g8u, h->fh, 256, 0, VF_ACT_RELU, s));
         VF_TRY(run_conv(h, h->fh2, h->fh, 256, g8u, h->delta, 8, 1, VF_ACT_NONE, s));

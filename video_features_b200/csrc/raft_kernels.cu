@@ -64,17 +64,17 @@ __global__ void phase_repack_kernel(const __half* __restrict__ in, Vol2 vi, int 
 
 // InstanceNorm2d statistics: per (sample, channel) sum and sum of squares over the valid region, accumulated in
 // double (fp32 partials per thread).  grid (row chunks, n), block = C threads.
-__global__ void instnorm_stats_kernel(const __half* __restrict__ x, Vol2 v, int C, double* __restrict__ stats) {
+__global__ void instnorm_stats_kernel(const float* __restrict__ x, Vol2 v, int C, double* __restrict__ stats) {
     const int b = blockIdx.y, c = threadIdx.x;
     const int H = v.h1 - v.h0, W = v.w1 - v.w0;
     const int rows_per = (H + gridDim.x - 1) / gridDim.x;
     const int y0 = blockIdx.x * rows_per, y1 = min(H, y0 + rows_per);
     double s = 0.0, ss = 0.0;
     for (int y = y0; y < y1; ++y) {
-        const __half* row = x + ((int64_t(b) * v.Hp + y + v.h0) * v.Wp + v.w0) * C + c;
+        const float* row = x + ((int64_t(b) * v.Hp + y + v.h0) * v.Wp + v.w0) * C + c;
         float fs = 0.f, fss = 0.f;
         for (int xw = 0; xw < W; ++xw) {
-            const float t = __half2float(row[int64_t(xw) * C]);
+            const float t = row[int64_t(xw) * C];
             fs += t;
             fss = fmaf(t, t, fss);
         }
@@ -86,43 +86,55 @@ __global__ void instnorm_stats_kernel(const __half* __restrict__ x, Vol2 v, int 
     }
 }
 
-// y = relu(IN(a))                                   (res == nullptr)
-// y = relu(res' + relu(IN(a)))  with res' = res or IN(res) (res_stats != nullptr)      -- ResidualBlock tail
-// only valid positions are touched (borders stay zero).  One thread = 8 channels.
-__global__ void instnorm_apply_kernel(const __half* __restrict__ a, const double* __restrict__ a_stats,
-                                      const __half* __restrict__ res, const double* __restrict__ res_stats,
-                                      __half* __restrict__ out, Vol2 v, int C) {
+// The raw conv outputs that feed InstanceNorm are kept in fp32 (an fp16 copy would lose |mean|/|std| bits in the
+// mean subtraction).
+// y = relu(IN(a))                                                    (res_h == res_raw == nullptr)
+// y = relu(res_h + relu(IN(a)))                                      stride-1 ResidualBlock tail (res_h: fp16 x)
+// y = relu(IN(res_raw) + relu(IN(a)))                                stride-2 ResidualBlock tail (norm3(downsample))
+// Every position of the volume is written; border positions get zeros (the next conv's padding).  8 channels/thread.
+__global__ void instnorm_apply_kernel(const float* __restrict__ a, const double* __restrict__ a_stats,
+                                      const __half* __restrict__ res_h, const float* __restrict__ res_raw,
+                                      const double* __restrict__ res_stats, __half* __restrict__ out, Vol2 v, int C) {
     const int cg = C >> 3;
     const int H = v.h1 - v.h0, W = v.w1 - v.w0;
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    const int64_t total = int64_t(v.n) * H * W * cg;
+    const int64_t total = int64_t(v.n) * v.Hp * v.Wp * cg;
     if (idx >= total) return;
     const int c8 = int(idx % cg);
     const int64_t pos = idx / cg;
-    const int xw = int(pos % W), y = int((pos / W) % H), b = int(pos / (int64_t(W) * H));
-    const int64_t off = ((int64_t(b) * v.Hp + y + v.h0) * v.Wp + xw + v.w0) * C + c8 * 8;
+    const int wq = int(pos % v.Wp), hq = int((pos / v.Wp) % v.Hp), b = int(pos / (int64_t(v.Wp) * v.Hp));
+    const int64_t off = pos * C + c8 * 8;
+    if (hq < v.h0 || hq >= v.h1 || wq < v.w0 || wq >= v.w1) {
+        *reinterpret_cast<uint4*>(out + off) = make_uint4(0, 0, 0, 0);
+        return;
+    }
     const double cnt = double(H) * double(W);
-    const uint4 raw = *reinterpret_cast<const uint4*>(a + off);
-    const __half* ah = reinterpret_cast<const __half*>(&raw);
-    uint4 rraw = make_uint4(0, 0, 0, 0);
-    if (res) rraw = *reinterpret_cast<const uint4*>(res + off);
-    const __half* rh = reinterpret_cast<const __half*>(&rraw);
+    float av[8], rv[8];
+    *reinterpret_cast<float4*>(av) = *reinterpret_cast<const float4*>(a + off);
+    *reinterpret_cast<float4*>(av + 4) = *reinterpret_cast<const float4*>(a + off + 4);
+    if (res_raw) {
+        *reinterpret_cast<float4*>(rv) = *reinterpret_cast<const float4*>(res_raw + off);
+        *reinterpret_cast<float4*>(rv + 4) = *reinterpret_cast<const float4*>(res_raw + off + 4);
+    } else if (res_h) {
+        const uint4 rr = *reinterpret_cast<const uint4*>(res_h + off);
+        const __half* rh = reinterpret_cast<const __half*>(&rr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rv[j] = __half2float(rh[j]);
+    }
     __align__(16) __half o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int c = c8 * 8 + j;
         const double m = a_stats[(int64_t(b) * C + c) * 2] / cnt;
         const double var = a_stats[(int64_t(b) * C + c) * 2 + 1] / cnt - m * m;
-        float y0 = (__half2float(ah[j]) - float(m)) * rsqrtf(float(var) + 1e-5f);
+        float y0 = float((double(av[j]) - m)) * rsqrtf(float(var) + 1e-5f);
         y0 = fmaxf(y0, 0.f);
-        if (res) {
-            float r = __half2float(rh[j]);
-            if (res_stats) {
-                const double rm = res_stats[(int64_t(b) * C + c) * 2] / cnt;
-                const double rv = res_stats[(int64_t(b) * C + c) * 2 + 1] / cnt - rm * rm;
-                r = (r - float(rm)) * rsqrtf(float(rv) + 1e-5f);
-            }
-            y0 = fmaxf(r + y0, 0.f);
+        if (res_raw) {
+            const double rm = res_stats[(int64_t(b) * C + c) * 2] / cnt;
+            const double rvv = res_stats[(int64_t(b) * C + c) * 2 + 1] / cnt - rm * rm;
+            y0 = fmaxf(float(double(rv[j]) - rm) * rsqrtf(float(rvv) + 1e-5f) + y0, 0.f);
+        } else if (res_h) {
+            y0 = fmaxf(rv[j] + y0, 0.f);
         }
         o[j] = __float2half_rn(y0);
     }
@@ -133,14 +145,17 @@ __global__ void instnorm_apply_kernel(const __half* __restrict__ a, const double
 __global__ void add_relu_kernel(const __half* __restrict__ a, const __half* __restrict__ bsrc, __half* __restrict__ out,
                                 Vol2 v, int C) {
     const int cg = C >> 3;
-    const int H = v.h1 - v.h0, W = v.w1 - v.w0;
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    const int64_t total = int64_t(v.n) * H * W * cg;
+    const int64_t total = int64_t(v.n) * v.Hp * v.Wp * cg;
     if (idx >= total) return;
     const int c8 = int(idx % cg);
     const int64_t pos = idx / cg;
-    const int xw = int(pos % W), y = int((pos / W) % H), b = int(pos / (int64_t(W) * H));
-    const int64_t off = ((int64_t(b) * v.Hp + y + v.h0) * v.Wp + xw + v.w0) * C + c8 * 8;
+    const int wq = int(pos % v.Wp), hq = int((pos / v.Wp) % v.Hp);
+    const int64_t off = pos * C + c8 * 8;
+    if (hq < v.h0 || hq >= v.h1 || wq < v.w0 || wq >= v.w1) {
+        *reinterpret_cast<uint4*>(out + off) = make_uint4(0, 0, 0, 0);
+        return;
+    }
     const uint4 ra = *reinterpret_cast<const uint4*>(a + off), rb = *reinterpret_cast<const uint4*>(bsrc + off);
     const __half2* ha = reinterpret_cast<const __half2*>(&ra);
     const __half2* hb = reinterpret_cast<const __half2*>(&rb);
@@ -225,7 +240,7 @@ __global__ void corr_lookup_kernel(const float* __restrict__ corr, int ld, const
 // context network output (raw conv2 output, 256 ch at border-1 geometry) -> hx: h = tanh(net) in cols [0,128),
 // inp = relu(inp) in cols [128,256) of both hx and qx (raft.py:141-143)
 __global__ void cnet_split_kernel(const __half* __restrict__ cnet, Vol2 vi, __half* __restrict__ hx,
-                                  __half* __restrict__ qx, Vol2 vo, int ld) {
+                                  __half* __restrict__ qx, float* __restrict__ h32, Vol2 vo, int ld) {
     const int H = vo.h1 - vo.h0, W = vo.w1 - vo.w0;
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t total = int64_t(vo.n) * H * W * 256;
@@ -236,7 +251,9 @@ __global__ void cnet_split_kernel(const __half* __restrict__ cnet, Vol2 vi, __ha
     const float v = __half2float(cnet[((int64_t(b) * vi.Hp + y + vi.h0) * vi.Wp + xw + vi.w0) * 256 + c]);
     const int64_t orow = (int64_t(b) * vo.Hp + y + vo.h0) * vo.Wp + xw + vo.w0;
     if (c < 128) {
-        hx[orow * ld + c] = __float2half_rn(tanhf(v));
+        const float t = tanhf(v);
+        h32[orow * 128 + c] = t;                      // fp32 master copy of the recurrent state
+        hx[orow * ld + c] = __float2half_rn(t);
     } else {
         const __half r = __float2half_rn(fmaxf(v, 0.f));
         hx[orow * ld + c] = r;
@@ -245,8 +262,8 @@ __global__ void cnet_split_kernel(const __half* __restrict__ cnet, Vol2 vi, __ha
 }
 
 // qx[:, 0:128] = r * h ; qx[:, 256:392] = hx[:, 256:392] (motion features + flow), valid rows.  zr = [z | r].
-__global__ void gru_rh_kernel(const __half* __restrict__ hx, const __half* __restrict__ zr, __half* __restrict__ qx,
-                              Vol2 v, int ld) {
+__global__ void gru_rh_kernel(const __half* __restrict__ hx, const float* __restrict__ h32, const float* __restrict__ zr,
+                              __half* __restrict__ qx, Vol2 v, int ld) {
     const int H = v.h1 - v.h0, W = v.w1 - v.w0;
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t total = int64_t(v.n) * H * W * 33;       // 16 groups of 8 for r*h + 17 groups for cols 256..391
@@ -256,17 +273,16 @@ __global__ void gru_rh_kernel(const __half* __restrict__ hx, const __half* __res
     const int xw = int(pos % W), y = int((pos / W) % H), b = int(pos / (int64_t(W) * H));
     const int64_t row = (int64_t(b) * v.Hp + y + v.h0) * v.Wp + xw + v.w0;
     if (gidx < 16) {
-        const uint4 hr = *reinterpret_cast<const uint4*>(hx + row * ld + gidx * 8);
-        const uint4 rr = *reinterpret_cast<const uint4*>(zr + row * 256 + 128 + gidx * 8);
-        const __half2* hh = reinterpret_cast<const __half2*>(&hr);
-        const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+        float hv[8], rv[8];
+        *reinterpret_cast<float4*>(hv) = *reinterpret_cast<const float4*>(h32 + row * 128 + gidx * 8);
+        *reinterpret_cast<float4*>(hv + 4) = *reinterpret_cast<const float4*>(h32 + row * 128 + gidx * 8 + 4);
+        *reinterpret_cast<float4*>(rv) = *reinterpret_cast<const float4*>(zr + row * 256 + 128 + gidx * 8);
+        *reinterpret_cast<float4*>(rv + 4) = *reinterpret_cast<const float4*>(zr + row * 256 + 128 + gidx * 8 + 4);
         uint4 o;
-        __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float2 a = __half22float2(hh[j]), r = __half22float2(rh[j]);
-            oh[j] = __floats2half2_rn(a.x * r.x, a.y * r.y);
-        }
+        o.x = pack_half2(hv[0] * rv[0], hv[1] * rv[1]);
+        o.y = pack_half2(hv[2] * rv[2], hv[3] * rv[3]);
+        o.z = pack_half2(hv[4] * rv[4], hv[5] * rv[5]);
+        o.w = pack_half2(hv[6] * rv[6], hv[7] * rv[7]);
         *reinterpret_cast<uint4*>(qx + row * ld + gidx * 8) = o;
     } else {
         const int c = 256 + (gidx - 16) * 8;
@@ -274,9 +290,10 @@ __global__ void gru_rh_kernel(const __half* __restrict__ hx, const __half* __res
     }
 }
 
-// h = (1 - z) * h + z * q   (update.py:55,62), valid rows, in place in hx[:, 0:128]
-__global__ void gru_update_kernel(__half* __restrict__ hx, const __half* __restrict__ zr, const __half* __restrict__ q,
-                                  Vol2 v, int ld) {
+// h = (1 - z) * h + z * q   (update.py:55,62) on the fp32 master state; the fp16 copy in hx[:, 0:128] is the GEMM
+// operand of the next convolutions.  z and q arrive as fp32 GEMM outputs.
+__global__ void gru_update_kernel(__half* __restrict__ hx, float* __restrict__ h32, const float* __restrict__ zr,
+                                  const float* __restrict__ q, Vol2 v, int ld) {
     const int H = v.h1 - v.h0, W = v.w1 - v.w0;
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t total = int64_t(v.n) * H * W * 16;
@@ -285,20 +302,20 @@ __global__ void gru_update_kernel(__half* __restrict__ hx, const __half* __restr
     const int64_t pos = idx / 16;
     const int xw = int(pos % W), y = int((pos / W) % H), b = int(pos / (int64_t(W) * H));
     const int64_t row = (int64_t(b) * v.Hp + y + v.h0) * v.Wp + xw + v.w0;
-    const uint4 hr = *reinterpret_cast<const uint4*>(hx + row * ld + g8 * 8);
-    const uint4 zz = *reinterpret_cast<const uint4*>(zr + row * 256 + g8 * 8);
-    const uint4 qq = *reinterpret_cast<const uint4*>(q + row * 128 + g8 * 8);
-    const __half2* hh = reinterpret_cast<const __half2*>(&hr);
-    const __half2* zh = reinterpret_cast<const __half2*>(&zz);
-    const __half2* qh = reinterpret_cast<const __half2*>(&qq);
-    uint4 o;
-    __half2* oh = reinterpret_cast<__half2*>(&o);
+    float hv[8], zv[8], qv[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float2 a = __half22float2(hh[j]), z = __half22float2(zh[j]), qv = __half22float2(qh[j]);
-        oh[j] = __floats2half2_rn((1.f - z.x) * a.x + z.x * qv.x, (1.f - z.y) * a.y + z.y * qv.y);
+    for (int k = 0; k < 2; ++k) {
+        *reinterpret_cast<float4*>(hv + 4 * k) = *reinterpret_cast<const float4*>(h32 + row * 128 + g8 * 8 + 4 * k);
+        *reinterpret_cast<float4*>(zv + 4 * k) = *reinterpret_cast<const float4*>(zr + row * 256 + g8 * 8 + 4 * k);
+        *reinterpret_cast<float4*>(qv + 4 * k) = *reinterpret_cast<const float4*>(q + row * 128 + g8 * 8 + 4 * k);
     }
-    *reinterpret_cast<uint4*>(hx + row * ld + g8 * 8) = o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hv[j] = (1.f - zv[j]) * hv[j] + zv[j] * qv[j];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        *reinterpret_cast<float4*>(h32 + row * 128 + g8 * 8 + 4 * k) = *reinterpret_cast<const float4*>(hv + 4 * k);
+    *reinterpret_cast<uint4*>(hx + row * ld + g8 * 8) = make_uint4(pack_half2(hv[0], hv[1]), pack_half2(hv[2], hv[3]),
+                                                                   pack_half2(hv[4], hv[5]), pack_half2(hv[6], hv[7]));
 }
 
 // coords1 += delta (fp32, first 2 of 8 GEMM output columns; delta == nullptr initialises coords to the grid);
@@ -388,21 +405,21 @@ int raft_phase_repack(const __half* in, const Vol2& vi, int C, __half* out, cons
     phase_repack_kernel<<<nb(total, 256), 256, 0, s>>>(in, vi, C, out, vo);
     LAUNCH_CHECK();
 }
-int raft_instnorm_stats(const __half* x, const Vol2& v, int C, double* stats, cudaStream_t s) {
+int raft_instnorm_stats(const float* x, const Vol2& v, int C, double* stats, cudaStream_t s) {
     VF_CUDA(cudaMemsetAsync(stats, 0, size_t(v.n) * C * 2 * sizeof(double), s));
     const int H = v.h1 - v.h0;
     const int chunks = H < 32 ? H : 32;
     instnorm_stats_kernel<<<dim3(chunks, v.n), C, 0, s>>>(x, v, C, stats);
     LAUNCH_CHECK();
 }
-int raft_instnorm_apply(const __half* a, const double* a_stats, const __half* res, const double* res_stats, __half* out,
-                        const Vol2& v, int C, cudaStream_t s) {
-    const int64_t total = int64_t(v.n) * (v.h1 - v.h0) * (v.w1 - v.w0) * (C / 8);
-    instnorm_apply_kernel<<<nb(total, 256), 256, 0, s>>>(a, a_stats, res, res_stats, out, v, C);
+int raft_instnorm_apply(const float* a, const double* a_stats, const __half* res_h, const float* res_raw,
+                        const double* res_stats, __half* out, const Vol2& v, int C, cudaStream_t s) {
+    const int64_t total = int64_t(v.n) * v.Hp * v.Wp * (C / 8);
+    instnorm_apply_kernel<<<nb(total, 256), 256, 0, s>>>(a, a_stats, res_h, res_raw, res_stats, out, v, C);
     LAUNCH_CHECK();
 }
 int raft_add_relu(const __half* a, const __half* b, __half* out, const Vol2& v, int C, cudaStream_t s) {
-    const int64_t total = int64_t(v.n) * (v.h1 - v.h0) * (v.w1 - v.w0) * (C / 8);
+    const int64_t total = int64_t(v.n) * v.Hp * v.Wp * (C / 8);
     add_relu_kernel<<<nb(total, 256), 256, 0, s>>>(a, b, out, v, C);
     LAUNCH_CHECK();
 }
@@ -423,19 +440,20 @@ int raft_corr_lookup(const float* corr, int ld, const float* coords, int n, int 
     corr_lookup_kernel<<<nb(warps * 32, 256), 256, 0, s>>>(corr, ld, coords, n, H8, W8, out, vo, out_ld);
     LAUNCH_CHECK();
 }
-int raft_cnet_split(const __half* cnet, const Vol2& vi, __half* hx, __half* qx, const Vol2& vo, int ld, cudaStream_t s) {
+int raft_cnet_split(const __half* cnet, const Vol2& vi, __half* hx, __half* qx, float* h32, const Vol2& vo, int ld,
+                    cudaStream_t s) {
     const int64_t total = int64_t(vo.n) * (vo.h1 - vo.h0) * (vo.w1 - vo.w0) * 256;
-    cnet_split_kernel<<<nb(total, 256), 256, 0, s>>>(cnet, vi, hx, qx, vo, ld);
+    cnet_split_kernel<<<nb(total, 256), 256, 0, s>>>(cnet, vi, hx, qx, h32, vo, ld);
     LAUNCH_CHECK();
 }
-int raft_gru_rh(const __half* hx, const __half* zr, __half* qx, const Vol2& v, int ld, cudaStream_t s) {
+int raft_gru_rh(const __half* hx, const float* h32, const float* zr, __half* qx, const Vol2& v, int ld, cudaStream_t s) {
     const int64_t total = int64_t(v.n) * (v.h1 - v.h0) * (v.w1 - v.w0) * 33;
-    gru_rh_kernel<<<nb(total, 256), 256, 0, s>>>(hx, zr, qx, v, ld);
+    gru_rh_kernel<<<nb(total, 256), 256, 0, s>>>(hx, h32, zr, qx, v, ld);
     LAUNCH_CHECK();
 }
-int raft_gru_update(__half* hx, const __half* zr, const __half* q, const Vol2& v, int ld, cudaStream_t s) {
+int raft_gru_update(__half* hx, float* h32, const float* zr, const float* q, const Vol2& v, int ld, cudaStream_t s) {
     const int64_t total = int64_t(v.n) * (v.h1 - v.h0) * (v.w1 - v.w0) * 16;
-    gru_update_kernel<<<nb(total, 256), 256, 0, s>>>(hx, zr, q, v, ld);
+    gru_update_kernel<<<nb(total, 256), 256, 0, s>>>(hx, h32, zr, q, v, ld);
     LAUNCH_CHECK();
 }
 int raft_coords_update(float* coords1, const float* delta, __half* hx, __half* qx, __half* flow8, const Vol2& v, int ld,

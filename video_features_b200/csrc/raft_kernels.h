@@ -17,17 +17,18 @@ struct Vol2 {
 int raft_input_pack(const void* img, int is_u8, int chw, int n, int Hs, int Ws, int pad_top, int pad_left, int H, int W,
                     __half* out, int Hq, int Wq, cudaStream_t s);
 int raft_phase_repack(const __half* in, const Vol2& vi, int C, __half* out, const Vol2& vo, cudaStream_t s);
-int raft_instnorm_stats(const __half* x, const Vol2& v, int C, double* stats, cudaStream_t s);
-int raft_instnorm_apply(const __half* a, const double* a_stats, const __half* res, const double* res_stats, __half* out,
-                        const Vol2& v, int C, cudaStream_t s);
+int raft_instnorm_stats(const float* x, const Vol2& v, int C, double* stats, cudaStream_t s);
+int raft_instnorm_apply(const float* a, const double* a_stats, const __half* res_h, const float* res_raw,
+                        const double* res_stats, __half* out, const Vol2& v, int C, cudaStream_t s);
 int raft_add_relu(const __half* a, const __half* b, __half* out, const Vol2& v, int C, cudaStream_t s);
 int raft_gather_valid(const __half* in, const Vol2& v, int C, int ld, __half* out, cudaStream_t s);
 int raft_corr_pool(float* corr, int64_t rows, int ld, int off_in, int Hi, int Wi, int off_out, cudaStream_t s);
 int raft_corr_lookup(const float* corr, int ld, const float* coords, int n, int H8, int W8, __half* out, const Vol2& vo,
                      int out_ld, cudaStream_t s);
-int raft_cnet_split(const __half* cnet, const Vol2& vi, __half* hx, __half* qx, const Vol2& vo, int ld, cudaStream_t s);
-int raft_gru_rh(const __half* hx, const __half* zr, __half* qx, const Vol2& v, int ld, cudaStream_t s);
-int raft_gru_update(__half* hx, const __half* zr, const __half* q, const Vol2& v, int ld, cudaStream_t s);
+int raft_cnet_split(const __half* cnet, const Vol2& vi, __half* hx, __half* qx, float* h32, const Vol2& vo, int ld,
+                    cudaStream_t s);
+int raft_gru_rh(const __half* hx, const float* h32, const float* zr, __half* qx, const Vol2& v, int ld, cudaStream_t s);
+int raft_gru_update(__half* hx, float* h32, const float* zr, const float* q, const Vol2& v, int ld, cudaStream_t s);
 int raft_coords_update(float* coords1, const float* delta, __half* hx, __half* qx, __half* flow8, const Vol2& v, int ld,
                        cudaStream_t s);
 int raft_upsample_flow(const float* coords1, const float* mask, const Vol2& v, int n, int H8, int W8, int oy, int ox,
