@@ -258,8 +258,11 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 }
                 fence_proxy_async();
                 named_bar_sync(1 + grp, 128);
-                if (agent && n < N) {
-                    tma_store_2d(&tmO, buf, n, m0);     // rows >= M and columns >= N are clipped by the TMA unit
+                if (agent) {
+                    // rows >= M and columns >= N are clipped by the TMA unit.  A group is committed for EVERY slice,
+                    // also for the (empty) ones right of N: wait_group.read<1> above counts groups, and skipping a
+                    // commit would let a buffer be rewritten while its previous store is still reading it.
+                    if (n < N) tma_store_2d(&tmO, buf, n, m0);
                     bulk_commit();
                 }
                 ++it;

@@ -522,10 +522,15 @@ int vf_raft_debug_read(vf_raft_t* h, int what, float* out, int64_t capacity, int
     else if (what == 2) { dims4[0] = n; dims4[1] = 128; dims4[2] = H8; dims4[3] = W8; }
     else if (what == 3) { dims4[0] = n; dims4[1] = 2; dims4[2] = H8; dims4[3] = W8; }
     else if (what == 4) { dims4[0] = n; dims4[1] = 324; dims4[2] = H8; dims4[3] = W8; }
+    else if (what == 5) { dims4[0] = n; dims4[1] = H8 * W8; dims4[2] = 1; dims4[3] = h->corr_ld; }   // raw pyramid rows
     else return fail(VF_ERR_INVALID, "raft_debug_read: unknown tensor id %d", what);
     need = int64_t(dims4[0]) * dims4[1] * dims4[2] * dims4[3];
     if (!out) return VF_OK;
     if (capacity < need) return fail(VF_ERR_INVALID, "raft_debug_read: capacity too small");
+    if (what == 5) {
+        VF_CUDA(cudaMemcpyAsync(out, h->corr, size_t(need) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        return VF_OK;
+    }
     if (what == 0) { Vol2 v = h->g8e; v.n = n + 1; return raft_unpack2d(h->fmap_b, v, 256, 0, 256, out, s); }
     if (what == 1) return raft_unpack2d(h->cnet_b, h->g8e, 256, 0, 256, out, s);
     if (what == 2) return raft_unpack2d(h->hx, h->g8u, HX, 0, 128, out, s);          // GRU hidden state
