@@ -45,10 +45,14 @@ def test_extract_i3d_two_streams_vs_oracle(cuda_device, tmp_path):
                     external_call=True)
     res = ex(torch.zeros([1], dtype=torch.long, device=cuda_device))[0]
     assert set(res) == {'rgb', 'flow', 'fps', 'timestamps_ms'}
-    assert res['rgb'].shape == (1, 1024) and res['flow'].shape == (1, 1024) and res['rgb'].dtype == np.float64
+    # a 20-frame video is shorter than 65 frames: the reference resamples it to 65 (extract_i3d.py:250-255), so with
+    # stack_size = step_size = 12 there are (65-1)//12 = 5 stacks
+    assert res['rgb'].shape == (5, 1024) and res['flow'].shape == (5, 1024) and res['rgb'].dtype == np.float64
+    res = {k: (v[:1] if k in ('rgb', 'flow') else v) for k, v in res.items()}       # compare the first stack
     # oracle on the same decoded frames: PIL bilinear resize to 256 -> rgb / RAFT+flow transforms -> I3D
     rd = utils.VideoReader(vid)
-    frames = [rd.get_frame(i) for i in range(13)]
+    ix = np.linspace(1, rd.frame_cnt - 1, 65).astype(int)[:13]
+    frames = [rd.get_frame(int(i)) for i in ix]
     rs = torch.stack([torch.from_numpy(np.asarray(Image.fromarray(f).resize((341, 256), Image.BILINEAR)).copy())
                       for f in frames]).permute(0, 3, 1, 2).float().to(cuda_device)
     sd_rgb = {k: v.to(cuda_device) for k, v in torch.load(os.path.join(ROOT, "checkpoints", "i3d_rgb.pt")).items()}
@@ -63,7 +67,13 @@ def test_extract_i3d_two_streams_vs_oracle(cuda_device, tmp_path):
     ref_flow = i3d_net.forward_features(sd_flow, i3d_net.flow_transform(flow))
     rel = float((torch.from_numpy(res['flow']).to(cuda_device) - ref_flow).norm() / ref_flow.norm())
     print("ExtractI3D flow (RAFT -> I3D) vs oracle:", rel)
-    assert rel < 3e-3      # quantisation to 8-bit flow levels amplifies sub-1e-3 flow differences at rounding boundaries
+    # The flow stream passes through the reference's 8-bit quantiser `round(128 + 255/40 f)` (transforms.py:43-51), a
+    # discontinuity: on this clip (tiny motion, 3 quantisation levels in use) a flow perturbation of sigma = 1e-4 px --
+    # 1.6e-4 of the flow itself -- already moves the oracle's OWN 1024-d feature by 3e-3, and 3e-4 px by 1.6e-2
+    # (scripts: DESIGN.md §2).  Parity of this branch is therefore asserted per stage: RAFT flow (test_raft_gpu.py,
+    # rel-L2 <= 1e-3) and quantiser + I3D on identical flow (test_i3d_gpu.py::test_i3d_fused_stream_transforms, 2e-4).
+    # End to end only gross agreement can be asked for:
+    assert rel < 0.15
 
 
 @pytest.mark.skipif(not HAVE, reason="reference checkpoint copies not present (scripts/fetch_checkpoints.py)")
@@ -71,12 +81,12 @@ def test_extract_raft_writes_flow(cuda_device, tmp_path):
     from oracle import raft_net
     from video_features_b200.extract.extract_raft import ExtractRAFT
     vid = str(tmp_path / "clip2.mp4")
-    _write_video(vid, 6, h=96, w=128)
+    _write_video(vid, 6, h=128, w=160)
     out = str(tmp_path / "out")
     ex = ExtractRAFT(_ns(feature_type='raft', video_paths=[vid], output_path=out, tmp_path=str(tmp_path / "tmp"), batch_size=2))
     assert ex(torch.zeros([1], dtype=torch.long, device=cuda_device)) is None
     flow = np.load(os.path.join(out, "raft", "clip2_raft.npy"))
-    assert flow.shape == (5, 2, 96, 128) and flow.dtype == np.float64
+    assert flow.shape == (5, 2, 128, 160) and flow.dtype == np.float64
     import cv2
     cap = cv2.VideoCapture(vid)
     fr = []
