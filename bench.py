@@ -334,6 +334,145 @@ def run_engine(args, rank: int, world: int, local_rank: int) -> None:
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------- secondary workloads
+# BASELINE.json configs[2] (I3D rgb, 64-frame 224x224 stacks) and configs[3] (RAFT on 480x270 pairs -> I3D flow).
+# They print the same kind of JSON line (metric stacks/s resp. pairs/s) for profiles/; the headline stays CLIP.
+I3D_GFLOP = {"rgb": 222.30, "flow": 204.68}          # per 64-frame stack
+RAFT_GFLOP_272x480 = 309.82                          # per pair, 20 iterations, reference algorithm
+
+
+def _weights(kind: str):
+    """Reference checkpoint copy if present (checkpoints/), else seeded synthetic weights."""
+    import torch
+    p = os.path.join(ROOT, "checkpoints", {"rgb": "i3d_rgb.pt", "flow": "i3d_flow.pt", "raft": "raft-sintel.pth"}[kind])
+    if os.path.exists(p):
+        return torch.load(p, map_location="cpu"), "reference checkpoint"
+    from oracle import i3d_net
+    if kind == "raft":
+        raise SystemExit("bench --workload raft needs checkpoints/raft-sintel.pth (scripts/fetch_checkpoints.py)")
+    return i3d_net.synthetic_state_dict(kind, 0), "synthetic seed 0"
+
+
+def _timed_loop(fn, steps, warm):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def _gemm_roofline(fn, reps, algorithmic_flops_per_step, step_ms):
+    from video_features_b200 import ops
+    ops.gemm_profile(True)
+    for _ in range(reps):
+        fn()
+    ms, launches, executed = ops.gemm_profile_read()
+    ops.gemm_profile(False)
+    peaks = load_peaks()
+    ach = algorithmic_flops_per_step * reps / (ms / 1e3) / 1e12 if ms > 0 else 0.0
+    return {"bound": "tensor", "kernel": "vf::gemm_f16_pair_kernel (tcgen05, shifted-row conv mode)",
+            "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"],
+            "peak_source": peaks["source"] + ", bf16 dense sustained", "traffic": None,
+            "executed_tflops": executed / (ms / 1e3) / 1e12 if ms > 0 else 0.0,
+            "executed_over_algorithmic": executed / (algorithmic_flops_per_step * reps),
+            "launches_per_step": launches // reps, "gemm_share_of_step": (ms / reps) / step_ms}
+
+
+def run_i3d(args) -> None:
+    import torch
+    from video_features_b200.i3d_engine import I3DEngine
+    from oracle import i3d_net
+    torch.cuda.set_device(0)
+    sd, wsrc = _weights("rgb")
+    S = 8
+    eng = I3DEngine(sd, "rgb", 0, max_stacks=S, max_T=64)
+    g = torch.Generator().manual_seed(1)
+    frames_host = torch.randint(0, 256, (S, 65, 224, 224, 3), dtype=torch.uint8, generator=g).pin_memory()
+    frames = frames_host.cuda()
+    fn = lambda: eng.forward_frames_u8(frames[:, :64])
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+    sampler = ClockSampler(0)
+    ms = _timed_loop(fn, K, W)
+    clocks = sampler.stop()
+    def host_fn():
+        x = frames_host.cuda(non_blocking=True)
+        return eng.forward_frames_u8(x[:, :64]).cpu()
+    ms_e2e = _timed_loop(host_fn, K, 2)
+    roof = _gemm_roofline(fn, min(K, 3), I3D_GFLOP["rgb"] * 1e9 * S, ms / K)
+    line = {"metric": "stacks/sec I3D rgb (64x224x224)", "value": S * K / (ms / 1e3), "unit": "stacks/s", "n_gpus": 1,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "I3D rgb stream, stack_size=64, synthetic 224x224 clips (BASELINE.json configs[2])",
+                       "stacks_per_step": S, "frames_per_sec": S * 64 * K / (ms / 1e3), "weights": wsrc,
+                       "precision": "fp16 activations, hi+lo fp16 weights (2 MMA passes), fp32 accumulate"},
+            "clocks": clocks,
+            "e2e": {"value": S * K / (ms_e2e / 1e3), "unit": "stacks/s", "h2d_bytes_per_step": int(frames_host.numel()),
+                    "d2h_bytes_per_step": S * 1024 * 4},
+            "gpu_launches": int(eng.launch_count), "roofline": roof}
+    if not args.no_cpu:
+        cores = usable_cores()
+        torch.set_num_threads(cores)
+        x = i3d_net.rgb_transform(frames_host[0, :64].permute(0, 3, 1, 2).float())
+        i3d_net.forward_features(sd, x[:, :, :16])
+        t0 = time.perf_counter(); i3d_net.forward_features(sd, x); dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "stacks/s", "cores": cores, "kind": "port",
+                                "sample": f"1 stack (64x224x224), oracle port of I3D fp32, torch threads={cores}, {cpu_model_name()}"}
+    print(json.dumps(line), flush=True)
+
+
+def run_raft(args) -> None:
+    import torch
+    from video_features_b200.i3d_engine import I3DEngine
+    from video_features_b200.raft_engine import RAFTEngine
+    from oracle import raft_net
+    torch.cuda.set_device(0)
+    sd, wsrc = _weights("raft")
+    sdf, _ = _weights("flow")
+    F = 65
+    eng = RAFTEngine(sd, 0, max_frames=F, max_h=270, max_w=480)
+    i3d = I3DEngine(sdf, "flow", 0, max_stacks=1, max_T=64)
+    frames_host = raft_net.synthetic_frames(F, 270, 480, seed=2).permute(0, 2, 3, 1).contiguous().to(torch.uint8).pin_memory()
+    frames = frames_host.cuda()
+    def fn():
+        flow = eng.flow(frames, iters=20, unpad=False)         # padded, as the I3D path consumes it
+        return i3d.forward_flow(flow[None])
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+    sampler = ClockSampler(0)
+    ms = _timed_loop(fn, K, W)
+    clocks = sampler.stop()
+    ms_raft = _timed_loop(lambda: eng.flow(frames, iters=20, unpad=False), K, 1)
+    def host_fn():
+        flow = eng.flow(frames_host.cuda(non_blocking=True), iters=20, unpad=False)
+        return i3d.forward_flow(flow[None]).cpu()
+    ms_e2e = _timed_loop(host_fn, K, 1)
+    roof = _gemm_roofline(lambda: eng.flow(frames, iters=20, unpad=False), min(K, 2), RAFT_GFLOP_272x480 * 1e9 * (F - 1), ms_raft / K)
+    line = {"metric": "pairs/sec RAFT 480x270 (20 iters) -> I3D flow", "value": (F - 1) * K / (ms / 1e3), "unit": "pairs/s",
+            "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "RAFT optical flow on 480x270 frame pairs -> I3D flow branch (BASELINE.json configs[3])",
+                       "pairs_per_step": F - 1, "raft_only_pairs_per_sec": (F - 1) * K / (ms_raft / 1e3), "weights": wsrc,
+                       "note": "mask head + convex upsample run once (the reference runs them 20x and discards 19)"},
+            "clocks": clocks,
+            "e2e": {"value": (F - 1) * K / (ms_e2e / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": int(frames_host.numel()),
+                    "d2h_bytes_per_step": 1024 * 4},
+            "gpu_launches": int(eng.launch_count + i3d.launch_count), "roofline": roof}
+    if not args.no_cpu:
+        cores = usable_cores()
+        torch.set_num_threads(cores)
+        x = raft_net.pad(frames_host[:3].permute(0, 3, 1, 2).float())
+        raft_net.forward(sd, x[:1], x[1:2], 2)
+        t0 = time.perf_counter(); raft_net.forward(sd, x[:-1], x[1:], 20); dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": 2.0 / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+                                "sample": f"2 pairs 272x480, 20 iterations, oracle port of RAFT fp32, torch threads={cores}, {cpu_model_name()}"}
+    print(json.dumps(line), flush=True)
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -342,6 +481,8 @@ def main() -> None:
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--chunk", type=int, default=0, help="frames per tower chunk (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="clip", choices=["clip", "i3d", "raft"],
+                    help="clip = the headline (BASELINE.json configs[1]); i3d / raft = configs[2] / configs[3], 1 GPU")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -349,6 +490,10 @@ def main() -> None:
     if args.impl == "reference":
         run_reference(args, rank)
         return
+    if args.workload == "i3d":
+        return run_i3d(args)
+    if args.workload == "raft":
+        return run_raft(args)
     if world != args.gpus and world == 1 and args.gpus > 1:
         # launched without torchrun: re-exec under torch.distributed.run on this node
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",

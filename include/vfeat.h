@@ -67,6 +67,12 @@ int vf_clip_normalize_u8(const uint8_t* src, int n, int src_h, int src_w, float*
 int vf_gemm_f16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, void* D, int ldd, int out_f32,
                 const float* bias, const float* scale, int act, void* stream);
 
+/* Roofline instrumentation (bench.py): while enabled on the calling thread, every tcgen05 GEMM launch of any handle
+ * is bracketed by CUDA events on its stream.  _read synchronises the device and returns the summed device time (ms),
+ * the launch count and the EXECUTED flops (2*M*N*K including zero-padded K blocks and hi/lo weight passes). */
+int vf_gemm_profile(int enable);
+int vf_gemm_profile_read(double* ms, int64_t* launches, double* executed_flops);
+
 /* ---- CLIP ViT-B/32 image tower: replaces `clip.load(...)` + `model.encode_image(frames)`
  * (models/CLIP/extract_clip.py:47,128).  Weight pointers are HOST fp32 arrays in openai layout. */
 typedef struct vf_clip_layer_weights {

@@ -23,6 +23,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -351,6 +353,23 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t ro
     return VF_OK;
 }
 
+// Roofline instrumentation shared by every handle (vf_gemm_profile): CUDA-event pairs around each GEMM launch on the
+// launching stream, per host thread.
+struct GemmProf {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;
+    size_t used = 0;
+    double flops = 0.0;
+};
+static thread_local GemmProf g_prof;
+
+static int run_gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, int bn, const GemmEpi& ep,
+                           int M, int N, const ConvGeom& cg, cudaStream_t stream) {
+    if (bn == 256) return launch_gemm_pair<256, 5>(tmA, tmB, tmO, ep, M, N, cg, stream);
+    if (bn == 128) return launch_gemm_pair<128, 6>(tmA, tmB, tmO, ep, M, N, cg, stream);
+    return launch_gemm_pair<64, 8>(tmA, tmB, tmO, ep, M, N, cg, stream);
+}
+
 static int run_gemm(const CUtensorMap& tmA, const __half* B, int ldb, int64_t Ktot, int M, int N, const ConvGeom& cg,
                     const GemmEpi& ep, cudaStream_t stream) {
     if (!ep.out) return fail(VF_ERR_INVALID, "gemm: null output");
@@ -361,9 +380,39 @@ static int run_gemm(const CUtensorMap& tmA, const __half* B, int ldb, int64_t Kt
     VF_TRY(make_tmap_2d(&tmB, B, 2, uint64_t(N), uint64_t(Ktot), uint64_t(ldb) * 2, uint32_t(bn / 2), BK));
     if (ep.out_f32) VF_TRY(make_tmap_2d(&tmO, ep.out, 4, uint64_t(M), uint64_t(N), uint64_t(ep.ldo) * 4, BM, 32));
     else            VF_TRY(make_tmap_2d(&tmO, ep.out, 2, uint64_t(M), uint64_t(N), uint64_t(ep.ldo) * 2, BM, 64));
-    if (bn == 256) return launch_gemm_pair<256, 5>(tmA, tmB, tmO, ep, M, N, cg, stream);
-    if (bn == 128) return launch_gemm_pair<128, 6>(tmA, tmB, tmO, ep, M, N, cg, stream);
-    return launch_gemm_pair<64, 8>(tmA, tmB, tmO, ep, M, N, cg, stream);
+    if (!g_prof.on) return run_gemm_launch(tmA, tmB, tmO, bn, ep, M, N, cg, stream);
+    if (g_prof.used + 2 > g_prof.ev.size())
+        for (int i = 0; i < 2; ++i) {
+            cudaEvent_t e;
+            VF_CUDA(cudaEventCreate(&e));
+            g_prof.ev.push_back(e);
+        }
+    VF_CUDA(cudaEventRecord(g_prof.ev[g_prof.used], stream));
+    const int st = run_gemm_launch(tmA, tmB, tmO, bn, ep, M, N, cg, stream);
+    VF_CUDA(cudaEventRecord(g_prof.ev[g_prof.used + 1], stream));
+    g_prof.used += 2;
+    g_prof.flops += 2.0 * double(M) * double(N) * double(Ktot);
+    return st;
+}
+
+int gemm_profile(int enable) {
+    g_prof.on = enable != 0;
+    return VF_OK;
+}
+int gemm_profile_read(double* ms, int64_t* launches, double* flops) {
+    VF_CUDA(cudaDeviceSynchronize());
+    double t = 0.0;
+    for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
+        float x = 0.f;
+        VF_CUDA(cudaEventElapsedTime(&x, g_prof.ev[i], g_prof.ev[i + 1]));
+        t += x;
+    }
+    if (ms) *ms = t;
+    if (launches) *launches = int64_t(g_prof.used / 2);
+    if (flops) *flops = g_prof.flops;
+    g_prof.used = 0;
+    g_prof.flops = 0.0;
+    return VF_OK;
 }
 
 int gemm_f16(const __half* A, int lda, const __half* B, int ldb, int M, int N, int K, const GemmEpi& ep,

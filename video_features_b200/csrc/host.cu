@@ -230,6 +230,11 @@ int vf_clip_normalize_u8(const uint8_t* src, int n, int src_h, int src_w, float*
                                      center_crop_offset(src_w, 224), dst, static_cast<cudaStream_t>(stream));
 }
 
+int vf_gemm_profile(int enable) { return gemm_profile(enable); }
+int vf_gemm_profile_read(double* ms, int64_t* launches, double* executed_flops) {
+    return gemm_profile_read(ms, launches, executed_flops);
+}
+
 int vf_gemm_f16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, void* D, int ldd, int out_f32,
                 const float* bias, const float* scale, int act, void* stream) {
     if (!A || !B || !D) return fail(VF_ERR_INVALID, "gemm: null buffer");

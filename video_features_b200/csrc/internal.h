@@ -64,6 +64,8 @@ struct ConvGeom {
 int conv_gemm_f16(const __half* X, int C, int64_t P, const __half* Wt, int N, const ConvGeom& g, const GemmEpi& ep,
                   cudaStream_t stream);
 int device_sm_count();
+int gemm_profile(int enable);
+int gemm_profile_read(double* ms, int64_t* launches, double* flops);
 
 // ---- elementwise / reduction kernels
 int launch_clip_patchify(const uint8_t* src, int n, int src_h, int src_w, int crop_y, int crop_x, __half* patches,

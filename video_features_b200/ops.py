@@ -108,3 +108,14 @@ def shard_range(n_items: int, n_parts: int, part: int):
     b, e = C.c_int64(), C.c_int64()
     check(lib().vf_shard_range(n_items, n_parts, part, C.byref(b), C.byref(e)))
     return b.value, e.value
+
+
+def gemm_profile(enable: bool) -> None:
+    check(lib().vf_gemm_profile(int(enable)))
+
+
+def gemm_profile_read():
+    """-> (device ms, launches, executed FLOPs) of the GEMM launches since the last read (this thread)."""
+    ms, n, fl = C.c_double(), C.c_int64(), C.c_double()
+    check(lib().vf_gemm_profile_read(C.byref(ms), C.byref(n), C.byref(fl)))
+    return ms.value, n.value, fl.value
