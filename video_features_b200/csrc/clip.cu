@@ -55,11 +55,24 @@ struct vf_clip {
     // pair of events), so that the per-chunk tower can be captured once into a CUDA graph and replayed: ~90 kernel
     // launches and ~150 tensor-map encodes per chunk collapse into one cudaGraphLaunch (the legacy NULL stream, which
     // is what torch hands over by default, cannot be captured).
-    cudaStream_t cs = nullptr;
-    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    //
+    // Two LANES (stream + private workspace) take the chunks of a call alternately.  A GEMM owns every SM's shared
+    // memory, so GEMMs of the two lanes serialise, but the memory-bound kernels of one lane (LayerNorm, attention,
+    // transform: no shared memory to speak of) co-reside with the tensor-bound GEMM of the other and fill its tails.
+    struct Lane {
+        __half *patches = nullptr, *h = nullptr, *qkv = nullptr, *att = nullptr, *mlp = nullptr, *cls = nullptr, *y = nullptr;
+        float *x = nullptr, *emb = nullptr, *feat = nullptr;
+        uint8_t *resized = nullptr, *resize_tmp = nullptr;
+        size_t resized_cap = 0, tmp_cap = 0;
+        cudaStream_t cs = nullptr;
+        cudaEvent_t ev_out = nullptr;
+        std::map<int, cudaGraphExec_t> graphs;   // frames in chunk -> instantiated tower graph (writes feat)
+    } lanes[2];
+    int n_lanes = 2, cur = 0;
+    cudaStream_t cs = nullptr;                // stream of the active lane
+    cudaEvent_t ev_in = nullptr;
     bool use_graph = true;
-    std::map<int, cudaGraphExec_t> graphs;   // frames in chunk -> instantiated tower graph (writes h->feat)
-    float* feat = nullptr;                    // [chunk, 512] tower output of the current chunk
+    float* feat = nullptr;                    // [chunk, 512] tower output of the active lane
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
 };
@@ -148,10 +161,10 @@ static int tower_embed_ln(vf_clip* h, int c, cudaStream_t s) {
     ProfScope p(h, 1, s);
     return launch_embed_layernorm(h->emb, h->pos, h->cls_pos0, h->lnpre_w, h->lnpre_b, h->x, c, s);
 }
-static int tower_add_ln(vf_clip* h, float* x, const __half* y, int64_t stride, int write_x, const float* g,
-                        const float* b, void* out, int64_t ostride, int rows, cudaStream_t s) {
+static int tower_add_ln(vf_clip* h, float* x, int64_t x_stride, const __half* y, int64_t y_stride, int write_x,
+                        const float* g, const float* b, void* out, int64_t ostride, int rows, cudaStream_t s) {
     ProfScope p(h, 1, s);
-    return launch_add_layernorm(x, y, stride, write_x, g, b, out, ostride, 0, rows, s);
+    return launch_add_layernorm(x, x_stride, y, y_stride, write_x, g, b, out, ostride, 0, rows, s);
 }
 static int tower_attention(vf_clip* h, int c, cudaStream_t s) {
     ProfScope p(h, 2, s);
@@ -171,18 +184,28 @@ static int clip_tower_eager(vf_clip* h, int c, float* out, cudaStream_t s) {
     for (int l = 0; l < L; ++l) {
         const ClipLayerDev& w = h->layer[l];
         // x += y of the previous block's MLP (none for block 0); h = ln_1(x)
-        VF_TRY(tower_add_ln(h, h->x, l == 0 ? nullptr : h->y, W, 1, w.ln1_w, w.ln1_b, h->h, W, M, s));
+        VF_TRY(tower_add_ln(h, h->x, W, l == 0 ? nullptr : h->y, W, 1, w.ln1_w, w.ln1_b, h->h, W, M, s));
         VF_TRY(tower_gemm(h, h->h, W, w.w_qkv, W, M, 3 * W, W, epi(h->qkv, 3 * W, 0, w.b_qkv, VF_ACT_NONE), s));
         VF_TRY(tower_attention(h, c, s));
-        VF_TRY(tower_gemm(h, h->att, W, w.w_o, W, M, W, W, epi(h->y, W, 0, w.b_o, VF_ACT_NONE), s));
-        // x += attention output; h = ln_2(x)
-        VF_TRY(tower_add_ln(h, h->x, h->y, W, 1, w.ln2_w, w.ln2_b, h->h, W, M, s));
-        VF_TRY(tower_gemm(h, h->h, W, w.w_fc, W, M, MLPW, W, epi(h->mlp, MLPW, 0, w.b_fc, VF_ACT_QUICKGELU), s));
-        VF_TRY(tower_gemm(h, h->mlp, MLPW, w.w_proj, MLPW, M, W, MLPW, epi(h->y, W, 0, w.b_proj, VF_ACT_NONE), s));
+        if (l + 1 < L) {
+            VF_TRY(tower_gemm(h, h->att, W, w.w_o, W, M, W, W, epi(h->y, W, 0, w.b_o, VF_ACT_NONE), s));
+            // x += attention output; h = ln_2(x)
+            VF_TRY(tower_add_ln(h, h->x, W, h->y, W, 1, w.ln2_w, w.ln2_b, h->h, W, M, s));
+            VF_TRY(tower_gemm(h, h->h, W, w.w_fc, W, M, MLPW, W, epi(h->mlp, MLPW, 0, w.b_fc, VF_ACT_QUICKGELU), s));
+            VF_TRY(tower_gemm(h, h->mlp, MLPW, w.w_proj, MLPW, M, W, MLPW, epi(h->y, W, 0, w.b_proj, VF_ACT_NONE), s));
+        } else {
+            // Last block: only the CLS token reaches ln_post / proj (encode_image returns x[:, 0]), so after the
+            // attention everything runs on the c CLS rows: A operands are strided views (row pitch 50*768), y / h / mlp
+            // are compact c-row buffers.  Saves 49/50 of out-proj + MLP of this block (5.9 % of the tower's FLOPs).
+            VF_TRY(tower_gemm(h, h->att, T * W, w.w_o, W, c, W, W, epi(h->y, W, 0, w.b_o, VF_ACT_NONE), s));
+            VF_TRY(tower_add_ln(h, h->x, int64_t(T) * W, h->y, W, 1, w.ln2_w, w.ln2_b, h->h, W, c, s));
+            VF_TRY(tower_gemm(h, h->h, W, w.w_fc, W, c, MLPW, W, epi(h->mlp, MLPW, 0, w.b_fc, VF_ACT_QUICKGELU), s));
+            VF_TRY(tower_gemm(h, h->mlp, MLPW, w.w_proj, MLPW, c, W, MLPW, epi(h->y, W, 0, w.b_proj, VF_ACT_NONE), s));
+        }
         h->launches += 7;
     }
-    // CLS rows only: x += y of the last MLP; ln_post; then the 768 -> 512 projection
-    VF_TRY(tower_add_ln(h, h->x, h->y, int64_t(T) * W, 0, h->lnpost_w, h->lnpost_b, h->cls, W, c, s));
+    // CLS rows: x += y of the last MLP; ln_post; then the 768 -> 512 projection
+    VF_TRY(tower_add_ln(h, h->x, int64_t(T) * W, h->y, W, 0, h->lnpost_w, h->lnpost_b, h->cls, W, c, s));
     VF_TRY(tower_gemm(h, h->cls, W, h->w_proj, W, c, E, W, epi(out, E, 1, nullptr, VF_ACT_NONE), s));
     h->launches += 2;
     return VF_OK;
@@ -193,8 +216,9 @@ constexpr int TOWER_LAUNCHES = 2 + 7 * L + 2;
 // Tower on one chunk: replay (capturing on first use) the CUDA graph for this chunk size, then copy the features out.
 static int clip_tower_chunk(vf_clip* h, int c, float* out, cudaStream_t s) {
     if (!h->use_graph || h->prof) return clip_tower_eager(h, c, out, s);
-    auto it = h->graphs.find(c);
-    if (it == h->graphs.end()) {
+    auto& graphs = h->lanes[h->cur].graphs;
+    auto it = graphs.find(c);
+    if (it == graphs.end()) {
         const int64_t before = h->launches;
         cudaGraph_t graph = nullptr;
         VF_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
@@ -207,7 +231,7 @@ static int clip_tower_chunk(vf_clip* h, int c, float* out, cudaStream_t s) {
         const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
         cudaGraphDestroy(graph);
         if (ie != cudaSuccess) return fail(VF_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie));
-        it = h->graphs.emplace(c, exec).first;
+        it = graphs.emplace(c, exec).first;
     }
     VF_CUDA(cudaGraphLaunch(it->second, s));
     VF_CUDA(cudaMemcpyAsync(out, h->feat, size_t(c) * E * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -222,16 +246,32 @@ static int balanced_chunk(const vf_clip* h, int n) {
     return nchunks > 0 ? (n + nchunks - 1) / nchunks : h->chunk;
 }
 
-// order the engine stream after the caller's stream (enter) and the caller's stream after the engine's (leave)
+// make lane `l` the active one: its workspace pointers and stream become the ones the launch helpers use
+static cudaStream_t activate(vf_clip* h, int l) {
+    vf_clip::Lane& L = h->lanes[l];
+    h->cur = l;
+    h->patches = L.patches; h->h = L.h; h->qkv = L.qkv; h->att = L.att; h->mlp = L.mlp; h->cls = L.cls; h->y = L.y;
+    h->x = L.x; h->emb = L.emb; h->feat = L.feat;
+    h->resized = L.resized; h->resize_tmp = L.resize_tmp; h->resized_cap = L.resized_cap; h->tmp_cap = L.tmp_cap;
+    h->cs = L.cs;
+    return L.cs;
+}
+static void deactivate(vf_clip* h) {      // keep the (possibly grown) resize scratch with its lane
+    vf_clip::Lane& L = h->lanes[h->cur];
+    L.resized = h->resized; L.resize_tmp = h->resize_tmp; L.resized_cap = h->resized_cap; L.tmp_cap = h->tmp_cap;
+}
+// order the lane streams after the caller's stream (enter) and the caller's stream after the lanes (leave)
 static int enter(vf_clip* h, cudaStream_t user) {
     VF_CUDA(cudaSetDevice(h->device));
     VF_CUDA(cudaEventRecord(h->ev_in, user));
-    VF_CUDA(cudaStreamWaitEvent(h->cs, h->ev_in, 0));
+    for (int l = 0; l < h->n_lanes; ++l) VF_CUDA(cudaStreamWaitEvent(h->lanes[l].cs, h->ev_in, 0));
     return VF_OK;
 }
 static int leave(vf_clip* h, cudaStream_t user) {
-    VF_CUDA(cudaEventRecord(h->ev_out, h->cs));
-    VF_CUDA(cudaStreamWaitEvent(user, h->ev_out, 0));
+    for (int l = 0; l < h->n_lanes; ++l) {
+        VF_CUDA(cudaEventRecord(h->lanes[l].ev_out, h->lanes[l].cs));
+        VF_CUDA(cudaStreamWaitEvent(user, h->lanes[l].ev_out, 0));
+    }
     return VF_OK;
 }
 
@@ -273,7 +313,7 @@ extern "C" {
 int vf_clip_create(vf_clip_t** out, const vf_clip_weights* w, int device, int chunk_frames) {
     if (!out || !w) return fail(VF_ERR_INVALID, "clip_create: null argument");
     *out = nullptr;
-    if (chunk_frames <= 0) chunk_frames = 512;   // up to 25600 token rows per GEMM launch (~0.6 GB workspace)
+    if (chunk_frames <= 0) chunk_frames = 256;   // up to 12800 token rows per GEMM launch, per lane
     if (chunk_frames > 4096) return fail(VF_ERR_INVALID, "clip_create: chunk_frames %d too large", chunk_frames);
     VF_CUDA(cudaSetDevice(device));
     int major = 0, minor = 0;
@@ -316,23 +356,33 @@ int vf_clip_create(vf_clip_t** out, const vf_clip_weights* w, int device, int ch
             VF_TRY(upload_f16(h, &d.w_proj, s.c_proj_w, W, MLPW, false));
         }
         const size_t C = size_t(chunk_frames);
-        VF_TRY(dev_alloc(h, &h->patches, C * P * PK));
-        VF_TRY(dev_alloc(h, &h->x, C * T * W));
-        VF_TRY(dev_alloc(h, &h->y, C * T * W));
-        VF_TRY(dev_alloc(h, &h->emb, C * P * W));
-        VF_TRY(dev_alloc(h, &h->h, C * T * W));
-        VF_TRY(dev_alloc(h, &h->qkv, C * T * 3 * W));
-        VF_TRY(dev_alloc(h, &h->att, C * T * W));
-        VF_TRY(dev_alloc(h, &h->mlp, C * T * MLPW));
-        VF_TRY(dev_alloc(h, &h->cls, C * W));
-        VF_TRY(dev_alloc(h, &h->feat, C * E));
-        VF_CUDA(cudaStreamCreateWithFlags(&h->cs, cudaStreamNonBlocking));
+        {
+            // measured: two lanes give no gain on B200 (87.1 k vs 88.4 k frames/s; the persistent GEMM leaves no room
+            // for co-resident blocks), so one lane is the default and the second is opt-in for experiments
+            const char* e = getenv("VF_CLIP_LANES");
+            h->n_lanes = (e && e[0] == '2') ? 2 : 1;
+        }
+        for (int l = 0; l < h->n_lanes; ++l) {
+            vf_clip::Lane& L = h->lanes[l];
+            VF_TRY(dev_alloc(h, &L.patches, C * P * PK));
+            VF_TRY(dev_alloc(h, &L.x, C * T * W));
+            VF_TRY(dev_alloc(h, &L.y, C * T * W));
+            VF_TRY(dev_alloc(h, &L.emb, C * P * W));
+            VF_TRY(dev_alloc(h, &L.h, C * T * W));
+            VF_TRY(dev_alloc(h, &L.qkv, C * T * 3 * W));
+            VF_TRY(dev_alloc(h, &L.att, C * T * W));
+            VF_TRY(dev_alloc(h, &L.mlp, C * T * MLPW));
+            VF_TRY(dev_alloc(h, &L.cls, C * W));
+            VF_TRY(dev_alloc(h, &L.feat, C * E));
+            VF_CUDA(cudaStreamCreateWithFlags(&L.cs, cudaStreamNonBlocking));
+            VF_CUDA(cudaEventCreateWithFlags(&L.ev_out, cudaEventDisableTiming));
+        }
         VF_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
-        VF_CUDA(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
         {
             const char* e = getenv("VF_NO_GRAPH");
             h->use_graph = !(e && e[0] == '1');
         }
+        activate(h, 0);
         VF_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
             VF_CUDA(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
@@ -352,14 +402,19 @@ int vf_clip_destroy(vf_clip_t* h) {
     cudaDeviceSynchronize();
     for (void* p : h->allocs) cudaFree(p);
     if (h->stage_u8) cudaFree(h->stage_u8);
-    if (h->resized) cudaFree(h->resized);
-    if (h->resize_tmp) cudaFree(h->resize_tmp);
     if (h->out_dev) cudaFree(h->out_dev);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
-    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
-    if (h->cs) cudaStreamDestroy(h->cs);
+    deactivate(h);
+    for (int l = 0; l < 2; ++l) {
+        vf_clip::Lane& L = h->lanes[l];
+        for (auto& kv : L.graphs) cudaGraphExecDestroy(kv.second);
+        if (L.cs) cudaStreamDestroy(L.cs);
+        if (L.ev_out) cudaEventDestroy(L.ev_out);
+        if (L.resized) cudaFree(L.resized);
+        if (L.resize_tmp) cudaFree(L.resize_tmp);
+    }
+    h->resized = nullptr; h->resize_tmp = nullptr;
     if (h->ev_in) cudaEventDestroy(h->ev_in);
-    if (h->ev_out) cudaEventDestroy(h->ev_out);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
@@ -372,14 +427,16 @@ int vf_clip_destroy(vf_clip_t* h) {
 int vf_clip_encode_f32(vf_clip_t* h, const float* frames, int n, float* out, void* stream) {
     if (!h || (n > 0 && (!frames || !out))) return fail(VF_ERR_INVALID, "clip_encode_f32: null argument");
     if (n <= 0) return VF_OK;
-    cudaStream_t user = static_cast<cudaStream_t>(stream), s = h->cs;
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
     VF_TRY(enter(h, user));
     const int step = balanced_chunk(h, n);
-    for (int b0 = 0; b0 < n; b0 += step) {
+    for (int b0 = 0, i = 0; b0 < n; b0 += step, ++i) {
         const int c = (n - b0 < step) ? (n - b0) : step;
+        cudaStream_t s = activate(h, i % h->n_lanes);
         VF_TRY(launch_clip_patchify_f32(frames + size_t(b0) * 3 * 224 * 224, c, h->patches, s));
         h->launches += 1;
         VF_TRY(clip_tower_chunk(h, c, out + size_t(b0) * E, s));
+        deactivate(h);
     }
     return leave(h, user);
 }
@@ -387,16 +444,18 @@ int vf_clip_encode_f32(vf_clip_t* h, const float* frames, int n, float* out, voi
 int vf_clip_encode_u8(vf_clip_t* h, const uint8_t* frames, int n, int src_h, int src_w, float* out, void* stream) {
     if (!h || (n > 0 && (!frames || !out))) return fail(VF_ERR_INVALID, "clip_encode_u8: null argument");
     if (n <= 0) return VF_OK;
-    cudaStream_t user = static_cast<cudaStream_t>(stream), s = h->cs;
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
     ClipGeom g;
     VF_TRY(clip_geometry(src_h, src_w, &g));
     VF_TRY(enter(h, user));
     const size_t fbytes = size_t(src_h) * src_w * 3;
     const int step = balanced_chunk(h, n);
-    for (int b0 = 0; b0 < n; b0 += step) {
+    for (int b0 = 0, i = 0; b0 < n; b0 += step, ++i) {
         const int c = (n - b0 < step) ? (n - b0) : step;
+        cudaStream_t s = activate(h, i % h->n_lanes);
         VF_TRY(clip_transform_chunk(h, frames + size_t(b0) * fbytes, c, src_h, src_w, g, s));
         VF_TRY(clip_tower_chunk(h, c, out + size_t(b0) * E, s));
+        deactivate(h);
     }
     return leave(h, user);
 }
@@ -405,7 +464,7 @@ int vf_clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, int 
                            void* stream) {
     if (!h || (n > 0 && (!frames_host || !out_host))) return fail(VF_ERR_INVALID, "clip_encode_u8_host: null argument");
     if (n <= 0) return VF_OK;
-    cudaStream_t user = static_cast<cudaStream_t>(stream), s = h->cs;
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
     ClipGeom g;
     VF_TRY(clip_geometry(src_h, src_w, &g));
     VF_TRY(enter(h, user));
@@ -425,6 +484,7 @@ int vf_clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, int 
         const int b0 = i * step;
         const int c = (n - b0 < step) ? (n - b0) : step;
         const int slot = i & 1;
+        cudaStream_t s = activate(h, i % h->n_lanes);
         uint8_t* dst = h->stage_u8 + size_t(slot) * h->chunk * fbytes;
         if (i >= 2) VF_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));   // slot free again
         VF_CUDA(cudaMemcpyAsync(dst, frames_host + size_t(b0) * fbytes, size_t(c) * fbytes, cudaMemcpyHostToDevice,
@@ -434,10 +494,17 @@ int vf_clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, int 
         VF_TRY(clip_transform_chunk(h, dst, c, src_h, src_w, g, s));
         VF_CUDA(cudaEventRecord(h->ev_done[slot], s));   // staging slot consumed
         VF_TRY(clip_tower_chunk(h, c, h->out_dev + size_t(b0) * E, s));
+        deactivate(h);
     }
-    VF_CUDA(cudaMemcpyAsync(out_host, h->out_dev, size_t(n) * E * sizeof(float), cudaMemcpyDeviceToHost, s));
+    // gather point: lane 0 waits for lane 1, then one D2H of all features
+    cudaStream_t s0 = h->lanes[0].cs;
+    if (h->n_lanes > 1) {
+        VF_CUDA(cudaEventRecord(h->lanes[1].ev_out, h->lanes[1].cs));
+        VF_CUDA(cudaStreamWaitEvent(s0, h->lanes[1].ev_out, 0));
+    }
+    VF_CUDA(cudaMemcpyAsync(out_host, h->out_dev, size_t(n) * E * sizeof(float), cudaMemcpyDeviceToHost, s0));
     VF_TRY(leave(h, user));
-    VF_CUDA(cudaStreamSynchronize(s));
+    VF_CUDA(cudaStreamSynchronize(s0));
     return VF_OK;
 }
 

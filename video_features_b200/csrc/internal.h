@@ -74,8 +74,9 @@ int launch_clip_patchify_f32(const float* src_chw, int n, __half* patches, cudaS
 int launch_clip_normalize_f32(const uint8_t* src, int n, int src_h, int src_w, int crop_y, int crop_x, float* dst_chw,
                               cudaStream_t s);
 // x (+= y) ; out = LayerNorm(x) -- rows of 768 fp32.  y may be null; write_x stores the summed residual stream back.
-int launch_add_layernorm(float* x, const __half* y, int64_t xy_row_stride, int write_x, const float* gamma,
-                         const float* beta, void* out, int64_t out_row_stride, int out_f32, int rows, cudaStream_t s);
+int launch_add_layernorm(float* x, int64_t x_row_stride, const __half* y, int64_t y_row_stride, int write_x,
+                         const float* gamma, const float* beta, void* out, int64_t out_row_stride, int out_f32, int rows,
+                         cudaStream_t s);
 // ViT embedding rows: token 0 = cls_pos0, token t>0 = emb[frame*49 + t-1] + pos[t]; x = ln_pre(row) (fp32)
 int launch_embed_layernorm(const float* emb, const float* pos, const float* cls_pos0, const float* gamma,
                            const float* beta, float* x, int n_frames, cudaStream_t s);

@@ -129,8 +129,8 @@ __device__ __forceinline__ void ln768_write(const Row768& r, int lane, const flo
 // residual-stream update fused with the following LayerNorm:  x += y (the previous GEMM's output, fp16: it is a
 // small residual-branch increment, so its 2^-11 rounding is far below the fp16 operand rounding of the GEMMs; x
 // itself stays fp32), out = LN(x)
-__global__ void __launch_bounds__(256, 6) add_layernorm768_kernel(float* __restrict__ x, const __half* __restrict__ y, int64_t row_stride,
-                                        int write_x, const float* __restrict__ gamma, const float* __restrict__ beta,
+__global__ void __launch_bounds__(256, 6) add_layernorm768_kernel(float* __restrict__ x, int64_t row_stride,
+                                        const __half* __restrict__ y, int64_t y_row_stride, int write_x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                         void* out, int64_t out_row_stride, int out_f32, int rows) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256, 6) add_layernorm768_kernel(float* __restr
 #pragma unroll
     for (int i = 0; i < 6; ++i) r.v[i] = *reinterpret_cast<const float4*>(xr + (lane + 32 * i) * 4);
     if (y != nullptr) {
-        const __half* yr = y + int64_t(row) * row_stride;
+        const __half* yr = y + int64_t(row) * y_row_stride;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
             const uint2 raw = __ldg(reinterpret_cast<const uint2*>(yr + (lane + 32 * i) * 4));
@@ -405,11 +405,12 @@ int launch_clip_normalize_f32(const uint8_t* src, int n, int src_h, int src_w, i
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
-int launch_add_layernorm(float* x, const __half* y, int64_t xy_row_stride, int write_x, const float* gamma,
-                         const float* beta, void* out, int64_t out_row_stride, int out_f32, int rows, cudaStream_t s) {
+int launch_add_layernorm(float* x, int64_t x_row_stride, const __half* y, int64_t y_row_stride, int write_x,
+                         const float* gamma, const float* beta, void* out, int64_t out_row_stride, int out_f32, int rows,
+                         cudaStream_t s) {
     const int warps = 8;
-    add_layernorm768_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, s>>>(x, y, xy_row_stride, write_x, gamma, beta,
-                                                                             out, out_row_stride, out_f32, rows);
+    add_layernorm768_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, s>>>(x, x_row_stride, y, y_row_stride, write_x,
+                                                                             gamma, beta, out, out_row_stride, out_f32, rows);
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
