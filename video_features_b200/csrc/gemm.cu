@@ -395,6 +395,7 @@ static int run_gemm(const CUtensorMap& tmA, const __half* B, int ldb, int64_t Kt
     return st;
 }
 
+bool gemm_profile_on() { return g_prof.on; }
 int gemm_profile(int enable) {
     g_prof.on = enable != 0;
     return VF_OK;

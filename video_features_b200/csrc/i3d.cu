@@ -20,6 +20,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <utility>
 #include <vector>
 
 #include "internal.h"
@@ -86,6 +88,12 @@ struct vf_i3d {
     __half *bufA = nullptr, *bufB = nullptr, *t1 = nullptr, *t2 = nullptr, *tp = nullptr;
     size_t cap_s0 = 0, cap_a1 = 0, cap_s1 = 0, cap_rows2 = 0;
     int64_t launches = 0;
+    // engine-owned stream + per-(clips, T) CUDA graph of the trunk (same scheme as the CLIP tower)
+    cudaStream_t cs = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    bool use_graph = true;
+    std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
+    float* feat = nullptr;            // [max_stacks, 1024] trunk output
     // last forward's stage views, for vf_i3d_read_stage
     struct StageRef { const __half* p; Vol v; int C; } stages[5];
 };
@@ -145,7 +153,10 @@ static int prepare_unit(vf_i3d* h, ConvUnit& u, const vf_conv_unit& src, int idx
         return fail(VF_ERR_UNSUPPORTED, "i3d_create: unit %d has kernel size %d", idx, k);
     }
     if (u.k_per_tap % 8) return fail(VF_ERR_UNSUPPORTED, "i3d_create: unit %d: %d channels per tap", idx, u.k_per_tap);
-    u.nsplit = h->nsplit;
+    // hi+lo weights everywhere except the stem: CPU emulation on the trained checkpoints gives 8.0e-4 with every
+    // layer split and 7.4e-4 with the stem single (its K is 1029 real taps over inputs in [-1,1]); the stem is also the
+    // one layer bound by operand traffic (N = 64), so a second pass there costs real time
+    u.nsplit = (k == 7) ? 1 : h->nsplit;
     const size_t Kb = size_t(u.ntaps) * u.k_per_tap, Kt = Kb * u.nsplit;
     std::vector<__half> wh(size_t(co) * Kt);
     for (int o = 0; o < co; ++o)
@@ -251,6 +262,14 @@ int vf_i3d_create(vf_i3d_t** out, const vf_i3d_weights* w, int in_channels, int 
         VF_TRY(i3d_alloc(h, &h->t2, rows2 * 64));
         VF_TRY(i3d_alloc(h, &h->tp, rows2 * 832));
         h->cap_rows2 = rows2;
+        VF_TRY(i3d_alloc(h, &h->feat, n * 1024));
+        VF_CUDA(cudaStreamCreateWithFlags(&h->cs, cudaStreamNonBlocking));
+        VF_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+        VF_CUDA(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+        {
+            const char* e = getenv("VF_NO_GRAPH");
+            h->use_graph = !(e && e[0] == '1');
+        }
         return VF_OK;
     };
     const int st = body();
@@ -264,6 +283,10 @@ int vf_i3d_destroy(vf_i3d_t* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (void* p : h->allocs) cudaFree(p);
+    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+    if (h->cs) cudaStreamDestroy(h->cs);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->ev_out) cudaEventDestroy(h->ev_out);
     delete h;
     return VF_OK;
 }
@@ -312,6 +335,43 @@ static int i3d_trunk(vf_i3d* h, int nb, int T, float* out, cudaStream_t s) {
     return VF_OK;
 }
 
+// trunk through a CUDA graph (captured once per (clips, T)); the features land in h->feat and are copied out
+static int i3d_trunk_graphed(vf_i3d* h, int nb, int T, float* out, cudaStream_t s) {
+    if (!h->use_graph || gemm_profile_on()) return i3d_trunk(h, nb, T, out, s);
+    auto key = std::make_pair(nb, T);
+    auto it = h->graphs.find(key);
+    if (it == h->graphs.end()) {
+        const int64_t before = h->launches;
+        cudaGraph_t graph = nullptr;
+        VF_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+        const int st = i3d_trunk(h, nb, T, h->feat, s);
+        const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        if (st != VF_OK) { if (graph) cudaGraphDestroy(graph); return st; }
+        if (ce != cudaSuccess) return fail(VF_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) return fail(VF_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie));
+        it = h->graphs.emplace(key, exec).first;
+        h->launches = before;
+    }
+    VF_CUDA(cudaGraphLaunch(it->second, s));
+    VF_CUDA(cudaMemcpyAsync(out, h->feat, size_t(nb) * 1024 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    h->launches += 72;
+    return VF_OK;
+}
+static int i3d_enter(vf_i3d* h, cudaStream_t user) {
+    VF_CUDA(cudaSetDevice(h->device));
+    VF_CUDA(cudaEventRecord(h->ev_in, user));
+    VF_CUDA(cudaStreamWaitEvent(h->cs, h->ev_in, 0));
+    return VF_OK;
+}
+static int i3d_leave(vf_i3d* h, cudaStream_t user) {
+    VF_CUDA(cudaEventRecord(h->ev_out, h->cs));
+    VF_CUDA(cudaStreamWaitEvent(user, h->ev_out, 0));
+    return VF_OK;
+}
+
 static int i3d_check(vf_i3d* h, const void* in, int n, int T, const void* out, int need_cin) {
     if (!h || (n > 0 && (!in || !out))) return fail(VF_ERR_INVALID, "i3d_forward: null argument");
     if (T < 10 || T > h->max_T) return fail(VF_ERR_INVALID, "i3d_forward: T=%d outside [10, %d]", T, h->max_T);
@@ -323,45 +383,48 @@ extern "C" {
 
 int vf_i3d_forward_f32(vf_i3d_t* h, const float* clips, int n, int T, float* out, void* stream) {
     VF_TRY(i3d_check(h, clips, n, T, out, 0));
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    VF_CUDA(cudaSetDevice(h->device));
+    if (n <= 0) return VF_OK;
+    cudaStream_t user = static_cast<cudaStream_t>(stream), s = h->cs;
+    VF_TRY(i3d_enter(h, user));
     for (int b0 = 0; b0 < n; b0 += h->max_stacks) {
         const int nb = (n - b0 < h->max_stacks) ? (n - b0) : h->max_stacks;
         VF_TRY(launch_i3d_phase_pack_f32(clips + size_t(b0) * h->cin * T * 224 * 224, nb, h->cin, T, h->s0, T / 2 + 3, s));
         h->launches += 1;
-        VF_TRY(i3d_trunk(h, nb, T, out + size_t(b0) * 1024, s));
+        VF_TRY(i3d_trunk_graphed(h, nb, T, out + size_t(b0) * 1024, s));
     }
-    return VF_OK;
+    return i3d_leave(h, user);
 }
 
 int vf_i3d_forward_u8(vf_i3d_t* h, const uint8_t* frames, int n, int T, int Hr, int Wr, float* out, void* stream) {
     VF_TRY(i3d_check(h, frames, n, T, out, 3));
     if (Hr < 224 || Wr < 224) return fail(VF_ERR_INVALID, "i3d_forward_u8: %dx%d frames are smaller than the 224 crop", Hr, Wr);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    VF_CUDA(cudaSetDevice(h->device));
+    if (n <= 0) return VF_OK;
+    cudaStream_t user = static_cast<cudaStream_t>(stream), s = h->cs;
+    VF_TRY(i3d_enter(h, user));
     const int cy = (Hr - 224) / 2, cx = (Wr - 224) / 2;     // TensorCenterCrop: floor offsets (transforms.py:14-15)
     for (int b0 = 0; b0 < n; b0 += h->max_stacks) {
         const int nb = (n - b0 < h->max_stacks) ? (n - b0) : h->max_stacks;
         VF_TRY(launch_i3d_phase_pack_u8(frames + size_t(b0) * T * Hr * Wr * 3, nb, T, Hr, Wr, cy, cx, h->s0, T / 2 + 3, s));
         h->launches += 1;
-        VF_TRY(i3d_trunk(h, nb, T, out + size_t(b0) * 1024, s));
+        VF_TRY(i3d_trunk_graphed(h, nb, T, out + size_t(b0) * 1024, s));
     }
-    return VF_OK;
+    return i3d_leave(h, user);
 }
 
 int vf_i3d_forward_flow(vf_i3d_t* h, const float* flow, int n, int T, int H, int W, float* out, void* stream) {
     VF_TRY(i3d_check(h, flow, n, T, out, 2));
     if (H < 224 || W < 224) return fail(VF_ERR_INVALID, "i3d_forward_flow: %dx%d flow is smaller than the 224 crop", H, W);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    VF_CUDA(cudaSetDevice(h->device));
+    if (n <= 0) return VF_OK;
+    cudaStream_t user = static_cast<cudaStream_t>(stream), s = h->cs;
+    VF_TRY(i3d_enter(h, user));
     const int cy = (H - 224) / 2, cx = (W - 224) / 2;
     for (int b0 = 0; b0 < n; b0 += h->max_stacks) {
         const int nb = (n - b0 < h->max_stacks) ? (n - b0) : h->max_stacks;
         VF_TRY(launch_i3d_phase_pack_flow(flow + size_t(b0) * T * 2 * H * W, nb, T, H, W, cy, cx, h->s0, T / 2 + 3, s));
         h->launches += 1;
-        VF_TRY(i3d_trunk(h, nb, T, out + size_t(b0) * 1024, s));
+        VF_TRY(i3d_trunk_graphed(h, nb, T, out + size_t(b0) * 1024, s));
     }
-    return VF_OK;
+    return i3d_leave(h, user);
 }
 
 int vf_i3d_read_stage(vf_i3d_t* h, int stage, float* out, int64_t capacity, int* dims5, void* stream) {
@@ -372,7 +435,10 @@ int vf_i3d_read_stage(vf_i3d_t* h, int stage, float* out, int64_t capacity, int*
     const int64_t need = int64_t(r.v.n) * r.C * r.v.T() * r.v.H() * r.v.W();
     if (!out) return VF_OK;
     if (capacity < need) return fail(VF_ERR_INVALID, "i3d_read_stage: capacity %lld < %lld", (long long)capacity, (long long)need);
-    return launch_unpack_ndhwc(r.p, r.v, r.C, 0, r.C, r.C, out, static_cast<cudaStream_t>(stream));
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
+    VF_TRY(i3d_enter(h, user));
+    VF_TRY(launch_unpack_ndhwc(r.p, r.v, r.C, 0, r.C, r.C, out, h->cs));
+    return i3d_leave(h, user);
 }
 
 int64_t vf_i3d_launch_count(const vf_i3d_t* h) { return h ? h->launches : 0; }

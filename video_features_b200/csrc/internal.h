@@ -65,6 +65,7 @@ int conv_gemm_f16(const __half* X, int C, int64_t P, const __half* Wt, int N, co
                   cudaStream_t stream);
 int device_sm_count();
 int gemm_profile(int enable);
+bool gemm_profile_on();   // event-bracketed launches cannot be captured into a graph: callers fall back to eager
 int gemm_profile_read(double* ms, int64_t* launches, double* flops);
 
 // ---- elementwise / reduction kernels
