@@ -37,13 +37,17 @@ constexpr int BK = 64;           // 64 fp16 = one 128-byte swizzle row
 constexpr int EPI_WARPS = 8;
 constexpr uint32_t SLICE_BYTES = 128 * 128;   // 128 rows x 128 B (32 fp32 or 64 fp16 columns)
 
-template <int BN, int STAGES>
+// NSPLIT = 2: the B stage holds the hi and the lo half-tile of a split-fp16 weight matrix and every K step issues two
+// MMAs against the same A tile; the epilogue then keeps ONE slice buffer per group to make room for the wider stages.
+template <int BN, int STAGES, int NSPLIT = 1>
 struct GemmCfg {
     static constexpr uint32_t A_BYTES = BM * BK * 2;          // 128 rows of A per CTA
-    static constexpr uint32_t B_BYTES = (BN / 2) * BK * 2;    // half of the B tile per CTA
+    static constexpr uint32_t B_HALF = (BN / 2) * BK * 2;     // half of the B tile per CTA (one of hi / lo)
+    static constexpr uint32_t B_BYTES = NSPLIT * B_HALF;
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr uint32_t TMEM_COLS = 2 * BN;             // two accumulator stages
-    static constexpr uint32_t STG_BYTES = 2 * 2 * SLICE_BYTES;   // 2 epilogue groups x 2 slice buffers
+    static constexpr uint32_t EPI_BUFS = NSPLIT == 2 ? 1 : 2;
+    static constexpr uint32_t STG_BYTES = 2 * EPI_BUFS * SLICE_BYTES;   // 2 epilogue groups x EPI_BUFS slice buffers
     static constexpr uint32_t BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;   // + align slack
     static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns");
@@ -90,12 +94,12 @@ __device__ __forceinline__ void epi_math32(float* v, const GemmEpi& ep, int n, i
     }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NSPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmO, const GemmEpi ep, const int M, const int N,
                      const __grid_constant__ ConvGeom cg) {
-    using Cfg = GemmCfg<BN, STAGES>;
+    using Cfg = GemmCfg<BN, STAGES, NSPLIT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
@@ -157,6 +161,9 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
                         tma_load_2d_2sm(sA + stage * Cfg::A_BYTES, &tmA, bar, kk * BK, arow);
                         tma_load_2d_2sm(sB + stage * Cfg::B_BYTES, &tmB, bar, bcol + kk * BK, n0);
+                        if (NSPLIT == 2)   // the lo half of the weights lives ntaps*k_per_tap columns to the right
+                            tma_load_2d_2sm(sB + stage * Cfg::B_BYTES + Cfg::B_HALF, &tmB, bar,
+                                            cg.ntaps * cg.k_per_tap + bcol + kk * BK, n0);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -178,8 +185,11 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     const uint64_t adesc = umma_desc_sw128(sA + stage * Cfg::A_BYTES);
                     const uint64_t bdesc = umma_desc_sw128(sB + stage * Cfg::B_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)   // +32 B (encoded 2) per K step inside the swizzle row
+                    for (int k = 0; k < BK / 16; ++k) {   // +32 B (encoded 2) per K step inside the swizzle row
                         umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (NSPLIT == 2)
+                            umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + (Cfg::B_HALF >> 4) + 2 * k, idesc, 1u);
+                    }
                     umma_commit_2sm(&empty[stage], 3);    // free this smem slot in both CTAs
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -193,7 +203,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int q = e & 3;                   // TMEM lane quarter (== warp id % 4)
         const int grp = e >> 2;
         const int row = q * 32 + lane;         // row inside this CTA's 128-row block == TMEM lane
-        uint8_t* bufs = stg + grp * 2 * SLICE_BYTES;
+        uint8_t* bufs = stg + grp * Cfg::EPI_BUFS * SLICE_BYTES;
         const bool agent = (q == 0) && (lane == 0);
         const int slice_cols = ep.out_f32 ? 32 : 64;
         const uint32_t sw = uint32_t(row & 7);
@@ -215,10 +225,10 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
 #pragma unroll 1
             for (int c = grp * slice_cols; c < BN; c += 2 * slice_cols) {
-                uint8_t* buf = bufs + (it & 1) * SLICE_BYTES;
+                uint8_t* buf = bufs + (Cfg::EPI_BUFS == 2 ? (it & 1) : 0) * SLICE_BYTES;
                 uint8_t* myrow = buf + row * 128;
-                // the TMA store issued from this buffer two slices ago must have finished reading it
-                if (agent) bulk_wait_read<1>();
+                // the TMA store that last used this buffer must have finished reading it
+                if (agent) bulk_wait_read<Cfg::EPI_BUFS - 1>();
                 named_bar_sync(1 + grp, 128);
                 const int n = n_blk * BN + c;
                 if (ep.out_f32) {
@@ -301,22 +311,22 @@ EncodeTiledFn get_encode_tiled() {
     return fn;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NSPLIT>
 int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmEpi& ep, int M,
                      int N, const ConvGeom& cg, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN, STAGES>;
+    using Cfg = GemmCfg<BN, STAGES, NSPLIT>;
     static bool attr_set[64] = {false};
     int dev = 0;
     VF_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        VF_CUDA(cudaFuncSetAttribute(gemm_f16_pair_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        VF_CUDA(cudaFuncSetAttribute(gemm_f16_pair_kernel<BN, STAGES, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::SMEM_BYTES));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
     const int pairs = device_sm_count() / 2;
     const int grid = 2 * (tiles < pairs ? tiles : pairs);
-    gemm_f16_pair_kernel<BN, STAGES><<<grid, 384, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, ep, M, N, cg);
+    gemm_f16_pair_kernel<BN, STAGES, NSPLIT><<<grid, 384, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, ep, M, N, cg);
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
@@ -365,9 +375,14 @@ static thread_local GemmProf g_prof;
 
 static int run_gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, int bn, const GemmEpi& ep,
                            int M, int N, const ConvGeom& cg, cudaStream_t stream) {
-    if (bn == 256) return launch_gemm_pair<256, 5>(tmA, tmB, tmO, ep, M, N, cg, stream);
-    if (bn == 128) return launch_gemm_pair<128, 6>(tmA, tmB, tmO, ep, M, N, cg, stream);
-    return launch_gemm_pair<64, 8>(tmA, tmB, tmO, ep, M, N, cg, stream);
+    if (cg.nsplit == 2) {
+        if (bn == 256) return launch_gemm_pair<256, 4, 2>(tmA, tmB, tmO, ep, M, N, cg, stream);
+        if (bn == 128) return launch_gemm_pair<128, 6, 2>(tmA, tmB, tmO, ep, M, N, cg, stream);
+        return launch_gemm_pair<64, 8, 2>(tmA, tmB, tmO, ep, M, N, cg, stream);
+    }
+    if (bn == 256) return launch_gemm_pair<256, 5, 1>(tmA, tmB, tmO, ep, M, N, cg, stream);
+    if (bn == 128) return launch_gemm_pair<128, 6, 1>(tmA, tmB, tmO, ep, M, N, cg, stream);
+    return launch_gemm_pair<64, 8, 1>(tmA, tmB, tmO, ep, M, N, cg, stream);
 }
 
 static int run_gemm(const CUtensorMap& tmA, const __half* B, int ldb, int64_t Ktot, int M, int N, const ConvGeom& cg,
@@ -424,6 +439,7 @@ int gemm_f16(const __half* A, int lda, const __half* B, int ldb, int M, int N, i
     memset(&cg, 0, sizeof(cg));
     cg.ntaps = 1;
     cg.k_per_tap = K;
+    cg.nsplit = 1;
     CUtensorMap tmA;
     VF_TRY(make_tmap_2d(&tmA, A, 2, uint64_t(M), uint64_t(K), uint64_t(lda) * 2, BM, BK));
     return run_gemm(tmA, B, ldb, K, M, N, cg, ep, stream);
@@ -438,7 +454,8 @@ int conv_gemm_f16(const __half* X, int C, int64_t P, const __half* Wt, int N, co
     // overlapping-row view: row p = k_per_tap contiguous elements starting at element p*C
     CUtensorMap tmA;
     VF_TRY(make_tmap_2d(&tmA, X, 2, uint64_t(P), uint64_t(g.k_per_tap), uint64_t(C) * 2, BM, BK));
-    const int64_t Ktot = int64_t(g.ntaps) * g.k_per_tap;
+    if (g.nsplit != 1 && g.nsplit != 2) return fail(VF_ERR_INVALID, "conv_gemm: nsplit must be 1 or 2");
+    const int64_t Ktot = int64_t(g.ntaps) * g.k_per_tap * g.nsplit;
     if (Ktot % 8) return fail(VF_ERR_INVALID, "conv_gemm: K must be a multiple of 8");
     return run_gemm(tmA, Wt, int(Ktot), Ktot, int(P), N, g, ep, stream);
 }

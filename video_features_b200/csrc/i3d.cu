@@ -190,15 +190,15 @@ static int run_unit(vf_i3d* h, const ConvUnit& u, const __half* X, int ldx_chann
     ConvGeom g;
     memset(&g, 0, sizeof(g));
     g.k_per_tap = u.k_per_tap;
-    g.ntaps = u.ntaps * u.nsplit;
+    g.ntaps = u.ntaps;
+    g.nsplit = u.nsplit;          // hi/lo weight passes share each A tile inside the kernel
     const int hw = v.Hp * v.Wp;
-    for (int rep = 0; rep < u.nsplit; ++rep)
-        for (int j = 0; j < u.ntaps; ++j) {
-            int off = 0;
-            if (u.k == 3) off = (j / 3 - 1) * hw + (j % 3 - 1) * v.Wp - 1;
-            else if (u.k == 7) off = (j / 4 - 1) * hw + (j % 4 - 1) * v.Wp - 1;
-            g.tap_off[rep * u.ntaps + j] = off;
-        }
+    for (int j = 0; j < u.ntaps; ++j) {
+        int off = 0;
+        if (u.k == 3) off = (j / 3 - 1) * hw + (j % 3 - 1) * v.Wp - 1;
+        else if (u.k == 7) off = (j / 4 - 1) * hw + (j % 4 - 1) * v.Wp - 1;
+        g.tap_off[j] = off;
+    }
     g.mask = 1;
     g.Tp = v.Tp; g.Hp = v.Hp; g.Wp = v.Wp;
     g.t0 = v.t0; g.t1 = v.t1; g.h0 = v.h0; g.h1 = v.h1; g.w0 = v.w0; g.w1 = v.w1;

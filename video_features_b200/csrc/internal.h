@@ -56,6 +56,8 @@ struct ConvGeom {
     int ntaps;          // number of (dt,dh) taps (1 for a 1x1x1 conv)
     int k_per_tap;      // contiguous K elements per tap (kw * C)
     int tap_off[64];    // row shift of each tap (includes the shift to the first kw tap)
+    int nsplit;         // 1, or 2: weights are a hi+lo fp16 pair, Wt = [hi (ntaps*k_per_tap) | lo (same)] along K; every
+                        // A tile is loaded once and multiplied with both (A.W_hi + A.W_lo)
     int mask;           // 1: zero the rows outside the valid region
     int Tp, Hp, Wp;     // padded volume extents (rows per sample = Tp*Hp*Wp)
     int t0, t1, h0, h1, w0, w1;

@@ -19,7 +19,9 @@
 #include <string.h>
 
 #include <functional>
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "internal.h"
@@ -61,6 +63,12 @@ struct vf_raft {
     __half *corrfeat = nullptr, *c1 = nullptr, *c2f = nullptr, *f1 = nullptr, *flow8 = nullptr, *hx = nullptr, *qx = nullptr,
            *fh = nullptr, *mk = nullptr;
     int64_t launches = 0;
+    // engine-owned stream; everything between the input pack and the convex upsample is replayed as one CUDA graph per
+    // (frames, H, W, iterations): ~600-1000 launches and ~1000 tensor-map encodes per window otherwise
+    cudaStream_t cs = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    bool use_graph = true;
+    std::map<std::tuple<int, int, int, int>, std::pair<cudaGraphExec_t, int64_t>> graphs;
     // geometry of the last call (for debug reads)
     int last_n = 0, last_H8 = 0, last_W8 = 0, corr_ld = 0, P8 = 0;
     Vol2 g8e{}, g8u{};
@@ -235,7 +243,7 @@ static int run_conv(vf_raft* h, const ConvW& cw, const __half* X, int pitch, con
                     int act, cudaStream_t s) {
     ConvGeom g;
     memset(&g, 0, sizeof(g));
-    g.ntaps = cw.ntaps; g.k_per_tap = cw.k_per_tap;
+    g.ntaps = cw.ntaps; g.k_per_tap = cw.k_per_tap; g.nsplit = 1;
     for (int j = 0; j < cw.ntaps; ++j) g.tap_off[j] = cw.dh[j] * v.Wp + cw.dw0[j];
     g.mask = 1;
     g.Tp = 1; g.Hp = v.Hp; g.Wp = v.Wp; g.t0 = 0; g.t1 = 1; g.h0 = v.h0; g.h1 = v.h1; g.w0 = v.w0; g.w1 = v.w1;
@@ -400,6 +408,13 @@ int vf_raft_create(vf_raft_t** out, const vf_named_tensor* tensors, int n_tensor
         VF_TRY(ralloc(h, &h->h32, rows8u * 128));
         VF_TRY(ralloc(h, &h->mk, rows8u * 256));
         VF_TRY(ralloc(h, &h->delta, rows8u * 8));     VF_TRY(ralloc(h, &h->mask, rows8u * 576));
+        VF_CUDA(cudaStreamCreateWithFlags(&h->cs, cudaStreamNonBlocking));
+        VF_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+        VF_CUDA(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+        {
+            const char* e = getenv("VF_NO_GRAPH");
+            h->use_graph = !(e && e[0] == '1');
+        }
         return VF_OK;
     };
     const int st = body();
@@ -413,38 +428,25 @@ int vf_raft_destroy(vf_raft_t* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (void* p : h->allocs) cudaFree(p);
+    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
+    if (h->cs) cudaStreamDestroy(h->cs);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->ev_out) cudaEventDestroy(h->ev_out);
     delete h;
     return VF_OK;
 }
 
-int vf_raft_flow(vf_raft_t* h, const void* frames, int is_u8, int chw_layout, int n_frames, int Hs, int Ws, int iters,
-                 int unpad, float* out, void* stream) {
-    if (!h || !frames || !out) return fail(VF_ERR_INVALID, "raft_flow: null argument");
-    if (n_frames < 2 || n_frames > h->max_frames) return fail(VF_ERR_INVALID, "raft_flow: %d frames outside [2, %d]", n_frames, h->max_frames);
-    if (iters < 1) return fail(VF_ERR_INVALID, "raft_flow: iters must be >= 1");
-    // InputPadder 'sintel' (raft.py:29-34)
-    const int pad_h = (((Hs / 8) + 1) * 8 - Hs) % 8, pad_w = (((Ws / 8) + 1) * 8 - Ws) % 8;
-    const int pl = pad_w / 2, pt = pad_h / 2;
-    const int H = Hs + pad_h, W = Ws + pad_w;
-    if (H > h->max_h || W > h->max_w || H < 16 || W < 16)
-        return fail(VF_ERR_INVALID, "raft_flow: padded frame %dx%d outside the workspace (%dx%d)", H, W, h->max_h, h->max_w);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    VF_CUDA(cudaSetDevice(h->device));
-    const int F = n_frames, NP = F - 1, H8 = H / 8, W8 = W / 8, P = H8 * W8, P8 = (P + 7) / 8 * 8;
-    if (P8 != P) return fail(VF_ERR_UNSUPPORTED, "raft_flow: (H/8)*(W/8) = %d must be a multiple of 8", P);
-    // ---- feature network on all F frames (instance norm)
-    VF_TRY(raft_input_pack(frames, is_u8, chw_layout, F, Hs, Ws, pt, pl, H, W, h->s0, H / 2 + 3, W / 2 + 3, s));
+}  // extern "C"
+
+namespace vf {
+
+// encoders -> correlation pyramid -> `iters` refinement steps -> mask head; the stem phase volume is already in h->s0
+static int raft_core(vf_raft* h, int F, int H, int W, int iters, cudaStream_t s) {
+    const int NP = F - 1, H8 = H / 8, W8 = W / 8, P = H8 * W8, P8 = (P + 7) / 8 * 8;
     VF_TRY(run_encoder(h, h->enc[0], true, F, H, W, h->fmap_b, 256, s));
     const Vol2 g8eF{F, H8 + 2, W8 + 2, 1, 1 + H8, 1, 1 + W8};
     VF_CUDA(cudaMemsetAsync(h->fmaps, 0, size_t(F) * P8 * 256 * sizeof(__half), s));
-    if (P8 == P) {
-        VF_TRY(raft_gather_valid(h->fmap_b, g8eF, 256, 256, h->fmaps, s));
-    } else {   // per-frame slabs of P8 rows (zero tail rows)
-        for (int f = 0; f < F; ++f) {
-            const Vol2 one{1, H8 + 2, W8 + 2, 1, 1 + H8, 1, 1 + W8};
-            VF_TRY(raft_gather_valid(h->fmap_b + size_t(f) * one.rows() * 256, one, 256, 256, h->fmaps + size_t(f) * P8 * 256, s));
-        }
-    }
+    VF_TRY(raft_gather_valid(h->fmap_b, g8eF, 256, 256, h->fmaps, s));
     // ---- all-pairs correlation + pyramid: corr[b] = fmap[b] . fmap[b+1]^T / 16
     int lvl_off[4], lvl_h[4], lvl_w[4];
     lvl_off[0] = 0; lvl_h[0] = H8; lvl_w[0] = W8;
@@ -460,9 +462,8 @@ int vf_raft_flow(vf_raft_t* h, const void* frames, int is_u8, int chw_layout, in
     for (int l = 1; l < 4; ++l)
         VF_TRY(raft_corr_pool(h->corr, int64_t(NP) * P, ldc, lvl_off[l - 1], lvl_h[l - 1], lvl_w[l - 1], lvl_off[l], s));
     h->launches += NP + 6;
-    // (the lookup kernel recomputes the level offsets as cumulative H*W, which equals lvl_off because P8 == P)
-    // ---- context network on frames[:-1] (batch norm folded)
-    VF_TRY(run_encoder(h, h->enc[1], false, NP, H, W, h->cnet_b, 256, s));   // reuses s0: the first NP frames' phase rows
+    // ---- context network on frames[:-1] (batch norm folded); reuses s0: the first NP frames' phase rows
+    VF_TRY(run_encoder(h, h->enc[1], false, NP, H, W, h->cnet_b, 256, s));
     const Vol2 g8e{NP, H8 + 2, W8 + 2, 1, 1 + H8, 1, 1 + W8};
     const Vol2 g8u{NP, H8 + 6, W8 + 6, 3, 3 + H8, 3, 3 + W8};
     const size_t rows8u = size_t(g8u.rows());
@@ -474,7 +475,6 @@ int vf_raft_flow(vf_raft_t* h, const void* frames, int is_u8, int chw_layout, in
     VF_TRY(raft_cnet_split(h->cnet_b, g8e, h->hx, h->qx, h->h32, g8u, HX, s));
     VF_TRY(raft_coords_update(h->coords1, nullptr, h->hx, h->qx, h->flow8, g8u, HX, s));    // coords1 = grid, flow = 0
     h->launches += 4;
-    // ---- refinement iterations
     for (int it = 0; it < iters; ++it) {
         VF_TRY(raft_corr_lookup(h->corr, ldc, h->coords1, NP, H8, W8, h->corrfeat, g8u, CF, s));
         VF_TRY(run_conv(h, h->convc1, h->corrfeat, CF, g8u, h->c1, 256, 0, VF_ACT_RELU, s));
@@ -495,13 +495,75 @@ int vf_raft_flow(vf_raft_t* h, const void* frames, int is_u8, int chw_layout, in
         VF_TRY(raft_coords_update(h->coords1, h->delta, h->hx, h->qx, h->flow8, g8u, HX, s));
         h->launches += 6;
     }
-    // ---- convex upsampling, once
+    // ---- mask head (once, after the last iteration)
     VF_TRY(run_conv(h, h->mk0, h->hx, HX, g8u, h->mk, 256, 0, VF_ACT_RELU, s));
     VF_TRY(run_conv(h, h->mk2, h->mk, 256, g8u, h->mask, 576, 1, VF_ACT_NONE, s));
-    if (unpad) VF_TRY(raft_upsample_flow(h->coords1, h->mask, g8u, NP, H8, W8, pt, pl, Hs, Ws, out, s));
-    else       VF_TRY(raft_upsample_flow(h->coords1, h->mask, g8u, NP, H8, W8, 0, 0, H, W, out, s));
-    h->launches += 1;
     h->last_n = NP; h->last_H8 = H8; h->last_W8 = W8; h->corr_ld = ldc; h->P8 = P8; h->g8e = g8e; h->g8u = g8u;
+    return VF_OK;
+}
+
+}  // namespace vf
+
+extern "C" {
+
+int vf_raft_flow(vf_raft_t* h, const void* frames, int is_u8, int chw_layout, int n_frames, int Hs, int Ws, int iters,
+                 int unpad, float* out, void* stream) {
+    if (!h || !frames || !out) return fail(VF_ERR_INVALID, "raft_flow: null argument");
+    if (n_frames < 2 || n_frames > h->max_frames) return fail(VF_ERR_INVALID, "raft_flow: %d frames outside [2, %d]", n_frames, h->max_frames);
+    if (iters < 1) return fail(VF_ERR_INVALID, "raft_flow: iters must be >= 1");
+    // InputPadder 'sintel' (raft.py:29-34)
+    const int pad_h = (((Hs / 8) + 1) * 8 - Hs) % 8, pad_w = (((Ws / 8) + 1) * 8 - Ws) % 8;
+    const int pl = pad_w / 2, pt = pad_h / 2;
+    const int H = Hs + pad_h, W = Ws + pad_w;
+    if (H > h->max_h || W > h->max_w || H < 16 || W < 16)
+        return fail(VF_ERR_INVALID, "raft_flow: padded frame %dx%d outside the workspace (%dx%d)", H, W, h->max_h, h->max_w);
+    const int F = n_frames, NP = F - 1, H8 = H / 8, W8 = W / 8, P = H8 * W8;
+    if (P % 8) return fail(VF_ERR_UNSUPPORTED, "raft_flow: (H/8)*(W/8) = %d must be a multiple of 8", P);
+    cudaStream_t user = static_cast<cudaStream_t>(stream), s = h->cs;
+    VF_CUDA(cudaSetDevice(h->device));
+    VF_CUDA(cudaEventRecord(h->ev_in, user));
+    VF_CUDA(cudaStreamWaitEvent(s, h->ev_in, 0));
+    VF_TRY(raft_input_pack(frames, is_u8, chw_layout, F, Hs, Ws, pt, pl, H, W, h->s0, H / 2 + 3, W / 2 + 3, s));
+    h->launches += 1;
+    if (!h->use_graph || gemm_profile_on()) {
+        VF_TRY(raft_core(h, F, H, W, iters, s));
+    } else {
+        auto key = std::make_tuple(F, H, W, iters);
+        auto it = h->graphs.find(key);
+        if (it == h->graphs.end()) {
+            const int64_t before = h->launches;
+            cudaGraph_t graph = nullptr;
+            VF_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+            const int st = raft_core(h, F, H, W, iters, s);
+            const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+            const int64_t n_launch = h->launches - before;
+            h->launches = before;
+            if (st != VF_OK) { if (graph) cudaGraphDestroy(graph); return st; }
+            if (ce != cudaSuccess) return fail(VF_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+            cudaGraphExec_t exec = nullptr;
+            const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ie != cudaSuccess) return fail(VF_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie));
+            it = h->graphs.emplace(key, std::make_pair(exec, n_launch)).first;
+        }
+        VF_CUDA(cudaGraphLaunch(it->second.first, s));
+        h->launches += it->second.second;
+        // geometry bookkeeping normally done inside raft_core
+        h->last_n = NP; h->last_H8 = H8; h->last_W8 = W8;
+        {
+            int ldc = P, lh = H8, lw = W8;
+            for (int l = 1; l < 4; ++l) { lh /= 2; lw /= 2; ldc += lh * lw; }
+            h->corr_ld = (ldc + 3) / 4 * 4;
+        }
+        h->g8e = Vol2{NP, H8 + 2, W8 + 2, 1, 1 + H8, 1, 1 + W8};
+        h->g8u = Vol2{NP, H8 + 6, W8 + 6, 3, 3 + H8, 3, 3 + W8};
+    }
+    // ---- convex upsampling, once
+    if (unpad) VF_TRY(raft_upsample_flow(h->coords1, h->mask, h->g8u, NP, H8, W8, pt, pl, Hs, Ws, out, s));
+    else       VF_TRY(raft_upsample_flow(h->coords1, h->mask, h->g8u, NP, H8, W8, 0, 0, H, W, out, s));
+    h->launches += 1;
+    VF_CUDA(cudaEventRecord(h->ev_out, s));
+    VF_CUDA(cudaStreamWaitEvent(user, h->ev_out, 0));
     return VF_OK;
 }
 
@@ -515,6 +577,7 @@ int vf_raft_padded_size(int Hs, int Ws, int* H, int* W) {
 int vf_raft_debug_read(vf_raft_t* h, int what, float* out, int64_t capacity, int* dims4, void* stream) {
     if (!h || !dims4 || h->last_n <= 0) return fail(VF_ERR_INVALID, "raft_debug_read: no forward has run");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    VF_CUDA(cudaStreamSynchronize(h->cs));      // diagnostics only: the engine stream has finished the last call
     const int n = h->last_n, H8 = h->last_H8, W8 = h->last_W8;
     int64_t need = 0;
     if (what == 0) { dims4[0] = n + 1; dims4[1] = 256; dims4[2] = H8; dims4[3] = W8; }
