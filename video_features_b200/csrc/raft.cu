@@ -8,8 +8,9 @@
 // BatchNorm (cnet, eval) is folded into the conv epilogue.  All-pairs correlation is one GEMM per pair
 // (fmap1 . fmap2^T / 16, fp32 out) followed by the 3-level average pooling; the per-iteration lookup gathers the
 // 4 x 9x9 bilinear windows (the reference's transposed window) straight into the motion encoder's operand rows.
-// The GRU state lives in `hx` = [h | inp | motion(126)+pad | flow(2)+pad] (392 columns) so that the 1x5 / 5x1 gate
-// convolutions read one contiguous run per tap; `qx` is the same row with r*h in place of h.
+// The GRU state lives in `hx` = [h_hi | h_lo | inp | motion(126)+pad | flow hi,lo + pad] (520 columns) so that the
+// 1x5 / 5x1 gate convolutions read one contiguous run per tap; `qx` is the same row with r*h in place of h.  h, the flow
+// and the correlation features are split-fp16 pairs (see raft_kernels.cu).
 // The convex-upsampling mask head and the 8x upsample run once, after the last iteration (the reference evaluates
 // them every iteration and discards 19 of the 20 results, raft.py:166-172).
 // fnet runs once per frame (the reference encodes every interior frame twice: as image2 of one pair and image1 of
@@ -37,8 +38,8 @@ struct ConvW {       // a convolution prepared for conv_gemm_f16
     float *scale = nullptr, *bias = nullptr;
 };
 
-static const int HX = 392;   // [h 128 | inp 128 | motion-out 126 + 2 pad | flow 2 + 6 pad]
-static const int CF = 328;   // 324 correlation features + 4 pad
+static const int HX = 520;   // [h_hi 128 | h_lo 128 | inp 128 | motion-out 126 + 2 pad | flow (hi,hi,lo,lo) + 4 pad]
+static const int CF = 656;   // [324 correlation features hi + 4 pad | 324 lo + 4 pad]
 
 }  // namespace vf
 
@@ -96,9 +97,12 @@ struct TensorTable {
 };
 
 // Generic filter re-layout.  w: [co][ci][kh][kw]; col(dh, dw, c) -> K column or -1.  Output rows padded to n_out.
+// col_lo (optional): a second K column receiving the same weight -- the column of the operand's lo half when the
+// activation is stored as a split-fp16 pair.
 static int upload_conv(vf_raft* h, ConvW& cw, const float* w, const float* b, int co, int ci, int kh, int kw, int n_out,
                        int Ktot, const std::function<int(int, int, int)>& col, const float* bn_scale,
-                       const float* bn_shift, float extra_scale) {
+                       const float* bn_shift, float extra_scale,
+                       const std::function<int(int, int, int)>& col_lo = nullptr) {
     std::vector<__half> B(size_t(n_out) * Ktot, __float2half_rn(0.f));
     for (int o = 0; o < co; ++o)
         for (int c = 0; c < ci; ++c)
@@ -107,7 +111,13 @@ static int upload_conv(vf_raft* h, ConvW& cw, const float* w, const float* b, in
                     const int k = col(a, d, c);
                     if (k < 0) continue;
                     if (k >= Ktot) return fail(VF_ERR_INVALID, "raft_create: filter column out of range");
-                    B[size_t(o) * Ktot + k] = __float2half_rn(w[((size_t(o) * ci + c) * kh + a) * kw + d]);
+                    const __half wv = __float2half_rn(w[((size_t(o) * ci + c) * kh + a) * kw + d]);
+                    B[size_t(o) * Ktot + k] = wv;
+                    if (col_lo) {
+                        const int k2 = col_lo(a, d, c);
+                        if (k2 >= Ktot) return fail(VF_ERR_INVALID, "raft_create: filter column out of range");
+                        if (k2 >= 0) B[size_t(o) * Ktot + k2] = wv;
+                    }
                 }
     std::vector<float> sc(n_out, 0.f), bi(n_out, 0.f);
     for (int o = 0; o < co; ++o) {
@@ -143,7 +153,7 @@ static bool bn_fold(const TensorTable& T, const std::string& p, int c, BnFold* f
 // taps = kernel rows, each a run of kw*pitch elements starting (kw/2) positions to the left.
 static int prep_same_conv(vf_raft* h, ConvW& cw, const TensorTable& T, const std::string& name, int co, int ci, int kh,
                           int kw, int pitch, const std::function<int(int)>& chan, int n_out, const BnFold* bn,
-                          float extra_scale = 1.f) {
+                          float extra_scale = 1.f, const std::function<int(int)>& chan_lo = nullptr) {
     const float* w = T.get(name + ".weight", int64_t(co) * ci * kh * kw);
     const float* b = T.get(name + ".bias", co);
     if (!w || !b) return fail(VF_ERR_INVALID, "raft_create: missing or mis-shaped tensor '%s'", name.c_str());
@@ -153,20 +163,28 @@ static int prep_same_conv(vf_raft* h, ConvW& cw, const TensorTable& T, const std
     const int kpt = cw.k_per_tap;
     return upload_conv(h, cw, w, b, co, ci, kh, kw, n_out, kh * kpt,
                        [=](int a, int d, int c) { return a * kpt + d * pitch + chan(c); },
-                       bn ? bn->scale.data() : nullptr, bn ? bn->shift.data() : nullptr, extra_scale);
+                       bn ? bn->scale.data() : nullptr, bn ? bn->shift.data() : nullptr, extra_scale,
+                       chan_lo ? std::function<int(int, int, int)>([=](int a, int d, int c) {
+                           const int k = chan_lo(c);
+                           return k < 0 ? -1 : a * kpt + d * pitch + k;
+                       }) : nullptr);
 }
 // same, but every (kh, kw) position is its own tap reading `ci` channels at column offset 0 of rows with a wider pitch
+// (dup: the operand row holds [x_hi (ci) | x_lo (ci)], the weight is written to both halves)
 static int prep_unmerged_conv(vf_raft* h, ConvW& cw, const TensorTable& T, const std::string& name, int co, int ci, int kh,
-                              int kw, int n_out, float extra_scale = 1.f) {
+                              int kw, int n_out, bool dup, float extra_scale = 1.f) {
     const float* w = T.get(name + ".weight", int64_t(co) * ci * kh * kw);
     const float* b = T.get(name + ".bias", co);
     if (!w || !b) return fail(VF_ERR_INVALID, "raft_create: missing or mis-shaped tensor '%s'", name.c_str());
-    cw.ntaps = kh * kw; cw.k_per_tap = ci;
+    const int kpt = dup ? 2 * ci : ci;
+    cw.ntaps = kh * kw; cw.k_per_tap = kpt;
     cw.dh.clear(); cw.dw0.clear();
     for (int a = 0; a < kh; ++a)
         for (int d = 0; d < kw; ++d) { cw.dh.push_back(a - kh / 2); cw.dw0.push_back(d - kw / 2); }
-    return upload_conv(h, cw, w, b, co, ci, kh, kw, n_out, kh * kw * ci,
-                       [=](int a, int d, int c) { return (a * kw + d) * ci + c; }, nullptr, nullptr, extra_scale);
+    return upload_conv(h, cw, w, b, co, ci, kh, kw, n_out, kh * kw * kpt,
+                       [=](int a, int d, int c) { return (a * kw + d) * kpt + c; }, nullptr, nullptr, extra_scale,
+                       dup ? std::function<int(int, int, int)>([=](int a, int d, int c) { return (a * kw + d) * kpt + ci + c; })
+                           : nullptr);
 }
 // stride-2 k x k conv (pad k/2) on the phase repack of its input: phase volume row q holds x[2(q-B)+p] with B =
 // border-before (2 for k=7, 1 for k=3) and `pc` = 4*C' channels ((ph*2+pw)*C' + c); filter index = 2a + p - 1
@@ -343,13 +361,18 @@ int vf_raft_create(vf_raft_t** out, const vf_named_tensor* tensors, int n_tensor
         VF_TRY(prep_encoder(h, h->enc[0], T, "fnet", false, 256));
         VF_TRY(prep_encoder(h, h->enc[1], T, "cnet", true, 256));
         const std::string u = "update_block.";
-        VF_TRY(prep_same_conv(h, h->convc1, T, u + "encoder.convc1", 256, 324, 1, 1, CF, ident, 256, nullptr));
+        VF_TRY(prep_same_conv(h, h->convc1, T, u + "encoder.convc1", 256, 324, 1, 1, CF, ident, 256, nullptr, 1.f,
+                              [](int c) { return 328 + c; }));                       // lo half of the correlation features
         VF_TRY(prep_same_conv(h, h->convc2, T, u + "encoder.convc2", 192, 256, 3, 3, 256, ident, 192, nullptr));
-        VF_TRY(prep_same_conv(h, h->convf1, T, u + "encoder.convf1", 128, 2, 7, 7, 8, ident, 128, nullptr));
+        VF_TRY(prep_same_conv(h, h->convf1, T, u + "encoder.convf1", 128, 2, 7, 7, 8, ident, 128, nullptr, 1.f,
+                              [](int c) { return 2 + c; }));                         // flow8 = (fx_hi, fy_hi, fx_lo, fy_lo, ...)
         VF_TRY(prep_same_conv(h, h->convf2, T, u + "encoder.convf2", 64, 128, 3, 3, 128, ident, 64, nullptr));
         VF_TRY(prep_same_conv(h, h->convm, T, u + "encoder.conv", 126, 256, 3, 3, 256, ident, 128, nullptr));
-        // GRU gates read hx / qx rows: input channel j -> column j for j < 382 (h, inp, motion-out), flow -> 384, 385
-        auto gmap = [](int c) { return c < 382 ? c : c + 2; };
+        // GRU gates read hx / qx rows (layout in raft_kernels.cu): conv input channel c -> column
+        //   h (c < 128) -> c [+ lo at 128 + c], inp (128..255) -> 128 + c, motion-out (256..381) -> 128 + c,
+        //   flow (382, 383) -> 512 + (c - 382) [+ lo at 514 + (c - 382)]
+        auto gmap = [](int c) { return c < 128 ? c : (c < 382 ? 128 + c : 512 + (c - 382)); };
+        auto gmap_lo = [](int c) { return c < 128 ? 128 + c : (c < 382 ? -1 : 514 + (c - 382)); };
         // z and r share their input: one GEMM with N = 256 (z | r)
         for (int dir = 0; dir < 2; ++dir) {
             const std::string sfx = dir == 0 ? "1" : "2";
@@ -367,12 +390,12 @@ int vf_raft_create(vf_raft_t** out, const vf_named_tensor* tensors, int n_tensor
             memcpy(bzr.data() + 128, br, sizeof(float) * 128);
             const vf_named_tensor tmp[2] = {{"zr.weight", wzr.data(), int64_t(wzr.size())}, {"zr.bias", bzr.data(), 256}};
             const TensorTable TT{tmp, 2};
-            VF_TRY(prep_same_conv(h, zr, TT, "zr", 256, 384, kh, kw, HX, gmap, 256, nullptr));
-            VF_TRY(prep_same_conv(h, qq, T, u + "gru.convq" + sfx, 128, 384, kh, kw, HX, gmap, 128, nullptr));
+            VF_TRY(prep_same_conv(h, zr, TT, "zr", 256, 384, kh, kw, HX, gmap, 256, nullptr, 1.f, gmap_lo));
+            VF_TRY(prep_same_conv(h, qq, T, u + "gru.convq" + sfx, 128, 384, kh, kw, HX, gmap, 128, nullptr, 1.f, gmap_lo));
         }
-        VF_TRY(prep_unmerged_conv(h, h->fh1, T, u + "flow_head.conv1", 256, 128, 3, 3, 256));
+        VF_TRY(prep_unmerged_conv(h, h->fh1, T, u + "flow_head.conv1", 256, 128, 3, 3, 256, true));    // reads [h_hi | h_lo]
         VF_TRY(prep_same_conv(h, h->fh2, T, u + "flow_head.conv2", 2, 256, 3, 3, 256, ident, 8, nullptr));
-        VF_TRY(prep_unmerged_conv(h, h->mk0, T, u + "mask.0", 256, 128, 3, 3, 256));
+        VF_TRY(prep_unmerged_conv(h, h->mk0, T, u + "mask.0", 256, 128, 3, 3, 256, true));
         VF_TRY(prep_same_conv(h, h->mk2, T, u + "mask.2", 576, 256, 1, 1, 256, ident, 576, nullptr, 0.25f));   // .25 * mask
         {
             const size_t np8 = (size_t(h->max_h / 8) * (h->max_w / 8) + 7) / 8 * 8 + 64;
@@ -481,7 +504,7 @@ static int raft_core(vf_raft* h, int F, int H, int W, int iters, cudaStream_t s)
         VF_TRY(run_conv(h, h->convc2, h->c1, 256, g8u, h->c2f, 256, 0, VF_ACT_RELU, s));            // cols 0..191
         VF_TRY(run_conv(h, h->convf1, h->flow8, 8, g8u, h->f1, 128, 0, VF_ACT_RELU, s));
         VF_TRY(run_conv(h, h->convf2, h->f1, 128, g8u, h->c2f + 192, 256, 0, VF_ACT_RELU, s));       // cols 192..255
-        VF_TRY(run_conv(h, h->convm, h->c2f, 256, g8u, h->hx + 256, HX, 0, VF_ACT_RELU, s));         // cols 256..383
+        VF_TRY(run_conv(h, h->convm, h->c2f, 256, g8u, h->hx + 384, HX, 0, VF_ACT_RELU, s));         // cols 384..511
         for (int dir = 0; dir < 2; ++dir) {
             const ConvW& zr = dir == 0 ? h->zr1 : h->zr2;
             const ConvW& qq = dir == 0 ? h->q1 : h->q2;
@@ -597,8 +620,8 @@ int vf_raft_debug_read(vf_raft_t* h, int what, float* out, int64_t capacity, int
     if (what == 0) { Vol2 v = h->g8e; v.n = n + 1; return raft_unpack2d(h->fmap_b, v, 256, 0, 256, out, s); }
     if (what == 1) return raft_unpack2d(h->cnet_b, h->g8e, 256, 0, 256, out, s);
     if (what == 2) return raft_unpack2d(h->hx, h->g8u, HX, 0, 128, out, s);          // GRU hidden state
-    if (what == 3) return raft_unpack2d(h->hx, h->g8u, HX, 384, 2, out, s);          // low-res flow (fp16 copy)
-    return raft_unpack2d(h->corrfeat, h->g8u, CF, 0, 324, out, s);                   // last lookup
+    if (what == 3) return raft_unpack2d(h->hx, h->g8u, HX, 512, 2, out, s);          // low-res flow (hi half)
+    return raft_unpack2d(h->corrfeat, h->g8u, CF, 0, 324, out, s);                   // last lookup (hi half)
 }
 
 int64_t vf_raft_launch_count(const vf_raft_t* h) { return h ? h->launches : 0; }

@@ -8,6 +8,12 @@ namespace vf {
 
 namespace {
 
+// split-fp16 representation of an fp32 value: v ~= hi + lo with |lo| <= 2^-11 |hi|
+__device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+
 inline unsigned nb(int64_t total, int threads) { return unsigned((total + threads - 1) / threads); }
 
 // images [n][H][W][3] (uint8 or fp32 in [0,255]) -> 2*(x/255) - 1 (raft.py:118-119) -> phase volume for the 7x7
@@ -232,13 +238,22 @@ __global__ void corr_lookup_kernel(const float* __restrict__ corr, int ld, const
         const float v00 = nbr[j * 10 + i], v01 = nbr[j * 10 + i + 1];
         const float v10 = nbr[(j + 1) * 10 + i], v11 = nbr[(j + 1) * 10 + i + 1];
         const float v = (1.f - ay) * ((1.f - ax) * v00 + ax * v01) + ay * ((1.f - ax) * v10 + ax * v11);
-        o[k] = __float2half_rn(v);
+        __half hi, lo;
+        split_half(v, hi, lo);
+        o[k] = hi;            // columns [0, 324): hi part
+        o[328 + k] = lo;      // columns [328, 652): lo part (the conv weights are duplicated over both halves)
     }
-    if (lvl == 3 && lane < 4) o[81 + lane] = __float2half_rn(0.f);    // pad channels 324..327
+    if (lvl == 3 && lane < 4) { o[81 + lane] = __float2half_rn(0.f); o[328 + 81 + lane] = __float2half_rn(0.f); }
 }
 
-// context network output (raw conv2 output, 256 ch at border-1 geometry) -> hx: h = tanh(net) in cols [0,128),
-// inp = relu(inp) in cols [128,256) of both hx and qx (raft.py:141-143)
+// Row layout of hx / qx (HX = 520 columns): [h_hi 0..127 | h_lo 128..255 | inp 256..383 | motion 384..511 |
+// flow 512..519 = (fx_hi, fy_hi, fx_lo, fy_lo, 0, 0, 0, 0)].  The recurrent state h, the flow and the correlation
+// features are carried as split-fp16 pairs (weights duplicated over the hi / lo columns): they are the operands the
+// flow is most sensitive to (CPU emulation on compressed video), and they are produced by these
+// elementwise kernels, so the extra precision costs no extra GEMM pass -- only a wider K.
+//
+// context network output (raw conv2 output, 256 ch at border-1 geometry): h = tanh(net) -> h32 / hx[0..255],
+// inp = relu(inp) -> cols 256..383 of both hx and qx (raft.py:141-143)
 __global__ void cnet_split_kernel(const __half* __restrict__ cnet, Vol2 vi, __half* __restrict__ hx,
                                   __half* __restrict__ qx, float* __restrict__ h32, Vol2 vo, int ld) {
     const int H = vo.h1 - vo.h0, W = vo.w1 - vo.w0;
@@ -253,20 +268,23 @@ __global__ void cnet_split_kernel(const __half* __restrict__ cnet, Vol2 vi, __ha
     if (c < 128) {
         const float t = tanhf(v);
         h32[orow * 128 + c] = t;                      // fp32 master copy of the recurrent state
-        hx[orow * ld + c] = __float2half_rn(t);
+        __half hi, lo;
+        split_half(t, hi, lo);
+        hx[orow * ld + c] = hi;
+        hx[orow * ld + 128 + c] = lo;
     } else {
         const __half r = __float2half_rn(fmaxf(v, 0.f));
-        hx[orow * ld + c] = r;
-        qx[orow * ld + c] = r;
+        hx[orow * ld + 128 + c] = r;                  // cols 256..383
+        qx[orow * ld + 128 + c] = r;
     }
 }
 
-// qx[:, 0:128] = r * h ; qx[:, 256:392] = hx[:, 256:392] (motion features + flow), valid rows.  zr = [z | r].
+// qx[:, 0:256] = split(r * h) ; qx[:, 384:520] = hx[:, 384:520] (motion features + flow), valid rows.  zr = [z | r].
 __global__ void gru_rh_kernel(const __half* __restrict__ hx, const float* __restrict__ h32, const float* __restrict__ zr,
                               __half* __restrict__ qx, Vol2 v, int ld) {
     const int H = v.h1 - v.h0, W = v.w1 - v.w0;
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    const int64_t total = int64_t(v.n) * H * W * 33;       // 16 groups of 8 for r*h + 17 groups for cols 256..391
+    const int64_t total = int64_t(v.n) * H * W * 33;       // 16 groups of 8 for r*h + 17 groups for cols 384..519
     if (idx >= total) return;
     const int gidx = int(idx % 33);
     const int64_t pos = idx / 33;
@@ -278,14 +296,13 @@ __global__ void gru_rh_kernel(const __half* __restrict__ hx, const float* __rest
         *reinterpret_cast<float4*>(hv + 4) = *reinterpret_cast<const float4*>(h32 + row * 128 + gidx * 8 + 4);
         *reinterpret_cast<float4*>(rv) = *reinterpret_cast<const float4*>(zr + row * 256 + 128 + gidx * 8);
         *reinterpret_cast<float4*>(rv + 4) = *reinterpret_cast<const float4*>(zr + row * 256 + 128 + gidx * 8 + 4);
-        uint4 o;
-        o.x = pack_half2(hv[0] * rv[0], hv[1] * rv[1]);
-        o.y = pack_half2(hv[2] * rv[2], hv[3] * rv[3]);
-        o.z = pack_half2(hv[4] * rv[4], hv[5] * rv[5]);
-        o.w = pack_half2(hv[6] * rv[6], hv[7] * rv[7]);
-        *reinterpret_cast<uint4*>(qx + row * ld + gidx * 8) = o;
+        __align__(16) __half hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split_half(hv[j] * rv[j], hi[j], lo[j]);
+        *reinterpret_cast<uint4*>(qx + row * ld + gidx * 8) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(qx + row * ld + 128 + gidx * 8) = *reinterpret_cast<const uint4*>(lo);
     } else {
-        const int c = 256 + (gidx - 16) * 8;
+        const int c = 384 + (gidx - 16) * 8;
         *reinterpret_cast<uint4*>(qx + row * ld + c) = *reinterpret_cast<const uint4*>(hx + row * ld + c);
     }
 }
@@ -314,12 +331,15 @@ __global__ void gru_update_kernel(__half* __restrict__ hx, float* __restrict__ h
 #pragma unroll
     for (int k = 0; k < 2; ++k)
         *reinterpret_cast<float4*>(h32 + row * 128 + g8 * 8 + 4 * k) = *reinterpret_cast<const float4*>(hv + 4 * k);
-    *reinterpret_cast<uint4*>(hx + row * ld + g8 * 8) = make_uint4(pack_half2(hv[0], hv[1]), pack_half2(hv[2], hv[3]),
-                                                                   pack_half2(hv[4], hv[5]), pack_half2(hv[6], hv[7]));
+    __align__(16) __half hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) split_half(hv[j], hi[j], lo[j]);
+    *reinterpret_cast<uint4*>(hx + row * ld + g8 * 8) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(hx + row * ld + 128 + g8 * 8) = *reinterpret_cast<const uint4*>(lo);
 }
 
 // coords1 += delta (fp32, first 2 of 8 GEMM output columns; delta == nullptr initialises coords to the grid);
-// flow = coords1 - coords0 written (fp16) to the flow slots of hx / qx (cols 384,385) and of flow8 (cols 0,1).
+// flow = coords1 - coords0 written as a split-fp16 pair to the flow slots of hx / qx (cols 512..515) and flow8 (0..3).
 __global__ void coords_update_kernel(float* __restrict__ coords1, const float* __restrict__ delta, __half* __restrict__ hx,
                                      __half* __restrict__ qx, __half* __restrict__ flow8, Vol2 v, int ld) {
     const int H = v.h1 - v.h0, W = v.w1 - v.w0;
@@ -337,10 +357,14 @@ __global__ void coords_update_kernel(float* __restrict__ coords1, const float* _
     }
     coords1[idx * 2] = cx;
     coords1[idx * 2 + 1] = cy;
-    const __half fx = __float2half_rn(cx - float(xw)), fy = __float2half_rn(cy - float(y));
-    hx[row * ld + 384] = fx; hx[row * ld + 385] = fy;
-    qx[row * ld + 384] = fx; qx[row * ld + 385] = fy;
-    flow8[row * 8] = fx; flow8[row * 8 + 1] = fy;
+    __half fxh, fxl, fyh, fyl;
+    split_half(cx - float(xw), fxh, fxl);
+    split_half(cy - float(y), fyh, fyl);
+    const uint2 packed = make_uint2(uint32_t(__half_as_ushort(fxh)) | (uint32_t(__half_as_ushort(fyh)) << 16),
+                                    uint32_t(__half_as_ushort(fxl)) | (uint32_t(__half_as_ushort(fyl)) << 16));
+    *reinterpret_cast<uint2*>(hx + row * ld + 512) = packed;       // (fx_hi, fy_hi, fx_lo, fy_lo)
+    *reinterpret_cast<uint2*>(qx + row * ld + 512) = packed;
+    *reinterpret_cast<uint2*>(flow8 + row * 8) = packed;
 }
 
 // RAFT.upsample_flow (raft.py:100-111): convex combination of the 3x3 neighbourhood of 8*flow with
