@@ -50,6 +50,22 @@ def base_config(n_gpus: int) -> dict:
     }
 
 
+def ncu_traffic_per_launch():
+    """Mean DRAM bytes (read + write) per launch of the dominant kernel, from the committed ncu --set full capture
+    (profiles/r1_prof_gemm_raw.csv: 4 consecutive GEMM launches of one 250-frame chunk); None if absent."""
+    import csv
+    p = os.path.join(ROOT, "profiles", "r1_prof_gemm_raw.csv")
+    try:
+        rows = list(csv.reader(open(p)))
+        hdr, units, data = rows[0], rows[1], rows[2:]
+        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        tot = [float(d[ir]) * mult[units[ir]] + float(d[iw]) * mult[units[iw]] for d in data]
+        return sum(tot) / len(tot)
+    except Exception:
+        return None
+
+
 def load_peaks() -> dict:
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -299,7 +315,8 @@ def run_engine(args, rank: int, world: int, local_rank: int) -> None:
         "bound": "tensor", "kernel": "vf::gemm_f16_kernel (tcgen05.mma kind::f16, fp32 accumulate in TMEM)",
         "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
         "frac": achieved / peaks["tflops_sustained"], "peak_source": peaks["source"] + ", bf16 dense sustained",
-        "traffic": None, "executed_tflops": executed,
+        "traffic": ncu_traffic_per_launch(), "traffic_unit": "bytes/launch (ncu dram__bytes_read+write, mean of 4 launches)",
+        "executed_tflops": executed,
         "executed_over_algorithmic": gemm_flops / (GEMM_FLOP_PER_FRAME * n * pk),
         "launches_per_step": gemm_launches // pk, "avg_launch_us": 1e3 * gemm_ms / max(gemm_launches, 1),
         "algorithmic_flop_per_launch_avg": GEMM_FLOP_PER_FRAME * n * pk / max(gemm_launches, 1),
