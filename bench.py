@@ -28,6 +28,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE JSON line: everything else a library prints there (NCCL's version banner, ...) is sent to
+# stderr by pointing fd 1 at fd 2 for the life of the process and writing the result to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 FRAMES_PER_STEP = 1000
 METRIC = "frames/sec CLIP-ViT-B/32 @224px"
 UNIT = "frames/s"
@@ -225,7 +235,7 @@ def run_reference(args, rank: int) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
@@ -349,7 +359,7 @@ def run_engine(args, rank: int, world: int, local_rank: int) -> None:
                       f"(oracle port of the reference --cpu path), torch threads={cores}, {cpu_model_name()}",
             "median_s_per_rep": statistics.median(ts)}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -444,7 +454,7 @@ def run_i3d(args) -> None:
         t0 = time.perf_counter(); i3d_net.forward_features(sd, x); dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "stacks/s", "cores": cores, "kind": "port",
                                 "sample": f"1 stack (64x224x224), oracle port of I3D fp32, torch threads={cores}, {cpu_model_name()}"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_raft(args) -> None:
@@ -491,7 +501,7 @@ def run_raft(args) -> None:
         t0 = time.perf_counter(); raft_net.forward(sd, x[:-1], x[1:], 20); dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": 2.0 / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
                                 "sample": f"2 pairs 272x480, 20 iterations, oracle port of RAFT fp32, torch threads={cores}, {cpu_model_name()}"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main() -> None:
