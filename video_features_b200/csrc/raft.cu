@@ -38,7 +38,7 @@ struct ConvW {       // a convolution prepared for conv_gemm_f16
     float *scale = nullptr, *bias = nullptr;
 };
 
-static const int HX = 520;   // [h_hi 128 | h_lo 128 | inp 128 | motion-out 126 + 2 pad | flow (hi,hi,lo,lo) + 4 pad]
+static const int HX = 648;   // [h_hi 128 | h_lo 128 | inp_hi 128 | inp_lo 128 | motion-out 126 + 2 pad | flow (hi,hi,lo,lo) + 4 pad]
 static const int CF = 656;   // [324 correlation features hi + 4 pad | 324 lo + 4 pad]
 
 }  // namespace vf
@@ -56,7 +56,8 @@ struct vf_raft {
     float* sixteenth = nullptr;      // 1/16 for the correlation scale
     // workspace
     __half *s0 = nullptr, *bufA = nullptr, *bufB = nullptr, *bufC = nullptr, *bufD = nullptr, *bufE = nullptr;
-    __half *fmap_b = nullptr, *fmaps = nullptr, *cnet_b = nullptr;
+    float *fmap32 = nullptr, *cnet32 = nullptr;     // fp32 encoder outputs (border-1 /8 geometry, 256 ch)
+    __half *corrA = nullptr, *corrB = nullptr;       // split operands of the correlation GEMM, dense [F][P8][768]
     double *st_a = nullptr, *st_b = nullptr;
     float *corr = nullptr, *coords1 = nullptr, *delta = nullptr, *mask = nullptr;
     float *rawA = nullptr, *rawB = nullptr;     // fp32 conv outputs feeding InstanceNorm
@@ -187,39 +188,47 @@ static int prep_unmerged_conv(vf_raft* h, ConvW& cw, const TensorTable& T, const
                            : nullptr);
 }
 // stride-2 k x k conv (pad k/2) on the phase repack of its input: phase volume row q holds x[2(q-B)+p] with B =
-// border-before (2 for k=7, 1 for k=3) and `pc` = 4*C' channels ((ph*2+pw)*C' + c); filter index = 2a + p - 1
-// for tap a (both k=7: a in 0..3, k=3: a in 0..1).
+// border-before (2 for k=7, 1 for k=3); filter index = 2a + p - 1 for tap a (k=7: a in 0..3, k=3: a in 0..1).
+// Row layout: `pitch` channels per position, channel c of phase (ph,pw) at (ph*2+pw)*phase_stride + c, and -- when the
+// activation is a split-fp16 pair -- its lo half `lo_off` columns further (lo_off < 0: single fp16).
 static int prep_stride2_conv(vf_raft* h, ConvW& cw, const TensorTable& T, const std::string& name, int co, int ci, int k,
-                             int cpad, int n_out, const BnFold* bn) {
+                             int pitch, int phase_stride, int lo_off, int n_out, const BnFold* bn) {
     const float* w = T.get(name + ".weight", int64_t(co) * ci * k * k);
     const float* b = T.get(name + ".bias", co);
     if (!w || !b) return fail(VF_ERR_INVALID, "raft_create: missing or mis-shaped tensor '%s'", name.c_str());
-    const int na = (k == 7) ? 4 : 2, before = (k == 7) ? 2 : 1, pc = 4 * cpad;
-    cw.ntaps = na; cw.k_per_tap = na * pc;
+    const int na = (k == 7) ? 4 : 2, before = (k == 7) ? 2 : 1;
+    cw.ntaps = na; cw.k_per_tap = na * pitch;
     cw.dh.clear(); cw.dw0.clear();
     for (int a = 0; a < na; ++a) { cw.dh.push_back(a - before); cw.dw0.push_back(-before); }
     const int kpt = cw.k_per_tap;
     // invert (kh, kw) -> (a, ph), (bq, pw): kh = 2a + ph - 1
-    return upload_conv(h, cw, w, b, co, ci, k, k, n_out, na * kpt,
-                       [=](int kh, int kw, int c) {
-                           const int a = (kh + 1) / 2, ph = (kh + 1) % 2, bq = (kw + 1) / 2, pw = (kw + 1) % 2;
-                           return a * kpt + bq * pc + (ph * 2 + pw) * cpad + c;
-                       },
-                       bn ? bn->scale.data() : nullptr, bn ? bn->shift.data() : nullptr, 1.f);
+    auto col = [=](int kh, int kw, int c) {
+        const int a = (kh + 1) / 2, ph = (kh + 1) % 2, bq = (kw + 1) / 2, pw = (kw + 1) % 2;
+        return a * kpt + bq * pitch + (ph * 2 + pw) * phase_stride + c;
+    };
+    return upload_conv(h, cw, w, b, co, ci, k, k, n_out, na * kpt, col,
+                       bn ? bn->scale.data() : nullptr, bn ? bn->shift.data() : nullptr, 1.f,
+                       lo_off >= 0 ? std::function<int(int, int, int)>([=](int kh, int kw, int c) { return col(kh, kw, c) + lo_off; })
+                                   : nullptr);
 }
-// 1x1 stride-2 downsample: phase (0,0) of the repacked row = its first `ci` channels
+// 1x1 stride-2 downsample: phase (0,0) of the repacked row = its first channels ([hi ci | lo ci] when split)
 static int prep_down_conv(vf_raft* h, ConvW& cw, const TensorTable& T, const std::string& name, int co, int ci, int n_out,
-                          const BnFold* bn) {
+                          bool split, const BnFold* bn) {
     const float* w = T.get(name + ".weight", int64_t(co) * ci);
     const float* b = T.get(name + ".bias", co);
     if (!w || !b) return fail(VF_ERR_INVALID, "raft_create: missing or mis-shaped tensor '%s'", name.c_str());
-    cw.ntaps = 1; cw.k_per_tap = ci;
+    cw.ntaps = 1; cw.k_per_tap = split ? 2 * ci : ci;
     cw.dh = {0}; cw.dw0 = {0};
-    return upload_conv(h, cw, w, b, co, ci, 1, 1, n_out, ci, [=](int, int, int c) { return c; },
-                       bn ? bn->scale.data() : nullptr, bn ? bn->shift.data() : nullptr, 1.f);
+    return upload_conv(h, cw, w, b, co, ci, 1, 1, n_out, cw.k_per_tap, [=](int, int, int c) { return c; },
+                       bn ? bn->scale.data() : nullptr, bn ? bn->shift.data() : nullptr, 1.f,
+                       split ? std::function<int(int, int, int)>([=](int, int, int c) { return ci + c; }) : nullptr);
 }
 
+// `split`: the encoder's activations are split-fp16 pairs, rows = [hi C | lo C] (the instance-norm encoder: all of
+// its conv inputs are written by elementwise kernels); otherwise single fp16 rows of C channels (batch-norm encoder:
+// conv inputs come from GEMM epilogues).  The stem reads the split input phase volume in both cases.
 static int prep_encoder(vf_raft* h, vf_raft::Enc& e, const TensorTable& T, const std::string& p, bool batch, int out_dim) {
+    const bool split = !batch;
     auto ident = [](int c) { return c; };
     BnFold f; const BnFold* bn = nullptr;
     auto fold = [&](const std::string& name, int c) -> int {
@@ -227,13 +236,18 @@ static int prep_encoder(vf_raft* h, vf_raft::Enc& e, const TensorTable& T, const
         if (!bn_fold(T, name, c, &f)) return fail(VF_ERR_INVALID, "raft_create: missing BatchNorm '%s'", name.c_str());
         bn = &f; return VF_OK;
     };
+    auto same3 = [&](ConvW& cw, const std::string& name, int co, int ci) -> int {
+        if (split) return prep_same_conv(h, cw, T, name, co, ci, 3, 3, 2 * ci, ident, co, bn, 1.f, [=](int c) { return ci + c; });
+        return prep_same_conv(h, cw, T, name, co, ci, 3, 3, ci, ident, co, bn);
+    };
     VF_TRY(fold(p + ".norm1", 64));
-    VF_TRY(prep_stride2_conv(h, e.conv1, T, p + ".conv1", 64, 3, 7, 4, 64, bn));     // phase row: 4 phases x 4 (3 used)
+    // stem: input phase rows = [16 hi | 16 lo], 4 (3 used) channels per phase
+    VF_TRY(prep_stride2_conv(h, e.conv1, T, p + ".conv1", 64, 3, 7, 32, 4, 16, 64, bn));
     for (int blk = 0; blk < 2; ++blk)
         for (int cv = 0; cv < 2; ++cv) {
             const std::string b = p + ".layer1." + std::to_string(blk);
             VF_TRY(fold(b + ".norm" + std::to_string(cv + 1), 64));
-            VF_TRY(prep_same_conv(h, e.l1[blk * 2 + cv], T, b + ".conv" + std::to_string(cv + 1), 64, 64, 3, 3, 64, ident, 64, bn));
+            VF_TRY(same3(e.l1[blk * 2 + cv], b + ".conv" + std::to_string(cv + 1), 64, 64));
         }
     const int dims[2][2] = {{64, 96}, {96, 128}};
     for (int L = 0; L < 2; ++L) {
@@ -242,18 +256,21 @@ static int prep_encoder(vf_raft* h, vf_raft::Enc& e, const TensorTable& T, const
         ConvW& c1 = L == 0 ? e.l2c1 : e.l3c1;
         ConvW& dn = L == 0 ? e.l2down : e.l3down;
         ConvW* rest = L == 0 ? e.l2 : e.l3;
+        const int crow = split ? 2 * ci : ci;          // channels per phase block of the repacked row
         VF_TRY(fold(lp + ".0.norm1", co));
-        VF_TRY(prep_stride2_conv(h, c1, T, lp + ".0.conv1", co, ci, 3, ci, co, bn));
+        VF_TRY(prep_stride2_conv(h, c1, T, lp + ".0.conv1", co, ci, 3, 4 * crow, crow, split ? ci : -1, co, bn));
         VF_TRY(fold(lp + ".0.downsample.1", co));
-        VF_TRY(prep_down_conv(h, dn, T, lp + ".0.downsample.0", co, ci, co, bn));
+        VF_TRY(prep_down_conv(h, dn, T, lp + ".0.downsample.0", co, ci, co, split, bn));
         VF_TRY(fold(lp + ".0.norm2", co));
-        VF_TRY(prep_same_conv(h, rest[0], T, lp + ".0.conv2", co, co, 3, 3, co, ident, co, bn));
+        VF_TRY(same3(rest[0], lp + ".0.conv2", co, co));
         VF_TRY(fold(lp + ".1.norm1", co));
-        VF_TRY(prep_same_conv(h, rest[1], T, lp + ".1.conv1", co, co, 3, 3, co, ident, co, bn));
+        VF_TRY(same3(rest[1], lp + ".1.conv1", co, co));
         VF_TRY(fold(lp + ".1.norm2", co));
-        VF_TRY(prep_same_conv(h, rest[2], T, lp + ".1.conv2", co, co, 3, 3, co, ident, co, bn));
+        VF_TRY(same3(rest[2], lp + ".1.conv2", co, co));
     }
-    VF_TRY(prep_same_conv(h, e.conv2, T, p + ".conv2", out_dim, 128, 1, 1, 128, ident, out_dim, nullptr));
+    if (split) VF_TRY(prep_same_conv(h, e.conv2, T, p + ".conv2", out_dim, 128, 1, 1, 256, ident, out_dim, nullptr, 1.f,
+                                     [](int c) { return 128 + c; }));
+    else       VF_TRY(prep_same_conv(h, e.conv2, T, p + ".conv2", out_dim, 128, 1, 1, 128, ident, out_dim, nullptr));
     return VF_OK;
 }
 
@@ -272,28 +289,30 @@ static int run_conv(vf_raft* h, const ConvW& cw, const __half* X, int pitch, con
     return conv_gemm_f16(X, pitch, v.rows(), cw.w, cw.n_out, g, ep, s);
 }
 
-// BasicEncoder.forward on m frames whose stem phase volume is in h->s0; result rows (border-1 /8 geometry) in `out`
-static int run_encoder(vf_raft* h, const vf_raft::Enc& e, bool inst, int m, int H, int W, __half* out, int out_dim,
+// BasicEncoder.forward on m frames whose (split) stem phase volume is in h->s0; the 256-channel output is written in
+// fp32 to `out` (border-1 /8 geometry).  inst: instance-norm encoder with split-fp16 activations (rows of 2C channels).
+static int run_encoder(vf_raft* h, const vf_raft::Enc& e, bool inst, int m, int H, int W, float* out, int out_dim,
                        cudaStream_t s) {
     const Vol2 g2{m, H / 2 + 3, W / 2 + 3, 2, 2 + H / 2, 2, 2 + W / 2};
     const Vol2 g4{m, H / 4 + 2, W / 4 + 2, 1, 1 + H / 4, 1, 1 + W / 4};
     const Vol2 g8{m, H / 8 + 2, W / 8 + 2, 1, 1 + H / 8, 1, 1 + W / 8};
     __half *x = h->bufA, *y = h->bufB, *r = h->bufC, *r2 = h->bufD, *ph = h->bufE;
     float *rf = h->rawA, *rf2 = h->rawB;
-    auto norm_relu = [&](const float* raw, __half* dst, const Vol2& v, int C) -> int {   // dst = relu(IN(raw))
+    const int mul = inst ? 2 : 1;          // row pitch multiplier of the activation buffers
+    auto norm_relu = [&](const float* raw, __half* dst, const Vol2& v, int C) -> int {   // dst = split(relu(IN(raw)))
         VF_TRY(raft_instnorm_stats(raw, v, C, h->st_a, s));
         h->launches += 2;
         return raft_instnorm_apply(raw, h->st_a, nullptr, nullptr, nullptr, dst, v, C, s);
     };
     // conv1 + norm1 + relu
-    if (inst) { VF_TRY(run_conv(h, e.conv1, h->s0, 16, g2, rf, 64, 1, VF_ACT_NONE, s)); VF_TRY(norm_relu(rf, x, g2, 64)); }
-    else      { VF_TRY(run_conv(h, e.conv1, h->s0, 16, g2, x, 64, 0, VF_ACT_RELU, s)); }
+    if (inst) { VF_TRY(run_conv(h, e.conv1, h->s0, 32, g2, rf, 64, 1, VF_ACT_NONE, s)); VF_TRY(norm_relu(rf, x, g2, 64)); }
+    else      { VF_TRY(run_conv(h, e.conv1, h->s0, 32, g2, x, 64, 0, VF_ACT_RELU, s)); }
     // a stride-1 residual block at geometry v with C channels: x <- relu(x + relu(norm2(conv2(relu(norm1(conv1(x)))))))
     auto res_block = [&](const ConvW& c1, const ConvW& c2, const Vol2& v, int C) -> int {
         if (inst) {
-            VF_TRY(run_conv(h, c1, x, C, v, rf, C, 1, VF_ACT_NONE, s));
+            VF_TRY(run_conv(h, c1, x, 2 * C, v, rf, C, 1, VF_ACT_NONE, s));
             VF_TRY(norm_relu(rf, y, v, C));
-            VF_TRY(run_conv(h, c2, y, C, v, rf, C, 1, VF_ACT_NONE, s));
+            VF_TRY(run_conv(h, c2, y, 2 * C, v, rf, C, 1, VF_ACT_NONE, s));
             VF_TRY(raft_instnorm_stats(rf, v, C, h->st_a, s));
             VF_TRY(raft_instnorm_apply(rf, h->st_a, x, nullptr, nullptr, x, v, C, s));
             h->launches += 2;
@@ -310,13 +329,13 @@ static int run_encoder(vf_raft* h, const vf_raft::Enc& e, bool inst, int m, int 
     // a stride-2 residual block: vin (Cin) -> vout (Cout)
     auto down_block = [&](const ConvW& c1, const ConvW& dn, const ConvW& c2, const Vol2& vin, const Vol2& vout, int Cin,
                           int Cout) -> int {
-        VF_TRY(raft_phase_repack(x, vin, Cin, ph, vout, s));
+        VF_TRY(raft_phase_repack(x, vin, mul * Cin, ph, vout, s));
         h->launches += 1;
         if (inst) {
-            VF_TRY(run_conv(h, c1, ph, 4 * Cin, vout, rf, Cout, 1, VF_ACT_NONE, s));
+            VF_TRY(run_conv(h, c1, ph, 8 * Cin, vout, rf, Cout, 1, VF_ACT_NONE, s));
             VF_TRY(norm_relu(rf, y, vout, Cout));
-            VF_TRY(run_conv(h, c2, y, Cout, vout, rf, Cout, 1, VF_ACT_NONE, s));
-            VF_TRY(run_conv(h, dn, ph, 4 * Cin, vout, rf2, Cout, 1, VF_ACT_NONE, s));
+            VF_TRY(run_conv(h, c2, y, 2 * Cout, vout, rf, Cout, 1, VF_ACT_NONE, s));
+            VF_TRY(run_conv(h, dn, ph, 8 * Cin, vout, rf2, Cout, 1, VF_ACT_NONE, s));
             VF_TRY(raft_instnorm_stats(rf, vout, Cout, h->st_a, s));
             VF_TRY(raft_instnorm_stats(rf2, vout, Cout, h->st_b, s));
             VF_TRY(raft_instnorm_apply(rf, h->st_a, nullptr, rf2, h->st_b, x, vout, Cout, s));   // relu(IN(down) + relu(IN(c2)))
@@ -334,7 +353,7 @@ static int run_encoder(vf_raft* h, const vf_raft::Enc& e, bool inst, int m, int 
     VF_TRY(res_block(e.l2[1], e.l2[2], g4, 96));
     VF_TRY(down_block(e.l3c1, e.l3down, e.l3[0], g4, g8, 96, 128));
     VF_TRY(res_block(e.l3[1], e.l3[2], g8, 128));
-    VF_TRY(run_conv(h, e.conv2, x, 128, g8, out, out_dim, 0, VF_ACT_NONE, s));
+    VF_TRY(run_conv(h, e.conv2, x, mul * 128, g8, out, out_dim, 1, VF_ACT_NONE, s));      // fp32 output
     return VF_OK;
 }
 
@@ -369,10 +388,10 @@ int vf_raft_create(vf_raft_t** out, const vf_named_tensor* tensors, int n_tensor
         VF_TRY(prep_same_conv(h, h->convf2, T, u + "encoder.convf2", 64, 128, 3, 3, 128, ident, 64, nullptr));
         VF_TRY(prep_same_conv(h, h->convm, T, u + "encoder.conv", 126, 256, 3, 3, 256, ident, 128, nullptr));
         // GRU gates read hx / qx rows (layout in raft_kernels.cu): conv input channel c -> column
-        //   h (c < 128) -> c [+ lo at 128 + c], inp (128..255) -> 128 + c, motion-out (256..381) -> 128 + c,
-        //   flow (382, 383) -> 512 + (c - 382) [+ lo at 514 + (c - 382)]
-        auto gmap = [](int c) { return c < 128 ? c : (c < 382 ? 128 + c : 512 + (c - 382)); };
-        auto gmap_lo = [](int c) { return c < 128 ? 128 + c : (c < 382 ? -1 : 514 + (c - 382)); };
+        //   h (c < 128) -> c [+ lo at 128 + c], inp (128..255) -> 128 + c [+ lo at 256 + c],
+        //   motion-out (256..381) -> 256 + c, flow (382, 383) -> 640 + (c - 382) [+ lo at 642 + (c - 382)]
+        auto gmap = [](int c) { return c < 128 ? c : (c < 256 ? 128 + c : (c < 382 ? 256 + c : 640 + (c - 382))); };
+        auto gmap_lo = [](int c) { return c < 128 ? 128 + c : (c < 256 ? 256 + c : (c < 382 ? -1 : 642 + (c - 382))); };
         // z and r share their input: one GEMM with N = 256 (z | r)
         for (int dir = 0; dir < 2; ++dir) {
             const std::string sfx = dir == 0 ? "1" : "2";
@@ -409,16 +428,17 @@ int vf_raft_create(vf_raft_t** out, const vf_named_tensor* tensors, int n_tensor
         const size_t rows2 = F * (H / 2 + 3) * (W / 2 + 3), rows4 = F * (H / 4 + 2) * (W / 4 + 2);
         const size_t rows8e = F * (H / 8 + 2) * (W / 8 + 2), rows8u = NP * (H / 8 + 6) * (W / 8 + 6);
         const size_t enc_elems = rows2 * 64 > rows4 * 96 ? rows2 * 64 : rows4 * 96;
-        VF_TRY(ralloc(h, &h->s0, rows2 * 16));
-        VF_TRY(ralloc(h, &h->bufA, enc_elems)); VF_TRY(ralloc(h, &h->bufB, enc_elems));
+        VF_TRY(ralloc(h, &h->s0, rows2 * 32));
+        VF_TRY(ralloc(h, &h->bufA, 2 * enc_elems)); VF_TRY(ralloc(h, &h->bufB, 2 * enc_elems));   // split rows
         VF_TRY(ralloc(h, &h->bufC, enc_elems)); VF_TRY(ralloc(h, &h->bufD, enc_elems));
         VF_TRY(ralloc(h, &h->rawA, enc_elems)); VF_TRY(ralloc(h, &h->rawB, enc_elems));
         const size_t ph_elems = rows4 * 256 > rows8e * 384 ? rows4 * 256 : rows8e * 384;
-        VF_TRY(ralloc(h, &h->bufE, ph_elems));
-        VF_TRY(ralloc(h, &h->fmap_b, rows8e * 256));
-        VF_TRY(ralloc(h, &h->cnet_b, rows8e * 256));
+        VF_TRY(ralloc(h, &h->bufE, 2 * ph_elems));
+        VF_TRY(ralloc(h, &h->fmap32, rows8e * 256));
+        VF_TRY(ralloc(h, &h->cnet32, rows8e * 256));
         const size_t P = size_t(H / 8) * (W / 8), P8 = (P + 7) / 8 * 8;
-        VF_TRY(ralloc(h, &h->fmaps, F * P8 * 256));
+        VF_TRY(ralloc(h, &h->corrA, F * P8 * 768));
+        VF_TRY(ralloc(h, &h->corrB, F * P8 * 768));
         VF_TRY(ralloc(h, &h->st_a, F * 128 * 2)); VF_TRY(ralloc(h, &h->st_b, F * 128 * 2));
         const size_t ld = (P8 + P / 4 + P / 16 + P / 64 + 64 + 3) / 4 * 4;
         VF_TRY(ralloc(h, &h->corr, NP * P * ld));
@@ -466,10 +486,9 @@ namespace vf {
 // encoders -> correlation pyramid -> `iters` refinement steps -> mask head; the stem phase volume is already in h->s0
 static int raft_core(vf_raft* h, int F, int H, int W, int iters, cudaStream_t s) {
     const int NP = F - 1, H8 = H / 8, W8 = W / 8, P = H8 * W8, P8 = (P + 7) / 8 * 8;
-    VF_TRY(run_encoder(h, h->enc[0], true, F, H, W, h->fmap_b, 256, s));
+    VF_TRY(run_encoder(h, h->enc[0], true, F, H, W, h->fmap32, 256, s));
     const Vol2 g8eF{F, H8 + 2, W8 + 2, 1, 1 + H8, 1, 1 + W8};
-    VF_CUDA(cudaMemsetAsync(h->fmaps, 0, size_t(F) * P8 * 256 * sizeof(__half), s));
-    VF_TRY(raft_gather_valid(h->fmap_b, g8eF, 256, 256, h->fmaps, s));
+    VF_TRY(raft_corr_operands(h->fmap32, g8eF, P8, h->corrA, h->corrB, s));
     // ---- all-pairs correlation + pyramid: corr[b] = fmap[b] . fmap[b+1]^T / 16
     int lvl_off[4], lvl_h[4], lvl_w[4];
     lvl_off[0] = 0; lvl_h[0] = H8; lvl_w[0] = W8;
@@ -480,13 +499,14 @@ static int raft_core(vf_raft* h, int F, int H, int W, int iters, cudaStream_t s)
         GemmEpi ep;
         memset(&ep, 0, sizeof(ep));
         ep.out = h->corr + size_t(b) * P * ldc; ep.ldo = ldc; ep.out_f32 = 1; ep.scale = h->sixteenth; ep.act = VF_ACT_NONE;
-        VF_TRY(gemm_f16(h->fmaps + size_t(b) * P8 * 256, 256, h->fmaps + size_t(b + 1) * P8 * 256, 256, P, P8, 256, ep, s));
+        // 3-term split product: [f1_hi | f1_lo | f1_hi] . [f2_hi | f2_hi | f2_lo]^T
+        VF_TRY(gemm_f16(h->corrA + size_t(b) * P8 * 768, 768, h->corrB + size_t(b + 1) * P8 * 768, 768, P, P8, 768, ep, s));
     }
     for (int l = 1; l < 4; ++l)
         VF_TRY(raft_corr_pool(h->corr, int64_t(NP) * P, ldc, lvl_off[l - 1], lvl_h[l - 1], lvl_w[l - 1], lvl_off[l], s));
     h->launches += NP + 6;
     // ---- context network on frames[:-1] (batch norm folded); reuses s0: the first NP frames' phase rows
-    VF_TRY(run_encoder(h, h->enc[1], false, NP, H, W, h->cnet_b, 256, s));
+    VF_TRY(run_encoder(h, h->enc[1], false, NP, H, W, h->cnet32, 256, s));
     const Vol2 g8e{NP, H8 + 2, W8 + 2, 1, 1 + H8, 1, 1 + W8};
     const Vol2 g8u{NP, H8 + 6, W8 + 6, 3, 3 + H8, 3, 3 + W8};
     const size_t rows8u = size_t(g8u.rows());
@@ -495,7 +515,7 @@ static int raft_core(vf_raft* h, int F, int H, int W, int iters, cudaStream_t s)
     VF_CUDA(cudaMemsetAsync(h->qx, 0, rows8u * HX * sizeof(__half), s));
     VF_CUDA(cudaMemsetAsync(h->flow8, 0, rows8u * 8 * sizeof(__half), s));
     VF_CUDA(cudaMemsetAsync(h->corrfeat, 0, rows8u * CF * sizeof(__half), s));
-    VF_TRY(raft_cnet_split(h->cnet_b, g8e, h->hx, h->qx, h->h32, g8u, HX, s));
+    VF_TRY(raft_cnet_split(h->cnet32, g8e, h->hx, h->qx, h->h32, g8u, HX, s));
     VF_TRY(raft_coords_update(h->coords1, nullptr, h->hx, h->qx, h->flow8, g8u, HX, s));    // coords1 = grid, flow = 0
     h->launches += 4;
     for (int it = 0; it < iters; ++it) {
@@ -504,7 +524,7 @@ static int raft_core(vf_raft* h, int F, int H, int W, int iters, cudaStream_t s)
         VF_TRY(run_conv(h, h->convc2, h->c1, 256, g8u, h->c2f, 256, 0, VF_ACT_RELU, s));            // cols 0..191
         VF_TRY(run_conv(h, h->convf1, h->flow8, 8, g8u, h->f1, 128, 0, VF_ACT_RELU, s));
         VF_TRY(run_conv(h, h->convf2, h->f1, 128, g8u, h->c2f + 192, 256, 0, VF_ACT_RELU, s));       // cols 192..255
-        VF_TRY(run_conv(h, h->convm, h->c2f, 256, g8u, h->hx + 384, HX, 0, VF_ACT_RELU, s));         // cols 384..511
+        VF_TRY(run_conv(h, h->convm, h->c2f, 256, g8u, h->hx + 512, HX, 0, VF_ACT_RELU, s));         // cols 512..639
         for (int dir = 0; dir < 2; ++dir) {
             const ConvW& zr = dir == 0 ? h->zr1 : h->zr2;
             const ConvW& qq = dir == 0 ? h->q1 : h->q2;
@@ -617,10 +637,10 @@ int vf_raft_debug_read(vf_raft_t* h, int what, float* out, int64_t capacity, int
         VF_CUDA(cudaMemcpyAsync(out, h->corr, size_t(need) * sizeof(float), cudaMemcpyDeviceToDevice, s));
         return VF_OK;
     }
-    if (what == 0) { Vol2 v = h->g8e; v.n = n + 1; return raft_unpack2d(h->fmap_b, v, 256, 0, 256, out, s); }
-    if (what == 1) return raft_unpack2d(h->cnet_b, h->g8e, 256, 0, 256, out, s);
+    if (what == 0) { Vol2 v = h->g8e; v.n = n + 1; return raft_unpack2d_f32(h->fmap32, v, 256, 0, 256, out, s); }
+    if (what == 1) return raft_unpack2d_f32(h->cnet32, h->g8e, 256, 0, 256, out, s);
     if (what == 2) return raft_unpack2d(h->hx, h->g8u, HX, 0, 128, out, s);          // GRU hidden state
-    if (what == 3) return raft_unpack2d(h->hx, h->g8u, HX, 512, 2, out, s);          // low-res flow (hi half)
+    if (what == 3) return raft_unpack2d(h->hx, h->g8u, HX, 640, 2, out, s);          // low-res flow (hi half)
     return raft_unpack2d(h->corrfeat, h->g8u, CF, 0, 324, out, s);                   // last lookup (hi half)
 }
 

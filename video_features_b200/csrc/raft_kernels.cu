@@ -17,7 +17,8 @@ __device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
 inline unsigned nb(int64_t total, int threads) { return unsigned((total + threads - 1) / threads); }
 
 // images [n][H][W][3] (uint8 or fp32 in [0,255]) -> 2*(x/255) - 1 (raft.py:118-119) -> phase volume for the 7x7
-// stride-2 pad-3 stem: out[hq][wq][((ph*2+pw)*4 + c)] = x[2(hq-2)+ph][2(wq-2)+pw][c], 16 channels (12 used).
+// stride-2 pad-3 stem: out[hq][wq][((ph*2+pw)*4 + c)] = x[2(hq-2)+ph][2(wq-2)+pw][c] as a split-fp16 pair:
+// 32 channels = [16 hi (12 used) | 16 lo].
 // (Hs, Ws) is the source frame; (H, W) the /8-padded frame with the source at (pad_top, pad_left): InputPadder's
 // replicate padding (raft.py:36-37) is a coordinate clamp.
 template <typename TIn>
@@ -27,9 +28,9 @@ __global__ void raft_input_pack_kernel(const TIn* __restrict__ img, int n, int H
     const int64_t total = int64_t(n) * Hq * Wq;
     if (idx >= total) return;
     const int wq = int(idx % Wq), hq = int((idx / Wq) % Hq), b = int(idx / (int64_t(Wq) * Hq));
-    __align__(16) __half vals[16];
+    __align__(16) __half vals[32];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) vals[i] = __float2half_rn(0.f);
+    for (int i = 0; i < 32; ++i) vals[i] = __float2half_rn(0.f);
 #pragma unroll
     for (int ph = 0; ph < 2; ++ph)
 #pragma unroll
@@ -41,13 +42,13 @@ __global__ void raft_input_pack_kernel(const TIn* __restrict__ img, int n, int H
             for (int c = 0; c < 3; ++c) {
                 const float v = chw_layout ? float(img[((int64_t(b) * 3 + c) * Hs + y) * Ws + x])
                                            : float(img[((int64_t(b) * Hs + y) * Ws + x) * 3 + c]);
-                vals[(ph * 2 + pw) * 4 + c] =
-                    __float2half_rn(__fsub_rn(__fmul_rn(2.0f, __fdiv_rn(v, 255.0f)), 1.0f));
+                split_half(__fsub_rn(__fmul_rn(2.0f, __fdiv_rn(v, 255.0f)), 1.0f), vals[(ph * 2 + pw) * 4 + c],
+                           vals[16 + (ph * 2 + pw) * 4 + c]);
             }
         }
-    uint4* o = reinterpret_cast<uint4*>(out + idx * 16);
-    o[0] = reinterpret_cast<const uint4*>(vals)[0];
-    o[1] = reinterpret_cast<const uint4*>(vals)[1];
+    uint4* o = reinterpret_cast<uint4*>(out + idx * 32);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = reinterpret_cast<const uint4*>(vals)[i];
 }
 
 // space-to-depth for a stride-2 3x3 (pad 1) consumer: out[q][(ph*2+pw)*C + c] = in_valid[2(q-1)+ph][2(q'-1)+pw][c]
@@ -93,9 +94,10 @@ __global__ void instnorm_stats_kernel(const float* __restrict__ x, Vol2 v, int C
 }
 
 // The raw conv outputs that feed InstanceNorm are kept in fp32 (an fp16 copy would lose |mean|/|std| bits in the
-// mean subtraction).
+// mean subtraction), and the normalised activations -- the A operands of the next conv -- are written as split-fp16
+// pairs: row = [hi C | lo C] (the conv weights are duplicated over both halves).
 // y = relu(IN(a))                                                    (res_h == res_raw == nullptr)
-// y = relu(res_h + relu(IN(a)))                                      stride-1 ResidualBlock tail (res_h: fp16 x)
+// y = relu(res_h + relu(IN(a)))                                      stride-1 ResidualBlock tail (res_h: split x)
 // y = relu(IN(res_raw) + relu(IN(a)))                                stride-2 ResidualBlock tail (norm3(downsample))
 // Every position of the volume is written; border positions get zeros (the next conv's padding).  8 channels/thread.
 __global__ void instnorm_apply_kernel(const float* __restrict__ a, const double* __restrict__ a_stats,
@@ -109,9 +111,11 @@ __global__ void instnorm_apply_kernel(const float* __restrict__ a, const double*
     const int c8 = int(idx % cg);
     const int64_t pos = idx / cg;
     const int wq = int(pos % v.Wp), hq = int((pos / v.Wp) % v.Hp), b = int(pos / (int64_t(v.Wp) * v.Hp));
-    const int64_t off = pos * C + c8 * 8;
+    const int64_t off = pos * C + c8 * 8;              // fp32 raw rows: pitch C
+    const int64_t off2 = pos * (2 * C) + c8 * 8;       // split rows: pitch 2C
     if (hq < v.h0 || hq >= v.h1 || wq < v.w0 || wq >= v.w1) {
-        *reinterpret_cast<uint4*>(out + off) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(out + off2) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(out + off2 + C) = make_uint4(0, 0, 0, 0);
         return;
     }
     const double cnt = double(H) * double(W);
@@ -122,12 +126,14 @@ __global__ void instnorm_apply_kernel(const float* __restrict__ a, const double*
         *reinterpret_cast<float4*>(rv) = *reinterpret_cast<const float4*>(res_raw + off);
         *reinterpret_cast<float4*>(rv + 4) = *reinterpret_cast<const float4*>(res_raw + off + 4);
     } else if (res_h) {
-        const uint4 rr = *reinterpret_cast<const uint4*>(res_h + off);
-        const __half* rh = reinterpret_cast<const __half*>(&rr);
+        const uint4 rh = *reinterpret_cast<const uint4*>(res_h + off2);
+        const uint4 rl = *reinterpret_cast<const uint4*>(res_h + off2 + C);
+        const __half* hh = reinterpret_cast<const __half*>(&rh);
+        const __half* hl = reinterpret_cast<const __half*>(&rl);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) rv[j] = __half2float(rh[j]);
+        for (int j = 0; j < 8; ++j) rv[j] = __half2float(hh[j]) + __half2float(hl[j]);
     }
-    __align__(16) __half o[8];
+    __align__(16) __half oh[8], ol[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int c = c8 * 8 + j;
@@ -142,9 +148,10 @@ __global__ void instnorm_apply_kernel(const float* __restrict__ a, const double*
         } else if (res_h) {
             y0 = fmaxf(rv[j] + y0, 0.f);
         }
-        o[j] = __float2half_rn(y0);
+        split_half(y0, oh[j], ol[j]);
     }
-    *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(o);
+    *reinterpret_cast<uint4*>(out + off2) = *reinterpret_cast<const uint4*>(oh);
+    *reinterpret_cast<uint4*>(out + off2 + C) = *reinterpret_cast<const uint4*>(ol);
 }
 
 // out = relu(a + b) on valid positions (batch-norm encoder: norms are folded into the conv epilogues)
@@ -188,6 +195,35 @@ __global__ void gather_valid_kernel(const __half* __restrict__ in, Vol2 v, int C
     const int xw = int(pos % W), y = int((pos / W) % H), b = int(pos / (int64_t(W) * H));
     const int64_t off = ((int64_t(b) * v.Hp + y + v.h0) * v.Wp + xw + v.w0) * ld + c8 * 8;
     *reinterpret_cast<uint4*>(out + pos * C + c8 * 8) = *reinterpret_cast<const uint4*>(in + off);
+}
+
+// fnet features (fp32 rows of a border-1 volume, 256 ch) -> the two operand forms of the 3-term split correlation
+//   corr = f1 . f2 ~= f1_hi.f2_hi + f1_lo.f2_hi + f1_hi.f2_lo :  A rows = [hi | lo | hi], B rows = [hi | hi | lo]  (K = 768)
+// so the all-pairs volume is exact to ~2^-22 instead of carrying two fp16 operand roundings.  Dense [n][P8][768].
+__global__ void corr_operands_kernel(const float* __restrict__ f, Vol2 v, int P8, __half* __restrict__ A,
+                                     __half* __restrict__ B) {
+    const int H = v.h1 - v.h0, W = v.w1 - v.w0;
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(v.n) * H * W * 32;       // 8 channels per thread
+    if (idx >= total) return;
+    const int c8 = int(idx % 32);
+    const int64_t pos = idx / 32;
+    const int xw = int(pos % W), y = int((pos / W) % H), b = int(pos / (int64_t(W) * H));
+    const float* src = f + ((int64_t(b) * v.Hp + y + v.h0) * v.Wp + xw + v.w0) * 256 + c8 * 8;
+    float fv[8];
+    *reinterpret_cast<float4*>(fv) = *reinterpret_cast<const float4*>(src);
+    *reinterpret_cast<float4*>(fv + 4) = *reinterpret_cast<const float4*>(src + 4);
+    __align__(16) __half hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) split_half(fv[j], hi[j], lo[j]);
+    const int64_t row = (int64_t(b) * P8 + y * W + xw) * 768 + c8 * 8;
+    const uint4 H4 = *reinterpret_cast<const uint4*>(hi), L4 = *reinterpret_cast<const uint4*>(lo);
+    *reinterpret_cast<uint4*>(A + row) = H4;
+    *reinterpret_cast<uint4*>(A + row + 256) = L4;
+    *reinterpret_cast<uint4*>(A + row + 512) = H4;
+    *reinterpret_cast<uint4*>(B + row) = H4;
+    *reinterpret_cast<uint4*>(B + row + 256) = H4;
+    *reinterpret_cast<uint4*>(B + row + 512) = L4;
 }
 
 // correlation pyramid: level l+1 = avg_pool2d(level l, 2, 2) over the (h2, w2) axes of every query row
@@ -246,15 +282,15 @@ __global__ void corr_lookup_kernel(const float* __restrict__ corr, int ld, const
     if (lvl == 3 && lane < 4) { o[81 + lane] = __float2half_rn(0.f); o[328 + 81 + lane] = __float2half_rn(0.f); }
 }
 
-// Row layout of hx / qx (HX = 520 columns): [h_hi 0..127 | h_lo 128..255 | inp 256..383 | motion 384..511 |
-// flow 512..519 = (fx_hi, fy_hi, fx_lo, fy_lo, 0, 0, 0, 0)].  The recurrent state h, the flow and the correlation
-// features are carried as split-fp16 pairs (weights duplicated over the hi / lo columns): they are the operands the
-// flow is most sensitive to (CPU emulation on compressed video), and they are produced by these
-// elementwise kernels, so the extra precision costs no extra GEMM pass -- only a wider K.
+// Row layout of hx / qx (HX = 648 columns): [h_hi 0..127 | h_lo 128..255 | inp_hi 256..383 | inp_lo 384..511 |
+// motion 512..639 | flow 640..647 = (fx_hi, fy_hi, fx_lo, fy_lo, 0, 0, 0, 0)].  The recurrent state h, the context
+// features, the flow and the correlation features are carried as split-fp16 pairs (weights duplicated over the hi / lo
+// columns): they are the operands the flow is most sensitive to (CPU emulation on compressed video), and
+// they are produced by these elementwise kernels, so the extra precision costs no extra GEMM pass -- only a wider K.
 //
-// context network output (raw conv2 output, 256 ch at border-1 geometry): h = tanh(net) -> h32 / hx[0..255],
-// inp = relu(inp) -> cols 256..383 of both hx and qx (raft.py:141-143)
-__global__ void cnet_split_kernel(const __half* __restrict__ cnet, Vol2 vi, __half* __restrict__ hx,
+// context network output (fp32 conv2 output, 256 ch at border-1 geometry): h = tanh(net) -> h32 / hx[0..255],
+// inp = relu(inp) -> cols 256..511 of both hx and qx (raft.py:141-143)
+__global__ void cnet_split_kernel(const float* __restrict__ cnet, Vol2 vi, __half* __restrict__ hx,
                                   __half* __restrict__ qx, float* __restrict__ h32, Vol2 vo, int ld) {
     const int H = vo.h1 - vo.h0, W = vo.w1 - vo.w0;
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -263,28 +299,30 @@ __global__ void cnet_split_kernel(const __half* __restrict__ cnet, Vol2 vi, __ha
     const int c = int(idx % 256);
     const int64_t pos = idx / 256;
     const int xw = int(pos % W), y = int((pos / W) % H), b = int(pos / (int64_t(W) * H));
-    const float v = __half2float(cnet[((int64_t(b) * vi.Hp + y + vi.h0) * vi.Wp + xw + vi.w0) * 256 + c]);
+    const float v = cnet[((int64_t(b) * vi.Hp + y + vi.h0) * vi.Wp + xw + vi.w0) * 256 + c];
     const int64_t orow = (int64_t(b) * vo.Hp + y + vo.h0) * vo.Wp + xw + vo.w0;
+    __half hi, lo;
     if (c < 128) {
         const float t = tanhf(v);
         h32[orow * 128 + c] = t;                      // fp32 master copy of the recurrent state
-        __half hi, lo;
         split_half(t, hi, lo);
         hx[orow * ld + c] = hi;
         hx[orow * ld + 128 + c] = lo;
     } else {
-        const __half r = __float2half_rn(fmaxf(v, 0.f));
-        hx[orow * ld + 128 + c] = r;                  // cols 256..383
-        qx[orow * ld + 128 + c] = r;
+        split_half(fmaxf(v, 0.f), hi, lo);
+        hx[orow * ld + 128 + c] = hi;                 // cols 256..383
+        hx[orow * ld + 256 + c] = lo;                 // cols 384..511
+        qx[orow * ld + 128 + c] = hi;
+        qx[orow * ld + 256 + c] = lo;
     }
 }
 
-// qx[:, 0:256] = split(r * h) ; qx[:, 384:520] = hx[:, 384:520] (motion features + flow), valid rows.  zr = [z | r].
+// qx[:, 0:256] = split(r * h) ; qx[:, 512:648] = hx[:, 512:648] (motion features + flow), valid rows.  zr = [z | r].
 __global__ void gru_rh_kernel(const __half* __restrict__ hx, const float* __restrict__ h32, const float* __restrict__ zr,
                               __half* __restrict__ qx, Vol2 v, int ld) {
     const int H = v.h1 - v.h0, W = v.w1 - v.w0;
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    const int64_t total = int64_t(v.n) * H * W * 33;       // 16 groups of 8 for r*h + 17 groups for cols 384..519
+    const int64_t total = int64_t(v.n) * H * W * 33;       // 16 groups of 8 for r*h + 17 groups for cols 512..647
     if (idx >= total) return;
     const int gidx = int(idx % 33);
     const int64_t pos = idx / 33;
@@ -302,7 +340,7 @@ __global__ void gru_rh_kernel(const __half* __restrict__ hx, const float* __rest
         *reinterpret_cast<uint4*>(qx + row * ld + gidx * 8) = *reinterpret_cast<const uint4*>(hi);
         *reinterpret_cast<uint4*>(qx + row * ld + 128 + gidx * 8) = *reinterpret_cast<const uint4*>(lo);
     } else {
-        const int c = 384 + (gidx - 16) * 8;
+        const int c = 512 + (gidx - 16) * 8;
         *reinterpret_cast<uint4*>(qx + row * ld + c) = *reinterpret_cast<const uint4*>(hx + row * ld + c);
     }
 }
@@ -339,7 +377,7 @@ __global__ void gru_update_kernel(__half* __restrict__ hx, float* __restrict__ h
 }
 
 // coords1 += delta (fp32, first 2 of 8 GEMM output columns; delta == nullptr initialises coords to the grid);
-// flow = coords1 - coords0 written as a split-fp16 pair to the flow slots of hx / qx (cols 512..515) and flow8 (0..3).
+// flow = coords1 - coords0 written as a split-fp16 pair to the flow slots of hx / qx (cols 640..643) and flow8 (0..3).
 __global__ void coords_update_kernel(float* __restrict__ coords1, const float* __restrict__ delta, __half* __restrict__ hx,
                                      __half* __restrict__ qx, __half* __restrict__ flow8, Vol2 v, int ld) {
     const int H = v.h1 - v.h0, W = v.w1 - v.w0;
@@ -362,8 +400,8 @@ __global__ void coords_update_kernel(float* __restrict__ coords1, const float* _
     split_half(cy - float(y), fyh, fyl);
     const uint2 packed = make_uint2(uint32_t(__half_as_ushort(fxh)) | (uint32_t(__half_as_ushort(fyh)) << 16),
                                     uint32_t(__half_as_ushort(fxl)) | (uint32_t(__half_as_ushort(fyl)) << 16));
-    *reinterpret_cast<uint2*>(hx + row * ld + 512) = packed;       // (fx_hi, fy_hi, fx_lo, fy_lo)
-    *reinterpret_cast<uint2*>(qx + row * ld + 512) = packed;
+    *reinterpret_cast<uint2*>(hx + row * ld + 640) = packed;       // (fx_hi, fy_hi, fx_lo, fy_lo)
+    *reinterpret_cast<uint2*>(qx + row * ld + 640) = packed;
     *reinterpret_cast<uint2*>(flow8 + row * 8) = packed;
 }
 
@@ -413,13 +451,23 @@ __global__ void unpack2d_kernel(const __half* __restrict__ in, Vol2 v, int ld, i
     out[idx] = __half2float(in[((int64_t(b) * v.Hp + y + v.h0) * v.Wp + xw + v.w0) * ld + c0 + c]);
 }
 
+__global__ void unpack2d_f32_kernel(const float* __restrict__ in, Vol2 v, int ld, int c0, int cc, float* __restrict__ out) {
+    const int H = v.h1 - v.h0, W = v.w1 - v.w0;
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(v.n) * cc * H * W;
+    if (idx >= total) return;
+    const int xw = int(idx % W), y = int((idx / W) % H), c = int((idx / (int64_t(W) * H)) % cc);
+    const int b = int(idx / (int64_t(W) * H * cc));
+    out[idx] = in[((int64_t(b) * v.Hp + y + v.h0) * v.Wp + xw + v.w0) * ld + c0 + c];
+}
+
 }  // namespace
 
 #define LAUNCH_CHECK() do { VF_CUDA(cudaGetLastError()); return VF_OK; } while (0)
 
 int raft_input_pack(const void* img, int is_u8, int chw, int n, int Hs, int Ws, int pad_top, int pad_left, int H, int W,
                     __half* out, int Hq, int Wq, cudaStream_t s) {
-    const int64_t total = int64_t(n) * Hq * Wq;
+    const int64_t total = int64_t(n) * Hq * Wq;      // rows of 32 channels (16 hi | 16 lo)
     if (is_u8) raft_input_pack_kernel<uint8_t><<<nb(total, 256), 256, 0, s>>>(static_cast<const uint8_t*>(img), n, Hs, Ws, pad_top, pad_left, H, W, chw, out, Hq, Wq);
     else       raft_input_pack_kernel<float><<<nb(total, 256), 256, 0, s>>>(static_cast<const float*>(img), n, Hs, Ws, pad_top, pad_left, H, W, chw, out, Hq, Wq);
     LAUNCH_CHECK();
@@ -464,7 +512,12 @@ int raft_corr_lookup(const float* corr, int ld, const float* coords, int n, int 
     corr_lookup_kernel<<<nb(warps * 32, 256), 256, 0, s>>>(corr, ld, coords, n, H8, W8, out, vo, out_ld);
     LAUNCH_CHECK();
 }
-int raft_cnet_split(const __half* cnet, const Vol2& vi, __half* hx, __half* qx, float* h32, const Vol2& vo, int ld,
+int raft_corr_operands(const float* f, const Vol2& v, int P8, __half* A, __half* B, cudaStream_t s) {
+    const int64_t total = int64_t(v.n) * (v.h1 - v.h0) * (v.w1 - v.w0) * 32;
+    corr_operands_kernel<<<nb(total, 256), 256, 0, s>>>(f, v, P8, A, B);
+    LAUNCH_CHECK();
+}
+int raft_cnet_split(const float* cnet, const Vol2& vi, __half* hx, __half* qx, float* h32, const Vol2& vo, int ld,
                     cudaStream_t s) {
     const int64_t total = int64_t(vo.n) * (vo.h1 - vo.h0) * (vo.w1 - vo.w0) * 256;
     cnet_split_kernel<<<nb(total, 256), 256, 0, s>>>(cnet, vi, hx, qx, h32, vo, ld);
@@ -490,6 +543,11 @@ int raft_upsample_flow(const float* coords1, const float* mask, const Vol2& v, i
                        int Ho, int Wo, float* flow_up, cudaStream_t s) {
     const int64_t total = int64_t(n) * Ho * Wo;
     upsample_flow_kernel<<<nb(total, 256), 256, 0, s>>>(coords1, mask, v, n, H8, W8, oy, ox, Ho, Wo, flow_up);
+    LAUNCH_CHECK();
+}
+int raft_unpack2d_f32(const float* in, const Vol2& v, int ld, int c0, int cc, float* out, cudaStream_t s) {
+    const int64_t total = int64_t(v.n) * cc * (v.h1 - v.h0) * (v.w1 - v.w0);
+    unpack2d_f32_kernel<<<nb(total, 256), 256, 0, s>>>(in, v, ld, c0, cc, out);
     LAUNCH_CHECK();
 }
 int raft_unpack2d(const __half* in, const Vol2& v, int ld, int c0, int cc, float* out, cudaStream_t s) {

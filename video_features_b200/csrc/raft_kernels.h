@@ -25,7 +25,8 @@ int raft_gather_valid(const __half* in, const Vol2& v, int C, int ld, __half* ou
 int raft_corr_pool(float* corr, int64_t rows, int ld, int off_in, int Hi, int Wi, int off_out, cudaStream_t s);
 int raft_corr_lookup(const float* corr, int ld, const float* coords, int n, int H8, int W8, __half* out, const Vol2& vo,
                      int out_ld, cudaStream_t s);
-int raft_cnet_split(const __half* cnet, const Vol2& vi, __half* hx, __half* qx, float* h32, const Vol2& vo, int ld,
+int raft_corr_operands(const float* f, const Vol2& v, int P8, __half* A, __half* B, cudaStream_t s);
+int raft_cnet_split(const float* cnet, const Vol2& vi, __half* hx, __half* qx, float* h32, const Vol2& vo, int ld,
                     cudaStream_t s);
 int raft_gru_rh(const __half* hx, const float* h32, const float* zr, __half* qx, const Vol2& v, int ld, cudaStream_t s);
 int raft_gru_update(__half* hx, float* h32, const float* zr, const float* q, const Vol2& v, int ld, cudaStream_t s);
@@ -33,6 +34,7 @@ int raft_coords_update(float* coords1, const float* delta, __half* hx, __half* q
                        cudaStream_t s);
 int raft_upsample_flow(const float* coords1, const float* mask, const Vol2& v, int n, int H8, int W8, int oy, int ox,
                        int Ho, int Wo, float* flow_up, cudaStream_t s);
+int raft_unpack2d_f32(const float* in, const Vol2& v, int ld, int c0, int cc, float* out, cudaStream_t s);
 int raft_unpack2d(const __half* in, const Vol2& v, int ld, int c0, int cc, float* out, cudaStream_t s);
 
 }  // namespace vf
