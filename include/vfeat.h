@@ -66,6 +66,11 @@ int vf_clip_normalize_u8(const uint8_t* src, int n, int src_h, int src_w, float*
  * D: fp16 or fp32 (out_f32, row pitch ldd elements, 16-byte aligned rows), bias/scale: fp32 [N] or NULL. */
 int vf_gemm_f16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, void* D, int ldd, int out_f32,
                 const float* bias, const float* scale, int act, void* stream);
+/* Same GEMM with the result written as a split-fp16 pair: D[m][n] = fp16(v) and D[m][split_off + n] = fp16(v - fp16(v))
+ * (split_off >= N, multiple of 8, ldd >= split_off + N).  RAFT's GEMM -> GEMM activations are carried this way: the
+ * consumer's weights are duplicated over both halves, which restores ~22 mantissa bits on the activation operand. */
+int vf_gemm_f16_split(const void* A, int lda, const void* B, int ldb, int M, int N, int K, void* D, int ldd, int split_off,
+                      const float* bias, const float* scale, int act, void* stream);
 
 /* Roofline instrumentation (bench.py): while enabled on the calling thread, every tcgen05 GEMM launch of any handle
  * is bracketed by CUDA events on its stream.  _read synchronises the device and returns the summed device time (ms),

@@ -94,6 +94,32 @@ def test_gemm_partial_n_tile_is_race_free(cuda_device):
         assert rel_l2(out.float(), ref2) < 1.5e-3
 
 
+@pytest.mark.parametrize("M,N,K,act", [(700, 256, 320, 2), (1000, 96, 192, 0), (300, 192, 136, 2), (5000, 128, 648, 2)])
+def test_gemm_split_output_is_a_hi_lo_pair(cuda_device, M, N, K, act):
+    """vf_gemm_f16_split: hi half bit-equal to the plain fp16 output, lo half == fp16(v - hi) of the fp32 output,
+    columns between / right of the two halves untouched (N = 96 / 192: the hi store's 64-wide box overlaps the lo
+    half's columns and must be clipped at N, not at the row pitch)."""
+    from video_features_b200 import _lib
+    from video_features_b200.ops import _stream
+    g = torch.Generator(device="cpu").manual_seed(M + N)
+    a = (torch.randn(M, K, generator=g) * 0.5).half().to(cuda_device)
+    b = (torch.randn(N, K, generator=g) * 0.1).half().to(cuda_device)
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    plain16 = torch.ops.vfeat.gemm_f16(a, b, bias, None, act, False)
+    plain32 = torch.ops.vfeat.gemm_f16(a, b, bias, None, act, True)
+    off, ld = N + 8, 2 * N + 24
+    out = torch.full((M, ld), 7.0, device=cuda_device, dtype=torch.float16)
+    with torch.cuda.device(cuda_device):
+        _lib.check(_lib.lib().vf_gemm_f16_split(a.data_ptr(), K, b.data_ptr(), K, M, N, K, out.data_ptr(), ld, off,
+                                                bias.data_ptr(), None, act, _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out[:, :N], plain16)
+    lo = (plain32 - plain16.float()).half()
+    assert torch.equal(out[:, off:off + N], lo)
+    assert bool((out[:, N:off] == 7.0).all()) and bool((out[:, off + N:] == 7.0).all())
+    assert rel_l2(out[:, :N].float() + out[:, off:off + N].float(), plain32) < 1e-6
+
+
 def test_gemm_rejects_bad_arguments(cuda_device):
     from video_features_b200._lib import VfError
     a = torch.zeros(16, 60, dtype=torch.float16, device=cuda_device)   # K not a multiple of 8

@@ -97,8 +97,8 @@ __device__ __forceinline__ void epi_math32(float* v, const GemmEpi& ep, int n, i
 template <int BN, int STAGES, int NSPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ CUtensorMap tmO, const GemmEpi ep, const int M, const int N,
-                     const __grid_constant__ ConvGeom cg) {
+                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2, const GemmEpi ep,
+                     const int M, const int N, const __grid_constant__ ConvGeom cg) {
     using Cfg = GemmCfg<BN, STAGES, NSPLIT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -125,6 +125,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmO);
+        tma_prefetch_desc(&tmO2);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -206,6 +207,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         uint8_t* bufs = stg + grp * Cfg::EPI_BUFS * SLICE_BYTES;
         const bool agent = (q == 0) && (lane == 0);
         const int slice_cols = ep.out_f32 ? 32 : 64;
+        const int nsp = (!ep.out_f32 && ep.split_off > 0) ? 2 : 1;
         const uint32_t sw = uint32_t(row & 7);
         int acc = 0, it = 0;
         uint32_t acc_phase = 0;
@@ -224,7 +226,8 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 keep = (w >= cg.w0) && (w < cg.w1) && (hh >= cg.h0) && (hh < cg.h1) && (tt >= cg.t0) && (tt < cg.t1);
             }
 #pragma unroll 1
-            for (int c = grp * slice_cols; c < BN; c += 2 * slice_cols) {
+            for (int c = grp * slice_cols; c < BN; c += 2 * slice_cols)
+            for (int sp = 0; sp < nsp; ++sp) {     // split output: the slice is produced twice, hi then lo
                 uint8_t* buf = bufs + (Cfg::EPI_BUFS == 2 ? (it & 1) : 0) * SLICE_BYTES;
                 uint8_t* myrow = buf + row * 128;
                 // the TMA store that last used this buffer must have finished reading it
@@ -261,6 +264,10 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = 0.f;
                         }
+                        if (sp) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] -= __half2float(__float2half_rn(v[j]));
+                        }
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             *reinterpret_cast<uint4*>(myrow + ((uint32_t(hh * 4 + j) ^ sw) << 4)) =
@@ -274,7 +281,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     // rows >= M and columns >= N are clipped by the TMA unit.  A group is committed for EVERY slice,
                     // also for the (empty) ones right of N: wait_group.read<1> above counts groups, and skipping a
                     // commit would let a buffer be rewritten while its previous store is still reading it.
-                    if (n < N) tma_store_2d(&tmO, buf, n, m0);
+                    if (n < N) tma_store_2d(sp ? &tmO2 : &tmO, buf, n, m0);
                     bulk_commit();
                 }
                 ++it;
@@ -312,7 +319,8 @@ EncodeTiledFn get_encode_tiled() {
 }
 
 template <int BN, int STAGES, int NSPLIT>
-int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmEpi& ep, int M,
+int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmO2,
+                     const GemmEpi& ep, int M,
                      int N, const ConvGeom& cg, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, STAGES, NSPLIT>;
     static bool attr_set[64] = {false};
@@ -326,7 +334,7 @@ int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
     const int pairs = device_sm_count() / 2;
     const int grid = 2 * (tiles < pairs ? tiles : pairs);
-    gemm_f16_pair_kernel<BN, STAGES, NSPLIT><<<grid, 384, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, ep, M, N, cg);
+    gemm_f16_pair_kernel<BN, STAGES, NSPLIT><<<grid, 384, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, tmO2, ep, M, N, cg);
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
@@ -373,16 +381,17 @@ struct GemmProf {
 };
 static thread_local GemmProf g_prof;
 
-static int run_gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, int bn, const GemmEpi& ep,
+static int run_gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmO2,
+                           int bn, const GemmEpi& ep,
                            int M, int N, const ConvGeom& cg, cudaStream_t stream) {
     if (cg.nsplit == 2) {
-        if (bn == 256) return launch_gemm_pair<256, 4, 2>(tmA, tmB, tmO, ep, M, N, cg, stream);
-        if (bn == 128) return launch_gemm_pair<128, 6, 2>(tmA, tmB, tmO, ep, M, N, cg, stream);
-        return launch_gemm_pair<64, 8, 2>(tmA, tmB, tmO, ep, M, N, cg, stream);
+        if (bn == 256) return launch_gemm_pair<256, 4, 2>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+        if (bn == 128) return launch_gemm_pair<128, 6, 2>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+        return launch_gemm_pair<64, 8, 2>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
     }
-    if (bn == 256) return launch_gemm_pair<256, 5, 1>(tmA, tmB, tmO, ep, M, N, cg, stream);
-    if (bn == 128) return launch_gemm_pair<128, 6, 1>(tmA, tmB, tmO, ep, M, N, cg, stream);
-    return launch_gemm_pair<64, 8, 1>(tmA, tmB, tmO, ep, M, N, cg, stream);
+    if (bn == 256) return launch_gemm_pair<256, 5, 1>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+    if (bn == 128) return launch_gemm_pair<128, 6, 1>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+    return launch_gemm_pair<64, 8, 1>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
 }
 
 static int run_gemm(const CUtensorMap& tmA, const __half* B, int ldb, int64_t Ktot, int M, int N, const ConvGeom& cg,
@@ -391,11 +400,18 @@ static int run_gemm(const CUtensorMap& tmA, const __half* B, int ldb, int64_t Kt
     if (N % 8) return fail(VF_ERR_INVALID, "gemm: N=%d must be a multiple of 8", N);
     if (ep.out_f32 ? (ep.ldo % 4) : (ep.ldo % 8)) return fail(VF_ERR_INVALID, "gemm: ldo breaks 16-byte rows");
     const int bn = (N > 128) ? 256 : (N > 64) ? 128 : 64;     // pair-tile width; the B box is half of it
-    CUtensorMap tmB, tmO;
+    CUtensorMap tmB, tmO, tmO2;
     VF_TRY(make_tmap_2d(&tmB, B, 2, uint64_t(N), uint64_t(Ktot), uint64_t(ldb) * 2, uint32_t(bn / 2), BK));
     if (ep.out_f32) VF_TRY(make_tmap_2d(&tmO, ep.out, 4, uint64_t(M), uint64_t(N), uint64_t(ep.ldo) * 4, BM, 32));
     else            VF_TRY(make_tmap_2d(&tmO, ep.out, 2, uint64_t(M), uint64_t(N), uint64_t(ep.ldo) * 2, BM, 64));
-    if (!g_prof.on) return run_gemm_launch(tmA, tmB, tmO, bn, ep, M, N, cg, stream);
+    tmO2 = tmO;
+    if (ep.split_off) {     // second view of the output rows: the lo halves, both views clip at N columns
+        if (ep.out_f32 || ep.split_off < N || ep.split_off % 8)
+            return fail(VF_ERR_INVALID, "gemm: split output needs fp16 out and split_off >= N, multiple of 8");
+        VF_TRY(make_tmap_2d(&tmO2, static_cast<__half*>(ep.out) + ep.split_off, 2, uint64_t(M), uint64_t(N),
+                            uint64_t(ep.ldo) * 2, BM, 64));
+    }
+    if (!g_prof.on) return run_gemm_launch(tmA, tmB, tmO, tmO2, bn, ep, M, N, cg, stream);
     if (g_prof.used + 2 > g_prof.ev.size())
         for (int i = 0; i < 2; ++i) {
             cudaEvent_t e;
@@ -403,7 +419,7 @@ static int run_gemm(const CUtensorMap& tmA, const __half* B, int ldb, int64_t Kt
             g_prof.ev.push_back(e);
         }
     VF_CUDA(cudaEventRecord(g_prof.ev[g_prof.used], stream));
-    const int st = run_gemm_launch(tmA, tmB, tmO, bn, ep, M, N, cg, stream);
+    const int st = run_gemm_launch(tmA, tmB, tmO, tmO2, bn, ep, M, N, cg, stream);
     VF_CUDA(cudaEventRecord(g_prof.ev[g_prof.used + 1], stream));
     g_prof.used += 2;
     g_prof.flops += 2.0 * double(M) * double(N) * double(Ktot);

@@ -245,4 +245,15 @@ int vf_gemm_f16(const void* A, int lda, const void* B, int ldb, int M, int N, in
                     static_cast<cudaStream_t>(stream));
 }
 
+int vf_gemm_f16_split(const void* A, int lda, const void* B, int ldb, int M, int N, int K, void* D, int ldd, int split_off,
+                      const float* bias, const float* scale, int act, void* stream) {
+    if (!A || !B || !D) return fail(VF_ERR_INVALID, "gemm: null buffer");
+    if (split_off < N || ldd < split_off + N) return fail(VF_ERR_INVALID, "gemm: split output needs ldd >= split_off + N, split_off >= N");
+    GemmEpi ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.out = D; ep.ldo = ldd; ep.out_f32 = 0; ep.bias = bias; ep.scale = scale; ep.act = act; ep.split_off = split_off;
+    return gemm_f16(static_cast<const __half*>(A), lda, static_cast<const __half*>(B), ldb, M, N, K, ep,
+                    static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -41,6 +41,8 @@ struct GemmEpi {
     int ldo;
     int out_f32;            // 0: fp16 out, 1: fp32 out
     int act;                // VF_ACT_*
+    int split_off;          // fp16 out only: > 0 writes the result as a split-fp16 pair, hi at column n and
+                            // lo = fp16(v - hi) at column split_off + n of the same row (0: plain fp16)
 };
 int gemm_f16(const __half* A, int lda, const __half* B, int ldb, int M, int N, int K, const GemmEpi& ep,
              cudaStream_t stream);

@@ -34,11 +34,12 @@ struct ConvW {       // a convolution prepared for conv_gemm_f16
     int n_out = 0;          // GEMM N (padded to a multiple of 8)
     int ntaps = 0, k_per_tap = 0;
     std::vector<int> dh, dw0;   // per tap: row offset (in kernel rows) and the column shift of its first element
+    int nsplit = 1;             // 2: w = [hi (ntaps*k_per_tap) | lo (same)] along K (ConvGeom::nsplit)
     __half* w = nullptr;
     float *scale = nullptr, *bias = nullptr;
 };
 
-static const int HX = 648;   // [h_hi 128 | h_lo 128 | inp_hi 128 | inp_lo 128 | motion-out 126 + 2 pad | flow (hi,hi,lo,lo) + 4 pad]
+static const int HX = RAFT_HX;   // hx / qx row layout: raft_kernels.h
 static const int CF = 656;   // [324 correlation features hi + 4 pad | 324 lo + 4 pad]
 
 }  // namespace vf
@@ -47,6 +48,7 @@ using namespace vf;
 
 struct vf_raft {
     int device = 0, max_frames = 0, max_h = 0, max_w = 0;
+    int wsplit = 2;             // weights as hi+lo fp16 pairs (VF_RAFT_FAST=1: single fp16 weights, outside the parity bar)
     std::vector<void*> allocs;
     // encoders: [0] = fnet (instance norm), [1] = cnet (batch norm folded)
     struct Enc {
@@ -103,8 +105,11 @@ struct TensorTable {
 static int upload_conv(vf_raft* h, ConvW& cw, const float* w, const float* b, int co, int ci, int kh, int kw, int n_out,
                        int Ktot, const std::function<int(int, int, int)>& col, const float* bn_scale,
                        const float* bn_shift, float extra_scale,
-                       const std::function<int(int, int, int)>& col_lo = nullptr) {
-    std::vector<__half> B(size_t(n_out) * Ktot, __float2half_rn(0.f));
+                       const std::function<int(int, int, int)>& col_lo = nullptr, int nsplit = -1) {
+    if (nsplit < 0) nsplit = h->wsplit;
+    cw.nsplit = nsplit;
+    const size_t Kall = size_t(Ktot) * nsplit;
+    std::vector<__half> B(size_t(n_out) * Kall, __float2half_rn(0.f));
     for (int o = 0; o < co; ++o)
         for (int c = 0; c < ci; ++c)
             for (int a = 0; a < kh; ++a)
@@ -112,12 +117,18 @@ static int upload_conv(vf_raft* h, ConvW& cw, const float* w, const float* b, in
                     const int k = col(a, d, c);
                     if (k < 0) continue;
                     if (k >= Ktot) return fail(VF_ERR_INVALID, "raft_create: filter column out of range");
-                    const __half wv = __float2half_rn(w[((size_t(o) * ci + c) * kh + a) * kw + d]);
-                    B[size_t(o) * Ktot + k] = wv;
+                    const float wf = w[((size_t(o) * ci + c) * kh + a) * kw + d];
+                    const __half wv = __float2half_rn(wf);
+                    const __half wl = __float2half_rn(wf - __half2float(wv));
+                    B[size_t(o) * Kall + k] = wv;
+                    if (nsplit == 2) B[size_t(o) * Kall + Ktot + k] = wl;
                     if (col_lo) {
                         const int k2 = col_lo(a, d, c);
                         if (k2 >= Ktot) return fail(VF_ERR_INVALID, "raft_create: filter column out of range");
-                        if (k2 >= 0) B[size_t(o) * Ktot + k2] = wv;
+                        if (k2 >= 0) {
+                            B[size_t(o) * Kall + k2] = wv;
+                            if (nsplit == 2) B[size_t(o) * Kall + Ktot + k2] = wl;
+                        }
                     }
                 }
     std::vector<float> sc(n_out, 0.f), bi(n_out, 0.f);
@@ -154,7 +165,7 @@ static bool bn_fold(const TensorTable& T, const std::string& p, int c, BnFold* f
 // taps = kernel rows, each a run of kw*pitch elements starting (kw/2) positions to the left.
 static int prep_same_conv(vf_raft* h, ConvW& cw, const TensorTable& T, const std::string& name, int co, int ci, int kh,
                           int kw, int pitch, const std::function<int(int)>& chan, int n_out, const BnFold* bn,
-                          float extra_scale = 1.f, const std::function<int(int)>& chan_lo = nullptr) {
+                          float extra_scale = 1.f, const std::function<int(int)>& chan_lo = nullptr, int nsplit = -1) {
     const float* w = T.get(name + ".weight", int64_t(co) * ci * kh * kw);
     const float* b = T.get(name + ".bias", co);
     if (!w || !b) return fail(VF_ERR_INVALID, "raft_create: missing or mis-shaped tensor '%s'", name.c_str());
@@ -168,12 +179,12 @@ static int prep_same_conv(vf_raft* h, ConvW& cw, const TensorTable& T, const std
                        chan_lo ? std::function<int(int, int, int)>([=](int a, int d, int c) {
                            const int k = chan_lo(c);
                            return k < 0 ? -1 : a * kpt + d * pitch + k;
-                       }) : nullptr);
+                       }) : nullptr, nsplit);
 }
 // same, but every (kh, kw) position is its own tap reading `ci` channels at column offset 0 of rows with a wider pitch
 // (dup: the operand row holds [x_hi (ci) | x_lo (ci)], the weight is written to both halves)
 static int prep_unmerged_conv(vf_raft* h, ConvW& cw, const TensorTable& T, const std::string& name, int co, int ci, int kh,
-                              int kw, int n_out, bool dup, float extra_scale = 1.f) {
+                              int kw, int n_out, bool dup, float extra_scale = 1.f, int nsplit = -1) {
     const float* w = T.get(name + ".weight", int64_t(co) * ci * kh * kw);
     const float* b = T.get(name + ".bias", co);
     if (!w || !b) return fail(VF_ERR_INVALID, "raft_create: missing or mis-shaped tensor '%s'", name.c_str());
@@ -185,7 +196,7 @@ static int prep_unmerged_conv(vf_raft* h, ConvW& cw, const TensorTable& T, const
     return upload_conv(h, cw, w, b, co, ci, kh, kw, n_out, kh * kw * kpt,
                        [=](int a, int d, int c) { return (a * kw + d) * kpt + c; }, nullptr, nullptr, extra_scale,
                        dup ? std::function<int(int, int, int)>([=](int a, int d, int c) { return (a * kw + d) * kpt + ci + c; })
-                           : nullptr);
+                           : nullptr, nsplit);
 }
 // stride-2 k x k conv (pad k/2) on the phase repack of its input: phase volume row q holds x[2(q-B)+p] with B =
 // border-before (2 for k=7, 1 for k=3); filter index = 2a + p - 1 for tap a (k=7: a in 0..3, k=3: a in 0..1).
@@ -211,24 +222,23 @@ static int prep_stride2_conv(vf_raft* h, ConvW& cw, const TensorTable& T, const 
                        lo_off >= 0 ? std::function<int(int, int, int)>([=](int kh, int kw, int c) { return col(kh, kw, c) + lo_off; })
                                    : nullptr);
 }
-// 1x1 stride-2 downsample: phase (0,0) of the repacked row = its first channels ([hi ci | lo ci] when split)
+// 1x1 stride-2 downsample: phase (0,0) of the repacked row = its first 2*ci channels [hi ci | lo ci]
 static int prep_down_conv(vf_raft* h, ConvW& cw, const TensorTable& T, const std::string& name, int co, int ci, int n_out,
-                          bool split, const BnFold* bn) {
+                          const BnFold* bn) {
     const float* w = T.get(name + ".weight", int64_t(co) * ci);
     const float* b = T.get(name + ".bias", co);
     if (!w || !b) return fail(VF_ERR_INVALID, "raft_create: missing or mis-shaped tensor '%s'", name.c_str());
-    cw.ntaps = 1; cw.k_per_tap = split ? 2 * ci : ci;
+    cw.ntaps = 1; cw.k_per_tap = 2 * ci;
     cw.dh = {0}; cw.dw0 = {0};
     return upload_conv(h, cw, w, b, co, ci, 1, 1, n_out, cw.k_per_tap, [=](int, int, int c) { return c; },
                        bn ? bn->scale.data() : nullptr, bn ? bn->shift.data() : nullptr, 1.f,
-                       split ? std::function<int(int, int, int)>([=](int, int, int c) { return ci + c; }) : nullptr);
+                       [=](int, int, int c) { return ci + c; });
 }
 
-// `split`: the encoder's activations are split-fp16 pairs, rows = [hi C | lo C] (the instance-norm encoder: all of
-// its conv inputs are written by elementwise kernels); otherwise single fp16 rows of C channels (batch-norm encoder:
-// conv inputs come from GEMM epilogues).  The stem reads the split input phase volume in both cases.
+// Both encoders keep their activations as split-fp16 pairs, rows = [hi C | lo C]: the instance-norm encoder's are
+// written by the normalisation kernels (fp32 conv outputs), the batch-norm encoder's by the GEMM epilogue's split
+// output (norms folded into scale / bias).  The stem reads the split input phase volume.
 static int prep_encoder(vf_raft* h, vf_raft::Enc& e, const TensorTable& T, const std::string& p, bool batch, int out_dim) {
-    const bool split = !batch;
     auto ident = [](int c) { return c; };
     BnFold f; const BnFold* bn = nullptr;
     auto fold = [&](const std::string& name, int c) -> int {
@@ -237,8 +247,7 @@ static int prep_encoder(vf_raft* h, vf_raft::Enc& e, const TensorTable& T, const
         bn = &f; return VF_OK;
     };
     auto same3 = [&](ConvW& cw, const std::string& name, int co, int ci) -> int {
-        if (split) return prep_same_conv(h, cw, T, name, co, ci, 3, 3, 2 * ci, ident, co, bn, 1.f, [=](int c) { return ci + c; });
-        return prep_same_conv(h, cw, T, name, co, ci, 3, 3, ci, ident, co, bn);
+        return prep_same_conv(h, cw, T, name, co, ci, 3, 3, 2 * ci, ident, co, bn, 1.f, [=](int c) { return ci + c; });
     };
     VF_TRY(fold(p + ".norm1", 64));
     // stem: input phase rows = [16 hi | 16 lo], 4 (3 used) channels per phase
@@ -256,11 +265,10 @@ static int prep_encoder(vf_raft* h, vf_raft::Enc& e, const TensorTable& T, const
         ConvW& c1 = L == 0 ? e.l2c1 : e.l3c1;
         ConvW& dn = L == 0 ? e.l2down : e.l3down;
         ConvW* rest = L == 0 ? e.l2 : e.l3;
-        const int crow = split ? 2 * ci : ci;          // channels per phase block of the repacked row
         VF_TRY(fold(lp + ".0.norm1", co));
-        VF_TRY(prep_stride2_conv(h, c1, T, lp + ".0.conv1", co, ci, 3, 4 * crow, crow, split ? ci : -1, co, bn));
+        VF_TRY(prep_stride2_conv(h, c1, T, lp + ".0.conv1", co, ci, 3, 8 * ci, 2 * ci, ci, co, bn));
         VF_TRY(fold(lp + ".0.downsample.1", co));
-        VF_TRY(prep_down_conv(h, dn, T, lp + ".0.downsample.0", co, ci, co, split, bn));
+        VF_TRY(prep_down_conv(h, dn, T, lp + ".0.downsample.0", co, ci, co, bn));
         VF_TRY(fold(lp + ".0.norm2", co));
         VF_TRY(same3(rest[0], lp + ".0.conv2", co, co));
         VF_TRY(fold(lp + ".1.norm1", co));
@@ -268,29 +276,30 @@ static int prep_encoder(vf_raft* h, vf_raft::Enc& e, const TensorTable& T, const
         VF_TRY(fold(lp + ".1.norm2", co));
         VF_TRY(same3(rest[2], lp + ".1.conv2", co, co));
     }
-    if (split) VF_TRY(prep_same_conv(h, e.conv2, T, p + ".conv2", out_dim, 128, 1, 1, 256, ident, out_dim, nullptr, 1.f,
-                                     [](int c) { return 128 + c; }));
-    else       VF_TRY(prep_same_conv(h, e.conv2, T, p + ".conv2", out_dim, 128, 1, 1, 128, ident, out_dim, nullptr));
+    VF_TRY(prep_same_conv(h, e.conv2, T, p + ".conv2", out_dim, 128, 1, 1, 256, ident, out_dim, nullptr, 1.f,
+                          [](int c) { return 128 + c; }));
     return VF_OK;
 }
 
-static int run_conv(vf_raft* h, const ConvW& cw, const __half* X, int pitch, const Vol2& v, void* out, int ldo, int out_f32,
-                    int act, cudaStream_t s) {
+// out_mode: 0 fp16, 1 fp32, 2 split-fp16 pair (hi at column n, lo at column split_off + n of the same rows)
+static int run_conv(vf_raft* h, const ConvW& cw, const __half* X, int pitch, const Vol2& v, void* out, int ldo, int out_mode,
+                    int act, cudaStream_t s, int split_off = 0) {
     ConvGeom g;
     memset(&g, 0, sizeof(g));
-    g.ntaps = cw.ntaps; g.k_per_tap = cw.k_per_tap; g.nsplit = 1;
+    g.ntaps = cw.ntaps; g.k_per_tap = cw.k_per_tap; g.nsplit = cw.nsplit;
     for (int j = 0; j < cw.ntaps; ++j) g.tap_off[j] = cw.dh[j] * v.Wp + cw.dw0[j];
     g.mask = 1;
     g.Tp = 1; g.Hp = v.Hp; g.Wp = v.Wp; g.t0 = 0; g.t1 = 1; g.h0 = v.h0; g.h1 = v.h1; g.w0 = v.w0; g.w1 = v.w1;
     GemmEpi ep;
     memset(&ep, 0, sizeof(ep));
-    ep.out = out; ep.ldo = ldo; ep.out_f32 = out_f32; ep.bias = cw.bias; ep.scale = cw.scale; ep.act = act;
+    ep.out = out; ep.ldo = ldo; ep.out_f32 = out_mode == 1; ep.bias = cw.bias; ep.scale = cw.scale; ep.act = act;
+    ep.split_off = out_mode == 2 ? split_off : 0;
     h->launches += 1;
     return conv_gemm_f16(X, pitch, v.rows(), cw.w, cw.n_out, g, ep, s);
 }
 
 // BasicEncoder.forward on m frames whose (split) stem phase volume is in h->s0; the 256-channel output is written in
-// fp32 to `out` (border-1 /8 geometry).  inst: instance-norm encoder with split-fp16 activations (rows of 2C channels).
+// fp32 to `out` (border-1 /8 geometry).  Activation rows are split-fp16 pairs of 2C channels in both encoders.
 static int run_encoder(vf_raft* h, const vf_raft::Enc& e, bool inst, int m, int H, int W, float* out, int out_dim,
                        cudaStream_t s) {
     const Vol2 g2{m, H / 2 + 3, W / 2 + 3, 2, 2 + H / 2, 2, 2 + W / 2};
@@ -298,7 +307,6 @@ static int run_encoder(vf_raft* h, const vf_raft::Enc& e, bool inst, int m, int 
     const Vol2 g8{m, H / 8 + 2, W / 8 + 2, 1, 1 + H / 8, 1, 1 + W / 8};
     __half *x = h->bufA, *y = h->bufB, *r = h->bufC, *r2 = h->bufD, *ph = h->bufE;
     float *rf = h->rawA, *rf2 = h->rawB;
-    const int mul = inst ? 2 : 1;          // row pitch multiplier of the activation buffers
     auto norm_relu = [&](const float* raw, __half* dst, const Vol2& v, int C) -> int {   // dst = split(relu(IN(raw)))
         VF_TRY(raft_instnorm_stats(raw, v, C, h->st_a, s));
         h->launches += 2;
@@ -306,7 +314,7 @@ static int run_encoder(vf_raft* h, const vf_raft::Enc& e, bool inst, int m, int 
     };
     // conv1 + norm1 + relu
     if (inst) { VF_TRY(run_conv(h, e.conv1, h->s0, 32, g2, rf, 64, 1, VF_ACT_NONE, s)); VF_TRY(norm_relu(rf, x, g2, 64)); }
-    else      { VF_TRY(run_conv(h, e.conv1, h->s0, 32, g2, x, 64, 0, VF_ACT_RELU, s)); }
+    else      { VF_TRY(run_conv(h, e.conv1, h->s0, 32, g2, x, 128, 2, VF_ACT_RELU, s, 64)); }
     // a stride-1 residual block at geometry v with C channels: x <- relu(x + relu(norm2(conv2(relu(norm1(conv1(x)))))))
     auto res_block = [&](const ConvW& c1, const ConvW& c2, const Vol2& v, int C) -> int {
         if (inst) {
@@ -317,8 +325,8 @@ static int run_encoder(vf_raft* h, const vf_raft::Enc& e, bool inst, int m, int 
             VF_TRY(raft_instnorm_apply(rf, h->st_a, x, nullptr, nullptr, x, v, C, s));
             h->launches += 2;
         } else {
-            VF_TRY(run_conv(h, c1, x, C, v, y, C, 0, VF_ACT_RELU, s));
-            VF_TRY(run_conv(h, c2, y, C, v, r, C, 0, VF_ACT_RELU, s));
+            VF_TRY(run_conv(h, c1, x, 2 * C, v, y, 2 * C, 2, VF_ACT_RELU, s, C));
+            VF_TRY(run_conv(h, c2, y, 2 * C, v, r, 2 * C, 2, VF_ACT_RELU, s, C));
             VF_TRY(raft_add_relu(x, r, x, v, C, s));
             h->launches += 1;
         }
@@ -329,7 +337,7 @@ static int run_encoder(vf_raft* h, const vf_raft::Enc& e, bool inst, int m, int 
     // a stride-2 residual block: vin (Cin) -> vout (Cout)
     auto down_block = [&](const ConvW& c1, const ConvW& dn, const ConvW& c2, const Vol2& vin, const Vol2& vout, int Cin,
                           int Cout) -> int {
-        VF_TRY(raft_phase_repack(x, vin, mul * Cin, ph, vout, s));
+        VF_TRY(raft_phase_repack(x, vin, 2 * Cin, ph, vout, s));
         h->launches += 1;
         if (inst) {
             VF_TRY(run_conv(h, c1, ph, 8 * Cin, vout, rf, Cout, 1, VF_ACT_NONE, s));
@@ -341,9 +349,9 @@ static int run_encoder(vf_raft* h, const vf_raft::Enc& e, bool inst, int m, int 
             VF_TRY(raft_instnorm_apply(rf, h->st_a, nullptr, rf2, h->st_b, x, vout, Cout, s));   // relu(IN(down) + relu(IN(c2)))
             h->launches += 3;
         } else {
-            VF_TRY(run_conv(h, c1, ph, 4 * Cin, vout, y, Cout, 0, VF_ACT_RELU, s));
-            VF_TRY(run_conv(h, c2, y, Cout, vout, r, Cout, 0, VF_ACT_RELU, s));
-            VF_TRY(run_conv(h, dn, ph, 4 * Cin, vout, r2, Cout, 0, VF_ACT_NONE, s));    // norm3 folded, no relu
+            VF_TRY(run_conv(h, c1, ph, 8 * Cin, vout, y, 2 * Cout, 2, VF_ACT_RELU, s, Cout));
+            VF_TRY(run_conv(h, c2, y, 2 * Cout, vout, r, 2 * Cout, 2, VF_ACT_RELU, s, Cout));
+            VF_TRY(run_conv(h, dn, ph, 8 * Cin, vout, r2, 2 * Cout, 2, VF_ACT_NONE, s, Cout));    // norm3 folded, no relu
             VF_TRY(raft_add_relu(r2, r, x, vout, Cout, s));
             h->launches += 1;
         }
@@ -353,7 +361,7 @@ static int run_encoder(vf_raft* h, const vf_raft::Enc& e, bool inst, int m, int 
     VF_TRY(res_block(e.l2[1], e.l2[2], g4, 96));
     VF_TRY(down_block(e.l3c1, e.l3down, e.l3[0], g4, g8, 96, 128));
     VF_TRY(res_block(e.l3[1], e.l3[2], g8, 128));
-    VF_TRY(run_conv(h, e.conv2, x, mul * 128, g8, out, out_dim, 1, VF_ACT_NONE, s));      // fp32 output
+    VF_TRY(run_conv(h, e.conv2, x, 256, g8, out, out_dim, 1, VF_ACT_NONE, s));      // fp32 output
     return VF_OK;
 }
 
@@ -376,22 +384,29 @@ int vf_raft_create(vf_raft_t** out, const vf_named_tensor* tensors, int n_tensor
     h->max_h = (max_h + 7) / 8 * 8; h->max_w = (max_w + 7) / 8 * 8;
     const TensorTable T{tensors, n_tensors};
     auto ident = [](int c) { return c; };
+    {
+        const char* e = getenv("VF_RAFT_FAST");
+        h->wsplit = (e && e[0] == '1') ? 1 : 2;
+    }
     auto body = [&]() -> int {
         VF_TRY(prep_encoder(h, h->enc[0], T, "fnet", false, 256));
         VF_TRY(prep_encoder(h, h->enc[1], T, "cnet", true, 256));
         const std::string u = "update_block.";
         VF_TRY(prep_same_conv(h, h->convc1, T, u + "encoder.convc1", 256, 324, 1, 1, CF, ident, 256, nullptr, 1.f,
                               [](int c) { return 328 + c; }));                       // lo half of the correlation features
-        VF_TRY(prep_same_conv(h, h->convc2, T, u + "encoder.convc2", 192, 256, 3, 3, 256, ident, 192, nullptr));
+        auto lo256 = [](int c) { return 256 + c; };
+        VF_TRY(prep_same_conv(h, h->convc2, T, u + "encoder.convc2", 192, 256, 3, 3, 512, ident, 192, nullptr, 1.f, lo256));
         VF_TRY(prep_same_conv(h, h->convf1, T, u + "encoder.convf1", 128, 2, 7, 7, 8, ident, 128, nullptr, 1.f,
                               [](int c) { return 2 + c; }));                         // flow8 = (fx_hi, fy_hi, fx_lo, fy_lo, ...)
-        VF_TRY(prep_same_conv(h, h->convf2, T, u + "encoder.convf2", 64, 128, 3, 3, 128, ident, 64, nullptr));
-        VF_TRY(prep_same_conv(h, h->convm, T, u + "encoder.conv", 126, 256, 3, 3, 256, ident, 128, nullptr));
+        VF_TRY(prep_same_conv(h, h->convf2, T, u + "encoder.convf2", 64, 128, 3, 3, 256, ident, 64, nullptr, 1.f,
+                              [](int c) { return 128 + c; }));
+        // reads c2f rows = [cor 192 | flo 64 | cor_lo 192 | flo_lo 64]
+        VF_TRY(prep_same_conv(h, h->convm, T, u + "encoder.conv", 126, 256, 3, 3, 512, ident, 128, nullptr, 1.f, lo256));
         // GRU gates read hx / qx rows (layout in raft_kernels.cu): conv input channel c -> column
         //   h (c < 128) -> c [+ lo at 128 + c], inp (128..255) -> 128 + c [+ lo at 256 + c],
-        //   motion-out (256..381) -> 256 + c, flow (382, 383) -> 640 + (c - 382) [+ lo at 642 + (c - 382)]
-        auto gmap = [](int c) { return c < 128 ? c : (c < 256 ? 128 + c : (c < 382 ? 256 + c : 640 + (c - 382))); };
-        auto gmap_lo = [](int c) { return c < 128 ? 128 + c : (c < 256 ? 256 + c : (c < 382 ? -1 : 642 + (c - 382))); };
+        //   motion-out (256..381) -> 256 + c [+ lo at 384 + c], flow (382, 383) -> 768 + (c - 382) [+ lo at 770 + (c - 382)]
+        auto gmap = [](int c) { return c < 128 ? c : (c < 256 ? 128 + c : (c < 382 ? 256 + c : RAFT_HX_FLOW + (c - 382))); };
+        auto gmap_lo = [](int c) { return c < 128 ? 128 + c : (c < 256 ? 256 + c : (c < 382 ? 384 + c : RAFT_HX_FLOW + 2 + (c - 382))); };
         // z and r share their input: one GEMM with N = 256 (z | r)
         for (int dir = 0; dir < 2; ++dir) {
             const std::string sfx = dir == 0 ? "1" : "2";
@@ -413,9 +428,10 @@ int vf_raft_create(vf_raft_t** out, const vf_named_tensor* tensors, int n_tensor
             VF_TRY(prep_same_conv(h, qq, T, u + "gru.convq" + sfx, 128, 384, kh, kw, HX, gmap, 128, nullptr, 1.f, gmap_lo));
         }
         VF_TRY(prep_unmerged_conv(h, h->fh1, T, u + "flow_head.conv1", 256, 128, 3, 3, 256, true));    // reads [h_hi | h_lo]
-        VF_TRY(prep_same_conv(h, h->fh2, T, u + "flow_head.conv2", 2, 256, 3, 3, 256, ident, 8, nullptr));
-        VF_TRY(prep_unmerged_conv(h, h->mk0, T, u + "mask.0", 256, 128, 3, 3, 256, true));
-        VF_TRY(prep_same_conv(h, h->mk2, T, u + "mask.2", 576, 256, 1, 1, 256, ident, 576, nullptr, 0.25f));   // .25 * mask
+        VF_TRY(prep_same_conv(h, h->fh2, T, u + "flow_head.conv2", 2, 256, 3, 3, 512, ident, 8, nullptr, 1.f, lo256));
+        // the convex-upsampling mask is three orders of magnitude less sensitive (4e-6 from fp16 weights): single fp16
+        VF_TRY(prep_unmerged_conv(h, h->mk0, T, u + "mask.0", 256, 128, 3, 3, 256, true, 1.f, 1));
+        VF_TRY(prep_same_conv(h, h->mk2, T, u + "mask.2", 576, 256, 1, 1, 256, ident, 576, nullptr, 0.25f, nullptr, 1));   // .25 * mask
         {
             const size_t np8 = (size_t(h->max_h / 8) * (h->max_w / 8) + 7) / 8 * 8 + 64;
             std::vector<float> s16(np8, 1.0f / 16.0f);     // corr / sqrt(256) (corr.py:60)
@@ -430,7 +446,7 @@ int vf_raft_create(vf_raft_t** out, const vf_named_tensor* tensors, int n_tensor
         const size_t enc_elems = rows2 * 64 > rows4 * 96 ? rows2 * 64 : rows4 * 96;
         VF_TRY(ralloc(h, &h->s0, rows2 * 32));
         VF_TRY(ralloc(h, &h->bufA, 2 * enc_elems)); VF_TRY(ralloc(h, &h->bufB, 2 * enc_elems));   // split rows
-        VF_TRY(ralloc(h, &h->bufC, enc_elems)); VF_TRY(ralloc(h, &h->bufD, enc_elems));
+        VF_TRY(ralloc(h, &h->bufC, 2 * enc_elems)); VF_TRY(ralloc(h, &h->bufD, 2 * enc_elems));
         VF_TRY(ralloc(h, &h->rawA, enc_elems)); VF_TRY(ralloc(h, &h->rawB, enc_elems));
         const size_t ph_elems = rows4 * 256 > rows8e * 384 ? rows4 * 256 : rows8e * 384;
         VF_TRY(ralloc(h, &h->bufE, 2 * ph_elems));
@@ -443,11 +459,11 @@ int vf_raft_create(vf_raft_t** out, const vf_named_tensor* tensors, int n_tensor
         const size_t ld = (P8 + P / 4 + P / 16 + P / 64 + 64 + 3) / 4 * 4;
         VF_TRY(ralloc(h, &h->corr, NP * P * ld));
         VF_TRY(ralloc(h, &h->coords1, NP * P * 2));
-        VF_TRY(ralloc(h, &h->corrfeat, rows8u * CF)); VF_TRY(ralloc(h, &h->c1, rows8u * 256));
-        VF_TRY(ralloc(h, &h->c2f, rows8u * 256));     VF_TRY(ralloc(h, &h->f1, rows8u * 128));
+        VF_TRY(ralloc(h, &h->corrfeat, rows8u * CF)); VF_TRY(ralloc(h, &h->c1, rows8u * 512));
+        VF_TRY(ralloc(h, &h->c2f, rows8u * 512));     VF_TRY(ralloc(h, &h->f1, rows8u * 256));
         VF_TRY(ralloc(h, &h->flow8, rows8u * 8));     VF_TRY(ralloc(h, &h->hx, rows8u * HX));
         VF_TRY(ralloc(h, &h->qx, rows8u * HX));       VF_TRY(ralloc(h, &h->zr, rows8u * 256));
-        VF_TRY(ralloc(h, &h->qb, rows8u * 128));      VF_TRY(ralloc(h, &h->fh, rows8u * 256));
+        VF_TRY(ralloc(h, &h->qb, rows8u * 128));      VF_TRY(ralloc(h, &h->fh, rows8u * 512));
         VF_TRY(ralloc(h, &h->h32, rows8u * 128));
         VF_TRY(ralloc(h, &h->mk, rows8u * 256));
         VF_TRY(ralloc(h, &h->delta, rows8u * 8));     VF_TRY(ralloc(h, &h->mask, rows8u * 576));
@@ -520,11 +536,12 @@ static int raft_core(vf_raft* h, int F, int H, int W, int iters, cudaStream_t s)
     h->launches += 4;
     for (int it = 0; it < iters; ++it) {
         VF_TRY(raft_corr_lookup(h->corr, ldc, h->coords1, NP, H8, W8, h->corrfeat, g8u, CF, s));
-        VF_TRY(run_conv(h, h->convc1, h->corrfeat, CF, g8u, h->c1, 256, 0, VF_ACT_RELU, s));
-        VF_TRY(run_conv(h, h->convc2, h->c1, 256, g8u, h->c2f, 256, 0, VF_ACT_RELU, s));            // cols 0..191
-        VF_TRY(run_conv(h, h->convf1, h->flow8, 8, g8u, h->f1, 128, 0, VF_ACT_RELU, s));
-        VF_TRY(run_conv(h, h->convf2, h->f1, 128, g8u, h->c2f + 192, 256, 0, VF_ACT_RELU, s));       // cols 192..255
-        VF_TRY(run_conv(h, h->convm, h->c2f, 256, g8u, h->hx + 512, HX, 0, VF_ACT_RELU, s));         // cols 512..639
+        // every intermediate is a split pair written by the GEMM epilogue: rows = [hi | lo]
+        VF_TRY(run_conv(h, h->convc1, h->corrfeat, CF, g8u, h->c1, 512, 2, VF_ACT_RELU, s, 256));
+        VF_TRY(run_conv(h, h->convc2, h->c1, 512, g8u, h->c2f, 512, 2, VF_ACT_RELU, s, 256));         // cols 0..191 | 256..447
+        VF_TRY(run_conv(h, h->convf1, h->flow8, 8, g8u, h->f1, 256, 2, VF_ACT_RELU, s, 128));
+        VF_TRY(run_conv(h, h->convf2, h->f1, 256, g8u, h->c2f + 192, 512, 2, VF_ACT_RELU, s, 256));   // cols 192..255 | 448..511
+        VF_TRY(run_conv(h, h->convm, h->c2f, 512, g8u, h->hx + RAFT_HX_MOTION, HX, 2, VF_ACT_RELU, s, 128));   // 512..639 | 640..767
         for (int dir = 0; dir < 2; ++dir) {
             const ConvW& zr = dir == 0 ? h->zr1 : h->zr2;
             const ConvW& qq = dir == 0 ? h->q1 : h->q2;
@@ -533,8 +550,8 @@ static int raft_core(vf_raft* h, int F, int H, int W, int iters, cudaStream_t s)
             VF_TRY(run_conv(h, qq, h->qx, HX, g8u, h->qb, 128, 1, VF_ACT_TANH, s));
             VF_TRY(raft_gru_update(h->hx, h->h32, h->zr, h->qb, g8u, HX, s));
         }
-        VF_TRY(run_conv(h, h->fh1, h->hx, HX, g8u, h->fh, 256, 0, VF_ACT_RELU, s));
-        VF_TRY(run_conv(h, h->fh2, h->fh, 256, g8u, h->delta, 8, 1, VF_ACT_NONE, s));
+        VF_TRY(run_conv(h, h->fh1, h->hx, HX, g8u, h->fh, 512, 2, VF_ACT_RELU, s, 256));
+        VF_TRY(run_conv(h, h->fh2, h->fh, 512, g8u, h->delta, 8, 1, VF_ACT_NONE, s));
         VF_TRY(raft_coords_update(h->coords1, h->delta, h->hx, h->qx, h->flow8, g8u, HX, s));
         h->launches += 6;
     }
@@ -640,7 +657,7 @@ int vf_raft_debug_read(vf_raft_t* h, int what, float* out, int64_t capacity, int
     if (what == 0) { Vol2 v = h->g8e; v.n = n + 1; return raft_unpack2d_f32(h->fmap32, v, 256, 0, 256, out, s); }
     if (what == 1) return raft_unpack2d_f32(h->cnet32, h->g8e, 256, 0, 256, out, s);
     if (what == 2) return raft_unpack2d(h->hx, h->g8u, HX, 0, 128, out, s);          // GRU hidden state
-    if (what == 3) return raft_unpack2d(h->hx, h->g8u, HX, 640, 2, out, s);          // low-res flow (hi half)
+    if (what == 3) return raft_unpack2d(h->hx, h->g8u, HX, RAFT_HX_FLOW, 2, out, s);          // low-res flow (hi half)
     return raft_unpack2d(h->corrfeat, h->g8u, CF, 0, 324, out, s);                   // last lookup (hi half)
 }
 

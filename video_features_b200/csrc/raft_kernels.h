@@ -6,6 +6,11 @@
 
 namespace vf {
 
+// Row layout of the GRU operand buffers hx / qx (raft_kernels.cu, cnet_split_kernel):
+//   [h_hi 0..127 | h_lo 128..255 | inp_hi 256..383 | inp_lo 384..511 | motion_hi 512..639 | motion_lo 640..767 |
+//    flow 768..775 = (fx_hi, fy_hi, fx_lo, fy_lo, 0, 0, 0, 0)]
+constexpr int RAFT_HX = 776, RAFT_HX_MOTION = 512, RAFT_HX_FLOW = 768;
+
 // zero-bordered 2-D volume [n][Hp][Wp][C]; valid region [h0,h1) x [w0,w1)
 struct Vol2 {
     int n, Hp, Wp, h0, h1, w0, w1;
