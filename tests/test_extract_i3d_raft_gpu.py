@@ -72,8 +72,8 @@ def test_extract_i3d_two_streams_vs_oracle(cuda_device, tmp_path):
     # 1.6e-4 of the flow itself -- already moves the oracle's OWN 1024-d feature by 3e-3, and 3e-4 px by 1.6e-2
     # (scripts: DESIGN.md §2).  Parity of this branch is therefore asserted per stage: RAFT flow (test_raft_gpu.py,
     # rel-L2 <= 1e-3) and quantiser + I3D on identical flow (test_i3d_gpu.py::test_i3d_fused_stream_transforms, 2e-4).
-    # End to end only gross agreement can be asked for:
-    assert rel < 0.15
+    # End to end only gross agreement can be asked for (measured 9.4e-3 with the split-fp16 RAFT, 4e-2 before it):
+    assert rel < 0.05
 
 
 @pytest.mark.skipif(not HAVE, reason="reference checkpoint copies not present (scripts/fetch_checkpoints.py)")
@@ -100,8 +100,8 @@ def test_extract_raft_writes_flow(cuda_device, tmp_path):
     ref = raft_net.forward(sd, x[:-1], x[1:], 20).cpu().numpy()
     rel = np.linalg.norm(flow - ref) / np.linalg.norm(ref)
     print("ExtractRAFT vs oracle:", rel)
-    # Decoded (block-compressed) 128x160 frames are a hard case for reduced-precision RAFT: a CPU emulation that only
-    # rounds every conv INPUT to fp16 (weights fp32) already gives 7.6e-3 here, while smooth frames give 1e-4 .. 3e-4
-    # (test_raft_gpu.py).  With the flow / correlation / hidden-state operands carried as split-fp16 pairs the engine
-    # measures 5.9e-3; the remaining term is the fp16 activation storage inside the encoders (known gap).
-    assert rel < 2e-2
+    # Decoded (block-compressed) 128x160 frames are the hard case for reduced-precision RAFT: rounding only the conv
+    # INPUTS to fp16 gives 7.6e-3 here in a CPU emulation, fp16 weights alone 6e-4 with a 4.6e-3 max-abs outlier.  With
+    # every operand carried as a split-fp16 pair the engine measures 5.7e-5 (the fp32 oracle's own thread-count noise
+    # on these frames is 2.5e-5).
+    assert rel < 5e-4

@@ -1,11 +1,12 @@
 """RAFT flow through the C ABI against the fp32 oracle (oracle/raft_net.py, pinned bit-for-bit to the reference
 module) and against the reference module's own output (tests/golden/raft_outputs.npz).
 
-Bar: rel-L2 <= 1e-3 and max-abs <= 1e-3 * max|ref| on the flow field.  STATUS on smooth synthetic motion:
-rel-L2 is met with margin (1.1e-4 at 128x160, 3.4e-4 at 270x480); max-abs is met at 128x160 (3.5e-4) and NOT at 270x480
-(4.3e-3 = 0.0075 px at the worst of 2.6e5 values, p99.9 0.0035 px).  On block-compressed video frames the fp16
-activation rounding of the encoders is amplified (6e-3 rel-L2, see test_extract_i3d_raft_gpu.py and DESIGN.md §2):
-a known gap, the asserted bounds below are the measured ones.  Needs the reference checkpoint copy
+Bar: rel-L2 <= 1e-3 and max-abs <= 1e-3 * max|ref| on the flow field.  RAFT's 20 refinement steps amplify
+operand rounding by two to three orders of magnitude on hard inputs (the fp32 oracle itself moves by 2.5e-5 between 1
+and 16 CPU threads on block-compressed frames), so the engine carries EVERY GEMM operand as a split-fp16 pair
+(activations [hi | lo] with duplicated weight columns, weights as hi + lo passes).  Measured: rel-L2
+5.5e-6 / max 3.8e-5 at 128x160, 1.7e-5 / 1.8e-4 at 270x480, 5.7e-5 on block-compressed video
+(test_extract_i3d_raft_gpu.py) -- both parts of the bar are met with margin.  Needs the reference checkpoint copy
 under checkpoints/ (scripts/fetch_checkpoints.py) -- RAFT with random weights is not a meaningful dynamical system."""
 import os
 
@@ -51,7 +52,7 @@ def test_raft_stages_and_one_iteration(raft, cuda_device):
     cnet = R.encoder(sdg, "cnet", img[:-1], "batch")
     e2 = _err(eng.debug_read(1), cnet)
     print("cnet output:", e2)
-    assert e[0] < 3e-3 and e2[0] < 3e-3
+    assert e[0] < 1e-4 and e2[0] < 1e-4         # measured 3.8e-6 / 6.8e-6
     # first lookup (coords = grid) against the oracle's pyramid lookup
     pyr = R.corr_pyramid(fmap[:-1].float(), fmap[1:].float())
     H8, W8 = 16, 20
@@ -61,14 +62,14 @@ def test_raft_stages_and_one_iteration(raft, cuda_device):
     eng.flow(x, iters=1, unpad=False)
     e = _err(eng.debug_read(4), look)       # (the last lookup of a 1-iteration run is the first one)
     print("corr lookup:", e)
-    assert e[0] < 5e-3
+    assert e[0] < 1e-4
     ref1, low1 = R.forward(sd_to(sd, cuda_device), x[:-1], x[1:], 1, return_lowres=True)
     e = _err(eng.debug_read(3), low1)
     print("low-res flow after 1 iteration:", e)
-    assert e[0] < 5e-3
+    assert e[0] < 1e-4
     e = _err(y1, ref1)
     print("flow_up after 1 iteration:", e)
-    assert e[0] < 5e-3
+    assert e[0] < 1e-4 and e[1] < 1e-3
 
 
 def sd_to(sd, dev):
@@ -89,13 +90,13 @@ def test_raft_20_iterations_vs_oracle_and_reference_golden(raft, cuda_device, h,
     d = (y.double().cpu() - ref.double().cpu()).abs().flatten()
     print(f"    abs err px: max {float(d.max()):.4f}  p99.9 {float(d.kthvalue(int(d.numel() * 0.999)).values):.4f}  "
           f"median {float(d.median()):.5f}  (max |flow| {float(ref.abs().max()):.3f})")
-    assert rel < 1e-3            # the north-star bar
-    assert mx < 8e-3             # measured 3.5e-4 / 4.3e-3: the larger one is above the 1e-3 max-abs bar (documented gap)
+    assert rel < 1e-4            # north-star bar 1e-3; measured 5.5e-6 / 1.7e-5
+    assert mx < 1e-3             # the north-star max-abs bar; measured 3.8e-5 / 1.8e-4
     gold = np.load(os.path.join(ROOT, "tests", "golden", "raft_outputs.npz"))[f"flow_{h}x{w}"]
     got = y.cpu().numpy() if h < 200 else y.cpu().numpy()[:, :, ::3, ::3]
     rel_g = float(np.linalg.norm(got - gold) / np.linalg.norm(gold))
     print(f"{h}x{w}: vs reference-module golden rel-L2 {rel_g:.3e}")
-    assert rel_g < 1e-3
+    assert rel_g < 1e-4
     # uint8 HWC entry == float CHW entry on integer-valued frames
     y8 = eng.flow(fr.permute(0, 2, 3, 1).contiguous().to(torch.uint8).to(cuda_device), iters=20, unpad=True)
     assert torch.equal(y8, y)

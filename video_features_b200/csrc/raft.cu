@@ -656,9 +656,9 @@ int vf_raft_debug_read(vf_raft_t* h, int what, float* out, int64_t capacity, int
     }
     if (what == 0) { Vol2 v = h->g8e; v.n = n + 1; return raft_unpack2d_f32(h->fmap32, v, 256, 0, 256, out, s); }
     if (what == 1) return raft_unpack2d_f32(h->cnet32, h->g8e, 256, 0, 256, out, s);
-    if (what == 2) return raft_unpack2d(h->hx, h->g8u, HX, 0, 128, out, s);          // GRU hidden state
-    if (what == 3) return raft_unpack2d(h->hx, h->g8u, HX, RAFT_HX_FLOW, 2, out, s);          // low-res flow (hi half)
-    return raft_unpack2d(h->corrfeat, h->g8u, CF, 0, 324, out, s);                   // last lookup (hi half)
+    if (what == 2) return raft_unpack2d(h->hx, h->g8u, HX, 0, 128, 128, out, s);                     // GRU hidden state (hi + lo)
+    if (what == 3) return raft_unpack2d(h->hx, h->g8u, HX, RAFT_HX_FLOW, 2, 2, out, s);              // low-res flow (hi + lo)
+    return raft_unpack2d(h->corrfeat, h->g8u, CF, 0, 324, 328, out, s);                               // last lookup (hi + lo)
 }
 
 int64_t vf_raft_launch_count(const vf_raft_t* h) { return h ? h->launches : 0; }

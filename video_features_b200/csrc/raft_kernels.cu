@@ -445,14 +445,17 @@ __global__ void upsample_flow_kernel(const float* __restrict__ coords1, const fl
 }
 
 // diagnostics: valid region of channels [c0, c0+cc) of a bordered fp16 volume -> fp32 NCHW
-__global__ void unpack2d_kernel(const __half* __restrict__ in, Vol2 v, int ld, int c0, int cc, float* __restrict__ out) {
+// lo_off > 0: the columns are the hi halves of split pairs whose lo halves sit lo_off columns to the right
+__global__ void unpack2d_kernel(const __half* __restrict__ in, Vol2 v, int ld, int c0, int cc, int lo_off,
+                                float* __restrict__ out) {
     const int H = v.h1 - v.h0, W = v.w1 - v.w0;
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t total = int64_t(v.n) * cc * H * W;
     if (idx >= total) return;
     const int xw = int(idx % W), y = int((idx / W) % H), c = int((idx / (int64_t(W) * H)) % cc);
     const int b = int(idx / (int64_t(W) * H * cc));
-    out[idx] = __half2float(in[((int64_t(b) * v.Hp + y + v.h0) * v.Wp + xw + v.w0) * ld + c0 + c]);
+    const __half* src = in + ((int64_t(b) * v.Hp + y + v.h0) * v.Wp + xw + v.w0) * ld + c0 + c;
+    out[idx] = __half2float(src[0]) + (lo_off > 0 ? __half2float(src[lo_off]) : 0.f);
 }
 
 __global__ void unpack2d_f32_kernel(const float* __restrict__ in, Vol2 v, int ld, int c0, int cc, float* __restrict__ out) {
@@ -554,9 +557,9 @@ int raft_unpack2d_f32(const float* in, const Vol2& v, int ld, int c0, int cc, fl
     unpack2d_f32_kernel<<<nb(total, 256), 256, 0, s>>>(in, v, ld, c0, cc, out);
     LAUNCH_CHECK();
 }
-int raft_unpack2d(const __half* in, const Vol2& v, int ld, int c0, int cc, float* out, cudaStream_t s) {
+int raft_unpack2d(const __half* in, const Vol2& v, int ld, int c0, int cc, int lo_off, float* out, cudaStream_t s) {
     const int64_t total = int64_t(v.n) * cc * (v.h1 - v.h0) * (v.w1 - v.w0);
-    unpack2d_kernel<<<nb(total, 256), 256, 0, s>>>(in, v, ld, c0, cc, out);
+    unpack2d_kernel<<<nb(total, 256), 256, 0, s>>>(in, v, ld, c0, cc, lo_off, out);
     LAUNCH_CHECK();
 }
 

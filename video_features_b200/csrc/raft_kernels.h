@@ -40,6 +40,6 @@ int raft_coords_update(float* coords1, const float* delta, __half* hx, __half* q
 int raft_upsample_flow(const float* coords1, const float* mask, const Vol2& v, int n, int H8, int W8, int oy, int ox,
                        int Ho, int Wo, float* flow_up, cudaStream_t s);
 int raft_unpack2d_f32(const float* in, const Vol2& v, int ld, int c0, int cc, float* out, cudaStream_t s);
-int raft_unpack2d(const __half* in, const Vol2& v, int ld, int c0, int cc, float* out, cudaStream_t s);
+int raft_unpack2d(const __half* in, const Vol2& v, int ld, int c0, int cc, int lo_off, float* out, cudaStream_t s);
 
 }  // namespace vf
