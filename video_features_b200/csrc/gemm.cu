@@ -158,11 +158,13 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     const int bcol = tap * cg.k_per_tap;
                     for (int kk = 0; kk < kpt; ++kk) {
                         mbar_wait(&empty[stage], phase ^ 1);
-                        if (cta == 0) mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+                        const bool lo_blk = NSPLIT == 2 && ((cg.lo_mask >> kk) & 1ull);    // W_lo not needed
+                        if (cta == 0)
+                            mbar_expect_tx(&full[stage], 2 * (Cfg::A_BYTES + (lo_blk ? Cfg::B_HALF : Cfg::B_BYTES)));
                         const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
                         tma_load_2d_2sm(sA + stage * Cfg::A_BYTES, &tmA, bar, kk * BK, arow);
                         tma_load_2d_2sm(sB + stage * Cfg::B_BYTES, &tmB, bar, bcol + kk * BK, n0);
-                        if (NSPLIT == 2)   // the lo half of the weights lives ntaps*k_per_tap columns to the right
+                        if (NSPLIT == 2 && !lo_blk)   // the lo half of the weights lives ntaps*k_per_tap columns to the right
                             tma_load_2d_2sm(sB + stage * Cfg::B_BYTES + Cfg::B_HALF, &tmB, bar,
                                             cg.ntaps * cg.k_per_tap + bcol + kk * BK, n0);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -180,19 +182,21 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_k; ++kb) {
+                for (int kb = 0, kk = 0; kb < num_k; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint64_t adesc = umma_desc_sw128(sA + stage * Cfg::A_BYTES);
                     const uint64_t bdesc = umma_desc_sw128(sB + stage * Cfg::B_BYTES);
+                    const bool lo_blk = NSPLIT == 2 && ((cg.lo_mask >> kk) & 1ull);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {   // +32 B (encoded 2) per K step inside the swizzle row
                         umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                        if (NSPLIT == 2)
+                        if (NSPLIT == 2 && !lo_blk)
                             umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + (Cfg::B_HALF >> 4) + 2 * k, idesc, 1u);
                     }
                     umma_commit_2sm(&empty[stage], 3);    // free this smem slot in both CTAs
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++kk == kpt) kk = 0;              // K block index inside the current tap
                 }
                 umma_commit_2sm(&tfull[acc], 3);           // accumulators of both CTAs complete
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -219,11 +223,11 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const uint32_t t_row = tmem_base + acc * BN + (uint32_t(q * 32) << 16);
             bool keep = true;     // rows outside the valid conv region become the next layer's zero padding
             if (cg.mask) {
-                const int m = m0 + row;
+                const int m = m0 + row - cg.row0;
                 const int w = m % cg.Wp, r1 = m / cg.Wp;
                 const int hh = r1 % cg.Hp, r2 = r1 / cg.Hp;
                 const int tt = r2 % cg.Tp;
-                keep = (w >= cg.w0) && (w < cg.w1) && (hh >= cg.h0) && (hh < cg.h1) && (tt >= cg.t0) && (tt < cg.t1);
+                keep = (m >= 0) && (w >= cg.w0) && (w < cg.w1) && (hh >= cg.h0) && (hh < cg.h1) && (tt >= cg.t0) && (tt < cg.t1);
             }
 #pragma unroll 1
             for (int c = grp * slice_cols; c < BN; c += 2 * slice_cols)
@@ -402,13 +406,14 @@ static int run_gemm(const CUtensorMap& tmA, const __half* B, int ldb, int64_t Kt
     const int bn = (N > 128) ? 256 : (N > 64) ? 128 : 64;     // pair-tile width; the B box is half of it
     CUtensorMap tmB, tmO, tmO2;
     VF_TRY(make_tmap_2d(&tmB, B, 2, uint64_t(N), uint64_t(Ktot), uint64_t(ldb) * 2, uint32_t(bn / 2), BK));
-    if (ep.out_f32) VF_TRY(make_tmap_2d(&tmO, ep.out, 4, uint64_t(M), uint64_t(N), uint64_t(ep.ldo) * 4, BM, 32));
-    else            VF_TRY(make_tmap_2d(&tmO, ep.out, 2, uint64_t(M), uint64_t(N), uint64_t(ep.ldo) * 2, BM, 64));
+    const uint64_t ncols = uint64_t(N);     // (N % 8 == 0: a store view narrower than a 16-byte multiple corrupts its neighbours)
+    if (ep.out_f32) VF_TRY(make_tmap_2d(&tmO, ep.out, 4, uint64_t(M), ncols, uint64_t(ep.ldo) * 4, BM, 32));
+    else            VF_TRY(make_tmap_2d(&tmO, ep.out, 2, uint64_t(M), ncols, uint64_t(ep.ldo) * 2, BM, 64));
     tmO2 = tmO;
     if (ep.split_off) {     // second view of the output rows: the lo halves, both views clip at N columns
         if (ep.out_f32 || ep.split_off < N || ep.split_off % 8)
             return fail(VF_ERR_INVALID, "gemm: split output needs fp16 out and split_off >= N, multiple of 8");
-        VF_TRY(make_tmap_2d(&tmO2, static_cast<__half*>(ep.out) + ep.split_off, 2, uint64_t(M), uint64_t(N),
+        VF_TRY(make_tmap_2d(&tmO2, static_cast<__half*>(ep.out) + ep.split_off, 2, uint64_t(M), ncols,
                             uint64_t(ep.ldo) * 2, BM, 64));
     }
     if (!g_prof.on) return run_gemm_launch(tmA, tmB, tmO, tmO2, bn, ep, M, N, cg, stream);
@@ -422,7 +427,14 @@ static int run_gemm(const CUtensorMap& tmA, const __half* B, int ldb, int64_t Kt
     const int st = run_gemm_launch(tmA, tmB, tmO, tmO2, bn, ep, M, N, cg, stream);
     VF_CUDA(cudaEventRecord(g_prof.ev[g_prof.used + 1], stream));
     g_prof.used += 2;
-    g_prof.flops += 2.0 * double(M) * double(N) * double(Ktot);
+    double kexec = double(Ktot);
+    if (cg.nsplit == 2 && cg.lo_mask) {      // K blocks whose W_lo pass is skipped
+        const int kpt = (cg.k_per_tap + BK - 1) / BK;
+        int skipped = 0;
+        for (int kk = 0; kk < kpt && kk < 64; ++kk) skipped += int((cg.lo_mask >> kk) & 1ull);
+        kexec -= double(cg.ntaps) * skipped * BK;
+    }
+    g_prof.flops += 2.0 * double(M) * double(N) * kexec;
     return st;
 }
 

@@ -60,6 +60,9 @@ struct ConvGeom {
     int tap_off[64];    // row shift of each tap (includes the shift to the first kw tap)
     int nsplit;         // 1, or 2: weights are a hi+lo fp16 pair, Wt = [hi (ntaps*k_per_tap) | lo (same)] along K; every
                         // A tile is loaded once and multiplied with both (A.W_hi + A.W_lo)
+    unsigned long long lo_mask;   // nsplit == 2 only: bit kk set = K block kk of every tap holds only lo halves of split-fp16
+                        // activations (or unused columns): the W_lo pass is skipped there (a_lo.w_lo is below fp32 eps)
+    int row0;           // leading guard rows: row m of the matrix is position m - row0 of the volume (rows < row0 are zeroed)
     int mask;           // 1: zero the rows outside the valid region
     int Tp, Hp, Wp;     // padded volume extents (rows per sample = Tp*Hp*Wp)
     int t0, t1, h0, h1, w0, w1;

@@ -35,12 +35,13 @@ struct ConvW {       // a convolution prepared for conv_gemm_f16
     int ntaps = 0, k_per_tap = 0;
     std::vector<int> dh, dw0;   // per tap: row offset (in kernel rows) and the column shift of its first element
     int nsplit = 1;             // 2: w = [hi (ntaps*k_per_tap) | lo (same)] along K (ConvGeom::nsplit)
+    unsigned long long lo_mask = 0;   // K blocks (per tap) holding only lo-half activation columns (ConvGeom::lo_mask)
     __half* w = nullptr;
     float *scale = nullptr, *bias = nullptr;
 };
 
 static const int HX = RAFT_HX;   // hx / qx row layout: raft_kernels.h
-static const int CF = 656;   // [324 correlation features hi + 4 pad | 324 lo + 4 pad]
+static const int CF = RAFT_CF;    // correlation-feature rows: raft_kernels.h
 
 }  // namespace vf
 
@@ -48,6 +49,7 @@ using namespace vf;
 
 struct vf_raft {
     int device = 0, max_frames = 0, max_h = 0, max_w = 0;
+    int lead_alloc = 0;         // guard rows in front of every update-block buffer (pointers below are past them)
     int wsplit = 2;             // weights as hi+lo fp16 pairs (VF_RAFT_FAST=1: single fp16 weights, outside the parity bar)
     std::vector<void*> allocs;
     // encoders: [0] = fnet (instance norm), [1] = cnet (batch norm folded)
@@ -110,6 +112,7 @@ static int upload_conv(vf_raft* h, ConvW& cw, const float* w, const float* b, in
     cw.nsplit = nsplit;
     const size_t Kall = size_t(Ktot) * nsplit;
     std::vector<__half> B(size_t(n_out) * Kall, __float2half_rn(0.f));
+    std::vector<char> has_hi(size_t(Ktot), 0);      // K columns that multiply a hi (or single-fp16) activation
     for (int o = 0; o < co; ++o)
         for (int c = 0; c < ci; ++c)
             for (int a = 0; a < kh; ++a)
@@ -121,6 +124,7 @@ static int upload_conv(vf_raft* h, ConvW& cw, const float* w, const float* b, in
                     const __half wv = __float2half_rn(wf);
                     const __half wl = __float2half_rn(wf - __half2float(wv));
                     B[size_t(o) * Kall + k] = wv;
+                    has_hi[k] = 1;
                     if (nsplit == 2) B[size_t(o) * Kall + Ktot + k] = wl;
                     if (col_lo) {
                         const int k2 = col_lo(a, d, c);
@@ -138,6 +142,19 @@ static int upload_conv(vf_raft* h, ConvW& cw, const float* w, const float* b, in
         bi[o] = (b ? b[o] : 0.f) * s + (bn_shift ? bn_shift[o] : 0.f) * extra_scale;
     }
     cw.n_out = n_out;
+    // a K block none of whose columns meets a hi half needs only the W_hi pass (a_lo . w_lo < 2^-22 of the product)
+    cw.lo_mask = 0;
+    const int kpt_blocks = (cw.k_per_tap + 63) / 64;
+    if (nsplit == 2 && kpt_blocks <= 64 && cw.ntaps * cw.k_per_tap == Ktot) {
+        unsigned long long m = ~0ull;
+        for (int t = 0; t < cw.ntaps; ++t)
+            for (int kk = 0; kk < kpt_blocks; ++kk) {
+                bool any_hi = false;
+                for (int j = kk * 64; j < (kk + 1) * 64 && j < cw.k_per_tap; ++j) any_hi |= has_hi[size_t(t) * cw.k_per_tap + j] != 0;
+                if (any_hi) m &= ~(1ull << kk);
+            }
+        cw.lo_mask = kpt_blocks == 64 ? m : (m & ((1ull << kpt_blocks) - 1));
+    }
     VF_TRY(ralloc(h, &cw.w, B.size()));
     VF_TRY(ralloc(h, &cw.scale, size_t(n_out)));
     VF_TRY(ralloc(h, &cw.bias, size_t(n_out)));
@@ -282,20 +299,23 @@ static int prep_encoder(vf_raft* h, vf_raft::Enc& e, const TensorTable& T, const
 }
 
 // out_mode: 0 fp16, 1 fp32, 2 split-fp16 pair (hi at column n, lo at column split_off + n of the same rows)
+// lead: guard rows in front of X and out (both pointers are past them); the GEMM covers them and writes them as zeros
 static int run_conv(vf_raft* h, const ConvW& cw, const __half* X, int pitch, const Vol2& v, void* out, int ldo, int out_mode,
-                    int act, cudaStream_t s, int split_off = 0) {
+                    int act, cudaStream_t s, int split_off = 0, int lead = 0) {
     ConvGeom g;
     memset(&g, 0, sizeof(g));
-    g.ntaps = cw.ntaps; g.k_per_tap = cw.k_per_tap; g.nsplit = cw.nsplit;
+    g.ntaps = cw.ntaps; g.k_per_tap = cw.k_per_tap; g.nsplit = cw.nsplit; g.lo_mask = cw.lo_mask;
     for (int j = 0; j < cw.ntaps; ++j) g.tap_off[j] = cw.dh[j] * v.Wp + cw.dw0[j];
-    g.mask = 1;
+    g.mask = 1; g.row0 = lead;
     g.Tp = 1; g.Hp = v.Hp; g.Wp = v.Wp; g.t0 = 0; g.t1 = 1; g.h0 = v.h0; g.h1 = v.h1; g.w0 = v.w0; g.w1 = v.w1;
+    X -= size_t(lead) * pitch;
+    out = static_cast<char*>(out) - size_t(lead) * ldo * (out_mode == 1 ? 4 : 2);
     GemmEpi ep;
     memset(&ep, 0, sizeof(ep));
     ep.out = out; ep.ldo = ldo; ep.out_f32 = out_mode == 1; ep.bias = cw.bias; ep.scale = cw.scale; ep.act = act;
     ep.split_off = out_mode == 2 ? split_off : 0;
     h->launches += 1;
-    return conv_gemm_f16(X, pitch, v.rows(), cw.w, cw.n_out, g, ep, s);
+    return conv_gemm_f16(X, pitch, v.rows() + lead, cw.w, cw.n_out, g, ep, s);
 }
 
 // BasicEncoder.forward on m frames whose (split) stem phase volume is in h->s0; the 256-channel output is written in
@@ -393,7 +413,7 @@ int vf_raft_create(vf_raft_t** out, const vf_named_tensor* tensors, int n_tensor
         VF_TRY(prep_encoder(h, h->enc[1], T, "cnet", true, 256));
         const std::string u = "update_block.";
         VF_TRY(prep_same_conv(h, h->convc1, T, u + "encoder.convc1", 256, 324, 1, 1, CF, ident, 256, nullptr, 1.f,
-                              [](int c) { return 328 + c; }));                       // lo half of the correlation features
+                              [](int c) { return RAFT_CF_LO + c; }));                // lo half of the correlation features
         auto lo256 = [](int c) { return 256 + c; };
         VF_TRY(prep_same_conv(h, h->convc2, T, u + "encoder.convc2", 192, 256, 3, 3, 512, ident, 192, nullptr, 1.f, lo256));
         VF_TRY(prep_same_conv(h, h->convf1, T, u + "encoder.convf1", 128, 2, 7, 7, 8, ident, 128, nullptr, 1.f,
@@ -402,11 +422,14 @@ int vf_raft_create(vf_raft_t** out, const vf_named_tensor* tensors, int n_tensor
                               [](int c) { return 128 + c; }));
         // reads c2f rows = [cor 192 | flo 64 | cor_lo 192 | flo_lo 64]
         VF_TRY(prep_same_conv(h, h->convm, T, u + "encoder.conv", 126, 256, 3, 3, 512, ident, 128, nullptr, 1.f, lo256));
+        // (columns 126, 127 of the motion block hold the flow: raft_flow_fill rewrites them after this conv's 128-wide
+        // store.  Clipping the store at 126 columns does not work: a TMA store view whose row is not a multiple of 16 bytes
+        // damaged the two neighbouring elements -- measured 5e-3 flow error.)
         // GRU gates read hx / qx rows (layout in raft_kernels.cu): conv input channel c -> column
         //   h (c < 128) -> c [+ lo at 128 + c], inp (128..255) -> 128 + c [+ lo at 256 + c],
-        //   motion-out (256..381) -> 256 + c [+ lo at 384 + c], flow (382, 383) -> 768 + (c - 382) [+ lo at 770 + (c - 382)]
-        auto gmap = [](int c) { return c < 128 ? c : (c < 256 ? 128 + c : (c < 382 ? 256 + c : RAFT_HX_FLOW + (c - 382))); };
-        auto gmap_lo = [](int c) { return c < 128 ? 128 + c : (c < 256 ? 256 + c : (c < 382 ? 384 + c : RAFT_HX_FLOW + 2 + (c - 382))); };
+        //   motion-out (256..381) and flow (382, 383) -> 256 + c [+ lo at 384 + c]   (12 K blocks, alternately hi / lo)
+        auto gmap = [](int c) { return c < 128 ? c : (c < 256 ? 128 + c : 256 + c); };
+        auto gmap_lo = [](int c) { return c < 128 ? 128 + c : (c < 256 ? 256 + c : 384 + c); };
         // z and r share their input: one GEMM with N = 256 (z | r)
         for (int dir = 0; dir < 2; ++dir) {
             const std::string sfx = dir == 0 ? "1" : "2";
@@ -459,14 +482,23 @@ int vf_raft_create(vf_raft_t** out, const vf_named_tensor* tensors, int n_tensor
         const size_t ld = (P8 + P / 4 + P / 16 + P / 64 + 64 + 3) / 4 * 4;
         VF_TRY(ralloc(h, &h->corr, NP * P * ld));
         VF_TRY(ralloc(h, &h->coords1, NP * P * 2));
-        VF_TRY(ralloc(h, &h->corrfeat, rows8u * CF)); VF_TRY(ralloc(h, &h->c1, rows8u * 512));
-        VF_TRY(ralloc(h, &h->c2f, rows8u * 512));     VF_TRY(ralloc(h, &h->f1, rows8u * 256));
-        VF_TRY(ralloc(h, &h->flow8, rows8u * 8));     VF_TRY(ralloc(h, &h->hx, rows8u * HX));
-        VF_TRY(ralloc(h, &h->qx, rows8u * HX));       VF_TRY(ralloc(h, &h->zr, rows8u * 256));
-        VF_TRY(ralloc(h, &h->qb, rows8u * 128));      VF_TRY(ralloc(h, &h->fh, rows8u * 512));
-        VF_TRY(ralloc(h, &h->h32, rows8u * 128));
-        VF_TRY(ralloc(h, &h->mk, rows8u * 256));
-        VF_TRY(ralloc(h, &h->delta, rows8u * 8));     VF_TRY(ralloc(h, &h->mask, rows8u * 576));
+        // update-block volumes: `lead` zeroed guard rows in front of the first sample (run_conv's row0), see raft_core
+        h->lead_alloc = 3 * (W / 8 + 3) + 3;
+        auto ualloc = [&](auto** p, size_t ld) -> int {
+            const size_t count = (size_t(h->lead_alloc) + rows8u + 8) * ld;
+            VF_TRY(ralloc(h, p, count));
+            VF_CUDA(cudaMemset(*p, 0, count * sizeof(**p)));
+            *p += size_t(h->lead_alloc) * ld;
+            return VF_OK;
+        };
+        VF_TRY(ualloc(&h->corrfeat, CF)); VF_TRY(ualloc(&h->c1, 512));
+        VF_TRY(ualloc(&h->c2f, 512));     VF_TRY(ualloc(&h->f1, 256));
+        VF_TRY(ualloc(&h->flow8, 8));     VF_TRY(ualloc(&h->hx, HX));
+        VF_TRY(ualloc(&h->qx, HX));       VF_TRY(ualloc(&h->zr, 256));
+        VF_TRY(ualloc(&h->qb, 128));      VF_TRY(ualloc(&h->fh, 512));
+        VF_TRY(ualloc(&h->h32, 128));
+        VF_TRY(ualloc(&h->mk, 256));
+        VF_TRY(ualloc(&h->delta, 8));     VF_TRY(ualloc(&h->mask, 576));
         VF_CUDA(cudaStreamCreateWithFlags(&h->cs, cudaStreamNonBlocking));
         VF_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
         VF_CUDA(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
@@ -499,6 +531,9 @@ int vf_raft_destroy(vf_raft_t* h) {
 
 namespace vf {
 
+// geometry of the update-block volumes (see raft_core)
+static Vol2 update_vol(int NP, int H8, int W8) { return Vol2{NP, H8 + 3, W8 + 3, 0, H8, 0, W8}; }
+
 // encoders -> correlation pyramid -> `iters` refinement steps -> mask head; the stem phase volume is already in h->s0
 static int raft_core(vf_raft* h, int F, int H, int W, int iters, cudaStream_t s) {
     const int NP = F - 1, H8 = H / 8, W8 = W / 8, P = H8 * W8, P8 = (P + 7) / 8 * 8;
@@ -524,7 +559,12 @@ static int raft_core(vf_raft* h, int F, int H, int W, int iters, cudaStream_t s)
     // ---- context network on frames[:-1] (batch norm folded); reuses s0: the first NP frames' phase rows
     VF_TRY(run_encoder(h, h->enc[1], false, NP, H, W, h->cnet32, 256, s));
     const Vol2 g8e{NP, H8 + 2, W8 + 2, 1, 1 + H8, 1, 1 + W8};
-    const Vol2 g8u{NP, H8 + 6, W8 + 6, 3, 3 + H8, 3, 3 + W8};
+    // update-block volume: 3 zero rows / columns AFTER the valid region only.  In the flattened row space the pad behind
+    // image row y is also the pad in front of row y+1, and the pad below sample b the pad above sample b+1; in front of
+    // the first sample sit `lead` zeroed guard rows (a merged-kw tap starts kw/2 rows early, so they must be real rows,
+    // not TMA out-of-bounds fill).  (H8+3)(W8+3) rows per sample instead of (H8+6)(W8+6): 12 % fewer GEMM rows at 270x480.
+    const Vol2 g8u = update_vol(NP, H8, W8);
+    const int lead = 3 * g8u.Wp + 3;
     const size_t rows8u = size_t(g8u.rows());
     // zero the update-block operand buffers once: their border rows are read as conv padding
     VF_CUDA(cudaMemsetAsync(h->hx, 0, rows8u * HX * sizeof(__half), s));
@@ -537,27 +577,29 @@ static int raft_core(vf_raft* h, int F, int H, int W, int iters, cudaStream_t s)
     for (int it = 0; it < iters; ++it) {
         VF_TRY(raft_corr_lookup(h->corr, ldc, h->coords1, NP, H8, W8, h->corrfeat, g8u, CF, s));
         // every intermediate is a split pair written by the GEMM epilogue: rows = [hi | lo]
-        VF_TRY(run_conv(h, h->convc1, h->corrfeat, CF, g8u, h->c1, 512, 2, VF_ACT_RELU, s, 256));
-        VF_TRY(run_conv(h, h->convc2, h->c1, 512, g8u, h->c2f, 512, 2, VF_ACT_RELU, s, 256));         // cols 0..191 | 256..447
-        VF_TRY(run_conv(h, h->convf1, h->flow8, 8, g8u, h->f1, 256, 2, VF_ACT_RELU, s, 128));
-        VF_TRY(run_conv(h, h->convf2, h->f1, 256, g8u, h->c2f + 192, 512, 2, VF_ACT_RELU, s, 256));   // cols 192..255 | 448..511
-        VF_TRY(run_conv(h, h->convm, h->c2f, 512, g8u, h->hx + RAFT_HX_MOTION, HX, 2, VF_ACT_RELU, s, 128));   // 512..639 | 640..767
+        VF_TRY(run_conv(h, h->convc1, h->corrfeat, CF, g8u, h->c1, 512, 2, VF_ACT_RELU, s, 256, lead));
+        VF_TRY(run_conv(h, h->convc2, h->c1, 512, g8u, h->c2f, 512, 2, VF_ACT_RELU, s, 256, lead));         // cols 0..191 | 256..447
+        VF_TRY(run_conv(h, h->convf1, h->flow8, 8, g8u, h->f1, 256, 2, VF_ACT_RELU, s, 128, lead));
+        VF_TRY(run_conv(h, h->convf2, h->f1, 256, g8u, h->c2f + 192, 512, 2, VF_ACT_RELU, s, 256, lead));   // cols 192..255 | 448..511
+        VF_TRY(run_conv(h, h->convm, h->c2f, 512, g8u, h->hx + RAFT_HX_MOTION, HX, 2, VF_ACT_RELU, s, RAFT_HX_LO, lead));   // 512..637 | 640..765
+        VF_TRY(raft_flow_fill(h->flow8, h->hx, g8u, HX, s));
+        h->launches += 1;
         for (int dir = 0; dir < 2; ++dir) {
             const ConvW& zr = dir == 0 ? h->zr1 : h->zr2;
             const ConvW& qq = dir == 0 ? h->q1 : h->q2;
-            VF_TRY(run_conv(h, zr, h->hx, HX, g8u, h->zr, 256, 1, VF_ACT_SIGMOID, s));
+            VF_TRY(run_conv(h, zr, h->hx, HX, g8u, h->zr, 256, 1, VF_ACT_SIGMOID, s, 0, lead));
             VF_TRY(raft_gru_rh(h->hx, h->h32, h->zr, h->qx, g8u, HX, s));
-            VF_TRY(run_conv(h, qq, h->qx, HX, g8u, h->qb, 128, 1, VF_ACT_TANH, s));
+            VF_TRY(run_conv(h, qq, h->qx, HX, g8u, h->qb, 128, 1, VF_ACT_TANH, s, 0, lead));
             VF_TRY(raft_gru_update(h->hx, h->h32, h->zr, h->qb, g8u, HX, s));
         }
-        VF_TRY(run_conv(h, h->fh1, h->hx, HX, g8u, h->fh, 512, 2, VF_ACT_RELU, s, 256));
-        VF_TRY(run_conv(h, h->fh2, h->fh, 512, g8u, h->delta, 8, 1, VF_ACT_NONE, s));
+        VF_TRY(run_conv(h, h->fh1, h->hx, HX, g8u, h->fh, 512, 2, VF_ACT_RELU, s, 256, lead));
+        VF_TRY(run_conv(h, h->fh2, h->fh, 512, g8u, h->delta, 8, 1, VF_ACT_NONE, s, 0, lead));
         VF_TRY(raft_coords_update(h->coords1, h->delta, h->hx, h->qx, h->flow8, g8u, HX, s));
         h->launches += 6;
     }
     // ---- mask head (once, after the last iteration)
-    VF_TRY(run_conv(h, h->mk0, h->hx, HX, g8u, h->mk, 256, 0, VF_ACT_RELU, s));
-    VF_TRY(run_conv(h, h->mk2, h->mk, 256, g8u, h->mask, 576, 1, VF_ACT_NONE, s));
+    VF_TRY(run_conv(h, h->mk0, h->hx, HX, g8u, h->mk, 256, 0, VF_ACT_RELU, s, 0, lead));
+    VF_TRY(run_conv(h, h->mk2, h->mk, 256, g8u, h->mask, 576, 1, VF_ACT_NONE, s, 0, lead));
     h->last_n = NP; h->last_H8 = H8; h->last_W8 = W8; h->corr_ld = ldc; h->P8 = P8; h->g8e = g8e; h->g8u = g8u;
     return VF_OK;
 }
@@ -616,7 +658,7 @@ int vf_raft_flow(vf_raft_t* h, const void* frames, int is_u8, int chw_layout, in
             h->corr_ld = (ldc + 3) / 4 * 4;
         }
         h->g8e = Vol2{NP, H8 + 2, W8 + 2, 1, 1 + H8, 1, 1 + W8};
-        h->g8u = Vol2{NP, H8 + 6, W8 + 6, 3, 3 + H8, 3, 3 + W8};
+        h->g8u = update_vol(NP, H8, W8);
     }
     // ---- convex upsampling, once
     if (unpad) VF_TRY(raft_upsample_flow(h->coords1, h->mask, h->g8u, NP, H8, W8, pt, pl, Hs, Ws, out, s));
@@ -657,8 +699,8 @@ int vf_raft_debug_read(vf_raft_t* h, int what, float* out, int64_t capacity, int
     if (what == 0) { Vol2 v = h->g8e; v.n = n + 1; return raft_unpack2d_f32(h->fmap32, v, 256, 0, 256, out, s); }
     if (what == 1) return raft_unpack2d_f32(h->cnet32, h->g8e, 256, 0, 256, out, s);
     if (what == 2) return raft_unpack2d(h->hx, h->g8u, HX, 0, 128, 128, out, s);                     // GRU hidden state (hi + lo)
-    if (what == 3) return raft_unpack2d(h->hx, h->g8u, HX, RAFT_HX_FLOW, 2, 2, out, s);              // low-res flow (hi + lo)
-    return raft_unpack2d(h->corrfeat, h->g8u, CF, 0, 324, 328, out, s);                               // last lookup (hi + lo)
+    if (what == 3) return raft_unpack2d(h->hx, h->g8u, HX, RAFT_HX_FLOW, 2, RAFT_HX_LO, out, s);     // low-res flow (hi + lo)
+    return raft_unpack2d(h->corrfeat, h->g8u, CF, 0, 324, RAFT_CF_LO, out, s);                               // last lookup (hi + lo)
 }
 
 int64_t vf_raft_launch_count(const vf_raft_t* h) { return h ? h->launches : 0; }

@@ -278,14 +278,13 @@ __global__ void corr_lookup_kernel(const float* __restrict__ corr, int ld, const
         const float v = (1.f - ay) * ((1.f - ax) * v00 + ax * v01) + ay * ((1.f - ax) * v10 + ax * v11);
         __half hi, lo;
         split_half(v, hi, lo);
-        o[k] = hi;            // columns [0, 324): hi part
-        o[328 + k] = lo;      // columns [328, 652): lo part (the conv weights are duplicated over both halves)
-    }
-    if (lvl == 3 && lane < 4) { o[81 + lane] = __float2half_rn(0.f); o[328 + 81 + lane] = __float2half_rn(0.f); }
+        o[k] = hi;                  // columns [0, 324): hi part
+        o[RAFT_CF_LO + k] = lo;     // columns [384, 708): lo part (the conv weights are duplicated over both halves)
+    }                               // columns 324..383 / 708..767 stay zero (the buffer is cleared once per call)
 }
 
-// Row layout of hx / qx (RAFT_HX = 776 columns, raft_kernels.h): [h_hi 0..127 | h_lo 128..255 | inp_hi 256..383 |
-// inp_lo 384..511 | motion_hi 512..639 | motion_lo 640..767 | flow 768..775 = (fx_hi, fy_hi, fx_lo, fy_lo, 0, 0, 0, 0)].
+// Row layout of hx / qx (RAFT_HX = 768 columns, raft_kernels.h): [h_hi 0..127 | h_lo 128..255 | inp_hi 256..383 |
+// inp_lo 384..511 | motion_hi 512..637, flow_hi 638..639 | motion_lo 640..765, flow_lo 766..767].
 // Every GEMM operand of the update block is carried as a split-fp16 pair (weights duplicated over the hi / lo columns):
 // RAFT's 20-step refinement amplifies operand rounding by ~400x on compressed video, so single fp16
 // operands cannot meet the 1e-3 bar.  The pairs are written by these elementwise kernels or by the GEMM epilogue's
@@ -320,12 +319,12 @@ __global__ void cnet_split_kernel(const float* __restrict__ cnet, Vol2 vi, __hal
     }
 }
 
-// qx[:, 0:256] = split(r * h) ; qx[:, 512:776] = hx[:, 512:776] (motion features + flow), valid rows.  zr = [z | r].
+// qx[:, 0:256] = split(r * h) ; qx[:, 512:768] = hx[:, 512:768] (motion features + flow), valid rows.  zr = [z | r].
 __global__ void gru_rh_kernel(const __half* __restrict__ hx, const float* __restrict__ h32, const float* __restrict__ zr,
                               __half* __restrict__ qx, Vol2 v, int ld) {
     const int H = v.h1 - v.h0, W = v.w1 - v.w0;
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    constexpr int NG = 16 + (RAFT_HX - RAFT_HX_MOTION) / 8;    // 16 groups of 8 for r*h + 33 groups for cols 512..775
+    constexpr int NG = 16 + (RAFT_HX - RAFT_HX_MOTION) / 8;    // 16 groups of 8 for r*h + 32 groups for cols 512..767
     const int64_t total = int64_t(v.n) * H * W * NG;
     if (idx >= total) return;
     const int gidx = int(idx % NG);
@@ -381,7 +380,7 @@ __global__ void gru_update_kernel(__half* __restrict__ hx, float* __restrict__ h
 }
 
 // coords1 += delta (fp32, first 2 of 8 GEMM output columns; delta == nullptr initialises coords to the grid);
-// flow = coords1 - coords0 written as a split-fp16 pair to the flow slots of hx / qx (cols 768..771) and flow8 (0..3).
+// flow = coords1 - coords0 written as a split-fp16 pair to the flow slots of hx / qx (hi pair at cols 638..639, lo pair at 766..767) and flow8 (0..3).
 __global__ void coords_update_kernel(float* __restrict__ coords1, const float* __restrict__ delta, __half* __restrict__ hx,
                                      __half* __restrict__ qx, __half* __restrict__ flow8, Vol2 v, int ld) {
     const int H = v.h1 - v.h0, W = v.w1 - v.w0;
@@ -404,9 +403,24 @@ __global__ void coords_update_kernel(float* __restrict__ coords1, const float* _
     split_half(cy - float(y), fyh, fyl);
     const uint2 packed = make_uint2(uint32_t(__half_as_ushort(fxh)) | (uint32_t(__half_as_ushort(fyh)) << 16),
                                     uint32_t(__half_as_ushort(fxl)) | (uint32_t(__half_as_ushort(fyl)) << 16));
-    *reinterpret_cast<uint2*>(hx + row * ld + RAFT_HX_FLOW) = packed;       // (fx_hi, fy_hi, fx_lo, fy_lo)
-    *reinterpret_cast<uint2*>(qx + row * ld + RAFT_HX_FLOW) = packed;
-    *reinterpret_cast<uint2*>(flow8 + row * 8) = packed;
+    *reinterpret_cast<uint32_t*>(hx + row * ld + RAFT_HX_FLOW) = packed.x;                    // (fx_hi, fy_hi)
+    *reinterpret_cast<uint32_t*>(hx + row * ld + RAFT_HX_FLOW + RAFT_HX_LO) = packed.y;       // (fx_lo, fy_lo)
+    *reinterpret_cast<uint32_t*>(qx + row * ld + RAFT_HX_FLOW) = packed.x;
+    *reinterpret_cast<uint32_t*>(qx + row * ld + RAFT_HX_FLOW + RAFT_HX_LO) = packed.y;
+    *reinterpret_cast<uint2*>(flow8 + row * 8) = packed;                                      // (fx_hi, fy_hi, fx_lo, fy_lo)
+}
+
+// flow slots of hx <- flow8 (the motion conv's 128-wide store has just cleared them)
+__global__ void flow_fill_kernel(const __half* __restrict__ flow8, __half* __restrict__ hx, Vol2 v, int ld) {
+    const int H = v.h1 - v.h0, W = v.w1 - v.w0;
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(v.n) * H * W;
+    if (idx >= total) return;
+    const int xw = int(idx % W), y = int((idx / W) % H), b = int(idx / (int64_t(W) * H));
+    const int64_t row = (int64_t(b) * v.Hp + y + v.h0) * v.Wp + xw + v.w0;
+    const uint2 packed = *reinterpret_cast<const uint2*>(flow8 + row * 8);
+    *reinterpret_cast<uint32_t*>(hx + row * ld + RAFT_HX_FLOW) = packed.x;
+    *reinterpret_cast<uint32_t*>(hx + row * ld + RAFT_HX_FLOW + RAFT_HX_LO) = packed.y;
 }
 
 // RAFT.upsample_flow (raft.py:100-111): convex combination of the 3x3 neighbourhood of 8*flow with
@@ -544,6 +558,11 @@ int raft_coords_update(float* coords1, const float* delta, __half* hx, __half* q
                        cudaStream_t s) {
     const int64_t total = int64_t(v.n) * (v.h1 - v.h0) * (v.w1 - v.w0);
     coords_update_kernel<<<nb(total, 256), 256, 0, s>>>(coords1, delta, hx, qx, flow8, v, ld);
+    LAUNCH_CHECK();
+}
+int raft_flow_fill(const __half* flow8, __half* hx, const Vol2& v, int ld, cudaStream_t s) {
+    const int64_t total = int64_t(v.n) * (v.h1 - v.h0) * (v.w1 - v.w0);
+    flow_fill_kernel<<<nb(total, 256), 256, 0, s>>>(flow8, hx, v, ld);
     LAUNCH_CHECK();
 }
 int raft_upsample_flow(const float* coords1, const float* mask, const Vol2& v, int n, int H8, int W8, int oy, int ox,

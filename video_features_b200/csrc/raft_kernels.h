@@ -6,10 +6,14 @@
 
 namespace vf {
 
-// Row layout of the GRU operand buffers hx / qx (raft_kernels.cu, cnet_split_kernel):
-//   [h_hi 0..127 | h_lo 128..255 | inp_hi 256..383 | inp_lo 384..511 | motion_hi 512..639 | motion_lo 640..767 |
-//    flow 768..775 = (fx_hi, fy_hi, fx_lo, fy_lo, 0, 0, 0, 0)]
-constexpr int RAFT_HX = 776, RAFT_HX_MOTION = 512, RAFT_HX_FLOW = 768;
+// Row layout of the GRU operand buffers hx / qx (768 columns = 12 K blocks of 64, each purely hi or purely lo):
+//   [h_hi 0..127 | h_lo 128..255 | inp_hi 256..383 | inp_lo 384..511 | motion_hi 512..637, flow_hi 638..639 |
+//    motion_lo 640..765, flow_lo 766..767]
+// (the GRU input is cat[h, inp, motion-encoder output (126), flow (2)]: the flow takes the two spare slots of the
+// 128-wide motion block; the motion conv stores only its first 126 columns.)
+constexpr int RAFT_HX = 768, RAFT_HX_MOTION = 512, RAFT_HX_FLOW = 638, RAFT_HX_LO = 128;
+// correlation features (324 = 4 levels x 81): [hi 324 + 60 zero | lo 324 + 60 zero]
+constexpr int RAFT_CF = 768, RAFT_CF_LO = 384;
 
 // zero-bordered 2-D volume [n][Hp][Wp][C]; valid region [h0,h1) x [w0,w1)
 struct Vol2 {
@@ -37,6 +41,7 @@ int raft_gru_rh(const __half* hx, const float* h32, const float* zr, __half* qx,
 int raft_gru_update(__half* hx, float* h32, const float* zr, const float* q, const Vol2& v, int ld, cudaStream_t s);
 int raft_coords_update(float* coords1, const float* delta, __half* hx, __half* qx, __half* flow8, const Vol2& v, int ld,
                        cudaStream_t s);
+int raft_flow_fill(const __half* flow8, __half* hx, const Vol2& v, int ld, cudaStream_t s);
 int raft_upsample_flow(const float* coords1, const float* mask, const Vol2& v, int n, int H8, int W8, int oy, int ox,
                        int Ho, int Wo, float* flow_up, cudaStream_t s);
 int raft_unpack2d_f32(const float* in, const Vol2& v, int ld, int c0, int cc, float* out, cudaStream_t s);
