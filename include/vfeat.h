@@ -148,6 +148,10 @@ int vf_i3d_forward_f32(vf_i3d_t* h, const float* clips, int n, int T, float* out
 /* rgb stream with the T2 transform fused (extract_i3d.py:62-66): frames n x T x Hr x Wr x 3 uint8 on the device,
  * already resized (vf_resize_u8, bilinear, short side 256) -> TensorCenterCrop(224) -> 2x/255-1 -> I3D. */
 int vf_i3d_forward_u8(vf_i3d_t* h, const uint8_t* frames, int n, int T, int Hr, int Wr, float* out, void* stream);
+/* same, stack b = frames [b * stack_stride, b * stack_stride + T) of the buffer (stack_stride >= T, in frames): the rgb
+ * stream of the reference is `stack[:-1]` of the 65-frame stacks the flow stream also reads (extract_i3d.py:150-158). */
+int vf_i3d_forward_u8_strided(vf_i3d_t* h, const uint8_t* frames, int n, int T, int64_t stack_stride, int Hr, int Wr,
+                              float* out, void* stream);
 /* flow stream with the T3 transform fused (extract_i3d.py:67-73): flow n x T x 2 x H x W fp32 on the device (the RAFT
  * output, still padded) -> crop 224 -> clamp(+-20) -> 128+255/40 f -> round -> 2x/255-1 -> I3D. */
 int vf_i3d_forward_flow(vf_i3d_t* h, const float* flow, int n, int T, int H, int W, float* out, void* stream);

@@ -38,6 +38,10 @@ CASES = [
     (6000, 768, 3072, True, False, 0, True),     # ViT fc2
     (120, 512, 768, False, False, 0, True),      # final projection (single partial pair tile)
     (20000, 768, 768, True, False, 0, True),     # many tiles per CTA pair (persistent loop, barrier phase wrap)
+    (3000, 192, 320, True, True, 2, False),      # 192-wide pair tile (I3D / RAFT channel counts), fp16 out
+    (3000, 160, 192, True, False, 0, True),      # 192-wide tile, clipped N, fp32 out
+    (40000, 384, 256, True, False, 2, False),    # two 192-wide tiles per row block, many tiles per pair
+    (700, 288, 128, False, False, 0, True),      # 288 -> 2 x 192
     (11760, 768, 3072, False, False, 0, True),   # patch embedding
 ]
 

@@ -93,7 +93,17 @@ def test_i3d_fused_stream_transforms(cuda_device):
     assert rel < 1e-3 and mx < 1e-3
     # the fused transform must equal transform-then-forward bit for bit
     assert torch.equal(y, eng(x.to(cuda_device)))
+    # a window stacks[:, :12] of longer (13-frame) stacks is read in place (the reference's rgb_stack[:-1]): same bits
+    longer = torch.cat([frames, torch.randint(0, 256, (1, 1, 256, 341, 3), dtype=torch.uint8, generator=g)], 1).to(cuda_device)
+    win = longer[:, :12]
+    assert not win.is_contiguous() or win.shape[0] == 1
+    assert torch.equal(eng.forward_frames_u8(win), y)
     eng.close()
+    eng2 = I3DEngine(sd, "rgb", 0, max_stacks=2, max_T=16)
+    two = torch.randint(0, 256, (2, 13, 256, 341, 3), dtype=torch.uint8, generator=g).to(cuda_device)
+    assert not two[:, :12].is_contiguous()
+    assert torch.equal(eng2.forward_frames_u8(two[:, :12]), eng2.forward_frames_u8(two[:, :12].contiguous()))
+    eng2.close()
     # flow: values beyond +-20, exact +-20 and half-way quantisation points
     sdf = i3d_net.synthetic_state_dict("flow", 2)
     flow = torch.randn(1, 12, 2, 256, 344, generator=g) * 12

@@ -45,7 +45,7 @@ struct GemmCfg {
     static constexpr uint32_t B_HALF = (BN / 2) * BK * 2;     // half of the B tile per CTA (one of hi / lo)
     static constexpr uint32_t B_BYTES = NSPLIT * B_HALF;
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr uint32_t TMEM_COLS = 2 * BN;             // two accumulator stages
+    static constexpr uint32_t TMEM_COLS = BN == 192 ? 512 : 2 * BN;   // two accumulator stages BN columns apart (power of 2)
     static constexpr uint32_t EPI_BUFS = NSPLIT == 2 ? 1 : 2;
     static constexpr uint32_t STG_BYTES = 2 * EPI_BUFS * SLICE_BYTES;   // 2 epilogue groups x EPI_BUFS slice buffers
     static constexpr uint32_t BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
@@ -390,10 +390,12 @@ static int run_gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const
                            int M, int N, const ConvGeom& cg, cudaStream_t stream) {
     if (cg.nsplit == 2) {
         if (bn == 256) return launch_gemm_pair<256, 4, 2>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+        if (bn == 192) return launch_gemm_pair<192, 4, 2>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
         if (bn == 128) return launch_gemm_pair<128, 6, 2>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
         return launch_gemm_pair<64, 8, 2>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
     }
     if (bn == 256) return launch_gemm_pair<256, 5, 1>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+    if (bn == 192) return launch_gemm_pair<192, 5, 1>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
     if (bn == 128) return launch_gemm_pair<128, 6, 1>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
     return launch_gemm_pair<64, 8, 1>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
 }
@@ -403,7 +405,15 @@ static int run_gemm(const CUtensorMap& tmA, const __half* B, int ldb, int64_t Kt
     if (!ep.out) return fail(VF_ERR_INVALID, "gemm: null output");
     if (N % 8) return fail(VF_ERR_INVALID, "gemm: N=%d must be a multiple of 8", N);
     if (ep.out_f32 ? (ep.ldo % 4) : (ep.ldo % 8)) return fail(VF_ERR_INVALID, "gemm: ldo breaks 16-byte rows");
-    const int bn = (N > 128) ? 256 : (N > 64) ? 128 : 64;     // pair-tile width; the B box is half of it
+    // pair-tile width (the B box is half of it): the candidate that pads N least, the widest on a tie
+    int bn = 64;
+    if (N > 64) {
+        int best = 0x7fffffff;
+        for (int cand : {256, 192, 128}) {
+            const int padded = (N + cand - 1) / cand * cand;
+            if (padded < best) { best = padded; bn = cand; }
+        }
+    }
     CUtensorMap tmB, tmO, tmO2;
     VF_TRY(make_tmap_2d(&tmB, B, 2, uint64_t(N), uint64_t(Ktot), uint64_t(ldb) * 2, uint32_t(bn / 2), BK));
     const uint64_t ncols = uint64_t(N);     // (N % 8 == 0: a store view narrower than a 16-byte multiple corrupts its neighbours)

@@ -47,7 +47,8 @@ struct ConvUnit {
 
 // kernels (i3d_kernels.cu); volumes are passed as pointers to the 10 leading ints of Vol
 int launch_i3d_phase_pack_f32(const float* x, int n, int C, int T, __half* out, int Tq, cudaStream_t s);
-int launch_i3d_phase_pack_u8(const uint8_t* frames, int n, int T, int Hr, int Wr, int cy, int cx, __half* out, int Tq,
+int launch_i3d_phase_pack_u8(const uint8_t* frames, int n, int T, int64_t stack_stride, int Hr, int Wr, int cy, int cx,
+                             __half* out, int Tq,
                              cudaStream_t s);
 int launch_i3d_phase_pack_flow(const float* flow, int n, int T, int H, int W, int cy, int cx, __half* out, int Tq,
                                cudaStream_t s);
@@ -399,7 +400,13 @@ int vf_i3d_forward_f32(vf_i3d_t* h, const float* clips, int n, int T, float* out
 }
 
 int vf_i3d_forward_u8(vf_i3d_t* h, const uint8_t* frames, int n, int T, int Hr, int Wr, float* out, void* stream) {
+    return vf_i3d_forward_u8_strided(h, frames, n, T, T, Hr, Wr, out, stream);
+}
+
+int vf_i3d_forward_u8_strided(vf_i3d_t* h, const uint8_t* frames, int n, int T, int64_t stack_stride, int Hr, int Wr,
+                              float* out, void* stream) {
     VF_TRY(i3d_check(h, frames, n, T, out, 3));
+    if (stack_stride < T) return fail(VF_ERR_INVALID, "i3d_forward_u8: stack stride %lld < T = %d", (long long)stack_stride, T);
     if (Hr < 224 || Wr < 224) return fail(VF_ERR_INVALID, "i3d_forward_u8: %dx%d frames are smaller than the 224 crop", Hr, Wr);
     if (n <= 0) return VF_OK;
     cudaStream_t user = static_cast<cudaStream_t>(stream), s = h->cs;
@@ -407,7 +414,8 @@ int vf_i3d_forward_u8(vf_i3d_t* h, const uint8_t* frames, int n, int T, int Hr, 
     const int cy = (Hr - 224) / 2, cx = (Wr - 224) / 2;     // TensorCenterCrop: floor offsets (transforms.py:14-15)
     for (int b0 = 0; b0 < n; b0 += h->max_stacks) {
         const int nb = (n - b0 < h->max_stacks) ? (n - b0) : h->max_stacks;
-        VF_TRY(launch_i3d_phase_pack_u8(frames + size_t(b0) * T * Hr * Wr * 3, nb, T, Hr, Wr, cy, cx, h->s0, T / 2 + 3, s));
+        VF_TRY(launch_i3d_phase_pack_u8(frames + size_t(b0) * stack_stride * Hr * Wr * 3, nb, T, stack_stride, Hr, Wr, cy, cx,
+                                        h->s0, T / 2 + 3, s));
         h->launches += 1;
         VF_TRY(i3d_trunk_graphed(h, nb, T, out + size_t(b0) * 1024, s));
     }

@@ -46,8 +46,9 @@ __global__ void i3d_phase_pack_f32_kernel(const float* __restrict__ x, int n, in
 // Fused T2 transform + phase packing straight from the resized uint8 frames (extract_i3d.py:62-66 rgb stream):
 // frames [n][T][Hr][Wr][3] uint8 -> TensorCenterCrop(224) at (cy,cx) -> 2*x/255 - 1 (fp32, the reference's operation
 // order) -> fp16 phase volume.  Channel order is the decoder's (the reference never swaps BGR).
-__global__ void i3d_phase_pack_u8_kernel(const uint8_t* __restrict__ frames, int n, int T, int Hr, int Wr, int cy, int cx,
-                                         __half* __restrict__ out, int Tq) {
+// stack b starts at frame b * stack_stride (>= T: a stack may be a window of a longer frame buffer).
+__global__ void i3d_phase_pack_u8_kernel(const uint8_t* __restrict__ frames, int n, int T, int64_t stack_stride, int Hr,
+                                         int Wr, int cy, int cx, __half* __restrict__ out, int Tq) {
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t total = int64_t(n) * Tq * 115 * 115;
     if (idx >= total) return;
@@ -64,7 +65,7 @@ __global__ void i3d_phase_pack_u8_kernel(const uint8_t* __restrict__ frames, int
         for (int ph = 0; ph < 2; ++ph) {
             const int hh = 2 * (hq - 1) + ph;
             const bool ok = (t >= 0) && (t < T) && (hh >= 0) && (hh < 224) && (w0 >= 0) && (w0 < 224);
-            const uint8_t* p = frames + (((int64_t(b) * T + (ok ? t : 0)) * Hr + cy + (ok ? hh : 0)) * Wr + cx + (ok ? w0 : 0)) * 3;
+            const uint8_t* p = frames + (((int64_t(b) * stack_stride + (ok ? t : 0)) * Hr + cy + (ok ? hh : 0)) * Wr + cx + (ok ? w0 : 0)) * 3;
 #pragma unroll
             for (int pw = 0; pw < 2; ++pw)
 #pragma unroll
@@ -175,6 +176,54 @@ __global__ void maxpool3d_kernel(const __half* __restrict__ in, DVol vi, __half*
     *reinterpret_cast<uint4*>(out + pos * C + c8 * 8) = o;
 }
 
+// The Mixed blocks' branch-3 pool: 3x3x3, stride 1, zero padding 1, same volume geometry in and out (border >= 1 of
+// zeros all around, which IS the padding: no bounds checks).  One thread = (clip, t, w, 8 channels) marching down h: per
+// step it folds the 3 (t) x 3 (w) neighbours of one input row into a row maximum (9 coalesced 16-byte loads) and emits
+// the maximum of the last three row maxima -- 9 loads per output instead of 27.  Border positions are written as zeros.
+__global__ void maxpool3d_same3_kernel(const __half* __restrict__ in, DVol v, __half* __restrict__ out, int C) {
+    const int cg = C >> 3;
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(v.n) * v.Tp * v.Wp * cg;
+    if (idx >= total) return;
+    const int c8 = int(idx % cg);
+    const int w = int((idx / cg) % v.Wp);
+    const int t = int((idx / (int64_t(cg) * v.Wp)) % v.Tp);
+    const int b = int(idx / (int64_t(cg) * v.Wp * v.Tp));
+    const int64_t plane = int64_t(v.Hp) * v.Wp * C, rowp = int64_t(v.Wp) * C;
+    const int64_t base = (int64_t(b) * v.Tp + t) * plane + int64_t(w) * C + c8 * 8;     // (b, t, h = 0, w)
+    const uint4 z4 = make_uint4(0, 0, 0, 0);
+    if (t < v.t0 || t >= v.t1 || w < v.w0 || w >= v.w1) {
+        for (int hh = 0; hh < v.Hp; ++hh) *reinterpret_cast<uint4*>(out + base + hh * rowp) = z4;
+        return;
+    }
+    const __half2 zero = __float2half2_rn(0.f);
+    auto row_max = [&](int hh, __half2* m) {          // max over (t-1..t+1, w-1..w+1) of input row hh
+        m[0] = m[1] = m[2] = m[3] = zero;
+#pragma unroll
+        for (int dt = -1; dt <= 1; ++dt)
+#pragma unroll
+            for (int dw = -1; dw <= 1; ++dw) {
+                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(in + base + dt * plane + hh * rowp + dw * C));
+                const __half2* x = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) m[j] = __hmax2(m[j], x[j]);
+            }
+    };
+    __half2 r0[4], r1[4], r2[4];
+    for (int hh = 0; hh < v.h0; ++hh) *reinterpret_cast<uint4*>(out + base + hh * rowp) = z4;
+    row_max(v.h0 - 1, r0);
+    row_max(v.h0, r1);
+    for (int hh = v.h0; hh < v.h1; ++hh) {
+        row_max(hh + 1, r2);
+        uint4 o;
+        __half2* po = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { po[j] = __hmax2(__hmax2(r0[j], r1[j]), r2[j]); r0[j] = r1[j]; r1[j] = r2[j]; }
+        *reinterpret_cast<uint4*>(out + base + hh * rowp) = o;
+    }
+    for (int hh = v.h1; hh < v.Hp; ++hh) *reinterpret_cast<uint4*>(out + base + hh * rowp) = z4;
+}
+
 // AvgPool3d((2,7,7), stride 1) on a T3 x 7 x 7 map -> (T3-1) x 1 x 1, squeeze, mean over time (i3d_net.py:258-264):
 // feature[c] = 1/(T3-1) * sum_{t'} 1/98 * sum_{dt<2,h,w} x[t'+dt][h][w][c].   One block per clip, thread = channel.
 __global__ void i3d_head_kernel(const __half* __restrict__ in, DVol v, int C, float* __restrict__ out) {
@@ -229,10 +278,10 @@ int launch_i3d_phase_pack_f32(const float* x, int n, int C, int T, __half* out, 
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
-int launch_i3d_phase_pack_u8(const uint8_t* frames, int n, int T, int Hr, int Wr, int cy, int cx, __half* out, int Tq,
-                             cudaStream_t s) {
+int launch_i3d_phase_pack_u8(const uint8_t* frames, int n, int T, int64_t stack_stride, int Hr, int Wr, int cy, int cx,
+                             __half* out, int Tq, cudaStream_t s) {
     const int64_t total = int64_t(n) * Tq * 115 * 115;
-    i3d_phase_pack_u8_kernel<<<nblocks(total, 256), 256, 0, s>>>(frames, n, T, Hr, Wr, cy, cx, out, Tq);
+    i3d_phase_pack_u8_kernel<<<nblocks(total, 256), 256, 0, s>>>(frames, n, T, stack_stride, Hr, Wr, cy, cx, out, Tq);
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
@@ -247,6 +296,15 @@ int launch_maxpool3d_raw(const __half* in, const void* vi, __half* out, const vo
                          int st, int sh, int sw, int pt, int ph, int pw, cudaStream_t s) {
     if (C % 8) return fail(VF_ERR_INVALID, "maxpool3d: C=%d must be a multiple of 8", C);
     const DVol a = to_dev(vi), b = to_dev(vo);
+    const bool same_geom = a.n == b.n && a.Tp == b.Tp && a.Hp == b.Hp && a.Wp == b.Wp && a.t0 == b.t0 && a.t1 == b.t1 &&
+                           a.h0 == b.h0 && a.h1 == b.h1 && a.w0 == b.w0 && a.w1 == b.w1;
+    if (same_geom && kt == 3 && kh == 3 && kw == 3 && st == 1 && sh == 1 && sw == 1 && pt == 1 && ph == 1 && pw == 1 &&
+        a.t0 >= 1 && a.h0 >= 1 && a.w0 >= 1 && a.t1 < a.Tp && a.h1 < a.Hp && a.w1 < a.Wp) {
+        const int64_t threads = int64_t(a.n) * a.Tp * a.Wp * (C / 8);
+        maxpool3d_same3_kernel<<<nblocks(threads, 128), 128, 0, s>>>(in, a, out, C);
+        VF_CUDA(cudaGetLastError());
+        return VF_OK;
+    }
     const int64_t total = int64_t(b.n) * b.Tp * b.Hp * b.Wp * (C / 8);
     maxpool3d_kernel<<<nblocks(total, 256), 256, 0, s>>>(in, a, out, b, C, kt, kh, kw, st, sh, sw, pt, ph, pw);
     VF_CUDA(cudaGetLastError());

@@ -75,12 +75,18 @@ class I3DEngine:
     def forward_frames_u8(self, frames: torch.Tensor) -> torch.Tensor:
         """rgb stream from resized uint8 frames (n, T, Hr, Wr, 3) on this device; crop/scale/permute fused."""
         assert frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 5 and frames.shape[4] == 3
-        frames = frames.contiguous()
         n, T, Hr, Wr, _ = frames.shape
+        fsz = Hr * Wr * 3
+        # a window `stacks[:, :T]` of longer stacks (the reference's rgb_stack[:-1]) is read in place
+        windowed = (n > 0 and frames.stride()[1:] == (fsz, Wr * 3, 3, 1) and frames.stride(0) % fsz == 0
+                    and frames.stride(0) >= T * fsz)
+        if not windowed:
+            frames = frames.contiguous()
+        stride = frames.stride(0) // fsz if n > 0 else T
         out = torch.empty((n, 1024), device=frames.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
-            check(lib().vf_i3d_forward_u8(self._h, frames.data_ptr(), n, T, Hr, Wr, out.data_ptr(),
-                                          torch.cuda.current_stream().cuda_stream))
+            check(lib().vf_i3d_forward_u8_strided(self._h, frames.data_ptr(), n, T, stride, Hr, Wr, out.data_ptr(),
+                                                  torch.cuda.current_stream().cuda_stream))
         return out
 
     def forward_flow(self, flow: torch.Tensor) -> torch.Tensor:
