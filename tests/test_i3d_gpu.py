@@ -65,13 +65,13 @@ def test_i3d_reference_checkpoint_vs_oracle_and_golden(cuda_device, modality):
         ref = torch.from_numpy(gold[f"{modality}_T{T}"])          # the reference module's own output (fixture)
         rel, mx = _rel(y, ref)
         print(f"{modality} real weights T={T}: rel-L2 {rel:.3e} max {mx:.3e}")
-        assert rel < 1e-3 and mx < 1.5e-3
+        assert rel < 6e-4 and mx < 1e-3          # measured 1.9e-4 .. 4.0e-4 / 2.6e-4 .. 4.7e-4 (pair tensors)
     x = torch.rand(1, cin, 64, 224, 224, generator=torch.Generator().manual_seed(5)) * 2 - 1
     y = eng(x.to(cuda_device))
     ref = _oracle_gpu(sd, x, cuda_device)
     rel, mx = _rel(y, ref)
     print(f"{modality} real weights T=64: rel-L2 {rel:.3e} max {mx:.3e}")
-    assert rel < 1e-3
+    assert rel < 6e-4 and mx < 1e-3
     eng.close()
 
 

@@ -41,6 +41,7 @@ struct ConvUnit {
     int cout = 0, cin = 0, k = 0;     // k: 1, 3, or 7 (the stem)
     int ntaps = 0, k_per_tap = 0;     // base tap geometry (before the hi/lo split)
     int nsplit = 1;
+    unsigned long long lo_mask = 0;   // K blocks that meet only lo halves of a pair input (ConvGeom::lo_mask)
     __half* w = nullptr;              // [cout, nsplit * ntaps * k_per_tap]
     float *scale = nullptr, *bias = nullptr;
 };
@@ -55,7 +56,7 @@ int launch_i3d_phase_pack_flow(const float* flow, int n, int T, int H, int W, in
 int launch_maxpool3d_raw(const __half* in, const void* vi, __half* out, const void* vo, int C, int kt, int kh, int kw,
                          int st, int sh, int sw, int pt, int ph, int pw, cudaStream_t s);
 int launch_i3d_head_raw(const __half* in, const void* vi, int C, float* out, cudaStream_t s);
-int launch_unpack_ndhwc_raw(const __half* in, const void* vi, int C, int c_off, int c_cnt, int ld, float* out,
+int launch_unpack_ndhwc_raw(const __half* in, const void* vi, int C, int c_off, int c_cnt, int ld, int lo_off, float* out,
                             cudaStream_t s);
 static int launch_maxpool3d(const __half* in, const Vol& vi, __half* out, const Vol& vo, int C, int kt, int kh, int kw,
                             int st, int sh, int sw, int pt, int ph, int pw, cudaStream_t s) {
@@ -64,9 +65,9 @@ static int launch_maxpool3d(const __half* in, const Vol& vi, __half* out, const 
 static int launch_i3d_head(const __half* in, const Vol& vi, int C, float* out, cudaStream_t s) {
     return launch_i3d_head_raw(in, &vi, C, out, s);
 }
-static int launch_unpack_ndhwc(const __half* in, const Vol& vi, int C, int c_off, int c_cnt, int ld, float* out,
+static int launch_unpack_ndhwc(const __half* in, const Vol& vi, int C, int c_off, int c_cnt, int ld, int lo_off, float* out,
                                cudaStream_t s) {
-    return launch_unpack_ndhwc_raw(in, &vi, C, c_off, c_cnt, ld, out, s);
+    return launch_unpack_ndhwc_raw(in, &vi, C, c_off, c_cnt, ld, lo_off, out, s);
 }
 
 }  // namespace vf
@@ -119,8 +120,15 @@ static int prepare_unit(vf_i3d* h, ConvUnit& u, const vf_conv_unit& src, int idx
     const int co = u.cout, ci = u.cin, k = u.k;
     std::vector<float> wt;   // [co][ntaps*k_per_tap]
     if (k == 1) {
-        u.ntaps = 1; u.k_per_tap = ci;
-        wt.assign(src.w, src.w + size_t(co) * ci);
+        // every 1x1x1 conv reads a pair tensor, rows [hi ci | lo ci]: the filter is laid over both halves, and K blocks
+        // that fall entirely into the lo half skip the W_lo pass
+        u.ntaps = 1; u.k_per_tap = 2 * ci;
+        wt.resize(size_t(co) * 2 * ci);
+        for (int o = 0; o < co; ++o)
+            for (int c = 0; c < ci; ++c) wt[size_t(o) * 2 * ci + c] = wt[size_t(o) * 2 * ci + ci + c] = src.w[size_t(o) * ci + c];
+        const int kb = (2 * ci + 63) / 64;
+        for (int kk = 0; kk < kb && kk < 64; ++kk)
+            if (kk * 64 >= ci) u.lo_mask |= 1ull << kk;
     } else if (k == 3) {
         u.ntaps = 9; u.k_per_tap = 3 * ci;
         wt.resize(size_t(co) * 27 * ci);
@@ -133,10 +141,12 @@ static int prepare_unit(vf_i3d* h, ConvUnit& u, const vf_conv_unit& src, int idx
                                 src.w[(((size_t(o) * ci + c) * 3 + kt) * 3 + kh) * 3 + kw];
     } else if (k == 7) {
         // stride-2 7x7x7 with TF-SAME padding (2 before, 3 after) == 4x4x4 stride-1 over the 8 phases:
-        // filter index kk = 2*a + p for tap a in 0..3 (row offset a-1) and phase p in 0..1; kk == 7 does not exist
+        // filter index kk = 2*a + p for tap a in 0..3 (row offset a-1) and phase p in 0..1; kk == 7 does not exist.
+        // The phase volume carries the 4 h-taps inside each row (slot b = source row h + b - 1, i3d_kernels.cu), so the
+        // GEMM taps are the 4 t-taps, each a run of 4 w-positions x (4 slots x 8 phases x ci) channels.
         const int pc = 8 * ci;
-        u.ntaps = 16; u.k_per_tap = 4 * pc;
-        wt.assign(size_t(co) * 16 * 4 * pc, 0.f);
+        u.ntaps = 4; u.k_per_tap = 16 * pc;
+        wt.assign(size_t(co) * 4 * 16 * pc, 0.f);
         for (int o = 0; o < co; ++o)
             for (int c = 0; c < ci; ++c)
                 for (int a = 0; a < 4; ++a) for (int pt = 0; pt < 2; ++pt) {
@@ -145,7 +155,7 @@ static int prepare_unit(vf_i3d* h, ConvUnit& u, const vf_conv_unit& src, int idx
                         const int kh = 2 * b + ph; if (kh > 6) continue;
                         for (int cw = 0; cw < 4; ++cw) for (int pw = 0; pw < 2; ++pw) {
                             const int kw = 2 * cw + pw; if (kw > 6) continue;
-                            wt[(size_t(o) * 16 + a * 4 + b) * (4 * pc) + cw * pc + ((pt * 2 + ph) * 2 + pw) * ci + c] =
+                            wt[(size_t(o) * 4 + a) * (16 * pc) + cw * (4 * pc) + b * pc + ((pt * 2 + ph) * 2 + pw) * ci + c] =
                                 src.w[(((size_t(o) * ci + c) * 7 + kt) * 7 + kh) * 7 + kw];
                         }
                     }
@@ -160,6 +170,7 @@ static int prepare_unit(vf_i3d* h, ConvUnit& u, const vf_conv_unit& src, int idx
     {
         const char* e = getenv("VF_I3D_STEM_SINGLE");
         u.nsplit = (k == 7 && e && e[0] == '1') ? 1 : h->nsplit;
+        if (u.nsplit != 2) u.lo_mask = 0;
     }
     const size_t Kb = size_t(u.ntaps) * u.k_per_tap, Kt = Kb * u.nsplit;
     std::vector<__half> wh(size_t(co) * Kt);
@@ -186,18 +197,20 @@ static int prepare_unit(vf_i3d* h, ConvUnit& u, const vf_conv_unit& src, int idx
 }
 
 // conv + BN + ReLU of one unit over a bordered volume; out rows keep the input's row indexing
+// split_off > 0: the output is a pair tensor, hi at column n and lo at column split_off + n of the rows at `out`
 static int run_unit(vf_i3d* h, const ConvUnit& u, const __half* X, int ldx_channels, const Vol& v, __half* out, int ldo,
-                    cudaStream_t s) {
+                    cudaStream_t s, int split_off = 0) {
     ConvGeom g;
     memset(&g, 0, sizeof(g));
     g.k_per_tap = u.k_per_tap;
     g.ntaps = u.ntaps;
     g.nsplit = u.nsplit;          // hi/lo weight passes share each A tile inside the kernel
+    g.lo_mask = u.lo_mask;
     const int hw = v.Hp * v.Wp;
     for (int j = 0; j < u.ntaps; ++j) {
         int off = 0;
         if (u.k == 3) off = (j / 3 - 1) * hw + (j % 3 - 1) * v.Wp - 1;
-        else if (u.k == 7) off = (j / 4 - 1) * hw + (j % 4 - 1) * v.Wp - 1;
+        else if (u.k == 7) off = (j - 1) * hw - 1;        // t-taps only: the h-taps live inside the row
         g.tap_off[j] = off;
     }
     g.mask = 1;
@@ -206,22 +219,24 @@ static int run_unit(vf_i3d* h, const ConvUnit& u, const __half* X, int ldx_chann
     GemmEpi ep;
     memset(&ep, 0, sizeof(ep));
     ep.out = out; ep.ldo = ldo; ep.out_f32 = 0; ep.bias = u.bias; ep.scale = u.scale; ep.act = VF_ACT_RELU;
+    ep.split_off = split_off;
     h->launches += 1;
     return conv_gemm_f16(X, ldx_channels, v.rows(), u.w, u.cout, g, ep, s);
 }
 
+// x and out are pair tensors (rows [hi C | lo C]); the 1x1x1 reducers' outputs t1 / t2 feed 3x3x3 convs and are single fp16
 static int mixed_block(vf_i3d* h, int m, const __half* x, const Vol& v, __half* out, cudaStream_t s) {
     const int* c = kMixed[m];
     const ConvUnit* u = &h->units[3 + 6 * m];
     const int cin = c[0], ctot = c[1] + c[3] + c[5] + c[6];
-    VF_TRY(run_unit(h, u[0], x, cin, v, out, ctot, s));                                   // branch_0
-    VF_TRY(run_unit(h, u[1], x, cin, v, h->t1, c[2], s));                                 // branch_1.0
-    VF_TRY(run_unit(h, u[2], h->t1, c[2], v, out + c[1], ctot, s));                       // branch_1.1 (3x3x3)
-    VF_TRY(run_unit(h, u[3], x, cin, v, h->t2, c[4], s));                                 // branch_2.0
-    VF_TRY(run_unit(h, u[4], h->t2, c[4], v, out + c[1] + c[3], ctot, s));                // branch_2.1 (3x3x3)
-    VF_TRY(launch_maxpool3d(x, v, h->tp, v, cin, 3, 3, 3, 1, 1, 1, 1, 1, 1, s));          // branch_3 pool (zero pad)
+    VF_TRY(run_unit(h, u[0], x, 2 * cin, v, out, 2 * ctot, s, ctot));                              // branch_0
+    VF_TRY(run_unit(h, u[1], x, 2 * cin, v, h->t1, c[2], s));                                      // branch_1.0
+    VF_TRY(run_unit(h, u[2], h->t1, c[2], v, out + c[1], 2 * ctot, s, ctot));                      // branch_1.1 (3x3x3)
+    VF_TRY(run_unit(h, u[3], x, 2 * cin, v, h->t2, c[4], s));                                      // branch_2.0
+    VF_TRY(run_unit(h, u[4], h->t2, c[4], v, out + c[1] + c[3], 2 * ctot, s, ctot));               // branch_2.1 (3x3x3)
+    VF_TRY(launch_maxpool3d(x, v, h->tp, v, cin, 3, 3, 3, 1, 1, 1, 1, 1, 1, s));                   // branch_3 pool (zero pad)
     h->launches += 1;
-    VF_TRY(run_unit(h, u[5], h->tp, cin, v, out + c[1] + c[3] + c[5], ctot, s));          // branch_3.1
+    VF_TRY(run_unit(h, u[5], h->tp, 2 * cin, v, out + c[1] + c[3] + c[5], 2 * ctot, s, ctot));     // branch_3.1
     return VF_OK;
 }
 
@@ -253,18 +268,18 @@ int vf_i3d_create(vf_i3d_t** out, const vf_i3d_weights* w, int in_channels, int 
         const size_t n = size_t(max_stacks);
         const int T1 = max_T / 2, Tq = T1 + 3;       // stem: floor((T + 5 - 7) / 2) + 1 = T / 2
         const size_t rows0 = n * Tq * 115 * 115;
-        VF_TRY(i3d_alloc(h, &h->s0, rows0 * 8 * in_channels + 4096));
-        VF_TRY(i3d_alloc(h, &h->a1, rows0 * 64));
+        VF_TRY(i3d_alloc(h, &h->s0, rows0 * 32 * in_channels + 4096));
+        VF_TRY(i3d_alloc(h, &h->a1, rows0 * 128));          // pair tensors: 2 x channels
         const size_t rows1 = n * (T1 + 2) * 58 * 58;
-        VF_TRY(i3d_alloc(h, &h->p1, rows1 * 64));
+        VF_TRY(i3d_alloc(h, &h->p1, rows1 * 128));
         VF_TRY(i3d_alloc(h, &h->c2b, rows1 * 64));
-        VF_TRY(i3d_alloc(h, &h->c2c, rows1 * 192));
+        VF_TRY(i3d_alloc(h, &h->c2c, rows1 * 384));
         const size_t rows2 = n * (T1 + 2) * 30 * 30;    // largest Mixed stage
-        VF_TRY(i3d_alloc(h, &h->bufA, rows2 * 1024));
-        VF_TRY(i3d_alloc(h, &h->bufB, rows2 * 1024));
+        VF_TRY(i3d_alloc(h, &h->bufA, rows2 * 2048));
+        VF_TRY(i3d_alloc(h, &h->bufB, rows2 * 2048));
         VF_TRY(i3d_alloc(h, &h->t1, rows2 * 192));
         VF_TRY(i3d_alloc(h, &h->t2, rows2 * 64));
-        VF_TRY(i3d_alloc(h, &h->tp, rows2 * 832));
+        VF_TRY(i3d_alloc(h, &h->tp, rows2 * 1664));
         h->cap_rows2 = rows2;
         VF_TRY(i3d_alloc(h, &h->feat, n * 1024));
         VF_CUDA(cudaStreamCreateWithFlags(&h->cs, cudaStreamNonBlocking));
@@ -301,12 +316,12 @@ int vf_i3d_destroy(vf_i3d_t* h) {
 static int i3d_trunk(vf_i3d* h, int nb, int T, float* out, cudaStream_t s) {
     const int T1 = T / 2, Tq = T1 + 3;            // torch conv3d, pad (2,3), stride 2: floor((T-2)/2)+1
     const Vol v0{nb, Tq, 115, 115, 1, 1 + T1, 1, 113, 1, 113};
-    VF_TRY(run_unit(h, h->units[0], h->s0, 8 * h->cin, v0, h->a1, 64, s));
+    VF_TRY(run_unit(h, h->units[0], h->s0, 32 * h->cin, v0, h->a1, 128, s, 64));       // a1: pair tensor
     // ---- maxPool3d_2a (1,3,3)/(1,2,2), SAME pad (0,1) on H,W
     const Vol v1 = bordered(nb, T1, 56, 56);
     VF_TRY(launch_maxpool3d(h->a1, v0, h->p1, v1, 64, 1, 3, 3, 1, 2, 2, 0, 0, 0, s));
-    VF_TRY(run_unit(h, h->units[1], h->p1, 64, v1, h->c2b, 64, s));
-    VF_TRY(run_unit(h, h->units[2], h->c2b, 64, v1, h->c2c, 192, s));
+    VF_TRY(run_unit(h, h->units[1], h->p1, 128, v1, h->c2b, 64, s));                   // pair in, single out
+    VF_TRY(run_unit(h, h->units[2], h->c2b, 64, v1, h->c2c, 384, s, 192));             // single in, pair out
     // ---- maxPool3d_3a
     const Vol v2 = bordered(nb, T1, 28, 28);
     VF_TRY(launch_maxpool3d(h->c2c, v1, h->bufA, v2, 192, 1, 3, 3, 1, 2, 2, 0, 0, 0, s));
@@ -448,7 +463,7 @@ int vf_i3d_read_stage(vf_i3d_t* h, int stage, float* out, int64_t capacity, int*
     if (capacity < need) return fail(VF_ERR_INVALID, "i3d_read_stage: capacity %lld < %lld", (long long)capacity, (long long)need);
     cudaStream_t user = static_cast<cudaStream_t>(stream);
     VF_TRY(i3d_enter(h, user));
-    VF_TRY(launch_unpack_ndhwc(r.p, r.v, r.C, 0, r.C, r.C, out, h->cs));
+    VF_TRY(launch_unpack_ndhwc(r.p, r.v, r.C, 0, r.C, 2 * r.C, r.C, out, h->cs));      // retained stages are pair tensors
     return i3d_leave(h, user);
 }
 

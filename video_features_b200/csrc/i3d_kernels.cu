@@ -13,9 +13,15 @@ namespace {
 
 inline unsigned nblocks(int64_t total, int threads) { return unsigned((total + threads - 1) / threads); }
 
+// Stem operand layout ("phase volume", all three pack kernels): the stride-2 7x7x7 stem is a stride-1 4x4x4 conv over the
+// 8 space-time phases.  Row (tq, hq, wq) of the volume [n][Tq][115][115] holds FOUR phase vectors, those of the source
+// rows hq-1 .. hq+2 (slot sb = source row hq + sb - 1), each 8*C channels:
+//   out[tq][hq][wq][sb*8C + ((pt*2+ph)*2+pw)*C + c] = x[c][2(tq-1)+pt][2(hq+sb-2)+ph][2(wq-1)+pw]   (zero outside the clip)
+// i.e. the 4 h-taps are pre-gathered into the row, so the GEMM needs only the 4 t-taps (each a run of 4 w-positions x
+// 32*C channels): 3 KB of A operand per output row instead of 16 unaligned 192-byte runs -- the stem was bound by L2
+// operand traffic (ncu: 22.5 GB through L2, tensor pipe 31 %).
+//
 // x: [n][C][T][224][224] fp32 (already cropped + scaled to [-1,1], what the reference feeds I3D)
-// out: [n][Tq][115][115][8*C] fp16 with out[tq][hq][wq][((pt*2+ph)*2+pw)*C + c] = x[c][2(tq-1)+pt][2(hq-1)+ph][2(wq-1)+pw]
-// (zero outside the clip): the 8 space-time phases of the stride-2 stem as channels, origin shifted by one.
 __global__ void i3d_phase_pack_f32_kernel(const float* __restrict__ x, int n, int C, int T, __half* __restrict__ out,
                                           int Tq) {
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -25,19 +31,22 @@ __global__ void i3d_phase_pack_f32_kernel(const float* __restrict__ x, int n, in
     const int hq = int((idx / 115) % 115);
     const int tq = int((idx / (115 * 115)) % Tq);
     const int b = int(idx / (int64_t(115) * 115 * Tq));
-    __half* o = out + idx * (8 * C);
     const int w0 = 2 * (wq - 1);
-    for (int pt = 0; pt < 2; ++pt) {
-        const int t = 2 * (tq - 1) + pt;
-        for (int ph = 0; ph < 2; ++ph) {
-            const int hh = 2 * (hq - 1) + ph;
-            const bool ok = (t >= 0) && (t < T) && (hh >= 0) && (hh < 224) && (w0 >= 0) && (w0 < 224);
-            for (int c = 0; c < C; ++c) {
-                float2 v = make_float2(0.f, 0.f);
-                if (ok) v = __ldg(reinterpret_cast<const float2*>(
-                            x + (((int64_t(b) * C + c) * T + t) * 224 + hh) * 224 + w0));
-                o[((pt * 2 + ph) * 2 + 0) * C + c] = __float2half_rn(v.x);
-                o[((pt * 2 + ph) * 2 + 1) * C + c] = __float2half_rn(v.y);
+    for (int sb = 0; sb < 4; ++sb) {
+        __half* o = out + idx * (32 * C) + sb * (8 * C);
+        const int hs = hq + sb - 1;
+        for (int pt = 0; pt < 2; ++pt) {
+            const int t = 2 * (tq - 1) + pt;
+            for (int ph = 0; ph < 2; ++ph) {
+                const int hh = 2 * (hs - 1) + ph;
+                const bool ok = (t >= 0) && (t < T) && (hh >= 0) && (hh < 224) && (w0 >= 0) && (w0 < 224);
+                for (int c = 0; c < C; ++c) {
+                    float2 v = make_float2(0.f, 0.f);
+                    if (ok) v = __ldg(reinterpret_cast<const float2*>(
+                                x + (((int64_t(b) * C + c) * T + t) * 224 + hh) * 224 + w0));
+                    o[((pt * 2 + ph) * 2 + 0) * C + c] = __float2half_rn(v.x);
+                    o[((pt * 2 + ph) * 2 + 1) * C + c] = __float2half_rn(v.y);
+                }
             }
         }
     }
@@ -56,29 +65,33 @@ __global__ void i3d_phase_pack_u8_kernel(const uint8_t* __restrict__ frames, int
     const int hq = int((idx / 115) % 115);
     const int tq = int((idx / (115 * 115)) % Tq);
     const int b = int(idx / (int64_t(115) * 115 * Tq));
-    __align__(16) __half vals[24];
     const int w0 = 2 * (wq - 1);
+#pragma unroll 1
+    for (int sb = 0; sb < 4; ++sb) {
+        __align__(16) __half vals[24];
+        const int hs = hq + sb - 1;
 #pragma unroll
-    for (int pt = 0; pt < 2; ++pt) {
-        const int t = 2 * (tq - 1) + pt;
+        for (int pt = 0; pt < 2; ++pt) {
+            const int t = 2 * (tq - 1) + pt;
 #pragma unroll
-        for (int ph = 0; ph < 2; ++ph) {
-            const int hh = 2 * (hq - 1) + ph;
-            const bool ok = (t >= 0) && (t < T) && (hh >= 0) && (hh < 224) && (w0 >= 0) && (w0 < 224);
-            const uint8_t* p = frames + (((int64_t(b) * stack_stride + (ok ? t : 0)) * Hr + cy + (ok ? hh : 0)) * Wr + cx + (ok ? w0 : 0)) * 3;
+            for (int ph = 0; ph < 2; ++ph) {
+                const int hh = 2 * (hs - 1) + ph;
+                const bool ok = (t >= 0) && (t < T) && (hh >= 0) && (hh < 224) && (w0 >= 0) && (w0 < 224);
+                const uint8_t* p = frames + (((int64_t(b) * stack_stride + (ok ? t : 0)) * Hr + cy + (ok ? hh : 0)) * Wr + cx + (ok ? w0 : 0)) * 3;
 #pragma unroll
-            for (int pw = 0; pw < 2; ++pw)
+                for (int pw = 0; pw < 2; ++pw)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    float v = 0.f;
-                    if (ok) v = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, float(__ldg(p + pw * 3 + c))), 255.0f), 1.0f);
-                    vals[((pt * 2 + ph) * 2 + pw) * 3 + c] = __float2half_rn(v);
-                }
+                    for (int c = 0; c < 3; ++c) {
+                        float v = 0.f;
+                        if (ok) v = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, float(__ldg(p + pw * 3 + c))), 255.0f), 1.0f);
+                        vals[((pt * 2 + ph) * 2 + pw) * 3 + c] = __float2half_rn(v);
+                    }
+            }
         }
+        uint4* o = reinterpret_cast<uint4*>(out + idx * 96 + sb * 24);
+        const uint4* v4 = reinterpret_cast<const uint4*>(vals);
+        o[0] = v4[0]; o[1] = v4[1]; o[2] = v4[2];
     }
-    uint4* o = reinterpret_cast<uint4*>(out + idx * 24);
-    const uint4* v4 = reinterpret_cast<const uint4*>(vals);
-    o[0] = v4[0]; o[1] = v4[1]; o[2] = v4[2];
 }
 
 // Fused T3 transform + phase packing for the flow stream (extract_i3d.py:67-73): flow [n][T][2][H][W] fp32 (the RAFT
@@ -93,44 +106,74 @@ __global__ void i3d_phase_pack_flow_kernel(const float* __restrict__ flow, int n
     const int hq = int((idx / 115) % 115);
     const int tq = int((idx / (115 * 115)) % Tq);
     const int b = int(idx / (int64_t(115) * 115 * Tq));
-    __align__(16) __half vals[16];
     const int w0 = 2 * (wq - 1);
+#pragma unroll 1
+    for (int sb = 0; sb < 4; ++sb) {
+        __align__(16) __half vals[16];
+        const int hs = hq + sb - 1;
 #pragma unroll
-    for (int pt = 0; pt < 2; ++pt) {
-        const int t = 2 * (tq - 1) + pt;
+        for (int pt = 0; pt < 2; ++pt) {
+            const int t = 2 * (tq - 1) + pt;
 #pragma unroll
-        for (int ph = 0; ph < 2; ++ph) {
-            const int hh = 2 * (hq - 1) + ph;
-            const bool ok = (t >= 0) && (t < T) && (hh >= 0) && (hh < 224) && (w0 >= 0) && (w0 < 224);
+            for (int ph = 0; ph < 2; ++ph) {
+                const int hh = 2 * (hs - 1) + ph;
+                const bool ok = (t >= 0) && (t < T) && (hh >= 0) && (hh < 224) && (w0 >= 0) && (w0 < 224);
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                float2 f = make_float2(0.f, 0.f);
-                bool live = ok;
-                if (ok) {
-                    const float* p = flow + (((int64_t(b) * T + t) * 2 + c) * H + cy + hh) * W + cx + w0;
-                    f.x = __ldg(p); f.y = __ldg(p + 1);
-                }
-#pragma unroll
-                for (int pw = 0; pw < 2; ++pw) {
-                    float v = pw ? f.y : f.x;
-                    if (live) {
-                        v = fminf(fmaxf(v, -20.0f), 20.0f);
-                        v = rintf(__fadd_rn(128.0f, __fmul_rn(6.375f, v)));
-                        v = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, v), 255.0f), 1.0f);
+                for (int c = 0; c < 2; ++c) {
+                    float2 f = make_float2(0.f, 0.f);
+                    if (ok) {
+                        const float* p = flow + (((int64_t(b) * T + t) * 2 + c) * H + cy + hh) * W + cx + w0;
+                        f.x = __ldg(p); f.y = __ldg(p + 1);
                     }
-                    vals[((pt * 2 + ph) * 2 + pw) * 2 + c] = __float2half_rn(v);
+#pragma unroll
+                    for (int pw = 0; pw < 2; ++pw) {
+                        float v = pw ? f.y : f.x;
+                        if (ok) {
+                            v = fminf(fmaxf(v, -20.0f), 20.0f);
+                            v = rintf(__fadd_rn(128.0f, __fmul_rn(6.375f, v)));
+                            v = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, v), 255.0f), 1.0f);
+                        }
+                        vals[((pt * 2 + ph) * 2 + pw) * 2 + c] = __float2half_rn(v);
+                    }
                 }
             }
         }
+        uint4* o = reinterpret_cast<uint4*>(out + idx * 64 + sb * 16);
+        const uint4* v4 = reinterpret_cast<const uint4*>(vals);
+        o[0] = v4[0]; o[1] = v4[1];
     }
-    uint4* o = reinterpret_cast<uint4*>(out + idx * 16);
-    const uint4* v4 = reinterpret_cast<const uint4*>(vals);
-    o[0] = v4[0]; o[1] = v4[1];
+}
+
+// ---- split-fp16 pair tensors.  Every tensor that a 1x1x1 conv or a pool reads is stored as a pair x = hi + lo (two fp16
+// numbers, ~22 mantissa bits), row = [hi C | lo C]: a CPU emulation of the trained rgb net puts 6.8e-4 of the 8.1e-4 output
+// error on the fp16 rounding of exactly these tensors (the stem pool output alone: 4.1e-4), and only 2.7e-4 on the inputs of
+// the 3x3x3 convs, which carry the FLOPs and stay single fp16.  A pair is the canonical split of its fp32 value, so
+// hi + lo is exact in fp32 and max() picks one of the input pairs.
+__device__ __forceinline__ void pair_split8(const float* v, uint4& hi4, uint4& lo4) {
+    __align__(16) __half hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        hi[j] = __float2half_rn(v[j]);
+        lo[j] = __float2half_rn(v[j] - __half2float(hi[j]));
+    }
+    hi4 = *reinterpret_cast<const uint4*>(hi);
+    lo4 = *reinterpret_cast<const uint4*>(lo);
+}
+__device__ __forceinline__ void pair_load_max8(const __half* p, int C, float* m) {
+    const uint4 h4 = __ldg(reinterpret_cast<const uint4*>(p)), l4 = __ldg(reinterpret_cast<const uint4*>(p + C));
+    const __half2* hh = reinterpret_cast<const __half2*>(&h4);
+    const __half2* ll = reinterpret_cast<const __half2*>(&l4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 a = __half22float2(hh[j]), b = __half22float2(ll[j]);
+        m[2 * j] = fmaxf(m[2 * j], a.x + b.x);
+        m[2 * j + 1] = fmaxf(m[2 * j + 1], a.y + b.y);
+    }
 }
 
 // Max pool over the VALID region of the input volume with ZERO padding semantics (MaxPool3dTFPadding: ConstantPad3d(0)
-// then ceil-mode MaxPool3d; inputs are post-ReLU so 0 never wins wrongly).  One thread = one output position x 8
-// channels; border positions of the output volume are written as zeros.
+// then ceil-mode MaxPool3d; inputs are post-ReLU so 0 never wins wrongly).  Input and output are pair tensors (rows of
+// 2C).  One thread = one output position x 8 channels; border positions of the output volume are written as zeros.
 __global__ void maxpool3d_kernel(const __half* __restrict__ in, DVol vi, __half* __restrict__ out, DVol vo, int C,
                                  int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph, int pw) {
     const int cg = C >> 3;
@@ -143,9 +186,9 @@ __global__ void maxpool3d_kernel(const __half* __restrict__ in, DVol vi, __half*
     const int hh = int((pos / vo.Wp) % vo.Hp);
     const int t = int((pos / (int64_t(vo.Wp) * vo.Hp)) % vo.Tp);
     const int b = int(pos / (int64_t(vo.Wp) * vo.Hp * vo.Tp));
-    __half2 m[4];
-    const __half2 zero = __float2half2_rn(0.f);
-    m[0] = m[1] = m[2] = m[3] = zero;
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = 0.f;
     const bool valid = (t >= vo.t0) && (t < vo.t1) && (hh >= vo.h0) && (hh < vo.h1) && (w >= vo.w0) && (w < vo.w1);
     if (valid) {
         const int ot = t - vo.t0, oh = hh - vo.h0, ow = w - vo.w0;     // output coordinates
@@ -160,28 +203,24 @@ __global__ void maxpool3d_kernel(const __half* __restrict__ in, DVol vi, __half*
                     const int iw = ow * sw - pw + cc;
                     if (iw < 0 || iw >= Wi) continue;
                     const int64_t r = ((int64_t(b) * vi.Tp + it + vi.t0) * vi.Hp + ih + vi.h0) * vi.Wp + iw + vi.w0;
-                    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(in + r * C + c8 * 8));
-                    const __half2* v = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) m[j] = __hmax2(m[j], v[j]);
+                    pair_load_max8(in + r * (2 * C) + c8 * 8, C, m);
                 }
             }
         }
     }
-    uint4 o;
-    o.x = *reinterpret_cast<uint32_t*>(&m[0]);
-    o.y = *reinterpret_cast<uint32_t*>(&m[1]);
-    o.z = *reinterpret_cast<uint32_t*>(&m[2]);
-    o.w = *reinterpret_cast<uint32_t*>(&m[3]);
-    *reinterpret_cast<uint4*>(out + pos * C + c8 * 8) = o;
+    uint4 hi4, lo4;
+    pair_split8(m, hi4, lo4);
+    *reinterpret_cast<uint4*>(out + pos * (2 * C) + c8 * 8) = hi4;
+    *reinterpret_cast<uint4*>(out + pos * (2 * C) + C + c8 * 8) = lo4;
 }
 
 // The Mixed blocks' branch-3 pool: 3x3x3, stride 1, zero padding 1, same volume geometry in and out (border >= 1 of
-// zeros all around, which IS the padding: no bounds checks).  One thread = (clip, t, w, 8 channels) marching down h: per
-// step it folds the 3 (t) x 3 (w) neighbours of one input row into a row maximum (9 coalesced 16-byte loads) and emits
-// the maximum of the last three row maxima -- 9 loads per output instead of 27.  Border positions are written as zeros.
+// zeros all around, which IS the padding: no bounds checks), pair tensors in and out.  One thread = (clip, t, w, 8
+// channels) marching down h: per step it folds the 3 (t) x 3 (w) neighbours of one input row into a row maximum (9
+// coalesced pair loads) and emits the maximum of the last three row maxima -- 9 positions per output instead of 27.
+// Border positions are written as zeros.
 __global__ void maxpool3d_same3_kernel(const __half* __restrict__ in, DVol v, __half* __restrict__ out, int C) {
-    const int cg = C >> 3;
+    const int cg = C >> 3, ld = 2 * C;
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t total = int64_t(v.n) * v.Tp * v.Wp * cg;
     if (idx >= total) return;
@@ -189,43 +228,45 @@ __global__ void maxpool3d_same3_kernel(const __half* __restrict__ in, DVol v, __
     const int w = int((idx / cg) % v.Wp);
     const int t = int((idx / (int64_t(cg) * v.Wp)) % v.Tp);
     const int b = int(idx / (int64_t(cg) * v.Wp * v.Tp));
-    const int64_t plane = int64_t(v.Hp) * v.Wp * C, rowp = int64_t(v.Wp) * C;
-    const int64_t base = (int64_t(b) * v.Tp + t) * plane + int64_t(w) * C + c8 * 8;     // (b, t, h = 0, w)
+    const int64_t plane = int64_t(v.Hp) * v.Wp * ld, rowp = int64_t(v.Wp) * ld;
+    const int64_t base = (int64_t(b) * v.Tp + t) * plane + int64_t(w) * ld + c8 * 8;     // (b, t, h = 0, w), hi half
     const uint4 z4 = make_uint4(0, 0, 0, 0);
+    auto store_zero = [&](int hh) {
+        *reinterpret_cast<uint4*>(out + base + hh * rowp) = z4;
+        *reinterpret_cast<uint4*>(out + base + hh * rowp + C) = z4;
+    };
     if (t < v.t0 || t >= v.t1 || w < v.w0 || w >= v.w1) {
-        for (int hh = 0; hh < v.Hp; ++hh) *reinterpret_cast<uint4*>(out + base + hh * rowp) = z4;
+        for (int hh = 0; hh < v.Hp; ++hh) store_zero(hh);
         return;
     }
-    const __half2 zero = __float2half2_rn(0.f);
-    auto row_max = [&](int hh, __half2* m) {          // max over (t-1..t+1, w-1..w+1) of input row hh
-        m[0] = m[1] = m[2] = m[3] = zero;
+    auto row_max = [&](int hh, float* m) {          // max over (t-1..t+1, w-1..w+1) of input row hh
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = 0.f;
 #pragma unroll
         for (int dt = -1; dt <= 1; ++dt)
 #pragma unroll
-            for (int dw = -1; dw <= 1; ++dw) {
-                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(in + base + dt * plane + hh * rowp + dw * C));
-                const __half2* x = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) m[j] = __hmax2(m[j], x[j]);
-            }
+            for (int dw = -1; dw <= 1; ++dw) pair_load_max8(in + base + dt * plane + hh * rowp + dw * ld, C, m);
     };
-    __half2 r0[4], r1[4], r2[4];
-    for (int hh = 0; hh < v.h0; ++hh) *reinterpret_cast<uint4*>(out + base + hh * rowp) = z4;
+    float r0[8], r1[8], r2[8];
+    for (int hh = 0; hh < v.h0; ++hh) store_zero(hh);
     row_max(v.h0 - 1, r0);
     row_max(v.h0, r1);
     for (int hh = v.h0; hh < v.h1; ++hh) {
         row_max(hh + 1, r2);
-        uint4 o;
-        __half2* po = reinterpret_cast<__half2*>(&o);
+        float o[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { po[j] = __hmax2(__hmax2(r0[j], r1[j]), r2[j]); r0[j] = r1[j]; r1[j] = r2[j]; }
-        *reinterpret_cast<uint4*>(out + base + hh * rowp) = o;
+        for (int j = 0; j < 8; ++j) { o[j] = fmaxf(fmaxf(r0[j], r1[j]), r2[j]); r0[j] = r1[j]; r1[j] = r2[j]; }
+        uint4 hi4, lo4;
+        pair_split8(o, hi4, lo4);
+        *reinterpret_cast<uint4*>(out + base + hh * rowp) = hi4;
+        *reinterpret_cast<uint4*>(out + base + hh * rowp + C) = lo4;
     }
-    for (int hh = v.h1; hh < v.Hp; ++hh) *reinterpret_cast<uint4*>(out + base + hh * rowp) = z4;
+    for (int hh = v.h1; hh < v.Hp; ++hh) store_zero(hh);
 }
 
 // AvgPool3d((2,7,7), stride 1) on a T3 x 7 x 7 map -> (T3-1) x 1 x 1, squeeze, mean over time (i3d_net.py:258-264):
 // feature[c] = 1/(T3-1) * sum_{t'} 1/98 * sum_{dt<2,h,w} x[t'+dt][h][w][c].   One block per clip, thread = channel.
+// The input is a pair tensor (rows of 2C).
 __global__ void i3d_head_kernel(const __half* __restrict__ in, DVol v, int C, float* __restrict__ out) {
     const int b = blockIdx.y;
     const int T3 = v.t1 - v.t0;
@@ -236,7 +277,7 @@ __global__ void i3d_head_kernel(const __half* __restrict__ in, DVol v, int C, fl
             for (int hh = 0; hh < 7; ++hh)
                 for (int w = 0; w < 7; ++w) {
                     const int64_t r = ((int64_t(b) * v.Tp + t + v.t0) * v.Hp + hh + v.h0) * v.Wp + w + v.w0;
-                    plane += __half2float(in[r * C + c]);
+                    plane += __half2float(in[r * (2 * C) + c]) + __half2float(in[r * (2 * C) + C + c]);
                 }
             const float wgt = (t == 0 || t == T3 - 1) ? 1.f : 2.f;    // interior planes sit in two (2,7,7) windows
             acc += wgt * plane;
@@ -246,7 +287,8 @@ __global__ void i3d_head_kernel(const __half* __restrict__ in, DVol v, int C, fl
 }
 
 // diagnostic: valid region of a bordered channels-last volume -> fp32 NCTHW
-__global__ void unpack_ndhwc_kernel(const __half* __restrict__ in, DVol v, int ld, int c_off, int c_cnt,
+// (lo_off > 0: the columns are hi halves of a pair tensor, lo halves lo_off columns to the right)
+__global__ void unpack_ndhwc_kernel(const __half* __restrict__ in, DVol v, int ld, int c_off, int c_cnt, int lo_off,
                                     float* __restrict__ out) {
     const int T = v.t1 - v.t0, H = v.h1 - v.h0, W = v.w1 - v.w0;
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -258,7 +300,7 @@ __global__ void unpack_ndhwc_kernel(const __half* __restrict__ in, DVol v, int l
     const int c = int((idx / (int64_t(W) * H * T)) % c_cnt);
     const int b = int(idx / (int64_t(W) * H * T * c_cnt));
     const int64_t r = ((int64_t(b) * v.Tp + t + v.t0) * v.Hp + hh + v.h0) * v.Wp + w + v.w0;
-    out[idx] = __half2float(in[r * ld + c_off + c]);
+    out[idx] = __half2float(in[r * ld + c_off + c]) + (lo_off > 0 ? __half2float(in[r * ld + c_off + c + lo_off]) : 0.f);
 }
 
 }  // namespace
@@ -316,12 +358,12 @@ int launch_i3d_head_raw(const __half* in, const void* vi, int C, float* out, cud
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
-int launch_unpack_ndhwc_raw(const __half* in, const void* vi, int C, int c_off, int c_cnt, int ld, float* out,
+int launch_unpack_ndhwc_raw(const __half* in, const void* vi, int C, int c_off, int c_cnt, int ld, int lo_off, float* out,
                             cudaStream_t s) {
     const DVol a = to_dev(vi);
     const int64_t total = int64_t(a.n) * c_cnt * (a.t1 - a.t0) * (a.h1 - a.h0) * (a.w1 - a.w0);
     (void)C;
-    unpack_ndhwc_kernel<<<nblocks(total, 256), 256, 0, s>>>(in, a, ld, c_off, c_cnt, out);
+    unpack_ndhwc_kernel<<<nblocks(total, 256), 256, 0, s>>>(in, a, ld, c_off, c_cnt, lo_off, out);
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
