@@ -69,25 +69,27 @@ __global__ void phase_repack_kernel(const __half* __restrict__ in, Vol2 vi, int 
     *reinterpret_cast<uint4*>(out + pos * (4 * C) + p * C + c8 * 8) = v;
 }
 
-// InstanceNorm2d statistics: per (sample, channel) sum and sum of squares over the valid region, accumulated in
-// double (fp32 partials per thread).  grid (row chunks, n), block = C threads.
+// InstanceNorm2d statistics: per (sample, channel) sum and sum of squares over the valid region.  grid (H, n): one block
+// per image row, block = C * S threads (S position phases per channel); fp32 partials per thread over <= W/S values, the
+// S partials and the rows are combined in double.
 __global__ void instnorm_stats_kernel(const float* __restrict__ x, Vol2 v, int C, double* __restrict__ stats) {
-    const int b = blockIdx.y, c = threadIdx.x;
-    const int H = v.h1 - v.h0, W = v.w1 - v.w0;
-    const int rows_per = (H + gridDim.x - 1) / gridDim.x;
-    const int y0 = blockIdx.x * rows_per, y1 = min(H, y0 + rows_per);
-    double s = 0.0, ss = 0.0;
-    for (int y = y0; y < y1; ++y) {
-        const float* row = x + ((int64_t(b) * v.Hp + y + v.h0) * v.Wp + v.w0) * C + c;
-        float fs = 0.f, fss = 0.f;
-        for (int xw = 0; xw < W; ++xw) {
-            const float t = row[int64_t(xw) * C];
-            fs += t;
-            fss = fmaf(t, t, fss);
-        }
-        s += fs; ss += fss;
+    __shared__ double red[2][256];
+    const int b = blockIdx.y, y = blockIdx.x;
+    const int c = threadIdx.x % C, sub = threadIdx.x / C, S = blockDim.x / C;
+    const int W = v.w1 - v.w0;
+    const float* row = x + ((int64_t(b) * v.Hp + y + v.h0) * v.Wp + v.w0) * C + c;
+    float fs = 0.f, fss = 0.f;
+    for (int xw = sub; xw < W; xw += S) {
+        const float t = row[int64_t(xw) * C];
+        fs += t;
+        fss = fmaf(t, t, fss);
     }
-    if (y1 > y0) {
+    red[0][threadIdx.x] = double(fs);
+    red[1][threadIdx.x] = double(fss);
+    __syncthreads();
+    if (sub == 0) {
+        double s = 0.0, ss = 0.0;
+        for (int j = 0; j < S; ++j) { s += red[0][j * C + c]; ss += red[1][j * C + c]; }
         atomicAdd(&stats[(int64_t(b) * C + c) * 2], s);
         atomicAdd(&stats[(int64_t(b) * C + c) * 2 + 1], ss);
     }
@@ -501,8 +503,9 @@ int raft_phase_repack(const __half* in, const Vol2& vi, int C, __half* out, cons
 int raft_instnorm_stats(const float* x, const Vol2& v, int C, double* stats, cudaStream_t s) {
     VF_CUDA(cudaMemsetAsync(stats, 0, size_t(v.n) * C * 2 * sizeof(double), s));
     const int H = v.h1 - v.h0;
-    const int chunks = H < 32 ? H : 32;
-    instnorm_stats_kernel<<<dim3(chunks, v.n), C, 0, s>>>(x, v, C, stats);
+    if (C > 256) return fail(VF_ERR_INVALID, "instnorm_stats: C=%d > 256", C);
+    const int S = 256 / C;       // 4 / 2 / 2 position phases for C = 64 / 96 / 128
+    instnorm_stats_kernel<<<dim3(H, v.n), C * S, 0, s>>>(x, v, C, stats);
     LAUNCH_CHECK();
 }
 int raft_instnorm_apply(const float* a, const double* a_stats, const __half* res_h, const float* res_raw,
