@@ -92,6 +92,58 @@ if os.path.exists(rep):
         except Exception:
             pass
 
+# ---- I3D: per-launch list of one forward (8 clips x 64 frames)
+lp = os.path.join(G, "r1_launches_i3d.csv")
+if os.path.exists(lp):
+    shutil.copy(lp, os.path.join(P, "r1_launches_i3d.csv"))
+    per = collections.OrderedDict()
+    for x in csv.DictReader([l for l in open(lp) if not l.startswith("==")]):
+        d = per.setdefault(x["ID"], {"name": re.sub(r"\(.*", "", x["Kernel Name"]).replace("void ", "").replace("vf::<unnamed>::", "")})
+        d[x["Metric Name"]] = float(x["Metric Value"].replace(",", ""))
+    L = list(per.values())
+    first = [i for i, x in enumerate(L) if "phase_pack" in x["name"]]
+    if len(first) >= 3:
+        S = L[first[1]:first[2]]          # the second forward: pack .. head
+        tot = sum(x["gpu__time_duration.sum"] for x in S)
+        md = ["# I3D rgb forward, 8 clips x 64 frames: ncu per-launch list (cold-cache, serialised; one forward)\n",
+              f"{len(S)} launches, {tot/1e6:.3f} ms\n",
+              "| # | kernel | µs | tensor pipe % | DRAM read MB | DRAM write MB | L2 MB | grid |\n|---|---|---|---|---|---|---|---|"]
+        for i, x in enumerate(S):
+            md.append(f"| {i} | `{x['name'][:40]}` | {x['gpu__time_duration.sum']/1e3:.1f} | "
+                      f"{x.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 0):.1f} | "
+                      f"{x.get('dram__bytes_read.sum', 0)/1e6:.1f} | {x.get('dram__bytes_write.sum', 0)/1e6:.1f} | "
+                      f"{x.get('lts__t_bytes.sum', 0)/1e6:.0f} | {int(x.get('launch__grid_size', 0))} |")
+        open(os.path.join(P, "r1_i3d_launches.md"), "w").write("\n".join(md) + "\n")
+        agg = collections.OrderedDict()
+        for x in S:
+            a = agg.setdefault(x["name"], [0, 0.0]); a[0] += 1; a[1] += x["gpu__time_duration.sum"]
+        out.append("## I3D forward (8 clips x 64 frames): ncu kernel shares of one forward (full list: `r1_i3d_launches.md`)\n")
+        out.append("| kernel | launches | total µs | share |\n|---|---|---|---|")
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            out.append(f"| `{k}` | {v[0]} | {v[1]/1e3:.1f} | {100*v[1]/tot:.1f} % |")
+        stem = next((x for x in S if "gemm" in x["name"]), None)
+        if stem:
+            out.append(f"\nstem GEMM (first GEMM launch): {stem['gpu__time_duration.sum']/1e3:.1f} µs = {100*stem['gpu__time_duration.sum']/tot:.1f} % of the forward, "
+                       f"tensor pipe {stem.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 0):.1f} %, L2 traffic {stem.get('lts__t_bytes.sum', 0)/1e9:.2f} GB\n")
+
+# ---- RAFT: kernel shares of one call (8 pairs 270x480, 20 iterations)
+lp = os.path.join(G, "r1_launches_raft.csv")
+if os.path.exists(lp):
+    shutil.copy(lp, os.path.join(P, "r1_launches_raft.csv"))
+    rows = list(csv.DictReader([l for l in open(lp) if not l.startswith("==")]))
+    rows = rows[len(rows) // 2:]           # the second of the two calls
+    agg = collections.OrderedDict()
+    for x in rows:
+        name = re.sub(r"\(.*", "", x["Kernel Name"]).replace("void ", "").replace("vf::<unnamed>::", "")
+        a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += float(x["Metric Value"].replace(",", ""))
+    tot = sum(v[1] for v in agg.values())
+    out.append("## RAFT, one call of 8 pairs 270x480 x 20 iterations: ncu kernel shares (cold-cache, serialised)\n")
+    out.append(f"{len(rows)} launches, {tot/1e6:.3f} ms\n")
+    out.append("| kernel | launches | total µs | avg µs | share |\n|---|---|---|---|---|")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        out.append(f"| `{k}` | {v[0]} | {v[1]/1e3:.1f} | {v[1]/v[0]/1e3:.1f} | {100*v[1]/tot:.1f} % |")
+    out.append("")
+
 t = os.path.join(G, "r1_pytest_gpu.txt")
 if os.path.exists(t):
     out.append("## `pytest tests -m gpu` on the same box\n\n```\n" + open(t).read().strip() + "\n```\n")
