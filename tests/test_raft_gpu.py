@@ -72,6 +72,18 @@ def test_raft_stages_and_one_iteration(raft, cuda_device):
     assert e[0] < 1e-4 and e[1] < 1e-3
 
 
+def test_raft_odd_map_size(raft, cuda_device):
+    """200x200 frames: the 25x25 = 625-position /8 map is not a multiple of 8 (padded GEMM width, odd pooling sizes)."""
+    from oracle import raft_net as R
+    sd, eng = raft
+    x = R.synthetic_frames(2, 200, 200, seed=7).to(cuda_device)
+    y = eng.flow(x, iters=12, unpad=True)
+    ref = R.forward(sd_to(sd, cuda_device), x[:-1], x[1:], 12)
+    rel, mx = _err(y, ref)
+    print(f"200x200: rel-L2 {rel:.3e} max {mx:.3e}")
+    assert torch.isfinite(y).all() and rel < 1e-4 and mx < 1e-3
+
+
 def sd_to(sd, dev):
     return {k: v.to(dev) for k, v in sd.items()}
 

@@ -478,6 +478,9 @@ int vf_raft_create(vf_raft_t** out, const vf_named_tensor* tensors, int n_tensor
         const size_t P = size_t(H / 8) * (W / 8), P8 = (P + 7) / 8 * 8;
         VF_TRY(ralloc(h, &h->corrA, F * P8 * 768));
         VF_TRY(ralloc(h, &h->corrB, F * P8 * 768));
+        // rows P .. P8-1 of a frame are never written: they must hold finite values (they only feed unread corr columns)
+        VF_CUDA(cudaMemset(h->corrA, 0, F * P8 * 768 * sizeof(__half)));
+        VF_CUDA(cudaMemset(h->corrB, 0, F * P8 * 768 * sizeof(__half)));
         VF_TRY(ralloc(h, &h->st_a, F * 128 * 2)); VF_TRY(ralloc(h, &h->st_b, F * 128 * 2));
         const size_t ld = (P8 + P / 4 + P / 16 + P / 64 + 64 + 3) / 4 * 4;
         VF_TRY(ralloc(h, &h->corr, NP * P * ld));
@@ -620,7 +623,6 @@ int vf_raft_flow(vf_raft_t* h, const void* frames, int is_u8, int chw_layout, in
     if (H > h->max_h || W > h->max_w || H < 16 || W < 16)
         return fail(VF_ERR_INVALID, "raft_flow: padded frame %dx%d outside the workspace (%dx%d)", H, W, h->max_h, h->max_w);
     const int F = n_frames, NP = F - 1, H8 = H / 8, W8 = W / 8, P = H8 * W8;
-    if (P % 8) return fail(VF_ERR_UNSUPPORTED, "raft_flow: (H/8)*(W/8) = %d must be a multiple of 8", P);
     cudaStream_t user = static_cast<cudaStream_t>(stream), s = h->cs;
     VF_CUDA(cudaSetDevice(h->device));
     VF_CUDA(cudaEventRecord(h->ev_in, user));
@@ -653,7 +655,7 @@ int vf_raft_flow(vf_raft_t* h, const void* frames, int is_u8, int chw_layout, in
         // geometry bookkeeping normally done inside raft_core
         h->last_n = NP; h->last_H8 = H8; h->last_W8 = W8;
         {
-            int ldc = P, lh = H8, lw = W8;
+            int ldc = (P + 7) / 8 * 8, lh = H8, lw = W8;
             for (int l = 1; l < 4; ++l) { lh /= 2; lw /= 2; ldc += lh * lw; }
             h->corr_ld = (ldc + 3) / 4 * 4;
         }

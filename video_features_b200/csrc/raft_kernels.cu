@@ -256,8 +256,10 @@ __global__ void corr_lookup_kernel(const float* __restrict__ corr, int ld, const
     const int lvl = int(wid & 3);
     const int64_t q = wid >> 2;                      // b*H8*W8 + y*W8 + x
     const int x0 = int(q % W8), y0 = int((q / W8) % H8), b = int(q / (int64_t(W8) * H8));
+    // level offsets inside a corr row: level 0 occupies P8 = roundup(H8*W8, 8) columns (the GEMM's N), the pooled levels
+    // follow densely (raft.cu: lvl_off)
     int Hl = H8, Wl = W8, off = 0;
-    for (int l = 0; l < lvl; ++l) { off += Hl * Wl; Hl >>= 1; Wl >>= 1; }
+    for (int l = 0; l < lvl; ++l) { off += (l == 0) ? ((Hl * Wl + 7) & ~7) : Hl * Wl; Hl >>= 1; Wl >>= 1; }
     const float inv = 1.0f / float(1 << lvl);
     const float cx = coords[q * 2] * inv, cy = coords[q * 2 + 1] * inv;
     const float fx0 = floorf(cx), fy0 = floorf(cy);
