@@ -421,7 +421,7 @@ def run_i3d(args) -> None:
     from oracle import i3d_net
     torch.cuda.set_device(0)
     sd, wsrc = _weights("rgb")
-    S = int(os.environ.get("VF_BENCH_I3D_STACKS", "8"))
+    S = int(os.environ.get("VF_BENCH_I3D_STACKS", "16"))
     eng = I3DEngine(sd, "rgb", 0, max_stacks=S, max_T=64)
     g = torch.Generator().manual_seed(1)
     frames_host = torch.randint(0, 256, (S, 65, 224, 224, 3), dtype=torch.uint8, generator=g).pin_memory()

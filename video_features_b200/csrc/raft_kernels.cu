@@ -120,7 +120,7 @@ __global__ void instnorm_apply_kernel(const float* __restrict__ a, const double*
         *reinterpret_cast<uint4*>(out + off2 + C) = make_uint4(0, 0, 0, 0);
         return;
     }
-    const double cnt = double(H) * double(W);
+    const double inv_cnt = 1.0 / (double(H) * double(W));     // one divide per thread; the 8 channels multiply
     float av[8], rv[8];
     *reinterpret_cast<float4*>(av) = *reinterpret_cast<const float4*>(a + off);
     *reinterpret_cast<float4*>(av + 4) = *reinterpret_cast<const float4*>(a + off + 4);
@@ -139,13 +139,13 @@ __global__ void instnorm_apply_kernel(const float* __restrict__ a, const double*
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int c = c8 * 8 + j;
-        const double m = a_stats[(int64_t(b) * C + c) * 2] / cnt;
-        const double var = a_stats[(int64_t(b) * C + c) * 2 + 1] / cnt - m * m;
+        const double m = a_stats[(int64_t(b) * C + c) * 2] * inv_cnt;
+        const double var = a_stats[(int64_t(b) * C + c) * 2 + 1] * inv_cnt - m * m;
         float y0 = float((double(av[j]) - m)) * rsqrtf(float(var) + 1e-5f);
         y0 = fmaxf(y0, 0.f);
         if (res_raw) {
-            const double rm = res_stats[(int64_t(b) * C + c) * 2] / cnt;
-            const double rvv = res_stats[(int64_t(b) * C + c) * 2 + 1] / cnt - rm * rm;
+            const double rm = res_stats[(int64_t(b) * C + c) * 2] * inv_cnt;
+            const double rvv = res_stats[(int64_t(b) * C + c) * 2 + 1] * inv_cnt - rm * rm;
             y0 = fmaxf(float(double(rv[j]) - rm) * rsqrtf(float(rvv) + 1e-5f) + y0, 0.f);
         } else if (res_h) {
             y0 = fmaxf(rv[j] + y0, 0.f);
