@@ -94,7 +94,9 @@ __device__ __forceinline__ void epi_math32(float* v, const GemmEpi& ep, int n, i
     }
 }
 
-template <int BN, int STAGES, int NSPLIT>
+// SPLIT: split-fp16 output (GemmEpi::split_off) -- every fp16 slice is emitted twice, hi then lo, through tmO / tmO2.  A
+// compile-time switch: as a run-time loop it cost the plain epilogue 20 % on K = 768 shapes.
+template <int BN, int STAGES, int NSPLIT, bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2, const GemmEpi ep,
@@ -211,7 +213,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         uint8_t* bufs = stg + grp * Cfg::EPI_BUFS * SLICE_BYTES;
         const bool agent = (q == 0) && (lane == 0);
         const int slice_cols = ep.out_f32 ? 32 : 64;
-        const int nsp = (!ep.out_f32 && ep.split_off > 0) ? 2 : 1;
+        constexpr int NSP = SPLIT ? 2 : 1;
         const uint32_t sw = uint32_t(row & 7);
         int acc = 0, it = 0;
         uint32_t acc_phase = 0;
@@ -231,7 +233,8 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
 #pragma unroll 1
             for (int c = grp * slice_cols; c < BN; c += 2 * slice_cols)
-            for (int sp = 0; sp < nsp; ++sp) {     // split output: the slice is produced twice, hi then lo
+#pragma unroll
+            for (int sp = 0; sp < NSP; ++sp) {     // split output: the slice is produced twice, hi then lo
                 uint8_t* buf = bufs + (Cfg::EPI_BUFS == 2 ? (it & 1) : 0) * SLICE_BYTES;
                 uint8_t* myrow = buf + row * 128;
                 // the TMA store that last used this buffer must have finished reading it
@@ -268,7 +271,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = 0.f;
                         }
-                        if (sp) {
+                        if (SPLIT && sp) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] -= __half2float(__float2half_rn(v[j]));
                         }
@@ -285,7 +288,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     // rows >= M and columns >= N are clipped by the TMA unit.  A group is committed for EVERY slice,
                     // also for the (empty) ones right of N: wait_group.read<1> above counts groups, and skipping a
                     // commit would let a buffer be rewritten while its previous store is still reading it.
-                    if (n < N) tma_store_2d(sp ? &tmO2 : &tmO, buf, n, m0);
+                    if (n < N) tma_store_2d((SPLIT && sp) ? &tmO2 : &tmO, buf, n, m0);
                     bulk_commit();
                 }
                 ++it;
@@ -322,7 +325,7 @@ EncodeTiledFn get_encode_tiled() {
     return fn;
 }
 
-template <int BN, int STAGES, int NSPLIT>
+template <int BN, int STAGES, int NSPLIT, bool SPLIT = false>
 int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmO2,
                      const GemmEpi& ep, int M,
                      int N, const ConvGeom& cg, cudaStream_t stream) {
@@ -331,14 +334,14 @@ int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     int dev = 0;
     VF_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        VF_CUDA(cudaFuncSetAttribute(gemm_f16_pair_kernel<BN, STAGES, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        VF_CUDA(cudaFuncSetAttribute(gemm_f16_pair_kernel<BN, STAGES, NSPLIT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::SMEM_BYTES));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
     const int pairs = device_sm_count() / 2;
     const int grid = 2 * (tiles < pairs ? tiles : pairs);
-    gemm_f16_pair_kernel<BN, STAGES, NSPLIT><<<grid, 384, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, tmO2, ep, M, N, cg);
+    gemm_f16_pair_kernel<BN, STAGES, NSPLIT, SPLIT><<<grid, 384, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, tmO2, ep, M, N, cg);
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
@@ -388,6 +391,18 @@ static thread_local GemmProf g_prof;
 static int run_gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmO2,
                            int bn, const GemmEpi& ep,
                            int M, int N, const ConvGeom& cg, cudaStream_t stream) {
+    if (ep.split_off > 0 && !ep.out_f32) {
+        if (cg.nsplit == 2) {
+            if (bn == 256) return launch_gemm_pair<256, 4, 2, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+            if (bn == 192) return launch_gemm_pair<192, 4, 2, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+            if (bn == 128) return launch_gemm_pair<128, 6, 2, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+            return launch_gemm_pair<64, 8, 2, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+        }
+        if (bn == 256) return launch_gemm_pair<256, 5, 1, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+        if (bn == 192) return launch_gemm_pair<192, 5, 1, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+        if (bn == 128) return launch_gemm_pair<128, 6, 1, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+        return launch_gemm_pair<64, 8, 1, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+    }
     if (cg.nsplit == 2) {
         if (bn == 256) return launch_gemm_pair<256, 4, 2>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
         if (bn == 192) return launch_gemm_pair<192, 4, 2>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
