@@ -46,6 +46,19 @@ for name, title in (("r1_bench_clip.json", "CLIP ViT-B/32 (headline, BASELINE co
         out.append(f"* clocks under load: {json.dumps(d['clocks'])}")
     out.append(f"* launches in timed region: {d.get('gpu_launches')}\n")
 
+# ---- 2-GPU line (gpurun --gpus 2, torchrun); kept in profiles/ between passes
+p2 = os.path.join(G, "r1_bench_clip_2gpu.json")
+if os.path.exists(p2):
+    shutil.copy(p2, os.path.join(P, "r1_bench_clip_2gpu.json"))
+try:
+    d2 = json.loads([l for l in open(os.path.join(P, "r1_bench_clip_2gpu.json")) if l.startswith("{")][-1])
+    d1 = load("r1_bench_clip.json")
+    out.append("## CLIP, 2 x B200 (`gpurun --gpus 2`, torchrun, NCCL all_gather of the (2000,512) features inside the timed region)\n")
+    out.append(f"* **{d2['value']:.1f} frames/s** whole job ({d2['ms_per_step']:.3f} ms/step max over ranks; weak scaling: 1000 frames per rank per step),"
+               f" e2e {d2['e2e']['value']:.1f} frames/s" + (f"; vs 1 GPU ({d1['value']:.0f} frames/s): x{d2['value']/d1['value']:.2f}" if d1 else "") + "\n")
+except Exception:
+    pass
+
 # ---- ncu launch list
 lp = os.path.join(G, "r1_launches_clip.csv")
 if os.path.exists(lp):

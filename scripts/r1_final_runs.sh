@@ -11,7 +11,7 @@ timeout -s KILL 400 ncu --metrics gpu__time_duration.sum --clock-control none -s
 timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:gemm_f16_pair -s 60 -c 4 -o gpurun_out/r1_prof_gemm \
     python scripts/ncu_clip_once.py 250 250 > gpurun_out/r1_ncu_full.log 2>&1
 timeout -s KILL 300 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,launch__grid_size \
-    --clock-control none -c 300 --csv --log-file gpurun_out/r1_launches_i3d.csv python bench.py --workload i3d --steps 1 --warmup 1 --no-cpu > gpurun_out/r1_ncu_i3d.log 2>&1
+    --clock-control none -c 300 --csv --log-file gpurun_out/r1_launches_i3d.csv env VF_BENCH_I3D_STACKS=8 python bench.py --workload i3d --steps 1 --warmup 1 --no-cpu > gpurun_out/r1_ncu_i3d.log 2>&1
 timeout -s KILL 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r1_launches_raft.csv \
     python scripts/ncu_raft_once.py 9 > gpurun_out/r1_ncu_raft.log 2>&1
 cat gpurun_out/r1_pytest_gpu.txt

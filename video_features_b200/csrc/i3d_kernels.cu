@@ -58,6 +58,12 @@ __global__ void i3d_phase_pack_f32_kernel(const float* __restrict__ x, int n, in
 // stack b starts at frame b * stack_stride (>= T: a stack may be a window of a longer frame buffer).
 __global__ void i3d_phase_pack_u8_kernel(const uint8_t* __restrict__ frames, int n, int T, int64_t stack_stride, int Hr,
                                          int Wr, int cy, int cx, __half* __restrict__ out, int Tq) {
+    // the transform of a byte, in the reference's fp32 operation order, has 256 possible results: one table per block
+    // instead of 96 IEEE divisions per thread
+    __shared__ __half lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        lut[i] = __float2half_rn(__fsub_rn(__fdiv_rn(__fmul_rn(2.0f, float(i)), 255.0f), 1.0f));
+    __syncthreads();
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t total = int64_t(n) * Tq * 115 * 115;
     if (idx >= total) return;
@@ -66,6 +72,7 @@ __global__ void i3d_phase_pack_u8_kernel(const uint8_t* __restrict__ frames, int
     const int tq = int((idx / (115 * 115)) % Tq);
     const int b = int(idx / (int64_t(115) * 115 * Tq));
     const int w0 = 2 * (wq - 1);
+    const __half zero = __float2half_rn(0.f);
 #pragma unroll 1
     for (int sb = 0; sb < 4; ++sb) {
         __align__(16) __half vals[24];
@@ -81,11 +88,8 @@ __global__ void i3d_phase_pack_u8_kernel(const uint8_t* __restrict__ frames, int
 #pragma unroll
                 for (int pw = 0; pw < 2; ++pw)
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        float v = 0.f;
-                        if (ok) v = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, float(__ldg(p + pw * 3 + c))), 255.0f), 1.0f);
-                        vals[((pt * 2 + ph) * 2 + pw) * 3 + c] = __float2half_rn(v);
-                    }
+                    for (int c = 0; c < 3; ++c)
+                        vals[((pt * 2 + ph) * 2 + pw) * 3 + c] = ok ? lut[__ldg(p + pw * 3 + c)] : zero;
             }
         }
         uint4* o = reinterpret_cast<uint4*>(out + idx * 96 + sb * 24);
