@@ -103,6 +103,10 @@ def test_i3d_fused_stream_transforms(cuda_device):
     two = torch.randint(0, 256, (2, 13, 256, 341, 3), dtype=torch.uint8, generator=g).to(cuda_device)
     assert not two[:, :12].is_contiguous()
     assert torch.equal(eng2.forward_frames_u8(two[:, :12]), eng2.forward_frames_u8(two[:, :12].contiguous()))
+    # host entry (pipelined H2D): 5 stacks in groups of 2 == device entry
+    five = torch.randint(0, 256, (5, 13, 256, 341, 3), dtype=torch.uint8, generator=g).pin_memory()
+    yh = eng2.forward_frames_u8_host(five, 12, group=2)
+    assert not yh.is_cuda and torch.equal(yh, eng2.forward_frames_u8(five.to(cuda_device)[:, :12]).cpu())
     eng2.close()
     # flow: values beyond +-20, exact +-20 and half-way quantisation points
     sdf = i3d_net.synthetic_state_dict("flow", 2)

@@ -89,6 +89,45 @@ class I3DEngine:
                                                   torch.cuda.current_stream().cuda_stream))
         return out
 
+    def forward_frames_u8_host(self, frames: torch.Tensor, T: int, group: int = 8) -> torch.Tensor:
+        """rgb stream from HOST stacks (n, >=T, Hr, Wr, 3) uint8 (pinned memory for asynchronous copies): the first T
+        frames of every stack are used; the host->device copy of stack group k+1 runs on a copy stream while group k is
+        in the network.  Returns (n, 1024) float32 on the host."""
+        assert not frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 5 and frames.shape[4] == 3
+        n = frames.shape[0]
+        out = torch.empty((n, 1024), dtype=torch.float32).pin_memory()
+        if n == 0:
+            return out
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream()
+            copy = getattr(self, "_copy_stream", None)
+            if copy is None:
+                copy = self._copy_stream = torch.cuda.Stream(device=self.device)
+            bufs, ready, freed = [None, None], [None, None], [None, None]
+            groups = [(a, min(n, a + group)) for a in range(0, n, group)]
+
+            def stage(k):
+                a, b = groups[k]
+                with torch.cuda.stream(copy):
+                    if freed[k & 1] is not None:
+                        copy.wait_event(freed[k & 1])          # the network has finished reading this buffer
+                    bufs[k & 1] = frames[a:b].to(self.device, non_blocking=True)
+                    ready[k & 1] = torch.cuda.Event()
+                    ready[k & 1].record(copy)
+
+            stage(0)
+            for k, (a, b) in enumerate(groups):
+                if k + 1 < len(groups):
+                    stage(k + 1)
+                main.wait_event(ready[k & 1])
+                y = self.forward_frames_u8(bufs[k & 1][:, :T])
+                bufs[k & 1].record_stream(main)
+                freed[k & 1] = torch.cuda.Event()
+                freed[k & 1].record(main)
+                out[a:b].copy_(y, non_blocking=True)
+            main.synchronize()
+        return out
+
     def forward_flow(self, flow: torch.Tensor) -> torch.Tensor:
         """flow stream from raw optical flow (n, T, 2, H, W) fp32 on this device; T3 transform fused."""
         assert flow.is_cuda and flow.dtype == torch.float32 and flow.dim() == 5 and flow.shape[2] == 2
