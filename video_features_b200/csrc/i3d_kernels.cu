@@ -218,6 +218,42 @@ __global__ void maxpool3d_kernel(const __half* __restrict__ in, DVol vi, __half*
     *reinterpret_cast<uint4*>(out + pos * (2 * C) + C + c8 * 8) = lo4;
 }
 
+// Same pool without bounds checks for the strided pools between stages (window / stride compile-time, padding 0 before):
+// the window may run past the valid region only into the zero border, which is the zero padding (host-checked).  All
+// KT*KH*KW pair loads of a thread are independent and unrolled.
+template <int KT, int KH, int KW, int ST, int SH, int SW>
+__global__ void maxpool3d_fast_kernel(const __half* __restrict__ in, DVol vi, __half* __restrict__ out, DVol vo, int C) {
+    const int cg = C >> 3;
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = int64_t(vo.n) * vo.Tp * vo.Hp * vo.Wp * cg;
+    if (idx >= total) return;
+    const int c8 = int(idx % cg);
+    const int64_t pos = idx / cg;
+    const int w = int(pos % vo.Wp);
+    const int hh = int((pos / vo.Wp) % vo.Hp);
+    const int t = int((pos / (int64_t(vo.Wp) * vo.Hp)) % vo.Tp);
+    const int b = int(pos / (int64_t(vo.Wp) * vo.Hp * vo.Tp));
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = 0.f;
+    const bool valid = (t >= vo.t0) && (t < vo.t1) && (hh >= vo.h0) && (hh < vo.h1) && (w >= vo.w0) && (w < vo.w1);
+    if (valid) {
+        const int it0 = (t - vo.t0) * ST + vi.t0, ih0 = (hh - vo.h0) * SH + vi.h0, iw0 = (w - vo.w0) * SW + vi.w0;
+        const __half* p0 = in + (((int64_t(b) * vi.Tp + it0) * vi.Hp + ih0) * vi.Wp + iw0) * (2 * C) + c8 * 8;
+        const int64_t sh = int64_t(vi.Wp) * 2 * C, st = sh * vi.Hp;
+#pragma unroll
+        for (int a = 0; a < KT; ++a)
+#pragma unroll
+            for (int bq = 0; bq < KH; ++bq)
+#pragma unroll
+                for (int cc = 0; cc < KW; ++cc) pair_load_max8(p0 + a * st + bq * sh + cc * 2 * C, C, m);
+    }
+    uint4 hi4, lo4;
+    pair_split8(m, hi4, lo4);
+    *reinterpret_cast<uint4*>(out + pos * (2 * C) + c8 * 8) = hi4;
+    *reinterpret_cast<uint4*>(out + pos * (2 * C) + C + c8 * 8) = lo4;
+}
+
 // The Mixed blocks' branch-3 pool: 3x3x3, stride 1, zero padding 1, same volume geometry in and out (border >= 1 of
 // zeros all around, which IS the padding: no bounds checks), pair tensors in and out.  One thread = (clip, t, w, 8
 // channels) marching down h: per step it folds the 3 (t) x 3 (w) neighbours of one input row into a row maximum (9
@@ -352,6 +388,22 @@ int launch_maxpool3d_raw(const __half* in, const void* vi, __half* out, const vo
         return VF_OK;
     }
     const int64_t total = int64_t(b.n) * b.Tp * b.Hp * b.Wp * (C / 8);
+    {   // fast path: padding 0 before, and the last window of every axis ends inside the input's zero border
+        const int To = b.t1 - b.t0, Ho = b.h1 - b.h0, Wo = b.w1 - b.w0;
+        const bool fits = pt == 0 && ph == 0 && pw == 0 && To > 0 && Ho > 0 && Wo > 0 &&
+                          a.t0 + (To - 1) * st + kt <= a.Tp && a.h0 + (Ho - 1) * sh + kh <= a.Hp &&
+                          a.w0 + (Wo - 1) * sw + kw <= a.Wp;
+#define VF_POOL_CASE(KT, KH, KW, ST, SH, SW)                                                                      \
+        if (fits && kt == KT && kh == KH && kw == KW && st == ST && sh == SH && sw == SW) {                       \
+            maxpool3d_fast_kernel<KT, KH, KW, ST, SH, SW><<<nblocks(total, 256), 256, 0, s>>>(in, a, out, b, C);   \
+            VF_CUDA(cudaGetLastError());                                                                          \
+            return VF_OK;                                                                                         \
+        }
+        VF_POOL_CASE(1, 3, 3, 1, 2, 2)
+        VF_POOL_CASE(3, 3, 3, 2, 2, 2)
+        VF_POOL_CASE(2, 2, 2, 2, 2, 2)
+#undef VF_POOL_CASE
+    }
     maxpool3d_kernel<<<nblocks(total, 256), 256, 0, s>>>(in, a, out, b, C, kt, kh, kw, st, sh, sw, pt, ph, pw);
     VF_CUDA(cudaGetLastError());
     return VF_OK;
