@@ -58,6 +58,16 @@ try:
                f" e2e {d2['e2e']['value']:.1f} frames/s" + (f"; vs 1 GPU ({d1['value']:.0f} frames/s): x{d2['value']/d1['value']:.2f}" if d1 else "") + "\n")
 except Exception:
     pass
+p4 = os.path.join(G, "r1_bench_clip_4gpu.json")
+if os.path.exists(p4):
+    shutil.copy(p4, os.path.join(P, "r1_bench_clip_4gpu.json"))
+try:
+    d4 = json.loads([l for l in open(os.path.join(P, "r1_bench_clip_4gpu.json")) if l.startswith("{")][-1])
+    d1 = load("r1_bench_clip.json")
+    out.append(f"* 4 x B200 (`gpurun --gpus 4`): **{d4['value']:.1f} frames/s** ({d4['ms_per_step']:.3f} ms/step), e2e {d4['e2e']['value']:.1f} frames/s"
+               + (f"; x{d4['value']/d1['value']:.2f} of 1 GPU" if d1 else "") + "\n")
+except Exception:
+    pass
 
 # ---- ncu launch list
 lp = os.path.join(G, "r1_launches_clip.csv")
