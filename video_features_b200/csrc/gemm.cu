@@ -237,9 +237,13 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int sp = 0; sp < NSP; ++sp) {     // split output: the slice is produced twice, hi then lo
                 uint8_t* buf = bufs + (Cfg::EPI_BUFS == 2 ? (it & 1) : 0) * SLICE_BYTES;
                 uint8_t* myrow = buf + row * 128;
-                // the TMA store that last used this buffer must have finished reading it
-                if (agent) bulk_wait_read<Cfg::EPI_BUFS - 1>();
-                named_bar_sync(1 + grp, 128);
+                // The TMA store that last used this buffer must have finished reading it.  With two buffers that is
+                // guaranteed by the barrier of the previous slice (the agent drains the older store before arriving
+                // there, below); with one buffer it has to be checked here, at the cost of a second barrier.
+                if (Cfg::EPI_BUFS == 1) {
+                    if (agent) bulk_wait_read<0>();
+                    named_bar_sync(1 + grp, 128);
+                }
                 const int n = n_blk * BN + c;
                 if (ep.out_f32) {
                     uint32_t raw[32];
@@ -283,11 +287,13 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     }
                 }
                 fence_proxy_async();
+                // two buffers: the store of the previous slice (the OTHER buffer) has had this slice's compute time to
+                // read its source; once it has, everybody may overwrite that buffer in the next iteration
+                if (Cfg::EPI_BUFS == 2 && agent) bulk_wait_read<0>();
                 named_bar_sync(1 + grp, 128);
                 if (agent) {
                     // rows >= M and columns >= N are clipped by the TMA unit.  A group is committed for EVERY slice,
-                    // also for the (empty) ones right of N: wait_group.read<1> above counts groups, and skipping a
-                    // commit would let a buffer be rewritten while its previous store is still reading it.
+                    // also for the (empty) ones right of N, so that the group accounting of wait_group.read stays uniform.
                     if (n < N) tma_store_2d((SPLIT && sp) ? &tmO2 : &tmO, buf, n, m0);
                     bulk_commit();
                 }
