@@ -8,14 +8,18 @@
 //   * a 3x3x3 conv is 9 (dt,dh) "taps", each a constant row shift whose 3 kw neighbours are one contiguous run of
 //     3*C elements (conv_gemm_f16), the zero border IS the SAME padding, and the epilogue re-zeroes border rows,
 //   * the zero-padding max pools of the reference (MaxPool3dTFPadding pads with 0, i3d_net.py:114) read the border,
-//   * the 7x7x7 stride-2 stem becomes a 4x4x4 stride-1 conv over the 8 space-time phases of the input
-//     ([n][T/2+3][115][115][8*C]), 16 (dt,dh) taps of 4*8*C contiguous elements.
+//   * the 7x7x7 stride-2 stem becomes a 4x4x4 stride-1 conv over the 8 space-time phases of the input; the phase volume
+//     [n][T/2+3][115][115][4 x 8*C] carries the 4 h-taps inside each row, so the GEMM walks 4 t-taps of 4*32*C contiguous
+//     elements (i3d_kernels.cu).
 // BatchNorm (eval) is folded into the epilogue's per-channel scale/bias (fp32), ReLU fused; branch outputs of a Mixed
 // block are written straight into their channel slice of the concat buffer (TMA store with the concat row pitch).
 //
-// Numerics: activations fp16, accumulate fp32.  With single-fp16 weights the 1024-d feature is 1.7e-3 off the fp32
-// reference (trained weights; CPU emulation in DESIGN.md); weights are therefore carried as a hi+lo fp16 pair and
-// every K block is issued twice (A.W_hi + A.W_lo), which brings it to 8e-4.  VF_I3D_FAST=1 selects single fp16.
+// Numerics: accumulate fp32.  With single-fp16 weights the 1024-d feature is 1.7e-3 off the fp32 reference (trained
+// weights; CPU emulation in DESIGN.md); weights are therefore carried as a hi+lo fp16 pair and every K block is issued
+// twice (A.W_hi + A.W_lo): 8e-4 .. 1.06e-3 with single-fp16 activations.  Of that, 6.8e-4 comes from the rounding of the
+// tensors read by the 1x1x1 convs and the pools, so exactly those are "pair tensors", rows [hi C | lo C] of split-fp16
+// pairs (written by the GEMM's split-output epilogue or by the pool kernels); the inputs of the 3x3x3 convs, which carry
+// the FLOPs, stay single fp16: 1.5e-4 .. 4.0e-4.  VF_I3D_FAST=1 selects single-fp16 weights.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>

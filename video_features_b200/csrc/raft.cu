@@ -5,12 +5,14 @@
 // Layout: channels-last fp16 rows of zero-bordered 2-D volumes; every convolution is a shifted-row GEMM
 // (conv_gemm_f16): kw taps of one kernel row are one contiguous K run, stride-2 convs run on a space-to-depth
 // ("phase") repack of their input, InstanceNorm (fnet) is a stats + apply pass around the raw conv output,
-// BatchNorm (cnet, eval) is folded into the conv epilogue.  All-pairs correlation is one GEMM per pair
+// BatchNorm (cnet, eval) is folded into the conv epilogue.  All-pairs correlation is one 3-term split GEMM per pair
 // (fmap1 . fmap2^T / 16, fp32 out) followed by the 3-level average pooling; the per-iteration lookup gathers the
 // 4 x 9x9 bilinear windows (the reference's transposed window) straight into the motion encoder's operand rows.
-// The GRU state lives in `hx` = [h_hi | h_lo | inp | motion(126)+pad | flow hi,lo + pad] (520 columns) so that the
-// 1x5 / 5x1 gate convolutions read one contiguous run per tap; `qx` is the same row with r*h in place of h.  h, the flow
-// and the correlation features are split-fp16 pairs (see raft_kernels.cu).
+// The GRU operands live in `hx` rows of 768 columns (layout: raft_kernels.h) so that the 1x5 / 5x1 gate convolutions read
+// one contiguous run per tap; `qx` is the same row with r*h in place of h.
+// Numerics: RAFT's refinement amplifies operand rounding by 2-3 orders of magnitude, so EVERY GEMM operand is a
+// split-fp16 pair (activations [hi | lo] with duplicated weight columns, weights as hi + lo passes, W_lo skipped on
+// lo-only K blocks): emulated fp32 on the fp16 tensor cores, 1e-5-class agreement with the fp32 reference.
 // The convex-upsampling mask head and the 8x upsample run once, after the last iteration (the reference evaluates
 // them every iteration and discards 19 of the 20 results, raft.py:166-172).
 // fnet runs once per frame (the reference encodes every interior frame twice: as image2 of one pair and image1 of
