@@ -108,8 +108,10 @@ namespace vf {
 
 template <typename Tp>
 static int i3d_alloc(vf_i3d* h, Tp** p, size_t count) {
+    // + 64 KB: the overlapping-row TMA view of a conv input (row p = k_per_tap elements from element p*C) extends
+    // (kw-1)*C elements past the last row; those reads meet zero weights but must stay inside the allocation
     void* q = nullptr;
-    cudaError_t e = cudaMalloc(&q, count * sizeof(Tp));
+    cudaError_t e = cudaMalloc(&q, count * sizeof(Tp) + 65536);
     if (e != cudaSuccess) return fail(VF_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(Tp), cudaGetErrorString(e));
     h->allocs.push_back(q);
     *p = static_cast<Tp*>(q);

@@ -86,8 +86,9 @@ namespace vf {
 
 template <typename Tp>
 static int ralloc(vf_raft* h, Tp** p, size_t count) {
+    // + 64 KB: the overlapping-row TMA view of a conv input extends (kw-1)*pitch elements past its last row
     void* q = nullptr;
-    cudaError_t e = cudaMalloc(&q, count * sizeof(Tp));
+    cudaError_t e = cudaMalloc(&q, count * sizeof(Tp) + 65536);
     if (e != cudaSuccess) return fail(VF_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(Tp), cudaGetErrorString(e));
     h->allocs.push_back(q);
     *p = static_cast<Tp*>(q);
