@@ -358,6 +358,11 @@ def run_engine(args, rank: int, world: int, local_rank: int) -> None:
             "sample": f"{sample} of the 1000 frames x {len(ts)} reps (+1 warm-up); PIL transform + fp32 torch tower "
                       f"(oracle port of the reference --cpu path), torch threads={cores}, {cpu_model_name()}",
             "median_s_per_rep": statistics.median(ts)}
+    if rank == 0 and world == 1 and args.torch_gpu:
+        sdg = {k: v.to(dev) for k, v in sd.items()}
+        xg = torch.randn(250, 3, 224, 224, device=dev)
+        line["torch_gpu_baseline"] = _torch_gpu_leg(lambda: clip_tower.encode_image(sdg, xg), 250, UNIT,
+                                                    "oracle port of the ViT-B/32 tower (torch eager, cuBLAS), 250 pre-normalised frames per call, transform excluded")
     if rank == 0:
         emit(line)
     eng.close()
@@ -415,13 +420,34 @@ def _gemm_roofline(fn, reps, algorithmic_flops_per_step, step_ms):
             "launches_per_step": launches // reps, "gemm_share_of_step": (ms / reps) / step_ms}
 
 
+def _torch_gpu_leg(fn, units, unit, what):
+    """The oracle's fp32 torch modules (cuDNN / cuBLAS library calls) on the same GPU: the "library call" bar of
+    SURVEY 8(d).  Measured with TF32 off (the oracle's numerics) and on (the library's fast fp32 path)."""
+    import torch
+    out = {"unit": unit, "what": what}
+    for tf32 in (False, True):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        with torch.no_grad():
+            fn(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+        out["tf32" if tf32 else "fp32"] = units * 2 / (e0.elapsed_time(e1) / 1e3)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return out
+
+
 def run_i3d(args) -> None:
     import torch
     from video_features_b200.i3d_engine import I3DEngine
     from oracle import i3d_net
     torch.cuda.set_device(0)
     sd, wsrc = _weights("rgb")
-    S = int(os.environ.get("VF_BENCH_I3D_STACKS", "16"))
+    S = int(os.environ.get("VF_BENCH_I3D_STACKS", "32"))
     eng = I3DEngine(sd, "rgb", 0, max_stacks=S, max_T=64)
     g = torch.Generator().manual_seed(1)
     frames_host = torch.randint(0, 256, (S, 65, 224, 224, 3), dtype=torch.uint8, generator=g).pin_memory()
@@ -453,6 +479,11 @@ def run_i3d(args) -> None:
         t0 = time.perf_counter(); i3d_net.forward_features(sd, x); dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "stacks/s", "cores": cores, "kind": "port",
                                 "sample": f"1 stack (64x224x224), oracle port of I3D fp32, torch threads={cores}, {cpu_model_name()}"}
+    if args.torch_gpu:
+        sdg = {k: v.cuda() for k, v in sd.items()}
+        xg = torch.cat([i3d_net.rgb_transform(frames_host[i, :64].permute(0, 3, 1, 2).float()) for i in range(2)]).cuda()
+        line["torch_gpu_baseline"] = _torch_gpu_leg(lambda: i3d_net.forward_features(sdg, xg), 2, "stacks/s",
+                                                    "oracle port of I3D (torch conv3d / cuDNN, eager), 2 stacks per call")
     emit(line)
 
 
@@ -500,6 +531,11 @@ def run_raft(args) -> None:
         t0 = time.perf_counter(); raft_net.forward(sd, x[:-1], x[1:], 20); dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": 2.0 / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
                                 "sample": f"2 pairs 272x480, 20 iterations, oracle port of RAFT fp32, torch threads={cores}, {cpu_model_name()}"}
+    if args.torch_gpu:
+        sdg = {k: v.cuda() for k, v in sd.items()}
+        xg = raft_net.pad(frames_host[:9].permute(0, 3, 1, 2).float()).cuda()
+        line["torch_gpu_baseline"] = _torch_gpu_leg(lambda: raft_net.forward(sdg, xg[:-1], xg[1:], 20), 8, "pairs/s",
+                                                    "oracle port of RAFT (torch conv2d / cuDNN, eager), 8 pairs per call, 20 iterations")
     emit(line)
 
 
@@ -511,6 +547,8 @@ def main() -> None:
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--chunk", type=int, default=0, help="frames per tower chunk (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--torch-gpu", action="store_true", dest="torch_gpu",
+                    help="also time the oracle's fp32 torch modules on the same GPU (library-call bar), key torch_gpu_baseline")
     ap.add_argument("--workload", default="clip", choices=["clip", "i3d", "raft"],
                     help="clip = the headline (BASELINE.json configs[1]); i3d / raft = configs[2] / configs[3], 1 GPU")
     args = ap.parse_args()

@@ -167,6 +167,24 @@ if os.path.exists(lp):
         out.append(f"| `{k}` | {v[0]} | {v[1]/1e3:.1f} | {v[1]/v[0]/1e3:.1f} | {100*v[1]/tot:.1f} % |")
     out.append("")
 
+# ---- library-call bar: the oracle's torch modules on the same GPU (bench.py --torch-gpu)
+rows = []
+for w, title in (("clip", "CLIP ViT-B/32 tower"), ("i3d", "I3D rgb"), ("raft", "RAFT -> I3D flow")):
+    src = os.path.join(G, f"r1_torchgpu_{w}.json")
+    if os.path.exists(src):
+        shutil.copy(src, os.path.join(P, f"r1_torchgpu_{w}.json"))
+    try:
+        d = json.loads(open(os.path.join(P, f"r1_torchgpu_{w}.json")).readline())
+        b = d["torch_gpu_baseline"]
+        rows.append(f"| {title} | {d['value']:.0f} {d['unit']} | {b['fp32']:.1f} | x{d['value']/b['fp32']:.1f} | {b['tf32']:.1f} | x{d['value']/b['tf32']:.1f} | {b['what']} |")
+    except Exception:
+        pass
+if rows:
+    out.append("## Library-call bar: the fp32 torch modules of the oracle, eager, on the same B200 (`bench.py --torch-gpu`)\n")
+    out.append("| workload | this engine | torch fp32 (TF32 off) | ratio | torch TF32 | ratio | what |\n|---|---|---|---|---|---|---|")
+    out += rows
+    out.append("\n(The reference runs I3D and RAFT in fp32 and CLIP in fp16 on CUDA; a torch fp16 tower was not measured.)\n")
+
 t = os.path.join(G, "r1_pytest_gpu.txt")
 if os.path.exists(t):
     out.append("## `pytest tests -m gpu` on the same box\n\n```\n" + open(t).read().strip() + "\n```\n")
