@@ -36,55 +36,51 @@ def parallel_feature_extraction(args):
     run(functools.partial(build_extractor, args), len(video_paths), args.device_ids)
 
 
+_FEATURE_TYPES = ('i3d vggish r21d_rgb resnet18 resnet34 resnet50 resnet101 resnet152 raft pwc CLIP-ViT-B/32 CLIP-ViT-B/16 '
+                  'CLIP4CLIP-ViT-B-32 vggish_torch').split()
+
+# (flag, argparse keywords): names, types, defaults, choices and dests are the reference's (main.py:93-149)
+_FLAGS = [
+    ('--feature_type', dict(required=True, choices=_FEATURE_TYPES, help='which extractor to run')),
+    ('--video_paths', dict(nargs='+', help='videos to process')),
+    ('--flow_paths', dict(nargs='+', help='precomputed flow images (I3D --flow_type flow; not built here)')),
+    ('--file_with_video_paths', dict(help='text file, one video path per line')),
+    ('--video_dir', dict(type=str, help='directory whose files are all processed')),
+    ('--flow_dir', dict(type=str, help='root of <video id>/flow_{x,y}_NNNNNN.jpg trees')),
+    ('--device_ids', dict(type=int, nargs='+', help='GPUs to use: one process per id')),
+    ('--cpu', dict(action='store_true', help='accepted for compatibility; refused at run time')),
+    ('--tmp_path', dict(default='./tmp', help='scratch folder')),
+    ('--keep_tmp_files', dict(dest='keep_tmp_files', action='store_true', default=False, help='keep the scratch files')),
+    ('--on_extraction', dict(default='print', choices=['print', 'save_numpy', 'save_pickle'], help='sink of the features')),
+    ('--output_path', dict(default='./output', help='root of the saved features')),
+    ('--output_direct', dict(action='store_true', help='save as <output_path>/<video stem>.npy')),
+    ('--extraction_fps', dict(type=float, help='resample to this frame rate first (I3D)')),
+    ('--extract_method', dict(type=str, help='frame sampler: uni_N or fix_N')),
+    ('--stack_size', dict(type=int, help='frames per I3D stack')),
+    ('--step_size', dict(type=int, help='frames between I3D stacks')),
+    ('--streams', dict(nargs='+', choices=['flow', 'rgb'], help='I3D streams (default: both)')),
+    ('--flow_type', dict(choices=['raft', 'pwc', 'flow'], default='pwc', help='optical flow feeding the I3D flow stream')),
+    ('--batch_size', dict(type=int, default=1, help='frame pairs per RAFT call')),
+    ('--resize_to_larger_edge', dict(dest='resize_to_smaller_edge', action='store_false', default=True,
+                                    help='--side_size applies to the larger edge instead of the smaller one')),
+    ('--side_size', dict(type=int, help='RAFT: resize frames to this edge length first')),
+    ('--show_pred', dict(dest='show_pred', action='store_true', default=False, help='print class predictions (not built here)')),
+]
+
+
 def make_parser():
-    parser = argparse.ArgumentParser(description='Extract Features')
-    parser.add_argument('--feature_type', required=True,
-                        choices=['i3d', 'vggish', 'r21d_rgb', 'resnet18', 'resnet34', 'resnet50', 'resnet101',
-                                 'resnet152', 'raft', 'pwc', 'CLIP-ViT-B/32', 'CLIP-ViT-B/16', 'CLIP4CLIP-ViT-B-32',
-                                 'vggish_torch'])
-    parser.add_argument('--video_paths', nargs='+', help='space-separated paths to videos')
-    parser.add_argument('--flow_paths', nargs='+', help='space-separated paths to video flow images')
-    parser.add_argument('--file_with_video_paths', help='.txt file where each line is a path')
-    parser.add_argument('--video_dir', type=str, help='dir of videos')
-    parser.add_argument('--flow_dir', type=str,
-                        help='dir of optical flow of videos. [flow_dir]/[video id]/[flow_(x/y)_000001.jpg]')
-    parser.add_argument('--device_ids', type=int, nargs='+', help='space-separated device ids')
-    parser.add_argument('--cpu', action='store_true', help='use cpu only')
-    parser.add_argument('--tmp_path', default='./tmp',
-                        help='folder to store the temporary files used for extraction (frames or aud files)')
-    parser.add_argument('--keep_tmp_files', dest='keep_tmp_files', action='store_true', default=False,
-                        help='to keep temp files after feature extraction. (works only for vggish and i3d)')
-    parser.add_argument('--on_extraction', default='print', choices=['print', 'save_numpy', 'save_pickle'],
-                        help='what to do once the stack is extracted')
-    parser.add_argument('--output_path', default='./output', help='where to store results if saved')
-    parser.add_argument('--output_direct', action="store_true",
-                        help='if so, files will be directly saved in output_path')
-    parser.add_argument('--extraction_fps', type=float, help='(Outdated)For original video fps, leave unspecified')
-    parser.add_argument('--extract_method', type=str, help='extraction frames method.')
-    parser.add_argument('--stack_size', type=int, help='Feature time span in fps')
-    parser.add_argument('--step_size', type=int, help='Feature step size in fps')
-    parser.add_argument('--streams', nargs='+', choices=['flow', 'rgb'],
-                        help='Streams to use for feature extraction. Both used if not specified')
-    parser.add_argument('--flow_type', choices=['raft', 'pwc', 'flow'], default='pwc',
-                        help='Flow to use in I3D. PWC is faster while RAFT is more accurate.')
-    parser.add_argument('--batch_size', type=int, default=1,
-                        help='Batchsize (only frame-wise extractors are supported)')
-    parser.add_argument('--resize_to_larger_edge', dest='resize_to_smaller_edge', action='store_false',
-                        default=True, help='The larger side will be resized to this number maintaining the'
-                        + 'aspect ratio. By default, uses the smaller side (as Resize in torchvision).')
-    parser.add_argument('--side_size', type=int,
-                        help='If specified, the input images will be resized to this value in RAFT.')
-    parser.add_argument('--show_pred', dest='show_pred', action='store_true', default=False,
-                        help='to show preds of a model, i.e. on a pre-train dataset (imagenet or kinetics) for each feature')
+    parser = argparse.ArgumentParser(description='B200-native video feature extraction')
+    for flag, kw in _FLAGS:
+        parser.add_argument(flag, **kw)
     return parser
 
 
 if __name__ == "__main__":
     args = make_parser().parse_args()
-    if args.on_extraction in ['save_numpy', 'save_pickle']:
-        print(f'Saving features to {args.output_path}')
+    if args.on_extraction != 'print':
+        print(f'features -> {args.output_path}')
     if args.keep_tmp_files:
-        print(f'Keeping temp files in {args.tmp_path}')
+        print(f'scratch files stay in {args.tmp_path}')
     sanity_check(args)
     if args.cpu:
         raise SystemExit('--cpu: this engine has no CPU path (the reference CPU flow is timed by '

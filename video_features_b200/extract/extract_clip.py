@@ -53,19 +53,16 @@ def load_clip_state_dict(feature_type: str) -> Dict[str, torch.Tensor]:
 class ExtractCLIP(torch.nn.Module):
 
     def __init__(self, args, external_call=False):
-        super(ExtractCLIP, self).__init__()
-        self.feature_type = args.feature_type
+        super().__init__()
+        for name in ('feature_type', 'extraction_fps', 'extract_method', 'on_extraction'):
+            setattr(self, name, getattr(args, name))
         self.path_list = form_list_from_user_input(args)
-        self.extraction_fps = args.extraction_fps
-        self.extract_method = args.extract_method
-        self.on_extraction = args.on_extraction
         self.external_call = external_call
-        if external_call is False:
+        if not external_call:
+            # --output_direct writes <output_path>/<stem>.npy; otherwise a per-feature sub-folder (which cannot exist for
+            # 'CLIP-ViT-B/32': the '/' in the key -- reference quirk)
             self.output_direct = args.output_direct
-            if self.output_direct is True:
-                self.output_path = args.output_path
-            else:
-                self.output_path = os.path.join(args.output_path, self.feature_type)
+            self.output_path = args.output_path if self.output_direct is True else os.path.join(args.output_path, self.feature_type)
         self.progress = tqdm(total=len(self.path_list))
         self._engines: Dict[int, ClipEngine] = {}
 
@@ -86,35 +83,31 @@ class ExtractCLIP(torch.nn.Module):
         """indices {torch.LongTensor} -- indices to self.path_list; the device is taken from ``indices.device``."""
         device = indices.device
         model = self._engine(device)          # one engine per device, kept across calls
-        feats_list = []
+        collected = []
         for idx in indices:
-            try:
-                feats_dict = self.extract(device, model, None, self.path_list[idx])
-                if self.external_call is False:
-                    action_on_extraction(feats_dict, self.path_list[idx], self.output_path,
-                                         self.on_extraction, self.output_direct)
+            video = self.path_list[idx]
+            try:                                # per-video catch-print-continue (extract_clip.py:71-84)
+                feats = self.extract(device, model, None, video)
+                if self.external_call:
+                    collected.append(feats)
                 else:
-                    feats_list.append(feats_dict)
+                    action_on_extraction(feats, video, self.output_path, self.on_extraction, self.output_direct)
             except KeyboardInterrupt:
-                raise KeyboardInterrupt
-            except Exception as e:
-                print(e)
-                print(f'Extraction failed at: {self.path_list[idx]} with error (↑). Continuing extraction')
+                raise
+            except Exception as err:
+                print(err)
+                print(f'Extraction failed at: {video} with error (↑). Continuing extraction')
                 traceback.print_exc()
             self.progress.update()
-        return feats_list
+        return collected
 
     def extract(self, device: torch.device, model: ClipEngine, preprocess_func=None, video_path=None):
         """-> {feature_type: (T,512) float32, 'fps': (), 'timestamps_ms': (T,)}.  ``preprocess_func`` is accepted for
         signature compatibility; the transform is fused into the engine call."""
-        frames, fps, timestamps_ms = extract_frames(str(video_path), self.extract_method)
-        frames = [f for f in frames if f is not None]
-        if len(frames) == 0:
+        decoded, fps, stamps = extract_frames(str(video_path), self.extract_method)
+        decoded = [f for f in decoded if f is not None]
+        if not decoded:
             raise RuntimeError(f"no frames decoded from {video_path}")
-        batch = torch.from_numpy(np.stack(frames))          # (T,H,W,3) uint8, decoder channel order untouched
-        features = model.encode_frames_u8_host(batch)       # H2D + transform + tower + D2H
-        return {
-            self.feature_type: features.numpy(),
-            'fps': np.array(fps),
-            'timestamps_ms': np.array(timestamps_ms),
-        }
+        batch = torch.from_numpy(np.stack(decoded))         # (T,H,W,3) uint8, decoder channel order untouched
+        feats = model.encode_frames_u8_host(batch)          # H2D + transform + tower + D2H
+        return {self.feature_type: feats.numpy(), 'fps': np.array(fps), 'timestamps_ms': np.array(stamps)}

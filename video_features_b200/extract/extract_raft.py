@@ -22,21 +22,20 @@ from ..utils import action_on_extraction, form_list_from_user_input
 from .extract_i3d import load_checkpoint
 
 
+# attributes the reference's constructor copies from `args` unchanged (extract_raft.py:24-36)
+_ARG_ATTRS = ('feature_type', 'batch_size', 'extraction_fps', 'resize_to_smaller_edge', 'side_size', 'show_pred',
+              'keep_tmp_files', 'on_extraction')
+
+
 class ExtractRAFT(torch.nn.Module):
 
     def __init__(self, args):
-        super(ExtractRAFT, self).__init__()
-        self.feature_type = args.feature_type
+        super().__init__()
+        for name in _ARG_ATTRS:
+            setattr(self, name, getattr(args, name))
         self.path_list = form_list_from_user_input(args)
-        self.batch_size = args.batch_size
-        self.extraction_fps = args.extraction_fps
-        self.resize_to_smaller_edge = args.resize_to_smaller_edge
-        self.side_size = args.side_size
-        self.show_pred = args.show_pred
-        self.keep_tmp_files = args.keep_tmp_files
-        self.on_extraction = args.on_extraction
-        self.tmp_path = os.path.join(args.tmp_path, self.feature_type)
-        self.output_path = os.path.join(args.output_path, self.feature_type)
+        # per-feature sub-folders of the scratch and output roots, as the reference lays them out
+        self.tmp_path, self.output_path = (os.path.join(root, self.feature_type) for root in (args.tmp_path, args.output_path))
         self.progress = tqdm(total=len(self.path_list))
         if self.extraction_fps is not None:
             raise NotImplementedError("extraction_fps re-encodes with ffmpeg (outside the rebuilt path, SURVEY.md §2)")
@@ -47,14 +46,14 @@ class ExtractRAFT(torch.nn.Module):
         if device.type != 'cuda':
             raise RuntimeError("the B200 engine has no CPU path: pass indices on a CUDA device")
         for idx in indices:
-            try:
-                feats_dict = self.extract(device, None, self.path_list[idx])
-                action_on_extraction(feats_dict, self.path_list[idx], self.output_path, self.on_extraction)
+            video = self.path_list[idx]
+            try:                                          # per-video catch-print-continue (extract_raft.py:60-75)
+                action_on_extraction(self.extract(device, None, video), video, self.output_path, self.on_extraction)
             except KeyboardInterrupt:
-                raise KeyboardInterrupt
-            except Exception as e:
-                print(e)
-                print(f'Extraction failed at: {self.path_list[idx]} with error (↑). Continuing extraction')
+                raise
+            except Exception as err:
+                print(err)
+                print(f'Extraction failed at: {video} with error (↑). Continuing extraction')
             self.progress.update()
 
     def _engine(self, device: torch.device, h: int, w: int) -> RAFTEngine:
@@ -63,38 +62,36 @@ class ExtractRAFT(torch.nn.Module):
             self._engines[key] = RAFTEngine(load_checkpoint('raft'), key[0], max_frames=self.batch_size + 1, max_h=h, max_w=w)
         return self._engines[key]
 
+    def _flow_of_window(self, window, device) -> list:
+        """window: batch_size+1 RGB frames (H, W, 3) uint8 -> batch_size flow fields as nested lists (float64 once
+        np.array'd, like the reference's `.tolist()`)."""
+        x = torch.from_numpy(np.stack(window)).to(device)
+        if self.side_size is not None:
+            oh, ow = ops.resize_geometry(x.shape[1], x.shape[2], self.side_size, self.resize_to_smaller_edge)
+            if (oh, ow) != tuple(x.shape[1:3]):
+                x = torch.ops.vfeat.resize_u8(x, oh, ow, VF_FILTER_BILINEAR)
+        return self._engine(device, x.shape[1], x.shape[2]).flow(x, iters=20, unpad=True).cpu().tolist()
+
     def extract(self, device, model, video_path=None) -> Dict[str, np.ndarray]:
         import cv2
         cap = cv2.VideoCapture(video_path)
         fps = cap.get(cv2.CAP_PROP_FPS)
-        timestamps_ms, batch, flow_frames = [], [], []
-        first_frame = True
-
-        def run(batch):
-            x = torch.from_numpy(np.stack(batch)).to(device)                     # (B+1, H, W, 3) uint8 RGB
-            if self.side_size is not None:
-                oh, ow = ops.resize_geometry(x.shape[1], x.shape[2], self.side_size, self.resize_to_smaller_edge)
-                if (oh, ow) != tuple(x.shape[1:3]):
-                    x = torch.ops.vfeat.resize_u8(x, oh, ow, VF_FILTER_BILINEAR)
-            eng = self._engine(device, x.shape[1], x.shape[2])
-            flow = eng.flow(x, iters=20, unpad=True)
-            flow_frames.extend(flow.cpu().tolist())
-
+        stamps, window, flows = [], [], []
+        seen_first = False
         while cap.isOpened():
-            frame_exists, bgr = cap.read()
-            if first_frame:
-                first_frame = False
-                if frame_exists is False:
+            ok, bgr = cap.read()
+            if not seen_first:                            # a failed FIRST read is retried (extract_raft.py:124-128)
+                seen_first = True
+                if ok is False:
                     continue
-            if frame_exists:
-                timestamps_ms.append(cap.get(cv2.CAP_PROP_POS_MSEC))
-                batch.append(cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB))
-                if len(batch) - 1 == self.batch_size:
-                    run(batch)
-                    batch = [batch[-1]]
-            else:
-                if len(batch) > 1:
-                    run(batch)
+            if not ok:                                    # end of stream: flush the partial window
+                if len(window) > 1:
+                    flows.extend(self._flow_of_window(window, device))
                 cap.release()
                 break
-        return {self.feature_type: np.array(flow_frames), 'fps': np.array(fps), 'timestamps_ms': np.array(timestamps_ms)}
+            stamps.append(cap.get(cv2.CAP_PROP_POS_MSEC))
+            window.append(cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB))      # the stand-alone extractor swaps to RGB
+            if len(window) == self.batch_size + 1:
+                flows.extend(self._flow_of_window(window, device))
+                window = window[-1:]                      # the last frame opens the next window
+        return {self.feature_type: np.array(flows), 'fps': np.array(fps), 'timestamps_ms': np.array(stamps)}

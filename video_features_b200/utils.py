@@ -56,104 +56,103 @@ class VideoReader:
 def extract_frames(path: str, method: str):
     """utils/utils.py:297-333.  method: ``uni_N`` (N frames uniformly) or ``fix_N`` (N frames per second).
     Returns (frames: list of HxWx3 uint8 BGR arrays or None, fps, timestamps_ms)."""
-    ext = method.split('_')[0]
-    params = method.split('_')[1:]
-    if ext not in ("fix", "uni"):
-        raise NotImplementedError(f'{ext} are not supported')
-    video = VideoReader(str(path))
-    fps, frame_cnt = video.fps, video.frame_cnt
-    mspf = 0.001 / fps                                   # (sic) utils/utils.py:312
-    samples_ix = ops.sample_indices(ext, int(params[0]), frame_cnt, fps)
-    timestamps_ms = [i * mspf for i in samples_ix]
-    frames = [video.get_frame(int(idx)) for idx in samples_ix]
-    return frames, fps, timestamps_ms
+    kind, *params = method.split('_')
+    if kind not in ('fix', 'uni'):
+        raise NotImplementedError(f'{kind} are not supported')
+    reader = VideoReader(str(path))
+    indices = ops.sample_indices(kind, int(params[0]), reader.frame_cnt, reader.fps)
+    per_frame = 0.001 / reader.fps                       # (sic) the reference's unit, utils/utils.py:312
+    return [reader.get_frame(int(i)) for i in indices], reader.fps, [i * per_frame for i in indices]
+
+
+_SINK_EXT = {'save_numpy': 'npy', 'save_pickle': 'pkl'}
+_NOT_FEATURES = ('fps', 'timestamps_ms')
+
+
+def _sink_path(video_path, key: str, output_path: str, on_extraction: str, output_direct: bool) -> str:
+    """<output_path>/<stem>.<ext> when output_direct, else <stem>_<key>.<ext> (utils/utils.py:83-88)."""
+    stem = plb.Path(video_path).stem
+    base = stem if output_direct is True else f'{stem}_{key}'
+    return os.path.join(output_path, f'{base}.{_SINK_EXT[on_extraction]}')
 
 
 def action_on_extraction(feats_dict: Dict[str, np.ndarray], video_path, output_path, on_extraction: str,
                          output_direct: bool = False):
     """utils/utils.py:50-114: print / save_numpy / save_pickle; 'fps' and 'timestamps_ms' are never saved."""
-    suffix = {'save_numpy': 'npy', 'save_pickle': 'pkl'}
-    if type(video_path) is list or type(video_path) is tuple:
+    if on_extraction != 'print' and on_extraction not in _SINK_EXT:
+        if any(k not in _NOT_FEATURES for k in feats_dict):
+            raise NotImplementedError(f'on_extraction: {on_extraction} is not implemented')
+        return
+    if isinstance(video_path, (list, tuple)):            # (video, flow) pairs: named after the video
         video_path = video_path[0]
-    name = plb.Path(video_path).stem
     for key, value in feats_dict.items():
-        if key in ['fps', 'timestamps_ms']:
+        if key in _NOT_FEATURES:
             continue
         if on_extraction == 'print':
             print(key)
             print(value)
             print(f'max: {value.max():.8f}; mean: {value.mean():.8f}; min: {value.min():.8f}')
             print()
-        elif on_extraction in ['save_numpy', 'save_pickle']:
-            os.makedirs(output_path, exist_ok=True)
-            if output_direct is True:
-                fname = f'{name}.{suffix[on_extraction]}'
-            else:
-                fname = f'{name}_{key}.{suffix[on_extraction]}'
-            fpath = os.path.join(output_path, fname)
-            if len(value) == 0:
-                print(f'Warning: the value is empty for {key} @ {fpath}')
-            if on_extraction == 'save_numpy':
-                np.save(fpath, value)
-            else:
-                pickle.dump(value, open(fpath, 'wb'))
+            continue
+        os.makedirs(output_path, exist_ok=True)
+        target = _sink_path(video_path, key, output_path, on_extraction, output_direct)
+        if len(value) == 0:
+            print(f'Warning: the value is empty for {key} @ {target}')
+        if on_extraction == 'save_numpy':
+            np.save(target, value)
         else:
-            raise NotImplementedError(f'on_extraction: {on_extraction} is not implemented')
+            with open(target, 'wb') as f:
+                pickle.dump(value, f)
 
 
 def form_slices(size: int, stack_size: int, step_size: int):
-    """utils/utils.py:117-126"""
-    full_stack_num = (size - stack_size) // step_size + 1
-    return [(i * step_size, i * step_size + stack_size) for i in range(full_stack_num)]
+    """utils/utils.py:117-126: (start, end) of every full stack."""
+    n_full = (size - stack_size) // step_size + 1
+    return [(k * step_size, k * step_size + stack_size) for k in range(n_full)]
 
 
 def sanity_check(args: argparse.Namespace):
     """utils/utils.py:129-150 (the checks that concern CLIP / I3D / RAFT)."""
-    assert os.path.relpath(args.output_path) != os.path.relpath(args.tmp_path), 'The same path for out & tmp'
+    if os.path.relpath(args.output_path) == os.path.relpath(args.tmp_path):
+        raise AssertionError('The same path for out & tmp')
     if args.show_pred:
-        print('You want to see predictions. So, I will use only the first GPU from the list you specified.')
-        args.device_ids = [args.device_ids[0]]
-    if args.feature_type == 'i3d':
-        message = f'I3D model does not support inputs shorter than 10 timestamps. You have: {args.stack_size}'
-        if args.stack_size is not None:
-            assert args.stack_size >= 10, message
+        print('--show_pred: only the first of the listed GPUs is used')
+        args.device_ids = args.device_ids[:1]
+    if args.feature_type == 'i3d' and args.stack_size is not None and args.stack_size < 10:
+        raise AssertionError(f'I3D model does not support inputs shorter than 10 timestamps. You have: {args.stack_size}')
+
+
+def _paired(videos, flows):
+    """(video, flow) pairs whose file stems agree, in the given order."""
+    return [(str(v), str(f)) for v, f in zip(videos, flows) if plb.Path(v).stem == plb.Path(f).stem]
 
 
 def form_list_from_user_input(args: argparse.Namespace) -> list:
     """utils/utils.py:153-204: file with paths / directory glob / explicit list; ValueError when nothing is given or
     a path is missing."""
-    if getattr(args, 'file_with_video_paths', None) is not None:
-        with open(args.file_with_video_paths) as rfile:
-            path_list = [line.replace('\n', '') for line in rfile.readlines()]
-            path_list = [path for path in path_list if len(path) > 0]
-    elif getattr(args, 'video_dir', None) is not None:
-        if getattr(args, 'flow_dir', None) is None:
-            path_list = [str(i) for i in plb.Path(args.video_dir).glob("*")]
+    listing, vdir, vpaths = (getattr(args, k, None) for k in ('file_with_video_paths', 'video_dir', 'video_paths'))
+    fdir, fpaths = getattr(args, 'flow_dir', None), getattr(args, 'flow_paths', None)
+    if listing is not None:
+        with open(listing) as f:
+            paths = [ln.replace('\n', '') for ln in f]
+        paths = [p for p in paths if p]
+    elif vdir is not None:
+        found = list(plb.Path(vdir).glob('*'))               # unsorted, as the reference (utils/utils.py:173)
+        if fdir is None:
+            paths = [str(p) for p in found]
         else:
-            path_list = []
-            v_list, f_list = list(plb.Path(args.video_dir).glob("*")), list(plb.Path(args.flow_dir).glob("*"))
-            v_list.sort(key=lambda x: x.stem)
-            f_list.sort(key=lambda x: x.stem)
-            for path_video, path_flow in zip(v_list, f_list):
-                if path_video.stem == path_flow.stem:
-                    path_list.append((str(path_video), str(path_flow)))
-    elif getattr(args, 'video_paths', None) is not None:
-        if getattr(args, 'flow_paths', None) is None:
-            path_list = args.video_paths
-        else:
-            path_list = []
-            for path_video, path_flow in zip(args.video_paths, args.flow_paths):
-                if plb.Path(path_video).stem == plb.Path(path_flow).stem:
-                    path_list.append((path_video, path_flow))
+            by_stem = lambda x: x.stem
+            paths = _paired(sorted(found, key=by_stem), sorted(plb.Path(fdir).glob('*'), key=by_stem))
+    elif vpaths is not None:
+        paths = vpaths if fpaths is None else _paired(vpaths, fpaths)
     else:
         raise ValueError('no video provided')
 
-    for path in path_list:
-        if type(path) is tuple:
-            assert os.path.exists(path[0])
-            assert os.path.exists(path[1])
-        else:
-            if not os.path.exists(path):
-                print(f'The path does not exist: {path}')
-                raise ValueError('path not exist')
-    return path_list
+    for entry in paths:
+        if isinstance(entry, tuple):
+            assert os.path.exists(entry[0])
+            assert os.path.exists(entry[1])
+        elif not os.path.exists(entry):
+            print(f'The path does not exist: {entry}')
+            raise ValueError('path not exist')
+    return paths
