@@ -1,0 +1,91 @@
+"""Output sink (utils/utils.py:50-114 semantics) and the opt-in extras of SURVEY 8(f) rank 2: the writer thread and the
+resume check.  CPU only."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from video_features_b200.utils import (AsyncSink, action_on_extraction, already_extracted, form_list_from_user_input,
+                                       form_slices, sink_targets)
+
+
+def _feats(key, n=4):
+    return {key: np.arange(n * 3, dtype=np.float32).reshape(n, 3), 'fps': np.array(25.0), 'timestamps_ms': np.arange(n)}
+
+
+def test_sink_file_names_follow_the_reference(tmp_path):
+    out = str(tmp_path / "o")
+    action_on_extraction(_feats('rgb'), "/v/clip_a.mp4", out, 'save_numpy')
+    action_on_extraction(_feats('CLIP'), ("/v/clip_b.mp4", "/f/clip_b"), out, 'save_numpy', output_direct=True)
+    action_on_extraction(_feats('flow'), "/v/clip_c.avi", out, 'save_pickle')
+    assert sorted(os.listdir(out)) == ["clip_a_rgb.npy", "clip_b.npy", "clip_c_flow.pkl"]        # fps / timestamps never saved
+    assert np.array_equal(np.load(os.path.join(out, "clip_a_rgb.npy")), _feats('rgb')['rgb'])
+    assert np.array_equal(pickle.load(open(os.path.join(out, "clip_c_flow.pkl"), "rb")), _feats('flow')['flow'])
+    with pytest.raises(NotImplementedError):
+        action_on_extraction(_feats('rgb'), "/v/x.mp4", out, 'save_hdf5')
+    # the reference's quirk 4: a key with '/' points into a directory that does not exist
+    with pytest.raises(FileNotFoundError):
+        action_on_extraction(_feats('CLIP-ViT-B/32'), "/v/x.mp4", out, 'save_numpy')
+
+
+def test_print_sink_writes_nothing(tmp_path, capsys):
+    action_on_extraction(_feats('rgb'), "/v/a.mp4", str(tmp_path / "o"), 'print')
+    assert not (tmp_path / "o").exists()
+    text = capsys.readouterr().out
+    assert text.startswith("rgb\n") and "max: 11.00000000; mean: 5.50000000; min: 0.00000000" in text
+
+
+def test_resume_check_and_targets(tmp_path):
+    out = str(tmp_path / "o")
+    assert sink_targets(['rgb', 'flow', 'fps'], "/v/a.mp4", out, 'save_numpy') == [os.path.join(out, "a_rgb.npy"),
+                                                                                  os.path.join(out, "a_flow.npy")]
+    assert sink_targets(['rgb'], "/v/a.mp4", out, 'print') == []
+    assert not already_extracted(['rgb', 'flow'], "/v/a.mp4", out, 'save_numpy')
+    action_on_extraction(_feats('rgb'), "/v/a.mp4", out, 'save_numpy')
+    assert not already_extracted(['rgb', 'flow'], "/v/a.mp4", out, 'save_numpy')          # flow still missing
+    action_on_extraction(_feats('flow'), "/v/a.mp4", out, 'save_numpy')
+    assert already_extracted(['rgb', 'flow'], "/v/a.mp4", out, 'save_numpy')
+    open(os.path.join(out, "a_flow.npy"), "w").close()                                     # truncated file = not done
+    assert not already_extracted(['rgb', 'flow'], "/v/a.mp4", out, 'save_numpy')
+    assert not already_extracted(['rgb'], "/v/a.mp4", out, 'print')
+
+
+def test_async_sink_writes_the_same_files_and_survives_a_failed_write(tmp_path, capsys):
+    out = str(tmp_path / "o")
+    with AsyncSink(max_pending=2) as sink:
+        for i in range(6):
+            sink.submit(_feats('rgb', n=i + 1), f"/v/clip{i}.mp4", out, 'save_numpy')
+        sink.submit(_feats('bad/key'), "/v/clipX.mp4", out, 'save_numpy')                  # write fails, extraction goes on
+        sink.submit(_feats('flow'), "/v/clip0.mp4", out, 'save_numpy')
+    assert sink.written == 7 and len(sink.errors) == 1 and sink.errors[0][0] == "/v/clipX.mp4"
+    assert "Saving failed at: /v/clipX.mp4" in capsys.readouterr().out
+    for i in range(6):
+        assert np.load(os.path.join(out, f"clip{i}_rgb.npy")).shape == (i + 1, 3)
+    assert os.path.exists(os.path.join(out, "clip0_flow.npy"))
+    with pytest.raises(RuntimeError):
+        sink.submit(_feats('rgb'), "/v/late.mp4", out, 'save_numpy')
+
+
+def test_path_listing_and_slices(tmp_path):
+    import argparse
+    (tmp_path / "v").mkdir(); (tmp_path / "f").mkdir()
+    for n in ("b.mp4", "a.mp4"):
+        (tmp_path / "v" / n).write_bytes(b"x")
+    for n in ("a", "b"):
+        (tmp_path / "f" / n).mkdir()
+    ns = argparse.Namespace(file_with_video_paths=None, video_dir=str(tmp_path / "v"), flow_dir=str(tmp_path / "f"),
+                            video_paths=None, flow_paths=None)
+    assert form_list_from_user_input(ns) == [(str(tmp_path / "v" / "a.mp4"), str(tmp_path / "f" / "a")),
+                                             (str(tmp_path / "v" / "b.mp4"), str(tmp_path / "f" / "b"))]
+    lst = tmp_path / "list.txt"
+    lst.write_text(f"{tmp_path / 'v' / 'a.mp4'}\n\n{tmp_path / 'v' / 'b.mp4'}\n")
+    ns = argparse.Namespace(file_with_video_paths=str(lst), video_dir=None, flow_dir=None, video_paths=None, flow_paths=None)
+    assert form_list_from_user_input(ns) == [str(tmp_path / "v" / "a.mp4"), str(tmp_path / "v" / "b.mp4")]
+    ns = argparse.Namespace(file_with_video_paths=None, video_dir=None, flow_dir=None, video_paths=[str(tmp_path / "nope.mp4")],
+                            flow_paths=None)
+    with pytest.raises(ValueError, match="path not exist"):
+        form_list_from_user_input(ns)
+    with pytest.raises(ValueError, match="no video provided"):
+        form_list_from_user_input(argparse.Namespace())
+    assert form_slices(65, 64, 64) == [(0, 64)] and form_slices(130, 64, 32) == [(0, 64), (32, 96), (64, 128)]

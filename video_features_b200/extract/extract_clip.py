@@ -23,7 +23,7 @@ import torch
 from tqdm import tqdm
 
 from ..clip_engine import ClipEngine
-from ..utils import action_on_extraction, extract_frames, form_list_from_user_input
+from ..utils import AsyncSink, action_on_extraction, already_extracted, extract_frames, form_list_from_user_input
 
 _CKPT_NAMES = {'CLIP-ViT-B/32': 'ViT-B-32.pt', 'CLIP4CLIP-ViT-B-32': 'CLIP4CLIP-ViT-B-32.pth'}
 
@@ -84,21 +84,36 @@ class ExtractCLIP(torch.nn.Module):
         device = indices.device
         model = self._engine(device)          # one engine per device, kept across calls
         collected = []
-        for idx in indices:
-            video = self.path_list[idx]
-            try:                                # per-video catch-print-continue (extract_clip.py:71-84)
-                feats = self.extract(device, model, None, video)
-                if self.external_call:
-                    collected.append(feats)
-                else:
-                    action_on_extraction(feats, video, self.output_path, self.on_extraction, self.output_direct)
-            except KeyboardInterrupt:
-                raise
-            except Exception as err:
-                print(err)
-                print(f'Extraction failed at: {video} with error (↑). Continuing extraction')
-                traceback.print_exc()
-            self.progress.update()
+        # opt-in extras beyond the reference: VF_ASYNC_SINK=1 saves from a writer thread,
+        # VF_RESUME=1 skips videos whose output files already exist
+        saving = not self.external_call
+        sink = AsyncSink() if saving and os.environ.get("VF_ASYNC_SINK") == "1" else None
+        resume = saving and os.environ.get("VF_RESUME") == "1"
+        try:
+            for idx in indices:
+                video = self.path_list[idx]
+                try:                                # per-video catch-print-continue (extract_clip.py:71-84)
+                    if resume and already_extracted([self.feature_type], video, self.output_path, self.on_extraction,
+                                                    self.output_direct):
+                        self.progress.update()
+                        continue
+                    feats = self.extract(device, model, None, video)
+                    if self.external_call:
+                        collected.append(feats)
+                    elif sink is not None:
+                        sink.submit(feats, video, self.output_path, self.on_extraction, self.output_direct)
+                    else:
+                        action_on_extraction(feats, video, self.output_path, self.on_extraction, self.output_direct)
+                except KeyboardInterrupt:
+                    raise
+                except Exception as err:
+                    print(err)
+                    print(f'Extraction failed at: {video} with error (↑). Continuing extraction')
+                    traceback.print_exc()
+                self.progress.update()
+        finally:
+            if sink is not None:
+                sink.close()
         return collected
 
     def extract(self, device: torch.device, model: ClipEngine, preprocess_func=None, video_path=None):

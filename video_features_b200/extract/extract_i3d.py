@@ -25,7 +25,7 @@ from .. import ops
 from .._lib import VF_FILTER_BILINEAR
 from ..i3d_engine import I3DEngine
 from ..raft_engine import RAFTEngine
-from ..utils import VideoReader, action_on_extraction, form_list_from_user_input
+from ..utils import AsyncSink, already_extracted, VideoReader, action_on_extraction, form_list_from_user_input
 
 PRE_CENTRAL_CROP_MIN_SIDE_SIZE = 256
 CENTRAL_CROP_MIN_SIDE_SIZE = 224
@@ -86,20 +86,32 @@ class ExtractI3D(torch.nn.Module):
         device = indices.device
         models = self._load(device)
         feats_list = []
-        for idx in indices:
-            try:
-                feats_dict = self.extract(device, None, models, self.path_list[idx])
-                if self.external_call is False:
-                    action_on_extraction(feats_dict, self.path_list[idx], self.output_path, self.on_extraction)
-                else:
-                    feats_list.append(feats_dict)
-            except KeyboardInterrupt:
-                raise KeyboardInterrupt
-            except Exception as e:
-                print(e)
-                print(f'Extraction failed at: {self.path_list[idx]}. Continuing extraction')
-                traceback.print_exc()
-            self.progress.update()
+        saving = self.external_call is False           # opt-in extras, see ExtractCLIP.forward
+        sink = AsyncSink() if saving and os.environ.get("VF_ASYNC_SINK") == "1" else None
+        resume = saving and os.environ.get("VF_RESUME") == "1"
+        try:
+            for idx in indices:
+                try:
+                    if resume and already_extracted(self.streams, self.path_list[idx], self.output_path, self.on_extraction):
+                        self.progress.update()
+                        continue
+                    feats_dict = self.extract(device, None, models, self.path_list[idx])
+                    if self.external_call is not False:
+                        feats_list.append(feats_dict)
+                    elif sink is not None:
+                        sink.submit(feats_dict, self.path_list[idx], self.output_path, self.on_extraction)
+                    else:
+                        action_on_extraction(feats_dict, self.path_list[idx], self.output_path, self.on_extraction)
+                except KeyboardInterrupt:
+                    raise KeyboardInterrupt
+                except Exception as e:
+                    print(e)
+                    print(f'Extraction failed at: {self.path_list[idx]}. Continuing extraction')
+                    traceback.print_exc()
+                self.progress.update()
+        finally:
+            if sink is not None:
+                sink.close()
         return feats_list
 
     def _run_on_a_stack(self, feats_dict, frames_u8: torch.Tensor, models: dict, device: torch.device):

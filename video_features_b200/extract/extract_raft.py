@@ -18,7 +18,7 @@ from tqdm import tqdm
 from .. import ops
 from .._lib import VF_FILTER_BILINEAR
 from ..raft_engine import RAFTEngine
-from ..utils import action_on_extraction, form_list_from_user_input
+from ..utils import AsyncSink, action_on_extraction, already_extracted, form_list_from_user_input
 from .extract_i3d import load_checkpoint
 
 
@@ -45,16 +45,29 @@ class ExtractRAFT(torch.nn.Module):
         device = indices.device
         if device.type != 'cuda':
             raise RuntimeError("the B200 engine has no CPU path: pass indices on a CUDA device")
-        for idx in indices:
-            video = self.path_list[idx]
-            try:                                          # per-video catch-print-continue (extract_raft.py:60-75)
-                action_on_extraction(self.extract(device, None, video), video, self.output_path, self.on_extraction)
-            except KeyboardInterrupt:
-                raise
-            except Exception as err:
-                print(err)
-                print(f'Extraction failed at: {video} with error (↑). Continuing extraction')
-            self.progress.update()
+        sink = AsyncSink() if os.environ.get("VF_ASYNC_SINK") == "1" else None     # opt-in extras, see ExtractCLIP.forward
+        resume = os.environ.get("VF_RESUME") == "1"
+        try:
+            for idx in indices:
+                video = self.path_list[idx]
+                try:                                      # per-video catch-print-continue (extract_raft.py:60-75)
+                    if resume and already_extracted([self.feature_type], video, self.output_path, self.on_extraction):
+                        self.progress.update()
+                        continue
+                    feats = self.extract(device, None, video)
+                    if sink is not None:
+                        sink.submit(feats, video, self.output_path, self.on_extraction)
+                    else:
+                        action_on_extraction(feats, video, self.output_path, self.on_extraction)
+                except KeyboardInterrupt:
+                    raise
+                except Exception as err:
+                    print(err)
+                    print(f'Extraction failed at: {video} with error (↑). Continuing extraction')
+                self.progress.update()
+        finally:
+            if sink is not None:
+                sink.close()
 
     def _engine(self, device: torch.device, h: int, w: int) -> RAFTEngine:
         key = (device.index or 0, h, w)

@@ -11,7 +11,9 @@ import argparse
 import os
 import pathlib as plb
 import pickle
-from typing import Dict, List
+import queue
+import threading
+from typing import Dict, List, Optional
 
 import numpy as np
 
@@ -103,6 +105,67 @@ def action_on_extraction(feats_dict: Dict[str, np.ndarray], video_path, output_p
         else:
             with open(target, 'wb') as f:
                 pickle.dump(value, f)
+
+
+def sink_targets(feats_keys, video_path, output_path, on_extraction: str, output_direct: bool = False) -> List[str]:
+    """Files `action_on_extraction` would write for these feature keys ([] for 'print')."""
+    if on_extraction not in _SINK_EXT:
+        return []
+    if isinstance(video_path, (list, tuple)):
+        video_path = video_path[0]
+    return [_sink_path(video_path, k, output_path, on_extraction, output_direct) for k in feats_keys if k not in _NOT_FEATURES]
+
+
+def already_extracted(feats_keys, video_path, output_path, on_extraction: str, output_direct: bool = False) -> bool:
+    """Resume check (the reference has none): every output file of this video exists and is
+    non-empty.  Only meaningful for the saving sinks."""
+    targets = sink_targets(feats_keys, video_path, output_path, on_extraction, output_direct)
+    return bool(targets) and all(os.path.isfile(t) and os.path.getsize(t) > 0 for t in targets)
+
+
+class AsyncSink:
+    """Writer thread behind `action_on_extraction`: the extractor hands a finished feature dict
+    over and goes on with the next video while `np.save` / `pickle.dump` run here.  Same files, same names, same
+    printed warnings; a failed write is reported like a failed extraction (message + continue) and counted in
+    ``errors``.  ``close()`` drains the queue; use as a context manager."""
+
+    def __init__(self, max_pending: int = 8):
+        self._q: "queue.Queue[Optional[tuple]]" = queue.Queue(maxsize=max_pending)
+        self.errors: List[tuple] = []
+        self.written = 0
+        self._t = threading.Thread(target=self._run, name="vf-sink", daemon=True)
+        self._t.start()
+
+    def _run(self):
+        while True:
+            item = self._q.get()
+            if item is None:
+                return
+            feats, video_path, rest = item
+            try:
+                action_on_extraction(feats, video_path, *rest)
+                self.written += 1
+            except Exception as err:                     # mirror the extractors' per-video catch-print-continue
+                self.errors.append((video_path, err))
+                print(err)
+                print(f'Saving failed at: {video_path}. Continuing extraction')
+
+    def submit(self, feats_dict, video_path, output_path, on_extraction, output_direct: bool = False):
+        if not self._t.is_alive():
+            raise RuntimeError("AsyncSink is closed")
+        self._q.put((feats_dict, video_path, (output_path, on_extraction, output_direct)))   # blocks when max_pending wait
+
+    def close(self):
+        if self._t.is_alive():
+            self._q.put(None)
+            self._t.join()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
 
 
 def form_slices(size: int, stack_size: int, step_size: int):
