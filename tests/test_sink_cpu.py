@@ -89,3 +89,82 @@ def test_path_listing_and_slices(tmp_path):
     with pytest.raises(ValueError, match="no video provided"):
         form_list_from_user_input(argparse.Namespace())
     assert form_slices(65, 64, 64) == [(0, 64)] and form_slices(130, 64, 32) == [(0, 64), (32, 96), (64, 128)]
+
+
+# ---- the forward loops of the three extractors, with the GPU work stubbed out (host logic only)
+class _FakeIndices(list):
+    """iterable of ints with a `.device` whose type is 'cuda' (the extractors take the device from the indices)."""
+    class _Dev:
+        type, index = 'cuda', 0
+    device = _Dev()
+
+
+def _ns(tmp_path, **kw):
+    import argparse
+    vids = []
+    for n in ("a.mp4", "b.mp4", "c.mp4"):
+        p = tmp_path / n
+        p.write_bytes(b"x")
+        vids.append(str(p))
+    d = dict(feature_type='i3d', video_paths=vids, flow_paths=None, file_with_video_paths=None, video_dir=None, flow_dir=None,
+             extraction_fps=None, extract_method='uni_4', on_extraction='save_numpy', output_path=str(tmp_path / "out"),
+             output_direct=False, tmp_path=str(tmp_path / "tmp"), streams=['rgb'], flow_type='raft', stack_size=None,
+             step_size=None, show_pred=False, keep_tmp_files=False, batch_size=1, resize_to_smaller_edge=True, side_size=None)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+@pytest.mark.parametrize("mode", ["default", "async", "resume"])
+def test_extractor_forward_loops_with_stubbed_engines(tmp_path, monkeypatch, mode):
+    from video_features_b200.extract.extract_clip import ExtractCLIP
+    from video_features_b200.extract.extract_i3d import ExtractI3D
+    from video_features_b200.extract.extract_raft import ExtractRAFT
+    monkeypatch.delenv("VF_ASYNC_SINK", raising=False)
+    monkeypatch.delenv("VF_RESUME", raising=False)
+    if mode == "async":
+        monkeypatch.setenv("VF_ASYNC_SINK", "1")
+    calls = []
+
+    def fake_extract(key):
+        def f(self, *a, **k):
+            video = a[-1] if a else k.get('video_path')
+            video = k.get('video_path', video)
+            calls.append((key, os.path.basename(str(video))))
+            if os.path.basename(str(video)) == "b.mp4":
+                raise RuntimeError("decoder says no")                  # per-video catch-print-continue
+            return _feats(key)
+        return f
+
+    # CLIP (output_direct, the documented way to save CLIP features)
+    ex = ExtractCLIP(_ns(tmp_path, feature_type='CLIP-ViT-B/32', output_direct=True))
+    monkeypatch.setattr(ExtractCLIP, "_engine", lambda self, device: object())
+    monkeypatch.setattr(ExtractCLIP, "extract", fake_extract('CLIP-ViT-B/32'))
+    out = tmp_path / "out"
+    if mode == "resume":
+        out.mkdir()
+        np.save(out / "a.npy", np.zeros((1, 3), np.float32))
+        monkeypatch.setenv("VF_RESUME", "1")
+    assert ex(_FakeIndices([0, 1, 2])) == []
+    assert sorted(os.listdir(out)) == ["a.npy", "c.npy"]
+    assert [c[1] for c in calls] == (["b.mp4", "c.mp4"] if mode == "resume" else ["a.mp4", "b.mp4", "c.mp4"])
+    # external_call=True returns the dicts and writes nothing
+    calls.clear()
+    exx = ExtractCLIP(_ns(tmp_path, feature_type='CLIP-ViT-B/32'), external_call=True)
+    got = exx(_FakeIndices([0, 2]))
+    assert len(got) == 2 and set(got[0]) == {'CLIP-ViT-B/32', 'fps', 'timestamps_ms'}
+
+    # I3D: files <stem>_<stream>.npy under <output_path>/i3d
+    calls.clear()
+    monkeypatch.delenv("VF_RESUME", raising=False)
+    ei = ExtractI3D(_ns(tmp_path))
+    monkeypatch.setattr(ExtractI3D, "_load", lambda self, device: {})
+    monkeypatch.setattr(ExtractI3D, "extract", fake_extract('rgb'))
+    assert ei(_FakeIndices([0, 1, 2])) == []
+    assert sorted(os.listdir(out / "i3d")) == ["a_rgb.npy", "c_rgb.npy"] and len(calls) == 3
+
+    # RAFT: forward returns None, files under <output_path>/raft
+    calls.clear()
+    er = ExtractRAFT(_ns(tmp_path, feature_type='raft'))
+    monkeypatch.setattr(ExtractRAFT, "extract", fake_extract('raft'))
+    assert er(_FakeIndices([0, 1, 2])) is None
+    assert sorted(os.listdir(out / "raft")) == ["a_raft.npy", "c_raft.npy"] and len(calls) == 3
