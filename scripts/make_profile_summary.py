@@ -167,6 +167,33 @@ if os.path.exists(lp):
         out.append(f"| `{k}` | {v[0]} | {v[1]/1e3:.1f} | {v[1]/v[0]/1e3:.1f} | {100*v[1]/tot:.1f} % |")
     out.append("")
 
+# ---- ncu --set full of other kernels captured during the round (attention, epilogue-only GEMMs)
+for rep_name, title in (("prof_ln", "add_layernorm768_kernel (HBM-bound; kernel unchanged since this capture)"),
+                        ("r1_prof_attn", "attention50_kernel (250-frame chunk, 3000 blocks)"),
+                        ("r1_prof_epi", "epilogue-dominated GEMMs: K = 64, M = 12000, N = 3072, fp16 out; launch 0 = +bias, launch 1 = +bias+QuickGELU")):
+    rep = os.path.join(G, rep_name + ".ncu-rep")
+    csvp = os.path.join(P, rep_name + "_raw.csv")
+    if os.path.exists(rep):
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        if raw.strip():
+            open(csvp, "w").write(raw)
+    if os.path.exists(csvp):
+        rr = list(csv.reader(open(csvp).read().splitlines()))
+        if len(rr) > 2:
+            hdr, units, data = rr[0], rr[1], rr[2:]
+            want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+                    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+                    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+                    "launch__registers_per_thread", "launch__grid_size"]
+            out.append(f"## ncu `--set full`: {title}\n")
+            out.append("| metric | unit | " + " | ".join(f"launch {i}" for i in range(len(data))) + " |\n|---|---|" + "---|" * len(data))
+            for w in want:
+                if w in hdr:
+                    i = hdr.index(w)
+                    out.append(f"| {w} | {units[i]} | " + " | ".join(d[i][:14] for d in data) + " |")
+            out.append("")
+
 # ---- library-call bar: the oracle's torch modules on the same GPU (bench.py --torch-gpu)
 rows = []
 for w, title in (("clip", "CLIP ViT-B/32 tower"), ("i3d", "I3D rgb"), ("raft", "RAFT -> I3D flow")):
