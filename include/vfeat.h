@@ -113,6 +113,11 @@ int vf_clip_encode_u8(vf_clip_t* h, const uint8_t* frames, int n, int src_h, int
  * `stream` and synchronises it before returning (the call ExtractCLIP.extract makes per video). */
 int vf_clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, int src_h, int src_w, float* out_host,
                            void* stream);
+/* Host frames in, features left ON THE DEVICE in out_dev (n x 512 fp32, ordered on `stream`) -- what a rank hands to the
+ * all-gather of main.py's --device_ids dispatch (main.py:49-53) -- and, when out_host is not NULL, copied to the host as
+ * well.  Returns once the host frames have been consumed (and out_host, if given, is complete). */
+int vf_clip_encode_u8_host_dev(vf_clip_t* h, const uint8_t* frames_host, int n, int src_h, int src_w, float* out_dev,
+                               float* out_host, void* stream);
 /* number of kernels this library has launched on behalf of `h` so far (diagnostics / bench). */
 int64_t vf_clip_launch_count(const vf_clip_t* h);
 /* Roofline instrumentation for bench.py: while enabled, every tensor-core GEMM launch of `h` is bracketed by a

@@ -30,10 +30,33 @@ def build_extractor(args):
     raise NotADirectoryError                      # main.py:41
 
 
+def _pin_path_list(args):
+    """Resolve the user's listing ONCE, here in the parent: every worker then sees the same list in the same order (a
+    directory glob is unordered, and shard r is only meaningful against one enumeration).  Returns the list."""
+    paths = form_list_from_user_input(args)
+    if paths and isinstance(paths[0], tuple):
+        args.video_paths, args.flow_paths = [p[0] for p in paths], [p[1] for p in paths]
+    else:
+        args.video_paths, args.flow_paths = list(paths), None
+    args.file_with_video_paths = args.video_dir = args.flow_dir = None
+    return paths
+
+
+def _save_gathered(target, blocks):
+    """--gather_features: every video's feature block, list order, in one .npz (rows + per-video row counts)."""
+    import numpy as np
+    rows = np.concatenate([b.numpy() for b in blocks]) if blocks else np.zeros((0, 0), np.float32)
+    np.savez(target, features=rows, rows_per_video=np.array([b.shape[0] for b in blocks], dtype=np.int64))
+    print(f'gathered {len(blocks)} feature blocks ({rows.shape[0]} rows) -> {target}')
+
+
 def parallel_feature_extraction(args):
     from video_features_b200.dispatch import parallel_feature_extraction as run
-    video_paths = form_list_from_user_input(args)
-    run(functools.partial(build_extractor, args), len(video_paths), args.device_ids)
+    video_paths = _pin_path_list(args)
+    gather = getattr(args, 'gather_features', None)
+    key = {'i3d': (args.streams or ['rgb'])[0]}.get(args.feature_type, args.feature_type)
+    run(functools.partial(build_extractor, args), len(video_paths), args.device_ids,
+        gather_key=key if gather else None, on_gathered=functools.partial(_save_gathered, gather) if gather else None)
 
 
 _FEATURE_TYPES = ('i3d vggish r21d_rgb resnet18 resnet34 resnet50 resnet101 resnet152 raft pwc CLIP-ViT-B/32 CLIP-ViT-B/16 '
@@ -43,7 +66,7 @@ _FEATURE_TYPES = ('i3d vggish r21d_rgb resnet18 resnet34 resnet50 resnet101 resn
 _FLAGS = [
     ('--feature_type', dict(required=True, choices=_FEATURE_TYPES, help='which extractor to run')),
     ('--video_paths', dict(nargs='+', help='videos to process')),
-    ('--flow_paths', dict(nargs='+', help='precomputed flow images (I3D --flow_type flow; not built here)')),
+    ('--flow_paths', dict(nargs='+', help='folders of precomputed flow images, one per video (I3D --flow_type flow)')),
     ('--file_with_video_paths', dict(help='text file, one video path per line')),
     ('--video_dir', dict(type=str, help='directory whose files are all processed')),
     ('--flow_dir', dict(type=str, help='root of <video id>/flow_{x,y}_NNNNNN.jpg trees')),
@@ -65,6 +88,9 @@ _FLAGS = [
                                     help='--side_size applies to the larger edge instead of the smaller one')),
     ('--side_size', dict(type=int, help='RAFT: resize frames to this edge length first')),
     ('--show_pred', dict(dest='show_pred', action='store_true', default=False, help='print class predictions (not built here)')),
+    # not in the reference: after extraction, ONE all-gather (NCCL over NVLink) returns every rank's feature blocks and
+    # rank 0 writes them, list order, to this .npz
+    ('--gather_features', dict(type=str, default=None, help='also all-gather the features of all GPUs into this .npz')),
 ]
 
 

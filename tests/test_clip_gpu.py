@@ -82,6 +82,29 @@ def test_encode_multi_chunk_vs_gpu_fp32_oracle(tower, cuda_device):
     assert torch.equal(y1.cpu(), y[100:101].cpu())
 
 
+def test_encode_with_outlier_channel_weights(cuda_device):
+    """Trained ViT-B/32 weights have what random ones lack: residual-stream channels of magnitude 50-200, heavy-tailed
+    LayerNorm gains, loud projection rows (synthetic_weights.clip_vit_b32_state_dict(outliers=True)).  The engine stores
+    QKV / attention / MLP activations in fp16: this is the regime that would break it.  Same 1e-3 / 1e-3 bar."""
+    from oracle import clip_tower
+    from video_features_b200 import synthetic_weights
+    from video_features_b200.clip_engine import ClipEngine
+    sd = synthetic_weights.clip_vit_b32_state_dict(5, outliers=True)
+    g = torch.Generator().manual_seed(4)
+    frames = torch.randint(0, 256, (24, 224, 224, 3), dtype=torch.uint8, generator=g)
+    frames[12:] = frames[12:] // 4 + 96                                    # half of them low-contrast
+    sd_gpu = {k: v.to(cuda_device) for k, v in sd.items()}
+    ref, hidden = clip_tower.encode_image(sd_gpu, _transform_224(frames).to(cuda_device), return_hidden=True)
+    peak = max(float(h.abs().max()) for h in hidden)
+    assert peak > 50.0, f"the outlier regime was not reached (residual peak {peak:.1f})"
+    eng = ClipEngine(sd, device=0)
+    try:
+        y = eng.encode_frames_u8(frames.to(cuda_device))
+        print(f"outlier weights: residual peak {peak:.1f};", _check_rows(y, ref))
+    finally:
+        eng.close()
+
+
 def test_encode_empty_and_single(tower, cuda_device):
     sd, eng = tower
     out = eng.encode_frames_u8(torch.empty((0, 224, 224, 3), dtype=torch.uint8, device=cuda_device))

@@ -73,3 +73,42 @@ def test_main_cli_parser_matches_reference_flags():
     assert a.tmp_path == "./tmp" and a.output_path == "./output" and a.cpu is False
     with pytest.raises(NotADirectoryError):
         main.build_extractor(argparse.Namespace(feature_type="nonsense"))
+
+
+class _BlockMaker:
+    """Stands in for ExtractCLIP under dispatch: video v yields a (v % 3 + 1, 4) block filled with v."""
+    keep_features = False
+
+    def __call__(self, indices):
+        assert self.keep_features is True                      # dispatch asked for the features back
+        return [{'feat': torch.full((int(i) % 3 + 1, 4), float(i)).numpy()} for i in indices]
+
+
+def _make_block_maker():
+    return _BlockMaker()
+
+
+def _write_gathered(path, blocks):
+    torch.save([b.clone() for b in blocks], path)
+
+
+@pytest.mark.parametrize("world", [1, 3])
+def test_parallel_feature_extraction_gathers_blocks_in_list_order(tmp_path, world):
+    """gather_key: every rank's feature blocks come back through ONE all-gather, list order, on rank 0 -- including a
+    world where the last rank's shard is shorter, and the single-device case (no process group at all)."""
+    import functools
+    from video_features_b200.dispatch import parallel_feature_extraction
+    target = str(tmp_path / "g.pt")
+    parallel_feature_extraction(_make_block_maker, 7, list(range(world)), backend="gloo", gather_key='feat',
+                                on_gathered=functools.partial(_write_gathered, target))
+    blocks = torch.load(target)
+    assert [tuple(b.shape) for b in blocks] == [(v % 3 + 1, 4) for v in range(7)]
+    assert all(float(b[0, 0]) == float(v) and float(b[-1, -1]) == float(v) for v, b in enumerate(blocks))
+
+
+def test_free_port_is_bindable():
+    import socket
+    from video_features_b200.dispatch import free_port
+    p = free_port()
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+        s.bind(("127.0.0.1", p))

@@ -32,7 +32,7 @@ def _args(paths, out, method="uni_6", **kw):
 def test_extract_clip_matches_oracle_and_writes_files(cuda_device, tmp_path, monkeypatch):
     monkeypatch.setenv("VF_CLIP_SYNTHETIC", "0")
     from oracle import clip_preprocess, clip_tower
-    from video_features_b200 import utils
+    from video_features_b200 import synthetic_weights, utils
     from video_features_b200.extract.extract_clip import ExtractCLIP
     vid = str(tmp_path / "clip_a.mp4")
     _write_video(vid)
@@ -43,7 +43,7 @@ def test_extract_clip_matches_oracle_and_writes_files(cuda_device, tmp_path, mon
     saved = np.load(os.path.join(out, "clip_a.npy"))
     assert saved.shape == (6, 512) and saved.dtype == np.float32
     frames, fps, ts = utils.extract_frames(vid, "uni_6")
-    ref = clip_tower.encode_image(clip_tower.synthetic_state_dict(0), clip_preprocess.preprocess_batch(frames)).numpy()
+    ref = clip_tower.encode_image(synthetic_weights.clip_vit_b32_state_dict(0), clip_preprocess.preprocess_batch(frames)).numpy()
     rel = np.linalg.norm(saved - ref, axis=1) / np.linalg.norm(ref, axis=1)
     assert rel.max() < 1e-3, rel.max()
 
@@ -78,3 +78,74 @@ def test_extract_clip_refuses_cpu(tmp_path, monkeypatch, capsys):
     ex = ExtractCLIP(_args([vid], str(tmp_path / "o")), external_call=True)
     with pytest.raises(RuntimeError, match="no CPU path"):
         ex(torch.zeros([1], dtype=torch.long))
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE config 1
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SAMPLE = os.path.join(GOLD, "v_GGSY1Qvo990.mp4")              # the reference's own sample (sample/v_GGSY1Qvo990.mp4)
+
+
+def test_config1_main_py_on_the_sample_video(cuda_device, tmp_path):
+    """BASELINE.json configs[0] == the reference README's command (README.md:33), through main.py as a user runs it:
+    uni_12 on sample/v_GGSY1Qvo990.mp4, --on_extraction save_numpy --output_direct.  Frame indices and decoded frames
+    are pinned to the reference sampler's (fixture made by scripts/make_golden.py from the reference's extract_frames);
+    features are compared with the oracle on the very same frames.  Weights: synthetic (real CLIP weights are not
+    available offline), the same seeded state dict on both sides."""
+    import subprocess
+    import sys
+    import time
+    from oracle import clip_preprocess, clip_tower
+    from video_features_b200 import synthetic_weights, utils
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "out")
+    env = dict(os.environ, VF_CLIP_SYNTHETIC="0")
+    t0 = time.perf_counter()
+    r = subprocess.run([sys.executable, os.path.join(root, "main.py"), "--feature_type", "CLIP-ViT-B/32",
+                        "--extract_method", "uni_12", "--video_paths", SAMPLE, "--on_extraction", "save_numpy",
+                        "--output_direct", "--output_path", out, "--tmp_path", str(tmp_path / "tmp"), "--device_ids", "0"],
+                       env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    wall = time.perf_counter() - t0
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert os.listdir(out) == ["v_GGSY1Qvo990.npy"]                          # utils/utils.py:83-87 naming
+    got = np.load(os.path.join(out, "v_GGSY1Qvo990.npy"))
+    assert got.shape == (12, 512) and got.dtype == np.float32
+    gold = np.load(os.path.join(GOLD, "config1_sample_video.npz"))
+    frames, fps, ts = utils.extract_frames(SAMPLE, "uni_12")
+    assert int(gold["frame_cnt"]) == 355 and list(gold["indices"]) == [1, 33, 65, 97, 129, 161, 193, 225, 257, 289, 321, 353]
+    assert abs(fps - float(gold["fps"])) < 1e-9 and np.allclose(ts, gold["timestamps_ms"], rtol=0, atol=1e-15)
+    # the decoder on this box returns the frames the reference's sampler returned in the build container
+    assert [int(f.astype(np.uint64).sum()) for f in frames] == [int(c) for c in gold["frame_checksums"]]
+    t1 = time.perf_counter()
+    ref = clip_tower.encode_image(synthetic_weights.clip_vit_b32_state_dict(0),
+                                  clip_preprocess.preprocess_batch(np.stack(frames))).numpy()
+    cpu_s = time.perf_counter() - t1
+    rel = np.linalg.norm(got - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    mx = np.abs(got - ref).max(axis=1) / np.abs(ref).max(axis=1)
+    print(f"config 1: main.py wall {wall:.2f} s (process start + weights + 12 frames); oracle transform+tower on the host "
+          f"{cpu_s:.2f} s; rel-L2 {rel.max():.3e} max-abs {mx.max():.3e}")
+    assert rel.max() <= 1e-3 and mx.max() <= 1e-3
+
+
+def test_extract_clip_list_is_batched_and_matches_per_video_calls(cuda_device, tmp_path, monkeypatch):
+    """A list of videos goes through the batched path (several videos per engine call); every video's features must be
+    identical to the one-video-per-call path (batch-composition independence), files and per-video errors included."""
+    monkeypatch.setenv("VF_CLIP_SYNTHETIC", "0")
+    from video_features_b200.extract.extract_clip import ExtractCLIP
+    vids = []
+    for i in range(5):
+        v = str(tmp_path / f"b{i}.mp4")
+        _write_video(v, n=16 + 4 * i, h=120 if i < 4 else 96, w=160 if i < 4 else 128)     # last one: another geometry
+        vids.append(v)
+    bad = str(tmp_path / "broken.mp4")
+    open(bad, "wb").write(b"not a video")
+    vids.insert(2, bad)
+    ex = ExtractCLIP(_args(vids, str(tmp_path / "o1"), method="uni_5"), external_call=True)
+    ex.batch_frames = 12                                  # 2 videos per call
+    got = ex(torch.arange(len(vids), device=cuda_device))
+    ex1 = ExtractCLIP(_args(vids, str(tmp_path / "o2"), method="uni_5"), external_call=True)
+    ex1.batch_frames = 0
+    one = ex1(torch.arange(len(vids), device=cuda_device))
+    assert len(got) == len(one) == 5
+    for a, b in zip(got, one):
+        assert a['CLIP-ViT-B/32'].shape == (5, 512) and np.array_equal(a['CLIP-ViT-B/32'], b['CLIP-ViT-B/32'])
+        assert np.array_equal(a['timestamps_ms'], b['timestamps_ms'])

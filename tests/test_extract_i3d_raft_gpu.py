@@ -9,13 +9,15 @@ import torch
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-HAVE = all(os.path.exists(os.path.join(ROOT, "checkpoints", f)) for f in ("i3d_rgb.pt", "i3d_flow.pt", "raft-sintel.pth"))
+import sys
+sys.path.insert(0, os.path.join(ROOT, "scripts", "precision"))
+from helpers import checkpoint  # noqa: E402  (a missing checkpoint copy FAILS these tests, it never skips them)
 
 
-def _write_video(path, n, h=120, w=160, fps=25.0):
+def _write_video(path, n, h=120, w=160, fps=25.0, shift=(0.8, 0.5)):
     import cv2
     from oracle import raft_net
-    fr = raft_net.synthetic_frames(n, h, w, seed=11, shift=(0.8, 0.5)).permute(0, 2, 3, 1).numpy().astype(np.uint8)
+    fr = raft_net.synthetic_frames(n, h, w, seed=11, shift=shift).permute(0, 2, 3, 1).numpy().astype(np.uint8)
     vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), fps, (w, h))
     assert vw.isOpened()
     for f in fr:
@@ -32,14 +34,18 @@ def _ns(**kw):
     return argparse.Namespace(**d)
 
 
-@pytest.mark.skipif(not HAVE, reason="reference checkpoint copies not present (scripts/fetch_checkpoints.py)")
-def test_extract_i3d_two_streams_vs_oracle(cuda_device, tmp_path):
+@pytest.mark.parametrize("clip,shift", [("low_motion", (0.8, 0.5)), ("high_motion", (4.5, -3.0))])
+def test_extract_i3d_two_streams_vs_oracle(cuda_device, tmp_path, clip, shift):
     from PIL import Image
+    from flow_quantiser_sensitivity import feature_sensitivity            # scripts/precision/
     from oracle import i3d_net, raft_net
     from video_features_b200 import utils
     from video_features_b200.extract.extract_i3d import ExtractI3D
+    from video_features_b200.raft_engine import RAFTEngine
+    for n in ("i3d_rgb.pt", "i3d_flow.pt", "raft-sintel.pth"):
+        checkpoint(n)
     vid = str(tmp_path / "clip.mp4")
-    _write_video(vid, 20)
+    _write_video(vid, 20, shift=shift)
     out = str(tmp_path / "out")
     ex = ExtractI3D(_ns(video_paths=[vid], output_path=out, tmp_path=str(tmp_path / "tmp"), stack_size=12, step_size=12),
                     external_call=True)
@@ -55,30 +61,84 @@ def test_extract_i3d_two_streams_vs_oracle(cuda_device, tmp_path):
     frames = [rd.get_frame(int(i)) for i in ix]
     rs = torch.stack([torch.from_numpy(np.asarray(Image.fromarray(f).resize((341, 256), Image.BILINEAR)).copy())
                       for f in frames]).permute(0, 3, 1, 2).float().to(cuda_device)
-    sd_rgb = {k: v.to(cuda_device) for k, v in torch.load(os.path.join(ROOT, "checkpoints", "i3d_rgb.pt")).items()}
+    sd_rgb = {k: v.to(cuda_device) for k, v in torch.load(checkpoint("i3d_rgb.pt")).items()}
     ref_rgb = i3d_net.forward_features(sd_rgb, i3d_net.rgb_transform(rs[:-1]))
     rel = float((torch.from_numpy(res['rgb']).to(cuda_device) - ref_rgb).norm() / ref_rgb.norm())
-    print("ExtractI3D rgb vs oracle:", rel)
+    print(f"[{clip}] ExtractI3D rgb vs oracle:", rel)
     assert rel < 1e-3
-    sd_raft = {k: v.to(cuda_device) for k, v in torch.load(os.path.join(ROOT, "checkpoints", "raft-sintel.pth")).items()}
+    sd_raft_cpu = torch.load(checkpoint("raft-sintel.pth"))
+    sd_raft = {k: v.to(cuda_device) for k, v in sd_raft_cpu.items()}
     xp = raft_net.pad(rs)
     flow = raft_net.forward(sd_raft, xp[:-1], xp[1:], 20)                # padded, never unpadded (extract_i3d.py:172)
-    sd_flow = {k: v.to(cuda_device) for k, v in torch.load(os.path.join(ROOT, "checkpoints", "i3d_flow.pt")).items()}
+    sd_flow = {k: v.to(cuda_device) for k, v in torch.load(checkpoint("i3d_flow.pt")).items()}
     ref_flow = i3d_net.forward_features(sd_flow, i3d_net.flow_transform(flow))
     rel = float((torch.from_numpy(res['flow']).to(cuda_device) - ref_flow).norm() / ref_flow.norm())
-    print("ExtractI3D flow (RAFT -> I3D) vs oracle:", rel)
     # The flow stream passes through the reference's 8-bit quantiser `round(128 + 255/40 f)` (transforms.py:43-51), a
-    # discontinuity: on this clip (tiny motion, 3 quantisation levels in use) a flow perturbation of sigma = 1e-4 px --
-    # 1.6e-4 of the flow itself -- already moves the oracle's OWN 1024-d feature by 3e-3, and 3e-4 px by 1.6e-2
-    # (scripts: DESIGN.md §2).  Parity of this branch is therefore asserted per stage: RAFT flow (test_raft_gpu.py,
-    # rel-L2 <= 1e-3) and quantiser + I3D on identical flow (test_i3d_gpu.py::test_i3d_fused_stream_transforms, 2e-4).
-    # End to end only gross agreement can be asked for (measured 9.4e-3 with the split-fp16 RAFT, 4e-2 before it):
-    assert rel < 0.05
+    # staircase: a flow perturbation of 1e-5 px already moves the oracle's OWN feature by 3e-3 .. 4e-3 on these clips, and
+    # the fp32 oracle with a different thread count differs from itself by more than that
+    # (scripts/precision/flow_quantiser_sensitivity.py -> profiles/r2_flow_sensitivity.json).  No implementation whose
+    # flow differs from the oracle's at all can therefore be held to 1e-3 on the composite.  The bar is derived, not
+    # guessed: (1) the engine's flow must meet the 1e-3 RAFT bar on this very clip, (2) quantiser + I3D on identical flow
+    # is asserted elsewhere (test_i3d_gpu.py, 2e-4), and (3) the composite may not exceed 3x the oracle's own
+    # sensitivity to Gaussian flow noise of the SAME rms as the engine's measured flow error.
+    eng = RAFTEngine(sd_raft_cpu, 0, max_frames=13, max_h=256, max_w=341)
+    eflow = eng.flow(rs.permute(0, 2, 3, 1).contiguous().to(torch.uint8), iters=20, unpad=False)
+    eng.close()
+    d = eflow - flow
+    flow_rel, flow_rms = float(d.norm() / flow.norm()), float(d.pow(2).mean().sqrt())
+    assert flow_rel <= 1e-3 and float(d.abs().max()) <= 1e-3 * float(flow.abs().max()), (flow_rel, float(d.abs().max()))
+    sens = feature_sensitivity(sd_flow, flow, [flow_rms], draws=5)[flow_rms]["feature_rel"]
+    bar = max(1e-3, 3.0 * sens)
+    print(f"[{clip}] ExtractI3D flow (RAFT -> quantiser -> I3D) vs oracle: {rel:.3e}; engine flow error {flow_rel:.2e} rel / "
+          f"{flow_rms:.2e} px rms; oracle's own sensitivity at that rms: {sens:.3e}; bar {bar:.3e}")
+    assert rel <= bar, (rel, bar)
 
 
-@pytest.mark.skipif(not HAVE, reason="reference checkpoint copies not present (scripts/fetch_checkpoints.py)")
+def test_extract_i3d_mixed_aspect_ratios_and_precomputed_flow(cuda_device, tmp_path):
+    """(a) a list whose second video is wider than the first: the RAFT engine's workspace must follow (the reference
+    handles any resolution per video); (b) --flow_type flow: pre-computed flow_x / flow_y jpg pairs
+    (extract_i3d.py:195-229,266-278) against the oracle fed with the very same jpgs."""
+    import cv2
+    from oracle import i3d_net
+    from video_features_b200.extract.extract_i3d import ExtractI3D
+    for n in ("i3d_rgb.pt", "i3d_flow.pt", "raft-sintel.pth"):
+        checkpoint(n)
+    a, b = str(tmp_path / "narrow.mp4"), str(tmp_path / "wide.mp4")
+    _write_video(a, 14, h=120, w=160)                     # -> 256x341
+    _write_video(b, 14, h=96, w=192)                      # -> 256x512: wider than the engine created for `a`
+    ex = ExtractI3D(_ns(video_paths=[a, b], output_path=str(tmp_path / "o"), tmp_path=str(tmp_path / "t"), stack_size=10,
+                        step_size=10, streams=['flow']), external_call=True)
+    res = ex(torch.arange(2, device=cuda_device))
+    assert len(res) == 2 and res[0]['flow'].shape == (6, 1024) and res[1]['flow'].shape == (6, 1024)
+    assert np.isfinite(res[1]['flow']).all() and np.abs(res[1]['flow']).max() > 0
+
+    # ---- pre-computed flow images
+    fdir = tmp_path / "flows" / "narrow"
+    fdir.mkdir(parents=True)
+    rng = np.random.default_rng(5)
+    base = cv2.GaussianBlur(rng.integers(0, 256, (256, 344), dtype=np.uint8), (0, 0), 6)
+    for i in range(14):
+        cv2.imwrite(str(fdir / f"flow_x_{i:05d}.jpg"), np.roll(base, 2 * i, axis=1))
+        cv2.imwrite(str(fdir / f"flow_y_{i:05d}.jpg"), np.roll(base, 3 * i, axis=0))
+    exf = ExtractI3D(_ns(video_paths=[a], flow_paths=[str(fdir)], output_path=str(tmp_path / "o"),
+                         tmp_path=str(tmp_path / "t"), stack_size=12, step_size=12, flow_type='flow'), external_call=True)
+    assert exf.path_list == [(a, str(fdir))]
+    got = exf(torch.zeros([1], dtype=torch.long, device=cuda_device))[0]
+    # 14 frames < 65: resampled to 65 indices; zip(frames, flows) stops at the 14 flow pairs -> one stack of 12
+    assert got['flow'].shape == (1, 1024) and got['rgb'].shape == (1, 1024)
+    imgs = torch.stack([torch.stack([torch.from_numpy(cv2.imread(str(fdir / f"flow_{c}_{i:05d}.jpg"), cv2.IMREAD_GRAYSCALE))
+                                     for c in "xy"]) for i in range(12)])            # uint8 (12,2,256,344), as mmcv.imread
+    sd_flow = {k: v.to(cuda_device) for k, v in torch.load(checkpoint("i3d_flow.pt")).items()}
+    # the reference applies its flow transform to these uint8 grey levels as they are: clamp(-20,20) keeps [0,20]
+    ref = i3d_net.forward_features(sd_flow, i3d_net.flow_transform(imgs.float().to(cuda_device)))
+    rel = float((torch.from_numpy(got['flow']).to(cuda_device) - ref).norm() / ref.norm())
+    print("ExtractI3D --flow_type flow vs oracle:", rel)
+    assert rel < 1e-3
+
+
 def test_extract_raft_writes_flow(cuda_device, tmp_path):
     from oracle import raft_net
+    checkpoint("raft-sintel.pth")
     from video_features_b200.extract.extract_raft import ExtractRAFT
     vid = str(tmp_path / "clip2.mp4")
     _write_video(vid, 6, h=128, w=160)
@@ -96,7 +156,7 @@ def test_extract_raft_writes_flow(cuda_device, tmp_path):
             break
         fr.append(cv2.cvtColor(f, cv2.COLOR_BGR2RGB))
     x = torch.from_numpy(np.stack(fr)).permute(0, 3, 1, 2).float().to(cuda_device)
-    sd = {k: v.to(cuda_device) for k, v in torch.load(os.path.join(ROOT, "checkpoints", "raft-sintel.pth")).items()}
+    sd = {k: v.to(cuda_device) for k, v in torch.load(checkpoint("raft-sintel.pth")).items()}
     ref = raft_net.forward(sd, x[:-1], x[1:], 20).cpu().numpy()
     rel = np.linalg.norm(flow - ref) / np.linalg.norm(ref)
     print("ExtractRAFT vs oracle:", rel)

@@ -51,9 +51,8 @@ def test_i3d_synthetic_weights_vs_oracle(cuda_device, modality, T):
 
 @pytest.mark.parametrize("modality", ["rgb", "flow"])
 def test_i3d_reference_checkpoint_vs_oracle_and_golden(cuda_device, modality):
-    path = os.path.join(ROOT, "checkpoints", f"i3d_{modality}.pt")
-    if not os.path.exists(path):
-        pytest.skip("reference checkpoint copy not present (scripts/fetch_checkpoints.py)")
+    from helpers import checkpoint
+    path = checkpoint(f"i3d_{modality}.pt")            # fails (never skips) when the copy is missing
     from video_features_b200.i3d_engine import I3DEngine
     sd = torch.load(path, map_location="cpu")
     cin = 3 if modality == "rgb" else 2

@@ -28,8 +28,8 @@ def _err(y, ref):
 
 @pytest.fixture(scope="module")
 def raft(cuda_device):
-    if not os.path.exists(CKPT):
-        pytest.skip("reference checkpoint copy not present (scripts/fetch_checkpoints.py)")
+    from helpers import checkpoint
+    checkpoint("raft-sintel.pth")                      # fails (never skips) when the copy is missing
     from video_features_b200.raft_engine import RAFTEngine
     sd = torch.load(CKPT, map_location="cpu")
     eng = RAFTEngine(sd, 0, max_frames=5, max_h=272, max_w=480)

@@ -137,6 +137,7 @@ def test_extractor_forward_loops_with_stubbed_engines(tmp_path, monkeypatch, mod
 
     # CLIP (output_direct, the documented way to save CLIP features)
     ex = ExtractCLIP(_ns(tmp_path, feature_type='CLIP-ViT-B/32', output_direct=True))
+    ex.batch_frames = 0                                # one engine call per video: the reference's loop shape
     monkeypatch.setattr(ExtractCLIP, "_engine", lambda self, device: object())
     monkeypatch.setattr(ExtractCLIP, "extract", fake_extract('CLIP-ViT-B/32'))
     out = tmp_path / "out"
@@ -150,6 +151,7 @@ def test_extractor_forward_loops_with_stubbed_engines(tmp_path, monkeypatch, mod
     # external_call=True returns the dicts and writes nothing
     calls.clear()
     exx = ExtractCLIP(_ns(tmp_path, feature_type='CLIP-ViT-B/32'), external_call=True)
+    exx.batch_frames = 0
     got = exx(_FakeIndices([0, 2]))
     assert len(got) == 2 and set(got[0]) == {'CLIP-ViT-B/32', 'fps', 'timestamps_ms'}
 
@@ -168,3 +170,65 @@ def test_extractor_forward_loops_with_stubbed_engines(tmp_path, monkeypatch, mod
     monkeypatch.setattr(ExtractRAFT, "extract", fake_extract('raft'))
     assert er(_FakeIndices([0, 1, 2])) is None
     assert sorted(os.listdir(out / "raft")) == ["a_raft.npy", "c_raft.npy"] and len(calls) == 3
+
+
+class _FakeClipEngine:
+    """Stands in for ClipEngine: feature row i = (mean of frame i, number of frames in the call, ...)."""
+    def __init__(self):
+        self.calls = []
+
+    def encode_frames_u8_host(self, frames, out=None):
+        import torch
+        if isinstance(frames, np.ndarray):
+            frames = torch.from_numpy(frames)
+        n = frames.shape[0]
+        self.calls.append((n, tuple(frames.shape[1:3])))
+        y = torch.zeros((n, 512), dtype=torch.float32)
+        y[:, 0] = frames.reshape(n, -1).float().mean(dim=1)
+        y[:, 1] = n
+        return y
+
+
+def test_extract_clip_batches_consecutive_videos_into_one_engine_call(tmp_path, monkeypatch, capsys):
+    """ExtractCLIP.forward over a list: frames of consecutive same-geometry videos share one engine call; results are
+    cut back per video; a failing decode and a geometry change behave like the reference's per-video loop."""
+    import argparse
+    from video_features_b200.extract.extract_clip import ExtractCLIP
+    vids = []
+    for i in range(7):
+        p = tmp_path / f"v{i}.mp4"
+        p.write_bytes(b"x")
+        vids.append(str(p))
+    ns = argparse.Namespace(feature_type='CLIP-ViT-B/32', video_paths=vids, flow_paths=None, file_with_video_paths=None,
+                            video_dir=None, flow_dir=None, extraction_fps=None, extract_method='uni_4',
+                            on_extraction='save_numpy', output_path=str(tmp_path / "out"), output_direct=True,
+                            tmp_path=str(tmp_path / "tmp"))
+
+    def source(path, method):
+        i = int(os.path.basename(path)[1])
+        if i == 2:
+            raise RuntimeError("decoder says no")
+        hw = (24, 32) if i < 5 else (16, 16)                       # geometry changes at video 5
+        n = 3 + i % 2
+        return [np.full(hw + (3,), 10 * i + k, np.uint8) for k in range(n)] + [None], 25.0, list(range(n))
+
+    eng = _FakeClipEngine()
+    monkeypatch.setattr(ExtractCLIP, "_engine", lambda self, device: eng)
+    ex = ExtractCLIP(ns)
+    ex.frame_source = source
+    ex.batch_frames = 8
+    assert ex(_FakeIndices(range(7))) == []
+    assert "Extraction failed at: " + vids[2] in capsys.readouterr().out
+    out = tmp_path / "out"
+    assert sorted(os.listdir(out)) == [f"v{i}.npy" for i in (0, 1, 3, 4, 5, 6)]
+    for i in (0, 1, 3, 4, 5, 6):
+        f = np.load(out / f"v{i}.npy")
+        assert f.shape == (3 + i % 2, 512) and np.allclose(f[:, 0], [10 * i + k for k in range(3 + i % 2)])
+    # videos 0,1 (3+4 frames) share a call; 3,4 (4+3) share the next; the geometry change splits 5,6 (4+3) off
+    assert eng.calls == [(7, (24, 32)), (7, (24, 32)), (7, (16, 16))]
+    # external_call returns the dicts in list order
+    ex2 = ExtractCLIP(ns, external_call=True)
+    ex2.frame_source = source
+    ex2.batch_frames = 8
+    got = ex2(_FakeIndices([6, 0, 1]))
+    assert [g['CLIP-ViT-B/32'].shape[0] for g in got] == [3, 3, 4] and float(got[0]['CLIP-ViT-B/32'][0, 0]) == 60.0

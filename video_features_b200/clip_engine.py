@@ -97,6 +97,20 @@ class ClipEngine:
                                                torch.cuda.current_stream().cuda_stream))
         return out
 
+    # ---- host frames in, features on the DEVICE (for an all-gather), optionally on the host as well
+    def encode_frames_u8_host_dev(self, frames: torch.Tensor, out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+        assert (not frames.is_cuda) and frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3
+        frames = frames.contiguous()
+        n, hh, ww, _ = frames.shape
+        out = torch.empty((n, 512), device=self.device, dtype=torch.float32)
+        if out_host is not None:
+            assert out_host.dtype == torch.float32 and out_host.is_contiguous() and tuple(out_host.shape) == (n, 512)
+        with torch.cuda.device(self.device):
+            check(lib().vf_clip_encode_u8_host_dev(self._h, frames.data_ptr(), n, hh, ww, out.data_ptr(),
+                                                   None if out_host is None else out_host.data_ptr(),
+                                                   torch.cuda.current_stream().cuda_stream))
+        return out
+
     @property
     def launch_count(self) -> int:
         return int(lib().vf_clip_launch_count(self._h))

@@ -260,6 +260,14 @@ static void deactivate(vf_clip* h) {      // keep the (possibly grown) resize sc
     vf_clip::Lane& L = h->lanes[h->cur];
     L.resized = h->resized; L.resize_tmp = h->resize_tmp; L.resized_cap = h->resized_cap; L.tmp_cap = h->tmp_cap;
 }
+// keeps a lane's (possibly re-allocated) resize scratch with the lane on EVERY exit path of a chunk, early error returns
+// included: a lane left holding pointers that grow() has already freed would be a use-after-free on the next call
+struct LaneScope {
+    vf_clip* h;
+    cudaStream_t s;
+    LaneScope(vf_clip* h_, int l) : h(h_), s(activate(h_, l)) {}
+    ~LaneScope() { deactivate(h); }
+};
 // order the lane streams after the caller's stream (enter) and the caller's stream after the lanes (leave)
 static int enter(vf_clip* h, cudaStream_t user) {
     VF_CUDA(cudaSetDevice(h->device));
@@ -432,11 +440,11 @@ int vf_clip_encode_f32(vf_clip_t* h, const float* frames, int n, float* out, voi
     const int step = balanced_chunk(h, n);
     for (int b0 = 0, i = 0; b0 < n; b0 += step, ++i) {
         const int c = (n - b0 < step) ? (n - b0) : step;
-        cudaStream_t s = activate(h, i % h->n_lanes);
+        LaneScope lane(h, i % h->n_lanes);
+        cudaStream_t s = lane.s;
         VF_TRY(launch_clip_patchify_f32(frames + size_t(b0) * 3 * 224 * 224, c, h->patches, s));
         h->launches += 1;
         VF_TRY(clip_tower_chunk(h, c, out + size_t(b0) * E, s));
-        deactivate(h);
     }
     return leave(h, user);
 }
@@ -452,17 +460,18 @@ int vf_clip_encode_u8(vf_clip_t* h, const uint8_t* frames, int n, int src_h, int
     const int step = balanced_chunk(h, n);
     for (int b0 = 0, i = 0; b0 < n; b0 += step, ++i) {
         const int c = (n - b0 < step) ? (n - b0) : step;
-        cudaStream_t s = activate(h, i % h->n_lanes);
+        LaneScope lane(h, i % h->n_lanes);
+        cudaStream_t s = lane.s;
         VF_TRY(clip_transform_chunk(h, frames + size_t(b0) * fbytes, c, src_h, src_w, g, s));
         VF_TRY(clip_tower_chunk(h, c, out + size_t(b0) * E, s));
-        deactivate(h);
     }
     return leave(h, user);
 }
 
-int vf_clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, int src_h, int src_w, float* out_host,
-                           void* stream) {
-    if (!h || (n > 0 && (!frames_host || !out_host))) return fail(VF_ERR_INVALID, "clip_encode_u8_host: null argument");
+static int clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, int src_h, int src_w, float* out_host,
+                               float* out_dev, void* stream) {
+    if (!h || (n > 0 && (!frames_host || (!out_host && !out_dev))))
+        return fail(VF_ERR_INVALID, "clip_encode_u8_host: null argument");
     if (n <= 0) return VF_OK;
     cudaStream_t user = static_cast<cudaStream_t>(stream);
     ClipGeom g;
@@ -471,11 +480,15 @@ int vf_clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, int 
     const size_t fbytes = size_t(src_h) * src_w * 3;
     // two staging slots: the H2D copy of chunk i+1 (copy stream) overlaps the tower on chunk i (compute stream)
     VF_TRY(grow(&h->stage_u8, &h->stage_cap, 2 * size_t(h->chunk) * fbytes));
-    if (h->out_cap < size_t(n) * E * sizeof(float)) {
-        if (h->out_dev) cudaFree(h->out_dev);
-        h->out_dev = nullptr; h->out_cap = 0;
-        VF_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->out_dev), size_t(n) * E * sizeof(float)));
-        h->out_cap = size_t(n) * E * sizeof(float);
+    float* feats = out_dev;                 // the caller's device buffer, else the handle's own
+    if (!feats) {
+        if (h->out_cap < size_t(n) * E * sizeof(float)) {
+            if (h->out_dev) cudaFree(h->out_dev);
+            h->out_dev = nullptr; h->out_cap = 0;
+            VF_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->out_dev), size_t(n) * E * sizeof(float)));
+            h->out_cap = size_t(n) * E * sizeof(float);
+        }
+        feats = h->out_dev;
     }
     const int step = balanced_chunk(h, n);
     const int nchunks = (n + step - 1) / step;
@@ -484,7 +497,8 @@ int vf_clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, int 
         const int b0 = i * step;
         const int c = (n - b0 < step) ? (n - b0) : step;
         const int slot = i & 1;
-        cudaStream_t s = activate(h, i % h->n_lanes);
+        LaneScope lane(h, i % h->n_lanes);
+        cudaStream_t s = lane.s;
         uint8_t* dst = h->stage_u8 + size_t(slot) * h->chunk * fbytes;
         if (i >= 2) VF_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));   // slot free again
         VF_CUDA(cudaMemcpyAsync(dst, frames_host + size_t(b0) * fbytes, size_t(c) * fbytes, cudaMemcpyHostToDevice,
@@ -493,8 +507,7 @@ int vf_clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, int 
         VF_CUDA(cudaStreamWaitEvent(s, h->ev_copy[slot], 0));
         VF_TRY(clip_transform_chunk(h, dst, c, src_h, src_w, g, s));
         VF_CUDA(cudaEventRecord(h->ev_done[slot], s));   // staging slot consumed
-        VF_TRY(clip_tower_chunk(h, c, h->out_dev + size_t(b0) * E, s));
-        deactivate(h);
+        VF_TRY(clip_tower_chunk(h, c, feats + size_t(b0) * E, s));
     }
     // gather point: lane 0 waits for lane 1, then one D2H of all features
     cudaStream_t s0 = h->lanes[0].cs;
@@ -502,10 +515,24 @@ int vf_clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, int 
         VF_CUDA(cudaEventRecord(h->lanes[1].ev_out, h->lanes[1].cs));
         VF_CUDA(cudaStreamWaitEvent(s0, h->lanes[1].ev_out, 0));
     }
-    VF_CUDA(cudaMemcpyAsync(out_host, h->out_dev, size_t(n) * E * sizeof(float), cudaMemcpyDeviceToHost, s0));
+    if (out_host)
+        VF_CUDA(cudaMemcpyAsync(out_host, feats, size_t(n) * E * sizeof(float), cudaMemcpyDeviceToHost, s0));
     VF_TRY(leave(h, user));
-    VF_CUDA(cudaStreamSynchronize(s0));
+    // the host frames may be reused (and out_host read) as soon as this returns
+    VF_CUDA(cudaStreamSynchronize(out_host ? s0 : h->copy_stream));
     return VF_OK;
+}
+
+int vf_clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, int src_h, int src_w, float* out_host,
+                           void* stream) {
+    if (n > 0 && !out_host) return fail(VF_ERR_INVALID, "clip_encode_u8_host: null argument");
+    return clip_encode_u8_host(h, frames_host, n, src_h, src_w, out_host, nullptr, stream);
+}
+
+int vf_clip_encode_u8_host_dev(vf_clip_t* h, const uint8_t* frames_host, int n, int src_h, int src_w, float* out_dev,
+                               float* out_host, void* stream) {
+    if (n > 0 && !out_dev) return fail(VF_ERR_INVALID, "clip_encode_u8_host_dev: null device output");
+    return clip_encode_u8_host(h, frames_host, n, src_h, src_w, out_host, out_dev, stream);
 }
 
 int64_t vf_clip_launch_count(const vf_clip_t* h) { return h ? h->launches : 0; }

@@ -5,6 +5,12 @@ changes underneath: ``clip.load`` is replaced by a ``ClipEngine`` (device weight
 ``model.encode_image`` by ONE call into libvfeat.so that takes the decoder's raw uint8 frames and runs the
 Pillow-exact bicubic resize, centre crop, normalisation and the ViT-B/32 tower on the GPU.
 
+A list of videos does not go through the engine one 12-frame video at a time (600 token rows would fill 3 of the
+GEMM's 74 tile slots): ``forward`` decodes ahead on a thread pool, packs the frames of consecutive videos of equal
+geometry into a pinned staging buffer (two buffers, filled by the pool while the GPU works on the other one) and makes
+one engine call per ``VF_CLIP_BATCH_FRAMES`` (default 1024) frames; the features are cut back per video and handed to
+the sink exactly as the reference does, per-video error behaviour included.
+
 Differences a user can observe, all deliberate:
   * features are float32 on the GPU as well (the reference's GPU path returns float16 because ``clip.load`` keeps the
     model in half precision on CUDA; its ``--cpu`` path returns float32);
@@ -15,39 +21,61 @@ from __future__ import annotations
 
 import os
 import pathlib
+import threading
 import traceback
-from typing import Dict
+from concurrent.futures import ThreadPoolExecutor
+from typing import Dict, List, Optional
 
 import numpy as np
 import torch
 from tqdm import tqdm
 
+from .. import synthetic_weights
 from ..clip_engine import ClipEngine
 from ..utils import AsyncSink, action_on_extraction, already_extracted, extract_frames, form_list_from_user_input
 
 _CKPT_NAMES = {'CLIP-ViT-B/32': 'ViT-B-32.pt', 'CLIP4CLIP-ViT-B-32': 'CLIP4CLIP-ViT-B-32.pth'}
 
 
+def read_clip_checkpoint(path: str) -> Dict[str, torch.Tensor]:
+    """A checkpoint in one of the forms ``clip.load`` accepts (third-party openai/CLIP ``clip/clip.py``): a TorchScript
+    archive (what it downloads) or a pickled state dict, possibly nested under 'state_dict' and possibly with the
+    ``clip.`` prefix CLIP4Clip checkpoints carry.  Returns openai's flat ``visual.*`` keys."""
+    try:
+        sd = torch.jit.load(path, map_location="cpu").state_dict()
+    except RuntimeError:
+        sd = torch.load(path, map_location="cpu")
+        sd = sd.get("state_dict", sd)
+    if not any(k.startswith("visual.") for k in sd) and any(k.startswith("clip.visual.") for k in sd):
+        sd = {k[5:]: v for k, v in sd.items() if k.startswith("clip.")}
+    return dict(sd)
+
+
 def load_clip_state_dict(feature_type: str) -> Dict[str, torch.Tensor]:
-    """Checkpoint in openai's format: a TorchScript archive (what ``clip.load`` downloads) or a plain state dict.
-    ``VF_CLIP_SYNTHETIC=<seed>`` selects seeded synthetic weights (benchmarks / tests without the real file)."""
+    """``$VF_CLIP_CKPT``, then ``<this dir>/checkpoints/<name>`` (where the reference keeps CLIP4CLIP's file,
+    extract_clip.py:56), then ``~/.cache/clip/<name>`` (where ``clip.load`` caches its download).
+    ``VF_CLIP_SYNTHETIC=<seed>[:outliers]`` selects seeded synthetic weights instead (benchmarks without the file)."""
     if os.environ.get("VF_CLIP_SYNTHETIC") is not None:
-        from oracle import clip_tower            # weight generator only
-        return clip_tower.synthetic_state_dict(int(os.environ["VF_CLIP_SYNTHETIC"] or 0))
+        return synthetic_weights.clip_vit_b32_state_dict(*synthetic_weights.parse_env(os.environ["VF_CLIP_SYNTHETIC"]))
     name = _CKPT_NAMES[feature_type]
     cands = [os.environ.get("VF_CLIP_CKPT"), os.path.join(pathlib.Path(__file__).parent, 'checkpoints', name),
              os.path.expanduser(os.path.join("~/.cache/clip", name))]
     for p in cands:
         if p and os.path.exists(p):
-            try:
-                return torch.jit.load(p, map_location="cpu").state_dict()
-            except RuntimeError:
-                sd = torch.load(p, map_location="cpu")
-                return sd.get("state_dict", sd)
+            return read_clip_checkpoint(p)
     if feature_type == 'CLIP4CLIP-ViT-B-32':
         raise ValueError(cands[1])                 # extract_clip.py:57-58
     raise FileNotFoundError(f"CLIP checkpoint {name} not found (looked at {[c for c in cands if c]}); "
                             "there is no network access -- set VF_CLIP_CKPT")
+
+
+class _Batch:
+    """Frames of consecutive videos of one geometry, waiting for one engine call."""
+
+    def __init__(self, hw):
+        self.hw = hw
+        self.items: List[tuple] = []       # (list position, video, frames (list of HxWx3 arrays), fps, stamps)
+        self.frames = 0
 
 
 class ExtractCLIP(torch.nn.Module):
@@ -65,6 +93,11 @@ class ExtractCLIP(torch.nn.Module):
             self.output_path = args.output_path if self.output_direct is True else os.path.join(args.output_path, self.feature_type)
         self.progress = tqdm(total=len(self.path_list))
         self._engines: Dict[int, ClipEngine] = {}
+        # engine-side knobs (not in the reference): where frames come from, and how many go into one engine call
+        self.frame_source = extract_frames                  # (path, method) -> (frames, fps, timestamps_ms)
+        self.batch_frames = int(os.environ.get("VF_CLIP_BATCH_FRAMES", "1024"))
+        self.decode_workers = int(os.environ.get("VF_DECODE_WORKERS", str(min(8, os.cpu_count() or 1))))
+        self.keep_features = False        # dispatch sets it when the features are all-gathered as well as saved
 
     def _engine(self, device: torch.device) -> ClipEngine:
         if device.type != 'cuda':
@@ -79,50 +112,192 @@ class ExtractCLIP(torch.nn.Module):
             self._engines[idx] = ClipEngine(load_clip_state_dict(self.feature_type), device=idx)
         return self._engines[idx]
 
+    # ------------------------------------------------------------------ forward
     def forward(self, indices: torch.LongTensor):
         """indices {torch.LongTensor} -- indices to self.path_list; the device is taken from ``indices.device``."""
         device = indices.device
         model = self._engine(device)          # one engine per device, kept across calls
-        collected = []
+        ids = [int(i) for i in indices]
         # opt-in extras beyond the reference (SURVEY 8(f) rank 2): VF_ASYNC_SINK=1 saves from a writer thread,
         # VF_RESUME=1 skips videos whose output files already exist
         saving = not self.external_call
         sink = AsyncSink() if saving and os.environ.get("VF_ASYNC_SINK") == "1" else None
         resume = saving and os.environ.get("VF_RESUME") == "1"
-        try:
-            for idx in indices:
-                video = self.path_list[idx]
-                try:                                # per-video catch-print-continue (extract_clip.py:71-84)
-                    if resume and already_extracted([self.feature_type], video, self.output_path, self.on_extraction,
-                                                    self.output_direct):
-                        self.progress.update()
-                        continue
-                    feats = self.extract(device, model, None, video)
-                    if self.external_call:
-                        collected.append(feats)
-                    elif sink is not None:
-                        sink.submit(feats, video, self.output_path, self.on_extraction, self.output_direct)
-                    else:
-                        action_on_extraction(feats, video, self.output_path, self.on_extraction, self.output_direct)
-                except KeyboardInterrupt:
-                    raise
-                except Exception as err:
-                    print(err)
-                    print(f'Extraction failed at: {video} with error (↑). Continuing extraction')
-                    traceback.print_exc()
+        todo = []
+        for pos, idx in enumerate(ids):
+            video = self.path_list[idx]
+            if resume and already_extracted([self.feature_type], video, self.output_path, self.on_extraction,
+                                            self.output_direct):
                 self.progress.update()
+                continue
+            todo.append((pos, video))
+        collected: Dict[int, dict] = {}
+        try:
+            if len(todo) > 1 and self.batch_frames > 0:
+                self._forward_batched(device, model, todo, collected, sink)
+            else:
+                for pos, video in todo:
+                    try:                            # per-video catch-print-continue (extract_clip.py:71-84)
+                        self._deliver(self.extract(device, model, None, video), pos, video, collected, sink)
+                    except KeyboardInterrupt:
+                        raise
+                    except Exception as err:
+                        self._report(err, video)
+                    self.progress.update()
         finally:
             if sink is not None:
                 sink.close()
-        return collected
+        return [collected[p] for p in sorted(collected)]
 
+    def _report(self, err, video):
+        print(err)
+        print(f'Extraction failed at: {video} with error (↑). Continuing extraction')
+        traceback.print_exception(type(err), err, err.__traceback__)
+
+    def _deliver(self, feats: dict, pos: int, video, collected: dict, sink: Optional[AsyncSink]):
+        if self.external_call or self.keep_features:
+            collected[pos] = feats
+        if self.external_call:
+            return
+        if sink is not None:
+            sink.submit(feats, video, self.output_path, self.on_extraction, self.output_direct)
+        else:
+            action_on_extraction(feats, video, self.output_path, self.on_extraction, self.output_direct)
+
+    def _decode(self, video):
+        frames, fps, stamps = self.frame_source(str(video), self.extract_method)
+        frames = [f for f in frames if f is not None]
+        if not frames:
+            raise RuntimeError(f"no frames decoded from {video}")
+        return frames, fps, stamps
+
+    def _forward_batched(self, device, model: ClipEngine, todo, collected, sink):
+        """Decode pool -> pinned double buffer -> one engine call per <= batch_frames frames -> per-video delivery."""
+        workers = max(1, self.decode_workers)
+        pool = ThreadPoolExecutor(workers, thread_name_prefix="vf-decode")
+        gpu = ThreadPoolExecutor(1, thread_name_prefix="vf-engine")           # engine calls are serialised: one handle
+        pinned: List[Optional[torch.Tensor]] = [None, None]
+        busy = [None, None]                                                   # engine future still reading slot k
+        slot = 0
+        lock = threading.Lock()
+
+        def run_batch(batch: _Batch, buf: torch.Tensor):
+            h, w = batch.hw
+            view = buf[:batch.frames * h * w * 3].view(batch.frames, h, w, 3)
+            try:
+                feats = model.encode_frames_u8_host(view).numpy()
+                off = 0
+                for pos, video, frames, fps, stamps in batch.items:
+                    one = {self.feature_type: feats[off:off + len(frames)].copy(), 'fps': np.array(fps),
+                           'timestamps_ms': np.array(stamps)}
+                    off += len(frames)
+                    try:
+                        with lock:
+                            self._deliver(one, pos, video, collected, sink)
+                    except Exception as err:
+                        self._report(err, video)
+                    self.progress.update()
+            except Exception:
+                # the batched call failed: find the culprit by running its videos one at a time
+                for pos, video, frames, fps, stamps in batch.items:
+                    try:
+                        f = model.encode_frames_u8_host(torch.from_numpy(np.stack(frames))).numpy()
+                        with lock:
+                            self._deliver({self.feature_type: f, 'fps': np.array(fps), 'timestamps_ms': np.array(stamps)},
+                                          pos, video, collected, sink)
+                    except Exception as err:
+                        self._report(err, video)
+                    self.progress.update()
+
+        def flush(batch: _Batch):
+            nonlocal slot
+            if not batch.items:
+                return
+            k, slot = slot, slot ^ 1
+            if busy[k] is not None:
+                busy[k].result()                                              # the engine has finished with this buffer
+            h, w = batch.hw
+            need = batch.frames * h * w * 3
+            if pinned[k] is None or pinned[k].numel() < need:
+                pinned[k] = torch.empty(max(need, self.batch_frames * h * w * 3), dtype=torch.uint8)
+                if torch.cuda.is_available():                                 # (host-logic tests run without a device)
+                    pinned[k] = pinned[k].pin_memory()
+            dst = pinned[k].numpy()[:need].reshape(batch.frames, h, w, 3)
+            copies, off = [], 0
+            for _, _, frames, _, _ in batch.items:                            # the pool fills the staging buffer
+                copies.append(pool.submit(_copy_frames, dst[off:off + len(frames)], frames))
+                off += len(frames)
+            for c in copies:
+                c.result()
+            busy[k] = gpu.submit(run_batch, batch, pinned[k])
+
+        try:
+            window = 4 * workers                                              # decodes in flight, bounds host memory
+            futs = {}
+            nxt = 0
+            batch: Optional[_Batch] = None
+            for i, (pos, video) in enumerate(todo):
+                while nxt < len(todo) and nxt < i + window:
+                    futs[nxt] = pool.submit(self._decode, todo[nxt][1])
+                    nxt += 1
+                try:
+                    frames, fps, stamps = futs.pop(i).result()
+                except KeyboardInterrupt:
+                    raise
+                except Exception as err:
+                    self._report(err, video)
+                    self.progress.update()
+                    continue
+                hw = tuple(frames[0].shape[:2])
+                if any(tuple(f.shape[:2]) != hw for f in frames):
+                    hw = None                                                 # mixed geometry inside one video: own call
+                if batch is not None and (hw is None or batch.hw != hw or batch.frames + len(frames) > self.batch_frames):
+                    flush(batch)
+                    batch = None
+                if hw is None:
+                    lone = _Batch(None)
+                    lone.items.append((pos, video, frames, fps, stamps))
+                    if busy[0] is not None: busy[0].result()
+                    if busy[1] is not None: busy[1].result()
+                    gpu.submit(self._run_mixed, model, lone, collected, sink, lock).result()
+                    continue
+                if batch is None:
+                    batch = _Batch(hw)
+                batch.items.append((pos, video, frames, fps, stamps))
+                batch.frames += len(frames)
+            if batch is not None:
+                flush(batch)
+            for b in busy:
+                if b is not None:
+                    b.result()
+        finally:
+            gpu.shutdown(wait=True)
+            pool.shutdown(wait=True)
+
+    def _run_mixed(self, model, batch, collected, sink, lock):
+        """A video whose frames differ in size (never seen from a real decoder): per-frame calls, like the reference's
+        per-frame preprocess."""
+        for pos, video, frames, fps, stamps in batch.items:
+            try:
+                f = np.concatenate([model.encode_frames_u8_host(torch.from_numpy(np.ascontiguousarray(x))[None]).numpy()
+                                    for x in frames])
+                with lock:
+                    self._deliver({self.feature_type: f, 'fps': np.array(fps), 'timestamps_ms': np.array(stamps)},
+                                  pos, video, collected, sink)
+            except Exception as err:
+                self._report(err, video)
+            self.progress.update()
+
+    # ------------------------------------------------------------------ extract (one video)
     def extract(self, device: torch.device, model: ClipEngine, preprocess_func=None, video_path=None):
         """-> {feature_type: (T,512) float32, 'fps': (), 'timestamps_ms': (T,)}.  ``preprocess_func`` is accepted for
         signature compatibility; the transform is fused into the engine call."""
-        decoded, fps, stamps = extract_frames(str(video_path), self.extract_method)
-        decoded = [f for f in decoded if f is not None]
-        if not decoded:
-            raise RuntimeError(f"no frames decoded from {video_path}")
+        decoded, fps, stamps = self._decode(video_path)
         batch = torch.from_numpy(np.stack(decoded))         # (T,H,W,3) uint8, decoder channel order untouched
         feats = model.encode_frames_u8_host(batch)          # H2D + transform + tower + D2H
         return {self.feature_type: feats.numpy(), 'fps': np.array(fps), 'timestamps_ms': np.array(stamps)}
+
+
+def _copy_frames(dst: np.ndarray, frames) -> None:
+    for i, f in enumerate(frames):
+        np.copyto(dst[i], f)

@@ -3,7 +3,7 @@
 Same constructor / attributes / ``forward`` (returns None) / ``extract`` surface; output key 'raft' is a float64
 ``(T-1, 2, H, W)`` array (the reference builds it with ``.tolist()``), saved under ``{output_path}/raft``.  Frames are
 read sequentially with OpenCV, converted BGR->RGB (extract_raft.py:133 -- the stand-alone extractor does swap),
-optionally resized (``--side_size``, Pillow-exact bilinear on the GPU), and processed in windows of batch_size+1 frames
+optionally resized (``--side_size``, Pillow-exact bilinear on the GPU), and processed in windows of max(batch_size, 16)+1 frames
 with the last frame carried over; padding to /8 and unpadding happen inside the engine.
 """
 from __future__ import annotations
@@ -39,7 +39,10 @@ class ExtractRAFT(torch.nn.Module):
         self.progress = tqdm(total=len(self.path_list))
         if self.extraction_fps is not None:
             raise NotImplementedError("extraction_fps re-encodes with ffmpeg (outside the rebuilt path, SURVEY.md §2)")
-        self._engines: Dict[tuple, RAFTEngine] = {}
+        self._engines: Dict[int, tuple] = {}              # device index -> (engine, (frames, h, w) capacity)
+        # pairs per engine call: frame pairs are independent, so how many share a call does not change any value; the
+        # reference's default of one pair per call (--batch_size 1) would leave the GPU idle between launches
+        self.pairs_per_call = max(self.batch_size, int(os.environ.get("VF_RAFT_PAIRS", "16")))
 
     def forward(self, indices: torch.LongTensor):
         device = indices.device
@@ -70,20 +73,28 @@ class ExtractRAFT(torch.nn.Module):
                 sink.close()
 
     def _engine(self, device: torch.device, h: int, w: int) -> RAFTEngine:
-        key = (device.index or 0, h, w)
-        if key not in self._engines:
-            self._engines[key] = RAFTEngine(load_checkpoint('raft'), key[0], max_frames=self.batch_size + 1, max_h=h, max_w=w)
-        return self._engines[key]
+        """One engine per device.  Its workspace is sized for the largest frame seen so far; a larger frame closes it
+        and creates a bigger one (a list of many resolutions must not accumulate engines until cudaMalloc fails)."""
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        eng, cap = self._engines.get(idx, (None, (0, 0, 0)))
+        if eng is None or h > cap[1] or w > cap[2]:
+            if eng is not None:
+                eng.close()
+            cap = (self.pairs_per_call + 1, max(cap[1], h), max(cap[2], w))
+            eng = RAFTEngine(load_checkpoint('raft'), idx, max_frames=cap[0], max_h=cap[1], max_w=cap[2])
+            self._engines[idx] = (eng, cap)
+        return eng
 
     def _flow_of_window(self, window, device) -> list:
-        """window: batch_size+1 RGB frames (H, W, 3) uint8 -> batch_size flow fields as nested lists (float64 once
-        np.array'd, like the reference's `.tolist()`)."""
+        """window: n+1 RGB frames (H, W, 3) uint8 -> [one (n, 2, H, W) float64 array]."""
         x = torch.from_numpy(np.stack(window)).to(device)
         if self.side_size is not None:
             oh, ow = ops.resize_geometry(x.shape[1], x.shape[2], self.side_size, self.resize_to_smaller_edge)
             if (oh, ow) != tuple(x.shape[1:3]):
                 x = torch.ops.vfeat.resize_u8(x, oh, ow, VF_FILTER_BILINEAR)
-        return self._engine(device, x.shape[1], x.shape[2]).flow(x, iters=20, unpad=True).cpu().tolist()
+        # float64 (T, 2, H, W) on the host: the same values `.tolist()` -> np.array gives the reference, without
+        # materialising 8 bytes + a Python float object per flow component
+        return [self._engine(device, x.shape[1], x.shape[2]).flow(x, iters=20, unpad=True).cpu().numpy().astype(np.float64)]
 
     def extract(self, device, model, video_path=None) -> Dict[str, np.ndarray]:
         import cv2
@@ -104,7 +115,8 @@ class ExtractRAFT(torch.nn.Module):
                 break
             stamps.append(cap.get(cv2.CAP_PROP_POS_MSEC))
             window.append(cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB))      # the stand-alone extractor swaps to RGB
-            if len(window) == self.batch_size + 1:
+            if len(window) == self.pairs_per_call + 1:
                 flows.extend(self._flow_of_window(window, device))
                 window = window[-1:]                      # the last frame opens the next window
-        return {self.feature_type: np.array(flows), 'fps': np.array(fps), 'timestamps_ms': np.array(stamps)}
+        flows = np.concatenate(flows) if flows else np.array(flows)
+        return {self.feature_type: flows, 'fps': np.array(fps), 'timestamps_ms': np.array(stamps)}

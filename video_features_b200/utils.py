@@ -100,11 +100,15 @@ def action_on_extraction(feats_dict: Dict[str, np.ndarray], video_path, output_p
         target = _sink_path(video_path, key, output_path, on_extraction, output_direct)
         if len(value) == 0:
             print(f'Warning: the value is empty for {key} @ {target}')
-        if on_extraction == 'save_numpy':
-            np.save(target, value)
-        else:
-            with open(target, 'wb') as f:
+        # written under a scratch name and renamed into place: an output file that exists is a complete file (the
+        # resume check relies on it; a job killed mid-write leaves only `<target>.tmp`)
+        scratch = target + '.tmp'
+        with open(scratch, 'wb') as f:
+            if on_extraction == 'save_numpy':
+                np.save(f, value)
+            else:
                 pickle.dump(value, f)
+        os.replace(scratch, target)
 
 
 def sink_targets(feats_keys, video_path, output_path, on_extraction: str, output_direct: bool = False) -> List[str]:
