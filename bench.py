@@ -44,6 +44,11 @@ UNIT = "frames/s"
 WORKLOAD = "CLIP-ViT-B/32 fix_2 on 1k synthetic 224x224 RGB frames (BASELINE.json configs[1])"
 GEMM_FLOP_PER_FRAME = 231_211_008 + 12 * (715_468_800 - 2 * 3_840_000) + 786_432   # 2*M*N*K of the GEMM launches
 FLOP_PER_FRAME = 231_211_008 + 12 * 715_468_800 + 786_432                            # 8.818 GFLOP
+# algorithmic HBM bytes per frame of the memory-bound kernel classes: LayerNorm = 24 passes over the
+# 50x768 residual rows + the embedding pass; attention = q,k,v in + o out per (frame, head, layer); transform = u8 in +
+# fp16 patch matrix out
+HBM_BYTES_PER_FRAME = {"layernorm": 24 * 50 * 768 * 12 + 50 * 768 * 8,   # x fp32 r+w, y fp16 r, h fp16 w = 12 B / element
+                       "attention": 12 * 50 * 768 * 2 * 4, "transform": 150_528 + 301_056}
 
 
 def base_config(n_gpus: int) -> dict:
@@ -55,8 +60,8 @@ def base_config(n_gpus: int) -> dict:
         "weights": "synthetic, seed 0, openai visual.* layout (real CLIP weights are not available offline)",
         "accumulate": "fp32",
         "l2": "inputs are 150.5 MB per step per GPU > 126 MB L2 (no explicit flush needed)",
-        "parallelism": f"dp{n_gpus}: frame list sharded per rank, one NCCL all_gather of the (n,512) features per step"
-        if n_gpus > 1 else "dp1",
+        "parallelism": f"dp{n_gpus}: frame list sharded per rank, one NCCL all_gather of the (n,512) features per step "
+                       "(side stream: overlaps the next step's tower)" if n_gpus > 1 else "dp1",
     }
 
 
@@ -184,10 +189,10 @@ def time_cpu(reps: int, warm: int, budget_s: float = 20.0):
     """Times the oracle port on a bounded sample: the sample size is chosen from a probe so that warm-up + reps stay
     near `budget_s` seconds of CPU work.  -> (per-rep seconds, cores, sample)"""
     import torch
-    from oracle import clip_tower
+    from video_features_b200 import synthetic_weights
     cores = usable_cores()
     torch.set_num_threads(cores)
-    sd = clip_tower.synthetic_state_dict(0)
+    sd = synthetic_weights.clip_vit_b32_state_dict(0)
     frames = synth_frames_host(256, 1234).numpy()
     cpu_step(sd, frames[:4])                                   # page in / thread pool start
     t0 = time.perf_counter()
@@ -242,7 +247,7 @@ def run_reference(args, rank: int) -> None:
 def run_engine(args, rank: int, world: int, local_rank: int) -> None:
     import torch
     import torch.distributed as dist
-    from oracle import clip_tower                      # synthetic weight generator only (checker infrastructure)
+    from video_features_b200 import synthetic_weights
     from video_features_b200.clip_engine import ClipEngine
 
     if not torch.cuda.is_available():
@@ -252,29 +257,44 @@ def run_engine(args, rank: int, world: int, local_rank: int) -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    sd = clip_tower.synthetic_state_dict(0)
+    sd = synthetic_weights.clip_vit_b32_state_dict(0)
     eng = ClipEngine(sd, device=local_rank, chunk_frames=args.chunk)
     n = FRAMES_PER_STEP
     frames_host = synth_frames_host(n, 100 + rank).pin_memory()
     frames_dev = frames_host.to(dev)
     out_host = torch.empty((n, 512), dtype=torch.float32).pin_memory()
-    gathered = torch.empty((world * n, 512), dtype=torch.float32, device=dev) if world > 1 else None
+    # N > 1: the all-gather of step k runs on a side stream while the tower of step k+1 runs (two landing buffers);
+    # the timed region ends only after the last gather has finished
+    gathered = [torch.empty((world * n, 512), dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    tick = [0]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def gather_async(y):
+        ev = torch.cuda.Event()
+        ev.record()
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            dist.all_gather_into_tensor(gathered[tick[0] & 1], y)
+        y.record_stream(side)
+        tick[0] += 1
+
     def step_dev():
         y = eng.encode_frames_u8(frames_dev)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, y)
+            gather_async(y)
         return y
 
     def step_host():
-        y = eng.encode_frames_u8_host(frames_host, out_host)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, y.to(dev, non_blocking=True))
+        if world == 1:
+            return eng.encode_frames_u8_host(frames_host, out_host)
+        # host frames in; features stay on the device for the gather AND come back to the host
+        y = eng.encode_frames_u8_host_dev(frames_host, out_host)
+        gather_async(y)
         return y
 
     def timed(fn, steps):
@@ -283,6 +303,8 @@ def run_engine(args, rank: int, world: int, local_rank: int) -> None:
         e0.record()
         for _ in range(steps):
             fn()
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -334,6 +356,13 @@ def run_engine(args, rank: int, world: int, local_rank: int) -> None:
         "eager_ms_per_step_by_kernel": cats,
         "whole_step_tflops": value / world * FLOP_PER_FRAME / 1e12,
         "whole_step_frac": value / world * FLOP_PER_FRAME / 1e12 / peaks["tflops_sustained"],
+        # the memory-bound kernels against the HBM roofline: ALGORITHMIC bytes per frame over their
+        # event-timed device time; the chunk's activations partly live in the 126 MB L2, so > 1 is possible
+        "hbm": {k: {"algorithmic_bytes_per_frame": b, "ms_per_step": cats.get(k, 0.0),
+                    "achieved_gbs": (b * n / (cats[k] / 1e3) / 1e9) if cats.get(k) else None,
+                    "frac_of_hbm_peak": (b * n / (cats[k] / 1e3) / 1e9 / peaks["hbm_gbs"]) if cats.get(k) else None}
+                for k, b in HBM_BYTES_PER_FRAME.items()},
+        "hbm_peak_gbs": peaks["hbm_gbs"],
     }
 
     line = {
@@ -359,13 +388,45 @@ def run_engine(args, rank: int, world: int, local_rank: int) -> None:
                       f"(oracle port of the reference --cpu path), torch threads={cores}, {cpu_model_name()}",
             "median_s_per_rep": statistics.median(ts)}
     if rank == 0 and world == 1 and args.torch_gpu:
+        from oracle import clip_tower                  # the library-call bar: the oracle's torch modules on this GPU
         sdg = {k: v.to(dev) for k, v in sd.items()}
         xg = torch.randn(250, 3, 224, 224, device=dev)
-        line["torch_gpu_baseline"] = _torch_gpu_leg(lambda: clip_tower.encode_image(sdg, xg), 250, UNIT,
-                                                    "oracle port of the ViT-B/32 tower (torch eager, cuBLAS), 250 pre-normalised frames per call, transform excluded")
+        leg = _torch_gpu_leg(lambda: clip_tower.encode_image(sdg, xg), 250, UNIT,
+                             "oracle port of the ViT-B/32 tower (torch eager, cuBLAS), 250 pre-normalised frames per call, transform excluded")
+        # fp16 weights and activations: what `clip.load` gives the reference on a CUDA device (its GPU arithmetic)
+        sdh = {k: v.half() for k, v in sdg.items()}
+        xh = xg.half()
+        with torch.no_grad():
+            for _ in range(2):
+                clip_tower.encode_image(sdh, xh)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(8):
+                clip_tower.encode_image(sdh, xh)
+            e1.record()
+            torch.cuda.synchronize()
+        leg["fp16"] = 250 * 8 / (e0.elapsed_time(e1) / 1e3)
+        line["torch_gpu_baseline"] = leg
+    eng.close()
+    del eng, frames_dev
+    torch.cuda.empty_cache()
+    # ---- secondary workloads, measured by the same (driver-run) command: the video-list product path (BASELINE.json
+    # configs[4], every N), I3D rgb (configs[2], N = 1) and RAFT -> I3D flow (configs[3], N = 1 and its 2-GPU form)
+    if not args.no_secondary:
+        sec = {}
+        for name, fn, ok in (("c5_video_list", lambda: run_c5(args, rank, world, local_rank, quick=True), True),
+                             ("i3d_rgb", lambda: run_i3d(args, quick=True), world == 1),
+                             ("raft_i3d_flow", lambda: run_raft(args, rank, world, local_rank, quick=True), world <= 2)):
+            if not ok:
+                continue
+            try:
+                sec[name] = fn()
+            except BaseException as err:               # a secondary line never takes the headline down with it
+                sec[name] = {"error": f"{type(err).__name__}: {err}"}
+        line["secondary"] = sec
     if rank == 0:
         emit(line)
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -441,10 +502,9 @@ def _torch_gpu_leg(fn, units, unit, what):
     return out
 
 
-def run_i3d(args) -> None:
+def run_i3d(args, quick: bool = False):
     import torch
     from video_features_b200.i3d_engine import I3DEngine
-    from oracle import i3d_net
     torch.cuda.set_device(0)
     sd, wsrc = _weights("rgb")
     S = int(os.environ.get("VF_BENCH_I3D_STACKS", "32"))
@@ -454,6 +514,8 @@ def run_i3d(args) -> None:
     frames = frames_host.cuda()
     fn = lambda: eng.forward_frames_u8(frames[:, :64])
     W, K = max(args.warmup, 3), max(args.steps, 1)
+    if quick:
+        W, K = 3, min(K, 8)
     sampler = ClockSampler(0)
     ms = _timed_loop(fn, K, W)
     clocks = sampler.stop()
@@ -471,7 +533,8 @@ def run_i3d(args) -> None:
             "e2e": {"value": S * K / (ms_e2e / 1e3), "unit": "stacks/s", "h2d_bytes_per_step": int(frames_host.numel()),
                     "d2h_bytes_per_step": S * 1024 * 4},
             "gpu_launches": int(eng.launch_count), "roofline": roof}
-    if not args.no_cpu:
+    if not args.no_cpu and not quick:
+        from oracle import i3d_net
         cores = usable_cores()
         torch.set_num_threads(cores)
         x = i3d_net.rgb_transform(frames_host[0, :64].permute(0, 3, 1, 2).float())
@@ -479,51 +542,104 @@ def run_i3d(args) -> None:
         t0 = time.perf_counter(); i3d_net.forward_features(sd, x); dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "stacks/s", "cores": cores, "kind": "port",
                                 "sample": f"1 stack (64x224x224), oracle port of I3D fp32, torch threads={cores}, {cpu_model_name()}"}
-    if args.torch_gpu:
+    if args.torch_gpu and not quick:
+        from oracle import i3d_net
         sdg = {k: v.cuda() for k, v in sd.items()}
         xg = torch.cat([i3d_net.rgb_transform(frames_host[i, :64].permute(0, 3, 1, 2).float()) for i in range(2)]).cuda()
         line["torch_gpu_baseline"] = _torch_gpu_leg(lambda: i3d_net.forward_features(sdg, xg), 2, "stacks/s",
                                                     "oracle port of I3D (torch conv3d / cuDNN, eager), 2 stacks per call")
-    emit(line)
+    eng.close()
+    del eng, frames
+    torch.cuda.empty_cache()
+    return line
 
 
-def run_raft(args) -> None:
+def smooth_frames(n: int, h: int, w: int, seed: int, shift=(1.7, -0.9)):
+    """Smooth texture translating by a sub-pixel shift per frame (non-degenerate optical flow): (n,h,w,3) uint8."""
     import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(seed)
+    base = torch.rand(1, 3, h // 4 + 8, w // 4 + 8, generator=g)
+    base = F.interpolate(base, size=(h + 64, w + 64), mode="bicubic", align_corners=False).clamp(0, 1)
+    ys, xs = torch.meshgrid(torch.arange(h).float(), torch.arange(w).float(), indexing="ij")
+    out = []
+    for i in range(n):
+        gx = (xs + 32 + shift[0] * i) / (w + 63) * 2 - 1
+        gy = (ys + 32 + shift[1] * i) / (h + 63) * 2 - 1
+        out.append(F.grid_sample(base, torch.stack([gx, gy], -1)[None], align_corners=True)[0])
+    return (torch.stack(out) * 255).round().permute(0, 2, 3, 1).contiguous().to(torch.uint8)
+
+
+def run_raft(args, rank: int = 0, world: int = 1, local_rank: int = 0, quick: bool = False):
+    """BASELINE.json configs[3]: RAFT on 480x270 frame pairs -> I3D flow branch.  world = 2 is the configuration the
+    baseline names (2 x B200): stacks are sharded over the ranks (each runs RAFT -> I3D flow on its own 64 pairs, no
+    data-path collective) and the (1, 1024) features are all-gathered."""
+    import torch
+    import torch.distributed as dist
     from video_features_b200.i3d_engine import I3DEngine
     from video_features_b200.raft_engine import RAFTEngine
-    from oracle import raft_net
-    torch.cuda.set_device(0)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
     sd, wsrc = _weights("raft")
     sdf, _ = _weights("flow")
     F = 65
-    eng = RAFTEngine(sd, 0, max_frames=F, max_h=270, max_w=480)
-    i3d = I3DEngine(sdf, "flow", 0, max_stacks=1, max_T=64)
-    frames_host = raft_net.synthetic_frames(F, 270, 480, seed=2).permute(0, 2, 3, 1).contiguous().to(torch.uint8).pin_memory()
-    frames = frames_host.cuda()
+    eng = RAFTEngine(sd, local_rank, max_frames=F, max_h=270, max_w=480)
+    i3d = I3DEngine(sdf, "flow", local_rank, max_stacks=1, max_T=64)
+    frames_host = smooth_frames(F, 270, 480, seed=2 + rank).pin_memory()
+    frames = frames_host.to(dev)
+    gathered = torch.empty((world, 1024), dtype=torch.float32, device=dev) if world > 1 else None
     def fn():
         flow = eng.flow(frames, iters=20, unpad=False)         # padded, as the I3D path consumes it
-        return i3d.forward_flow(flow[None])
+        y = i3d.forward_flow(flow[None])
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, y)
+        return y
     W, K = max(args.warmup, 3), max(args.steps, 1)
-    sampler = ClockSampler(0)
-    ms = _timed_loop(fn, K, W)
-    clocks = sampler.stop()
-    ms_raft = _timed_loop(lambda: eng.flow(frames, iters=20, unpad=False), K, 1)
+    if quick:
+        W, K = 3, min(K, 4)
+    def timed(f, steps, warm):
+        for _ in range(warm):
+            f()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            f()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms = timed(fn, K, W)
+    clocks = sampler.stop() if sampler else None
+    ms_raft = timed(lambda: eng.flow(frames, iters=20, unpad=False), K, 1)
     def host_fn():
-        flow = eng.flow(frames_host.cuda(non_blocking=True), iters=20, unpad=False)
-        return i3d.forward_flow(flow[None]).cpu()
-    ms_e2e = _timed_loop(host_fn, K, 1)
+        flow = eng.flow(frames_host.to(dev, non_blocking=True), iters=20, unpad=False)
+        y = i3d.forward_flow(flow[None])
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, y)
+        return y.cpu()
+    ms_e2e = timed(host_fn, K, 1)
     roof = _gemm_roofline(lambda: eng.flow(frames, iters=20, unpad=False), min(K, 2), RAFT_GFLOP_272x480 * 1e9 * (F - 1), ms_raft / K)
-    line = {"metric": "pairs/sec RAFT 480x270 (20 iters) -> I3D flow", "value": (F - 1) * K / (ms / 1e3), "unit": "pairs/s",
-            "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+    line = {"metric": "pairs/sec RAFT 480x270 (20 iters) -> I3D flow", "value": world * (F - 1) * K / (ms / 1e3), "unit": "pairs/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": "RAFT optical flow on 480x270 frame pairs -> I3D flow branch (BASELINE.json configs[3])",
-                       "pairs_per_step": F - 1, "raft_only_pairs_per_sec": (F - 1) * K / (ms_raft / 1e3), "weights": wsrc,
+                       "pairs_per_step_per_gpu": F - 1, "raft_only_pairs_per_sec": world * (F - 1) * K / (ms_raft / 1e3), "weights": wsrc,
+                       "parallelism": f"dp{world}: one 64-pair stack per rank per step, all_gather of the (1,1024) features" if world > 1 else "dp1",
                        "note": "mask head + convex upsample run once (the reference runs them 20x and discards 19)"},
             "clocks": clocks,
-            "e2e": {"value": (F - 1) * K / (ms_e2e / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": int(frames_host.numel()),
-                    "d2h_bytes_per_step": 1024 * 4},
+            "e2e": {"value": world * (F - 1) * K / (ms_e2e / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": int(frames_host.numel()) * world,
+                    "d2h_bytes_per_step": 1024 * 4 * world},
             "gpu_launches": int(eng.launch_count + i3d.launch_count), "roofline": roof}
-    if not args.no_cpu:
+    if not args.no_cpu and not quick and rank == 0:
+        from oracle import raft_net
         cores = usable_cores()
         torch.set_num_threads(cores)
         x = raft_net.pad(frames_host[:3].permute(0, 3, 1, 2).float())
@@ -531,12 +647,103 @@ def run_raft(args) -> None:
         t0 = time.perf_counter(); raft_net.forward(sd, x[:-1], x[1:], 20); dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": 2.0 / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
                                 "sample": f"2 pairs 272x480, 20 iterations, oracle port of RAFT fp32, torch threads={cores}, {cpu_model_name()}"}
-    if args.torch_gpu:
+    if args.torch_gpu and not quick and rank == 0:
+        from oracle import raft_net
         sdg = {k: v.cuda() for k, v in sd.items()}
         xg = raft_net.pad(frames_host[:9].permute(0, 3, 1, 2).float()).cuda()
         line["torch_gpu_baseline"] = _torch_gpu_leg(lambda: raft_net.forward(sdg, xg[:-1], xg[1:], 20), 8, "pairs/s",
                                                     "oracle port of RAFT (torch conv2d / cuDNN, eager), 8 pairs per call, 20 iterations")
-    emit(line)
+    eng.close(); i3d.close()
+    del eng, i3d, frames
+    torch.cuda.empty_cache()
+    return line
+
+
+# ----------------------------------------------------------------------------------------- the video-list product path
+def run_c5(args, rank: int, world: int, local_rank: int, quick: bool = False):
+    """BASELINE.json configs[4]: a 10k-video list through the product's own list path -- ExtractCLIP.forward (decode
+    pool -> pinned staging -> one engine call per 1024 frames -> per-video feature blocks) under the --device_ids
+    dispatch (`dispatch.run_shard`: the rank's torch.chunk of the list, then ONE NCCL all-gather of every video's
+    (12,512) block).  Decode is stubbed: list entry i maps to a deterministic synthetic 12-frame 224x224 clip, a function
+    of i alone; the sink is the all-gather (nothing is written to disk).  Timed with CUDA events around the whole shard
+    (they bracket the host work too), max over ranks."""
+    import argparse as ap
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from tqdm import tqdm
+    from video_features_b200 import dispatch
+    from video_features_b200.extract.extract_clip import ExtractCLIP
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    n_videos = int(os.environ.get("VF_BENCH_C5_VIDEOS", "10000"))
+    per = 12
+    pool_n = 64
+    pool = np.random.default_rng(77).integers(0, 256, (pool_n, per, 224, 224, 3), dtype=np.uint8)
+
+    def source(path, method):                              # (frames, fps, timestamps_ms) like utils.extract_frames
+        i = int(path.rsplit("/", 1)[1])
+        clip = pool[i % pool_n]
+        return [clip[k] for k in range(per)], 25.0, [0.0] * per
+
+    os.environ["VF_CLIP_SYNTHETIC"] = "0"
+    ns = ap.Namespace(feature_type="CLIP-ViT-B/32", video_paths=[os.path.abspath(__file__)], flow_paths=None,
+                      file_with_video_paths=None, video_dir=None, flow_dir=None, extraction_fps=None,
+                      extract_method=f"uni_{per}", on_extraction="print", output_path="./output", output_direct=True,
+                      tmp_path="./tmp")
+    ex = ExtractCLIP(ns, external_call=True)
+    ex.progress.close()
+    ex.progress = tqdm(total=0, disable=True)
+    ex.frame_source = source
+    ex.path_list = [f"synthetic://{i}" for i in range(n_videos)]
+    # warm-up: engine creation, graph capture for the chunk sizes in use, pinned buffers, thread pools
+    warm = ExtractCLIP.forward(ex, torch.arange(0, min(n_videos, 3 * 86), device=dev))
+    del warm
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    blocks = dispatch.run_shard(ex, n_videos, rank, world, dev, gather_key="CLIP-ViT-B/32")
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    # every rank holds every video's block, in list order: entries i and i + 64 are the same clip
+    assert len(blocks) == n_videos and all(tuple(b.shape) == (per, 512) for b in blocks[:: max(1, n_videos // 50)])
+    for i in (0, 1, pool_n - 1, n_videos // 2, n_videos - pool_n - 1):
+        if 0 <= i and i + pool_n < n_videos:
+            assert torch.equal(blocks[i], blocks[i + pool_n]), f"gathered block {i} != block {i + pool_n}"
+    engine = ex._engines[local_rank]
+    line = {"metric": "frames/sec CLIP-ViT-B/32 @224px, 10k-video list", "value": n_videos * per / (ms / 1e3), "unit": UNIT,
+            "videos_per_sec": n_videos / (ms / 1e3), "n_gpus": world, "steps": 1, "warmup": 1, "ms_per_step": ms,
+            "host_wall_s_rank0": wall, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
+            "data": "synthetic",
+            "config": {"workload": "10k-video synthetic list, CLIP-ViT-B/32, sharded across --device_ids (BASELINE.json configs[4])",
+                       "videos": n_videos, "frames_per_video": per, "frames_per_engine_call": ex.batch_frames,
+                       "decode": "stubbed (clip = f(list index)); staging copy into pinned memory, H2D, tower, D2H, per-video "
+                                 "blocks and the final all-gather are inside the timed region",
+                       "host_threads_per_rank": ex.decode_workers, "host_cores_usable": usable_cores(),
+                       "parallelism": f"dp{world}: torch.chunk of the list per rank + one all_gather of the feature blocks"},
+            "clocks": clocks,
+            "e2e": {"value": n_videos * per / (ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": n_videos * per * 150528,
+                    "d2h_bytes_per_step": n_videos * per * 2048,
+                    "api": "ExtractCLIP.forward under dispatch.run_shard (main.py --device_ids path)"},
+            "gpu_launches": int(engine.launch_count)}
+    for e in ex._engines.values():
+        e.close()
+    ex._engines.clear()
+    del blocks
+    torch.cuda.empty_cache()
+    return line
 
 
 def main() -> None:
@@ -549,8 +756,11 @@ def main() -> None:
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--torch-gpu", action="store_true", dest="torch_gpu",
                     help="also time the oracle's fp32 torch modules on the same GPU (library-call bar), key torch_gpu_baseline")
-    ap.add_argument("--workload", default="clip", choices=["clip", "i3d", "raft"],
-                    help="clip = the headline (BASELINE.json configs[1]); i3d / raft = configs[2] / configs[3], 1 GPU")
+    ap.add_argument("--workload", default="clip", choices=["clip", "i3d", "raft", "c5"],
+                    help="clip = the headline (BASELINE.json configs[1], with the other configs as `secondary`); i3d / raft "
+                         "/ c5 = configs[2] / configs[3] / configs[4] alone")
+    ap.add_argument("--no-secondary", action="store_true", dest="no_secondary",
+                    help="headline only: skip the secondary workloads (c5 video list, I3D, RAFT -> I3D flow)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -558,17 +768,24 @@ def main() -> None:
     if args.impl == "reference":
         run_reference(args, rank)
         return
-    if args.workload == "i3d":
-        return run_i3d(args)
-    if args.workload == "raft":
-        return run_raft(args)
     if world != args.gpus and world == 1 and args.gpus > 1:
         # launched without torchrun: re-exec under torch.distributed.run on this node
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29541"),
                os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
-    run_engine(args, rank, world, local_rank)
+    if args.workload == "clip":
+        return run_engine(args, rank, world, local_rank)
+    line = {"i3d": lambda: run_i3d(args), "raft": lambda: run_raft(args, rank, world, local_rank),
+            "c5": lambda: run_c5(args, rank, world, local_rank)}[args.workload]()
+    if rank == 0:
+        emit(line)
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
 
 
 if __name__ == "__main__":

@@ -34,7 +34,7 @@ def gather_feature_blocks(blocks: Sequence[torch.Tensor], width: int, device: to
     rank order (== list order, because shards are contiguous).  Without a process group (one device) it is the
     identity."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return [b.to(device, torch.float32) for b in blocks]
+        return [b.to(torch.float32) for b in blocks]            # nothing to exchange: the blocks stay where they are
     world = dist.get_world_size()
     counts = torch.tensor([b.shape[0] for b in blocks], dtype=torch.int64, device=device)
     n_local = torch.tensor([counts.numel(), int(counts.sum()) if counts.numel() else 0], dtype=torch.int64, device=device)
@@ -49,7 +49,8 @@ def gather_feature_blocks(blocks: Sequence[torch.Tensor], width: int, device: to
     all_cnt = all_cnt.view(world, cnt_pad.numel()).cpu()
     rows = torch.zeros((max(max_rows, 1), width), dtype=torch.float32, device=device)
     if counts.numel() and int(sizes[dist.get_rank(), 1]):
-        torch.cat([b.to(device, torch.float32) for b in blocks], out=rows[:int(sizes[dist.get_rank(), 1])])
+        # one concatenation where the blocks live, then ONE copy to the device (not a copy per video)
+        rows[:int(sizes[dist.get_rank(), 1])].copy_(torch.cat([b.to(torch.float32) for b in blocks]), non_blocking=True)
     all_rows = torch.empty((world * rows.shape[0], width), dtype=torch.float32, device=device)
     dist.all_gather_into_tensor(all_rows, rows)                    # concatenation along dim 0
     all_rows = all_rows.view(world, rows.shape[0], width)
