@@ -9,7 +9,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvfeat.so")
+# VF_LIBVFEAT selects another build of the same library (A/B variants of one kernel, scripts/build_variants.sh)
+LIB_PATH = os.environ.get("VF_LIBVFEAT") or os.path.join(_HERE, "libvfeat.so")
 
 VF_OK = 0
 VF_ACT_NONE, VF_ACT_QUICKGELU, VF_ACT_RELU, VF_ACT_SIGMOID, VF_ACT_TANH = 0, 1, 2, 3, 4

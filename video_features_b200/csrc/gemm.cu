@@ -23,16 +23,30 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <vector>
 
 #include "common.cuh"
 #include "internal.h"
 
+// Epilogue hand-off variant (compile-time; scripts/build_variants.sh builds one library per value for A/B runs):
+//   0  slice of 128 rows: 4 warps fill it, one named barrier, ONE elected thread issues a [128 x 128 B] TMA store
+//   5  per-warp: every warp owns its 32 rows of the slice (4 KB), fences, __syncwarp()s and issues its own
+//      [32 x 128 B] TMA store -- no barrier between warps, no agent serialisation
+//   4  per-warp transpose through the same 4 KB region, then coalesced 16-byte st.global (4 full 128-byte rows per
+//      warp instruction) -- no async proxy at all
+#ifndef VF_EPI_MODE
+#define VF_EPI_MODE 0
+#endif
+// measurement aids: VF_DBG_NO_EPI = accumulators are released unread (main loop only); VF_DBG_NO_STORE = the whole
+// epilogue except the global store instructions
 namespace vf {
 
 namespace {
 
+constexpr int EPI_MODE = VF_EPI_MODE;
 constexpr int BM = 128;          // rows per CTA (256 per pair)
+constexpr int STORE_ROWS = EPI_MODE == 5 ? 32 : BM;     // rows of one TMA store box
 constexpr int BK = 64;           // 64 fp16 = one 128-byte swizzle row
 constexpr int EPI_WARPS = 8;
 constexpr uint32_t SLICE_BYTES = 128 * 128;   // 128 rows x 128 B (32 fp32 or 64 fp16 columns)
@@ -223,6 +237,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * BN + (uint32_t(q * 32) << 16);
+#ifndef VF_DBG_NO_EPI
             bool keep = true;     // rows outside the valid conv region become the next layer's zero padding
             if (cg.mask) {
                 const int m = m0 + row - cg.row0;
@@ -237,12 +252,20 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int sp = 0; sp < NSP; ++sp) {     // split output: the slice is produced twice, hi then lo
                 uint8_t* buf = bufs + (Cfg::EPI_BUFS == 2 ? (it & 1) : 0) * SLICE_BYTES;
                 uint8_t* myrow = buf + row * 128;
-                // The TMA store that last used this buffer must have finished reading it.  With two buffers that is
-                // guaranteed by the barrier of the previous slice (the agent drains the older store before arriving
-                // there, below); with one buffer it has to be checked here, at the cost of a second barrier.
-                if (Cfg::EPI_BUFS == 1) {
-                    if (agent) bulk_wait_read<0>();
-                    named_bar_sync(1 + grp, 128);
+                if (EPI_MODE == 0) {
+                    // The TMA store that last used this buffer must have finished reading it.  With two buffers that is
+                    // guaranteed by the barrier of the previous slice (the agent drains the older store before arriving
+                    // there, below); with one buffer it has to be checked here, at the cost of a second barrier.
+                    if (Cfg::EPI_BUFS == 1) {
+                        if (agent) bulk_wait_read<0>();
+                        named_bar_sync(1 + grp, 128);
+                    }
+                } else if (EPI_MODE == 5) {
+                    // this warp's own store of two slices ago (one slice ago with a single buffer) has read its 4 KB
+                    if (lane == 0) {
+                        if (Cfg::EPI_BUFS == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+                    }
+                    __syncwarp();
                 }
                 const int n = n_blk * BN + c;
                 if (ep.out_f32) {
@@ -286,25 +309,59 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                            pack_half2(v[8 * j + 4], v[8 * j + 5]), pack_half2(v[8 * j + 6], v[8 * j + 7]));
                     }
                 }
-                fence_proxy_async();
-                // two buffers: the store of the previous slice (the OTHER buffer) has had this slice's compute time to
-                // read its source; once it has, everybody may overwrite that buffer in the next iteration
-                if (Cfg::EPI_BUFS == 2 && agent) bulk_wait_read<0>();
-                named_bar_sync(1 + grp, 128);
-                if (agent) {
-                    // rows >= M and columns >= N are clipped by the TMA unit.  A group is committed for EVERY slice,
-                    // also for the (empty) ones right of N, so that the group accounting of wait_group.read stays uniform.
-                    if (n < N) tma_store_2d((SPLIT && sp) ? &tmO2 : &tmO, buf, n, m0);
-                    bulk_commit();
+                if (EPI_MODE == 0) {
+                    fence_proxy_async();
+                    // two buffers: the store of the previous slice (the OTHER buffer) has had this slice's compute time to
+                    // read its source; once it has, everybody may overwrite that buffer in the next iteration
+                    if (Cfg::EPI_BUFS == 2 && agent) bulk_wait_read<0>();
+                    named_bar_sync(1 + grp, 128);
+                    if (agent) {
+                        // rows >= M and columns >= N are clipped by the TMA unit.  A group is committed for EVERY slice,
+                        // also for the (empty) ones right of N, so that the group accounting of wait_group.read stays uniform.
+#ifndef VF_DBG_NO_STORE
+                        if (n < N) tma_store_2d((SPLIT && sp) ? &tmO2 : &tmO, buf, n, m0);
+#endif
+                        bulk_commit();
+                    }
+                } else if (EPI_MODE == 5) {
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+#ifndef VF_DBG_NO_STORE
+                        if (n < N) tma_store_2d((SPLIT && sp) ? &tmO2 : &tmO, buf + q * 4096, n, m0 + q * 32);
+#endif
+                        bulk_commit();
+                    }
+                } else {
+                    // EPI_MODE 4: the warp reads its own 32 x 128 B back row-wise and writes 4 complete 128-byte rows per
+                    // instruction (lanes 8i..8i+7 cover row i of the group of 4)
+                    __syncwarp();
+                    uint8_t* obase = static_cast<uint8_t*>(ep.out) + ((SPLIT && sp) ? size_t(ep.split_off) * 2 : 0);
+                    const int esz = ep.out_f32 ? 4 : 2;
+                    const int ch = lane & 7;
+                    const bool col_ok = n + (ch * 16) / esz < N;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = i * 4 + (lane >> 3);
+                        const uint4 val = *reinterpret_cast<const uint4*>(buf + (q * 32 + r) * 128 + ((uint32_t(ch) ^ uint32_t(r & 7)) << 4));
+                        const int gm = m0 + q * 32 + r;
+#ifndef VF_DBG_NO_STORE
+                        if (gm < M && col_ok)
+                            *reinterpret_cast<uint4*>(obase + (size_t(gm) * ep.ldo + n) * esz + ch * 16) = val;
+#endif
+                    }
+                    if (Cfg::EPI_BUFS == 1) __syncwarp();      // the same 4 KB is rewritten by the next slice
                 }
                 ++it;
             }
+#endif  // VF_DBG_NO_EPI
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(&tempty[acc], 0);   // this accumulator stage is drained
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (agent) bulk_wait<0>();       // all global writes of this CTA are complete before it retires
+        // all global writes of this CTA are complete before it retires
+        if (EPI_MODE == 5 ? (lane == 0) : (EPI_MODE == 0 && agent)) bulk_wait<0>();
     }
 
     tc_fence_before();
@@ -336,13 +393,15 @@ int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
                      const GemmEpi& ep, int M,
                      int N, const ConvGeom& cg, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, STAGES, NSPLIT>;
-    static bool attr_set[64] = {false};
+    // one handle per thread, but several threads (one per handle) may reach the same instantiation at once: the attribute
+    // call is idempotent, the flag that remembers it is an atomic (acquire / release), so there is no data race
+    static std::atomic<bool> attr_set[64];
     int dev = 0;
     VF_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
         VF_CUDA(cudaFuncSetAttribute(gemm_f16_pair_kernel<BN, STAGES, NSPLIT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::SMEM_BYTES));
-        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
     }
     const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
     const int pairs = device_sm_count() / 2;
@@ -355,15 +414,15 @@ int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
 }  // namespace
 
 int device_sm_count() {
-    static int sms[64] = {0};
+    static std::atomic<int> sms[64];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
-    if (sms[dev] == 0) {
-        int v = 0;
+    int v = sms[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
         if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
-        sms[dev] = v;
+        sms[dev].store(v, std::memory_order_relaxed);
     }
-    return sms[dev];
+    return v;
 }
 
 int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols,
@@ -438,14 +497,14 @@ static int run_gemm(const CUtensorMap& tmA, const __half* B, int ldb, int64_t Kt
     CUtensorMap tmB, tmO, tmO2;
     VF_TRY(make_tmap_2d(&tmB, B, 2, uint64_t(N), uint64_t(Ktot), uint64_t(ldb) * 2, uint32_t(bn / 2), BK));
     const uint64_t ncols = uint64_t(N);     // (N % 8 == 0: a store view narrower than a 16-byte multiple corrupts its neighbours)
-    if (ep.out_f32) VF_TRY(make_tmap_2d(&tmO, ep.out, 4, uint64_t(M), ncols, uint64_t(ep.ldo) * 4, BM, 32));
-    else            VF_TRY(make_tmap_2d(&tmO, ep.out, 2, uint64_t(M), ncols, uint64_t(ep.ldo) * 2, BM, 64));
+    if (ep.out_f32) VF_TRY(make_tmap_2d(&tmO, ep.out, 4, uint64_t(M), ncols, uint64_t(ep.ldo) * 4, STORE_ROWS, 32));
+    else            VF_TRY(make_tmap_2d(&tmO, ep.out, 2, uint64_t(M), ncols, uint64_t(ep.ldo) * 2, STORE_ROWS, 64));
     tmO2 = tmO;
     if (ep.split_off) {     // second view of the output rows: the lo halves, both views clip at N columns
         if (ep.out_f32 || ep.split_off < N || ep.split_off % 8)
             return fail(VF_ERR_INVALID, "gemm: split output needs fp16 out and split_off >= N, multiple of 8");
         VF_TRY(make_tmap_2d(&tmO2, static_cast<__half*>(ep.out) + ep.split_off, 2, uint64_t(M), ncols,
-                            uint64_t(ep.ldo) * 2, BM, 64));
+                            uint64_t(ep.ldo) * 2, STORE_ROWS, 64));
     }
     if (!g_prof.on) return run_gemm_launch(tmA, tmB, tmO, tmO2, bn, ep, M, N, cg, stream);
     if (g_prof.used + 2 > g_prof.ev.size())
