@@ -66,6 +66,10 @@ int vf_clip_normalize_u8(const uint8_t* src, int n, int src_h, int src_w, float*
  * D: fp16 or fp32 (out_f32, row pitch ldd elements, 16-byte aligned rows), bias/scale: fp32 [N] or NULL. */
 int vf_gemm_f16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, void* D, int ldd, int out_f32,
                 const float* bias, const float* scale, int act, void* stream);
+/* D += act(A . B^T * scale + bias), D fp32: the add happens in the L2 (TMA reduction), each element exactly once -- the
+ * residual-stream update `x = x + attn(...)` / `x = x + mlp(...)` of clip/model.py ResidualAttentionBlock.forward. */
+int vf_gemm_f16_accumulate(const void* A, int lda, const void* B, int ldb, int M, int N, int K, float* D, int ldd,
+                           const float* bias, const float* scale, int act, void* stream);
 /* Same GEMM with the result written as a split-fp16 pair: D[m][n] = fp16(v) and D[m][split_off + n] = fp16(v - fp16(v))
  * (split_off >= N, multiple of 8, ldd >= split_off + N).  RAFT's GEMM -> GEMM activations are carried this way: the
  * consumer's weights are duplicated over both halves, which restores ~22 mantissa bits on the activation operand. */

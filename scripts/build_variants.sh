@@ -13,8 +13,9 @@ for f in kernels host clip i3d i3d_kernels raft raft_kernels; do
     nvcc $FLAGS -c $SRC/$f.cu -o $OBJ/$f.o & pids+=($!)
   fi
 done
-declare -A V=( [epi0]="-DVF_EPI_MODE=0" [epi4]="-DVF_EPI_MODE=4" [epi5]="-DVF_EPI_MODE=5" \
-               [noepi]="-DVF_DBG_NO_EPI" [nostore0]="-DVF_EPI_MODE=0 -DVF_DBG_NO_STORE" [nostore5]="-DVF_EPI_MODE=5 -DVF_DBG_NO_STORE" )
+declare -A V=( [m0g2]="-DVF_EPI_MODE=0 -DVF_EPI_GROUPS=2" [m5g2]="-DVF_EPI_MODE=5 -DVF_EPI_GROUPS=2" \
+               [m0g4]="-DVF_EPI_MODE=0 -DVF_EPI_GROUPS=4" [m5g4]="-DVF_EPI_MODE=5 -DVF_EPI_GROUPS=4" \
+               [m5g3]="-DVF_EPI_MODE=5 -DVF_EPI_GROUPS=3" [m0g3]="-DVF_EPI_MODE=0 -DVF_EPI_GROUPS=3" )
 for tag in "${!V[@]}"; do
   nvcc $FLAGS ${V[$tag]} -c $SRC/gemm.cu -o $OBJ/gemm_$tag.o & pids+=($!)
 done

@@ -130,3 +130,19 @@ def test_gemm_rejects_bad_arguments(cuda_device):
     b = torch.zeros(64, 60, dtype=torch.float16, device=cuda_device)
     with pytest.raises(VfError):
         torch.ops.vfeat.gemm_f16(a, b, None, None, 0, True)
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 256, 768), (6000, 768, 768), (6000, 768, 3072), (77, 96, 200), (250, 768, 768)])
+def test_gemm_accumulate_adds_into_fp32_output(cuda_device, M, N, K):
+    """out += a @ b.T + bias (TMA reduction in the L2): twice in a row, against the fp32 reference of the same op; rows /
+    columns outside M x N of a larger buffer stay untouched."""
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = (torch.randn(M, K, generator=g) * 0.5).half().to(cuda_device)
+    b = (torch.randn(N, K, generator=g) * K ** -0.5).half().to(cuda_device)
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    x0 = (torch.randn(M, N, generator=g) * 3).to(cuda_device)
+    x = x0.clone()
+    torch.ops.vfeat.gemm_f16_accumulate(x, a, b, bias, 0)
+    torch.ops.vfeat.gemm_f16_accumulate(x, a, b, bias, 0)
+    ref = x0 + 2 * _ref(a, b, bias, None, 0)
+    assert rel_l2(x, ref) < 2e-6, rel_l2(x, ref)            # fp32 accumulate of fp16 products: only summation order differs

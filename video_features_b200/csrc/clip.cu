@@ -72,6 +72,7 @@ struct vf_clip {
     cudaStream_t cs = nullptr;                // stream of the active lane
     cudaEvent_t ev_in = nullptr;
     bool use_graph = true;
+    bool acc_resid = true;                    // residual adds in the GEMM epilogue (TMA reduction) instead of an fp16 y
     float* feat = nullptr;                    // [chunk, 512] tower output of the active lane
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
@@ -120,10 +121,10 @@ static int grow(uint8_t** p, size_t* cap, size_t need) {
     return VF_OK;
 }
 
-static GemmEpi epi(void* out, int ldo, int out_f32, const float* bias, int act) {
+static GemmEpi epi(void* out, int ldo, int out_f32, const float* bias, int act, int accumulate = 0) {
     GemmEpi e;
     memset(&e, 0, sizeof(e));
-    e.out = out; e.ldo = ldo; e.out_f32 = out_f32; e.bias = bias; e.act = act;
+    e.out = out; e.ldo = ldo; e.out_f32 = out_f32; e.bias = bias; e.act = act; e.accumulate = accumulate;
     return e;
 }
 
@@ -172,8 +173,8 @@ static int tower_attention(vf_clip* h, int c, cudaStream_t s) {
 }
 
 // The tower on one chunk whose patch matrix is already in h->patches; writes c x 512 fp32 to out.
-// The residual stream x stays fp32; every "x += GEMM output" is fused into the LayerNorm kernel that follows it,
-// so GEMM epilogues are write-only (bias / QuickGELU) and stream out through TMA stores.
+// GEMM epilogues never read global memory: bias / QuickGELU in registers, then TMA stores -- or, for the two GEMMs that
+// end a residual branch, a TMA reduction that adds the tile into the fp32 residual stream x.
 static int clip_tower_eager(vf_clip* h, int c, float* out, cudaStream_t s) {
     const int M = c * T;
     // patch embedding: [c*49, 3072] x [768, 3072]^T -> emb (fp32)
@@ -181,31 +182,46 @@ static int clip_tower_eager(vf_clip* h, int c, float* out, cudaStream_t s) {
     // token assembly (+ class / positional embedding) fused with ln_pre -> x
     VF_TRY(tower_embed_ln(h, c, s));
     h->launches += 2;
+    // The residual stream x stays fp32 in HBM.  acc_resid (default): out-proj and fc2 ADD their result into x from the
+    // GEMM epilogue (TMA reduction in the L2), so a LayerNorm pass only reads x and writes h: 6 bytes per element instead
+    // of the 12 of "x += y; h = LN(x)" with a separate fp16 increment y (VF_CLIP_RESID=y keeps that form for A/B runs).
+    const bool acc = h->acc_resid;
     for (int l = 0; l < L; ++l) {
         const ClipLayerDev& w = h->layer[l];
-        // x += y of the previous block's MLP (none for block 0); h = ln_1(x)
-        VF_TRY(tower_add_ln(h, h->x, W, l == 0 ? nullptr : h->y, W, 1, w.ln1_w, w.ln1_b, h->h, W, M, s));
+        // h = ln_1(x)   (y form: x += y of the previous block's MLP first)
+        VF_TRY(tower_add_ln(h, h->x, W, (acc || l == 0) ? nullptr : h->y, W, 1, w.ln1_w, w.ln1_b, h->h, W, M, s));
         VF_TRY(tower_gemm(h, h->h, W, w.w_qkv, W, M, 3 * W, W, epi(h->qkv, 3 * W, 0, w.b_qkv, VF_ACT_NONE), s));
         VF_TRY(tower_attention(h, c, s));
         if (l + 1 < L) {
-            VF_TRY(tower_gemm(h, h->att, W, w.w_o, W, M, W, W, epi(h->y, W, 0, w.b_o, VF_ACT_NONE), s));
-            // x += attention output; h = ln_2(x)
-            VF_TRY(tower_add_ln(h, h->x, W, h->y, W, 1, w.ln2_w, w.ln2_b, h->h, W, M, s));
+            if (acc) {
+                VF_TRY(tower_gemm(h, h->att, W, w.w_o, W, M, W, W, epi(h->x, W, 1, w.b_o, VF_ACT_NONE, 1), s));
+                VF_TRY(tower_add_ln(h, h->x, W, nullptr, W, 0, w.ln2_w, w.ln2_b, h->h, W, M, s));
+            } else {
+                VF_TRY(tower_gemm(h, h->att, W, w.w_o, W, M, W, W, epi(h->y, W, 0, w.b_o, VF_ACT_NONE), s));
+                VF_TRY(tower_add_ln(h, h->x, W, h->y, W, 1, w.ln2_w, w.ln2_b, h->h, W, M, s));
+            }
             VF_TRY(tower_gemm(h, h->h, W, w.w_fc, W, M, MLPW, W, epi(h->mlp, MLPW, 0, w.b_fc, VF_ACT_QUICKGELU), s));
-            VF_TRY(tower_gemm(h, h->mlp, MLPW, w.w_proj, MLPW, M, W, MLPW, epi(h->y, W, 0, w.b_proj, VF_ACT_NONE), s));
+            if (acc) VF_TRY(tower_gemm(h, h->mlp, MLPW, w.w_proj, MLPW, M, W, MLPW, epi(h->x, W, 1, w.b_proj, VF_ACT_NONE, 1), s));
+            else     VF_TRY(tower_gemm(h, h->mlp, MLPW, w.w_proj, MLPW, M, W, MLPW, epi(h->y, W, 0, w.b_proj, VF_ACT_NONE), s));
         } else {
             // Last block: only the CLS token reaches ln_post / proj (encode_image returns x[:, 0]), so after the
-            // attention everything runs on the c CLS rows: A operands are strided views (row pitch 50*768), y / h / mlp
-            // are compact c-row buffers.  Saves 49/50 of out-proj + MLP of this block (5.9 % of the tower's FLOPs).
-            VF_TRY(tower_gemm(h, h->att, T * W, w.w_o, W, c, W, W, epi(h->y, W, 0, w.b_o, VF_ACT_NONE), s));
-            VF_TRY(tower_add_ln(h, h->x, int64_t(T) * W, h->y, W, 1, w.ln2_w, w.ln2_b, h->h, W, c, s));
+            // attention everything runs on the c CLS rows: A operands and the residual rows are strided views (row pitch
+            // 50*768), h / mlp are compact c-row buffers.  Saves 49/50 of out-proj + MLP of this block (5.9 % of the FLOPs).
+            if (acc) {
+                VF_TRY(tower_gemm(h, h->att, T * W, w.w_o, W, c, W, W, epi(h->x, T * W, 1, w.b_o, VF_ACT_NONE, 1), s));
+                VF_TRY(tower_add_ln(h, h->x, int64_t(T) * W, nullptr, W, 0, w.ln2_w, w.ln2_b, h->h, W, c, s));
+            } else {
+                VF_TRY(tower_gemm(h, h->att, T * W, w.w_o, W, c, W, W, epi(h->y, W, 0, w.b_o, VF_ACT_NONE), s));
+                VF_TRY(tower_add_ln(h, h->x, int64_t(T) * W, h->y, W, 1, w.ln2_w, w.ln2_b, h->h, W, c, s));
+            }
             VF_TRY(tower_gemm(h, h->h, W, w.w_fc, W, c, MLPW, W, epi(h->mlp, MLPW, 0, w.b_fc, VF_ACT_QUICKGELU), s));
-            VF_TRY(tower_gemm(h, h->mlp, MLPW, w.w_proj, MLPW, c, W, MLPW, epi(h->y, W, 0, w.b_proj, VF_ACT_NONE), s));
+            if (acc) VF_TRY(tower_gemm(h, h->mlp, MLPW, w.w_proj, MLPW, c, W, MLPW, epi(h->x, T * W, 1, w.b_proj, VF_ACT_NONE, 1), s));
+            else     VF_TRY(tower_gemm(h, h->mlp, MLPW, w.w_proj, MLPW, c, W, MLPW, epi(h->y, W, 0, w.b_proj, VF_ACT_NONE), s));
         }
         h->launches += 7;
     }
-    // CLS rows: x += y of the last MLP; ln_post; then the 768 -> 512 projection
-    VF_TRY(tower_add_ln(h, h->x, int64_t(T) * W, h->y, W, 0, h->lnpost_w, h->lnpost_b, h->cls, W, c, s));
+    // CLS rows: (y form: x += y of the last MLP;) ln_post; then the 768 -> 512 projection
+    VF_TRY(tower_add_ln(h, h->x, int64_t(T) * W, acc ? nullptr : h->y, W, 0, h->lnpost_w, h->lnpost_b, h->cls, W, c, s));
     VF_TRY(tower_gemm(h, h->cls, W, h->w_proj, W, c, E, W, epi(out, E, 1, nullptr, VF_ACT_NONE), s));
     h->launches += 2;
     return VF_OK;
@@ -389,6 +405,8 @@ int vf_clip_create(vf_clip_t** out, const vf_clip_weights* w, int device, int ch
         {
             const char* e = getenv("VF_NO_GRAPH");
             h->use_graph = !(e && e[0] == '1');
+            const char* r = getenv("VF_CLIP_RESID");
+            h->acc_resid = !(r && r[0] == 'y');
         }
         activate(h, 0);
         VF_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));

@@ -48,7 +48,11 @@ constexpr int EPI_MODE = VF_EPI_MODE;
 constexpr int BM = 128;          // rows per CTA (256 per pair)
 constexpr int STORE_ROWS = EPI_MODE == 5 ? 32 : BM;     // rows of one TMA store box
 constexpr int BK = 64;           // 64 fp16 = one 128-byte swizzle row
-constexpr int EPI_WARPS = 8;
+// epilogue warp groups (4 warps = the 4 TMEM lane quarters each) of the plain 256-wide configuration -- the ViT GEMMs, whose
+// K = 768 shapes are bounded by the epilogue's latency chain (TMEM load -> math -> shared -> store), not by its bandwidth
+#ifndef VF_EPI_GROUPS
+#define VF_EPI_GROUPS 2
+#endif
 constexpr uint32_t SLICE_BYTES = 128 * 128;   // 128 rows x 128 B (32 fp32 or 64 fp16 columns)
 
 // NSPLIT = 2: the B stage holds the hi and the lo half-tile of a split-fp16 weight matrix and every K step issues two
@@ -60,8 +64,11 @@ struct GemmCfg {
     static constexpr uint32_t B_BYTES = NSPLIT * B_HALF;
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr uint32_t TMEM_COLS = BN == 192 ? 512 : 2 * BN;   // two accumulator stages BN columns apart (power of 2)
-    static constexpr uint32_t EPI_BUFS = NSPLIT == 2 ? 1 : 2;
-    static constexpr uint32_t STG_BYTES = 2 * EPI_BUFS * SLICE_BYTES;   // 2 epilogue groups x EPI_BUFS slice buffers
+    static constexpr int NGRP = (NSPLIT == 1 && BN == 256) ? VF_EPI_GROUPS : 2;   // epilogue groups of 4 warps
+    static constexpr int EPI_WARPS = 4 * NGRP;
+    static constexpr int THREADS = (4 + EPI_WARPS) * 32;
+    static constexpr uint32_t EPI_BUFS = (NSPLIT == 2 || NGRP > 2) ? 1 : 2;
+    static constexpr uint32_t STG_BYTES = NGRP * EPI_BUFS * SLICE_BYTES;   // NGRP epilogue groups x EPI_BUFS slice buffers
     static constexpr uint32_t BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;   // + align slack
     static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns");
@@ -111,7 +118,7 @@ __device__ __forceinline__ void epi_math32(float* v, const GemmEpi& ep, int n, i
 // SPLIT: split-fp16 output (GemmEpi::split_off) -- every fp16 slice is emitted twice, hi then lo, through tmO / tmO2.  A
 // compile-time switch: as a run-time loop it cost the plain epilogue 20 % on K = 768 shapes.
 template <int BN, int STAGES, int NSPLIT, bool SPLIT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GemmCfg<BN, STAGES, NSPLIT>::THREADS, 1)
 gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2, const GemmEpi ep,
                      const int M, const int N, const __grid_constant__ ConvGeom cg) {
@@ -150,7 +157,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);               // multicast tcgen05.commit
-            mbar_init(&tempty[i], 2 * EPI_WARPS);  // every epilogue warp of both CTAs arrives on the LEADER's copy
+            mbar_init(&tempty[i], 2 * Cfg::EPI_WARPS);  // every epilogue warp of both CTAs arrives on the LEADER's copy
         }
         fence_mbar_init();
     }
@@ -247,7 +254,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 keep = (m >= 0) && (w >= cg.w0) && (w < cg.w1) && (hh >= cg.h0) && (hh < cg.h1) && (tt >= cg.t0) && (tt < cg.t1);
             }
 #pragma unroll 1
-            for (int c = grp * slice_cols; c < BN; c += 2 * slice_cols)
+            for (int c = grp * slice_cols; c < BN; c += Cfg::NGRP * slice_cols)
 #pragma unroll
             for (int sp = 0; sp < NSP; ++sp) {     // split output: the slice is produced twice, hi then lo
                 uint8_t* buf = bufs + (Cfg::EPI_BUFS == 2 ? (it & 1) : 0) * SLICE_BYTES;
@@ -319,7 +326,10 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         // rows >= M and columns >= N are clipped by the TMA unit.  A group is committed for EVERY slice,
                         // also for the (empty) ones right of N, so that the group accounting of wait_group.read stays uniform.
 #ifndef VF_DBG_NO_STORE
-                        if (n < N) tma_store_2d((SPLIT && sp) ? &tmO2 : &tmO, buf, n, m0);
+                        if (n < N) {
+                            if (ep.accumulate) tma_reduce_add_2d(&tmO, buf, n, m0);
+                            else tma_store_2d((SPLIT && sp) ? &tmO2 : &tmO, buf, n, m0);
+                        }
 #endif
                         bulk_commit();
                     }
@@ -328,7 +338,10 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     __syncwarp();
                     if (lane == 0) {
 #ifndef VF_DBG_NO_STORE
-                        if (n < N) tma_store_2d((SPLIT && sp) ? &tmO2 : &tmO, buf + q * 4096, n, m0 + q * 32);
+                        if (n < N) {
+                            if (ep.accumulate) tma_reduce_add_2d(&tmO, buf + q * 4096, n, m0 + q * 32);
+                            else tma_store_2d((SPLIT && sp) ? &tmO2 : &tmO, buf + q * 4096, n, m0 + q * 32);
+                        }
 #endif
                         bulk_commit();
                     }
@@ -346,8 +359,14 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         const uint4 val = *reinterpret_cast<const uint4*>(buf + (q * 32 + r) * 128 + ((uint32_t(ch) ^ uint32_t(r & 7)) << 4));
                         const int gm = m0 + q * 32 + r;
 #ifndef VF_DBG_NO_STORE
-                        if (gm < M && col_ok)
-                            *reinterpret_cast<uint4*>(obase + (size_t(gm) * ep.ldo + n) * esz + ch * 16) = val;
+                        if (gm < M && col_ok) {
+                            uint8_t* dst = obase + (size_t(gm) * ep.ldo + n) * esz + ch * 16;
+                            if (ep.accumulate)
+                                red_add_f32x4(reinterpret_cast<float*>(dst), make_float4(__uint_as_float(val.x), __uint_as_float(val.y),
+                                                                                         __uint_as_float(val.z), __uint_as_float(val.w)));
+                            else
+                                *reinterpret_cast<uint4*>(dst) = val;
+                        }
 #endif
                     }
                     if (Cfg::EPI_BUFS == 1) __syncwarp();      // the same 4 KB is rewritten by the next slice
@@ -406,7 +425,7 @@ int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
     const int pairs = device_sm_count() / 2;
     const int grid = 2 * (tiles < pairs ? tiles : pairs);
-    gemm_f16_pair_kernel<BN, STAGES, NSPLIT, SPLIT><<<grid, 384, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, tmO2, ep, M, N, cg);
+    gemm_f16_pair_kernel<BN, STAGES, NSPLIT, SPLIT><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, tmO2, ep, M, N, cg);
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
@@ -483,6 +502,7 @@ static int run_gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const
 static int run_gemm(const CUtensorMap& tmA, const __half* B, int ldb, int64_t Ktot, int M, int N, const ConvGeom& cg,
                     const GemmEpi& ep, cudaStream_t stream) {
     if (!ep.out) return fail(VF_ERR_INVALID, "gemm: null output");
+    if (ep.accumulate && !ep.out_f32) return fail(VF_ERR_INVALID, "gemm: accumulate needs fp32 output");
     if (N % 8) return fail(VF_ERR_INVALID, "gemm: N=%d must be a multiple of 8", N);
     if (ep.out_f32 ? (ep.ldo % 4) : (ep.ldo % 8)) return fail(VF_ERR_INVALID, "gemm: ldo breaks 16-byte rows");
     // pair-tile width (the B box is half of it): the candidate that pads N least, the widest on a tie

@@ -245,6 +245,16 @@ int vf_gemm_f16(const void* A, int lda, const void* B, int ldb, int M, int N, in
                     static_cast<cudaStream_t>(stream));
 }
 
+int vf_gemm_f16_accumulate(const void* A, int lda, const void* B, int ldb, int M, int N, int K, float* D, int ldd,
+                           const float* bias, const float* scale, int act, void* stream) {
+    if (!A || !B || !D) return fail(VF_ERR_INVALID, "gemm: null buffer");
+    GemmEpi ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.out = D; ep.ldo = ldd; ep.out_f32 = 1; ep.bias = bias; ep.scale = scale; ep.act = act; ep.accumulate = 1;
+    return gemm_f16(static_cast<const __half*>(A), lda, static_cast<const __half*>(B), ldb, M, N, K, ep,
+                    static_cast<cudaStream_t>(stream));
+}
+
 int vf_gemm_f16_split(const void* A, int lda, const void* B, int ldb, int M, int N, int K, void* D, int ldd, int split_off,
                       const float* bias, const float* scale, int act, void* stream) {
     if (!A || !B || !D) return fail(VF_ERR_INVALID, "gemm: null buffer");

@@ -1,6 +1,8 @@
 // Memory-bound kernels of the CLIP path: frame transform (normalise / patchify), LayerNorm,
 // 50-token attention, and the Pillow-compatible fixed-point resample.  All are HBM/L2-bound
 // byte-and-float shuffles: 128-bit accesses, warp-shuffle reductions, no tensor cores.
+#include <atomic>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -330,55 +332,107 @@ __global__ void __launch_bounds__(128) attention50_kernel(const __half* __restri
 
 // Pillow ImagingResampleHorizontal_8bpc / Vertical_8bpc (third-party Pillow, libImaging/Resample.c), 3 channels:
 //   acc = 2^21 + sum_i px[i] * k[i]  (int32) ;  out = clip8(acc >> 22)
+// Frames are byte streams whose rows (w*3 bytes) are rarely 16-byte multiples, so both passes move CONTIGUOUS SPANS of
+// rows through shared memory: the span is fetched / written back with 128-bit accesses on its 16-byte-aligned body (the
+// few head / tail bytes go one by one), staged at the same offset modulo 16 as in global memory, and the per-pixel
+// arithmetic reads and writes bytes in shared memory only.
 __device__ __forceinline__ uint8_t clip8(int acc) {
     const int v = acc >> 22;
     return uint8_t(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
-__global__ void resample_h_kernel(const uint8_t* __restrict__ src, int n, int in_h, int in_w, uint8_t* __restrict__ dst,
-                                  int out_w, const int* __restrict__ bounds, const int* __restrict__ coef, int ksize) {
-    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    const int64_t total = int64_t(n) * in_h * out_w;
-    if (idx >= total) return;
-    const int xx = int(idx % out_w);
-    const int64_t row = idx / out_w;   // b*in_h + y
-    const int xmin = __ldg(bounds + 2 * xx), cnt = __ldg(bounds + 2 * xx + 1);
-    const int* k = coef + int64_t(xx) * ksize;
-    const uint8_t* p = src + (row * in_w + xmin) * 3;
-    int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
-    for (int i = 0; i < cnt; ++i) {
-        const int kv = __ldg(k + i);
-        s0 += int(__ldg(p + 3 * i)) * kv;
-        s1 += int(__ldg(p + 3 * i + 1)) * kv;
-        s2 += int(__ldg(p + 3 * i + 2)) * kv;
-    }
-    uint8_t* o = dst + (row * out_w + xx) * 3;
-    o[0] = clip8(s0);
-    o[1] = clip8(s1);
-    o[2] = clip8(s2);
+// smem[off .. off+n) <- g[0 .. n)  with off == (address of g) mod 16
+__device__ __forceinline__ void span_load(uint8_t* smem, const uint8_t* __restrict__ g, int64_t n, int tid, int nthreads) {
+    const int off = int(reinterpret_cast<uintptr_t>(g) & 15);
+    const int head = off ? min(int64_t(16 - off), n) : 0;
+    const int64_t body = (n - head) >> 4;
+    for (int i = tid; i < head; i += nthreads) smem[off + i] = __ldg(g + i);
+    const uint4* g4 = reinterpret_cast<const uint4*>(g + head);
+    uint4* s4 = reinterpret_cast<uint4*>(smem + off + head);
+    for (int64_t i = tid; i < body; i += nthreads) s4[i] = __ldg(g4 + i);
+    const int64_t done = head + (body << 4);
+    for (int64_t i = done + tid; i < n; i += nthreads) smem[off + i] = __ldg(g + i);
 }
-__global__ void resample_v_kernel(const uint8_t* __restrict__ src, int n, int in_h, int w, uint8_t* __restrict__ dst,
-                                  int out_h, const int* __restrict__ bounds, const int* __restrict__ coef, int ksize) {
-    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    const int64_t total = int64_t(n) * out_h * w;
-    if (idx >= total) return;
-    const int x = int(idx % w);
-    const int yy = int((idx / w) % out_h);
-    const int b = int(idx / (int64_t(w) * out_h));
-    const int ymin = __ldg(bounds + 2 * yy), cnt = __ldg(bounds + 2 * yy + 1);
-    const int* k = coef + int64_t(yy) * ksize;
-    const uint8_t* p = src + ((int64_t(b) * in_h + ymin) * w + x) * 3;
-    const int64_t pitch = int64_t(w) * 3;
-    int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
-    for (int i = 0; i < cnt; ++i) {
-        const int kv = __ldg(k + i);
-        s0 += int(__ldg(p + i * pitch)) * kv;
-        s1 += int(__ldg(p + i * pitch + 1)) * kv;
-        s2 += int(__ldg(p + i * pitch + 2)) * kv;
+__device__ __forceinline__ void span_store(uint8_t* __restrict__ g, const uint8_t* smem, int64_t n, int tid, int nthreads) {
+    const int off = int(reinterpret_cast<uintptr_t>(g) & 15);
+    const int head = off ? min(int64_t(16 - off), n) : 0;
+    const int64_t body = (n - head) >> 4;
+    for (int i = tid; i < head; i += nthreads) g[i] = smem[off + i];
+    uint4* g4 = reinterpret_cast<uint4*>(g + head);
+    const uint4* s4 = reinterpret_cast<const uint4*>(smem + off + head);
+    for (int64_t i = tid; i < body; i += nthreads) g4[i] = s4[i];
+    const int64_t done = head + (body << 4);
+    for (int64_t i = done + tid; i < n; i += nthreads) g[i] = smem[off + i];
+}
+
+// horizontal pass: a block owns `rows_per_block` consecutive rows of the flattened (n * in_h) row list
+__global__ void __launch_bounds__(256) resample_h_kernel(const uint8_t* __restrict__ src, int64_t total_rows, int in_w,
+                                                         uint8_t* __restrict__ dst, int out_w, const int* __restrict__ bounds,
+                                                         const int* __restrict__ coef, int ksize, int rows_per_block,
+                                                         int in_cap) {
+    extern __shared__ __align__(16) uint8_t rs_smem[];
+    const int64_t row0 = int64_t(blockIdx.x) * rows_per_block;
+    const int rows = int(min(int64_t(rows_per_block), total_rows - row0));
+    const uint8_t* gin = src + row0 * in_w * 3;
+    uint8_t* gout = dst + row0 * out_w * 3;
+    uint8_t* sin = rs_smem;
+    uint8_t* sout = rs_smem + in_cap;                       // in_cap: multiple of 16 >= rows_per_block*in_w*3 + 16
+    span_load(sin, gin, int64_t(rows) * in_w * 3, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const uint8_t* pin = sin + (reinterpret_cast<uintptr_t>(gin) & 15);
+    uint8_t* pout = sout + (reinterpret_cast<uintptr_t>(gout) & 15);
+    for (int idx = threadIdx.x; idx < rows * out_w; idx += blockDim.x) {
+        const int r = idx / out_w, xx = idx - r * out_w;
+        const int xmin = __ldg(bounds + 2 * xx), cnt = __ldg(bounds + 2 * xx + 1);
+        const int* k = coef + int64_t(xx) * ksize;
+        const uint8_t* p = pin + (r * in_w + xmin) * 3;
+        int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
+        for (int i = 0; i < cnt; ++i) {
+            const int kv = __ldg(k + i);
+            s0 += int(p[3 * i]) * kv;
+            s1 += int(p[3 * i + 1]) * kv;
+            s2 += int(p[3 * i + 2]) * kv;
+        }
+        uint8_t* o = pout + idx * 3;
+        o[0] = clip8(s0);
+        o[1] = clip8(s1);
+        o[2] = clip8(s2);
     }
-    uint8_t* o = dst + ((int64_t(b) * out_h + yy) * w + x) * 3;
-    o[0] = clip8(s0);
-    o[1] = clip8(s1);
-    o[2] = clip8(s2);
+    __syncthreads();
+    span_store(gout, sout, int64_t(rows) * out_w * 3, threadIdx.x, blockDim.x);
+}
+
+// vertical pass: a block owns `rows_per_block` output rows of ONE frame and the input rows they read ([lo, hi), at
+// most in_rows_cap of them); every byte column of a row is an independent 1-D filter, so channels need no special case
+__global__ void __launch_bounds__(256) resample_v_kernel(const uint8_t* __restrict__ src, int in_h, int w3,
+                                                         uint8_t* __restrict__ dst, int out_h, const int* __restrict__ bounds,
+                                                         const int* __restrict__ coef, int ksize, int rows_per_block,
+                                                         int blocks_per_frame, int in_cap) {
+    extern __shared__ __align__(16) uint8_t rs_smem[];
+    const int b = blockIdx.x / blocks_per_frame;
+    const int yy0 = (blockIdx.x - b * blocks_per_frame) * rows_per_block;
+    const int rows = min(rows_per_block, out_h - yy0);
+    const int lo = __ldg(bounds + 2 * yy0);
+    const int hi = __ldg(bounds + 2 * (yy0 + rows - 1)) + __ldg(bounds + 2 * (yy0 + rows - 1) + 1);
+    const uint8_t* gin = src + (int64_t(b) * in_h + lo) * w3;
+    uint8_t* gout = dst + (int64_t(b) * out_h + yy0) * w3;
+    uint8_t* sin = rs_smem;
+    uint8_t* sout = rs_smem + in_cap;
+    span_load(sin, gin, int64_t(hi - lo) * w3, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const uint8_t* pin = sin + (reinterpret_cast<uintptr_t>(gin) & 15);
+    uint8_t* pout = sout + (reinterpret_cast<uintptr_t>(gout) & 15);
+    for (int idx = threadIdx.x; idx < rows * w3; idx += blockDim.x) {
+        const int r = idx / w3, j = idx - r * w3;
+        const int yy = yy0 + r;
+        const int ymin = __ldg(bounds + 2 * yy), cnt = __ldg(bounds + 2 * yy + 1);
+        const int* k = coef + int64_t(yy) * ksize;
+        const uint8_t* p = pin + (ymin - lo) * w3 + j;
+        int acc = 1 << 21;
+        for (int i = 0; i < cnt; ++i) acc += int(p[i * w3]) * __ldg(k + i);
+        pout[idx] = clip8(acc);
+    }
+    __syncthreads();
+    span_store(gout, sout, int64_t(rows) * w3, threadIdx.x, blockDim.x);
 }
 
 inline unsigned blocks_for(int64_t total, int threads) { return unsigned((total + threads - 1) / threads); }
@@ -434,18 +488,48 @@ int launch_resample(const uint8_t* src, int n, int in_h, int in_w, uint8_t* tmp,
     // axis size is unchanged (ImagingResample: need_horizontal / need_vertical).
     const bool need_h = out_w != in_w, need_v = out_h != in_h;
     const uint8_t* cur = src;
+    constexpr int kMaxSmem = 200 * 1024;
+    static std::atomic<bool> attr_done[64];
+    int dev = 0;
+    VF_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_done[dev].load(std::memory_order_acquire)) {
+        VF_CUDA(cudaFuncSetAttribute(resample_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        VF_CUDA(cudaFuncSetAttribute(resample_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        attr_done[dev].store(true, std::memory_order_release);
+    }
+    auto round16 = [](int64_t v) { return int((v + 15) / 16 * 16); };
     if (need_h) {
         uint8_t* hdst = need_v ? tmp : dst;
-        const int64_t total = int64_t(n) * in_h * out_w;
-        resample_h_kernel<<<blocks_for(total, 256), 256, 0, s>>>(cur, n, in_h, in_w, hdst, out_w, kh_bounds, kh_coef,
-                                                                 kh_size);
+        const int64_t total_rows = int64_t(n) * in_h;
+        // rows per block: as many as fit ~48 KB of staging (in + out), at least 1, at most 16
+        int rpb = int(48 * 1024 / (int64_t(in_w + out_w) * 3));
+        rpb = rpb < 1 ? 1 : (rpb > 16 ? 16 : rpb);
+        const int in_cap = round16(int64_t(rpb) * in_w * 3 + 16), out_cap = round16(int64_t(rpb) * out_w * 3 + 16);
+        if (in_cap + out_cap > kMaxSmem) return fail(VF_ERR_UNSUPPORTED, "resize: rows of %d px do not fit shared memory", in_w);
+        const unsigned blocks = unsigned((total_rows + rpb - 1) / rpb);
+        resample_h_kernel<<<blocks, 256, in_cap + out_cap, s>>>(cur, total_rows, in_w, hdst, out_w, kh_bounds, kh_coef, kh_size,
+                                                               rpb, in_cap);
         VF_CUDA(cudaGetLastError());
         cur = hdst;
     }
     if (need_v) {
-        const int64_t total = int64_t(n) * out_h * out_w;
-        resample_v_kernel<<<blocks_for(total, 256), 256, 0, s>>>(cur, n, in_h, out_w, dst, out_h, kv_bounds, kv_coef,
-                                                                 kv_size);
+        const int w3 = out_w * 3;
+        // output rows per block: 8 unless the rows are very wide; the input span of a block is bounded by
+        // rows * scale + filter taps (+1 for the fractional start)
+        const double scale = double(in_h) / double(out_h);
+        int rpb = 8;
+        int in_rows_cap = 0, in_cap = 0, out_cap = 0;
+        for (;; rpb = rpb / 2) {
+            in_rows_cap = int(rpb * (scale > 1.0 ? scale : 1.0)) + kv_size + 2;
+            if (in_rows_cap > in_h) in_rows_cap = in_h;
+            in_cap = round16(int64_t(in_rows_cap) * w3 + 16);
+            out_cap = round16(int64_t(rpb) * w3 + 16);
+            if (in_cap + out_cap <= 96 * 1024 || rpb == 1) break;
+        }
+        if (in_cap + out_cap > kMaxSmem) return fail(VF_ERR_UNSUPPORTED, "resize: rows of %d px do not fit shared memory", out_w);
+        const int bpf = (out_h + rpb - 1) / rpb;
+        resample_v_kernel<<<unsigned(n) * bpf, 256, in_cap + out_cap, s>>>(cur, in_h, w3, dst, out_h, kv_bounds, kv_coef, kv_size,
+                                                                          rpb, bpf, in_cap);
         VF_CUDA(cudaGetLastError());
     } else if (!need_h) {
         VF_CUDA(cudaMemcpyAsync(dst, src, size_t(n) * in_h * in_w * 3, cudaMemcpyDeviceToDevice, s));

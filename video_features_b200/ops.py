@@ -52,6 +52,19 @@ def _(a, b, bias, scale, act, out_f32):
     return a.new_empty((a.shape[0], b.shape[0]), dtype=torch.float32 if out_f32 else torch.float16)
 
 
+@torch.library.custom_op("vfeat::gemm_f16_accumulate", mutates_args=("out",))
+def gemm_f16_accumulate(out: torch.Tensor, a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor], act: int) -> None:
+    """out (M,N) fp32 += act(a @ b.T + bias): the residual-stream update, added in the L2 by a TMA reduction."""
+    _need_cuda(out, a, b, bias)
+    assert out.dtype == torch.float32 and a.dtype == torch.float16 and b.dtype == torch.float16
+    M, K = a.shape
+    N = b.shape[0]
+    assert tuple(out.shape) == (M, N) and b.shape[1] == K
+    with torch.cuda.device(a.device):
+        check(lib().vf_gemm_f16_accumulate(a.data_ptr(), K, b.data_ptr(), K, M, N, K, out.data_ptr(), N, _ptr(bias), None,
+                                           act, _stream()))
+
+
 # ----------------------------------------------------------------------------- transforms
 @torch.library.custom_op("vfeat::resize_u8", mutates_args=())
 def resize_u8(frames: torch.Tensor, out_h: int, out_w: int, filter: int) -> torch.Tensor:
