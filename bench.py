@@ -683,10 +683,14 @@ def run_c5(args, rank: int, world: int, local_rank: int, quick: bool = False):
     pool_n = 64
     pool = np.random.default_rng(77).integers(0, 256, (pool_n, per, 224, 224, 3), dtype=np.uint8)
 
-    def source(path, method):                              # (frames, fps, timestamps_ms) like utils.extract_frames
-        i = int(path.rsplit("/", 1)[1])
-        clip = pool[i % pool_n]
-        return [clip[k] for k in range(per)], 25.0, [0.0] * per
+    class SynthStream:                                     # the two-step source interface of utils.FrameStream
+        def __init__(self, path, method):
+            self.clip = pool[int(path.rsplit("/", 1)[1]) % pool_n]
+            self.count, self.hw, self.fps, self.timestamps_ms = per, (224, 224), 25.0, [0.0] * per
+
+        def read_into(self, dst):                          # "decode": the clip's pixels land in the staging rows
+            np.copyto(dst, self.clip)
+            return per
 
     os.environ["VF_CLIP_SYNTHETIC"] = "0"
     ns = ap.Namespace(feature_type="CLIP-ViT-B/32", video_paths=[os.path.abspath(__file__)], flow_paths=None,
@@ -696,7 +700,7 @@ def run_c5(args, rank: int, world: int, local_rank: int, quick: bool = False):
     ex = ExtractCLIP(ns, external_call=True)
     ex.progress.close()
     ex.progress = tqdm(total=0, disable=True)
-    ex.frame_source = source
+    ex.frame_stream = SynthStream
     ex.path_list = [f"synthetic://{i}" for i in range(n_videos)]
     # warm-up: engine creation, graph capture for the chunk sizes in use, pinned buffers, thread pools
     warm = ExtractCLIP.forward(ex, torch.arange(0, min(n_videos, 3 * 86), device=dev))

@@ -13,9 +13,9 @@ for f in kernels host clip i3d i3d_kernels raft raft_kernels; do
     nvcc $FLAGS -c $SRC/$f.cu -o $OBJ/$f.o & pids+=($!)
   fi
 done
-declare -A V=( [m0g2]="-DVF_EPI_MODE=0 -DVF_EPI_GROUPS=2" [m5g2]="-DVF_EPI_MODE=5 -DVF_EPI_GROUPS=2" \
-               [m0g4]="-DVF_EPI_MODE=0 -DVF_EPI_GROUPS=4" [m5g4]="-DVF_EPI_MODE=5 -DVF_EPI_GROUPS=4" \
-               [m5g3]="-DVF_EPI_MODE=5 -DVF_EPI_GROUPS=3" [m0g3]="-DVF_EPI_MODE=0 -DVF_EPI_GROUPS=3" )
+declare -A V=( [m5g4]="-DVF_EPI_MODE=5 -DVF_EPI_GROUPS=4" [m6g2]="-DVF_EPI_MODE=6 -DVF_EPI_GROUPS=2" \
+               [m6g4]="-DVF_EPI_MODE=6 -DVF_EPI_GROUPS=4" [m6g4s6]="-DVF_EPI_MODE=6 -DVF_EPI_GROUPS=4 -DVF_STAGES_256=6" \
+               [m5g4s4]="-DVF_EPI_MODE=5 -DVF_EPI_GROUPS=4 -DVF_STAGES_256=4" [m6g3]="-DVF_EPI_MODE=6 -DVF_EPI_GROUPS=3" )
 for tag in "${!V[@]}"; do
   nvcc $FLAGS ${V[$tag]} -c $SRC/gemm.cu -o $OBJ/gemm_$tag.o & pids+=($!)
 done

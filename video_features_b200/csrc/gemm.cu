@@ -35,6 +35,7 @@
 //      [32 x 128 B] TMA store -- no barrier between warps, no agent serialisation
 //   4  per-warp transpose through the same 4 KB region, then coalesced 16-byte st.global (4 full 128-byte rows per
 //      warp instruction) -- no async proxy at all
+//   6  no staging at all: every thread stores (or red.adds) the 16-byte pieces of its own row straight from registers
 #ifndef VF_EPI_MODE
 #define VF_EPI_MODE 0
 #endif
@@ -53,6 +54,9 @@ constexpr int BK = 64;           // 64 fp16 = one 128-byte swizzle row
 #ifndef VF_EPI_GROUPS
 #define VF_EPI_GROUPS 2
 #endif
+#ifndef VF_STAGES_256
+#define VF_STAGES_256 5       // TMA ring depth of the plain 256-wide configuration
+#endif
 constexpr uint32_t SLICE_BYTES = 128 * 128;   // 128 rows x 128 B (32 fp32 or 64 fp16 columns)
 
 // NSPLIT = 2: the B stage holds the hi and the lo half-tile of a split-fp16 weight matrix and every K step issues two
@@ -68,7 +72,7 @@ struct GemmCfg {
     static constexpr int EPI_WARPS = 4 * NGRP;
     static constexpr int THREADS = (4 + EPI_WARPS) * 32;
     static constexpr uint32_t EPI_BUFS = (NSPLIT == 2 || NGRP > 2) ? 1 : 2;
-    static constexpr uint32_t STG_BYTES = NGRP * EPI_BUFS * SLICE_BYTES;   // NGRP epilogue groups x EPI_BUFS slice buffers
+    static constexpr uint32_t STG_BYTES = EPI_MODE == 6 ? 0 : NGRP * EPI_BUFS * SLICE_BYTES;   // NGRP groups x EPI_BUFS slice buffers
     static constexpr uint32_t BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;   // + align slack
     static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns");
@@ -253,6 +257,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const int tt = r2 % cg.Tp;
                 keep = (m >= 0) && (w >= cg.w0) && (w < cg.w1) && (hh >= cg.h0) && (hh < cg.h1) && (tt >= cg.t0) && (tt < cg.t1);
             }
+            const bool grow_ok = m0 + row < M;       // (mode 6) this thread's output row exists
 #pragma unroll 1
             for (int c = grp * slice_cols; c < BN; c += Cfg::NGRP * slice_cols)
 #pragma unroll
@@ -287,10 +292,26 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = 0.f;
                     }
+                    if (EPI_MODE == 6) {
+                        // straight from registers: this thread's 128 bytes of its own output row
+#ifndef VF_DBG_NO_STORE
+                        if (grow_ok) {
+                            float* o = reinterpret_cast<float*>(ep.out) + size_t(m0 + row) * ep.ldo + n;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (n + 4 * j < N) {
+                                    const float4 val = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                                    if (ep.accumulate) red_add_f32x4(o + 4 * j, val);
+                                    else *reinterpret_cast<float4*>(o + 4 * j) = val;
+                                }
+                        }
+#endif
+                    } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         *reinterpret_cast<float4*>(myrow + ((uint32_t(j) ^ sw) << 4)) =
                             make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
                 } else {
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
@@ -309,11 +330,26 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] -= __half2float(__float2half_rn(v[j]));
                         }
+                        if (EPI_MODE == 6) {
+#ifndef VF_DBG_NO_STORE
+                            if (grow_ok) {
+                                __half* o = reinterpret_cast<__half*>(ep.out) + size_t(m0 + row) * ep.ldo + n + hh * 32 +
+                                            ((SPLIT && sp) ? ep.split_off : 0);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (n + hh * 32 + 8 * j < N)
+                                        *reinterpret_cast<uint4*>(o + 8 * j) =
+                                            make_uint4(pack_half2(v[8 * j], v[8 * j + 1]), pack_half2(v[8 * j + 2], v[8 * j + 3]),
+                                                       pack_half2(v[8 * j + 4], v[8 * j + 5]), pack_half2(v[8 * j + 6], v[8 * j + 7]));
+                            }
+#endif
+                        } else {
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             *reinterpret_cast<uint4*>(myrow + ((uint32_t(hh * 4 + j) ^ sw) << 4)) =
                                 make_uint4(pack_half2(v[8 * j], v[8 * j + 1]), pack_half2(v[8 * j + 2], v[8 * j + 3]),
                                            pack_half2(v[8 * j + 4], v[8 * j + 5]), pack_half2(v[8 * j + 6], v[8 * j + 7]));
+                        }
                     }
                 }
                 if (EPI_MODE == 0) {
@@ -345,7 +381,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #endif
                         bulk_commit();
                     }
-                } else {
+                } else if (EPI_MODE == 4) {
                     // EPI_MODE 4: the warp reads its own 32 x 128 B back row-wise and writes 4 complete 128-byte rows per
                     // instruction (lanes 8i..8i+7 cover row i of the group of 4)
                     __syncwarp();
@@ -493,7 +529,7 @@ static int run_gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const
         if (bn == 128) return launch_gemm_pair<128, 6, 2>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
         return launch_gemm_pair<64, 8, 2>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
     }
-    if (bn == 256) return launch_gemm_pair<256, 5, 1>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+    if (bn == 256) return launch_gemm_pair<256, VF_STAGES_256, 1>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
     if (bn == 192) return launch_gemm_pair<192, 5, 1>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
     if (bn == 128) return launch_gemm_pair<128, 6, 1>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
     return launch_gemm_pair<64, 8, 1>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);

@@ -32,7 +32,8 @@ from tqdm import tqdm
 
 from .. import synthetic_weights
 from ..clip_engine import ClipEngine
-from ..utils import AsyncSink, action_on_extraction, already_extracted, extract_frames, form_list_from_user_input
+from ..utils import (AsyncSink, FrameStream, action_on_extraction, already_extracted, extract_frames,
+                     form_list_from_user_input)
 
 _CKPT_NAMES = {'CLIP-ViT-B/32': 'ViT-B-32.pt', 'CLIP4CLIP-ViT-B-32': 'CLIP4CLIP-ViT-B-32.pth'}
 
@@ -70,12 +71,35 @@ def load_clip_state_dict(feature_type: str) -> Dict[str, torch.Tensor]:
 
 
 class _Batch:
-    """Frames of consecutive videos of one geometry, waiting for one engine call."""
+    """Videos of one geometry sharing one pinned staging buffer and one engine call."""
 
-    def __init__(self, hw):
+    def __init__(self, hw, slot):
         self.hw = hw
-        self.items: List[tuple] = []       # (list position, video, frames (list of HxWx3 arrays), fps, stamps)
-        self.frames = 0
+        self.slot = slot
+        self.items: List[list] = []       # [list position, video, stream, first row, future -> frames written]
+        self.rows = 0
+
+
+class _ListStream:
+    """A fully decoded video (what a one-step `frame_source` returns) behind the two-step stream interface."""
+
+    def __init__(self, frames, fps, stamps):
+        frames = [f for f in frames if f is not None]
+        if not frames:
+            raise RuntimeError("no frames decoded")
+        self._frames = frames
+        self.count = len(frames)
+        hw = tuple(frames[0].shape[:2])
+        self.hw = hw if all(tuple(f.shape[:2]) == hw for f in frames) else None
+        self.fps, self.timestamps_ms = fps, stamps
+
+    def read_into(self, dst) -> int:
+        for i, f in enumerate(self._frames):
+            np.copyto(dst[i], f)
+        return self.count
+
+    def frames(self):
+        return self._frames
 
 
 class ExtractCLIP(torch.nn.Module):
@@ -95,6 +119,10 @@ class ExtractCLIP(torch.nn.Module):
         self._engines: Dict[int, ClipEngine] = {}
         # engine-side knobs (not in the reference): where frames come from, and how many go into one engine call
         self.frame_source = extract_frames                  # (path, method) -> (frames, fps, timestamps_ms)
+        # two-step source used by the list path: stream = frame_stream(path, method) knows .count / .hw / .fps /
+        # .timestamps_ms, and stream.read_into(dst) decodes straight into the pinned staging rows (no extra copy).
+        # None: wrap `frame_source` (tests and callers that replaced it).
+        self.frame_stream = FrameStream
         self.batch_frames = int(os.environ.get("VF_CLIP_BATCH_FRAMES", "1024"))
         self.decode_workers = int(os.environ.get("VF_DECODE_WORKERS", str(min(8, os.cpu_count() or 1))))
         self.keep_features = False        # dispatch sets it when the features are all-gathered as well as saved
@@ -171,122 +199,169 @@ class ExtractCLIP(torch.nn.Module):
             raise RuntimeError(f"no frames decoded from {video}")
         return frames, fps, stamps
 
+    def _open(self, video):
+        if self.frame_stream is not None and self.frame_source is extract_frames:
+            st = self.frame_stream(str(video), self.extract_method)
+            if st.count <= 0:
+                raise RuntimeError(f"no frames decoded from {video}")
+            return st
+        return _ListStream(*self.frame_source(str(video), self.extract_method))
+
+    def _open_block(self, videos):
+        """Open a block of videos on one pool thread: [stream or the exception]."""
+        out = []
+        for v in videos:
+            try:
+                out.append(self._open(v))
+            except KeyboardInterrupt:
+                raise
+            except Exception as err:
+                out.append(err)
+        return out
+
     def _forward_batched(self, device, model: ClipEngine, todo, collected, sink):
-        """Decode pool -> pinned double buffer -> one engine call per <= batch_frames frames -> per-video delivery."""
+        """Stages, each on its own thread(s), so the GPU never waits for Python:
+             pool: open videos (blocks of 8)  ->  this thread: rows of a pinned staging slot are assigned in list order
+             ->  pool: every stream decodes INTO its rows  ->  engine thread: ONE engine call per <= batch_frames rows
+             ->  delivery thread: per-video slices, sink."""
         workers = max(1, self.decode_workers)
         pool = ThreadPoolExecutor(workers, thread_name_prefix="vf-decode")
         gpu = ThreadPoolExecutor(1, thread_name_prefix="vf-engine")           # engine calls are serialised: one handle
-        pinned: List[Optional[torch.Tensor]] = [None, None]
-        busy = [None, None]                                                   # engine future still reading slot k
-        slot = 0
+        out = ThreadPoolExecutor(1, thread_name_prefix="vf-deliver")
+        n_slots = 3
+        pinned: List[Optional[torch.Tensor]] = [None] * n_slots
+        busy = [None] * n_slots                                               # engine future still reading slot k
+        delivered = []
+        state = {"slot": 0}
         lock = threading.Lock()
 
-        def run_batch(batch: _Batch, buf: torch.Tensor):
-            h, w = batch.hw
-            view = buf[:batch.frames * h * w * 3].view(batch.frames, h, w, 3)
+        def deliver_one(pos, video, feats, fps, stamps):
             try:
-                feats = model.encode_frames_u8_host(view).numpy()
-                off = 0
-                for pos, video, frames, fps, stamps in batch.items:
-                    one = {self.feature_type: feats[off:off + len(frames)].copy(), 'fps': np.array(fps),
-                           'timestamps_ms': np.array(stamps)}
-                    off += len(frames)
-                    try:
-                        with lock:
-                            self._deliver(one, pos, video, collected, sink)
-                    except Exception as err:
-                        self._report(err, video)
-                    self.progress.update()
-            except Exception:
-                # the batched call failed: find the culprit by running its videos one at a time
-                for pos, video, frames, fps, stamps in batch.items:
-                    try:
-                        f = model.encode_frames_u8_host(torch.from_numpy(np.stack(frames))).numpy()
-                        with lock:
-                            self._deliver({self.feature_type: f, 'fps': np.array(fps), 'timestamps_ms': np.array(stamps)},
-                                          pos, video, collected, sink)
-                    except Exception as err:
-                        self._report(err, video)
-                    self.progress.update()
-
-        def flush(batch: _Batch):
-            nonlocal slot
-            if not batch.items:
-                return
-            k, slot = slot, slot ^ 1
-            if busy[k] is not None:
-                busy[k].result()                                              # the engine has finished with this buffer
-            h, w = batch.hw
-            need = batch.frames * h * w * 3
-            if pinned[k] is None or pinned[k].numel() < need:
-                pinned[k] = torch.empty(max(need, self.batch_frames * h * w * 3), dtype=torch.uint8)
-                if torch.cuda.is_available():                                 # (host-logic tests run without a device)
-                    pinned[k] = pinned[k].pin_memory()
-            dst = pinned[k].numpy()[:need].reshape(batch.frames, h, w, 3)
-            copies, off = [], 0
-            for _, _, frames, _, _ in batch.items:                            # the pool fills the staging buffer
-                copies.append(pool.submit(_copy_frames, dst[off:off + len(frames)], frames))
-                off += len(frames)
-            for c in copies:
-                c.result()
-            busy[k] = gpu.submit(run_batch, batch, pinned[k])
-
-        try:
-            window = 4 * workers                                              # decodes in flight, bounds host memory
-            futs = {}
-            nxt = 0
-            batch: Optional[_Batch] = None
-            for i, (pos, video) in enumerate(todo):
-                while nxt < len(todo) and nxt < i + window:
-                    futs[nxt] = pool.submit(self._decode, todo[nxt][1])
-                    nxt += 1
-                try:
-                    frames, fps, stamps = futs.pop(i).result()
-                except KeyboardInterrupt:
-                    raise
-                except Exception as err:
-                    self._report(err, video)
-                    self.progress.update()
-                    continue
-                hw = tuple(frames[0].shape[:2])
-                if any(tuple(f.shape[:2]) != hw for f in frames):
-                    hw = None                                                 # mixed geometry inside one video: own call
-                if batch is not None and (hw is None or batch.hw != hw or batch.frames + len(frames) > self.batch_frames):
-                    flush(batch)
-                    batch = None
-                if hw is None:
-                    lone = _Batch(None)
-                    lone.items.append((pos, video, frames, fps, stamps))
-                    if busy[0] is not None: busy[0].result()
-                    if busy[1] is not None: busy[1].result()
-                    gpu.submit(self._run_mixed, model, lone, collected, sink, lock).result()
-                    continue
-                if batch is None:
-                    batch = _Batch(hw)
-                batch.items.append((pos, video, frames, fps, stamps))
-                batch.frames += len(frames)
-            if batch is not None:
-                flush(batch)
-            for b in busy:
-                if b is not None:
-                    b.result()
-        finally:
-            gpu.shutdown(wait=True)
-            pool.shutdown(wait=True)
-
-    def _run_mixed(self, model, batch, collected, sink, lock):
-        """A video whose frames differ in size (never seen from a real decoder): per-frame calls, like the reference's
-        per-frame preprocess."""
-        for pos, video, frames, fps, stamps in batch.items:
-            try:
-                f = np.concatenate([model.encode_frames_u8_host(torch.from_numpy(np.ascontiguousarray(x))[None]).numpy()
-                                    for x in frames])
                 with lock:
-                    self._deliver({self.feature_type: f, 'fps': np.array(fps), 'timestamps_ms': np.array(stamps)},
+                    self._deliver({self.feature_type: feats, 'fps': np.array(fps), 'timestamps_ms': np.array(stamps)},
                                   pos, video, collected, sink)
             except Exception as err:
                 self._report(err, video)
             self.progress.update()
+
+        def deliver(batch: _Batch, feats, counts):
+            for (pos, video, st, row0, _), k in zip(batch.items, counts):
+                if isinstance(k, Exception):
+                    self._report(k, video)
+                    self.progress.update()
+                elif k <= 0:
+                    self._report(RuntimeError(f"no frames decoded from {video}"), video)
+                    self.progress.update()
+                else:
+                    deliver_one(pos, video, feats[row0:row0 + k].copy(), st.fps, st.timestamps_ms)
+
+        def run_batch(batch: _Batch):
+            counts = []
+            for it in batch.items:                                            # the decodes into this slot are complete
+                try:
+                    counts.append(it[4].result())
+                except Exception as err:
+                    counts.append(err)
+            h, w = batch.hw
+            view = pinned[batch.slot][:batch.rows * h * w * 3].view(batch.rows, h, w, 3)
+            try:
+                feats = model.encode_frames_u8_host(view).numpy()
+            except Exception:
+                # the batched call failed: find the culprit by running its videos one at a time
+                for (pos, video, st, row0, _), k in zip(batch.items, counts):
+                    try:
+                        if isinstance(k, Exception):
+                            raise k
+                        f = model.encode_frames_u8_host(view[row0:row0 + k]).numpy()
+                        deliver_one(pos, video, f, st.fps, st.timestamps_ms)
+                    except Exception as err:
+                        self._report(err, video)
+                        self.progress.update()
+                return
+            delivered.append(out.submit(deliver, batch, feats, counts))       # slicing + sink run beside the next call
+
+        def new_batch(hw):
+            k = state["slot"]
+            state["slot"] = (k + 1) % n_slots
+            if busy[k] is not None:
+                busy[k].result()                                              # the engine has finished with this buffer
+            need = self.batch_frames * hw[0] * hw[1] * 3
+            if pinned[k] is None or pinned[k].numel() < need:
+                pinned[k] = torch.empty(need, dtype=torch.uint8)
+                if torch.cuda.is_available():                                 # (host-logic tests run without a device)
+                    pinned[k] = pinned[k].pin_memory()
+            return _Batch(hw, k)
+
+        def seal(batch: _Batch):
+            if batch.items:
+                busy[batch.slot] = gpu.submit(run_batch, batch)
+
+        try:
+            block = 8                                                         # videos per open task
+            blocks = [todo[i:i + block] for i in range(0, len(todo), block)]
+            window = 4 * workers                                              # open blocks in flight, bounds host memory
+            futs = {}
+            nxt = 0
+            batch: Optional[_Batch] = None
+            for bi, blk in enumerate(blocks):
+                while nxt < len(blocks) and nxt < bi + window:
+                    futs[nxt] = pool.submit(self._open_block, [v for _, v in blocks[nxt]])
+                    nxt += 1
+                for (pos, video), st in zip(blk, futs.pop(bi).result()):
+                    if isinstance(st, Exception):
+                        self._report(st, video)
+                        self.progress.update()
+                        continue
+                    if st.hw is None or st.count > self.batch_frames:         # mixed geometry / longer than a batch: own call
+                        if batch is not None:
+                            seal(batch)
+                            batch = None
+                        for bsy in busy:
+                            if bsy is not None:
+                                bsy.result()
+                        gpu.submit(self._run_lone, model, pos, video, st, collected, sink, lock).result()
+                        continue
+                    if batch is not None and (batch.hw != st.hw or batch.rows + st.count > self.batch_frames):
+                        seal(batch)
+                        batch = None
+                    if batch is None:
+                        batch = new_batch(st.hw)
+                    h, w = st.hw
+                    dst = pinned[batch.slot].numpy()[batch.rows * h * w * 3:(batch.rows + st.count) * h * w * 3]
+                    fut = pool.submit(st.read_into, dst.reshape(st.count, h, w, 3))
+                    batch.items.append([pos, video, st, batch.rows, fut])
+                    batch.rows += st.count
+            if batch is not None:
+                seal(batch)
+            for bsy in busy:
+                if bsy is not None:
+                    bsy.result()
+            for d in delivered:
+                d.result()
+        finally:
+            gpu.shutdown(wait=True)
+            out.shutdown(wait=True)
+            pool.shutdown(wait=True)
+
+    def _run_lone(self, model, pos, video, st, collected, sink, lock):
+        """A video that cannot share a staging buffer (frames of different sizes -- never seen from a real decoder -- or
+        more frames than a batch holds): its own engine call(s), like the reference's per-video loop."""
+        try:
+            if st.hw is None:
+                f = np.concatenate([model.encode_frames_u8_host(torch.from_numpy(np.ascontiguousarray(x))[None]).numpy()
+                                    for x in st.frames()])
+            else:
+                buf = np.empty((st.count, st.hw[0], st.hw[1], 3), np.uint8)
+                k = st.read_into(buf)
+                if k <= 0:
+                    raise RuntimeError(f"no frames decoded from {video}")
+                f = model.encode_frames_u8_host(torch.from_numpy(buf[:k])).numpy()
+            with lock:
+                self._deliver({self.feature_type: f, 'fps': np.array(st.fps), 'timestamps_ms': np.array(st.timestamps_ms)},
+                              pos, video, collected, sink)
+        except Exception as err:
+            self._report(err, video)
+        self.progress.update()
 
     # ------------------------------------------------------------------ extract (one video)
     def extract(self, device: torch.device, model: ClipEngine, preprocess_func=None, video_path=None):
@@ -296,8 +371,3 @@ class ExtractCLIP(torch.nn.Module):
         batch = torch.from_numpy(np.stack(decoded))         # (T,H,W,3) uint8, decoder channel order untouched
         feats = model.encode_frames_u8_host(batch)          # H2D + transform + tower + D2H
         return {self.feature_type: feats.numpy(), 'fps': np.array(fps), 'timestamps_ms': np.array(stamps)}
-
-
-def _copy_frames(dst: np.ndarray, frames) -> None:
-    for i, f in enumerate(frames):
-        np.copyto(dst[i], f)

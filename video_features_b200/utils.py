@@ -54,6 +54,22 @@ class VideoReader:
             self._pos += 1
         return img if ok else None
 
+    def get_frame_into(self, frame_id: int, out: np.ndarray) -> bool:
+        """`get_frame(frame_id)` decoded straight into `out` ((H,W,3) uint8, C-contiguous -- e.g. a row of a pinned staging
+        buffer): the decoder's colour conversion writes there, no intermediate array.  False when the read fails."""
+        if frame_id < 0 or frame_id >= self.frame_cnt:
+            raise IndexError(f'"frame_id" must be between 0 and {self.frame_cnt - 1}')
+        if frame_id != self._pos:
+            self._cap.set(self._cv2.CAP_PROP_POS_FRAMES, frame_id)
+            pos = int(self._cap.get(self._cv2.CAP_PROP_POS_FRAMES))
+            for _ in range(max(frame_id - pos, 0)):
+                self._cap.read()
+        ok, img = self._cap.read(out)
+        self._pos = frame_id + 1 if ok else int(self._cap.get(self._cv2.CAP_PROP_POS_FRAMES))
+        if ok and img is not out and not np.shares_memory(img, out):
+            np.copyto(out, img)                       # OpenCV allocated its own array (shape / layout mismatch)
+        return bool(ok)
+
 
 def extract_frames(path: str, method: str):
     """utils/utils.py:297-333.  method: ``uni_N`` (N frames uniformly) or ``fix_N`` (N frames per second).
@@ -65,6 +81,32 @@ def extract_frames(path: str, method: str):
     indices = ops.sample_indices(kind, int(params[0]), reader.frame_cnt, reader.fps)
     per_frame = 0.001 / reader.fps                       # (sic) the reference's unit, utils/utils.py:312
     return [reader.get_frame(int(i)) for i in indices], reader.fps, [i * per_frame for i in indices]
+
+
+class FrameStream:
+    """`extract_frames` in two steps, for callers that own the destination memory: construction opens the video and fixes
+    the sampled indices (so `count`, `hw`, `fps`, `timestamps_ms` are known), `read_into(dst)` then decodes the frames
+    into `dst[(0..count)]`.  Frames whose read fails are dropped and later ones move up, as the reference drops its
+    `None` frames (models/CLIP/extract_clip.py:122); the number of frames written is returned."""
+
+    def __init__(self, path: str, method: str):
+        kind, *params = method.split('_')
+        if kind not in ('fix', 'uni'):
+            raise NotImplementedError(f'{kind} are not supported')
+        self._reader = VideoReader(str(path))
+        self._indices = [int(i) for i in ops.sample_indices(kind, int(params[0]), self._reader.frame_cnt, self._reader.fps)]
+        self.count = len(self._indices)
+        self.hw = (self._reader.height, self._reader.width)
+        self.fps = self._reader.fps
+        per_frame = 0.001 / self._reader.fps              # (sic) utils/utils.py:312
+        self.timestamps_ms = [i * per_frame for i in self._indices]
+
+    def read_into(self, dst: np.ndarray) -> int:
+        k = 0
+        for i in self._indices:
+            if self._reader.get_frame_into(i, dst[k]):
+                k += 1
+        return k
 
 
 _SINK_EXT = {'save_numpy': 'npy', 'save_pickle': 'pkl'}
