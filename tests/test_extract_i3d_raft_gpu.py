@@ -79,7 +79,7 @@ def test_extract_i3d_two_streams_vs_oracle(cuda_device, tmp_path, clip, shift):
     # (scripts/precision/flow_quantiser_sensitivity.py -> profiles/r2_flow_sensitivity.json).  No implementation whose
     # flow differs from the oracle's at all can therefore be held to 1e-3 on the composite.  The bar is derived, not
     # guessed: (1) the engine's flow must meet the 1e-3 RAFT bar on this very clip, (2) quantiser + I3D on identical flow
-    # is asserted elsewhere (test_i3d_gpu.py, 2e-4), and (3) the composite may not exceed 3x the oracle's own
+    # is asserted elsewhere (test_i3d_gpu.py, 2e-4), and (3) the composite may not exceed 2x the oracle's own
     # sensitivity to Gaussian flow noise of the SAME rms as the engine's measured flow error.
     eng = RAFTEngine(sd_raft_cpu, 0, max_frames=13, max_h=256, max_w=341)
     eflow = eng.flow(rs.permute(0, 2, 3, 1).contiguous().to(torch.uint8), iters=20, unpad=False)
@@ -92,7 +92,7 @@ def test_extract_i3d_two_streams_vs_oracle(cuda_device, tmp_path, clip, shift):
     # frames is a badly conditioned iteration and single pixels move by a few 1e-3 px (measured 3.2e-3 of max |flow|).
     assert flow_rel <= 1e-3 and flow_max <= 5e-3, (flow_rel, flow_max)
     sens = feature_sensitivity(sd_flow, flow, [flow_rms], draws=5)[flow_rms]["feature_rel"]
-    bar = max(1e-3, 3.0 * sens)
+    bar = max(1e-3, 2.0 * sens)
     print(f"[{clip}] ExtractI3D flow (RAFT -> quantiser -> I3D) vs oracle: {rel:.3e}; engine flow error {flow_rel:.2e} rel (max {flow_max:.2e}) / "
           f"{flow_rms:.2e} px rms; oracle's own sensitivity at that rms: {sens:.3e}; bar {bar:.3e}")
     assert rel <= bar, (rel, bar)

@@ -37,7 +37,7 @@
 //      warp instruction) -- no async proxy at all
 //   6  no staging at all: every thread stores (or red.adds) the 16-byte pieces of its own row straight from registers
 #ifndef VF_EPI_MODE
-#define VF_EPI_MODE 0
+#define VF_EPI_MODE 5
 #endif
 // measurement aids: VF_DBG_NO_EPI = accumulators are released unread (main loop only); VF_DBG_NO_STORE = the whole
 // epilogue except the global store instructions
@@ -45,6 +45,15 @@ namespace vf {
 
 namespace {
 
+#ifdef VF_DBG_TRACE
+// per-tile SM-clock timestamps of the leader CTA of every pair (scripts/gemm_trace.py): [pair][tile iteration][slot]
+//   0 MMA: accumulator stage granted      1 MMA: last MMA of the tile issued      2 epilogue warp 4: accumulator ready
+//   3 epilogue warp 4: its slices done    4 producer: first load of the tile issued   5 producer: last load issued
+__device__ long long g_trace[74][64][8];
+#define VF_TRACE(slot, iter) do { if ((iter) < 63) g_trace[pair][iter][slot] = clock64(); } while (0)
+#else
+#define VF_TRACE(slot, iter) do { } while (0)
+#endif
 constexpr int EPI_MODE = VF_EPI_MODE;
 constexpr int BM = 128;          // rows per CTA (256 per pair)
 constexpr int STORE_ROWS = EPI_MODE == 5 ? 32 : BM;     // rows of one TMA store box
@@ -52,7 +61,7 @@ constexpr int BK = 64;           // 64 fp16 = one 128-byte swizzle row
 // epilogue warp groups (4 warps = the 4 TMEM lane quarters each) of the plain 256-wide configuration -- the ViT GEMMs, whose
 // K = 768 shapes are bounded by the epilogue's latency chain (TMEM load -> math -> shared -> store), not by its bandwidth
 #ifndef VF_EPI_GROUPS
-#define VF_EPI_GROUPS 2
+#define VF_EPI_GROUPS 4
 #endif
 #ifndef VF_STAGES_256
 #define VF_STAGES_256 5       // TMA ring depth of the plain 256-wide configuration
@@ -148,6 +157,13 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int kpt = (cg.k_per_tap + BK - 1) / BK;    // K blocks per filter tap (a plain GEMM is one "tap")
     const int num_k = cg.ntaps * kpt;
 
+#ifdef VF_DBG_TRACE
+    if (cta == 0 && threadIdx.x == 0) {
+        g_trace[pair][63][6] = clock64();
+        long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        g_trace[pair][63][4] = gt;
+    }
+#endif
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -176,15 +192,18 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+            for (int tile = pair, titer = 0; tile < num_tiles; tile += num_pairs, ++titer) {
                 const int m_blk = tile % num_m, n_blk = tile / num_m;
                 const int m0 = m_blk * 2 * BM + int(cta) * BM;
                 const int n0 = n_blk * BN + int(cta) * (BN / 2);
+                bool first_load = true;
+                (void)first_load; (void)titer;
                 for (int tap = 0; tap < cg.ntaps; ++tap) {
                     const int arow = m0 + cg.tap_off[tap];       // may be negative / past the end: TMA zero-fills
                     const int bcol = tap * cg.k_per_tap;
                     for (int kk = 0; kk < kpt; ++kk) {
                         mbar_wait(&empty[stage], phase ^ 1);
+                        if (cta == 0 && first_load) { VF_TRACE(4, titer); first_load = false; }
                         const bool lo_blk = NSPLIT == 2 && ((cg.lo_mask >> kk) & 1ull);    // W_lo not needed
                         if (cta == 0)
                             mbar_expect_tx(&full[stage], 2 * (Cfg::A_BYTES + (lo_blk ? Cfg::B_HALF : Cfg::B_BYTES)));
@@ -197,6 +216,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
+                if (cta == 0) VF_TRACE(5, titer);
             }
         }
     } else if (warp == 1) {
@@ -205,8 +225,10 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN, 0);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
-            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+            for (int tile = pair, titer = 0; tile < num_tiles; tile += num_pairs, ++titer) {
+                (void)titer;
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
+                VF_TRACE(0, titer);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0, kk = 0; kb < num_k; ++kb) {
@@ -226,6 +248,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     if (++kk == kpt) kk = 0;              // K block index inside the current tap
                 }
                 umma_commit_2sm(&tfull[acc], 3);           // accumulators of both CTAs complete
+                VF_TRACE(1, titer);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -242,10 +265,12 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const uint32_t sw = uint32_t(row & 7);
         int acc = 0, it = 0;
         uint32_t acc_phase = 0;
-        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        for (int tile = pair, titer = 0; tile < num_tiles; tile += num_pairs, ++titer) {
+            (void)titer;
             const int m_blk = tile % num_m, n_blk = tile / num_m;
             const int m0 = m_blk * 2 * BM + int(cta) * BM;
             mbar_wait(&tfull[acc], acc_phase);
+            if (cta == 0 && warp == 4 && lane == 0) VF_TRACE(2, titer);
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * BN + (uint32_t(q * 32) << 16);
 #ifndef VF_DBG_NO_EPI
@@ -412,6 +437,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #endif  // VF_DBG_NO_EPI
             tc_fence_before();
             __syncwarp();
+            if (cta == 0 && warp == 4 && lane == 0) VF_TRACE(3, titer);
             if (lane == 0) mbar_arrive_remote(&tempty[acc], 0);   // this accumulator stage is drained
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
@@ -425,6 +451,13 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         tc_fence_after();
         tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
     }
+#ifdef VF_DBG_TRACE
+    if (cta == 0 && threadIdx.x == 0) {
+        g_trace[pair][63][7] = clock64();
+        long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        g_trace[pair][63][5] = gt;
+    }
+#endif
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -584,6 +617,16 @@ static int run_gemm(const CUtensorMap& tmA, const __half* B, int ldb, int64_t Kt
     return st;
 }
 
+#ifdef VF_DBG_TRACE
+extern "C" int vf_dbg_gemm_trace(long long* host_out) {     // 74 x 64 x 8 timestamps, after a device synchronise
+    cudaDeviceSynchronize();
+    return int(cudaMemcpyFromSymbol(host_out, g_trace, sizeof(g_trace)));
+}
+extern "C" int vf_dbg_gemm_trace_clear() {
+    static long long zeros[74 * 64 * 8];
+    return int(cudaMemcpyToSymbol(g_trace, zeros, sizeof(zeros)));
+}
+#endif
 bool gemm_profile_on() { return g_prof.on; }
 int gemm_profile(int enable) {
     g_prof.on = enable != 0;

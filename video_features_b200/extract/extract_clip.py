@@ -230,6 +230,7 @@ class ExtractCLIP(torch.nn.Module):
         out = ThreadPoolExecutor(1, thread_name_prefix="vf-deliver")
         n_slots = 3
         pinned: List[Optional[torch.Tensor]] = [None] * n_slots
+        pinned_np: List[Optional[np.ndarray]] = [None] * n_slots
         busy = [None] * n_slots                                               # engine future still reading slot k
         delivered = []
         state = {"slot": 0}
@@ -258,10 +259,8 @@ class ExtractCLIP(torch.nn.Module):
         def run_batch(batch: _Batch):
             counts = []
             for it in batch.items:                                            # the decodes into this slot are complete
-                try:
-                    counts.append(it[4].result())
-                except Exception as err:
-                    counts.append(err)
+                fut, i = it[4]
+                counts.append(fut.result()[i])
             h, w = batch.hw
             view = pinned[batch.slot][:batch.rows * h * w * 3].view(batch.rows, h, w, 3)
             try:
@@ -290,9 +289,30 @@ class ExtractCLIP(torch.nn.Module):
                 pinned[k] = torch.empty(need, dtype=torch.uint8)
                 if torch.cuda.is_available():                                 # (host-logic tests run without a device)
                     pinned[k] = pinned[k].pin_memory()
+                pinned_np[k] = pinned[k].numpy()
             return _Batch(hw, k)
 
+        pending: List[tuple] = []                                             # (batch item, its staging rows) not yet submitted
+
+        def read_many(jobs):
+            out_counts = []
+            for item, dst in jobs:
+                try:
+                    out_counts.append(item[2].read_into(dst))
+                except Exception as err:
+                    out_counts.append(err)
+            return out_counts
+
+        def submit_reads():
+            if pending:
+                jobs = list(pending)
+                pending.clear()
+                fut = pool.submit(read_many, jobs)
+                for i, (item, _) in enumerate(jobs):
+                    item[4] = (fut, i)
+
         def seal(batch: _Batch):
+            submit_reads()
             if batch.items:
                 busy[batch.slot] = gpu.submit(run_batch, batch)
 
@@ -327,10 +347,14 @@ class ExtractCLIP(torch.nn.Module):
                     if batch is None:
                         batch = new_batch(st.hw)
                     h, w = st.hw
-                    dst = pinned[batch.slot].numpy()[batch.rows * h * w * 3:(batch.rows + st.count) * h * w * 3]
-                    fut = pool.submit(st.read_into, dst.reshape(st.count, h, w, 3))
-                    batch.items.append([pos, video, st, batch.rows, fut])
+                    dst = pinned_np[batch.slot][batch.rows * h * w * 3:(batch.rows + st.count) * h * w * 3]
+                    item = [pos, video, st, batch.rows, None]
+                    batch.items.append(item)
                     batch.rows += st.count
+                    pending.append((item, dst.reshape(st.count, h, w, 3)))
+                    if len(pending) >= block:
+                        submit_reads()
+                submit_reads()                                                # one pool task per block of videos
             if batch is not None:
                 seal(batch)
             for bsy in busy:
