@@ -72,7 +72,7 @@ struct vf_clip {
     cudaStream_t cs = nullptr;                // stream of the active lane
     cudaEvent_t ev_in = nullptr;
     bool use_graph = true;
-    bool acc_resid = true;                    // residual adds in the GEMM epilogue (TMA reduction) instead of an fp16 y
+    bool acc_o = true, acc_m = true;          // residual adds in the GEMM epilogue (TMA reduction) instead of an fp16 y
     float* feat = nullptr;                    // [chunk, 512] tower output of the active lane
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
@@ -182,46 +182,37 @@ static int clip_tower_eager(vf_clip* h, int c, float* out, cudaStream_t s) {
     // token assembly (+ class / positional embedding) fused with ln_pre -> x
     VF_TRY(tower_embed_ln(h, c, s));
     h->launches += 2;
-    // The residual stream x stays fp32 in HBM.  acc_resid (default): out-proj and fc2 ADD their result into x from the
-    // GEMM epilogue (TMA reduction in the L2), so a LayerNorm pass only reads x and writes h: 6 bytes per element instead
-    // of the 12 of "x += y; h = LN(x)" with a separate fp16 increment y (VF_CLIP_RESID=y keeps that form for A/B runs).
-    const bool acc = h->acc_resid;
+    // The residual stream x stays fp32 in HBM.  A GEMM that ends a residual branch either ADDS its result into x from the
+    // epilogue (TMA reduction in the L2; the LayerNorm pass that follows then only reads x and writes h: 6 bytes per
+    // element), or writes an fp16 increment y that the LayerNorm kernel adds ("x += y; h = LN(x)": 12 bytes per element).
+    // acc_o / acc_m select the form for the attention out-projection / the MLP's second GEMM (VF_CLIP_RESID=acc|y|mix).
+    const bool acc_o = h->acc_o, acc_m = h->acc_m;
     for (int l = 0; l < L; ++l) {
         const ClipLayerDev& w = h->layer[l];
         // h = ln_1(x)   (y form: x += y of the previous block's MLP first)
-        VF_TRY(tower_add_ln(h, h->x, W, (acc || l == 0) ? nullptr : h->y, W, 1, w.ln1_w, w.ln1_b, h->h, W, M, s));
+        VF_TRY(tower_add_ln(h, h->x, W, (acc_m || l == 0) ? nullptr : h->y, W, 1, w.ln1_w, w.ln1_b, h->h, W, M, s));
         VF_TRY(tower_gemm(h, h->h, W, w.w_qkv, W, M, 3 * W, W, epi(h->qkv, 3 * W, 0, w.b_qkv, VF_ACT_NONE), s));
         VF_TRY(tower_attention(h, c, s));
-        if (l + 1 < L) {
-            if (acc) {
-                VF_TRY(tower_gemm(h, h->att, W, w.w_o, W, M, W, W, epi(h->x, W, 1, w.b_o, VF_ACT_NONE, 1), s));
-                VF_TRY(tower_add_ln(h, h->x, W, nullptr, W, 0, w.ln2_w, w.ln2_b, h->h, W, M, s));
-            } else {
-                VF_TRY(tower_gemm(h, h->att, W, w.w_o, W, M, W, W, epi(h->y, W, 0, w.b_o, VF_ACT_NONE), s));
-                VF_TRY(tower_add_ln(h, h->x, W, h->y, W, 1, w.ln2_w, w.ln2_b, h->h, W, M, s));
-            }
-            VF_TRY(tower_gemm(h, h->h, W, w.w_fc, W, M, MLPW, W, epi(h->mlp, MLPW, 0, w.b_fc, VF_ACT_QUICKGELU), s));
-            if (acc) VF_TRY(tower_gemm(h, h->mlp, MLPW, w.w_proj, MLPW, M, W, MLPW, epi(h->x, W, 1, w.b_proj, VF_ACT_NONE, 1), s));
-            else     VF_TRY(tower_gemm(h, h->mlp, MLPW, w.w_proj, MLPW, M, W, MLPW, epi(h->y, W, 0, w.b_proj, VF_ACT_NONE), s));
+        // Last block: only the CLS token reaches ln_post / proj (encode_image returns x[:, 0]), so after the attention
+        // everything runs on the c CLS rows: A operands and the residual rows are strided views (row pitch 50*768), h /
+        // mlp / y are compact c-row buffers.  Saves 49/50 of out-proj + MLP of this block (5.9 % of the FLOPs).
+        const bool last = l + 1 == L;
+        const int rows = last ? c : M;
+        const int a_ld = last ? T * W : W;                    // row pitch of att / x when only the CLS rows are read
+        if (acc_o) {
+            VF_TRY(tower_gemm(h, h->att, a_ld, w.w_o, W, rows, W, W, epi(h->x, a_ld, 1, w.b_o, VF_ACT_NONE, 1), s));
+            VF_TRY(tower_add_ln(h, h->x, a_ld, nullptr, W, 0, w.ln2_w, w.ln2_b, h->h, W, rows, s));
         } else {
-            // Last block: only the CLS token reaches ln_post / proj (encode_image returns x[:, 0]), so after the
-            // attention everything runs on the c CLS rows: A operands and the residual rows are strided views (row pitch
-            // 50*768), h / mlp are compact c-row buffers.  Saves 49/50 of out-proj + MLP of this block (5.9 % of the FLOPs).
-            if (acc) {
-                VF_TRY(tower_gemm(h, h->att, T * W, w.w_o, W, c, W, W, epi(h->x, T * W, 1, w.b_o, VF_ACT_NONE, 1), s));
-                VF_TRY(tower_add_ln(h, h->x, int64_t(T) * W, nullptr, W, 0, w.ln2_w, w.ln2_b, h->h, W, c, s));
-            } else {
-                VF_TRY(tower_gemm(h, h->att, T * W, w.w_o, W, c, W, W, epi(h->y, W, 0, w.b_o, VF_ACT_NONE), s));
-                VF_TRY(tower_add_ln(h, h->x, int64_t(T) * W, h->y, W, 1, w.ln2_w, w.ln2_b, h->h, W, c, s));
-            }
-            VF_TRY(tower_gemm(h, h->h, W, w.w_fc, W, c, MLPW, W, epi(h->mlp, MLPW, 0, w.b_fc, VF_ACT_QUICKGELU), s));
-            if (acc) VF_TRY(tower_gemm(h, h->mlp, MLPW, w.w_proj, MLPW, c, W, MLPW, epi(h->x, T * W, 1, w.b_proj, VF_ACT_NONE, 1), s));
-            else     VF_TRY(tower_gemm(h, h->mlp, MLPW, w.w_proj, MLPW, c, W, MLPW, epi(h->y, W, 0, w.b_proj, VF_ACT_NONE), s));
+            VF_TRY(tower_gemm(h, h->att, a_ld, w.w_o, W, rows, W, W, epi(h->y, W, 0, w.b_o, VF_ACT_NONE), s));
+            VF_TRY(tower_add_ln(h, h->x, a_ld, h->y, W, 1, w.ln2_w, w.ln2_b, h->h, W, rows, s));
         }
+        VF_TRY(tower_gemm(h, h->h, W, w.w_fc, W, rows, MLPW, W, epi(h->mlp, MLPW, 0, w.b_fc, VF_ACT_QUICKGELU), s));
+        if (acc_m) VF_TRY(tower_gemm(h, h->mlp, MLPW, w.w_proj, MLPW, rows, W, MLPW, epi(h->x, a_ld, 1, w.b_proj, VF_ACT_NONE, 1), s));
+        else       VF_TRY(tower_gemm(h, h->mlp, MLPW, w.w_proj, MLPW, rows, W, MLPW, epi(h->y, W, 0, w.b_proj, VF_ACT_NONE), s));
         h->launches += 7;
     }
     // CLS rows: (y form: x += y of the last MLP;) ln_post; then the 768 -> 512 projection
-    VF_TRY(tower_add_ln(h, h->x, int64_t(T) * W, acc ? nullptr : h->y, W, 0, h->lnpost_w, h->lnpost_b, h->cls, W, c, s));
+    VF_TRY(tower_add_ln(h, h->x, int64_t(T) * W, acc_m ? nullptr : h->y, W, 0, h->lnpost_w, h->lnpost_b, h->cls, W, c, s));
     VF_TRY(tower_gemm(h, h->cls, W, h->w_proj, W, c, E, W, epi(out, E, 1, nullptr, VF_ACT_NONE), s));
     h->launches += 2;
     return VF_OK;
@@ -405,8 +396,9 @@ int vf_clip_create(vf_clip_t** out, const vf_clip_weights* w, int device, int ch
         {
             const char* e = getenv("VF_NO_GRAPH");
             h->use_graph = !(e && e[0] == '1');
-            const char* r = getenv("VF_CLIP_RESID");
-            h->acc_resid = !(r && r[0] == 'y');
+            const char* r = getenv("VF_CLIP_RESID");     // acc (default) | y | mix (reduction for the MLP only)
+            h->acc_o = !(r && (r[0] == 'y' || r[0] == 'm'));
+            h->acc_m = !(r && r[0] == 'y');
         }
         activate(h, 0);
         VF_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));

@@ -6,16 +6,17 @@
 // A cluster of two CTAs (one TPC) owns a 256 x BN output tile.  Each CTA stages its own 128 rows of A and HALF of
 // the B tile (BN/2 rows) through a 128B-swizzled TMA ring; the leader CTA issues one UMMA of M=256 per 16-wide K
 // step that reads both halves, and each CTA's TMEM receives the 128 x BN block of its rows (two accumulator stages,
-// so the epilogue of tile i overlaps the main loop of tile i+1).  12 warps per CTA:
+// so the epilogue of tile i overlaps the main loop of tile i+1).  4 + 4*NGRP warps per CTA:
 //   warp 0      TMA producer (one lane, both CTAs)          warp 1   MMA issuer (one lane, leader CTA only)
 //   warp 2      TMEM allocator                              warp 3   idle
-//   warps 4-11  epilogue, two groups of 4 warps (128 threads = the 128 TMEM lanes / rows of this CTA):
-//               tcgen05.ld (thread = row) -> scale/bias/activation -> 128B-swizzled smem slice [128 rows x 128 B]
-//               -> ONE elected thread issues a TMA store of the slice.  Groups alternate column slices and
-//               double-buffer their slice, so global writes are asynchronous bulk copies (no per-thread STG);
-//               M/N tails are clipped by the TMA unit.
-// Measured motivation (profiles/r1_gemm_notes.md): with per-thread stores the epilogue, not the tensor pipe,
-// bounded every K=768 GEMM of the ViT (~35 SM-cycles per warp-level store instruction regardless of its width).
+//   warps 4..   epilogue, NGRP groups of 4 warps (one warp per TMEM lane quarter = 32 rows of this CTA's 128); groups
+//               take column slices of 128 bytes in turn.  Per slice a warp does tcgen05.ld (thread = row) -> scale / bias /
+//               activation -> its [32 rows x 128 B] of a 128B-swizzled staging slice -> fence.proxy.async + __syncwarp ->
+//               its elected lane issues a TMA store (or TMA reduce-add) of that box.  No barrier between warps; M/N tails
+//               are clipped by the TMA unit; no per-thread global stores.
+// How it got here (profiles/r1_gemm_notes.md, profiles/r2_gemm_notes.md): per-thread stores from registers are bound by
+// the LSU (32 sectors per warp instruction); one elected thread per 128-row slice serialises four warps on a named
+// barrier; with 8 epilogue warps the fc1 + QuickGELU epilogue (2 MUFU ops per element) was the critical path.
 //
 // Used for every dense contraction of the hot path: ViT patch-embed / QKV / out-proj / FFN GEMMs (reference:
 // third-party clip `VisionTransformer.forward`, called at models/CLIP/extract_clip.py:128).
@@ -29,18 +30,20 @@
 #include "common.cuh"
 #include "internal.h"
 
-// Epilogue hand-off variant (compile-time; scripts/build_variants.sh builds one library per value for A/B runs):
-//   0  slice of 128 rows: 4 warps fill it, one named barrier, ONE elected thread issues a [128 x 128 B] TMA store
-//   5  per-warp: every warp owns its 32 rows of the slice (4 KB), fences, __syncwarp()s and issues its own
-//      [32 x 128 B] TMA store -- no barrier between warps, no agent serialisation
-//   4  per-warp transpose through the same 4 KB region, then coalesced 16-byte st.global (4 full 128-byte rows per
-//      warp instruction) -- no async proxy at all
-//   6  no staging at all: every thread stores (or red.adds) the 16-byte pieces of its own row straight from registers
-#ifndef VF_EPI_MODE
-#define VF_EPI_MODE 5
+// epilogue warp groups (4 warps = the 4 TMEM lane quarters each) of the plain 256-wide configuration -- the ViT GEMMs.
+// Measured (profiles/r2_gemm_notes.md): 2 -> 4 groups takes the fc1 + QuickGELU epilogue off the critical path.
+#ifndef VF_EPI_GROUPS
+#define VF_EPI_GROUPS 4
 #endif
-// measurement aids: VF_DBG_NO_EPI = accumulators are released unread (main loop only); VF_DBG_NO_STORE = the whole
-// epilogue except the global store instructions
+#ifndef VF_STAGES_256
+#define VF_STAGES_256 5       // TMA ring depth of the plain 256-wide configuration
+#endif
+// measurement aid (scripts/build_variants.sh, scripts/gemm_trace.py): which parts of the epilogue run.
+//   0 all (product)   1 no TMA store   2 TMEM load + math only   3 TMEM load only   4 everything but the TMEM load
+//   9 nothing: accumulators are released unread (main loop only)
+#ifndef VF_DBG_EPI
+#define VF_DBG_EPI 0
+#endif
 namespace vf {
 
 namespace {
@@ -54,9 +57,8 @@ __device__ long long g_trace[74][64][8];
 #else
 #define VF_TRACE(slot, iter) do { } while (0)
 #endif
-constexpr int EPI_MODE = VF_EPI_MODE;
 constexpr int BM = 128;          // rows per CTA (256 per pair)
-constexpr int STORE_ROWS = EPI_MODE == 5 ? 32 : BM;     // rows of one TMA store box
+constexpr int STORE_ROWS = 32;   // rows of one TMA store box: every epilogue warp stores its own 32 rows
 constexpr int BK = 64;           // 64 fp16 = one 128-byte swizzle row
 // epilogue warp groups (4 warps = the 4 TMEM lane quarters each) of the plain 256-wide configuration -- the ViT GEMMs, whose
 // K = 768 shapes are bounded by the epilogue's latency chain (TMEM load -> math -> shared -> store), not by its bandwidth
@@ -81,7 +83,7 @@ struct GemmCfg {
     static constexpr int EPI_WARPS = 4 * NGRP;
     static constexpr int THREADS = (4 + EPI_WARPS) * 32;
     static constexpr uint32_t EPI_BUFS = (NSPLIT == 2 || NGRP > 2) ? 1 : 2;
-    static constexpr uint32_t STG_BYTES = EPI_MODE == 6 ? 0 : NGRP * EPI_BUFS * SLICE_BYTES;   // NGRP groups x EPI_BUFS slice buffers
+    static constexpr uint32_t STG_BYTES = NGRP * EPI_BUFS * SLICE_BYTES;   // NGRP groups x EPI_BUFS slice buffers
     static constexpr uint32_t BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;   // + align slack
     static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns");
@@ -128,12 +130,39 @@ __device__ __forceinline__ void epi_math32(float* v, const GemmEpi& ep, int n, i
     }
 }
 
-// SPLIT: split-fp16 output (GemmEpi::split_off) -- every fp16 slice is emitted twice, hi then lo, through tmO / tmO2.  A
+// 32 consecutive fp32 accumulator columns of this thread's row: TMEM -> registers -> scale / bias / activation (zeroed
+// for rows outside the valid conv region)
+__device__ __forceinline__ void epi_load32(float* v, uint32_t taddr, const GemmEpi& ep, int n, int N, bool keep) {
+#if VF_DBG_EPI == 4
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = float(n + j);        // measurement aid: the accumulator is never read
+    (void)taddr;
+#else
+    uint32_t raw[32];
+    tmem_ld_32x32(taddr, raw);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+#endif
+#if VF_DBG_EPI != 3
+    epi_math32(v, ep, n, N);
+#endif
+    if (!keep) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
+}
+__device__ __forceinline__ void epi_sink(const float* v) {      // measurement aid: keep the values alive without storing them
+#pragma unroll
+    for (int j = 0; j < 32; ++j) asm volatile("" ::"f"(v[j]));
+}
+
+// SPLIT: split-fp16 output (GemmEpi::split_off) -- every fp16 slice is emitted twice, hi then lo (split_off columns to the right).  A
 // compile-time switch: as a run-time loop it cost the plain epilogue 20 % on K = 768 shapes.
 template <int BN, int STAGES, int NSPLIT, bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GemmCfg<BN, STAGES, NSPLIT>::THREADS, 1)
 gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2, const GemmEpi ep,
+                     const __grid_constant__ CUtensorMap tmO, const GemmEpi ep,
                      const int M, const int N, const __grid_constant__ ConvGeom cg) {
     using Cfg = GemmCfg<BN, STAGES, NSPLIT>;
     extern __shared__ uint8_t smem_raw[];
@@ -168,7 +197,6 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmO);
-        tma_prefetch_desc(&tmO2);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -186,6 +214,10 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     cluster_sync_all();      // barriers of both CTAs initialised before any remote arrive / TMA credit
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above overlapped the tail of the previous kernel; its results (our operands, and buffers we overwrite)
+    // are complete past this point.  The next kernel may be scheduled as SMs drain.
+    pdl_wait();
+    pdl_trigger();
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (both CTAs)
@@ -259,7 +291,6 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int grp = e >> 2;
         const int row = q * 32 + lane;         // row inside this CTA's 128-row block == TMEM lane
         uint8_t* bufs = stg + grp * Cfg::EPI_BUFS * SLICE_BYTES;
-        const bool agent = (q == 0) && (lane == 0);
         const int slice_cols = ep.out_f32 ? 32 : 64;
         constexpr int NSP = SPLIT ? 2 : 1;
         const uint32_t sw = uint32_t(row & 7);
@@ -273,7 +304,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             if (cta == 0 && warp == 4 && lane == 0) VF_TRACE(2, titer);
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * BN + (uint32_t(q * 32) << 16);
-#ifndef VF_DBG_NO_EPI
+#if VF_DBG_EPI != 9
             bool keep = true;     // rows outside the valid conv region become the next layer's zero padding
             if (cg.mask) {
                 const int m = m0 + row - cg.row0;
@@ -282,23 +313,20 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const int tt = r2 % cg.Tp;
                 keep = (m >= 0) && (w >= cg.w0) && (w < cg.w1) && (hh >= cg.h0) && (hh < cg.h1) && (tt >= cg.t0) && (tt < cg.t1);
             }
-            const bool grow_ok = m0 + row < M;       // (mode 6) this thread's output row exists
+            // Plain outputs leave through st.global, NOT the TMA unit: measured (profiles/r2_gemm_notes.md, in-kernel
+            // timeline) the TMA engine of an SM does not overlap its stores with its loads -- 64 KB of TMA stores per tile
+            // stretched the main loop's tile period from 6144 to 9200 cycles.  Only the fp32 reduce-add (the residual-stream
+            // update, where the reduction has to happen in the L2) goes through TMA.
+            const bool via_tma = ep.accumulate != 0;
 #pragma unroll 1
             for (int c = grp * slice_cols; c < BN; c += Cfg::NGRP * slice_cols)
 #pragma unroll
             for (int sp = 0; sp < NSP; ++sp) {     // split output: the slice is produced twice, hi then lo
-                uint8_t* buf = bufs + (Cfg::EPI_BUFS == 2 ? (it & 1) : 0) * SLICE_BYTES;
-                uint8_t* myrow = buf + row * 128;
-                if (EPI_MODE == 0) {
-                    // The TMA store that last used this buffer must have finished reading it.  With two buffers that is
-                    // guaranteed by the barrier of the previous slice (the agent drains the older store before arriving
-                    // there, below); with one buffer it has to be checked here, at the cost of a second barrier.
-                    if (Cfg::EPI_BUFS == 1) {
-                        if (agent) bulk_wait_read<0>();
-                        named_bar_sync(1 + grp, 128);
-                    }
-                } else if (EPI_MODE == 5) {
-                    // this warp's own store of two slices ago (one slice ago with a single buffer) has read its 4 KB
+                // this warp's 32 rows x 128 B of the group's slice buffer.  TMA path: its own store of two slices ago (one
+                // slice ago with a single buffer) must have finished READING them before they are overwritten.
+                uint8_t* buf = bufs + (Cfg::EPI_BUFS == 2 ? (it & 1) : 0) * SLICE_BYTES + q * 4096;
+                uint8_t* myrow = buf + lane * 128;
+                if (via_tma) {
                     if (lane == 0) {
                         if (Cfg::EPI_BUFS == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
                     }
@@ -306,109 +334,51 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 }
                 const int n = n_blk * BN + c;
                 if (ep.out_f32) {
-                    uint32_t raw[32];
-                    tmem_ld_32x32(t_row + c, raw);
-                    tmem_ld_wait();
                     float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-                    epi_math32(v, ep, n, N);
-                    if (!keep) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-                    }
-                    if (EPI_MODE == 6) {
-                        // straight from registers: this thread's 128 bytes of its own output row
-#ifndef VF_DBG_NO_STORE
-                        if (grow_ok) {
-                            float* o = reinterpret_cast<float*>(ep.out) + size_t(m0 + row) * ep.ldo + n;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                if (n + 4 * j < N) {
-                                    const float4 val = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                                    if (ep.accumulate) red_add_f32x4(o + 4 * j, val);
-                                    else *reinterpret_cast<float4*>(o + 4 * j) = val;
-                                }
-                        }
-#endif
+                    epi_load32(v, t_row + c, ep, n, N, keep);
+                    if (VF_DBG_EPI >= 2 && VF_DBG_EPI <= 3) {
+                        epi_sink(v);
                     } else {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<float4*>(myrow + ((uint32_t(j) ^ sw) << 4)) =
-                            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4*>(myrow + ((uint32_t(j) ^ sw) << 4)) =
+                                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     }
                 } else {
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
-                        uint32_t raw[32];
-                        tmem_ld_32x32(t_row + c + hh * 32, raw);
-                        tmem_ld_wait();
                         float v[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-                        epi_math32(v, ep, n + hh * 32, N);
-                        if (!keep) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = 0.f;
-                        }
+                        epi_load32(v, t_row + c + hh * 32, ep, n + hh * 32, N, keep);
                         if (SPLIT && sp) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] -= __half2float(__float2half_rn(v[j]));
                         }
-                        if (EPI_MODE == 6) {
-#ifndef VF_DBG_NO_STORE
-                            if (grow_ok) {
-                                __half* o = reinterpret_cast<__half*>(ep.out) + size_t(m0 + row) * ep.ldo + n + hh * 32 +
-                                            ((SPLIT && sp) ? ep.split_off : 0);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    if (n + hh * 32 + 8 * j < N)
-                                        *reinterpret_cast<uint4*>(o + 8 * j) =
-                                            make_uint4(pack_half2(v[8 * j], v[8 * j + 1]), pack_half2(v[8 * j + 2], v[8 * j + 3]),
-                                                       pack_half2(v[8 * j + 4], v[8 * j + 5]), pack_half2(v[8 * j + 6], v[8 * j + 7]));
-                            }
-#endif
+                        if (VF_DBG_EPI >= 2 && VF_DBG_EPI <= 3) {
+                            epi_sink(v);
                         } else {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<uint4*>(myrow + ((uint32_t(hh * 4 + j) ^ sw) << 4)) =
-                                make_uint4(pack_half2(v[8 * j], v[8 * j + 1]), pack_half2(v[8 * j + 2], v[8 * j + 3]),
-                                           pack_half2(v[8 * j + 4], v[8 * j + 5]), pack_half2(v[8 * j + 6], v[8 * j + 7]));
+                            for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<uint4*>(myrow + ((uint32_t(hh * 4 + j) ^ sw) << 4)) =
+                                    make_uint4(pack_half2(v[8 * j], v[8 * j + 1]), pack_half2(v[8 * j + 2], v[8 * j + 3]),
+                                               pack_half2(v[8 * j + 4], v[8 * j + 5]), pack_half2(v[8 * j + 6], v[8 * j + 7]));
                         }
                     }
                 }
-                if (EPI_MODE == 0) {
-                    fence_proxy_async();
-                    // two buffers: the store of the previous slice (the OTHER buffer) has had this slice's compute time to
-                    // read its source; once it has, everybody may overwrite that buffer in the next iteration
-                    if (Cfg::EPI_BUFS == 2 && agent) bulk_wait_read<0>();
-                    named_bar_sync(1 + grp, 128);
-                    if (agent) {
-                        // rows >= M and columns >= N are clipped by the TMA unit.  A group is committed for EVERY slice,
-                        // also for the (empty) ones right of N, so that the group accounting of wait_group.read stays uniform.
-#ifndef VF_DBG_NO_STORE
-                        if (n < N) {
-                            if (ep.accumulate) tma_reduce_add_2d(&tmO, buf, n, m0);
-                            else tma_store_2d((SPLIT && sp) ? &tmO2 : &tmO, buf, n, m0);
-                        }
-#endif
-                        bulk_commit();
-                    }
-                } else if (EPI_MODE == 5) {
+                if (VF_DBG_EPI >= 2 && VF_DBG_EPI <= 3) {
+                    __syncwarp();
+                } else if (via_tma) {
+                    // generic-proxy writes -> visible to the async proxy; then the warp's elected lane hands its
+                    // [32 x 128 B] box to the TMA unit.  Rows >= M and columns >= N are clipped by the TMA unit.  A group is
+                    // committed for EVERY slice, also for the (empty) ones right of N: uniform wait_group.read accounting.
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-#ifndef VF_DBG_NO_STORE
-                        if (n < N) {
-                            if (ep.accumulate) tma_reduce_add_2d(&tmO, buf + q * 4096, n, m0 + q * 32);
-                            else tma_store_2d((SPLIT && sp) ? &tmO2 : &tmO, buf + q * 4096, n, m0 + q * 32);
-                        }
-#endif
+                        if ((VF_DBG_EPI == 0 || VF_DBG_EPI == 4) && n < N) tma_reduce_add_2d(&tmO, buf, n, m0 + q * 32);
                         bulk_commit();
                     }
-                } else if (EPI_MODE == 4) {
-                    // EPI_MODE 4: the warp reads its own 32 x 128 B back row-wise and writes 4 complete 128-byte rows per
-                    // instruction (lanes 8i..8i+7 cover row i of the group of 4)
+                } else {
+                    // the warp reads its 32 x 128 B back row-wise (the swizzle keeps this conflict-free) and writes 4
+                    // complete 128-byte output rows per instruction: lanes 8i..8i+7 cover row i of the group of 4
                     __syncwarp();
                     uint8_t* obase = static_cast<uint8_t*>(ep.out) + ((SPLIT && sp) ? size_t(ep.split_off) * 2 : 0);
                     const int esz = ep.out_f32 ? 4 : 2;
@@ -417,32 +387,23 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int r = i * 4 + (lane >> 3);
-                        const uint4 val = *reinterpret_cast<const uint4*>(buf + (q * 32 + r) * 128 + ((uint32_t(ch) ^ uint32_t(r & 7)) << 4));
+                        const uint4 val = *reinterpret_cast<const uint4*>(buf + r * 128 + ((uint32_t(ch) ^ uint32_t(r & 7)) << 4));
                         const int gm = m0 + q * 32 + r;
-#ifndef VF_DBG_NO_STORE
-                        if (gm < M && col_ok) {
-                            uint8_t* dst = obase + (size_t(gm) * ep.ldo + n) * esz + ch * 16;
-                            if (ep.accumulate)
-                                red_add_f32x4(reinterpret_cast<float*>(dst), make_float4(__uint_as_float(val.x), __uint_as_float(val.y),
-                                                                                         __uint_as_float(val.z), __uint_as_float(val.w)));
-                            else
-                                *reinterpret_cast<uint4*>(dst) = val;
-                        }
-#endif
+                        if ((VF_DBG_EPI == 0 || VF_DBG_EPI == 4) && gm < M && col_ok)
+                            *reinterpret_cast<uint4*>(obase + (size_t(gm) * ep.ldo + n) * esz + ch * 16) = val;
                     }
                     if (Cfg::EPI_BUFS == 1) __syncwarp();      // the same 4 KB is rewritten by the next slice
                 }
                 ++it;
             }
-#endif  // VF_DBG_NO_EPI
+#endif  // VF_DBG_EPI != 9
             tc_fence_before();
             __syncwarp();
             if (cta == 0 && warp == 4 && lane == 0) VF_TRACE(3, titer);
             if (lane == 0) mbar_arrive_remote(&tempty[acc], 0);   // this accumulator stage is drained
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        // all global writes of this CTA are complete before it retires
-        if (EPI_MODE == 5 ? (lane == 0) : (EPI_MODE == 0 && agent)) bulk_wait<0>();
+        if (lane == 0) bulk_wait<0>();   // all global writes of this warp are complete before the CTA retires
     }
 
     tc_fence_before();
@@ -477,7 +438,7 @@ EncodeTiledFn get_encode_tiled() {
 }
 
 template <int BN, int STAGES, int NSPLIT, bool SPLIT = false>
-int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmO2,
+int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                      const GemmEpi& ep, int M,
                      int N, const ConvGeom& cg, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, STAGES, NSPLIT>;
@@ -494,8 +455,8 @@ int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
     const int pairs = device_sm_count() / 2;
     const int grid = 2 * (tiles < pairs ? tiles : pairs);
-    gemm_f16_pair_kernel<BN, STAGES, NSPLIT, SPLIT><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, tmO2, ep, M, N, cg);
-    VF_CUDA(cudaGetLastError());
+    VF_CUDA(launch_pdl(gemm_f16_pair_kernel<BN, STAGES, NSPLIT, SPLIT>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream,
+                       tmA, tmB, tmO, ep, M, N, cg));
     return VF_OK;
 }
 
@@ -541,31 +502,31 @@ struct GemmProf {
 };
 static thread_local GemmProf g_prof;
 
-static int run_gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmO2,
+static int run_gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                            int bn, const GemmEpi& ep,
                            int M, int N, const ConvGeom& cg, cudaStream_t stream) {
     if (ep.split_off > 0 && !ep.out_f32) {
         if (cg.nsplit == 2) {
-            if (bn == 256) return launch_gemm_pair<256, 4, 2, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
-            if (bn == 192) return launch_gemm_pair<192, 4, 2, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
-            if (bn == 128) return launch_gemm_pair<128, 6, 2, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
-            return launch_gemm_pair<64, 8, 2, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+            if (bn == 256) return launch_gemm_pair<256, 4, 2, true>(tmA, tmB, tmO, ep, M, N, cg, stream);
+            if (bn == 192) return launch_gemm_pair<192, 4, 2, true>(tmA, tmB, tmO, ep, M, N, cg, stream);
+            if (bn == 128) return launch_gemm_pair<128, 6, 2, true>(tmA, tmB, tmO, ep, M, N, cg, stream);
+            return launch_gemm_pair<64, 8, 2, true>(tmA, tmB, tmO, ep, M, N, cg, stream);
         }
-        if (bn == 256) return launch_gemm_pair<256, 5, 1, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
-        if (bn == 192) return launch_gemm_pair<192, 5, 1, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
-        if (bn == 128) return launch_gemm_pair<128, 6, 1, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
-        return launch_gemm_pair<64, 8, 1, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+        if (bn == 256) return launch_gemm_pair<256, 5, 1, true>(tmA, tmB, tmO, ep, M, N, cg, stream);
+        if (bn == 192) return launch_gemm_pair<192, 5, 1, true>(tmA, tmB, tmO, ep, M, N, cg, stream);
+        if (bn == 128) return launch_gemm_pair<128, 6, 1, true>(tmA, tmB, tmO, ep, M, N, cg, stream);
+        return launch_gemm_pair<64, 8, 1, true>(tmA, tmB, tmO, ep, M, N, cg, stream);
     }
     if (cg.nsplit == 2) {
-        if (bn == 256) return launch_gemm_pair<256, 4, 2>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
-        if (bn == 192) return launch_gemm_pair<192, 4, 2>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
-        if (bn == 128) return launch_gemm_pair<128, 6, 2>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
-        return launch_gemm_pair<64, 8, 2>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+        if (bn == 256) return launch_gemm_pair<256, 4, 2>(tmA, tmB, tmO, ep, M, N, cg, stream);
+        if (bn == 192) return launch_gemm_pair<192, 4, 2>(tmA, tmB, tmO, ep, M, N, cg, stream);
+        if (bn == 128) return launch_gemm_pair<128, 6, 2>(tmA, tmB, tmO, ep, M, N, cg, stream);
+        return launch_gemm_pair<64, 8, 2>(tmA, tmB, tmO, ep, M, N, cg, stream);
     }
-    if (bn == 256) return launch_gemm_pair<256, VF_STAGES_256, 1>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
-    if (bn == 192) return launch_gemm_pair<192, 5, 1>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
-    if (bn == 128) return launch_gemm_pair<128, 6, 1>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
-    return launch_gemm_pair<64, 8, 1>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+    if (bn == 256) return launch_gemm_pair<256, VF_STAGES_256, 1>(tmA, tmB, tmO, ep, M, N, cg, stream);
+    if (bn == 192) return launch_gemm_pair<192, 5, 1>(tmA, tmB, tmO, ep, M, N, cg, stream);
+    if (bn == 128) return launch_gemm_pair<128, 6, 1>(tmA, tmB, tmO, ep, M, N, cg, stream);
+    return launch_gemm_pair<64, 8, 1>(tmA, tmB, tmO, ep, M, N, cg, stream);
 }
 
 static int run_gemm(const CUtensorMap& tmA, const __half* B, int ldb, int64_t Ktot, int M, int N, const ConvGeom& cg,
@@ -583,19 +544,16 @@ static int run_gemm(const CUtensorMap& tmA, const __half* B, int ldb, int64_t Kt
             if (padded < best) { best = padded; bn = cand; }
         }
     }
-    CUtensorMap tmB, tmO, tmO2;
+    CUtensorMap tmB, tmO;
     VF_TRY(make_tmap_2d(&tmB, B, 2, uint64_t(N), uint64_t(Ktot), uint64_t(ldb) * 2, uint32_t(bn / 2), BK));
     const uint64_t ncols = uint64_t(N);     // (N % 8 == 0: a store view narrower than a 16-byte multiple corrupts its neighbours)
     if (ep.out_f32) VF_TRY(make_tmap_2d(&tmO, ep.out, 4, uint64_t(M), ncols, uint64_t(ep.ldo) * 4, STORE_ROWS, 32));
     else            VF_TRY(make_tmap_2d(&tmO, ep.out, 2, uint64_t(M), ncols, uint64_t(ep.ldo) * 2, STORE_ROWS, 64));
-    tmO2 = tmO;
-    if (ep.split_off) {     // second view of the output rows: the lo halves, both views clip at N columns
+    if (ep.split_off) {     // second view of the output rows: the lo halves (written through a pointer offset)
         if (ep.out_f32 || ep.split_off < N || ep.split_off % 8)
             return fail(VF_ERR_INVALID, "gemm: split output needs fp16 out and split_off >= N, multiple of 8");
-        VF_TRY(make_tmap_2d(&tmO2, static_cast<__half*>(ep.out) + ep.split_off, 2, uint64_t(M), ncols,
-                            uint64_t(ep.ldo) * 2, STORE_ROWS, 64));
     }
-    if (!g_prof.on) return run_gemm_launch(tmA, tmB, tmO, tmO2, bn, ep, M, N, cg, stream);
+    if (!g_prof.on) return run_gemm_launch(tmA, tmB, tmO, bn, ep, M, N, cg, stream);
     if (g_prof.used + 2 > g_prof.ev.size())
         for (int i = 0; i < 2; ++i) {
             cudaEvent_t e;
@@ -603,7 +561,7 @@ static int run_gemm(const CUtensorMap& tmA, const __half* B, int ldb, int64_t Kt
             g_prof.ev.push_back(e);
         }
     VF_CUDA(cudaEventRecord(g_prof.ev[g_prof.used], stream));
-    const int st = run_gemm_launch(tmA, tmB, tmO, tmO2, bn, ep, M, N, cg, stream);
+    const int st = run_gemm_launch(tmA, tmB, tmO, bn, ep, M, N, cg, stream);
     VF_CUDA(cudaEventRecord(g_prof.ev[g_prof.used + 1], stream));
     g_prof.used += 2;
     double kexec = double(Ktot);
