@@ -231,15 +231,6 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask
         : "memory");
 }
 
-// ---------------------------------------------------------------- programmatic dependent launch (PDL)
-// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream
-// (or graph) is still running: everything before pdl_wait() -- barrier init, TMEM allocation, descriptor prefetch, index
-// arithmetic -- overlaps the predecessor's tail; pdl_wait() returns once the predecessor has completed and its writes are
-// visible.  pdl_trigger() lets the NEXT kernel's blocks be scheduled as soon as every block of this one has started.
-// Both are no-ops for a kernel launched without the attribute.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -157,12 +157,12 @@ __device__ __forceinline__ void epi_sink(const float* v) {      // measurement a
     for (int j = 0; j < 32; ++j) asm volatile("" ::"f"(v[j]));
 }
 
-// SPLIT: split-fp16 output (GemmEpi::split_off) -- every fp16 slice is emitted twice, hi then lo (split_off columns to the right).  A
+// SPLIT: split-fp16 output (GemmEpi::split_off) -- every fp16 slice is emitted twice, hi then lo, through tmO / tmO2.  A
 // compile-time switch: as a run-time loop it cost the plain epilogue 20 % on K = 768 shapes.
 template <int BN, int STAGES, int NSPLIT, bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GemmCfg<BN, STAGES, NSPLIT>::THREADS, 1)
 gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ CUtensorMap tmO, const GemmEpi ep,
+                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2, const GemmEpi ep,
                      const int M, const int N, const __grid_constant__ ConvGeom cg) {
     using Cfg = GemmCfg<BN, STAGES, NSPLIT>;
     extern __shared__ uint8_t smem_raw[];
@@ -197,6 +197,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmO);
+        tma_prefetch_desc(&tmO2);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -214,10 +215,6 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     cluster_sync_all();      // barriers of both CTAs initialised before any remote arrive / TMA credit
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // everything above overlapped the tail of the previous kernel; its results (our operands, and buffers we overwrite)
-    // are complete past this point.  The next kernel may be scheduled as SMs drain.
-    pdl_wait();
-    pdl_trigger();
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (both CTAs)
@@ -313,25 +310,18 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const int tt = r2 % cg.Tp;
                 keep = (m >= 0) && (w >= cg.w0) && (w < cg.w1) && (hh >= cg.h0) && (hh < cg.h1) && (tt >= cg.t0) && (tt < cg.t1);
             }
-            // Plain outputs leave through st.global, NOT the TMA unit: measured (profiles/r2_gemm_notes.md, in-kernel
-            // timeline) the TMA engine of an SM does not overlap its stores with its loads -- 64 KB of TMA stores per tile
-            // stretched the main loop's tile period from 6144 to 9200 cycles.  Only the fp32 reduce-add (the residual-stream
-            // update, where the reduction has to happen in the L2) goes through TMA.
-            const bool via_tma = ep.accumulate != 0;
 #pragma unroll 1
             for (int c = grp * slice_cols; c < BN; c += Cfg::NGRP * slice_cols)
 #pragma unroll
             for (int sp = 0; sp < NSP; ++sp) {     // split output: the slice is produced twice, hi then lo
-                // this warp's 32 rows x 128 B of the group's slice buffer.  TMA path: its own store of two slices ago (one
-                // slice ago with a single buffer) must have finished READING them before they are overwritten.
+                // this warp's 32 rows x 128 B of the group's slice buffer: its own TMA store of two slices ago (one slice ago
+                // with a single buffer) must have finished READING them before they are overwritten
                 uint8_t* buf = bufs + (Cfg::EPI_BUFS == 2 ? (it & 1) : 0) * SLICE_BYTES + q * 4096;
                 uint8_t* myrow = buf + lane * 128;
-                if (via_tma) {
-                    if (lane == 0) {
-                        if (Cfg::EPI_BUFS == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
-                    }
-                    __syncwarp();
+                if (lane == 0) {
+                    if (Cfg::EPI_BUFS == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
                 }
+                __syncwarp();
                 const int n = n_blk * BN + c;
                 if (ep.out_f32) {
                     float v[32];
@@ -366,33 +356,19 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 }
                 if (VF_DBG_EPI >= 2 && VF_DBG_EPI <= 3) {
                     __syncwarp();
-                } else if (via_tma) {
+                } else {
                     // generic-proxy writes -> visible to the async proxy; then the warp's elected lane hands its
                     // [32 x 128 B] box to the TMA unit.  Rows >= M and columns >= N are clipped by the TMA unit.  A group is
                     // committed for EVERY slice, also for the (empty) ones right of N: uniform wait_group.read accounting.
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        if ((VF_DBG_EPI == 0 || VF_DBG_EPI == 4) && n < N) tma_reduce_add_2d(&tmO, buf, n, m0 + q * 32);
+                        if ((VF_DBG_EPI == 0 || VF_DBG_EPI == 4) && n < N) {
+                            if (ep.accumulate) tma_reduce_add_2d(&tmO, buf, n, m0 + q * 32);
+                            else tma_store_2d((SPLIT && sp) ? &tmO2 : &tmO, buf, n, m0 + q * 32);
+                        }
                         bulk_commit();
                     }
-                } else {
-                    // the warp reads its 32 x 128 B back row-wise (the swizzle keeps this conflict-free) and writes 4
-                    // complete 128-byte output rows per instruction: lanes 8i..8i+7 cover row i of the group of 4
-                    __syncwarp();
-                    uint8_t* obase = static_cast<uint8_t*>(ep.out) + ((SPLIT && sp) ? size_t(ep.split_off) * 2 : 0);
-                    const int esz = ep.out_f32 ? 4 : 2;
-                    const int ch = lane & 7;
-                    const bool col_ok = n + (ch * 16) / esz < N;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = i * 4 + (lane >> 3);
-                        const uint4 val = *reinterpret_cast<const uint4*>(buf + r * 128 + ((uint32_t(ch) ^ uint32_t(r & 7)) << 4));
-                        const int gm = m0 + q * 32 + r;
-                        if ((VF_DBG_EPI == 0 || VF_DBG_EPI == 4) && gm < M && col_ok)
-                            *reinterpret_cast<uint4*>(obase + (size_t(gm) * ep.ldo + n) * esz + ch * 16) = val;
-                    }
-                    if (Cfg::EPI_BUFS == 1) __syncwarp();      // the same 4 KB is rewritten by the next slice
                 }
                 ++it;
             }
@@ -438,7 +414,7 @@ EncodeTiledFn get_encode_tiled() {
 }
 
 template <int BN, int STAGES, int NSPLIT, bool SPLIT = false>
-int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmO2,
                      const GemmEpi& ep, int M,
                      int N, const ConvGeom& cg, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, STAGES, NSPLIT>;
@@ -455,8 +431,8 @@ int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
     const int pairs = device_sm_count() / 2;
     const int grid = 2 * (tiles < pairs ? tiles : pairs);
-    VF_CUDA(launch_pdl(gemm_f16_pair_kernel<BN, STAGES, NSPLIT, SPLIT>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream,
-                       tmA, tmB, tmO, ep, M, N, cg));
+    gemm_f16_pair_kernel<BN, STAGES, NSPLIT, SPLIT><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, tmO2, ep, M, N, cg);
+    VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
 
@@ -502,31 +478,31 @@ struct GemmProf {
 };
 static thread_local GemmProf g_prof;
 
-static int run_gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+static int run_gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmO2,
                            int bn, const GemmEpi& ep,
                            int M, int N, const ConvGeom& cg, cudaStream_t stream) {
     if (ep.split_off > 0 && !ep.out_f32) {
         if (cg.nsplit == 2) {
-            if (bn == 256) return launch_gemm_pair<256, 4, 2, true>(tmA, tmB, tmO, ep, M, N, cg, stream);
-            if (bn == 192) return launch_gemm_pair<192, 4, 2, true>(tmA, tmB, tmO, ep, M, N, cg, stream);
-            if (bn == 128) return launch_gemm_pair<128, 6, 2, true>(tmA, tmB, tmO, ep, M, N, cg, stream);
-            return launch_gemm_pair<64, 8, 2, true>(tmA, tmB, tmO, ep, M, N, cg, stream);
+            if (bn == 256) return launch_gemm_pair<256, 4, 2, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+            if (bn == 192) return launch_gemm_pair<192, 4, 2, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+            if (bn == 128) return launch_gemm_pair<128, 6, 2, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+            return launch_gemm_pair<64, 8, 2, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
         }
-        if (bn == 256) return launch_gemm_pair<256, 5, 1, true>(tmA, tmB, tmO, ep, M, N, cg, stream);
-        if (bn == 192) return launch_gemm_pair<192, 5, 1, true>(tmA, tmB, tmO, ep, M, N, cg, stream);
-        if (bn == 128) return launch_gemm_pair<128, 6, 1, true>(tmA, tmB, tmO, ep, M, N, cg, stream);
-        return launch_gemm_pair<64, 8, 1, true>(tmA, tmB, tmO, ep, M, N, cg, stream);
+        if (bn == 256) return launch_gemm_pair<256, 5, 1, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+        if (bn == 192) return launch_gemm_pair<192, 5, 1, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+        if (bn == 128) return launch_gemm_pair<128, 6, 1, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+        return launch_gemm_pair<64, 8, 1, true>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
     }
     if (cg.nsplit == 2) {
-        if (bn == 256) return launch_gemm_pair<256, 4, 2>(tmA, tmB, tmO, ep, M, N, cg, stream);
-        if (bn == 192) return launch_gemm_pair<192, 4, 2>(tmA, tmB, tmO, ep, M, N, cg, stream);
-        if (bn == 128) return launch_gemm_pair<128, 6, 2>(tmA, tmB, tmO, ep, M, N, cg, stream);
-        return launch_gemm_pair<64, 8, 2>(tmA, tmB, tmO, ep, M, N, cg, stream);
+        if (bn == 256) return launch_gemm_pair<256, 4, 2>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+        if (bn == 192) return launch_gemm_pair<192, 4, 2>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+        if (bn == 128) return launch_gemm_pair<128, 6, 2>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+        return launch_gemm_pair<64, 8, 2>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
     }
-    if (bn == 256) return launch_gemm_pair<256, VF_STAGES_256, 1>(tmA, tmB, tmO, ep, M, N, cg, stream);
-    if (bn == 192) return launch_gemm_pair<192, 5, 1>(tmA, tmB, tmO, ep, M, N, cg, stream);
-    if (bn == 128) return launch_gemm_pair<128, 6, 1>(tmA, tmB, tmO, ep, M, N, cg, stream);
-    return launch_gemm_pair<64, 8, 1>(tmA, tmB, tmO, ep, M, N, cg, stream);
+    if (bn == 256) return launch_gemm_pair<256, VF_STAGES_256, 1>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+    if (bn == 192) return launch_gemm_pair<192, 5, 1>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+    if (bn == 128) return launch_gemm_pair<128, 6, 1>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
+    return launch_gemm_pair<64, 8, 1>(tmA, tmB, tmO, tmO2, ep, M, N, cg, stream);
 }
 
 static int run_gemm(const CUtensorMap& tmA, const __half* B, int ldb, int64_t Ktot, int M, int N, const ConvGeom& cg,
@@ -544,16 +520,19 @@ static int run_gemm(const CUtensorMap& tmA, const __half* B, int ldb, int64_t Kt
             if (padded < best) { best = padded; bn = cand; }
         }
     }
-    CUtensorMap tmB, tmO;
+    CUtensorMap tmB, tmO, tmO2;
     VF_TRY(make_tmap_2d(&tmB, B, 2, uint64_t(N), uint64_t(Ktot), uint64_t(ldb) * 2, uint32_t(bn / 2), BK));
     const uint64_t ncols = uint64_t(N);     // (N % 8 == 0: a store view narrower than a 16-byte multiple corrupts its neighbours)
     if (ep.out_f32) VF_TRY(make_tmap_2d(&tmO, ep.out, 4, uint64_t(M), ncols, uint64_t(ep.ldo) * 4, STORE_ROWS, 32));
     else            VF_TRY(make_tmap_2d(&tmO, ep.out, 2, uint64_t(M), ncols, uint64_t(ep.ldo) * 2, STORE_ROWS, 64));
-    if (ep.split_off) {     // second view of the output rows: the lo halves (written through a pointer offset)
+    tmO2 = tmO;
+    if (ep.split_off) {     // second view of the output rows: the lo halves, both views clip at N columns
         if (ep.out_f32 || ep.split_off < N || ep.split_off % 8)
             return fail(VF_ERR_INVALID, "gemm: split output needs fp16 out and split_off >= N, multiple of 8");
+        VF_TRY(make_tmap_2d(&tmO2, static_cast<__half*>(ep.out) + ep.split_off, 2, uint64_t(M), ncols,
+                            uint64_t(ep.ldo) * 2, STORE_ROWS, 64));
     }
-    if (!g_prof.on) return run_gemm_launch(tmA, tmB, tmO, bn, ep, M, N, cg, stream);
+    if (!g_prof.on) return run_gemm_launch(tmA, tmB, tmO, tmO2, bn, ep, M, N, cg, stream);
     if (g_prof.used + 2 > g_prof.ev.size())
         for (int i = 0; i < 2; ++i) {
             cudaEvent_t e;
@@ -561,7 +540,7 @@ static int run_gemm(const CUtensorMap& tmA, const __half* B, int ldb, int64_t Kt
             g_prof.ev.push_back(e);
         }
     VF_CUDA(cudaEventRecord(g_prof.ev[g_prof.used], stream));
-    const int st = run_gemm_launch(tmA, tmB, tmO, bn, ep, M, N, cg, stream);
+    const int st = run_gemm_launch(tmA, tmB, tmO, tmO2, bn, ep, M, N, cg, stream);
     VF_CUDA(cudaEventRecord(g_prof.ev[g_prof.used + 1], stream));
     g_prof.used += 2;
     double kexec = double(Ktot);

@@ -10,8 +10,6 @@
 #include <tuple>
 #include <vector>
 
-#include <stdlib.h>
-
 #include "internal.h"
 
 namespace vf {
@@ -124,11 +122,6 @@ static int get_dev_coefs(int in_size, int out_size, int filter, cudaStream_t s, 
     g_coef_cache[key] = d;
     *out = d;
     return VF_OK;
-}
-
-bool pdl_enabled() {
-    static const bool on = []() { const char* e = getenv("VF_NO_PDL"); return !(e && e[0] == '1'); }();
-    return on;
 }
 
 int resize_u8(const uint8_t* src, int n, int in_h, int in_w, uint8_t* dst, int out_h, int out_w, int filter,

@@ -5,7 +5,6 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
-#include <string.h>
 #include <string>
 
 #include "../../include/vfeat.h"
@@ -28,25 +27,6 @@ int fail(int code, const char* fmt, ...);
         int _s = (expr);              \
         if (_s != VF_OK) return _s;   \
     } while (0)
-
-// ---- kernel launch with programmatic dependent launch (common.cuh: pdl_wait / pdl_trigger).  VF_NO_PDL=1 launches
-// plainly (full stream serialisation), for A/B runs.
-bool pdl_enabled();
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-}
 
 // ---- tensor maps (driver entry point fetched at run time; the library does not link libcuda).
 // 2-D row-major tensor of 2- or 4-byte elements, 128-byte-swizzled boxes of box_rows x (128 / elem_bytes) columns.

@@ -24,8 +24,6 @@ __device__ __forceinline__ float clip_norm(uint8_t v, int c) {
 // One thread: 16 pixels (48 B in, 3 x 32 B out).
 __global__ void clip_patchify_u8_kernel(const uint8_t* __restrict__ src, int n, int src_h, int src_w, int cy, int cx,
                                         __half* __restrict__ out) {
-    pdl_wait();
-    pdl_trigger();
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t total = int64_t(n) * 224 * 14;
     if (idx >= total) return;
@@ -60,8 +58,6 @@ __global__ void clip_patchify_u8_kernel(const uint8_t* __restrict__ src, int n, 
 
 // fp32 CHW frames (already transformed, what encode_image receives) -> fp16 patch matrix. 8 px / thread.
 __global__ void clip_patchify_f32_kernel(const float* __restrict__ src, int n, __half* __restrict__ out) {
-    pdl_wait();
-    pdl_trigger();
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t total = int64_t(n) * 3 * 224 * 28;
     if (idx >= total) return;
@@ -138,8 +134,6 @@ __device__ __forceinline__ void ln768_write(const Row768& r, int lane, const flo
 __global__ void __launch_bounds__(256, 6) add_layernorm768_kernel(float* __restrict__ x, int64_t row_stride,
                                         const __half* __restrict__ y, int64_t y_row_stride, int write_x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                         void* out, int64_t out_row_stride, int out_f32, int rows) {
-    pdl_wait();
-    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + warp;
     if (row >= rows) return;
@@ -171,8 +165,6 @@ __global__ void __launch_bounds__(256, 6) add_layernorm768_kernel(float* __restr
 __global__ void __launch_bounds__(256, 6) embed_layernorm768_kernel(const float* __restrict__ emb, const float* __restrict__ pos,
                                           const float* __restrict__ cls_pos0, const float* __restrict__ gamma,
                                           const float* __restrict__ beta, float* __restrict__ x, int rows) {
-    pdl_wait();
-    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + warp;
     if (row >= rows) return;
@@ -229,8 +221,6 @@ __global__ void __launch_bounds__(128) attention50_kernel(const __half* __restri
     __shared__ __align__(16) __half Vs[64][ATT_LD];   // [key][dim]
     const int frame = blockIdx.x / heads, head = blockIdx.x % heads;
     const int width = heads * ATT_D;
-    pdl_wait();
-    pdl_trigger();
     const int ld = 3 * width;
     const int64_t row0 = int64_t(frame) * ATT_S;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -452,13 +442,14 @@ inline unsigned blocks_for(int64_t total, int threads) { return unsigned((total 
 int launch_clip_patchify(const uint8_t* src, int n, int src_h, int src_w, int crop_y, int crop_x, __half* patches,
                          cudaStream_t s) {
     const int64_t total = int64_t(n) * 224 * 14;
-    VF_CUDA(launch_pdl(clip_patchify_u8_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, s, src, n, src_h, src_w, crop_y, crop_x,
-                       patches));
+    clip_patchify_u8_kernel<<<blocks_for(total, 256), 256, 0, s>>>(src, n, src_h, src_w, crop_y, crop_x, patches);
+    VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
 int launch_clip_patchify_f32(const float* src_chw, int n, __half* patches, cudaStream_t s) {
     const int64_t total = int64_t(n) * 3 * 224 * 28;
-    VF_CUDA(launch_pdl(clip_patchify_f32_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, s, src_chw, n, patches));
+    clip_patchify_f32_kernel<<<blocks_for(total, 256), 256, 0, s>>>(src_chw, n, patches);
+    VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
 int launch_clip_normalize_f32(const uint8_t* src, int n, int src_h, int src_w, int crop_y, int crop_x, float* dst_chw,
@@ -472,20 +463,22 @@ int launch_add_layernorm(float* x, int64_t x_row_stride, const __half* y, int64_
                          const float* gamma, const float* beta, void* out, int64_t out_row_stride, int out_f32, int rows,
                          cudaStream_t s) {
     const int warps = 8;
-    VF_CUDA(launch_pdl(add_layernorm768_kernel, dim3((rows + warps - 1) / warps), dim3(warps * 32), 0, s, x, x_row_stride, y,
-                       y_row_stride, write_x, gamma, beta, out, out_row_stride, out_f32, rows));
+    add_layernorm768_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, s>>>(x, x_row_stride, y, y_row_stride, write_x,
+                                                                             gamma, beta, out, out_row_stride, out_f32, rows);
+    VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
 int launch_embed_layernorm(const float* emb, const float* pos, const float* cls_pos0, const float* gamma,
                            const float* beta, float* x, int n_frames, cudaStream_t s) {
     const int warps = 8, rows = n_frames * 50;
-    VF_CUDA(launch_pdl(embed_layernorm768_kernel, dim3((rows + warps - 1) / warps), dim3(warps * 32), 0, s, emb, pos, cls_pos0, gamma,
-                       beta, x, rows));
+    embed_layernorm768_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, s>>>(emb, pos, cls_pos0, gamma, beta, x, rows);
+    VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
 int launch_attention(const __half* qkv, __half* out, int n_frames, int tokens, int heads, cudaStream_t s) {
     if (tokens != ATT_S) return fail(VF_ERR_UNSUPPORTED, "attention: %d tokens (only 50 is built)", tokens);
-    VF_CUDA(launch_pdl(attention50_kernel, dim3(n_frames * heads), dim3(128), 0, s, qkv, out, heads));
+    attention50_kernel<<<n_frames * heads, 128, 0, s>>>(qkv, out, heads);
+    VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
 int launch_resample(const uint8_t* src, int n, int in_h, int in_w, uint8_t* tmp, uint8_t* dst, int out_h, int out_w,
