@@ -122,6 +122,11 @@ int vf_clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, int 
  * well.  Returns once the host frames have been consumed (and out_host, if given, is complete). */
 int vf_clip_encode_u8_host_dev(vf_clip_t* h, const uint8_t* frames_host, int n, int src_h, int src_w, float* out_dev,
                                float* out_host, void* stream);
+/* Diagnostics / parity tests: the attention half of resblock `layer` alone -- x: n_frames*50 x 768 fp16 (the ln_1 output),
+ * out: n_frames*50 x 768 fp16 = concat_heads(softmax(q k^T / 8) v) BEFORE the out-projection (third-party clip
+ * ResidualAttentionBlock.attention / nn.MultiheadAttention).  fused = 1: the QKV-projection + attention kernel the tower
+ * runs; fused = 0: QKV GEMM, then the stand-alone attention kernel. */
+int vf_clip_block_attention(vf_clip_t* h, int layer, const void* x, int n_frames, void* out, int fused, void* stream);
 /* number of kernels this library has launched on behalf of `h` so far (diagnostics / bench). */
 int64_t vf_clip_launch_count(const vf_clip_t* h);
 /* Roofline instrumentation for bench.py: while enabled, every tensor-core GEMM launch of `h` is bracketed by a

@@ -8,7 +8,7 @@ OBJ=build/obj
 mkdir -p $OBJ
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
 pids=()
-for f in kernels host clip i3d i3d_kernels raft raft_kernels; do
+for f in attn_gemm kernels host clip i3d i3d_kernels raft raft_kernels; do
   if [ ! -f $OBJ/$f.o ] || [ $SRC/$f.cu -nt $OBJ/$f.o ] || [ $SRC/common.cuh -nt $OBJ/$f.o ] || [ $SRC/internal.h -nt $OBJ/$f.o ]; then
     nvcc $FLAGS -c $SRC/$f.cu -o $OBJ/$f.o & pids+=($!)
   fi
@@ -21,7 +21,7 @@ for tag in "${!V[@]}"; do
 done
 for p in "${pids[@]}"; do wait $p; done
 for tag in "${!V[@]}"; do
-  nvcc -shared -o video_features_b200/libvfeat_$tag.so $OBJ/gemm_$tag.o $OBJ/kernels.o $OBJ/host.o $OBJ/clip.o $OBJ/i3d.o \
+  nvcc -shared -o video_features_b200/libvfeat_$tag.so $OBJ/gemm_$tag.o $OBJ/attn_gemm.o $OBJ/kernels.o $OBJ/host.o $OBJ/clip.o $OBJ/i3d.o \
        $OBJ/i3d_kernels.o $OBJ/raft.o $OBJ/raft_kernels.o
 done
 ls -la video_features_b200/libvfeat_*.so

@@ -105,6 +105,36 @@ def test_encode_with_outlier_channel_weights(cuda_device):
         eng.close()
 
 
+@pytest.mark.parametrize("n_frames", [1, 4, 5, 7, 23, 250])
+def test_fused_qkv_attention_vs_fp32_reference_and_split_path(tower, cuda_device, n_frames):
+    """The QKV-projection + attention kernel (one tile = 5 frames x 1 head on a CTA pair, the third frame straddling the
+    pair through distributed shared memory) against nn.MultiheadAttention's math in fp32, and against the split path (QKV
+    GEMM + stand-alone attention kernel).  Frame counts: single frame, below / at / above one 5-frame group, a ragged
+    last group, a full chunk."""
+    sd, eng = tower
+    g = torch.Generator().manual_seed(40 + n_frames)
+    x = torch.randn(n_frames * 50, 768, generator=g).half().to(cuda_device)
+    layer = 3
+    p = f"visual.transformer.resblocks.{layer}."
+    w, b = sd[p + "attn.in_proj_weight"].to(cuda_device), sd[p + "attn.in_proj_bias"].to(cuda_device)
+    qkv = x.float() @ w.half().float().t() + b                     # fp16 operands, fp32 accumulate, like the engine
+    q, k, v = (t.half().float().view(n_frames, 50, 12, 64).transpose(1, 2) for t in qkv.split(768, dim=1))
+    att = torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1)
+    ref = (att @ v).transpose(1, 2).reshape(n_frames * 50, 768)
+    fused = eng.block_attention(layer, x, fused=True)
+    split = eng.block_attention(layer, x, fused=False)
+    torch.cuda.synchronize()
+    for name, y in (("fused", fused), ("split", split)):
+        err = float((y.float() - ref).norm() / ref.norm())
+        mx = float((y.float() - ref).abs().max() / ref.abs().max())
+        print(f"{name} attention, {n_frames} frames: rel-L2 {err:.2e}, max-abs {mx:.2e}")
+        assert err < 1e-3 and mx < 2e-3, (name, err, mx)
+    # same arithmetic in both paths: identical up to the fp16 rounding of q, k, v (bit-identical in practice)
+    d = float((fused.float() - split.float()).abs().max())
+    print(f"fused vs split: max |diff| {d:.3e}, identical: {torch.equal(fused, split)}")
+    assert d <= 2e-3 * float(ref.abs().max())
+
+
 def test_encode_empty_and_single(tower, cuda_device):
     sd, eng = tower
     out = eng.encode_frames_u8(torch.empty((0, 224, 224, 3), dtype=torch.uint8, device=cuda_device))

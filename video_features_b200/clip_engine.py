@@ -111,6 +111,17 @@ class ClipEngine:
                                                    torch.cuda.current_stream().cuda_stream))
         return out
 
+    def block_attention(self, layer: int, x: torch.Tensor, fused: bool = True) -> torch.Tensor:
+        """Diagnostics: the attention half of resblock `layer` on x (n_frames*50, 768) fp16 -> (n_frames*50, 768) fp16,
+        before the out-projection; fused=False runs the QKV GEMM + stand-alone attention kernel instead."""
+        assert x.is_cuda and x.dtype == torch.float16 and x.dim() == 2 and x.shape[1] == 768 and x.shape[0] % 50 == 0
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            check(lib().vf_clip_block_attention(self._h, layer, x.data_ptr(), x.shape[0] // 50, out.data_ptr(), int(fused),
+                                                torch.cuda.current_stream().cuda_stream))
+        return out
+
     @property
     def launch_count(self) -> int:
         return int(lib().vf_clip_launch_count(self._h))

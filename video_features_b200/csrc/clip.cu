@@ -20,6 +20,9 @@ constexpr int W = 768, L = 12, H = 12, T = 50, P = 49, MLPW = 3072, E = 512, PK 
 struct ClipLayerDev {
     float *ln1_w, *ln1_b, *ln2_w, *ln2_b, *b_qkv, *b_o, *b_fc, *b_proj;
     __half *w_qkv, *w_o, *w_fc, *w_proj;
+    // in_proj regrouped per head ([q_h | k_h | v_h] rows contiguous) for the fused QKV + attention kernel
+    __half* w_qkv_heads;
+    float* b_qkv_heads;
 };
 
 }  // namespace vf
@@ -73,6 +76,7 @@ struct vf_clip {
     cudaEvent_t ev_in = nullptr;
     bool use_graph = true;
     bool acc_o = true, acc_m = true;          // residual adds in the GEMM epilogue (TMA reduction) instead of an fp16 y
+    bool fused_attn = true;                   // QKV projection + attention in one kernel (VF_CLIP_ATTN=split: GEMM + kernel)
     float* feat = nullptr;                    // [chunk, 512] tower output of the active lane
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
@@ -167,6 +171,11 @@ static int tower_add_ln(vf_clip* h, float* x, int64_t x_stride, const __half* y,
     ProfScope p(h, 1, s);
     return launch_add_layernorm(x, x_stride, y, y_stride, write_x, g, b, out, ostride, 0, rows, s);
 }
+static int tower_qkv_attention(vf_clip* h, const ClipLayerDev& w, int c, cudaStream_t s) {
+    ProfScope p(h, 0, s);      // counted with the GEMMs: its FLOPs are the QKV projection's (+ the attention core)
+    if (h->prof) h->prof_flops += 2.0 * double(c) * T * double(3 * W) * double(W);
+    return qkv_attention(h->h, W, w.w_qkv_heads, w.b_qkv_heads, h->att, c, H, s);
+}
 static int tower_attention(vf_clip* h, int c, cudaStream_t s) {
     ProfScope p(h, 2, s);
     return launch_attention(h->qkv, h->att, c, T, H, s);
@@ -191,8 +200,12 @@ static int clip_tower_eager(vf_clip* h, int c, float* out, cudaStream_t s) {
         const ClipLayerDev& w = h->layer[l];
         // h = ln_1(x)   (y form: x += y of the previous block's MLP first)
         VF_TRY(tower_add_ln(h, h->x, W, (acc_m || l == 0) ? nullptr : h->y, W, 1, w.ln1_w, w.ln1_b, h->h, W, M, s));
-        VF_TRY(tower_gemm(h, h->h, W, w.w_qkv, W, M, 3 * W, W, epi(h->qkv, 3 * W, 0, w.b_qkv, VF_ACT_NONE), s));
-        VF_TRY(tower_attention(h, c, s));
+        if (h->fused_attn) {
+            VF_TRY(tower_qkv_attention(h, w, c, s));
+        } else {
+            VF_TRY(tower_gemm(h, h->h, W, w.w_qkv, W, M, 3 * W, W, epi(h->qkv, 3 * W, 0, w.b_qkv, VF_ACT_NONE), s));
+            VF_TRY(tower_attention(h, c, s));
+        }
         // Last block: only the CLS token reaches ln_post / proj (encode_image returns x[:, 0]), so after the attention
         // everything runs on the c CLS rows: A operands and the residual rows are strided views (row pitch 50*768), h /
         // mlp / y are compact c-row buffers.  Saves 49/50 of out-proj + MLP of this block (5.9 % of the FLOPs).
@@ -209,7 +222,7 @@ static int clip_tower_eager(vf_clip* h, int c, float* out, cudaStream_t s) {
         VF_TRY(tower_gemm(h, h->h, W, w.w_fc, W, rows, MLPW, W, epi(h->mlp, MLPW, 0, w.b_fc, VF_ACT_QUICKGELU), s));
         if (acc_m) VF_TRY(tower_gemm(h, h->mlp, MLPW, w.w_proj, MLPW, rows, W, MLPW, epi(h->x, a_ld, 1, w.b_proj, VF_ACT_NONE, 1), s));
         else       VF_TRY(tower_gemm(h, h->mlp, MLPW, w.w_proj, MLPW, rows, W, MLPW, epi(h->y, W, 0, w.b_proj, VF_ACT_NONE), s));
-        h->launches += 7;
+        h->launches += h->fused_attn ? 6 : 7;
     }
     // CLS rows: (y form: x += y of the last MLP;) ln_post; then the 768 -> 512 projection
     VF_TRY(tower_add_ln(h, h->x, int64_t(T) * W, acc_m ? nullptr : h->y, W, 0, h->lnpost_w, h->lnpost_b, h->cls, W, c, s));
@@ -218,7 +231,7 @@ static int clip_tower_eager(vf_clip* h, int c, float* out, cudaStream_t s) {
     return VF_OK;
 }
 
-constexpr int TOWER_LAUNCHES = 2 + 7 * L + 2;
+constexpr int TOWER_LAUNCHES_SPLIT = 2 + 7 * L + 2, TOWER_LAUNCHES_FUSED = 2 + 6 * L + 2;
 
 // Tower on one chunk: replay (capturing on first use) the CUDA graph for this chunk size, then copy the features out.
 static int clip_tower_chunk(vf_clip* h, int c, float* out, cudaStream_t s) {
@@ -242,7 +255,7 @@ static int clip_tower_chunk(vf_clip* h, int c, float* out, cudaStream_t s) {
     }
     VF_CUDA(cudaGraphLaunch(it->second, s));
     VF_CUDA(cudaMemcpyAsync(out, h->feat, size_t(c) * E * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    h->launches += TOWER_LAUNCHES;
+    h->launches += h->fused_attn ? TOWER_LAUNCHES_FUSED : TOWER_LAUNCHES_SPLIT;
     return VF_OK;
 }
 
@@ -366,6 +379,19 @@ int vf_clip_create(vf_clip_t** out, const vf_clip_weights* w, int device, int ch
             VF_TRY(upload_f32(h, &d.b_fc, s.c_fc_b, MLPW));
             VF_TRY(upload_f32(h, &d.b_proj, s.c_proj_b, W));
             VF_TRY(upload_f16(h, &d.w_qkv, s.in_proj_w, 3 * W, W, false));
+            {
+                if (!s.in_proj_w || !s.in_proj_b) return fail(VF_ERR_INVALID, "clip_create: missing weight tensor");
+                std::vector<float> wp(size_t(3) * W * W), bp(3 * W);
+                for (int hd = 0; hd < H; ++hd)
+                    for (int part = 0; part < 3; ++part)
+                        for (int dd = 0; dd < 64; ++dd) {
+                            const size_t src = size_t(part) * W + hd * 64 + dd, dst = size_t(hd) * 192 + part * 64 + dd;
+                            memcpy(&wp[dst * W], &s.in_proj_w[src * W], W * sizeof(float));
+                            bp[dst] = s.in_proj_b[src];
+                        }
+                VF_TRY(upload_f16(h, &d.w_qkv_heads, wp.data(), 3 * W, W, false));
+                VF_TRY(upload_f32(h, &d.b_qkv_heads, bp.data(), 3 * W));
+            }
             VF_TRY(upload_f16(h, &d.w_o, s.out_proj_w, W, W, false));
             VF_TRY(upload_f16(h, &d.w_fc, s.c_fc_w, MLPW, W, false));
             VF_TRY(upload_f16(h, &d.w_proj, s.c_proj_w, W, MLPW, false));
@@ -399,6 +425,8 @@ int vf_clip_create(vf_clip_t** out, const vf_clip_weights* w, int device, int ch
             const char* r = getenv("VF_CLIP_RESID");     // acc (default) | y | mix (reduction for the MLP only)
             h->acc_o = !(r && (r[0] == 'y' || r[0] == 'm'));
             h->acc_m = !(r && r[0] == 'y');
+            const char* a = getenv("VF_CLIP_ATTN");
+            h->fused_attn = !(a && a[0] == 's');
         }
         activate(h, 0);
         VF_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -543,6 +571,21 @@ int vf_clip_encode_u8_host_dev(vf_clip_t* h, const uint8_t* frames_host, int n, 
                                float* out_host, void* stream) {
     if (n > 0 && !out_dev) return fail(VF_ERR_INVALID, "clip_encode_u8_host_dev: null device output");
     return clip_encode_u8_host(h, frames_host, n, src_h, src_w, out_host, out_dev, stream);
+}
+
+int vf_clip_block_attention(vf_clip_t* h, int layer, const void* x, int n_frames, void* out, int fused, void* stream) {
+    if (!h || !x || !out) return fail(VF_ERR_INVALID, "clip_block_attention: null argument");
+    if (layer < 0 || layer >= L || n_frames <= 0 || n_frames > h->chunk)
+        return fail(VF_ERR_INVALID, "clip_block_attention: layer %d / %d frames outside the handle's limits", layer, n_frames);
+    VF_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const ClipLayerDev& w = h->layer[layer];
+    const __half* xin = static_cast<const __half*>(x);
+    __half* o = static_cast<__half*>(out);
+    if (fused) return qkv_attention(xin, W, w.w_qkv_heads, w.b_qkv_heads, o, n_frames, H, s);
+    __half* qkv = h->lanes[0].qkv;
+    VF_TRY(gemm_f16(xin, W, w.w_qkv, W, n_frames * T, 3 * W, W, epi(qkv, 3 * W, 0, w.b_qkv, VF_ACT_NONE), s));
+    return launch_attention(qkv, o, n_frames, T, H, s);
 }
 
 int64_t vf_clip_launch_count(const vf_clip_t* h) { return h ? h->launches : 0; }

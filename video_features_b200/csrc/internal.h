@@ -72,6 +72,10 @@ struct ConvGeom {
 // X: [P, C] fp16 (row pitch C), Wt: [N, ntaps*k_per_tap] fp16, output rows = P
 int conv_gemm_f16(const __half* X, int C, int64_t P, const __half* Wt, int N, const ConvGeom& g, const GemmEpi& ep,
                   cudaStream_t stream);
+// ---- QKV projection fused with the 50-token attention (csrc/attn_gemm.cu): h [n_frames*50, 768] fp16 -> att [.., heads*64]
+// w_perm: in_proj rows regrouped per head, row h*192 + part*64 + d = in_proj row part*768 + h*64 + d (bias likewise)
+int qkv_attention(const __half* h, int lda, const __half* w_perm, const float* bias_perm, __half* att, int n_frames, int heads,
+                  cudaStream_t stream);
 int device_sm_count();
 int gemm_profile(int enable);
 bool gemm_profile_on();   // event-bracketed launches cannot be captured into a graph: callers fall back to eager
