@@ -15,11 +15,14 @@
 // 6 rows of the next group that are computed and ignored).  Frame 2 straddles the pair: each CTA pushes its k / v rows of
 // that frame into the peer's staging buffer through distributed shared memory, and each handles the queries it owns.
 //
-// Warp roles per CTA (16 warps): 0 TMA producer, 1 MMA issuer (leader CTA), 2 TMEM allocator, 3 idle,
-// 4..15 epilogue: warp e = (TMEM lane quarter e & 3, part e >> 2 in {q, k, v}):
-//   phase 1  tcgen05.ld of its 32 rows x 64 columns -> + bias -> fp16 -> staging row (and the peer's halo for frame 2)
-//   phase 2  one 16-query m-tile of one frame per warp (10 per CTA): S = Q K^T on mma.sync m16n8k16, softmax in the
-//            accumulator fragments (fp32), O = P V, O through the unit's own Q rows, 16-byte global stores.
+// Warp roles per CTA (16 warps).  The epilogue is a two-stage pipeline over two staging buffers, so that the attention of
+// tile i, the staging of tile i+1 and the main loop of tile i+2 run at the same time (in-kernel timeline, profiles/r2:
+// with one set of warps doing both phases in turn a tile cost 13.4 k cycles against 4.6 k of main loop):
+//   0      TMA producer                      1   MMA issuer (leader CTA) + TMEM allocation
+//   4..7   loaders, one per TMEM lane quarter: tcgen05.ld of their 32 rows x 192 columns -> + bias -> fp16 -> staging row
+//          (and the peer's halo for the straddling frame), then release the accumulator stage
+//   2, 3, 8..15   attention warps: one 16-query m-tile of one frame per warp (10 per CTA): S = Q K^T on mma.sync m16n8k16,
+//          softmax in the accumulator fragments (fp32), O = P V, O through the unit's own Q rows, 16-byte global stores.
 // Numerics are those of attention50_kernel (fp16 q / k / v / P, fp32 scores and accumulation).
 #include <string.h>
 
@@ -32,16 +35,17 @@ namespace vf {
 
 namespace {
 
-constexpr int BM = 128, BK = 64, BN = 192, STAGES = 5;
+constexpr int BM = 128, BK = 64, BN = 192, STAGES = 3;
 constexpr int FRAMES_PER_TILE = 5, TOK = 50, TILE_ROWS = FRAMES_PER_TILE * TOK;   // 250
-constexpr int EPI_WARPS = 12, THREADS = (4 + EPI_WARPS) * 32;
+constexpr int LOADERS = 4, ATT_WARPS = 10, THREADS = 16 * 32;
 constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = (BN / 2) * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int PITCH = 200;                        // halfs per staging row: 192 + 8 (16-byte shift per row: conflict-free ldmatrix)
 constexpr int ROW0 = 28;                          // staging row of the CTA's local row 0 (rows 0..27: halo of CTA 1)
-constexpr int STG_ROWS = 192;                     // 28 + 128 + 22 halo rows of CTA 0 + 14 zero rows read by the last P.V step
-constexpr uint32_t STG_BYTES = STG_ROWS * PITCH * 2;
-constexpr uint32_t BAR_BYTES = (2 * STAGES + 4 + 2) * 8 + 16;
-constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;
+constexpr int STG_ROWS = 178;                     // 28 + 128 + 22 halo rows of CTA 0
+constexpr uint32_t STG_BYTES = STG_ROWS * PITCH * 2;          // one staging buffer (there are two)
+constexpr uint32_t ZERO_BYTES = 128, BIAS_BYTES = 2 * BN * 4;     // bias of the tile's head: one copy per tile parity
+constexpr uint32_t BAR_BYTES = (2 * STAGES + 4 + 4) * 8 + 16;
+constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STG_BYTES + ZERO_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
 constexpr uint32_t TMEM_COLS = 512, ACC_STRIDE = 256;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
@@ -83,7 +87,9 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 // one attention unit: 16 query rows (staging rows qrow0..qrow0+15) against the 50 keys at staging rows krow0..krow0+49
 // S: [row][q 0..63 | k 64..127 | v 128..191] fp16.  The result replaces the q columns of the unit's first `nvalid` rows (the
 // rows behind them belong to the next frame: they are read, their results discarded, and they are never written).
-__device__ __forceinline__ void attention_unit(__half* S, int qrow0, int krow0, int nvalid, int lane) {
+// `zero`: 128 bytes of zeros: key / value rows past the frame's 50 tokens are read from there (their scores are masked and
+// their probabilities 0, but 0 x an arbitrary bit pattern must stay 0).
+__device__ __forceinline__ void attention_unit(__half* S, const __half* zero, int qrow0, int krow0, int nvalid, int lane) {
     const int g = lane >> 2, t = lane & 3;
     uint32_t aq[4][4];
 #pragma unroll
@@ -95,7 +101,8 @@ __device__ __forceinline__ void attention_unit(__half* S, int qrow0, int krow0, 
 #pragma unroll
         for (int kp = 0; kp < 2; ++kp) {
             uint32_t bk[4];
-            ldsm_x4(bk, S + (krow0 + nt * 8 + (lane & 7)) * PITCH + 64 + kp * 32 + (lane >> 3) * 8);
+            const int kr = nt * 8 + (lane & 7);
+            ldsm_x4(bk, kr < TOK ? S + (krow0 + kr) * PITCH + 64 + kp * 32 + (lane >> 3) * 8 : zero);
             mma16816(s[nt], aq[2 * kp], bk[0], bk[1]);
             mma16816(s[nt], aq[2 * kp + 1], bk[2], bk[3]);
         }
@@ -149,7 +156,8 @@ __device__ __forceinline__ void attention_unit(__half* S, int qrow0, int krow0, 
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {     // keys 50..63 carry probability 0; their v rows hold finite values (see header)
             uint32_t bv[4];
-            ldsm_x4_trans(bv, S + (krow0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + 128 + np * 16 + (lane >> 4) * 8);
+            const int vr = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+            ldsm_x4_trans(bv, vr < TOK ? S + (krow0 + vr) * PITCH + 128 + np * 16 + (lane >> 4) * 8 : zero);
             mma16816(o0, pa[kk], bv[0], bv[1]);
             mma16816(o1, pa[kk], bv[2], bv[3]);
         }
@@ -165,6 +173,18 @@ __device__ __forceinline__ void attention_unit(__half* S, int qrow0, int krow0, 
     __syncwarp();
 }
 
+#ifdef VF_DBG_TRACE
+// SM-clock stamps of the leader CTA's attention warp 8 per tile (scripts/attn_trace.py): [pair][tile iteration][slot]
+//   3 tile staged (stg_full passed)   4 attention unit done   5 output stored / tile done
+// and of its loader warp 4:   0 accumulator ready   1 staging buffer free   2 rows staged, accumulator released
+__device__ long long g_attn_trace[74][64][8];
+#define ATR(slot) do { if (cta == 0 && warp == 8 && lane == 0 && titer < 63) g_attn_trace[pair][titer][slot] = clock64(); } while (0)
+#define LTR(slot) do { if (cta == 0 && warp == 4 && lane == 0 && titer < 63) g_attn_trace[pair][titer][slot] = clock64(); } while (0)
+#else
+#define ATR(slot) do { } while (0)
+#define LTR(slot) do { } while (0)
+#endif
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 qkv_attention_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const float* __restrict__ bias, __half* __restrict__ att, const int n_frames, const int heads) {
@@ -172,17 +192,20 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
-    __half* S = reinterpret_cast<__half*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + STG_BYTES);
+    uint8_t* stg = smem + STAGES * STAGE_BYTES;                         // two staging buffers, then 128 B of zeros
+    __half* zero = reinterpret_cast<__half*>(stg + 2 * STG_BYTES);
+    float* sbias = reinterpret_cast<float*>(stg + 2 * STG_BYTES + ZERO_BYTES);      // [tile parity][192]
+    uint64_t* full = reinterpret_cast<uint64_t*>(stg + 2 * STG_BYTES + ZERO_BYTES + BIAS_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
-    uint64_t* halo_full = tempty + 2;     // the peer's k / v rows of the straddling frame have landed in MY staging buffer
-    uint64_t* halo_free = halo_full + 1;  // the PEER has finished reading the halo I wrote into ITS staging buffer
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(halo_free + 1);
+    uint64_t* stg_full = tempty + 2;      // [2] q/k/v of the tile are staged in buffer b, the peer's halo rows included
+    uint64_t* stg_free = stg_full + 2;    // [2] nobody reads buffer b any more: neither this CTA nor (its halo) the peer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_free + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta = cluster_ctarank();
+    const uint32_t peer = cta ^ 1u;
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
     const int num_m = (n_frames + FRAMES_PER_TILE - 1) / FRAMES_PER_TILE;
     const int num_tiles = num_m * heads;
@@ -192,24 +215,22 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-    }
-    if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 2 * EPI_WARPS);
+            mbar_init(&tempty[i], 2 * LOADERS);          // the loader warps of both CTAs arrive on the LEADER's copy
+            mbar_init(&stg_full[i], LOADERS + 32);       // 4 local loader warps + every lane of the peer's halo-writing loader
+            mbar_init(&stg_free[i], 2 * ATT_WARPS);      // the attention warps of both CTAs
         }
-        mbar_init(halo_full, 2 * 32);        // every lane of the peer's two writer warps (k part, v part) arrives
-        mbar_init(halo_free, EPI_WARPS);     // every epilogue warp of the peer arrives once its attention units are done
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
-    // rows never written by a tile (zero padding read by the last P.V key step) -- and everything else once, so that no
-    // uninitialised bit pattern is ever multiplied by a zero probability
-    for (uint32_t i = threadIdx.x; i < STG_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(S)[i] = make_uint4(0, 0, 0, 0);
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    // staging rows a tile never writes are read (masked) by neighbouring units: no uninitialised bit patterns anywhere
+    for (uint32_t i = threadIdx.x; i < (2 * STG_BYTES + ZERO_BYTES) / 16; i += THREADS)
+        reinterpret_cast<uint4*>(stg)[i] = make_uint4(0, 0, 0, 0);
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
@@ -257,105 +278,140 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp >= 4) {
-        const int e = warp - 4;
-        const int q = e & 3;                   // TMEM lane quarter (== warp id % 4)
-        const int part = e >> 2;               // 0 q, 1 k, 2 v
+    } else if (warp >= 4 && warp < 8) {
+        // ------------------------------------------------------------ loaders: accumulator -> (+ bias) -> fp16 -> staging
+        const int q = warp - 4;                // TMEM lane quarter (== warp id % 4)
         const int lrow = q * 32 + lane;        // row inside this CTA's 128-row block == TMEM lane
-        const uint32_t peer = cta ^ 1u;
         // the straddling frame (index 2 of the tile): CTA 0 owns its tokens 0..27 (local rows 100..127), CTA 1 its tokens
         // 28..49 (local rows 0..21).  k / v of those rows are ALSO written into the peer's staging buffer:
         //   CTA 0 -> peer rows 0..27   (the peer's frame-2 keys start at staging row 0)
         //   CTA 1 -> peer rows 156..177 (CTA 0's frame-2 keys start at staging row 128 = ROW0 + 100)
         const bool halo_row = cta == 0 ? (lrow >= 100) : (lrow < 22);
         const int halo_dst = cta == 0 ? (lrow - 100) : (ROW0 + 128 + lrow);
-        const bool halo_writer = part != 0 && (cta == 0 ? q == 3 : q == 0);      // the warps that own such rows
+        const bool halo_writer = cta == 0 ? q == 3 : q == 0;       // the one loader of this CTA that owns such rows
         int acc = 0;
-        uint32_t acc_phase = 0, tile_par = 0;
-        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-            const int m_blk = tile % num_m, head = tile / num_m;
+        uint32_t acc_phase = 0;
+        for (int tile = pair, titer = 0; tile < num_tiles; tile += num_pairs, ++titer) {
+            const int head = tile / num_m;
+            const int b = titer & 1;
+            const uint32_t bpar = uint32_t(titer >> 1) & 1u;
+            __half* S = reinterpret_cast<__half*>(stg + b * STG_BYTES);
+            // this tile's 192 bias values into shared memory (then read as broadcasts).  Every loader writes the same values
+            // into the copy of this tile's parity and reads after its own __syncwarp; loaders are never more than one tile
+            // apart (a buffer is re-staged only after all four staged it two tiles ago), so two copies suffice.  The global
+            // loads are in flight while the warp waits for the accumulator.
+            float* mybias = sbias + b * BN;
+#pragma unroll
+            for (int j = 0; j < BN / 32; ++j) mybias[lane + 32 * j] = __ldg(bias + head * BN + lane + 32 * j);
+            __syncwarp();
             mbar_wait(&tfull[acc], acc_phase);
+            LTR(0);
             tc_fence_after();
-            // every warp of this CTA has finished the previous tile's attention: the staging rows may be overwritten
-            named_bar_sync(1, EPI_WARPS * 32);
-            // ... and the peer has finished reading the halo this CTA wrote last time
-            if (halo_writer) mbar_wait_cluster(halo_free, tile_par ^ 1);
-            // ---- phase 1: accumulator -> (+ bias) -> fp16 -> staging
-            const uint32_t t_row = tmem_base + acc * ACC_STRIDE + (uint32_t(q * 32) << 16) + part * 64;
-            __half* srow = S + (ROW0 + lrow) * PITCH + part * 64;
-            const float* b = bias + head * BN + part * 64;
+            // buffer b: the attention warps of BOTH CTAs are done with what was staged there two tiles ago
+            mbar_wait_cluster(&stg_free[b], bpar ^ 1);
+            LTR(1);
+            const uint32_t t_row = tmem_base + acc * ACC_STRIDE + (uint32_t(q * 32) << 16);
+            __half* srow = S + (ROW0 + lrow) * PITCH;
+            // q: columns 0..63, k: 64..127, v: 128..191.  Three 32-column TMEM loads are in flight per wait: under a busy
+            // tensor pipe a single tcgen05.ld takes ~1000 cycles to come back (timeline, profiles/r2), and the four loader
+            // warps are the stage that bounds the tile period.
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 96) {
+                uint32_t raw[3][32];
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                uint32_t raw[32];
-                tmem_ld_32x32(t_row + hh * 32, raw);
+                for (int u = 0; u < 3; ++u) tmem_ld_32x32(t_row + c0 + 32 * u, raw[u]);
                 tmem_ld_wait();
-                uint4 pk[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + hh * 32 + 8 * j));
-                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(b + hh * 32 + 8 * j + 4));
-                    pk[j] = make_uint4(pack_half2(__uint_as_float(raw[8 * j]) + b0.x, __uint_as_float(raw[8 * j + 1]) + b0.y),
-                                       pack_half2(__uint_as_float(raw[8 * j + 2]) + b0.z, __uint_as_float(raw[8 * j + 3]) + b0.w),
-                                       pack_half2(__uint_as_float(raw[8 * j + 4]) + b1.x, __uint_as_float(raw[8 * j + 5]) + b1.y),
-                                       pack_half2(__uint_as_float(raw[8 * j + 6]) + b1.z, __uint_as_float(raw[8 * j + 7]) + b1.w));
-                    *reinterpret_cast<uint4*>(srow + hh * 32 + 8 * j) = pk[j];
-                }
-                if (halo_writer && halo_row) {
-                    const uint32_t dst = smem_u32(S + halo_dst * PITCH + part * 64 + hh * 32);
+                for (int u = 0; u < 3; ++u) {
+                    const int c = c0 + 32 * u;
+                    uint4 pk[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) st_cluster_v4(dst + 16 * j, peer, pk[j]);
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 b0 = *reinterpret_cast<const float4*>(mybias + c + 8 * j);
+                        const float4 b1 = *reinterpret_cast<const float4*>(mybias + c + 8 * j + 4);
+                        pk[j] = make_uint4(pack_half2(__uint_as_float(raw[u][8 * j]) + b0.x, __uint_as_float(raw[u][8 * j + 1]) + b0.y),
+                                           pack_half2(__uint_as_float(raw[u][8 * j + 2]) + b0.z, __uint_as_float(raw[u][8 * j + 3]) + b0.w),
+                                           pack_half2(__uint_as_float(raw[u][8 * j + 4]) + b1.x, __uint_as_float(raw[u][8 * j + 5]) + b1.y),
+                                           pack_half2(__uint_as_float(raw[u][8 * j + 6]) + b1.z, __uint_as_float(raw[u][8 * j + 7]) + b1.w));
+                        *reinterpret_cast<uint4*>(srow + c + 8 * j) = pk[j];
+                    }
+                    if (halo_writer && halo_row && c >= 64) {
+                        const uint32_t dst = smem_u32(S + halo_dst * PITCH + c);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) st_cluster_v4(dst + 16 * j, peer, pk[j]);
+                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_remote(&tempty[acc], 0);     // this accumulator stage is drained
-            if (halo_writer) mbar_arrive_remote(halo_full, peer);   // every lane: its own remote rows are released
-            named_bar_sync(2, EPI_WARPS * 32);                      // q, k, v of this CTA's rows are staged
-            mbar_wait_cluster(halo_full, tile_par);                 // ... and the peer's rows of the straddling frame
-            // ---- phase 2: attention units (one 16-query m-tile each); CTA 0: frames 0, 1 + tokens 0..27 of frame 2,
-            //      CTA 1: tokens 28..49 of frame 2 + frames 3, 4
-            if (e < 10) {
-                int f, tok0, qrow0, krow0;      // frame in tile, first query token, staging rows of the queries / keys
-                if (cta == 0) {
-                    if (e < 8) { f = e >> 2; tok0 = (e & 3) * 16; krow0 = ROW0 + 50 * f; }
-                    else       { f = 2; tok0 = (e - 8) * 16; krow0 = ROW0 + 100; }
-                    qrow0 = krow0 + tok0;
-                } else {
-                    if (e < 2) { f = 2; tok0 = 28 + e * 16; krow0 = 0; }
-                    else       { f = 3 + ((e - 2) >> 2); tok0 = ((e - 2) & 3) * 16; krow0 = 50 * (f - 2); }
-                    qrow0 = krow0 + tok0;
-                }
-                const int tok_end = (cta == 0 && f == 2) ? 28 : TOK;       // queries this CTA owns in that frame
-                const int frame = m_blk * FRAMES_PER_TILE + f;
-                attention_unit(S, qrow0, krow0, tok_end - tok0, lane);
-                if (frame < n_frames) {
-                    __half* orow = att + (int64_t(frame) * TOK) * width + head * 64;
+            if (lane == 0) {
+                mbar_arrive_remote(&tempty[acc], 0);      // this accumulator stage is drained
+                mbar_arrive(&stg_full[b]);                // this warp's 32 rows are staged (release: the warp's writes)
+            }
+            if (halo_writer) mbar_arrive_remote(&stg_full[b], peer);   // every lane releases its own remote rows
+            LTR(2);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp == 2 || warp == 3 || warp >= 8) {
+        // ------------------------------------------------------------ attention: one 16-query m-tile of one frame per warp
+        const int e = warp < 4 ? warp - 2 : warp - 6;         // unit 0..9
+        // CTA 0: frames 0, 1 + tokens 0..27 of frame 2;  CTA 1: tokens 28..49 of frame 2 + frames 3, 4
+        int f, tok0, krow0;       // frame in tile, first query token, staging row of the frame's token 0
+        if (cta == 0) {
+            if (e < 8) { f = e >> 2; tok0 = (e & 3) * 16; krow0 = ROW0 + 50 * f; }
+            else       { f = 2; tok0 = (e - 8) * 16; krow0 = ROW0 + 100; }
+        } else {
+            if (e < 2) { f = 2; tok0 = 28 + e * 16; krow0 = 0; }
+            else       { f = 3 + ((e - 2) >> 2); tok0 = ((e - 2) & 3) * 16; krow0 = 50 * (f - 2); }
+        }
+        const int qrow0 = krow0 + tok0;
+        const int tok_end = (cta == 0 && f == 2) ? 28 : TOK;       // queries this CTA owns in that frame
+        for (int tile = pair, titer = 0; tile < num_tiles; tile += num_pairs, ++titer) {
+            const int m_blk = tile % num_m, head = tile / num_m;
+            const int b = titer & 1;
+            const uint32_t bpar = uint32_t(titer >> 1) & 1u;
+            __half* S = reinterpret_cast<__half*>(stg + b * STG_BYTES);
+            mbar_wait_cluster(&stg_full[b], bpar);                  // own rows staged + the peer's rows of the straddling frame
+            ATR(3);
+            attention_unit(S, zero, qrow0, krow0, tok_end - tok0, lane);
+            ATR(4);
+            const int frame = m_blk * FRAMES_PER_TILE + f;
+            if (frame < n_frames) {
+                __half* orow = att + (int64_t(frame) * TOK) * width + head * 64;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = i * 4 + (lane >> 3), seg = lane & 7;
-                        const int tok = tok0 + r;
-                        if (tok < tok_end)
-                            *reinterpret_cast<uint4*>(orow + int64_t(tok) * width + seg * 8) =
-                                *reinterpret_cast<const uint4*>(S + (qrow0 + r) * PITCH + seg * 8);
-                    }
+                for (int i = 0; i < 4; ++i) {
+                    const int r = i * 4 + (lane >> 3), seg = lane & 7;
+                    const int tok = tok0 + r;
+                    if (tok < tok_end)
+                        *reinterpret_cast<uint4*>(orow + int64_t(tok) * width + seg * 8) =
+                            *reinterpret_cast<const uint4*>(S + (qrow0 + r) * PITCH + seg * 8);
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive_remote(halo_free, peer);      // this warp no longer reads the halo the peer wrote
-            tile_par ^= 1;
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            ATR(5);
+            if (lane == 0) {                      // buffer b is free as far as this warp is concerned: tell both loaders' CTAs
+                mbar_arrive(&stg_free[b]);
+                mbar_arrive_remote(&stg_free[b], peer);
+            }
         }
     }
 
     tc_fence_before();
     cluster_sync_all();
-    if (warp == 2) {
+    if (warp == 1) {
         tc_fence_after();
         tmem_dealloc_2sm(tmem_base, TMEM_COLS);
     }
 }
 
 }  // namespace
+
+#ifdef VF_DBG_TRACE
+extern "C" int vf_dbg_attn_trace(long long* host_out) {
+    cudaDeviceSynchronize();
+    return int(cudaMemcpyFromSymbol(host_out, g_attn_trace, sizeof(g_attn_trace)));
+}
+#endif
 
 // h: [n_frames*50, 768] fp16 (row pitch lda); w_perm: [heads*192, 768] fp16, row h*192 + part*64 + d = in_proj row
 // part*768 + h*64 + d; bias_perm likewise (fp32); att: [n_frames*50, heads*64] fp16
