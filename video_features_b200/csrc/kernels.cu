@@ -128,12 +128,17 @@ __device__ __forceinline__ void ln768_write(const Row768& r, int lane, const flo
     }
 }
 
-// residual-stream update fused with the following LayerNorm:  x += y (the previous GEMM's output, fp16: it is a
-// small residual-branch increment, so its 2^-11 rounding is far below the fp16 operand rounding of the GEMMs; x
-// itself stays fp32), out = LN(x)
-__global__ void __launch_bounds__(256, 6) add_layernorm768_kernel(float* __restrict__ x, int64_t row_stride,
+// LayerNorm of the residual stream, optionally fused with its update:  HAS_Y: x += y first (y = the previous GEMM's
+// output as an fp16 increment; x itself stays fp32), out = LN(x).  Without y (the GEMM epilogue already added its result
+// into x with a TMA reduction) a pass reads 4 and writes 2 bytes per element.  Compile-time variants: the plain one keeps
+// no y registers live and fits 6 blocks of 8 warps per SM without spilling.
+#ifndef VF_LN_BLOCKS
+#define VF_LN_BLOCKS 5      // resident blocks per SM the register allocation targets (6 spills 40 bytes per thread)
+#endif
+template <bool HAS_Y, bool OUT_F32>
+__global__ void __launch_bounds__(256, VF_LN_BLOCKS) add_layernorm768_kernel(float* __restrict__ x, int64_t row_stride,
                                         const __half* __restrict__ y, int64_t y_row_stride, int write_x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                        void* out, int64_t out_row_stride, int out_f32, int rows) {
+                                        void* out, int64_t out_row_stride, int rows) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + warp;
     if (row >= rows) return;
@@ -141,7 +146,7 @@ __global__ void __launch_bounds__(256, 6) add_layernorm768_kernel(float* __restr
     Row768 r;
 #pragma unroll
     for (int i = 0; i < 6; ++i) r.v[i] = *reinterpret_cast<const float4*>(xr + (lane + 32 * i) * 4);
-    if (y != nullptr) {
+    if (HAS_Y) {
         const __half* yr = y + int64_t(row) * y_row_stride;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
@@ -155,9 +160,9 @@ __global__ void __launch_bounds__(256, 6) add_layernorm768_kernel(float* __restr
             for (int i = 0; i < 6; ++i) *reinterpret_cast<float4*>(xr + (lane + 32 * i) * 4) = r.v[i];
         }
     }
-    void* orow = out_f32 ? static_cast<void*>(reinterpret_cast<float*>(out) + int64_t(row) * out_row_stride)
+    void* orow = OUT_F32 ? static_cast<void*>(reinterpret_cast<float*>(out) + int64_t(row) * out_row_stride)
                          : static_cast<void*>(reinterpret_cast<__half*>(out) + int64_t(row) * out_row_stride);
-    ln768_write(r, lane, gamma, beta, orow, out_f32);
+    ln768_write(r, lane, gamma, beta, orow, OUT_F32 ? 1 : 0);
 }
 
 // ViT token assembly fused with ln_pre: row (frame, t): t == 0 -> class_embedding + pos[0] (precomputed),
@@ -463,8 +468,12 @@ int launch_add_layernorm(float* x, int64_t x_row_stride, const __half* y, int64_
                          const float* gamma, const float* beta, void* out, int64_t out_row_stride, int out_f32, int rows,
                          cudaStream_t s) {
     const int warps = 8;
-    add_layernorm768_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, s>>>(x, x_row_stride, y, y_row_stride, write_x,
-                                                                             gamma, beta, out, out_row_stride, out_f32, rows);
+    const dim3 grid((rows + warps - 1) / warps), block(warps * 32);
+#define VF_LN(HY, F32) add_layernorm768_kernel<HY, F32><<<grid, block, 0, s>>>(x, x_row_stride, y, y_row_stride, write_x, gamma, \
+                                                                             beta, out, out_row_stride, rows)
+    if (y != nullptr) { if (out_f32) VF_LN(true, true); else VF_LN(true, false); }
+    else              { if (out_f32) VF_LN(false, true); else VF_LN(false, false); }
+#undef VF_LN
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
