@@ -38,6 +38,10 @@ namespace {
 constexpr int BM = 128, BK = 64, BN = 192, STAGES = 3;
 constexpr int FRAMES_PER_TILE = 5, TOK = 50, TILE_ROWS = FRAMES_PER_TILE * TOK;   // 250
 constexpr int LOADERS = 4, ATT_WARPS = 10, THREADS = 16 * 32;
+#ifndef VF_ATTN_LOADER_WARP0
+#define VF_ATTN_LOADER_WARP0 4       // loaders = warps 4..7 (2..5 also satisfies warp % 4 == TMEM lane quarter)
+#endif
+constexpr int LOADER_WARP0 = VF_ATTN_LOADER_WARP0;
 constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = (BN / 2) * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int PITCH = 200;                        // halfs per staging row: 192 + 8 (16-byte shift per row: conflict-free ldmatrix)
 constexpr int ROW0 = 28;                          // staging row of the CTA's local row 0 (rows 0..27: halo of CTA 1)
@@ -178,8 +182,8 @@ __device__ __forceinline__ void attention_unit(__half* S, const __half* zero, in
 //   3 tile staged (stg_full passed)   4 attention unit done   5 output stored / tile done
 // and of its loader warp 4:   0 accumulator ready   1 staging buffer free   2 rows staged, accumulator released
 __device__ long long g_attn_trace[74][64][8];
-#define ATR(slot) do { if (cta == 0 && warp == 8 && lane == 0 && titer < 63) g_attn_trace[pair][titer][slot] = clock64(); } while (0)
-#define LTR(slot) do { if (cta == 0 && warp == 4 && lane == 0 && titer < 63) g_attn_trace[pair][titer][slot] = clock64(); } while (0)
+#define ATR(slot) do { if (cta == 0 && warp == 9 && lane == 0 && titer < 63) g_attn_trace[pair][titer][slot] = clock64(); } while (0)
+#define LTR(slot) do { if (cta == 0 && warp == LOADER_WARP0 && lane == 0 && titer < 63) g_attn_trace[pair][titer][slot] = clock64(); } while (0)
 #else
 #define ATR(slot) do { } while (0)
 #define LTR(slot) do { } while (0)
@@ -278,9 +282,9 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp >= LOADER_WARP0 && warp < LOADER_WARP0 + 4) {
         // ------------------------------------------------------------ loaders: accumulator -> (+ bias) -> fp16 -> staging
-        const int q = warp - 4;                // TMEM lane quarter (== warp id % 4)
+        const int q = warp & 3;                // TMEM lane quarter (== warp id % 4)
         const int lrow = q * 32 + lane;        // row inside this CTA's 128-row block == TMEM lane
         // the straddling frame (index 2 of the tile): CTA 0 owns its tokens 0..27 (local rows 100..127), CTA 1 its tokens
         // 28..49 (local rows 0..21).  k / v of those rows are ALSO written into the peer's staging buffer:
@@ -352,9 +356,9 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             LTR(2);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-    } else if (warp == 2 || warp == 3 || warp >= 8) {
+    } else if (warp >= 2) {
         // ------------------------------------------------------------ attention: one 16-query m-tile of one frame per warp
-        const int e = warp < 4 ? warp - 2 : warp - 6;         // unit 0..9
+        const int e = warp < LOADER_WARP0 ? warp - 2 : warp - 6;      // unit 0..9 (the 10 warps that are not loaders)
         // CTA 0: frames 0, 1 + tokens 0..27 of frame 2;  CTA 1: tokens 28..49 of frame 2 + frames 3, 4
         int f, tok0, krow0;       // frame in tile, first query token, staging row of the frame's token 0
         if (cta == 0) {

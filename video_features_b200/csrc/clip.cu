@@ -172,8 +172,7 @@ static int tower_add_ln(vf_clip* h, float* x, int64_t x_stride, const __half* y,
     return launch_add_layernorm(x, x_stride, y, y_stride, write_x, g, b, out, ostride, 0, rows, s);
 }
 static int tower_qkv_attention(vf_clip* h, const ClipLayerDev& w, int c, cudaStream_t s) {
-    ProfScope p(h, 0, s);      // counted with the GEMMs: its FLOPs are the QKV projection's (+ the attention core)
-    if (h->prof) h->prof_flops += 2.0 * double(c) * T * double(3 * W) * double(W);
+    ProfScope p(h, 2, s);      // its own category: QKV projection + attention core in one kernel
     return qkv_attention(h->h, W, w.w_qkv_heads, w.b_qkv_heads, h->att, c, H, s);
 }
 static int tower_attention(vf_clip* h, int c, cudaStream_t s) {
