@@ -454,6 +454,19 @@ def run_engine(args, rank: int, world: int, local_rank: int) -> None:
     # configs[4], every N), I3D rgb (configs[2], N = 1) and RAFT -> I3D flow (configs[3], N = 1 and its 2-GPU form)
     if not args.no_secondary:
         sec = {}
+        # watchdog: the secondary workloads contain collectives; if one ever hangs, the headline line (already complete)
+        # is still emitted and every rank leaves -- a secondary line never takes the headline down with it
+        import threading
+
+        def _bail():
+            line["secondary"] = dict(sec, error="timeout: secondary workloads did not finish within 420 s")
+            if rank == 0:
+                emit(line)
+            os._exit(0)
+
+        watchdog = threading.Timer(420.0, _bail)
+        watchdog.daemon = True
+        watchdog.start()
         for name, fn, ok in (("c5_video_list", lambda: run_c5(args, rank, world, local_rank, quick=True), True),
                              ("i3d_rgb", lambda: run_i3d(args, quick=True), world == 1),
                              ("raft_i3d_flow", lambda: run_raft(args, rank, world, local_rank, quick=True), world <= 2)):
@@ -463,6 +476,7 @@ def run_engine(args, rank: int, world: int, local_rank: int) -> None:
                 sec[name] = fn()
             except BaseException as err:               # a secondary line never takes the headline down with it
                 sec[name] = {"error": f"{type(err).__name__}: {err}"}
+        watchdog.cancel()
         line["secondary"] = sec
     if rank == 0:
         emit(line)
