@@ -170,12 +170,17 @@ static int prepare_unit(vf_i3d* h, ConvUnit& u, const vf_conv_unit& src, int idx
         return fail(VF_ERR_UNSUPPORTED, "i3d_create: unit %d has kernel size %d", idx, k);
     }
     if (u.k_per_tap % 8) return fail(VF_ERR_UNSUPPORTED, "i3d_create: unit %d: %d channels per tap", idx, u.k_per_tap);
-    // hi+lo weights on every layer.  (A single-pass stem measured +24 % stacks/s but moved the trained-checkpoint
-    // parity from 8.1e-4 / 6.1e-4 (rel-L2 / max) to 8.9e-4 / 1.1e-3 at T=16 -- over the max-abs bar -- so it stays
-    // split; VF_I3D_STEM_SINGLE=1 selects it.)
+    // Weight precision per layer: hi + lo fp16 pairs (two MMA passes per K step, ~22 mantissa bits) except where a CPU
+    // emulation of the trained checkpoints shows single fp16 weights to be harmless (scripts/precision/
+    // emulate_i3d_weights.py: rgb / flow, uniform-noise clips, 4 seeds): the stem and the four 3x3x3 convs of stage 3
+    // (mixed_3b / 3c branch_1.1, branch_2.1 -- 61 of the 222 GFLOP) move the feature error from 1.6..3.7e-4 to 3.1..4.3e-4
+    // rel-L2 (max-abs <= 6.0e-4); the 3x3x3 convs of stage 4 or conv3d_2c would take it to 5.4..6.8e-4 with max-abs at the
+    // 1e-3 bar, so they stay split.  VF_I3D_SINGLE=none keeps every layer split, VF_I3D_FAST=1 makes every layer single.
     {
-        const char* e = getenv("VF_I3D_STEM_SINGLE");
-        u.nsplit = (k == 7 && e && e[0] == '1') ? 1 : h->nsplit;
+        const char* e = getenv("VF_I3D_SINGLE");
+        const bool none = e && e[0] == 'n';
+        const bool chosen = k == 7 || idx == 5 || idx == 7 || idx == 11 || idx == 13;
+        u.nsplit = (h->nsplit == 2 && chosen && !none) ? 1 : h->nsplit;
         if (u.nsplit != 2) u.lo_mask = 0;
     }
     const size_t Kb = size_t(u.ntaps) * u.k_per_tap, Kt = Kb * u.nsplit;
