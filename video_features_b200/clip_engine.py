@@ -9,7 +9,7 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, ops  # noqa: F401  (ops registers torch.ops.vfeat.*)
 from ._lib import ClipWeights, check, lib
 
 _LAYER_KEYS = {
@@ -59,28 +59,23 @@ class ClipEngine:
         self._h = h
         del keep
 
+    @property
+    def handle(self) -> int:
+        """The vf_clip_t* as an integer: what the torch.ops.vfeat.clip_* custom ops take."""
+        return int(self._h.value)
+
     # ---- model.encode_image(frames) : frames (T,3,224,224) float on this device
     def encode_image(self, frames: torch.Tensor) -> torch.Tensor:
         if not frames.is_cuda:
             raise RuntimeError("encode_image expects CUDA frames (no CPU fallback)")
         frames = frames.to(torch.float32).contiguous()
         assert frames.dim() == 4 and tuple(frames.shape[1:]) == (3, 224, 224), frames.shape
-        out = torch.empty((frames.shape[0], 512), device=frames.device, dtype=torch.float32)
-        with torch.cuda.device(self.device):
-            check(lib().vf_clip_encode_f32(self._h, frames.data_ptr(), frames.shape[0], out.data_ptr(),
-                                           torch.cuda.current_stream().cuda_stream))
-        return out
+        return torch.ops.vfeat.clip_encode_image(self.handle, frames)          # PyTorch custom op over vf_clip_encode_f32
 
     # ---- fused preprocess + encode_image on raw decoder output: (T,H,W,3) uint8 on this device
     def encode_frames_u8(self, frames: torch.Tensor) -> torch.Tensor:
         assert frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3
-        frames = frames.contiguous()
-        n, hh, ww, _ = frames.shape
-        out = torch.empty((n, 512), device=frames.device, dtype=torch.float32)
-        with torch.cuda.device(self.device):
-            check(lib().vf_clip_encode_u8(self._h, frames.data_ptr(), n, hh, ww, out.data_ptr(),
-                                          torch.cuda.current_stream().cuda_stream))
-        return out
+        return torch.ops.vfeat.clip_encode_u8(self.handle, frames.contiguous())  # custom op over vf_clip_encode_u8
 
     # ---- same with host buffers (numpy / CPU tensors): H2D + tower + D2H, synchronous
     def encode_frames_u8_host(self, frames, out: Optional[torch.Tensor] = None) -> torch.Tensor:

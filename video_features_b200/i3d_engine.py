@@ -9,6 +9,7 @@ from typing import Dict
 import numpy as np
 import torch
 
+from . import ops  # noqa: F401  (registers torch.ops.vfeat.*)
 from ._lib import I3D_UNITS, I3DWeights, check, lib
 
 _MIXED = ["mixed_3b", "mixed_3c", "mixed_4b", "mixed_4c", "mixed_4d", "mixed_4e", "mixed_4f", "mixed_5b", "mixed_5c"]
@@ -66,11 +67,7 @@ class I3DEngine:
             raise RuntimeError("I3DEngine expects CUDA input (no CPU fallback)")
         x = x.to(torch.float32).contiguous()
         assert x.dim() == 5 and x.shape[1] == self.cin and tuple(x.shape[3:]) == (224, 224), x.shape
-        out = torch.empty((x.shape[0], 1024), device=x.device, dtype=torch.float32)
-        with torch.cuda.device(self.device):
-            check(lib().vf_i3d_forward_f32(self._h, x.data_ptr(), x.shape[0], x.shape[2], out.data_ptr(),
-                                           torch.cuda.current_stream().cuda_stream))
-        return out
+        return torch.ops.vfeat.i3d_forward(int(self._h.value), x)             # PyTorch custom op over vf_i3d_forward_f32
 
     def forward_frames_u8(self, frames: torch.Tensor) -> torch.Tensor:
         """rgb stream from resized uint8 frames (n, T, Hr, Wr, 3) on this device; crop/scale/permute fused."""

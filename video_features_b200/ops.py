@@ -65,6 +65,57 @@ def gemm_f16_accumulate(out: torch.Tensor, a: torch.Tensor, b: torch.Tensor, bia
                                            act, _stream()))
 
 
+# ----------------------------------------------------------------------------- encoders (handles are opaque int64 values)
+@torch.library.custom_op("vfeat::clip_encode_u8", mutates_args=())
+def clip_encode_u8(handle: int, frames: torch.Tensor) -> torch.Tensor:
+    """Fused CLIP transform + ViT-B/32 tower (vf_clip_encode_u8): (N,H,W,3) uint8 on the device -> (N,512) fp32.
+    `handle` is the vf_clip_t* of a ClipEngine (ClipEngine.handle)."""
+    _need_cuda(frames)
+    assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3
+    n, hh, ww, _ = frames.shape
+    out = torch.empty((n, 512), device=frames.device, dtype=torch.float32)
+    with torch.cuda.device(frames.device):
+        check(lib().vf_clip_encode_u8(C.c_void_p(handle), frames.data_ptr(), n, hh, ww, out.data_ptr(), _stream()))
+    return out
+
+
+@clip_encode_u8.register_fake
+def _(handle, frames):
+    return frames.new_empty((frames.shape[0], 512), dtype=torch.float32)
+
+
+@torch.library.custom_op("vfeat::clip_encode_image", mutates_args=())
+def clip_encode_image(handle: int, frames: torch.Tensor) -> torch.Tensor:
+    """`model.encode_image(frames)` (vf_clip_encode_f32): (N,3,224,224) fp32 on the device -> (N,512) fp32."""
+    _need_cuda(frames)
+    assert frames.dtype == torch.float32 and frames.dim() == 4 and tuple(frames.shape[1:]) == (3, 224, 224)
+    out = torch.empty((frames.shape[0], 512), device=frames.device, dtype=torch.float32)
+    with torch.cuda.device(frames.device):
+        check(lib().vf_clip_encode_f32(C.c_void_p(handle), frames.data_ptr(), frames.shape[0], out.data_ptr(), _stream()))
+    return out
+
+
+@clip_encode_image.register_fake
+def _(handle, frames):
+    return frames.new_empty((frames.shape[0], 512), dtype=torch.float32)
+
+
+@torch.library.custom_op("vfeat::i3d_forward", mutates_args=())
+def i3d_forward(handle: int, x: torch.Tensor) -> torch.Tensor:
+    """`I3D(x, features=True)` (vf_i3d_forward_f32): (B,C,T,224,224) fp32 in [-1,1] on the device -> (B,1024) fp32."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 5 and tuple(x.shape[3:]) == (224, 224)
+    out = torch.empty((x.shape[0], 1024), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(lib().vf_i3d_forward_f32(C.c_void_p(handle), x.data_ptr(), x.shape[0], x.shape[2], out.data_ptr(), _stream()))
+    return out
+
+
+@i3d_forward.register_fake
+def _(handle, x):
+    return x.new_empty((x.shape[0], 1024), dtype=torch.float32)
+
+
 # ----------------------------------------------------------------------------- transforms
 @torch.library.custom_op("vfeat::resize_u8", mutates_args=())
 def resize_u8(frames: torch.Tensor, out_h: int, out_w: int, filter: int) -> torch.Tensor:
