@@ -107,6 +107,10 @@ typedef struct vf_clip vf_clip_t;
 /* Uploads weights to `device` (fp16 GEMM operands, fp32 vectors) and allocates workspace for
  * chunks of `chunk_frames` frames (0 = default). */
 int vf_clip_create(vf_clip_t** out, const vf_clip_weights* w, int device, int chunk_frames);
+/* Same for the reference's other ViT-B feature type: patch_size 32 ('CLIP-ViT-B/32', identical to vf_clip_create) or 16
+ * ('CLIP-ViT-B/16': conv1_w is [768,3,16,16], positional_embedding [197,768]; same width, depth, heads and output size).
+ * Reference: models/CLIP/extract_clip.py:42-47 (clip.load(feature_type) for either name). */
+int vf_clip_create_vit(vf_clip_t** out, const vf_clip_weights* w, int device, int chunk_frames, int patch_size);
 int vf_clip_destroy(vf_clip_t* h);
 /* encode_image on n already-transformed frames: frames n x 3 x 224 x 224 fp32 (device) -> out n x 512 fp32. */
 int vf_clip_encode_f32(vf_clip_t* h, const float* frames, int n, float* out, void* stream);

@@ -10,12 +10,12 @@ import torch  # noqa: F401
 
 from video_features_b200.utils import form_list_from_user_input, sanity_check
 
-SUPPORTED = ['i3d', 'raft', 'CLIP-ViT-B/32', 'CLIP4CLIP-ViT-B-32']
+SUPPORTED = ['i3d', 'raft', 'CLIP-ViT-B/32', 'CLIP-ViT-B/16', 'CLIP4CLIP-ViT-B-32']
 
 
 def build_extractor(args):
     """feature_type -> extractor (main.py:15-41)."""
-    if args.feature_type in ['CLIP-ViT-B/32', 'CLIP4CLIP-ViT-B-32']:
+    if args.feature_type in ['CLIP-ViT-B/32', 'CLIP-ViT-B/16', 'CLIP4CLIP-ViT-B-32']:
         from video_features_b200.extract.extract_clip import ExtractCLIP
         return ExtractCLIP(args)
     if args.feature_type == 'i3d':
@@ -25,7 +25,7 @@ def build_extractor(args):
         from video_features_b200.extract.extract_raft import ExtractRAFT
         return ExtractRAFT(args)
     if args.feature_type in ['vggish', 'r21d_rgb', 'resnet18', 'resnet34', 'resnet50', 'resnet101', 'resnet152', 'pwc',
-                             'CLIP-ViT-B/16', 'vggish_torch']:
+                             'vggish_torch']:
         raise NotImplementedError(f'{args.feature_type}: outside the hot path this engine rebuilds (SURVEY.md §2)')
     raise NotADirectoryError                      # main.py:41
 

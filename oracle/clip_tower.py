@@ -35,7 +35,7 @@ EMBED = 512
 LN_EPS = 1e-5
 
 
-def synthetic_state_dict(seed: int = 0, dtype=torch.float32) -> "OrderedDict[str, torch.Tensor]":
+def synthetic_state_dict(seed: int = 0, dtype=torch.float32, patch: int = PATCH) -> "OrderedDict[str, torch.Tensor]":
     """Seeded synthetic weights in openai's ``visual.*`` key layout.
 
     Scales follow clip/model.py (VisionTransformer.__init__: ``scale = width**-0.5``
@@ -56,9 +56,9 @@ def synthetic_state_dict(seed: int = 0, dtype=torch.float32) -> "OrderedDict[str
     fc_std = (2 * WIDTH) ** -0.5
     sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
     sd["visual.class_embedding"] = rn(WIDTH, std=scale)
-    sd["visual.positional_embedding"] = rn(TOKENS, WIDTH, std=scale)
+    sd["visual.positional_embedding"] = rn((RES // patch) ** 2 + 1, WIDTH, std=scale)
     sd["visual.proj"] = rn(WIDTH, EMBED, std=scale)
-    sd["visual.conv1.weight"] = rn(WIDTH, 3, PATCH, PATCH, std=(3 * PATCH * PATCH) ** -0.5)
+    sd["visual.conv1.weight"] = rn(WIDTH, 3, patch, patch, std=(3 * patch * patch) ** -0.5)
     for name in ("ln_pre", "ln_post"):
         sd[f"visual.{name}.weight"] = 1.0 + rn(WIDTH, std=0.1)
         sd[f"visual.{name}.bias"] = rn(WIDTH, std=0.05)
@@ -117,8 +117,9 @@ def encode_image(sd: Dict[str, torch.Tensor], frames: torch.Tensor, *, return_hi
     """
     w = sd["visual.conv1.weight"]
     x = frames.to(w.dtype)
-    x = F.conv2d(x, w, None, stride=PATCH)                       # (B,768,7,7)
-    x = x.reshape(x.shape[0], x.shape[1], -1).permute(0, 2, 1)   # (B,49,768) row-major grid
+    patch = w.shape[-1]                                          # 32 (ViT-B/32) or 16 (ViT-B/16): conv stride == kernel
+    x = F.conv2d(x, w, None, stride=patch)                       # (B,768,7,7) / (B,768,14,14)
+    x = x.reshape(x.shape[0], x.shape[1], -1).permute(0, 2, 1)   # (B,49|196,768) row-major grid
     cls = sd["visual.class_embedding"].to(x.dtype).expand(x.shape[0], 1, -1)
     x = torch.cat([cls, x], dim=1) + sd["visual.positional_embedding"].to(x.dtype)
     x = _ln(x, sd["visual.ln_pre.weight"], sd["visual.ln_pre.bias"])

@@ -156,3 +156,87 @@ def test_resize_path_matches_pillow_then_oracle(tower, cuda_device):
     ref = clip_tower.encode_image(sd, _transform_224(torch.stack(tens)))
     y = eng.encode_frames_u8(frames.to(cuda_device))
     _check_rows(y, ref)
+
+
+# ---------------------------------------------------------------- ViT-B/16 (the reference's 'CLIP-ViT-B/16' feature type)
+@pytest.fixture(scope="module")
+def tower16(cuda_device):
+    from oracle import clip_tower
+    from video_features_b200.clip_engine import ClipEngine
+    sd = clip_tower.synthetic_state_dict(1, patch=16)
+    eng = ClipEngine(sd, device=0)
+    assert eng.patch == 16 and eng.tokens == 197
+    yield sd, eng
+    eng.close()
+
+
+def test_b16_encode_small_batch_vs_cpu_oracle(tower16, cuda_device):
+    from oracle import clip_tower
+    sd, eng = tower16
+    g = torch.Generator().manual_seed(2)
+    frames = torch.randint(0, 256, (5, 224, 224, 3), dtype=torch.uint8, generator=g)
+    ref = clip_tower.encode_image(sd, _transform_224(frames))            # fp32 on CPU
+    y_u8 = eng.encode_frames_u8(frames.to(cuda_device))
+    y_f32 = eng.encode_image(_transform_224(frames).to(cuda_device))
+    y_host = eng.encode_frames_u8_host(frames)
+    torch.cuda.synchronize()
+    _check_rows(y_u8, ref)
+    _check_rows(y_f32, ref)
+    assert torch.equal(y_u8.cpu(), y_f32.cpu()) and torch.equal(y_u8.cpu(), y_host)
+
+
+def test_b16_multi_chunk_vs_gpu_fp32_oracle(tower16, cuda_device):
+    """More frames than one chunk (63) and a ragged tail; the fp32 oracle runs on the GPU with TF32 off."""
+    from oracle import clip_tower
+    sd, eng = tower16
+    g = torch.Generator().manual_seed(7)
+    frames = torch.randint(0, 256, (150, 224, 224, 3), dtype=torch.uint8, generator=g)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd_dev = {k: v.to(cuda_device) for k, v in sd.items()}
+    ref = torch.cat([clip_tower.encode_image(sd_dev, _transform_224(frames[i:i + 50]).to(cuda_device))
+                     for i in range(0, 150, 50)])
+    y = eng.encode_frames_u8(frames.to(cuda_device))
+    torch.cuda.synchronize()
+    _check_rows(y, ref)
+
+
+def test_b16_attention_vs_fp32_reference(tower16, cuda_device):
+    """QKV GEMM + the 197-token attention kernel of block 0 against an fp32 computation on the same fp16 input."""
+    sd, eng = tower16
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = (torch.randn(3 * 197, 768, generator=g) * 0.8).to(torch.float16)
+    got = eng.block_attention(0, x.to(cuda_device), fused=False).float().cpu()
+    w = sd["visual.transformer.resblocks.0.attn.in_proj_weight"].to(torch.float16).float()
+    b = sd["visual.transformer.resblocks.0.attn.in_proj_bias"].float()
+    qkv = (x.float() @ w.t() + b).to(torch.float16).float().view(3, 197, 3, 12, 64)
+    q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))
+    att = torch.softmax((q * 0.125) @ k.transpose(-1, -2), dim=-1) @ v
+    ref = att.transpose(1, 2).reshape(3 * 197, 768)
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item(), err
+
+
+def test_b16_feature_type_through_extractor(cuda_device, tmp_path, monkeypatch):
+    """'CLIP-ViT-B/16' runs through ExtractCLIP (synthetic weights of that geometry) on the sample video and agrees
+    with the oracle on the same decoded frames."""
+    import argparse
+    import os
+    from oracle import clip_preprocess, clip_tower
+    from video_features_b200 import synthetic_weights, utils
+    from video_features_b200.extract.extract_clip import ExtractCLIP
+    monkeypatch.setenv("VF_CLIP_SYNTHETIC", "9")
+    video = os.path.join(os.path.dirname(__file__), "golden", "v_GGSY1Qvo990.mp4")
+    out = str(tmp_path / "out")
+    args = argparse.Namespace(feature_type='CLIP-ViT-B/16', video_paths=[video], flow_paths=None,
+                              file_with_video_paths=None, video_dir=None, flow_dir=None, extraction_fps=None,
+                              extract_method="uni_5", on_extraction='save_numpy', output_path=out, output_direct=True,
+                              tmp_path=os.path.join(out, 'tmp'))
+    ex = ExtractCLIP(args, external_call=True)
+    d = ex(torch.zeros([1], dtype=torch.long, device=cuda_device))[0]
+    feats = d['CLIP-ViT-B/16']
+    assert feats.shape == (5, 512)
+    frames, _, _ = utils.extract_frames(video, "uni_5")
+    sd = synthetic_weights.clip_vit_b32_state_dict(9, patch=16)
+    ref = clip_tower.encode_image(sd, clip_preprocess.preprocess_batch(frames))
+    _check_rows(torch.from_numpy(np.asarray(feats)), ref)

@@ -1,4 +1,4 @@
-"""CLIP ViT-B/32 image tower handle: the object that stands where the reference keeps the result of
+"""CLIP ViT-B image tower handle (patch 32 or 16): the object that stands where the reference keeps the result of
 ``clip.load("ViT-B/32", device)`` (models/CLIP/extract_clip.py:47) -- ``encode_image`` included.
 """
 from __future__ import annotations
@@ -25,7 +25,12 @@ _TOP_KEYS = {
     "positional_embedding": "positional_embedding", "ln_pre_w": "ln_pre.weight", "ln_pre_b": "ln_pre.bias",
     "ln_post_w": "ln_post.weight", "ln_post_b": "ln_post.bias", "proj": "proj",
 }
-_SHAPES = {"conv1_w": (768, 3, 32, 32), "class_embedding": (768,), "positional_embedding": (50, 768), "proj": (768, 512)}
+
+
+def _shapes(patch: int):
+    tokens = (224 // patch) ** 2 + 1
+    return {"conv1_w": (768, 3, patch, patch), "class_embedding": (768,), "positional_embedding": (tokens, 768),
+            "proj": (768, 512)}
 
 
 class ClipEngine:
@@ -37,6 +42,17 @@ class ClipEngine:
             raise RuntimeError("ClipEngine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device("cuda", device)
         keep = []     # keep numpy arrays alive across the create call
+        if "visual.conv1.weight" not in state_dict:
+            raise KeyError("CLIP checkpoint is missing 'visual.conv1.weight'")
+        patch = int(state_dict["visual.conv1.weight"].shape[-1])
+        if patch not in (32, 16):
+            raise ValueError(f"patch size {patch}: the ViT-B/32 and ViT-B/16 image towers are built")
+        n_blocks = len({k.split(".")[3] for k in state_dict if k.startswith("visual.transformer.resblocks.")})
+        if n_blocks != 12:
+            raise ValueError(f"{n_blocks} transformer blocks: only the 12-block, 768-wide ViT-B towers are built")
+        self.patch = patch
+        self.tokens = (224 // patch) ** 2 + 1
+        shapes = _shapes(patch)
 
         def arr(key: str, shape=None) -> C.POINTER(C.c_float):
             full = "visual." + key
@@ -44,18 +60,18 @@ class ClipEngine:
                 raise KeyError(f"CLIP checkpoint is missing '{full}'")
             a = np.ascontiguousarray(state_dict[full].detach().to("cpu", torch.float32).numpy())
             if shape is not None and tuple(a.shape) != tuple(shape):
-                raise ValueError(f"'{full}' has shape {a.shape}, ViT-B/32 needs {shape}")
+                raise ValueError(f"'{full}' has shape {a.shape}, ViT-B/{patch} needs {shape}")
             keep.append(a)
             return a.ctypes.data_as(C.POINTER(C.c_float))
 
         w = ClipWeights()
         for f, k in _TOP_KEYS.items():
-            setattr(w, f, arr(k, _SHAPES.get(f)))
+            setattr(w, f, arr(k, shapes.get(f)))
         for i in range(12):
             for f, k in _LAYER_KEYS.items():
                 setattr(w.layers[i], f, arr(f"transformer.resblocks.{i}.{k}"))
         h = C.c_void_p()
-        check(lib().vf_clip_create(C.byref(h), C.byref(w), device, chunk_frames))
+        check(lib().vf_clip_create_vit(C.byref(h), C.byref(w), device, chunk_frames, patch))
         self._h = h
         del keep
 
@@ -109,11 +125,12 @@ class ClipEngine:
     def block_attention(self, layer: int, x: torch.Tensor, fused: bool = True) -> torch.Tensor:
         """Diagnostics: the attention half of resblock `layer` on x (n_frames*50, 768) fp16 -> (n_frames*50, 768) fp16,
         before the out-projection; fused=False runs the QKV GEMM + stand-alone attention kernel instead."""
-        assert x.is_cuda and x.dtype == torch.float16 and x.dim() == 2 and x.shape[1] == 768 and x.shape[0] % 50 == 0
+        t = self.tokens
+        assert x.is_cuda and x.dtype == torch.float16 and x.dim() == 2 and x.shape[1] == 768 and x.shape[0] % t == 0
         x = x.contiguous()
         out = torch.empty_like(x)
         with torch.cuda.device(self.device):
-            check(lib().vf_clip_block_attention(self._h, layer, x.data_ptr(), x.shape[0] // 50, out.data_ptr(), int(fused),
+            check(lib().vf_clip_block_attention(self._h, layer, x.data_ptr(), x.shape[0] // t, out.data_ptr(), int(fused),
                                                 torch.cuda.current_stream().cuda_stream))
         return out
 

@@ -1,9 +1,10 @@
-// CLIP ViT-B/32 image tower on the tcgen05 GEMM + memory-bound kernels.
+// CLIP ViT-B image tower (patch 32: the north-star model; patch 16: the reference's 'CLIP-ViT-B/16' feature type, same
+// width / depth, 197 tokens) on the tcgen05 GEMM + memory-bound kernels.
 // Replaces `clip.load("ViT-B/32")` + `model.encode_image(frames)` (reference: models/CLIP/extract_clip.py:47,128;
 // algorithm: third-party openai/CLIP clip/model.py VisionTransformer.forward, restated in oracle/clip_tower.py).
 //
 // Numerics: GEMM operands fp16, accumulation fp32 (TMEM), residual stream / LayerNorm / softmax fp32.
-// Frames are packed along M (row = frame*50 + token), processed in chunks sized so that one chunk's
+// Frames are packed along M (row = frame*tokens + token), processed in chunks sized so that one chunk's
 // activations stay L2-resident between kernels.
 #include <stdlib.h>
 #include <string.h>
@@ -15,7 +16,7 @@
 
 namespace vf {
 
-constexpr int W = 768, L = 12, H = 12, T = 50, P = 49, MLPW = 3072, E = 512, PK = 3072;
+constexpr int W = 768, L = 12, H = 12, MLPW = 3072, E = 512;
 
 struct ClipLayerDev {
     float *ln1_w, *ln1_b, *ln2_w, *ln2_b, *b_qkv, *b_o, *b_fc, *b_proj;
@@ -30,10 +31,11 @@ struct ClipLayerDev {
 struct vf_clip {
     int device = 0;
     int chunk = 0;
+    int patch = 32, T = 50, P = 49, PK = 3072;   // patch size, tokens (P + 1), patches per frame, patch-matrix columns
     int64_t launches = 0;
     std::vector<void*> allocs;
     // weights
-    __half* w_patch = nullptr;   // [768, 3072]
+    __half* w_patch = nullptr;   // [768, PK]
     __half* w_proj = nullptr;    // [512, 768]  (proj^T)
     float *pos = nullptr, *cls_pos0 = nullptr, *lnpre_w = nullptr, *lnpre_b = nullptr, *lnpost_w = nullptr,
           *lnpost_b = nullptr;
@@ -164,7 +166,7 @@ static int tower_gemm(vf_clip* h, const __half* A, int lda, const __half* B, int
 }
 static int tower_embed_ln(vf_clip* h, int c, cudaStream_t s) {
     ProfScope p(h, 1, s);
-    return launch_embed_layernorm(h->emb, h->pos, h->cls_pos0, h->lnpre_w, h->lnpre_b, h->x, c, s);
+    return launch_embed_layernorm(h->emb, h->pos, h->cls_pos0, h->lnpre_w, h->lnpre_b, h->x, c, h->T, s);
 }
 static int tower_add_ln(vf_clip* h, float* x, int64_t x_stride, const __half* y, int64_t y_stride, int write_x,
                         const float* g, const float* b, void* out, int64_t ostride, int rows, cudaStream_t s) {
@@ -177,15 +179,16 @@ static int tower_qkv_attention(vf_clip* h, const ClipLayerDev& w, int c, cudaStr
 }
 static int tower_attention(vf_clip* h, int c, cudaStream_t s) {
     ProfScope p(h, 2, s);
-    return launch_attention(h->qkv, h->att, c, T, H, s);
+    return launch_attention(h->qkv, h->att, c, h->T, H, s);
 }
 
 // The tower on one chunk whose patch matrix is already in h->patches; writes c x 512 fp32 to out.
 // GEMM epilogues never read global memory: bias / QuickGELU in registers, then TMA stores -- or, for the two GEMMs that
 // end a residual branch, a TMA reduction that adds the tile into the fp32 residual stream x.
 static int clip_tower_eager(vf_clip* h, int c, float* out, cudaStream_t s) {
+    const int T = h->T, P = h->P, PK = h->PK;
     const int M = c * T;
-    // patch embedding: [c*49, 3072] x [768, 3072]^T -> emb (fp32)
+    // patch embedding: [c*P, PK] x [768, PK]^T -> emb (fp32)
     VF_TRY(tower_gemm(h, h->patches, PK, h->w_patch, PK, c * P, W, PK, epi(h->emb, W, 1, nullptr, VF_ACT_NONE), s));
     // token assembly (+ class / positional embedding) fused with ln_pre -> x
     VF_TRY(tower_embed_ln(h, c, s));
@@ -206,8 +209,8 @@ static int clip_tower_eager(vf_clip* h, int c, float* out, cudaStream_t s) {
             VF_TRY(tower_attention(h, c, s));
         }
         // Last block: only the CLS token reaches ln_post / proj (encode_image returns x[:, 0]), so after the attention
-        // everything runs on the c CLS rows: A operands and the residual rows are strided views (row pitch 50*768), h /
-        // mlp / y are compact c-row buffers.  Saves 49/50 of out-proj + MLP of this block (5.9 % of the FLOPs).
+        // everything runs on the c CLS rows: A operands and the residual rows are strided views (row pitch T*768), h /
+        // mlp / y are compact c-row buffers.  Saves (T-1)/T of out-proj + MLP of this block (5.9 % of the FLOPs at T = 50).
         const bool last = l + 1 == L;
         const int rows = last ? c : M;
         const int a_ld = last ? T * W : W;                    // row pitch of att / x when only the CLS rows are read
@@ -326,7 +329,7 @@ static int clip_transform_chunk(vf_clip* h, const uint8_t* frames, int c, int sr
         h->launches += (g.rh != src_h) + (g.rw != src_w);
         cur = h->resized; ch = g.rh; cw = g.rw;
     }
-    VF_TRY(launch_clip_patchify(cur, c, ch, cw, g.cy, g.cx, h->patches, s));
+    VF_TRY(launch_clip_patchify(cur, c, ch, cw, g.cy, g.cx, h->patches, h->patch, s));
     h->launches += 1;
     return VF_OK;
 }
@@ -338,9 +341,17 @@ using namespace vf;
 extern "C" {
 
 int vf_clip_create(vf_clip_t** out, const vf_clip_weights* w, int device, int chunk_frames) {
+    return vf_clip_create_vit(out, w, device, chunk_frames, 32);
+}
+
+int vf_clip_create_vit(vf_clip_t** out, const vf_clip_weights* w, int device, int chunk_frames, int patch_size) {
     if (!out || !w) return fail(VF_ERR_INVALID, "clip_create: null argument");
     *out = nullptr;
-    if (chunk_frames <= 0) chunk_frames = 256;   // up to 12800 token rows per GEMM launch, per lane
+    if (patch_size != 32 && patch_size != 16)
+        return fail(VF_ERR_UNSUPPORTED, "clip_create: patch size %d (ViT-B/32 and ViT-B/16 are built)", patch_size);
+    // default chunk: ~12.5 k token rows per GEMM launch (49 M-tiles of 256 rows: one wave of 74 CTA pairs is too few,
+    // the activations of one chunk still sit in the L2)
+    if (chunk_frames <= 0) chunk_frames = patch_size == 32 ? 256 : 126;
     if (chunk_frames > 4096) return fail(VF_ERR_INVALID, "clip_create: chunk_frames %d too large", chunk_frames);
     VF_CUDA(cudaSetDevice(device));
     int major = 0, minor = 0;
@@ -351,6 +362,11 @@ int vf_clip_create(vf_clip_t** out, const vf_clip_weights* w, int device, int ch
     vf_clip* h = new vf_clip();
     h->device = device;
     h->chunk = chunk_frames;
+    h->patch = patch_size;
+    h->P = (224 / patch_size) * (224 / patch_size);
+    h->T = h->P + 1;
+    h->PK = 3 * patch_size * patch_size;
+    const int T = h->T, P = h->P, PK = h->PK;
     int st = VF_OK;
     auto body = [&]() -> int {
         VF_TRY(upload_f16(h, &h->w_patch, w->conv1_w, W, PK, false));
@@ -425,7 +441,7 @@ int vf_clip_create(vf_clip_t** out, const vf_clip_weights* w, int device, int ch
             h->acc_o = !(r && (r[0] == 'y' || r[0] == 'm'));
             h->acc_m = !(r && r[0] == 'y');
             const char* a = getenv("VF_CLIP_ATTN");
-            h->fused_attn = !(a && a[0] == 's');
+            h->fused_attn = !(a && a[0] == 's') && T == 50;     // the fused kernel is built for 50-token frames
         }
         activate(h, 0);
         VF_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -479,7 +495,7 @@ int vf_clip_encode_f32(vf_clip_t* h, const float* frames, int n, float* out, voi
         const int c = (n - b0 < step) ? (n - b0) : step;
         LaneScope lane(h, i % h->n_lanes);
         cudaStream_t s = lane.s;
-        VF_TRY(launch_clip_patchify_f32(frames + size_t(b0) * 3 * 224 * 224, c, h->patches, s));
+        VF_TRY(launch_clip_patchify_f32(frames + size_t(b0) * 3 * 224 * 224, c, h->patches, h->patch, s));
         h->launches += 1;
         VF_TRY(clip_tower_chunk(h, c, out + size_t(b0) * E, s));
     }
@@ -576,6 +592,8 @@ int vf_clip_block_attention(vf_clip_t* h, int layer, const void* x, int n_frames
     if (!h || !x || !out) return fail(VF_ERR_INVALID, "clip_block_attention: null argument");
     if (layer < 0 || layer >= L || n_frames <= 0 || n_frames > h->chunk)
         return fail(VF_ERR_INVALID, "clip_block_attention: layer %d / %d frames outside the handle's limits", layer, n_frames);
+    if (fused && h->T != 50) return fail(VF_ERR_UNSUPPORTED, "clip_block_attention: the fused kernel needs 50-token frames");
+    const int T = h->T;
     VF_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const ClipLayerDev& w = h->layer[layer];

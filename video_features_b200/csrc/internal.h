@@ -82,18 +82,20 @@ bool gemm_profile_on();   // event-bracketed launches cannot be captured into a 
 int gemm_profile_read(double* ms, int64_t* launches, double* flops);
 
 // ---- elementwise / reduction kernels
+// patch = 32 (ViT-B/32: [n*49, 3072] patch rows) or 16 (ViT-B/16: [n*196, 768])
 int launch_clip_patchify(const uint8_t* src, int n, int src_h, int src_w, int crop_y, int crop_x, __half* patches,
-                         cudaStream_t s);
-int launch_clip_patchify_f32(const float* src_chw, int n, __half* patches, cudaStream_t s);
+                         int patch, cudaStream_t s);
+int launch_clip_patchify_f32(const float* src_chw, int n, __half* patches, int patch, cudaStream_t s);
 int launch_clip_normalize_f32(const uint8_t* src, int n, int src_h, int src_w, int crop_y, int crop_x, float* dst_chw,
                               cudaStream_t s);
 // x (+= y) ; out = LayerNorm(x) -- rows of 768 fp32.  y may be null; write_x stores the summed residual stream back.
 int launch_add_layernorm(float* x, int64_t x_row_stride, const __half* y, int64_t y_row_stride, int write_x,
                          const float* gamma, const float* beta, void* out, int64_t out_row_stride, int out_f32, int rows,
                          cudaStream_t s);
-// ViT embedding rows: token 0 = cls_pos0, token t>0 = emb[frame*49 + t-1] + pos[t]; x = ln_pre(row) (fp32)
+// ViT embedding rows: token 0 = cls_pos0, token t>0 = emb[frame*(tokens-1) + t-1] + pos[t]; x = ln_pre(row) (fp32)
 int launch_embed_layernorm(const float* emb, const float* pos, const float* cls_pos0, const float* gamma,
-                           const float* beta, float* x, int n_frames, cudaStream_t s);
+                           const float* beta, float* x, int n_frames, int tokens, cudaStream_t s);
+// self-attention per (frame, head) on a [n_frames*tokens, 3*heads*64] QKV matrix: tokens == 50 or 65..208
 int launch_attention(const __half* qkv, __half* out, int n_frames, int tokens, int heads, cudaStream_t s);
 int launch_resample(const uint8_t* src, int n, int in_h, int in_w, uint8_t* tmp, uint8_t* dst, int out_h, int out_w,
                     const int* kh_bounds, const int* kh_coef, int kh_size, const int* kv_bounds, const int* kv_coef,

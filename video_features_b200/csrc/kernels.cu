@@ -19,11 +19,13 @@ __device__ __forceinline__ float clip_norm(uint8_t v, int c) {
     return __fdiv_rn(__fsub_rn(__fdiv_rn(float(v), 255.0f), kClipMean[c]), kClipStd[c]);
 }
 
-// uint8 HWC frames (cropped window 224x224 at (cy,cx)) -> fp16 patch matrix [n*49, 3072],
-// column = c*1024 + ky*32 + kx  (the natural flattening of conv1.weight[768,3,32,32]).
-// One thread: 16 pixels (48 B in, 3 x 32 B out).
+// uint8 HWC frames (cropped window 224x224 at (cy,cx)) -> fp16 patch matrix [n*G*G, 3*PS*PS] (G = 224/PS patches a side:
+// [n*49, 3072] for ViT-B/32, [n*196, 768] for ViT-B/16), column = c*PS*PS + ky*PS + kx (the natural flattening of
+// conv1.weight[768,3,PS,PS]).  One thread: 16 pixels (48 B in, 3 x 32 B out).
+template <int PS>
 __global__ void clip_patchify_u8_kernel(const uint8_t* __restrict__ src, int n, int src_h, int src_w, int cy, int cx,
                                         __half* __restrict__ out) {
+    constexpr int G = 224 / PS, PP = PS * PS;
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t total = int64_t(n) * 224 * 14;
     if (idx >= total) return;
@@ -42,22 +44,24 @@ __global__ void clip_patchify_u8_kernel(const uint8_t* __restrict__ src, int n, 
 #pragma unroll
         for (int i = 0; i < 48; ++i) px[i] = __ldg(p + i);
     }
-    const int py = y >> 5, ky = y & 31, pxi = xg >> 1, kx0 = (xg & 1) * 16;
-    __half* orow = out + (int64_t(b) * 49 + py * 7 + pxi) * 3072 + ky * 32 + kx0;
+    const int py = y / PS, ky = y % PS, pxi = (xg * 16) / PS, kx0 = (xg * 16) % PS;
+    __half* orow = out + (int64_t(b) * (G * G) + py * G + pxi) * (3 * PP) + ky * PS + kx0;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         uint32_t pk[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
             pk[i] = pack_half2(clip_norm(px[(2 * i) * 3 + c], c), clip_norm(px[(2 * i + 1) * 3 + c], c));
-        uint4* o4 = reinterpret_cast<uint4*>(orow + c * 1024);
+        uint4* o4 = reinterpret_cast<uint4*>(orow + c * PP);
         o4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         o4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
 }
 
 // fp32 CHW frames (already transformed, what encode_image receives) -> fp16 patch matrix. 8 px / thread.
+template <int PS>
 __global__ void clip_patchify_f32_kernel(const float* __restrict__ src, int n, __half* __restrict__ out) {
+    constexpr int G = 224 / PS, PP = PS * PS;
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t total = int64_t(n) * 3 * 224 * 28;
     if (idx >= total) return;
@@ -67,8 +71,8 @@ __global__ void clip_patchify_f32_kernel(const float* __restrict__ src, int n, _
     const int b = int(idx / (28 * 224 * 3));
     const float4* p = reinterpret_cast<const float4*>(src + ((int64_t(b) * 3 + c) * 224 + y) * 224 + xg * 8);
     const float4 a = __ldg(p), d = __ldg(p + 1);
-    const int py = y >> 5, ky = y & 31, pxi = xg >> 2, kx0 = (xg & 3) * 8;
-    __half* o = out + (int64_t(b) * 49 + py * 7 + pxi) * 3072 + c * 1024 + ky * 32 + kx0;
+    const int py = y / PS, ky = y % PS, pxi = (xg * 8) / PS, kx0 = (xg * 8) % PS;
+    __half* o = out + (int64_t(b) * (G * G) + py * G + pxi) * (3 * PP) + c * PP + ky * PS + kx0;
     *reinterpret_cast<uint4*>(o) =
         make_uint4(pack_half2(a.x, a.y), pack_half2(a.z, a.w), pack_half2(d.x, d.y), pack_half2(d.z, d.w));
 }
@@ -166,20 +170,20 @@ __global__ void __launch_bounds__(256, VF_LN_BLOCKS) add_layernorm768_kernel(flo
 }
 
 // ViT token assembly fused with ln_pre: row (frame, t): t == 0 -> class_embedding + pos[0] (precomputed),
-// t > 0 -> patch embedding row (frame*49 + t-1) + pos[t];  x = ln_pre(row) in fp32.
+// t > 0 -> patch embedding row (frame*(tokens-1) + t-1) + pos[t];  x = ln_pre(row) in fp32.
 __global__ void __launch_bounds__(256, 6) embed_layernorm768_kernel(const float* __restrict__ emb, const float* __restrict__ pos,
                                           const float* __restrict__ cls_pos0, const float* __restrict__ gamma,
-                                          const float* __restrict__ beta, float* __restrict__ x, int rows) {
+                                          const float* __restrict__ beta, float* __restrict__ x, int rows, int tokens) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + warp;
     if (row >= rows) return;
-    const int frame = row / 50, t = row - frame * 50;
+    const int frame = row / tokens, t = row - frame * tokens;
     Row768 r;
     if (t == 0) {
 #pragma unroll
         for (int i = 0; i < 6; ++i) r.v[i] = __ldg(reinterpret_cast<const float4*>(cls_pos0 + (lane + 32 * i) * 4));
     } else {
-        const float* er = emb + (int64_t(frame) * 49 + (t - 1)) * 768;
+        const float* er = emb + (int64_t(frame) * (tokens - 1) + (t - 1)) * 768;
         const float* pr = pos + t * 768;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
@@ -335,6 +339,144 @@ __global__ void __launch_bounds__(128) attention50_kernel(const __half* __restri
     }
 }
 
+// The same attention for longer sequences (ViT-B/16: S = 197 tokens): NT 16-key tiles cover the padded sequence, one
+// block of NW warps per (frame, head), a warp owns query tiles w, w+NW, ...  K, V and Q of the head live in dynamic
+// shared memory (3 x 16*NT rows x 144 B).  The keys are taken in two halves with a running (max, sum) -- the usual
+// online softmax -- so that a thread holds the scores of half a row (52 registers at NT = 13), two blocks fit an SM and
+// one block's staging overlaps the other's arithmetic.  P is rounded to fp16 before normalisation (values in [0,1]),
+// the 1/sum factor is applied to the fp32 output.
+template <int KT0, int KTN>
+__device__ __forceinline__ void attention_keys(const __half (*Ks)[ATT_LD], const __half (*Vs)[ATT_LD], const uint32_t (*aq)[4],
+                                               float (*o)[4], float& m_lo, float& m_hi, float& l_lo, float& l_hi, int S,
+                                               int lane) {
+    const int t = lane & 3;
+    const float sc = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
+    float s[2 * KTN][4];
+#pragma unroll
+    for (int nt = 0; nt < 2 * KTN; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {
+            uint32_t bk[4];
+            ldsm_x4(bk, &Ks[KT0 * 16 + nt * 8 + (lane & 7)][kp * 32 + (lane >> 3) * 8]);
+            mma16816(s[nt], aq[2 * kp], bk[0], bk[1]);
+            mma16816(s[nt], aq[2 * kp + 1], bk[2], bk[3]);
+        }
+    }
+    float n_lo = m_lo, n_hi = m_hi;
+#pragma unroll
+    for (int nt = 0; nt < 2 * KTN; ++nt) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const bool valid = KT0 * 16 + nt * 8 + 2 * t + j < S;
+            s[nt][j] = valid ? s[nt][j] * sc : -INFINITY;
+            s[nt][2 + j] = valid ? s[nt][2 + j] * sc : -INFINITY;
+            n_lo = fmaxf(n_lo, s[nt][j]);
+            n_hi = fmaxf(n_hi, s[nt][2 + j]);
+        }
+    }
+    n_lo = fmaxf(n_lo, __shfl_xor_sync(0xffffffffu, n_lo, 1));
+    n_lo = fmaxf(n_lo, __shfl_xor_sync(0xffffffffu, n_lo, 2));
+    n_hi = fmaxf(n_hi, __shfl_xor_sync(0xffffffffu, n_hi, 1));
+    n_hi = fmaxf(n_hi, __shfl_xor_sync(0xffffffffu, n_hi, 2));
+    // rescale what has been accumulated under the old maximum (exp2f(-inf) == 0 on the first half)
+    const float r_lo = exp2f(m_lo - n_lo), r_hi = exp2f(m_hi - n_hi);
+    m_lo = n_lo; m_hi = n_hi;
+    l_lo *= r_lo; l_hi *= r_hi;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o[i][0] *= r_lo; o[i][1] *= r_lo; o[i][2] *= r_hi; o[i][3] *= r_hi; }
+#pragma unroll
+    for (int nt = 0; nt < 2 * KTN; ++nt) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            s[nt][j] = exp2f(s[nt][j] - m_lo);
+            s[nt][2 + j] = exp2f(s[nt][2 + j] - m_hi);
+            l_lo += s[nt][j];
+            l_hi += s[nt][2 + j];
+        }
+    }
+#pragma unroll
+    for (int kk = 0; kk < KTN; ++kk) {           // 16 keys per step: P fragments straight from the score fragments
+        uint32_t pa[4];
+        pa[0] = pack_half2(s[2 * kk][0], s[2 * kk][1]);
+        pa[1] = pack_half2(s[2 * kk][2], s[2 * kk][3]);
+        pa[2] = pack_half2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[3] = pack_half2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+            uint32_t bv[4];
+            ldsm_x4_trans(bv, &Vs[(KT0 + kk) * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][np * 16 + (lane >> 4) * 8]);
+            mma16816(o[2 * np], pa, bv[0], bv[1]);
+            mma16816(o[2 * np + 1], pa, bv[2], bv[3]);
+        }
+    }
+}
+
+template <int NT, int NW>
+__global__ void __launch_bounds__(NW * 32, 2) attention_long_kernel(const __half* __restrict__ qkv, __half* __restrict__ out,
+                                                                     int heads, int S) {
+    constexpr int SP = NT * 16, H0 = (NT + 1) / 2, H1 = NT - H0;
+    extern __shared__ __align__(16) uint8_t att_smem[];
+    __half (*Qs)[ATT_LD] = reinterpret_cast<__half (*)[ATT_LD]>(att_smem);
+    __half (*Ks)[ATT_LD] = Qs + SP;
+    __half (*Vs)[ATT_LD] = Ks + SP;
+    const int frame = blockIdx.x / heads, head = blockIdx.x % heads;
+    const int width = heads * ATT_D;
+    const int ld = 3 * width;
+    const int64_t row0 = int64_t(frame) * S;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+
+    for (int i = tid; i < 3 * S * 8; i += NW * 32) {
+        const int m = i / (S * 8), rem = i - m * (S * 8);
+        const int r = rem >> 3, seg = rem & 7;
+        const __half* src = qkv + (row0 + r) * ld + m * width + head * ATT_D + seg * 8;
+        cp_async16(m == 0 ? &Qs[r][seg * 8] : m == 1 ? &Ks[r][seg * 8] : &Vs[r][seg * 8], src);
+    }
+    const int pad = SP - S;                   // zero rows S..SP-1 of Q (finite scores), K and V (0 * garbage stays 0)
+    for (int i = tid; i < 3 * pad * 8; i += NW * 32) {
+        const int m = i / (pad * 8), rem = i - m * (pad * 8);
+        const int r = S + (rem >> 3), seg = rem & 7;
+        *reinterpret_cast<uint4*>(m == 0 ? &Qs[r][seg * 8] : m == 1 ? &Ks[r][seg * 8] : &Vs[r][seg * 8]) = make_uint4(0, 0, 0, 0);
+    }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    for (int mt = warp; mt * 16 < S; mt += NW) {
+        const int q0 = mt * 16;
+        uint32_t aq[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) ldsm_x4(aq[ks], &Qs[q0 + (lane & 15)][ks * 16 + (lane >> 4) * 8]);
+        float o[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+        float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+        attention_keys<0, H0>(Ks, Vs, aq, o, m_lo, m_hi, l_lo, l_hi, S, lane);
+        attention_keys<H0, H1>(Ks, Vs, aq, o, m_lo, m_hi, l_lo, l_hi, S, lane);
+        l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
+        l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+        l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
+        l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+        const float inv_lo = 1.0f / l_lo, inv_hi = 1.0f / l_hi;
+        __syncwarp();   // this warp's ldmatrix reads of its own Q rows are done; they become the O staging rows
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+            *reinterpret_cast<uint32_t*>(&Qs[q0 + g][np * 16 + 2 * t]) = pack_half2(o[2 * np][0] * inv_lo, o[2 * np][1] * inv_lo);
+            *reinterpret_cast<uint32_t*>(&Qs[q0 + g + 8][np * 16 + 2 * t]) = pack_half2(o[2 * np][2] * inv_hi, o[2 * np][3] * inv_hi);
+            *reinterpret_cast<uint32_t*>(&Qs[q0 + g][np * 16 + 8 + 2 * t]) = pack_half2(o[2 * np + 1][0] * inv_lo, o[2 * np + 1][1] * inv_lo);
+            *reinterpret_cast<uint32_t*>(&Qs[q0 + g + 8][np * 16 + 8 + 2 * t]) = pack_half2(o[2 * np + 1][2] * inv_hi, o[2 * np + 1][3] * inv_hi);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = q0 + i * 4 + (lane >> 3), seg = lane & 7;
+            if (r < S)
+                *reinterpret_cast<uint4*>(out + (row0 + r) * width + head * ATT_D + seg * 8) =
+                    *reinterpret_cast<const uint4*>(&Qs[r][seg * 8]);
+        }
+    }
+}
+
 // Pillow ImagingResampleHorizontal_8bpc / Vertical_8bpc (third-party Pillow, libImaging/Resample.c), 3 channels:
 //   acc = 2^21 + sum_i px[i] * k[i]  (int32) ;  out = clip8(acc >> 22)
 // Frames are byte streams whose rows (w*3 bytes) are rarely 16-byte multiples, so both passes move CONTIGUOUS SPANS of
@@ -445,15 +587,25 @@ inline unsigned blocks_for(int64_t total, int threads) { return unsigned((total 
 }  // namespace
 
 int launch_clip_patchify(const uint8_t* src, int n, int src_h, int src_w, int crop_y, int crop_x, __half* patches,
-                         cudaStream_t s) {
+                         int patch, cudaStream_t s) {
     const int64_t total = int64_t(n) * 224 * 14;
-    clip_patchify_u8_kernel<<<blocks_for(total, 256), 256, 0, s>>>(src, n, src_h, src_w, crop_y, crop_x, patches);
+    if (patch == 32)
+        clip_patchify_u8_kernel<32><<<blocks_for(total, 256), 256, 0, s>>>(src, n, src_h, src_w, crop_y, crop_x, patches);
+    else if (patch == 16)
+        clip_patchify_u8_kernel<16><<<blocks_for(total, 256), 256, 0, s>>>(src, n, src_h, src_w, crop_y, crop_x, patches);
+    else
+        return fail(VF_ERR_UNSUPPORTED, "patchify: patch size %d (32 and 16 are built)", patch);
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
-int launch_clip_patchify_f32(const float* src_chw, int n, __half* patches, cudaStream_t s) {
+int launch_clip_patchify_f32(const float* src_chw, int n, __half* patches, int patch, cudaStream_t s) {
     const int64_t total = int64_t(n) * 3 * 224 * 28;
-    clip_patchify_f32_kernel<<<blocks_for(total, 256), 256, 0, s>>>(src_chw, n, patches);
+    if (patch == 32)
+        clip_patchify_f32_kernel<32><<<blocks_for(total, 256), 256, 0, s>>>(src_chw, n, patches);
+    else if (patch == 16)
+        clip_patchify_f32_kernel<16><<<blocks_for(total, 256), 256, 0, s>>>(src_chw, n, patches);
+    else
+        return fail(VF_ERR_UNSUPPORTED, "patchify: patch size %d (32 and 16 are built)", patch);
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
@@ -478,15 +630,29 @@ int launch_add_layernorm(float* x, int64_t x_row_stride, const __half* y, int64_
     return VF_OK;
 }
 int launch_embed_layernorm(const float* emb, const float* pos, const float* cls_pos0, const float* gamma,
-                           const float* beta, float* x, int n_frames, cudaStream_t s) {
-    const int warps = 8, rows = n_frames * 50;
-    embed_layernorm768_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, s>>>(emb, pos, cls_pos0, gamma, beta, x, rows);
+                           const float* beta, float* x, int n_frames, int tokens, cudaStream_t s) {
+    const int warps = 8, rows = n_frames * tokens;
+    embed_layernorm768_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, s>>>(emb, pos, cls_pos0, gamma, beta, x, rows, tokens);
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
 int launch_attention(const __half* qkv, __half* out, int n_frames, int tokens, int heads, cudaStream_t s) {
-    if (tokens != ATT_S) return fail(VF_ERR_UNSUPPORTED, "attention: %d tokens (only 50 is built)", tokens);
-    attention50_kernel<<<n_frames * heads, 128, 0, s>>>(qkv, out, heads);
+    if (tokens == ATT_S) {
+        attention50_kernel<<<n_frames * heads, 128, 0, s>>>(qkv, out, heads);
+    } else if (tokens > 64 && tokens <= 208) {
+        constexpr int NT = 13, NW = 8;                       // 208 padded keys; 13 query tiles over 8 warps
+        constexpr int kSmem = 3 * NT * 16 * ATT_LD * int(sizeof(__half));
+        static std::atomic<bool> attr_done[64];
+        int dev = 0;
+        VF_CUDA(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 64 && !attr_done[dev].load(std::memory_order_acquire)) {
+            VF_CUDA(cudaFuncSetAttribute(attention_long_kernel<NT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+            attr_done[dev].store(true, std::memory_order_release);
+        }
+        attention_long_kernel<NT, NW><<<n_frames * heads, NW * 32, kSmem, s>>>(qkv, out, heads, tokens);
+    } else {
+        return fail(VF_ERR_UNSUPPORTED, "attention: %d tokens (50 and 65..208 are built)", tokens);
+    }
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }

@@ -35,7 +35,7 @@ from ..clip_engine import ClipEngine
 from ..utils import (AsyncSink, FrameStream, action_on_extraction, already_extracted, extract_frames,
                      form_list_from_user_input)
 
-_CKPT_NAMES = {'CLIP-ViT-B/32': 'ViT-B-32.pt', 'CLIP4CLIP-ViT-B-32': 'CLIP4CLIP-ViT-B-32.pth'}
+_CKPT_NAMES = {'CLIP-ViT-B/32': 'ViT-B-32.pt', 'CLIP-ViT-B/16': 'ViT-B-16.pt', 'CLIP4CLIP-ViT-B-32': 'CLIP4CLIP-ViT-B-32.pth'}
 
 
 def read_clip_checkpoint(path: str) -> Dict[str, torch.Tensor]:
@@ -57,7 +57,8 @@ def load_clip_state_dict(feature_type: str) -> Dict[str, torch.Tensor]:
     extract_clip.py:56), then ``~/.cache/clip/<name>`` (where ``clip.load`` caches its download).
     ``VF_CLIP_SYNTHETIC=<seed>[:outliers]`` selects seeded synthetic weights instead (benchmarks without the file)."""
     if os.environ.get("VF_CLIP_SYNTHETIC") is not None:
-        return synthetic_weights.clip_vit_b32_state_dict(*synthetic_weights.parse_env(os.environ["VF_CLIP_SYNTHETIC"]))
+        seed, outliers = synthetic_weights.parse_env(os.environ["VF_CLIP_SYNTHETIC"])
+        return synthetic_weights.clip_vit_b32_state_dict(seed, outliers, patch=16 if feature_type.endswith('/16') else 32)
     name = _CKPT_NAMES[feature_type]
     cands = [os.environ.get("VF_CLIP_CKPT"), os.path.join(pathlib.Path(__file__).parent, 'checkpoints', name),
              os.path.expanduser(os.path.join("~/.cache/clip", name))]
@@ -134,8 +135,8 @@ class ExtractCLIP(torch.nn.Module):
         idx = device.index if device.index is not None else torch.cuda.current_device()
         if idx not in self._engines:
             if self.feature_type not in _CKPT_NAMES:
-                # the reference lists B/16 and the ResNet towers as well (extract_clip.py:46-64); only the
-                # ViT-B/32 tower is built here (north_star)
+                # the reference's clip.load would also take the ResNet towers (extract_clip.py:46-64); the ViT-B
+                # towers (patch 32: north_star; patch 16) are the ones built here
                 raise NotImplementedError(self.feature_type)
             self._engines[idx] = ClipEngine(load_clip_state_dict(self.feature_type), device=idx)
         return self._engines[idx]

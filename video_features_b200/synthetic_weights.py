@@ -11,7 +11,12 @@ import torch
 WIDTH, LAYERS, TOKENS, PATCH, MLP, EMBED = 768, 12, 50, 32, 3072, 512
 
 
-def clip_vit_b32_state_dict(seed: int = 0, outliers: bool = False) -> "OrderedDict[str, torch.Tensor]":
+def clip_vit_b16_state_dict(seed: int = 0, outliers: bool = False) -> "OrderedDict[str, torch.Tensor]":
+    """The same for the ViT-B/16 tower (16-pixel patches, 197 tokens)."""
+    return clip_vit_b32_state_dict(seed, outliers, patch=16)
+
+
+def clip_vit_b32_state_dict(seed: int = 0, outliers: bool = False, patch: int = PATCH) -> "OrderedDict[str, torch.Tensor]":
     """openai ``visual.*`` key layout, fp32.  Initialisation scales are the ones openai/CLIP's
     ``initialize_parameters`` uses (width**-0.5 etc.), with perturbed LayerNorm gains / biases so that every term of the
     forward matters.
@@ -32,9 +37,9 @@ def clip_vit_b32_state_dict(seed: int = 0, outliers: bool = False) -> "OrderedDi
     fc_std = (2 * WIDTH) ** -0.5
     sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
     sd["visual.class_embedding"] = rn(WIDTH, std=scale)
-    sd["visual.positional_embedding"] = rn(TOKENS, WIDTH, std=scale)
+    sd["visual.positional_embedding"] = rn((224 // patch) ** 2 + 1, WIDTH, std=scale)
     sd["visual.proj"] = rn(WIDTH, EMBED, std=scale)
-    sd["visual.conv1.weight"] = rn(WIDTH, 3, PATCH, PATCH, std=(3 * PATCH * PATCH) ** -0.5)
+    sd["visual.conv1.weight"] = rn(WIDTH, 3, patch, patch, std=(3 * patch * patch) ** -0.5)
     for name in ("ln_pre", "ln_post"):
         sd[f"visual.{name}.weight"] = 1.0 + rn(WIDTH, std=0.1)
         sd[f"visual.{name}.bias"] = rn(WIDTH, std=0.05)
