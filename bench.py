@@ -266,6 +266,11 @@ def run_engine(args, rank: int, world: int, local_rank: int) -> None:
     frames_host = synth_frames_host(n, 100 + rank).pin_memory()
     frames_dev = frames_host.to(dev)
     out_host = torch.empty((n, 512), dtype=torch.float32).pin_memory()
+    # e2e: consecutive steps alternate between two pinned input / output buffer pairs (step k+1 is enqueued while step k
+    # runs, as a list of videos is processed: the second pair stands for "the next batch the decoder filled")
+    frames_host_b = synth_frames_host(n, 300 + rank).pin_memory()
+    out_host_b = torch.empty((n, 512), dtype=torch.float32).pin_memory()
+    inflight = []
     # N > 1: the all-gather of step k runs on a side stream while the tower of step k+1 runs (two landing buffers);
     # the timed region ends only after the last gather has finished
     gathered = [torch.empty((world * n, 512), dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
@@ -293,19 +298,32 @@ def run_engine(args, rank: int, world: int, local_rank: int) -> None:
         return y
 
     def step_host():
-        if world == 1:
-            return eng.encode_frames_u8_host(frames_host, out_host)
-        # host frames in; features stay on the device for the gather AND come back to the host
-        y = eng.encode_frames_u8_host_dev(frames_host, out_host)
-        gather_async(y)
+        # every step: H2D of its own pinned frames, tower, D2H of its features into its own pinned buffer.  The call is
+        # asynchronous (vf_clip_encode_u8_host_async); the PREVIOUS step's result is awaited right after this one is
+        # enqueued, so at most two steps are in flight and every result is on the host inside the timed region.
+        a = len(inflight) == 0 or inflight[-1][1] is out_host_b
+        fr, oh = (frames_host, out_host) if a else (frames_host_b, out_host_b)
+        # N > 1: the features also stay on the device for the gather
+        ticket, y = eng.encode_frames_u8_host_async(fr, oh, out_dev=world > 1)
+        if world > 1:
+            gather_async(y)
+        inflight.append((ticket, oh))
+        while len(inflight) > 1:
+            eng.wait(inflight.pop(0)[0])
         return y
 
-    def timed(fn, steps):
+    def drain_host():
+        while inflight:
+            eng.wait(inflight.pop(0)[0])
+
+    def timed(fn, steps, drain=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
+        if drain is not None:
+            drain()
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
         e1.record()
@@ -329,7 +347,8 @@ def run_engine(args, rank: int, world: int, local_rank: int) -> None:
     # end-to-end through the host-buffer entry point
     for _ in range(2):
         step_host()
-    ms_e2e = timed(step_host, K)
+    drain_host()
+    ms_e2e = timed(step_host, K, drain_host)
     e2e_value = world * n * K / (ms_e2e / 1e3)
 
     # roofline of the dominant kernel: per-launch CUDA events around every tcgen05 GEMM launch, separate pass over
@@ -413,7 +432,8 @@ def run_engine(args, rank: int, world: int, local_rank: int) -> None:
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": int(frames_host.numel()) * world,
                 "d2h_bytes_per_step": int(out_host.numel() * 4) * world,
-                "api": "vf_clip_encode_u8_host (ClipEngine.encode_frames_u8_host), pinned host buffers"},
+                "api": "vf_clip_encode_u8_host_async + vf_clip_wait (ClipEngine.encode_frames_u8_host_async), pinned host "
+                       "buffers, two steps in flight"},
         "gpu_launches": int(launches * K),
         "gpu_launches_per_step": int(launches),
         "roofline": roofline,
@@ -756,19 +776,39 @@ def run_c5(args, rank: int, world: int, local_rank: int, quick: bool = False):
     ex.frame_stream = SynthStream
     ex.path_list = [f"synthetic://{i}" for i in range(n_videos)]
     # warm-up: engine creation, graph capture for the chunk sizes in use, pinned buffers, thread pools
-    warm = ExtractCLIP.forward(ex, torch.arange(0, min(n_videos, 3 * 86), device=dev))
+    # (through the same run_shard, so the communicator has carried an all-gather of this kind before the timed pass)
+    warm = dispatch.run_shard(ex, min(n_videos, world * 3 * 86), rank, world, dev, gather_key="CLIP-ViT-B/32")
     del warm
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    trace = [] if os.environ.get("VF_C5_TRACE") == "1" else None     # host timeline of the engine calls (diagnostics)
+    if trace is not None:
+        eng0 = ex._engines[local_rank]
+        inner = eng0.encode_frames_u8_host
+
+        def traced(frames, out=None):
+            a = time.perf_counter()
+            r = inner(frames, out)
+            trace.append((a, time.perf_counter(), int(frames.shape[0])))
+            return r
+        eng0.encode_frames_u8_host = traced
     t0 = time.perf_counter()
     e0.record()
     blocks = dispatch.run_shard(ex, n_videos, rank, world, dev, gather_key="CLIP-ViT-B/32")
     e1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    if trace:
+        busy = sum(b - a for a, b, _ in trace)
+        gaps = sum(max(0.0, trace[i][0] - trace[i - 1][1]) for i in range(1, len(trace)))
+        print(f"[c5 trace rank {rank}] wall {wall:.3f} s; {len(trace)} engine calls busy {busy:.3f} s, gaps between calls "
+              f"{gaps:.3f} s, first call starts at {trace[0][0] - t0:.3f} s, last call ends at {trace[-1][1] - t0:.3f} s "
+              f"(then deliver + gather {wall - (trace[-1][1] - t0):.3f} s); per-call ms "
+              f"{[round((b - a) * 1e3, 1) for a, b, _ in trace[:6]]} ... {[round((b - a) * 1e3, 1) for a, b, _ in trace[-3:]]}",
+              file=sys.stderr, flush=True)
     clocks = sampler.stop() if sampler else None
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:

@@ -126,6 +126,16 @@ int vf_clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, int 
  * well.  Returns once the host frames have been consumed (and out_host, if given, is complete). */
 int vf_clip_encode_u8_host_dev(vf_clip_t* h, const uint8_t* frames_host, int n, int src_h, int src_w, float* out_dev,
                                float* out_host, void* stream);
+
+/* Asynchronous form of the two calls above: returns once the copies and kernels are enqueued.  `frames_host` and `out_host`
+ * must be pinned and stay untouched until vf_clip_wait(h, *ticket) returns; out_dev (may be NULL) is ordered on `stream`
+ * like any other device output.  Calls in flight share the handle's staging slots under event ordering, so the H2D copy
+ * of call k+1 overlaps the tower of call k -- the pattern of a list of videos (reference: the per-video loop of
+ * models/CLIP/extract_clip.py:70-88, where nothing overlaps).  At most 4 calls are in flight; a fifth blocks on the
+ * oldest.  One enqueuing host thread per handle; vf_clip_wait may be called from another thread. */
+int vf_clip_encode_u8_host_async(vf_clip_t* h, const uint8_t* frames_host, int n, int src_h, int src_w, float* out_dev,
+                                 float* out_host, void* stream, int64_t* ticket);
+int vf_clip_wait(vf_clip_t* h, int64_t ticket);
 /* Diagnostics / parity tests: the attention half of resblock `layer` alone -- x: n_frames*50 x 768 fp16 (the ln_1 output),
  * out: n_frames*50 x 768 fp16 = concat_heads(softmax(q k^T / 8) v) BEFORE the out-projection (third-party clip
  * ResidualAttentionBlock.attention / nn.MultiheadAttention).  fused = 1: the QKV-projection + attention kernel the tower

@@ -158,6 +158,34 @@ def test_resize_path_matches_pillow_then_oracle(tower, cuda_device):
     _check_rows(y, ref)
 
 
+def test_async_host_calls_match_the_synchronous_call(tower, cuda_device):
+    """vf_clip_encode_u8_host_async: six calls of different sizes / geometries enqueued back to back (more than the four
+    tickets the handle keeps), waited for out of order and from another thread -- bit-identical to the synchronous call."""
+    import threading
+    sd, eng = tower
+    g = torch.Generator().manual_seed(11)
+    shapes = [(300, 224, 224), (7, 240, 320), (513, 224, 224), (1, 224, 224), (64, 120, 160), (256, 224, 224)]
+    frames = [torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, generator=g).pin_memory() for n, h, w in shapes]
+    ref = [eng.encode_frames_u8_host(f).clone() for f in frames]
+    outs = [torch.empty((f.shape[0], 512), dtype=torch.float32).pin_memory() for f in frames]
+    tickets = []
+    devs = []
+    for f, o in zip(frames, outs):
+        t, d = eng.encode_frames_u8_host_async(f, o, out_dev=True)
+        tickets.append(t)
+        devs.append(d)
+    assert tickets == list(range(tickets[0], tickets[0] + 6))
+    th = threading.Thread(target=lambda: [eng.wait(t) for t in reversed(tickets)])
+    th.start()
+    th.join()
+    eng.wait(-1)
+    for o, d, r in zip(outs, devs, ref):
+        assert torch.equal(o, r)
+        assert torch.equal(d.cpu(), r)
+    with pytest.raises(RuntimeError):
+        eng.wait(tickets[-1] + 1)            # never issued
+
+
 # ---------------------------------------------------------------- ViT-B/16 (the reference's 'CLIP-ViT-B/16' feature type)
 @pytest.fixture(scope="module")
 def tower16(cuda_device):

@@ -188,6 +188,15 @@ class _FakeClipEngine:
         y[:, 1] = n
         return y
 
+    # the asynchronous pair the batcher uses (ClipEngine.encode_frames_u8_host_async / wait)
+    def encode_frames_u8_host_async(self, frames, out_host=None, out_dev=False):
+        out_host.copy_(self.encode_frames_u8_host(frames))
+        self.tickets = getattr(self, "tickets", 0) + 1
+        return self.tickets - 1, None
+
+    def wait(self, ticket):
+        assert 0 <= ticket < self.tickets
+
 
 def test_extract_clip_batches_consecutive_videos_into_one_engine_call(tmp_path, monkeypatch, capsys):
     """ExtractCLIP.forward over a list: frames of consecutive same-geometry videos share one engine call; results are

@@ -122,6 +122,32 @@ class ClipEngine:
                                                    torch.cuda.current_stream().cuda_stream))
         return out
 
+    # ---- asynchronous form: enqueue and return; `wait(ticket)` before touching the host buffers
+    def encode_frames_u8_host_async(self, frames: torch.Tensor, out_host: Optional[torch.Tensor] = None,
+                                    out_dev: bool = False):
+        """Pinned host frames in; features to ``out_host`` (pinned) and / or a new device tensor (``out_dev=True``).
+        Returns ``(ticket, device tensor or None)``.  The H2D copies of this call overlap the tower of the call before
+        it (vf_clip_encode_u8_host_async); ``frames`` and ``out_host`` belong to the engine until ``wait(ticket)``."""
+        assert (not frames.is_cuda) and frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3
+        assert frames.is_contiguous() and frames.is_pinned(), "asynchronous calls need pinned, contiguous host frames"
+        n, hh, ww, _ = frames.shape
+        if out_host is not None:
+            assert out_host.dtype == torch.float32 and out_host.is_contiguous() and tuple(out_host.shape) == (n, 512)
+            assert out_host.is_pinned(), "asynchronous calls need a pinned host output"
+        assert out_host is not None or out_dev
+        dev = torch.empty((n, 512), device=self.device, dtype=torch.float32) if out_dev else None
+        ticket = C.c_int64(-1)
+        with torch.cuda.device(self.device):
+            check(lib().vf_clip_encode_u8_host_async(self._h, frames.data_ptr(), n, hh, ww,
+                                                     None if dev is None else dev.data_ptr(),
+                                                     None if out_host is None else out_host.data_ptr(),
+                                                     torch.cuda.current_stream().cuda_stream, C.byref(ticket)))
+        return int(ticket.value), dev
+
+    def wait(self, ticket: int) -> None:
+        """Block until the asynchronous call `ticket` has finished with its host buffers."""
+        check(lib().vf_clip_wait(self._h, int(ticket)))
+
     def block_attention(self, layer: int, x: torch.Tensor, fused: bool = True) -> torch.Tensor:
         """Diagnostics: the attention half of resblock `layer` on x (n_frames*50, 768) fp16 -> (n_frames*50, 768) fp16,
         before the out-projection; fused=False runs the QKV GEMM + stand-alone attention kernel instead."""

@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <map>
 #include <vector>
 
@@ -82,6 +83,10 @@ struct vf_clip {
     float* feat = nullptr;                    // [chunk, 512] tower output of the active lane
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    // asynchronous host calls (vf_clip_encode_u8_host_async): completion events of the last kTickets calls
+    static constexpr int kTickets = 4;
+    cudaEvent_t ev_ticket[kTickets] = {nullptr, nullptr, nullptr, nullptr};
+    std::atomic<int64_t> seq{0};              // vf_clip_wait may run on another host thread than the enqueuing one
 };
 
 namespace vf {
@@ -449,6 +454,8 @@ int vf_clip_create_vit(vf_clip_t** out, const vf_clip_weights* w, int device, in
             VF_CUDA(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
             VF_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
         }
+        for (int i = 0; i < vf_clip::kTickets; ++i)
+            VF_CUDA(cudaEventCreateWithFlags(&h->ev_ticket[i], cudaEventDisableTiming | cudaEventBlockingSync));
         return VF_OK;
     };
     st = body();
@@ -481,6 +488,8 @@ int vf_clip_destroy(vf_clip_t* h) {
         if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
     }
+    for (int i = 0; i < vf_clip::kTickets; ++i)
+        if (h->ev_ticket[i]) cudaEventDestroy(h->ev_ticket[i]);
     delete h;
     return VF_OK;
 }
@@ -521,17 +530,25 @@ int vf_clip_encode_u8(vf_clip_t* h, const uint8_t* frames, int n, int src_h, int
     return leave(h, user);
 }
 
+// ticket == nullptr: synchronous (returns when the host buffers may be reused / read).  Otherwise the call returns once
+// everything is enqueued and *ticket names it for vf_clip_wait; the staging slots, the feature buffer and the streams
+// are shared with the calls still in flight, ordered by events, so the first H2D copy of call k+1 overlaps the last
+// tower chunk of call k.
 static int clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, int src_h, int src_w, float* out_host,
-                               float* out_dev, void* stream) {
+                               float* out_dev, void* stream, int64_t* ticket) {
     if (!h || (n > 0 && (!frames_host || (!out_host && !out_dev))))
         return fail(VF_ERR_INVALID, "clip_encode_u8_host: null argument");
-    if (n <= 0) return VF_OK;
+    if (n <= 0) {
+        if (ticket) *ticket = -1;              // nothing enqueued: vf_clip_wait(-1) returns at once
+        return VF_OK;
+    }
     cudaStream_t user = static_cast<cudaStream_t>(stream);
     ClipGeom g;
     VF_TRY(clip_geometry(src_h, src_w, &g));
     VF_TRY(enter(h, user));
     const size_t fbytes = size_t(src_h) * src_w * 3;
-    // two staging slots: the H2D copy of chunk i+1 (copy stream) overlaps the tower on chunk i (compute stream)
+    // two staging slots: the H2D copy of chunk i+1 (copy stream) overlaps the tower on chunk i (compute stream).
+    // (a re-allocation frees the old buffer with cudaFree, which waits for the calls in flight)
     VF_TRY(grow(&h->stage_u8, &h->stage_cap, 2 * size_t(h->chunk) * fbytes));
     float* feats = out_dev;                 // the caller's device buffer, else the handle's own
     if (!feats) {
@@ -545,7 +562,8 @@ static int clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, 
     }
     const int step = balanced_chunk(h, n);
     const int nchunks = (n + step - 1) / step;
-    VF_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_in, 0));
+    // the staging copies read HOST memory that is ready now: they are not ordered behind the caller's stream (which, after
+    // an asynchronous call, waits for that call's tower) -- only behind the staging slot's previous user
     for (int i = 0; i < nchunks; ++i) {
         const int b0 = i * step;
         const int c = (n - b0 < step) ? (n - b0) : step;
@@ -553,7 +571,9 @@ static int clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, 
         LaneScope lane(h, i % h->n_lanes);
         cudaStream_t s = lane.s;
         uint8_t* dst = h->stage_u8 + size_t(slot) * h->chunk * fbytes;
-        if (i >= 2) VF_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));   // slot free again
+        // slot free again: its previous user (an earlier chunk of this call, or of a call still in flight) has been
+        // transformed.  Waiting on a never-recorded event is a no-op.
+        VF_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));
         VF_CUDA(cudaMemcpyAsync(dst, frames_host + size_t(b0) * fbytes, size_t(c) * fbytes, cudaMemcpyHostToDevice,
                                 h->copy_stream));
         VF_CUDA(cudaEventRecord(h->ev_copy[slot], h->copy_stream));
@@ -570,6 +590,17 @@ static int clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, 
     }
     if (out_host)
         VF_CUDA(cudaMemcpyAsync(out_host, feats, size_t(n) * E * sizeof(float), cudaMemcpyDeviceToHost, s0));
+    if (ticket) {
+        // everything this call reads from / writes to the host is complete once s0 reaches this point (the tower
+        // depends on every staging copy)
+        const int64_t t = h->seq.load();
+        cudaEvent_t ev = h->ev_ticket[t % vf_clip::kTickets];
+        if (t >= vf_clip::kTickets) VF_CUDA(cudaEventSynchronize(ev));          // at most kTickets calls in flight
+        VF_CUDA(cudaEventRecord(ev, s0));
+        *ticket = t;
+        h->seq.store(t + 1);
+        return leave(h, user);
+    }
     VF_TRY(leave(h, user));
     // the host frames may be reused (and out_host read) as soon as this returns
     VF_CUDA(cudaStreamSynchronize(out_host ? s0 : h->copy_stream));
@@ -579,13 +610,29 @@ static int clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, 
 int vf_clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, int src_h, int src_w, float* out_host,
                            void* stream) {
     if (n > 0 && !out_host) return fail(VF_ERR_INVALID, "clip_encode_u8_host: null argument");
-    return clip_encode_u8_host(h, frames_host, n, src_h, src_w, out_host, nullptr, stream);
+    return clip_encode_u8_host(h, frames_host, n, src_h, src_w, out_host, nullptr, stream, nullptr);
 }
 
 int vf_clip_encode_u8_host_dev(vf_clip_t* h, const uint8_t* frames_host, int n, int src_h, int src_w, float* out_dev,
                                float* out_host, void* stream) {
     if (n > 0 && !out_dev) return fail(VF_ERR_INVALID, "clip_encode_u8_host_dev: null device output");
-    return clip_encode_u8_host(h, frames_host, n, src_h, src_w, out_host, out_dev, stream);
+    return clip_encode_u8_host(h, frames_host, n, src_h, src_w, out_host, out_dev, stream, nullptr);
+}
+
+int vf_clip_encode_u8_host_async(vf_clip_t* h, const uint8_t* frames_host, int n, int src_h, int src_w, float* out_dev,
+                                 float* out_host, void* stream, int64_t* ticket) {
+    if (!ticket) return fail(VF_ERR_INVALID, "clip_encode_u8_host_async: null ticket");
+    return clip_encode_u8_host(h, frames_host, n, src_h, src_w, out_host, out_dev, stream, ticket);
+}
+
+int vf_clip_wait(vf_clip_t* h, int64_t ticket) {
+    if (!h) return fail(VF_ERR_INVALID, "clip_wait: null handle");
+    if (ticket < 0) return VF_OK;
+    if (ticket >= h->seq.load()) return fail(VF_ERR_INVALID, "clip_wait: ticket %lld was never issued", (long long)ticket);
+    if (ticket + vf_clip::kTickets < h->seq.load())
+        return VF_OK;                          // its event has been reused: that only happens after it completed
+    VF_CUDA(cudaEventSynchronize(h->ev_ticket[ticket % vf_clip::kTickets]));
+    return VF_OK;
 }
 
 int vf_clip_block_attention(vf_clip_t* h, int layer, const void* x, int n_frames, void* out, int fused, void* stream) {

@@ -146,7 +146,7 @@ class ExtractCLIP(torch.nn.Module):
         """indices {torch.LongTensor} -- indices to self.path_list; the device is taken from ``indices.device``."""
         device = indices.device
         model = self._engine(device)          # one engine per device, kept across calls
-        ids = [int(i) for i in indices]
+        ids = indices.tolist() if hasattr(indices, 'tolist') else [int(i) for i in indices]   # ONE device read, not one per index
         # opt-in extras beyond the reference (SURVEY 8(f) rank 2): VF_ASYNC_SINK=1 saves from a writer thread,
         # VF_RESUME=1 skips videos whose output files already exist
         saving = not self.external_call
@@ -223,8 +223,9 @@ class ExtractCLIP(torch.nn.Module):
     def _forward_batched(self, device, model: ClipEngine, todo, collected, sink):
         """Stages, each on its own thread(s), so the GPU never waits for Python:
              pool: open videos (blocks of 8)  ->  this thread: rows of a pinned staging slot are assigned in list order
-             ->  pool: every stream decodes INTO its rows  ->  engine thread: ONE engine call per <= batch_frames rows
-             ->  delivery thread: per-video slices, sink."""
+             ->  pool: every stream decodes INTO its rows  ->  engine thread: ONE asynchronous engine call per
+             <= batch_frames rows (enqueued while the previous one still runs: its first H2D copy overlaps that tower)
+             ->  delivery thread: waits for the call, per-video slices, sink."""
         workers = max(1, self.decode_workers)
         pool = ThreadPoolExecutor(workers, thread_name_prefix="vf-decode")
         gpu = ThreadPoolExecutor(1, thread_name_prefix="vf-engine")           # engine calls are serialised: one handle
@@ -232,6 +233,7 @@ class ExtractCLIP(torch.nn.Module):
         n_slots = 3
         pinned: List[Optional[torch.Tensor]] = [None] * n_slots
         pinned_np: List[Optional[np.ndarray]] = [None] * n_slots
+        feats_out: List[Optional[torch.Tensor]] = [None] * n_slots            # pinned (batch_frames, 512) landing buffers
         busy = [None] * n_slots                                               # engine future still reading slot k
         delivered = []
         state = {"slot": 0}
@@ -257,6 +259,28 @@ class ExtractCLIP(torch.nn.Module):
                 else:
                     deliver_one(pos, video, feats[row0:row0 + k].copy(), st.fps, st.timestamps_ms)
 
+        def batch_failed(batch: _Batch, counts, view):
+            # the batched call failed: find the culprit by running its videos one at a time (engine thread only)
+            for (pos, video, st, row0, _), k in zip(batch.items, counts):
+                try:
+                    if isinstance(k, Exception):
+                        raise k
+                    f = model.encode_frames_u8_host(view[row0:row0 + k]).numpy()
+                    deliver_one(pos, video, f, st.fps, st.timestamps_ms)
+                except Exception as err:
+                    self._report(err, video)
+                    self.progress.update()
+
+        def finish(batch: _Batch, ticket, feats, counts):
+            try:
+                model.wait(ticket)                                            # features are in the pinned landing buffer
+            except Exception as err:                                          # a device fault: every video of the call is lost
+                for (pos, video, st, row0, _) in batch.items:
+                    self._report(err, video)
+                    self.progress.update()
+                return
+            deliver(batch, feats.numpy(), counts)
+
         def run_batch(batch: _Batch):
             counts = []
             for it in batch.items:                                            # the decodes into this slot are complete
@@ -264,33 +288,37 @@ class ExtractCLIP(torch.nn.Module):
                 counts.append(fut.result()[i])
             h, w = batch.hw
             view = pinned[batch.slot][:batch.rows * h * w * 3].view(batch.rows, h, w, 3)
+            feats = feats_out[batch.slot][:batch.rows]
             try:
-                feats = model.encode_frames_u8_host(view).numpy()
+                ticket, _ = model.encode_frames_u8_host_async(view, feats)
             except Exception:
-                # the batched call failed: find the culprit by running its videos one at a time
-                for (pos, video, st, row0, _), k in zip(batch.items, counts):
-                    try:
-                        if isinstance(k, Exception):
-                            raise k
-                        f = model.encode_frames_u8_host(view[row0:row0 + k]).numpy()
-                        deliver_one(pos, video, f, st.fps, st.timestamps_ms)
-                    except Exception as err:
-                        self._report(err, video)
-                        self.progress.update()
-                return
-            delivered.append(out.submit(deliver, batch, feats, counts))       # slicing + sink run beside the next call
+                batch_failed(batch, counts, view)
+                return None
+            done = out.submit(finish, batch, ticket, feats, counts)           # waiting, slicing and the sink run beside the
+            delivered.append(done)                                            # next call's enqueue
+            return done
+
+        def wait_slot(k):
+            if busy[k] is not None:
+                done = busy[k].result()                                       # enqueued ...
+                if done is not None:
+                    done.result()                                             # ... and finished with the slot's buffers
+                busy[k] = None
 
         def new_batch(hw):
             k = state["slot"]
             state["slot"] = (k + 1) % n_slots
-            if busy[k] is not None:
-                busy[k].result()                                              # the engine has finished with this buffer
+            wait_slot(k)                                                      # the engine has finished with this buffer
             need = self.batch_frames * hw[0] * hw[1] * 3
             if pinned[k] is None or pinned[k].numel() < need:
                 pinned[k] = torch.empty(need, dtype=torch.uint8)
                 if torch.cuda.is_available():                                 # (host-logic tests run without a device)
                     pinned[k] = pinned[k].pin_memory()
                 pinned_np[k] = pinned[k].numpy()
+            if feats_out[k] is None:
+                feats_out[k] = torch.empty((self.batch_frames, 512), dtype=torch.float32)
+                if torch.cuda.is_available():
+                    feats_out[k] = feats_out[k].pin_memory()
             return _Batch(hw, k)
 
         pending: List[tuple] = []                                             # (batch item, its staging rows) not yet submitted
@@ -337,9 +365,8 @@ class ExtractCLIP(torch.nn.Module):
                         if batch is not None:
                             seal(batch)
                             batch = None
-                        for bsy in busy:
-                            if bsy is not None:
-                                bsy.result()
+                        for k in range(n_slots):
+                            wait_slot(k)
                         gpu.submit(self._run_lone, model, pos, video, st, collected, sink, lock).result()
                         continue
                     if batch is not None and (batch.hw != st.hw or batch.rows + st.count > self.batch_frames):
@@ -358,9 +385,8 @@ class ExtractCLIP(torch.nn.Module):
                 submit_reads()                                                # one pool task per block of videos
             if batch is not None:
                 seal(batch)
-            for bsy in busy:
-                if bsy is not None:
-                    bsy.result()
+            for k in range(n_slots):
+                wait_slot(k)
             for d in delivered:
                 d.result()
         finally:
