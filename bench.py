@@ -784,17 +784,25 @@ def run_c5(args, rank: int, world: int, local_rank: int, quick: bool = False):
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    trace = [] if os.environ.get("VF_C5_TRACE") == "1" else None     # host timeline of the engine calls (diagnostics)
+    trace = {} if os.environ.get("VF_C5_TRACE") == "1" else None     # host timeline of the shard (diagnostics)
     if trace is not None:
-        eng0 = ex._engines[local_rank]
-        inner = eng0.encode_frames_u8_host
+        inner_gather, inner_forward = dispatch.gather_feature_blocks, ExtractCLIP.forward
 
-        def traced(frames, out=None):
+        def traced_gather(*a_, **k_):
+            torch.cuda.synchronize()
             a = time.perf_counter()
-            r = inner(frames, out)
-            trace.append((a, time.perf_counter(), int(frames.shape[0])))
+            r = inner_gather(*a_, **k_)
+            torch.cuda.synchronize()
+            trace["gather"] = (a, time.perf_counter())
             return r
-        eng0.encode_frames_u8_host = traced
+
+        def traced_forward(self, indices):
+            a = time.perf_counter()
+            r = inner_forward(self, indices)
+            trace["forward"] = (a, time.perf_counter())
+            return r
+        dispatch.gather_feature_blocks = traced_gather
+        ExtractCLIP.forward = traced_forward
     t0 = time.perf_counter()
     e0.record()
     blocks = dispatch.run_shard(ex, n_videos, rank, world, dev, gather_key="CLIP-ViT-B/32")
@@ -802,13 +810,10 @@ def run_c5(args, rank: int, world: int, local_rank: int, quick: bool = False):
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     if trace:
-        busy = sum(b - a for a, b, _ in trace)
-        gaps = sum(max(0.0, trace[i][0] - trace[i - 1][1]) for i in range(1, len(trace)))
-        print(f"[c5 trace rank {rank}] wall {wall:.3f} s; {len(trace)} engine calls busy {busy:.3f} s, gaps between calls "
-              f"{gaps:.3f} s, first call starts at {trace[0][0] - t0:.3f} s, last call ends at {trace[-1][1] - t0:.3f} s "
-              f"(then deliver + gather {wall - (trace[-1][1] - t0):.3f} s); per-call ms "
-              f"{[round((b - a) * 1e3, 1) for a, b, _ in trace[:6]]} ... {[round((b - a) * 1e3, 1) for a, b, _ in trace[-3:]]}",
-              file=sys.stderr, flush=True)
+        dispatch.gather_feature_blocks, ExtractCLIP.forward = inner_gather, inner_forward
+        f, g = trace.get("forward", (t0, t0)), trace.get("gather", (t0, t0))
+        print(f"[c5 trace rank {rank}] wall {wall:.3f} s: before forward {f[0] - t0:.3f}, forward {f[1] - f[0]:.3f}, "
+              f"forward -> gather {g[0] - f[1]:.3f}, gather {g[1] - g[0]:.3f}, after {t0 + wall - g[1]:.3f}", file=sys.stderr, flush=True)
     clocks = sampler.stop() if sampler else None
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:

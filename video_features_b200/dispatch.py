@@ -28,7 +28,8 @@ def free_port() -> int:
         return int(s.getsockname()[1])
 
 
-def gather_feature_blocks(blocks: Sequence[torch.Tensor], width: int, device: torch.device) -> List[torch.Tensor]:
+def gather_feature_blocks(blocks: Sequence[torch.Tensor], width: int, device: torch.device,
+                          rows_on_device: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
     """All-gather a per-rank list of (T_i, width) float32 blocks.  One collective for the row counts of every video
     (sizes first, so ranks can pad), one for the rows (padded to the largest rank).  Returns the blocks of ALL ranks in
     rank order (== list order, because shards are contiguous).  Without a process group (one device) it is the
@@ -50,7 +51,8 @@ def gather_feature_blocks(blocks: Sequence[torch.Tensor], width: int, device: to
     rows = torch.zeros((max(max_rows, 1), width), dtype=torch.float32, device=device)
     if counts.numel() and int(sizes[dist.get_rank(), 1]):
         # one concatenation where the blocks live, then ONE copy to the device (not a copy per video)
-        rows[:int(sizes[dist.get_rank(), 1])].copy_(torch.cat([b.to(torch.float32) for b in blocks]), non_blocking=True)
+        src = rows_on_device if rows_on_device is not None else [b.to(torch.float32) for b in blocks]
+        rows[:int(sizes[dist.get_rank(), 1])].copy_(torch.cat(list(src)), non_blocking=True)
     all_rows = torch.empty((world * rows.shape[0], width), dtype=torch.float32, device=device)
     dist.all_gather_into_tensor(all_rows, rows)                    # concatenation along dim 0
     all_rows = all_rows.view(world, rows.shape[0], width)
@@ -75,12 +77,18 @@ def run_shard(extractor, n_items: int, rank: int, world: int, device: torch.devi
     if gather_key is None:
         return None
     blocks = [torch.as_tensor(d[gather_key], dtype=torch.float32) for d in (res or [])]
+    chunks = getattr(extractor, "device_chunks", None)
+    rows_dev = None
+    if chunks and sum(c.shape[0] for _, c in chunks) == sum(b.shape[0] for b in blocks):
+        # the extractor kept the same rows on the GPU, one tensor per engine call: gather those (no host concatenation
+        # of thousands of blocks, no H2D copy)
+        rows_dev = [c for _, c in sorted(chunks, key=lambda pc: pc[0])]
     width = blocks[0].shape[1] if blocks else 0
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         wmax = torch.tensor([width], dtype=torch.int64, device=device)
         dist.all_reduce(wmax, op=dist.ReduceOp.MAX)                # a rank with an empty shard learns the width
         width = int(wmax)
-    return gather_feature_blocks(blocks, width, device)
+    return gather_feature_blocks(blocks, width, device, rows_dev)
 
 
 def _worker(rank: int, world: int, device_ids: List[int], make_extractor: Callable, n_items: int, port: int,

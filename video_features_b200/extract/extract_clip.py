@@ -127,6 +127,8 @@ class ExtractCLIP(torch.nn.Module):
         self.batch_frames = int(os.environ.get("VF_CLIP_BATCH_FRAMES", "1024"))
         self.decode_workers = int(os.environ.get("VF_DECODE_WORKERS", str(min(8, os.cpu_count() or 1))))
         self.keep_features = False        # dispatch sets it when the features are all-gathered as well as saved
+        # with keep_features: (first list position, rows of consecutive delivered videos still on the GPU), one per engine call
+        self.device_chunks: List[tuple] = []
 
     def _engine(self, device: torch.device) -> ClipEngine:
         if device.type != 'cuda':
@@ -161,6 +163,7 @@ class ExtractCLIP(torch.nn.Module):
                 continue
             todo.append((pos, video))
         collected: Dict[int, dict] = {}
+        self.device_chunks = []
         try:
             if len(todo) > 1 and self.batch_frames > 0:
                 self._forward_batched(device, model, todo, collected, sink)
@@ -244,11 +247,15 @@ class ExtractCLIP(torch.nn.Module):
                 with lock:
                     self._deliver({self.feature_type: feats, 'fps': np.array(fps), 'timestamps_ms': np.array(stamps)},
                                   pos, video, collected, sink)
+                ok = True
             except Exception as err:
                 self._report(err, video)
+                ok = False
             self.progress.update()
+            return ok
 
-        def deliver(batch: _Batch, feats, counts):
+        def deliver(batch: _Batch, feats, counts, dev=None):
+            good = []                                                         # (row0, k) of the videos that were delivered
             for (pos, video, st, row0, _), k in zip(batch.items, counts):
                 if isinstance(k, Exception):
                     self._report(k, video)
@@ -256,8 +263,13 @@ class ExtractCLIP(torch.nn.Module):
                 elif k <= 0:
                     self._report(RuntimeError(f"no frames decoded from {video}"), video)
                     self.progress.update()
-                else:
-                    deliver_one(pos, video, feats[row0:row0 + k].copy(), st.fps, st.timestamps_ms)
+                elif deliver_one(pos, video, feats[row0:row0 + k].copy(), st.fps, st.timestamps_ms):
+                    good.append((row0, k))
+            if dev is not None and good:
+                # the same rows, still on the GPU, for a gather: the call's tensor as it is when every video made it
+                rows = dev[:batch.rows] if sum(k for _, k in good) == batch.rows else torch.cat([dev[a:a + k] for a, k in good])
+                with lock:
+                    self.device_chunks.append((batch.items[0][0], rows))
 
         def batch_failed(batch: _Batch, counts, view):
             # the batched call failed: find the culprit by running its videos one at a time (engine thread only)
@@ -271,7 +283,7 @@ class ExtractCLIP(torch.nn.Module):
                     self._report(err, video)
                     self.progress.update()
 
-        def finish(batch: _Batch, ticket, feats, counts):
+        def finish(batch: _Batch, ticket, feats, counts, dev):
             try:
                 model.wait(ticket)                                            # features are in the pinned landing buffer
             except Exception as err:                                          # a device fault: every video of the call is lost
@@ -279,7 +291,7 @@ class ExtractCLIP(torch.nn.Module):
                     self._report(err, video)
                     self.progress.update()
                 return
-            deliver(batch, feats.numpy(), counts)
+            deliver(batch, feats.numpy(), counts, dev)
 
         def run_batch(batch: _Batch):
             counts = []
@@ -290,11 +302,11 @@ class ExtractCLIP(torch.nn.Module):
             view = pinned[batch.slot][:batch.rows * h * w * 3].view(batch.rows, h, w, 3)
             feats = feats_out[batch.slot][:batch.rows]
             try:
-                ticket, _ = model.encode_frames_u8_host_async(view, feats)
+                ticket, dev = model.encode_frames_u8_host_async(view, feats, out_dev=self.keep_features)
             except Exception:
                 batch_failed(batch, counts, view)
                 return None
-            done = out.submit(finish, batch, ticket, feats, counts)           # waiting, slicing and the sink run beside the
+            done = out.submit(finish, batch, ticket, feats, counts, dev)           # waiting, slicing and the sink run beside the
             delivered.append(done)                                            # next call's enqueue
             return done
 
