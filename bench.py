@@ -592,9 +592,29 @@ def run_i3d(args, quick: bool = False):
     sampler = ClockSampler(0)
     ms = _timed_loop(fn, K, W)
     clocks = sampler.stop()
-    def host_fn():      # pinned host stacks in, host features out; H2D of group k+1 overlaps the network on group k
-        return eng.forward_frames_u8_host(frames_host, 64, group=max(1, S // 2))
-    ms_e2e = _timed_loop(host_fn, K, 2)
+    pending = []
+
+    def host_fn():      # pinned host stacks in, host features out; H2D of group k+1 overlaps the network on group k, and
+        # the first copy of step k+1 overlaps the network of step k (the previous step's features are awaited right
+        # after this step is enqueued: two steps in flight, every result on the host inside the timed region)
+        pending.append(eng.forward_frames_u8_host(frames_host, 64, group=max(1, S // 2), wait=False))
+        while len(pending) > 1:
+            pending.pop(0)[1].synchronize()
+
+    for _ in range(2):
+        host_fn()
+    while pending:
+        pending.pop(0)[1].synchronize()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        host_fn()
+    while pending:
+        pending.pop(0)[1].synchronize()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1)
     roof = _gemm_roofline(fn, min(K, 3), I3D_GFLOP["rgb"] * 1e9 * S, ms / K)
     line = {"metric": "stacks/sec I3D rgb (64x224x224)", "value": S * K / (ms / 1e3), "unit": "stacks/s", "n_gpus": 1,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -10,7 +10,10 @@ timeout -s KILL 300 python bench.py --impl reference --steps 3 --warmup 1 > gpur
 timeout -s KILL 400 python bench.py --steps 20 --warmup 5 --no-cpu --no-secondary --torch-gpu > gpurun_out/r2_bench_clip_torchgpu.json 2>> gpurun_out/r2_bench_clip.err
 timeout -s KILL 400 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches_clip.csv \
     python scripts/ncu_clip_once.py 1000 250 > gpurun_out/r2_ncu_list.log 2>&1
-cat gpurun_out/r2_pytest_gpu.txt
+timeout -s KILL 300 python scripts/b16_time.py 1008 126 > gpurun_out/r2_b16_time.txt 2>&1
+# is the NVDEC user-mode library on the box at all?  headers / a demuxer are not in the image either way
+(ldconfig -p | grep -i -E "nvcuvid|nvidia-encode" || echo "libnvcuvid: not found by ldconfig"; ls /usr/lib/x86_64-linux-gnu | grep -i -E "nvcuvid|nvidia-encode" || true) > gpurun_out/r2_nvdec_probe.txt 2>&1
+cat gpurun_out/r2_pytest_gpu.txt gpurun_out/r2_b16_time.txt gpurun_out/r2_nvdec_probe.txt
 python - <<'PY'
 import json
 for f in ("r2_bench_clip", "r2_bench_clip_reference", "r2_bench_clip_torchgpu"):

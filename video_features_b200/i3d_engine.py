@@ -86,10 +86,12 @@ class I3DEngine:
                                                   torch.cuda.current_stream().cuda_stream))
         return out
 
-    def forward_frames_u8_host(self, frames: torch.Tensor, T: int, group: int = 8) -> torch.Tensor:
+    def forward_frames_u8_host(self, frames: torch.Tensor, T: int, group: int = 8, wait: bool = True):
         """rgb stream from HOST stacks (n, >=T, Hr, Wr, 3) uint8 (pinned memory for asynchronous copies): the first T
         frames of every stack are used; the host->device copy of stack group k+1 runs on a copy stream while group k is
-        in the network.  Returns (n, 1024) float32 on the host."""
+        in the network.  Returns (n, 1024) float32 on the host.  ``wait=False`` returns ``(features, event)`` as soon as
+        everything is enqueued -- the features (pinned) are valid after ``event.synchronize()``, and the copies of the
+        NEXT call overlap the network of this one (``frames`` must stay untouched until then)."""
         assert not frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 5 and frames.shape[4] == 3
         n = frames.shape[0]
         out = torch.empty((n, 1024), dtype=torch.float32).pin_memory()
@@ -122,6 +124,10 @@ class I3DEngine:
                 freed[k & 1] = torch.cuda.Event()
                 freed[k & 1].record(main)
                 out[a:b].copy_(y, non_blocking=True)
+            if not wait:
+                done = torch.cuda.Event(blocking=True)
+                done.record(main)
+                return out, done
             main.synchronize()
         return out
 
