@@ -823,6 +823,20 @@ def run_c5(args, rank: int, world: int, local_rank: int, quick: bool = False):
             return r
         dispatch.gather_feature_blocks = traced_gather
         ExtractCLIP.forward = traced_forward
+        # device timeline of the engine calls: an event pair on the calling stream around every asynchronous call (the
+        # stream waits for the call's tower, so consecutive end events are one call apart on the device)
+        eng0 = ex._engines[local_rank]
+        inner_async = eng0.encode_frames_u8_host_async
+        trace["calls"] = []
+
+        def traced_async(frames, out_host=None, out_dev=False):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = inner_async(frames, out_host, out_dev)
+            b.record()
+            trace["calls"].append((a, b, int(frames.shape[0])))
+            return r
+        eng0.encode_frames_u8_host_async = traced_async
     t0 = time.perf_counter()
     e0.record()
     blocks = dispatch.run_shard(ex, n_videos, rank, world, dev, gather_key="CLIP-ViT-B/32")
@@ -832,15 +846,26 @@ def run_c5(args, rank: int, world: int, local_rank: int, quick: bool = False):
     if trace:
         dispatch.gather_feature_blocks, ExtractCLIP.forward = inner_gather, inner_forward
         f, g = trace.get("forward", (t0, t0)), trace.get("gather", (t0, t0))
+        calls = trace.get("calls", [])
+        if len(calls) > 2:
+            gaps_ms = [calls[i][1].elapsed_time(calls[i + 1][1]) for i in range(len(calls) - 1)]   # spacing of call ends
+            own = [a.elapsed_time(b) for a, b, _ in calls]
+            print(f"[c5 trace rank {rank}] {len(calls)} engine calls of {calls[0][2]} frames: spacing of call ends median "
+                  f"{sorted(gaps_ms)[len(gaps_ms) // 2]:.2f} ms (min {min(gaps_ms):.2f}, max {max(gaps_ms):.2f}); start->end on the calling stream "
+                  f"median {sorted(own)[len(own) // 2]:.2f} ms; first end at {e0.elapsed_time(calls[0][1]):.1f} ms, last end at "
+                  f"{e0.elapsed_time(calls[-1][1]):.1f} ms", file=sys.stderr, flush=True)
         print(f"[c5 trace rank {rank}] wall {wall:.3f} s: before forward {f[0] - t0:.3f}, forward {f[1] - f[0]:.3f}, "
-              f"forward -> gather {g[0] - f[1]:.3f}, gather {g[1] - g[0]:.3f}, after {t0 + wall - g[1]:.3f}", file=sys.stderr, flush=True)
+              f"forward -> gather {g[0] - f[1]:.3f}, gather {g[1] - g[0]:.3f}, after {t0 + wall - g[1]:.3f}; stage waits "
+              f"{ {k: round(v, 3) for k, v in ex.stage_wait.items()} }", file=sys.stderr, flush=True)
     clocks = sampler.stop() if sampler else None
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms)
     # every rank holds every video's block, in list order: entries i and i + 64 are the same clip
-    assert len(blocks) == n_videos and all(tuple(b.shape) == (per, 512) for b in blocks[:: max(1, n_videos // 50)])
+    if len(blocks) != n_videos or not all(tuple(b.shape) == (per, 512) for b in blocks[:: max(1, n_videos // 50)]):
+        raise AssertionError(f"list path returned {len(blocks)} blocks for {n_videos} videos; shapes "
+                             f"{sorted({tuple(b.shape) for b in blocks})[:4]}")
     for i in (0, 1, pool_n - 1, n_videos // 2, n_videos - pool_n - 1):
         if 0 <= i and i + pool_n < n_videos:
             assert torch.equal(blocks[i], blocks[i + pool_n]), f"gathered block {i} != block {i + pool_n}"

@@ -8,7 +8,8 @@ Pillow-exact bicubic resize, centre crop, normalisation and the ViT-B/32 tower o
 A list of videos does not go through the engine one 12-frame video at a time (600 token rows would fill 3 of the
 GEMM's 74 tile slots): ``forward`` decodes ahead on a thread pool, packs the frames of consecutive videos of equal
 geometry into a pinned staging buffer (two buffers, filled by the pool while the GPU works on the other one) and makes
-one engine call per ``VF_CLIP_BATCH_FRAMES`` (default 1024) frames; the features are cut back per video and handed to
+one engine call per ``VF_CLIP_BATCH_FRAMES`` (default 1000: four tower chunks of <= 250 frames, whose 49 x 12 GEMM tiles
+fill 8 waves of the 74 CTA pairs; 1024 would spill a ninth) frames; the features are cut back per video and handed to
 the sink exactly as the reference does, per-video error behaviour included.
 
 Differences a user can observe, all deliberate:
@@ -22,6 +23,7 @@ from __future__ import annotations
 import os
 import pathlib
 import threading
+import time
 import traceback
 from concurrent.futures import ThreadPoolExecutor
 from typing import Dict, List, Optional
@@ -124,11 +126,13 @@ class ExtractCLIP(torch.nn.Module):
         # .timestamps_ms, and stream.read_into(dst) decodes straight into the pinned staging rows (no extra copy).
         # None: wrap `frame_source` (tests and callers that replaced it).
         self.frame_stream = FrameStream
-        self.batch_frames = int(os.environ.get("VF_CLIP_BATCH_FRAMES", "1024"))
+        self.batch_frames = int(os.environ.get("VF_CLIP_BATCH_FRAMES", "1000"))
         self.decode_workers = int(os.environ.get("VF_DECODE_WORKERS", str(min(8, os.cpu_count() or 1))))
         self.keep_features = False        # dispatch sets it when the features are all-gathered as well as saved
         # with keep_features: (first list position, rows of consecutive delivered videos still on the GPU), one per engine call
         self.device_chunks: List[tuple] = []
+        # seconds the stages of the last batched forward spent waiting on each other (diagnostics: which side is the limiter)
+        self.stage_wait = {"engine_for_decode": 0.0, "engine_enqueue": 0.0, "host_for_slot": 0.0, "deliver_for_gpu": 0.0}
 
     def _engine(self, device: torch.device) -> ClipEngine:
         if device.type != 'cuda':
@@ -241,6 +245,7 @@ class ExtractCLIP(torch.nn.Module):
         delivered = []
         state = {"slot": 0}
         lock = threading.Lock()
+        waits = self.stage_wait = dict.fromkeys(self.stage_wait, 0.0)
 
         def deliver_one(pos, video, feats, fps, stamps):
             try:
@@ -285,7 +290,9 @@ class ExtractCLIP(torch.nn.Module):
 
         def finish(batch: _Batch, ticket, feats, counts, dev):
             try:
+                t0 = time.perf_counter()
                 model.wait(ticket)                                            # features are in the pinned landing buffer
+                waits["deliver_for_gpu"] += time.perf_counter() - t0
             except Exception as err:                                          # a device fault: every video of the call is lost
                 for (pos, video, st, row0, _) in batch.items:
                     self._report(err, video)
@@ -295,9 +302,12 @@ class ExtractCLIP(torch.nn.Module):
 
         def run_batch(batch: _Batch):
             counts = []
+            t0 = time.perf_counter()
             for it in batch.items:                                            # the decodes into this slot are complete
                 fut, i = it[4]
                 counts.append(fut.result()[i])
+            t1 = time.perf_counter()
+            waits["engine_for_decode"] += t1 - t0
             h, w = batch.hw
             view = pinned[batch.slot][:batch.rows * h * w * 3].view(batch.rows, h, w, 3)
             feats = feats_out[batch.slot][:batch.rows]
@@ -306,16 +316,19 @@ class ExtractCLIP(torch.nn.Module):
             except Exception:
                 batch_failed(batch, counts, view)
                 return None
+            waits["engine_enqueue"] += time.perf_counter() - t1
             done = out.submit(finish, batch, ticket, feats, counts, dev)           # waiting, slicing and the sink run beside the
             delivered.append(done)                                            # next call's enqueue
             return done
 
         def wait_slot(k):
             if busy[k] is not None:
+                t0 = time.perf_counter()
                 done = busy[k].result()                                       # enqueued ...
                 if done is not None:
                     done.result()                                             # ... and finished with the slot's buffers
                 busy[k] = None
+                waits["host_for_slot"] += time.perf_counter() - t0
 
         def new_batch(hw):
             k = state["slot"]
