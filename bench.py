@@ -488,6 +488,7 @@ def run_engine(args, rank: int, world: int, local_rank: int) -> None:
         watchdog.daemon = True
         watchdog.start()
         for name, fn, ok in (("c5_video_list", lambda: run_c5(args, rank, world, local_rank, quick=True), True),
+                             ("clip_vit_b16", lambda: run_b16(args, quick=True), world == 1),
                              ("i3d_rgb", lambda: run_i3d(args, quick=True), world == 1),
                              ("raft_i3d_flow", lambda: run_raft(args, rank, world, local_rank, quick=True), world <= 2)):
             if not ok:
@@ -753,6 +754,74 @@ def run_raft(args, rank: int = 0, world: int = 1, local_rank: int = 0, quick: bo
 
 
 # ----------------------------------------------------------------------------------------- the video-list product path
+def run_b16(args, quick: bool = False):
+    """The reference's other ViT-B feature type ('CLIP-ViT-B/16'): same step as the headline (1000 synthetic
+    224x224 uint8 frames), 16-pixel patches -> 197 tokens per frame, 4.4x the FLOPs of ViT-B/32."""
+    import torch
+    from video_features_b200 import synthetic_weights
+    from video_features_b200.clip_engine import ClipEngine
+    torch.cuda.set_device(0)
+    eng = ClipEngine(synthetic_weights.clip_vit_b16_state_dict(0), device=0)
+    n = FRAMES_PER_STEP
+    frames_host = synth_frames_host(n, 500).pin_memory()
+    frames_host_b = synth_frames_host(n, 501).pin_memory()
+    outs = [torch.empty((n, 512), dtype=torch.float32).pin_memory() for _ in range(2)]
+    frames = frames_host.cuda()
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+    if quick:
+        W, K = 3, min(K, 10)
+    sampler = ClockSampler(0)
+    launches0 = eng.launch_count
+    ms = _timed_loop(lambda: eng.encode_frames_u8(frames), K, W)
+    launches = (eng.launch_count - launches0) // (K + W)
+    clocks = sampler.stop()
+    pending = []
+
+    def host_fn():                                     # as the headline's e2e: own H2D / D2H every step, two steps in flight
+        k = len(pending) and pending[-1][1] == 0
+        pending.append((eng.encode_frames_u8_host_async(frames_host_b if k else frames_host, outs[int(k)])[0], int(k)))
+        while len(pending) > 1:
+            eng.wait(pending.pop(0)[0])
+    for _ in range(2):
+        host_fn()
+    while pending:
+        eng.wait(pending.pop(0)[0])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        host_fn()
+    while pending:
+        eng.wait(pending.pop(0)[0])
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1)
+    eng.profile(True)
+    eng.encode_frames_u8(frames)
+    gemm_ms, gemm_launches, gemm_flops = eng.profile_read()
+    cats = eng.profile_categories()
+    eng.profile(False)
+    peaks = load_peaks()
+    line = {"metric": "frames/sec CLIP-ViT-B/16 @224px", "value": n * K / (ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+            "data": "synthetic",
+            "config": {"workload": "1000 synthetic 224x224x3 uint8 frames per step, CLIP ViT-B/16 tower (197 tokens per frame)",
+                       "frames_per_step": n, "weights": "synthetic (seeded, openai initialisation scales)"},
+            "clocks": clocks,
+            "e2e": {"value": n * K / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(frames_host.numel()),
+                    "d2h_bytes_per_step": n * 512 * 4},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "vf::gemm_f16_pair_kernel (QKV GEMM + attention_long_kernel: the fused kernel is 50-token only)",
+                         "achieved": gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0,
+                         "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": (gemm_flops / (gemm_ms / 1e3) / 1e12 / peaks["tflops_sustained"]) if gemm_ms > 0 else 0.0,
+                         "peak_source": peaks["source"] + ", bf16 dense sustained", "traffic": None,
+                         "eager_ms_per_step_by_kernel": cats}}
+    eng.close()
+    torch.cuda.empty_cache()
+    return line
+
+
 def run_c5(args, rank: int, world: int, local_rank: int, quick: bool = False):
     """BASELINE.json configs[4]: a 10k-video list through the product's own list path -- ExtractCLIP.forward (decode
     pool -> pinned staging -> one engine call per 1024 frames -> per-video feature blocks) under the --device_ids
@@ -903,7 +972,7 @@ def main() -> None:
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--torch-gpu", action="store_true", dest="torch_gpu",
                     help="also time the oracle's fp32 torch modules on the same GPU (library-call bar), key torch_gpu_baseline")
-    ap.add_argument("--workload", default="clip", choices=["clip", "i3d", "raft", "c5"],
+    ap.add_argument("--workload", default="clip", choices=["clip", "i3d", "raft", "c5", "b16"],
                     help="clip = the headline (BASELINE.json configs[1], with the other configs as `secondary`); i3d / raft "
                          "/ c5 = configs[2] / configs[3] / configs[4] alone")
     ap.add_argument("--no-secondary", action="store_true", dest="no_secondary",
@@ -924,7 +993,7 @@ def main() -> None:
     if args.workload == "clip":
         return run_engine(args, rank, world, local_rank)
     line = {"i3d": lambda: run_i3d(args), "raft": lambda: run_raft(args, rank, world, local_rank),
-            "c5": lambda: run_c5(args, rank, world, local_rank)}[args.workload]()
+            "c5": lambda: run_c5(args, rank, world, local_rank), "b16": lambda: run_b16(args)}[args.workload]()
     if rank == 0:
         emit(line)
     try:
