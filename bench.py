@@ -23,6 +23,7 @@ import subprocess
 import sys
 import tempfile
 import time
+import traceback
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -479,12 +480,12 @@ def run_engine(args, rank: int, world: int, local_rank: int) -> None:
         import threading
 
         def _bail():
-            line["secondary"] = dict(sec, error="timeout: secondary workloads did not finish within 420 s")
+            line["secondary"] = dict(sec, error="timeout: secondary workloads did not finish within 240 s")
             if rank == 0:
                 emit(line)
             os._exit(0)
 
-        watchdog = threading.Timer(420.0, _bail)
+        watchdog = threading.Timer(240.0, _bail)
         watchdog.daemon = True
         watchdog.start()
         for name, fn, ok in (("c5_video_list", lambda: run_c5(args, rank, world, local_rank, quick=True), True),
@@ -497,6 +498,8 @@ def run_engine(args, rank: int, world: int, local_rank: int) -> None:
                 sec[name] = fn()
             except BaseException as err:               # a secondary line never takes the headline down with it
                 sec[name] = {"error": f"{type(err).__name__}: {err}"}
+                print(f"[bench rank {rank}] secondary workload {name} failed: {type(err).__name__}: {err}", file=sys.stderr, flush=True)
+                traceback.print_exc()
         watchdog.cancel()
         line["secondary"] = sec
     if rank == 0:
@@ -899,6 +902,7 @@ def run_c5(args, rank: int, world: int, local_rank: int, quick: bool = False):
         trace["calls"] = []
 
         def traced_async(frames, out_host=None, out_dev=False):
+            torch.cuda.set_device(local_rank)          # the engine thread's own current device (per-thread state)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             r = inner_async(frames, out_host, out_dev)

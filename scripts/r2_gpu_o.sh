@@ -2,7 +2,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l > gpurun_out/r2o_ngpus.txt
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29555 bench.py --gpus 8 --steps 30 --warmup 5 > gpurun_out/r2o_bench_8gpu.json 2> gpurun_out/r2o_bench_8gpu.err
+VF_C5_TRACE=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29555 bench.py --gpus 8 --steps 30 --warmup 5 > gpurun_out/r2o_bench_8gpu.json 2> gpurun_out/r2o_bench_8gpu.err
 echo "rc=$?" >> gpurun_out/r2o_bench_8gpu.err
 python - <<'PY'
 import json
@@ -11,4 +11,4 @@ print('8 GPUs:', round(d['value']), 'e2e', round(d['e2e']['value']), 'ms', round
 for k,v in d.get('secondary',{}).items():
     print('   ', k, {kk:(round(vv,1) if isinstance(vv,float) else vv) for kk,vv in v.items() if kk in ('value','unit','ms_per_step','error','videos_per_sec','n_gpus','host_wall_s_rank0')})
 PY
-tail -3 gpurun_out/r2o_bench_8gpu.err
+grep "c5 trace rank [07]\]" gpurun_out/r2o_bench_8gpu.err | cut -c1-400; tail -2 gpurun_out/r2o_bench_8gpu.err
