@@ -18,6 +18,11 @@ def _gather_worker(rank, world, port, q):
     # video v has v+1 rows, every element equals v
     blocks = [torch.full((v + 1, 8), float(v)) for v in idx]
     allb = gather_feature_blocks(blocks, 8, torch.device("cpu"))
+    # the same rows handed over in a few large pieces (what ExtractCLIP keeps per engine call) give the same answer
+    rows = torch.cat(blocks) if blocks else torch.zeros((0, 8))
+    pieces = [rows[:2], rows[2:]] if rows.shape[0] > 2 else [rows]
+    allb2 = gather_feature_blocks(blocks, 8, torch.device("cpu"), rows_on_device=pieces)
+    assert len(allb) == len(allb2) and all(torch.equal(a, b) for a, b in zip(allb, allb2))
     q.put((rank, idx, [(b.shape[0], float(b[0, 0])) for b in allb]))
     dist.destroy_process_group()
 

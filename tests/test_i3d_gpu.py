@@ -122,3 +122,24 @@ def test_i3d_fused_stream_transforms(cuda_device):
     assert rel < 1e-3 and mx < 1e-3
     assert torch.equal(yf, engf(xf.to(cuda_device)))
     engf.close()
+
+
+def test_i3d_host_stacks_pipelined_calls(cuda_device):
+    """forward_frames_u8_host: host stacks in groups (copy of group k+1 under the network of group k) and, with
+    wait=False, two calls in flight -- same features as the device-resident call."""
+    from oracle import i3d_net
+    from video_features_b200.i3d_engine import I3DEngine
+    sd = i3d_net.synthetic_state_dict("rgb", 3)
+    eng = I3DEngine(sd, "rgb", 0, max_stacks=2, max_T=16)
+    g = torch.Generator().manual_seed(4)
+    a = torch.randint(0, 256, (5, 17, 224, 224, 3), dtype=torch.uint8, generator=g).pin_memory()
+    b = torch.randint(0, 256, (3, 17, 224, 224, 3), dtype=torch.uint8, generator=g).pin_memory()
+    ref_a = eng.forward_frames_u8(a.to(cuda_device)[:, :16]).cpu()
+    ref_b = eng.forward_frames_u8(b.to(cuda_device)[:, :16]).cpu()
+    assert torch.equal(eng.forward_frames_u8_host(a, 16, group=2), ref_a)
+    ya, ea = eng.forward_frames_u8_host(a, 16, group=2, wait=False)
+    yb, eb = eng.forward_frames_u8_host(b, 16, group=2, wait=False)
+    ea.synchronize()
+    eb.synchronize()
+    assert torch.equal(ya, ref_a) and torch.equal(yb, ref_b)
+    eng.close()
