@@ -88,6 +88,16 @@ for name, title in (("r2l_bench_2gpu.json", "2 x B200 (`gpurun --gpus 2`): headl
             if "value" in v:
                 describe(v, f"secondary `{k}` at 2 GPUs")
 
+# ---- later multi-GPU runs on the final code (the 2-GPU record above predates the asynchronous entry point)
+d = load("r2_c5_2gpu.json") or load("r2t_c5_2gpu.json")
+if d:
+    describe(d, "10k-video list at 2 GPUs, final code (`torchrun --nproc-per-node 2 bench.py --gpus 2 --workload c5`)")
+d = load("r2/bench_8gpu_run2.json")
+if d:
+    d = dict(d)
+    d.pop("secondary", None)
+    describe(d, "8 x B200, final code (`torchrun --nproc-per-node 8 bench.py --gpus 8 --steps 30 --warmup 5`; secondary lines: see r2/README.md)")
+
 # ---- ncu launch list
 src = os.path.join(G, "r2_launches_clip.csv")
 if os.path.exists(src):
