@@ -48,6 +48,7 @@ struct vf_clip {
     // transform scratch (grown on demand)
     uint8_t *stage_u8 = nullptr, *resized = nullptr, *resize_tmp = nullptr;
     size_t stage_cap = 0, resized_cap = 0, tmp_cap = 0;
+    size_t stage_fbytes = 0;      // frame size the two staging slots were last laid out for
     float* out_dev = nullptr;
     size_t out_cap = 0;
     // roofline instrumentation (vf_clip_profile)
@@ -564,6 +565,13 @@ static int clip_encode_u8_host(vf_clip_t* h, const uint8_t* frames_host, int n, 
     const int nchunks = (n + step - 1) / step;
     // the staging copies read HOST memory that is ready now: they are not ordered behind the caller's stream (which, after
     // an asynchronous call, waits for that call's tower) -- only behind the staging slot's previous user
+    if (fbytes != h->stage_fbytes) {
+        // another frame size moves the boundary between the two slots: a slot of this call may overlap EITHER slot of a
+        // call still in flight, so the first copy waits for both
+        VF_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[0], 0));
+        VF_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[1], 0));
+        h->stage_fbytes = fbytes;
+    }
     for (int i = 0; i < nchunks; ++i) {
         const int b0 = i * step;
         const int c = (n - b0 < step) ? (n - b0) : step;
