@@ -60,6 +60,15 @@ def main(mod="rgb", seed=116):
             "fp16 weights: stem + 3b only": lambda n, k: k == 7 or (k == 3 and n.startswith("mixed_3b")),
             "fp16 weights: stem + 3c only": lambda n, k: k == 7 or (k == 3 and n.startswith("mixed_3c")),
         }
+    if os.environ.get("VF_EMU_COMBOS") == "2":     # what could be added to the policy the engine ships (stem + stage 3)
+        cur = lambda n, k: k == 7 or (k == 3 and n.startswith("mixed_3"))
+        cases = {
+            "engine today (stem + stage-3 3x3x3 single)": cur,
+            "  + conv3d_2c": lambda n, k: cur(n, k) or n == "conv3d_2c_3x3",
+            "  + stage-5 3x3x3": lambda n, k: cur(n, k) or (k == 3 and n.startswith("mixed_5")),
+            "  + conv3d_2c + stage-5 3x3x3": lambda n, k: cur(n, k) or n == "conv3d_2c_3x3" or (k == 3 and n.startswith("mixed_5")),
+            "  + mixed_4b/4c 3x3x3": lambda n, k: cur(n, k) or (k == 3 and (n.startswith("mixed_4b") or n.startswith("mixed_4c"))),
+        }
     for tag, fn in cases.items():
         print(f"{mod} seed {seed}: {tag:55s} {run(fn)}", flush=True)
 

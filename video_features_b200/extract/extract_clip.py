@@ -7,7 +7,7 @@ Pillow-exact bicubic resize, centre crop, normalisation and the ViT-B/32 tower o
 
 A list of videos does not go through the engine one 12-frame video at a time (600 token rows would fill 3 of the
 GEMM's 74 tile slots): ``forward`` decodes ahead on a thread pool, packs the frames of consecutive videos of equal
-geometry into a pinned staging buffer (two buffers, filled by the pool while the GPU works on the other one) and makes
+geometry into a pinned staging buffer (three buffers: one being filled by the pool, two with engine calls in flight) and makes
 one engine call per ``VF_CLIP_BATCH_FRAMES`` (default 1000: four tower chunks of <= 250 frames, whose 49 x 12 GEMM tiles
 fill 8 waves of the 74 CTA pairs; 1024 would spill a ninth) frames; the features are cut back per video and handed to
 the sink exactly as the reference does, per-video error behaviour included.
