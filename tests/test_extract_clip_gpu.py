@@ -149,3 +149,42 @@ def test_extract_clip_list_is_batched_and_matches_per_video_calls(cuda_device, t
     for a, b in zip(got, one):
         assert a['CLIP-ViT-B/32'].shape == (5, 512) and np.array_equal(a['CLIP-ViT-B/32'], b['CLIP-ViT-B/32'])
         assert np.array_equal(a['timestamps_ms'], b['timestamps_ms'])
+
+
+def test_extract_clip_async_sink_and_resume_on_gpu(cuda_device, tmp_path, monkeypatch):
+    """VF_ASYNC_SINK=1 (features saved by a writer thread while the next engine call runs) writes the same files as the
+    reference-style synchronous sink; VF_RESUME=1 then skips every video whose file exists (no engine work at all)."""
+    monkeypatch.setenv("VF_CLIP_SYNTHETIC", "0")
+    from video_features_b200.extract.extract_clip import ExtractCLIP
+    vids = []
+    for i in range(6):
+        v = str(tmp_path / f"s{i}.mp4")
+        _write_video(v, n=12 + 2 * i)
+        vids.append(v)
+    idx = torch.arange(len(vids), device=cuda_device)
+    monkeypatch.delenv("VF_ASYNC_SINK", raising=False)
+    monkeypatch.delenv("VF_RESUME", raising=False)
+    ex = ExtractCLIP(_args(vids, str(tmp_path / "sync"), method="uni_4"))
+    ex.batch_frames = 8                                   # 2 videos per engine call: several calls in flight
+    assert ex(idx) == []
+    monkeypatch.setenv("VF_ASYNC_SINK", "1")
+    ex2 = ExtractCLIP(_args(vids, str(tmp_path / "async"), method="uni_4"))
+    ex2.batch_frames = 8
+    assert ex2(idx) == []
+    for i in range(6):
+        a = np.load(tmp_path / "sync" / f"s{i}.npy")
+        b = np.load(tmp_path / "async" / f"s{i}.npy")
+        assert a.shape == (4, 512) and np.array_equal(a, b)
+    assert not [f for f in os.listdir(tmp_path / "async") if f.endswith(".tmp")]       # atomic writes left nothing behind
+    # resume: nothing to do -> no engine launches, files untouched
+    monkeypatch.setenv("VF_RESUME", "1")
+    eng = ex2._engines[0]
+    before = eng.launch_count
+    stamp = os.path.getmtime(tmp_path / "async" / "s0.npy")
+    assert ex2(idx) == []
+    assert eng.launch_count == before and os.path.getmtime(tmp_path / "async" / "s0.npy") == stamp
+    # one file removed -> exactly that video is extracted again
+    os.remove(tmp_path / "async" / "s3.npy")
+    assert ex2(idx) == []
+    assert eng.launch_count > before
+    assert np.array_equal(np.load(tmp_path / "async" / "s3.npy"), np.load(tmp_path / "sync" / "s3.npy"))

@@ -56,56 +56,77 @@ __global__ void i3d_phase_pack_f32_kernel(const float* __restrict__ x, int n, in
 // frames [n][T][Hr][Wr][3] uint8 -> TensorCenterCrop(224) at (cy,cx) -> 2*x/255 - 1 (fp32, the reference's operation
 // order) -> fp16 phase volume.  Channel order is the decoder's (the reference never swaps BGR).
 // stack b starts at frame b * stack_stride (>= T: a stack may be a window of a longer frame buffer).
-__global__ void i3d_phase_pack_u8_kernel(const uint8_t* __restrict__ frames, int n, int T, int64_t stack_stride, int Hr,
-                                         int Wr, int cy, int cx, __half* __restrict__ out, int Tq) {
+// Stores: a thread owns one 192-byte row, so direct 16-byte stores of a warp would land 192 bytes apart (half-used
+// sectors).  The rows of a block are contiguous in the output, so they are staged in shared memory (row pitch 13 x 16 B:
+// conflict-free) and written out as one contiguous, fully coalesced run.
+constexpr int PACK_THREADS = 128;
+__device__ __forceinline__ void pack_flush(const uint4* stage, int row_u4, int pitch_u4, __half* out, int64_t row0, int rows) {
+    __syncthreads();
+    uint4* g = reinterpret_cast<uint4*>(out) + row0 * row_u4;
+    const int total = rows * row_u4;
+    for (int i = threadIdx.x; i < total; i += PACK_THREADS) {
+        const int r = i / row_u4, j = i - r * row_u4;
+        g[i] = stage[r * pitch_u4 + j];
+    }
+}
+
+__global__ void __launch_bounds__(PACK_THREADS) i3d_phase_pack_u8_kernel(const uint8_t* __restrict__ frames, int n, int T,
+                                         int64_t stack_stride, int Hr, int Wr, int cy, int cx, __half* __restrict__ out, int Tq) {
     // the transform of a byte, in the reference's fp32 operation order, has 256 possible results: one table per block
     // instead of 96 IEEE divisions per thread
     __shared__ __half lut[256];
+    __shared__ __align__(16) uint4 stage[PACK_THREADS * 13];
     for (int i = threadIdx.x; i < 256; i += blockDim.x)
         lut[i] = __float2half_rn(__fsub_rn(__fdiv_rn(__fmul_rn(2.0f, float(i)), 255.0f), 1.0f));
     __syncthreads();
-    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t row0 = int64_t(blockIdx.x) * PACK_THREADS;
+    const int64_t idx = row0 + threadIdx.x;
     const int64_t total = int64_t(n) * Tq * 115 * 115;
-    if (idx >= total) return;
-    const int wq = int(idx % 115);
-    const int hq = int((idx / 115) % 115);
-    const int tq = int((idx / (115 * 115)) % Tq);
-    const int b = int(idx / (int64_t(115) * 115 * Tq));
-    const int w0 = 2 * (wq - 1);
-    const __half zero = __float2half_rn(0.f);
+    if (idx < total) {
+        const int wq = int(idx % 115);
+        const int hq = int((idx / 115) % 115);
+        const int tq = int((idx / (115 * 115)) % Tq);
+        const int b = int(idx / (int64_t(115) * 115 * Tq));
+        const int w0 = 2 * (wq - 1);
+        const __half zero = __float2half_rn(0.f);
 #pragma unroll 1
-    for (int sb = 0; sb < 4; ++sb) {
-        __align__(16) __half vals[24];
-        const int hs = hq + sb - 1;
+        for (int sb = 0; sb < 4; ++sb) {
+            __align__(16) __half vals[24];
+            const int hs = hq + sb - 1;
 #pragma unroll
-        for (int pt = 0; pt < 2; ++pt) {
-            const int t = 2 * (tq - 1) + pt;
+            for (int pt = 0; pt < 2; ++pt) {
+                const int t = 2 * (tq - 1) + pt;
 #pragma unroll
-            for (int ph = 0; ph < 2; ++ph) {
-                const int hh = 2 * (hs - 1) + ph;
-                const bool ok = (t >= 0) && (t < T) && (hh >= 0) && (hh < 224) && (w0 >= 0) && (w0 < 224);
-                const uint8_t* p = frames + (((int64_t(b) * stack_stride + (ok ? t : 0)) * Hr + cy + (ok ? hh : 0)) * Wr + cx + (ok ? w0 : 0)) * 3;
+                for (int ph = 0; ph < 2; ++ph) {
+                    const int hh = 2 * (hs - 1) + ph;
+                    const bool ok = (t >= 0) && (t < T) && (hh >= 0) && (hh < 224) && (w0 >= 0) && (w0 < 224);
+                    const uint8_t* p = frames + (((int64_t(b) * stack_stride + (ok ? t : 0)) * Hr + cy + (ok ? hh : 0)) * Wr + cx + (ok ? w0 : 0)) * 3;
 #pragma unroll
-                for (int pw = 0; pw < 2; ++pw)
+                    for (int pw = 0; pw < 2; ++pw)
 #pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        vals[((pt * 2 + ph) * 2 + pw) * 3 + c] = ok ? lut[__ldg(p + pw * 3 + c)] : zero;
+                        for (int c = 0; c < 3; ++c)
+                            vals[((pt * 2 + ph) * 2 + pw) * 3 + c] = ok ? lut[__ldg(p + pw * 3 + c)] : zero;
+                }
             }
+            uint4* o = stage + threadIdx.x * 13 + sb * 3;
+            const uint4* v4 = reinterpret_cast<const uint4*>(vals);
+            o[0] = v4[0]; o[1] = v4[1]; o[2] = v4[2];
         }
-        uint4* o = reinterpret_cast<uint4*>(out + idx * 96 + sb * 24);
-        const uint4* v4 = reinterpret_cast<const uint4*>(vals);
-        o[0] = v4[0]; o[1] = v4[1]; o[2] = v4[2];
     }
+    const int rows = int(min(int64_t(PACK_THREADS), total - row0));
+    pack_flush(stage, 12, 13, out, row0, rows);
 }
 
 // Fused T3 transform + phase packing for the flow stream (extract_i3d.py:67-73): flow [n][T][2][H][W] fp32 (the RAFT
 // output, still padded) -> crop 224 at (cy,cx) -> clamp(+-20) -> 128 + 255/40*f -> round half-to-even (+20 -> 256, not
 // clipped, as the reference) -> 2*x/255 - 1 -> fp16 phase volume with 16 channels.
-__global__ void i3d_phase_pack_flow_kernel(const float* __restrict__ flow, int n, int T, int H, int W, int cy, int cx,
-                                           __half* __restrict__ out, int Tq) {
-    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(PACK_THREADS) i3d_phase_pack_flow_kernel(const float* __restrict__ flow, int n, int T, int H,
+                                           int W, int cy, int cx, __half* __restrict__ out, int Tq) {
+    __shared__ __align__(16) uint4 stage[PACK_THREADS * 9];      // 128-byte rows at a 144-byte pitch
+    const int64_t row0 = int64_t(blockIdx.x) * PACK_THREADS;
+    const int64_t idx = row0 + threadIdx.x;
     const int64_t total = int64_t(n) * Tq * 115 * 115;
-    if (idx >= total) return;
+    if (idx < total) {
     const int wq = int(idx % 115);
     const int hq = int((idx / 115) % 115);
     const int tq = int((idx / (115 * 115)) % Tq);
@@ -142,10 +163,13 @@ __global__ void i3d_phase_pack_flow_kernel(const float* __restrict__ flow, int n
                 }
             }
         }
-        uint4* o = reinterpret_cast<uint4*>(out + idx * 64 + sb * 16);
+        uint4* o = stage + threadIdx.x * 9 + sb * 2;
         const uint4* v4 = reinterpret_cast<const uint4*>(vals);
         o[0] = v4[0]; o[1] = v4[1];
     }
+    }
+    const int rows = int(min(int64_t(PACK_THREADS), total - row0));
+    pack_flush(stage, 8, 9, out, row0, rows);
 }
 
 // ---- split-fp16 pair tensors.  Every tensor that a 1x1x1 conv or a pool reads is stored as a pair x = hi + lo (two fp16
@@ -363,14 +387,14 @@ int launch_i3d_phase_pack_f32(const float* x, int n, int C, int T, __half* out, 
 int launch_i3d_phase_pack_u8(const uint8_t* frames, int n, int T, int64_t stack_stride, int Hr, int Wr, int cy, int cx,
                              __half* out, int Tq, cudaStream_t s) {
     const int64_t total = int64_t(n) * Tq * 115 * 115;
-    i3d_phase_pack_u8_kernel<<<nblocks(total, 256), 256, 0, s>>>(frames, n, T, stack_stride, Hr, Wr, cy, cx, out, Tq);
+    i3d_phase_pack_u8_kernel<<<nblocks(total, PACK_THREADS), PACK_THREADS, 0, s>>>(frames, n, T, stack_stride, Hr, Wr, cy, cx, out, Tq);
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
 int launch_i3d_phase_pack_flow(const float* flow, int n, int T, int H, int W, int cy, int cx, __half* out, int Tq,
                                cudaStream_t s) {
     const int64_t total = int64_t(n) * Tq * 115 * 115;
-    i3d_phase_pack_flow_kernel<<<nblocks(total, 256), 256, 0, s>>>(flow, n, T, H, W, cy, cx, out, Tq);
+    i3d_phase_pack_flow_kernel<<<nblocks(total, PACK_THREADS), PACK_THREADS, 0, s>>>(flow, n, T, H, W, cy, cx, out, Tq);
     VF_CUDA(cudaGetLastError());
     return VF_OK;
 }
