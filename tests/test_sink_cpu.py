@@ -241,3 +241,31 @@ def test_extract_clip_batches_consecutive_videos_into_one_engine_call(tmp_path, 
     ex2.batch_frames = 8
     got = ex2(_FakeIndices([6, 0, 1]))
     assert [g['CLIP-ViT-B/32'].shape[0] for g in got] == [3, 3, 4] and float(got[0]['CLIP-ViT-B/32'][0, 0]) == 60.0
+
+
+def test_extract_clip_first_engine_call_of_a_list_is_small(tmp_path, monkeypatch):
+    """The first call holds at most `first_batch_frames` frames (the GPU starts early), the following ones `batch_frames`."""
+    import argparse
+    from video_features_b200.extract.extract_clip import ExtractCLIP
+    vids = []
+    for i in range(30):
+        p = tmp_path / f"w{i:02d}.mp4"
+        p.write_bytes(b"x")
+        vids.append(str(p))
+    ns = argparse.Namespace(feature_type='CLIP-ViT-B/32', video_paths=vids, flow_paths=None, file_with_video_paths=None,
+                            video_dir=None, flow_dir=None, extraction_fps=None, extract_method='uni_4',
+                            on_extraction='save_numpy', output_path=str(tmp_path / "out"), output_direct=True,
+                            tmp_path=str(tmp_path / "tmp"))
+
+    def source(path, method):
+        i = int(os.path.basename(path)[1:3])
+        return [np.full((8, 8, 3), i, np.uint8) for _ in range(4)], 25.0, [0, 1, 2, 3]
+
+    eng = _FakeClipEngine()
+    monkeypatch.setattr(ExtractCLIP, "_engine", lambda self, device: eng)
+    ex = ExtractCLIP(ns, external_call=True)
+    ex.frame_source = source
+    ex.batch_frames, ex.first_batch_frames = 40, 8
+    got = ex(_FakeIndices(range(30)))
+    assert [c[0] for c in eng.calls] == [8, 40, 40, 32]
+    assert [float(g['CLIP-ViT-B/32'][0, 0]) for g in got] == [float(i) for i in range(30)]

@@ -76,9 +76,10 @@ def load_clip_state_dict(feature_type: str) -> Dict[str, torch.Tensor]:
 class _Batch:
     """Videos of one geometry sharing one pinned staging buffer and one engine call."""
 
-    def __init__(self, hw, slot):
+    def __init__(self, hw, slot, limit):
         self.hw = hw
         self.slot = slot
+        self.limit = limit                # frames this call may hold
         self.items: List[list] = []       # [list position, video, stream, first row, future -> frames written]
         self.rows = 0
 
@@ -127,6 +128,8 @@ class ExtractCLIP(torch.nn.Module):
         # None: wrap `frame_source` (tests and callers that replaced it).
         self.frame_stream = FrameStream
         self.batch_frames = int(os.environ.get("VF_CLIP_BATCH_FRAMES", "1000"))
+        # the first engine call of a list is one tower chunk: the GPU starts after ~250 decoded frames instead of 1000
+        self.first_batch_frames = int(os.environ.get("VF_CLIP_FIRST_BATCH_FRAMES", "250"))
         self.decode_workers = int(os.environ.get("VF_DECODE_WORKERS", str(min(8, os.cpu_count() or 1))))
         self.keep_features = False        # dispatch sets it when the features are all-gathered as well as saved
         # with keep_features: (first list position, rows of consecutive delivered videos still on the GPU), one per engine call
@@ -243,7 +246,7 @@ class ExtractCLIP(torch.nn.Module):
         feats_out: List[Optional[torch.Tensor]] = [None] * n_slots            # pinned (batch_frames, 512) landing buffers
         busy = [None] * n_slots                                               # engine future still reading slot k
         delivered = []
-        state = {"slot": 0}
+        state = {"slot": 0, "batches": 0}
         lock = threading.Lock()
         waits = self.stage_wait = dict.fromkeys(self.stage_wait, 0.0)
 
@@ -344,7 +347,9 @@ class ExtractCLIP(torch.nn.Module):
                 feats_out[k] = torch.empty((self.batch_frames, 512), dtype=torch.float32)
                 if torch.cuda.is_available():
                     feats_out[k] = feats_out[k].pin_memory()
-            return _Batch(hw, k)
+            first = state["batches"] == 0 and 0 < self.first_batch_frames < self.batch_frames
+            state["batches"] += 1
+            return _Batch(hw, k, self.first_batch_frames if first else self.batch_frames)
 
         pending: List[tuple] = []                                             # (batch item, its staging rows) not yet submitted
 
@@ -394,7 +399,7 @@ class ExtractCLIP(torch.nn.Module):
                             wait_slot(k)
                         gpu.submit(self._run_lone, model, pos, video, st, collected, sink, lock).result()
                         continue
-                    if batch is not None and (batch.hw != st.hw or batch.rows + st.count > self.batch_frames):
+                    if batch is not None and (batch.hw != st.hw or batch.rows + st.count > max(batch.limit, st.count)):
                         seal(batch)
                         batch = None
                     if batch is None:
