@@ -869,8 +869,10 @@ def run_c5(args, rank: int, world: int, local_rank: int, quick: bool = False):
     ex.path_list = [f"synthetic://{i}" for i in range(n_videos)]
     # warm-up: engine creation, graph capture for the chunk sizes in use, pinned buffers, thread pools
     # (through the same run_shard, so the communicator has carried an all-gather of this kind before the timed pass)
-    warm = dispatch.run_shard(ex, min(n_videos, world * 3 * 86), rank, world, dev, gather_key="CLIP-ViT-B/32")
-    del warm
+    # twice: a tower chunk size is captured into a CUDA graph the second time it is seen
+    for _ in range(2):
+        warm = dispatch.run_shard(ex, min(n_videos, world * 3 * 86), rank, world, dev, gather_key="CLIP-ViT-B/32")
+        del warm
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()

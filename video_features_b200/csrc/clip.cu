@@ -74,6 +74,7 @@ struct vf_clip {
         cudaStream_t cs = nullptr;
         cudaEvent_t ev_out = nullptr;
         std::map<int, cudaGraphExec_t> graphs;   // frames in chunk -> instantiated tower graph (writes feat)
+        std::map<int, int> seen;                 // frames in chunk -> times this size has been run without a graph
     } lanes[2];
     int n_lanes = 2, cur = 0;
     cudaStream_t cs = nullptr;                // stream of the active lane
@@ -240,6 +241,7 @@ static int clip_tower_eager(vf_clip* h, int c, float* out, cudaStream_t s) {
 }
 
 constexpr int TOWER_LAUNCHES_SPLIT = 2 + 7 * L + 2, TOWER_LAUNCHES_FUSED = 2 + 6 * L + 2;
+constexpr size_t kMaxTowerGraphs = 32;    // per lane; further sizes run eagerly
 
 // Tower on one chunk: replay (capturing on first use) the CUDA graph for this chunk size, then copy the features out.
 static int clip_tower_chunk(vf_clip* h, int c, float* out, cudaStream_t s) {
@@ -247,6 +249,12 @@ static int clip_tower_chunk(vf_clip* h, int c, float* out, cudaStream_t s) {
     auto& graphs = h->lanes[h->cur].graphs;
     auto it = graphs.find(c);
     if (it == graphs.end()) {
+        // A chunk size is captured the SECOND time it shows up: one-off sizes (the ragged tail of a list, batches of
+        // videos of unequal length) run eagerly instead of paying capture + instantiation for a graph that is never
+        // replayed, and the cache stays bounded.
+        auto& seen = h->lanes[h->cur].seen;
+        if (seen.size() > 4096) seen.clear();
+        if (++seen[c] < 2 || graphs.size() >= kMaxTowerGraphs) return clip_tower_eager(h, c, out, s);
         const int64_t before = h->launches;
         cudaGraph_t graph = nullptr;
         VF_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
