@@ -115,3 +115,18 @@ def test_raft_20_iterations_vs_oracle_and_reference_golden(raft, cuda_device, h,
     # unpadded window of the padded output
     yp = eng.flow(x, iters=20, unpad=False)
     assert torch.equal(R.unpad(yp, h, w), y)
+
+
+def test_raft_graph_cache_is_bounded(raft, cuda_device):
+    """More distinct (frames, H, W, iterations) keys than the engine keeps graphs for: evicted graphs are re-captured on
+    the next use and the results do not change."""
+    from oracle import raft_net as R
+    sd, eng = raft
+    x = R.synthetic_frames(3, 64, 96, seed=5).to(cuda_device)
+    first = eng.flow(x, iters=2).clone()
+    for k in range(18):                                    # 18 further keys (the cache holds 16)
+        eng.flow(R.synthetic_frames(2, 64 + 8 * (k % 6), 96 + 8 * (k // 6), seed=k).to(cuda_device), iters=2)
+    again = eng.flow(x, iters=2)
+    torch.cuda.synchronize()
+    # (InstanceNorm statistics are accumulated with atomics: the sum order, hence the last bits, may differ between runs)
+    assert float((first - again).abs().max()) <= 1e-4 * float(first.abs().max())

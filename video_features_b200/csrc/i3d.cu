@@ -382,6 +382,10 @@ static int i3d_trunk_graphed(vf_i3d* h, int nb, int T, float* out, cudaStream_t 
         const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
         cudaGraphDestroy(graph);
         if (ie != cudaSuccess) return fail(VF_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie));
+        if (h->graphs.size() >= 16) {          // bounded cache (an evicted graph still running is freed on completion)
+            cudaGraphExecDestroy(h->graphs.begin()->second);
+            h->graphs.erase(h->graphs.begin());
+        }
         it = h->graphs.emplace(key, exec).first;
         h->launches = before;
     }

@@ -651,6 +651,12 @@ int vf_raft_flow(vf_raft_t* h, const void* frames, int is_u8, int chw_layout, in
             const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
             cudaGraphDestroy(graph);
             if (ie != cudaSuccess) return fail(VF_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie));
+            // bounded cache: a list of videos of many resolutions (or ragged last calls) must not pile up executable
+            // graphs; an evicted graph that is still running is freed by the runtime when it completes
+            if (h->graphs.size() >= 16) {
+                cudaGraphExecDestroy(h->graphs.begin()->second.first);
+                h->graphs.erase(h->graphs.begin());
+            }
             it = h->graphs.emplace(key, std::make_pair(exec, n_launch)).first;
         }
         VF_CUDA(cudaGraphLaunch(it->second.first, s));
