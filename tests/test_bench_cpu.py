@@ -30,3 +30,17 @@ def test_reference_arm_prints_one_contract_line():
 def test_reference_arm_other_ranks_exit_without_work():
     lines = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert lines == []
+
+
+def test_engine_arm_fails_loudly_without_a_gpu():
+    """No CPU fallback: on a machine without a CUDA device the engine arm exits non-zero with a clear message and prints
+    no JSON line (a number must never come from a silent fallback)."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("this check is for GPU-less machines")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3", "--no-cpu", "--no-secondary"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode != 0
+    assert "no CUDA device" in (p.stderr + p.stdout)
+    assert not [l for l in p.stdout.splitlines() if l.startswith("{")]
