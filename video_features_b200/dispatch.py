@@ -88,7 +88,10 @@ def run_shard(extractor, n_items: int, rank: int, world: int, device: torch.devi
         wmax = torch.tensor([width], dtype=torch.int64, device=device)
         dist.all_reduce(wmax, op=dist.ReduceOp.MAX)                # a rank with an empty shard learns the width
         width = int(wmax)
-    return gather_feature_blocks(blocks, width, device, rows_dev)
+    gathered = gather_feature_blocks(blocks, width, device, rows_dev)
+    if chunks:
+        extractor.device_chunks = []                               # the per-call device copies are no longer needed
+    return gathered
 
 
 def _worker(rank: int, world: int, device_ids: List[int], make_extractor: Callable, n_items: int, port: int,
