@@ -958,7 +958,9 @@ def run_c5(args, rank: int, world: int, local_rank: int, quick: bool = False):
             "clocks": clocks,
             "e2e": {"value": n_videos * per / (ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": n_videos * per * 150528,
                     "d2h_bytes_per_step": n_videos * per * 2048,
-                    "api": "ExtractCLIP.forward under dispatch.run_shard (main.py --device_ids path)"},
+                    "api": "ExtractCLIP.forward under dispatch.run_shard (main.py --device_ids path)",
+                    "note": "this workload is host-to-host by construction (frames start in host memory, feature blocks end in "
+                            "the gathered list): `value` and `e2e` are the same measurement, not a device-resident number repeated"},
             "gpu_launches": int(engine.launch_count)}
     for e in ex._engines.values():
         e.close()
